@@ -1,0 +1,257 @@
+"""Backend-generic parity checks: each takes a binding.Library (CPU oracle or CUDA product) and
+asserts it against the hand-derived Appendix B vectors or the pyref golden fixtures.
+
+Tolerance classes (DESIGN.md "Parity"):
+  bit-exact : ray cell sequences, per-cell (nFree, nOcc), parent indices, poses (f32), likelihood
+              field (f64, same operation order), strongest index
+  toleranced: log-weights |d| <= 1e-9 (lane-product + log vs sequential sum of logs),
+              normalised weights rel 1e-9, Neff rel 1e-9, log-odds |d| <= 1e-9*(n+1),
+              weighted pose |d| <= 1e-6
+"""
+import math
+import os
+
+import numpy as np
+
+import appendix_b as AB
+from gridmap_slam_robot_b200 import binding as B
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LW_TOL = 1e-9
+W_RTOL = 1e-9
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def small_handle(lib, P=1, mode=B.MAP_PER_PARTICLE, **kw):
+    """60 x 50 map of the pyref fixtures: 3.0 m x 2.5 m at 0.05 m, origin (-1.5, -1.25)."""
+    return lib.create(num_particles=P, map_width_m=3.0, map_height_m=2.5, resolution=0.05, origin_x=-1.5,
+                      origin_y=-1.25, map_mode=mode, **kw)
+
+
+def grid10(lib):
+    return lib.create(num_particles=1, map_width_m=0.5, map_height_m=0.5, resolution=0.05, origin_x=0.0,
+                      origin_y=0.0)
+
+
+# ---------------------------------------------------------------- Appendix B (hand-derived) ----
+def check_constants(lib):
+    h = lib.create(num_particles=2)
+    assert (h.W, h.H) == (120, 120)
+    assert h.info.l_free == AB.L_FREE
+    assert h.info.l_occ == AB.L_OCC
+    assert h.info.kernel_taps == 7
+    k = list(h.info.kernel[:7])
+    assert k[:4] == AB.KERNEL_HALF and k[4:] == AB.KERNEL_HALF[2::-1]
+    h.close()
+    for width, cells in AB.GRID_SIZES:
+        h = lib.create(num_particles=1, map_width_m=width, map_height_m=0.05, resolution=0.05,
+                       map_mode=B.MAP_SHARED)
+        assert h.W == cells and h.H == 1
+        h.close()
+
+
+def check_appendix_b_rays(lib):
+    h = grid10(lib)
+    assert (h.W, h.H) == (10, 10)
+    for rid, s, e, n, err0, cells, cls_hit, cls_miss in AB.RAYS:
+        ray = np.asarray([s[0] + 0.5, s[1] + 0.5, e[0] + 0.5, e[1] + 0.5], np.float32)
+        got, cnt = h.trace_rays(ray, extra=2)
+        assert cnt[0] == len(cells), rid
+        assert [tuple(c) for c in got[0, : cnt[0]]] == cells, rid
+        meas = float(np.float32(math.hypot(e[0] - s[0], e[1] - s[1])))
+        for hit, classes in ((1, cls_hit), (0, cls_miss)):
+            h.reset()
+            h.map_apply_measurement(0, s[0], s[1], e[0], e[1], meas, hit)
+            nf, no = h.get_map(0, B.MAP_FREE_COUNT), h.get_map(0, B.MAP_OCC_COUNT)
+            ef, eo = np.zeros((10, 10), np.uint32), np.zeros((10, 10), np.uint32)
+            for (cx, cy), c in zip(cells, classes):
+                if c == "F":
+                    ef[cy, cx] += 1
+                elif c == "O":
+                    eo[cy, cx] += 1
+            assert np.array_equal(nf, ef) and np.array_equal(no, eo), (rid, hit)
+    h.close()
+
+
+def check_appendix_b_resample(lib):
+    for w, u, parents in AB.RESAMPLE:
+        h = lib.create(num_particles=len(w), map_width_m=0.5, map_height_m=0.5, map_mode=B.MAP_SHARED,
+                       resample_mode=B.RESAMPLE_LITERAL)
+        h.set_weights(w)
+        h.resample(u)
+        assert h.parents().tolist() == parents, (w, u)
+        h.close()
+    w, u = AB.RESAMPLE_CLAMP
+    h = lib.create(num_particles=4, map_width_m=0.5, map_height_m=0.5, map_mode=B.MAP_SHARED,
+                   resample_mode=B.RESAMPLE_LITERAL)
+    h.set_weights(w)
+    h.resample(u)  # Java would throw; the build clamps the walk at N-1
+    p = h.parents().tolist()
+    assert p[-1] == 3 and all(a <= b for a, b in zip(p, p[1:]))
+    h.set_weights(AB.NEFF[0])
+    assert h.calculate_neff() == AB.NEFF[1] or abs(h.calculate_neff() - AB.NEFF[1]) < 1e-12
+    h.close()
+
+
+def check_blank_likelihood(lib):
+    """B3: blank map -> exactly 0.5 at >= 3 cells from every border, strictly less within 3 cells."""
+    h = small_handle(lib)
+    h.map_compute_likelihood(0)
+    lik = h.get_map(0, B.MAP_LIKELIHOOD)
+    assert np.all(lik[3:-3, 3:-3] == 0.5)
+    border = np.ones_like(lik, bool)
+    border[3:-3, 3:-3] = False
+    assert np.all(lik[border] < 0.5)
+    # single occupied cell: 0.5 + 0.5*k[i]*k[j] on its 7x7 support
+    nf, no = np.zeros((h.H, h.W), np.uint32), np.zeros((h.H, h.W), np.uint32)
+    no[20, 30] = 1
+    h.set_map_counts(0, nf, no)
+    h.map_compute_likelihood(0)
+    lik = h.get_map(0, B.MAP_LIKELIHOOD)
+    k = np.asarray(h.info.kernel[:7])
+    np.testing.assert_allclose(lik[17:24, 27:34], 0.5 + 0.5 * np.outer(k, k), rtol=0, atol=1e-15)
+    assert np.all(lik[3:-3, 3:-3][(np.abs(np.arange(3, h.H - 3)[:, None] - 20) > 3) |
+                                  (np.abs(np.arange(3, h.W - 3)[None, :] - 30) > 3)] == 0.5)
+    h.close()
+
+
+# ---------------------------------------------------------------- pyref fixtures ----------------
+def check_rays(lib):
+    g = golden("pyref_rays.npz")
+    W, H = int(g["W"]), int(g["H"])
+    h = lib.create(num_particles=1, map_width_m=W * 0.05, map_height_m=H * 0.05, resolution=0.05,
+                   map_mode=B.MAP_SHARED)
+    assert (h.W, h.H) == (W, H)
+    cells, counts = h.trace_rays(g["rays"], extra=int(g["extra"]), cap=g["cells"].shape[1])
+    assert np.array_equal(counts, g["counts"])
+    assert np.array_equal(cells, g["cells"])
+    # a truncated capacity still reports the full count
+    cells2, counts2 = h.trace_rays(g["rays"], extra=int(g["extra"]), cap=5)
+    assert np.array_equal(counts2, g["counts"])
+    assert np.array_equal(cells2, g["cells"][:, :5])
+    h.close()
+
+
+def check_apply(lib):
+    g = golden("pyref_apply.npz")
+    h = small_handle(lib)
+    for a, hit in zip(g["args"], g["hits"]):
+        h.map_apply_measurement(0, *[float(v) for v in a], int(hit))
+    assert np.array_equal(h.get_map(0, B.MAP_FREE_COUNT), g["nfree"])
+    assert np.array_equal(h.get_map(0, B.MAP_OCC_COUNT), g["nocc"])
+    n = g["nfree"].astype(np.float64) + g["nocc"]
+    assert np.all(np.abs(h.get_map(0, B.MAP_LOG) - g["log"]) <= 1e-9 * (n + 1))
+    h.close()
+
+
+def check_blur(lib):
+    g = golden("pyref_blur.npz")
+    h = small_handle(lib)
+    assert np.array_equal(np.asarray(h.info.kernel[: h.info.kernel_taps]), g["kernel"])
+    h.set_map_counts(0, g["nfree"], g["nocc"])
+    h.map_compute_likelihood(0)
+    lik = h.get_map(0, B.MAP_LIKELIHOOD)
+    assert np.array_equal(lik, g["lik"])  # bit-exact f64: same operation order, no FMA
+    h.close()
+
+
+def check_resample(lib):
+    g = golden("pyref_resample.npz")
+    for k in range(int(g["num_cases"])):
+        w, u = g[f"w{k}"], float(g[f"u{k}"])
+        for mode, key in ((B.RESAMPLE_LITERAL, "lit"), (B.RESAMPLE_FIXED, "fix")):
+            h = lib.create(num_particles=len(w), map_width_m=0.5, map_height_m=0.5, map_mode=B.MAP_SHARED,
+                           resample_mode=mode)
+            h.set_weights(w)
+            assert abs(h.calculate_neff() / float(g[f"neff{k}"]) - 1) < 1e-12
+            h.resample(u)
+            assert np.array_equal(h.parents(), g[f"{key}{k}"]), (k, key)
+            assert np.array_equal(h.weights(), w[g[f"{key}{k}"]])  # weights are copied, not reset (SLAM.java:42)
+            h.close()
+
+
+def check_slam(lib, shared, via_dev=None):
+    """Replay of the pyref SLAM fixture.  `via_dev(handle, xy, dist, hit, dc, dth, normals)` lets the
+    CUDA tests route the update through the device-resident entry points instead of gms_update."""
+    g = golden("pyref_slam_shared.npz" if shared else "pyref_slam_pp.npz")
+    P, steps = int(g["P"]), int(g["steps"])
+    h = small_handle(lib, P=P, mode=B.MAP_SHARED if shared else B.MAP_PER_PARTICLE,
+                     resample_mode=B.RESAMPLE_LITERAL)
+    idx0, _, _ = h.strongest()
+    assert idx0 == -1
+    for s in range(steps):
+        args = (g[f"xy{s}"], g[f"dist{s}"], g[f"hit{s}"], float(g[f"dc{s}"]), float(g[f"dth{s}"]), g["normals"][s])
+        neff = via_dev(h, *args) if via_dev else h.update(*args)
+        assert np.array_equal(h.poses(), g[f"poses_upd{s}"]), s  # f32 poses bit-exact
+        np.testing.assert_allclose(h.log_weights(), g[f"lw{s}"], rtol=0, atol=LW_TOL)
+        np.testing.assert_allclose(h.weights(), g[f"w{s}"], rtol=W_RTOL, atol=1e-300)
+        assert abs(neff / float(g[f"neff{s}"]) - 1) < 1e-9
+        finite = np.isfinite(g[f"wlit{s}"]).all() and g[f"wlit{s}"].sum() > 0
+        if finite:  # Java's own (product) weights, where they did not underflow
+            np.testing.assert_allclose(h.weights(), g[f"wlit{s}"], rtol=1e-9, atol=1e-300)
+        idx, pose, w = h.strongest()
+        assert idx == int(g[f"strongest{s}"])
+        assert np.array_equal(pose, g[f"poses_upd{s}"][idx])
+        np.testing.assert_allclose(h.weighted_pose(), g[f"wpose{s}"], rtol=0, atol=1e-6)
+        if f"parents{s}" in g.files:
+            h.resample(float(g["uniforms"][s]))
+            assert np.array_equal(h.parents(), g[f"parents{s}"]), s
+        assert np.array_equal(h.poses(), g[f"poses{s}"]), s
+        for m in range(1 if shared else P):
+            assert np.array_equal(h.get_map(m, B.MAP_FREE_COUNT), g[f"nfree{s}"][m]), (s, m)
+            assert np.array_equal(h.get_map(m, B.MAP_OCC_COUNT), g[f"nocc{s}"][m]), (s, m)
+            assert np.array_equal(h.get_map(m, B.MAP_LIKELIHOOD), g[f"lik{s}"][m]), (s, m)
+            n = g[f"nfree{s}"][m].astype(np.float64) + g[f"nocc{s}"][m]
+            assert np.all(np.abs(h.get_map(m, B.MAP_LOG) - g[f"log{s}"][m]) <= 1e-9 * (n + 1))
+    h.close()
+
+
+def check_motion(lib):
+    """Motion model through gms_update on a map with no hits (weights irrelevant): P particles, one
+    step per fixture row group.  Poses must be bit-exact f32."""
+    g = golden("pyref_motion.npz")
+    poses, out = g["poses"], g["out"]
+    n = poses.shape[0]
+    # each fixture row has its own odometry: run them one particle at a time in groups sharing (dc, dth)
+    for i in range(0, n, 1):
+        if i >= 48:
+            break
+        h = lib.create(num_particles=1, map_width_m=0.5, map_height_m=0.5, map_mode=B.MAP_SHARED)
+        h.set_poses(poses[i])
+        h.update(np.zeros((0, 2)), np.zeros(0), np.zeros(0, np.uint8), float(g["d_center"][i]),
+                 float(g["d_theta"][i]), g["z"][i])
+        assert np.array_equal(h.poses()[0], out[i]), i
+        h.close()
+
+
+def check_errors(lib):
+    cfg = lib.default_config(num_particles=0)
+    try:
+        lib.create(cfg)
+        raise AssertionError("num_particles=0 accepted")
+    except B.GmsError as e:
+        assert e.code == B.ERR_INVALID_ARG
+    h = small_handle(lib, P=2)
+    try:
+        h.get_map(5, B.MAP_LOG)
+        raise AssertionError("bad particle accepted")
+    except B.GmsError as e:
+        assert e.code == B.ERR_INVALID_ARG
+    try:
+        h.get_map(0, 99)
+        raise AssertionError("bad kind accepted")
+    except B.GmsError as e:
+        assert e.code == B.ERR_INVALID_ARG
+    try:
+        h.resample(1.5)
+        raise AssertionError("u01 >= 1 accepted")
+    except B.GmsError as e:
+        assert e.code == B.ERR_INVALID_ARG
+    # empty scan: every weight is the empty product 1 -> uniform weights, Neff = P
+    neff = h.update(np.zeros((0, 2)), np.zeros(0), np.zeros(0, np.uint8), 0.0, 0.0, np.zeros(4))
+    assert abs(neff - 2.0) < 1e-12
+    assert np.array_equal(h.weights(), [0.5, 0.5])
+    h.close()

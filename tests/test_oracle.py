@@ -1,0 +1,64 @@
+"""CPU: the C oracle against (1) the hand-derived vectors of SURVEY.md Appendix B and (2) the golden
+fixtures written by the independent pure-Python restatement (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+
+import checks
+
+
+def test_constants(oracle):
+    checks.check_constants(oracle)
+
+
+def test_appendix_b_rays(oracle):
+    checks.check_appendix_b_rays(oracle)
+
+
+def test_appendix_b_resample(oracle):
+    checks.check_appendix_b_resample(oracle)
+
+
+def test_blank_likelihood(oracle):
+    checks.check_blank_likelihood(oracle)
+
+
+def test_golden_rays(oracle):
+    checks.check_rays(oracle)
+
+
+def test_golden_apply(oracle):
+    checks.check_apply(oracle)
+
+
+def test_golden_blur(oracle):
+    checks.check_blur(oracle)
+
+
+def test_golden_resample(oracle):
+    checks.check_resample(oracle)
+
+
+def test_golden_motion(oracle):
+    checks.check_motion(oracle)
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_golden_slam(oracle, shared):
+    checks.check_slam(oracle, shared)
+
+
+def test_errors(oracle):
+    checks.check_errors(oracle)
+
+
+def test_sign_of_count_form_is_robust():
+    """The CUDA path thresholds nFree*L_free + nOcc*L_occ instead of Java's sequentially accumulated
+    f64 sum.  The two can only disagree in sign if the exact value is within rounding error of 0;
+    show the closest approach over all count pairs up to 4096 is > 1e-4 (rounding error < 1e-11)."""
+    import appendix_b as AB
+
+    nf = np.arange(0, 4097, dtype=np.float64)[:, None]
+    no = np.arange(0, 4097, dtype=np.float64)[None, :]
+    v = np.abs(nf * AB.L_FREE + no * AB.L_OCC)
+    v[0, 0] = np.inf
+    assert v.min() > 1e-4
