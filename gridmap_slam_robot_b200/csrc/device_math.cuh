@@ -1,0 +1,196 @@
+// device_math.cuh — Java-exact scalar arithmetic shared by every kernel of libgms.
+//
+// The translation unit is compiled with --fmad=false: Java never contracts a*b+c, and the
+// bit-exact claims (ray cells, hit/miss counts, f32 poses, f64 likelihood field) depend on it.
+// References are to java/GridMapGL/src/main/java/com/fmsz/gridmapgl/.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gms {
+
+constexpr double kPi = 3.141592653589793;       // Math.PI
+constexpr double kTwoPi = 6.283185307179586;    // Math.PI * 2
+
+// Constants of one handle, passed by value to kernels (lives in the kernel parameter bank).
+struct Geometry {
+    int W, H;
+    int extra_steps;          // GridMap.java:210
+    int ktaps, khalf;         // GridMap.java:94-95
+    float res_f;              // GridMap.resolution
+    float tol_half;           // hitTolerance / 2 (SensorModel.java:35-37)
+    double res, posx, posy;   // (double) resolution / position: the promotions Java performs
+    double z_hit;             // GridMap.java:259
+    double uniform_term;      // 1.0 / SENSOR_MAX_RANGE                (GridMap.java:286)
+    double random_term;       // zRandom * 1.0 / SENSOR_MAX_RANGE      (GridMap.java:288)
+    double l_free, l_occ;     // Util.logOdds(P_FREE / P_OCCUPPIED)    (Util.java:35-37)
+    double kernel[31];        // Util.generateGaussianKernel           (Util.java:428-455)
+};
+
+// JLS 5.1.3 (int) of a double: NaN -> 0, saturating, truncation toward zero == cvt.rzi.s32.f64.
+__device__ __forceinline__ int java_d2i(double d) { return __double2int_rz(d); }
+
+// MathUtil.angleConstrain MathUtil.java:65-72.  The loops are replicated literally (they are NOT the
+// identity on in-range input: +2pi then -2pi rounds).  Deliberate divergence: |a| > 1e6 or
+// non-finite input returns unchanged where Java would spin (or hang on +-inf).
+__device__ __forceinline__ double angle_constrain(double a) {
+    if (!(fabs(a) <= 1e6)) return a;
+    while (a < kPi) a += kTwoPi;
+    while (a > kPi) a -= kTwoPi;
+    return a;
+}
+
+// MathUtil.cos(float) / sin(float) MathUtil.java:30-40: (float) FastMath.cos((double) radians).
+__device__ __forceinline__ float cos_f(float r) { return (float)cos((double)r); }
+__device__ __forceinline__ float sin_f(float r) { return (float)sin((double)r); }
+
+// Transform.fromRobotToWorld Transform.java:13-32: cos/sin rounded to f32, then widened.
+struct Xform {
+    double c, s, px, py;
+    __device__ __forceinline__ Xform(float x, float y, float theta)
+        : c((double)cos_f(theta)), s((double)sin_f(theta)), px((double)x), py((double)y) {}
+    __device__ __forceinline__ double tx(double x, double y) const { return x * c - y * s + px; }
+    __device__ __forceinline__ double ty(double x, double y) const { return x * s + y * c + py; }
+};
+
+// ---- Philox4x32-10: motion noise / resampling uniform when the caller does not inject draws ----
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b, bool centred) {
+    uint64_t k = ((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6);
+    return centred ? ((double)k + 0.5) * 0x1p-53 : (double)k * 0x1p-53;
+}
+__device__ __forceinline__ void philox_normals(uint64_t seed, uint32_t gidx, uint64_t step, double& zd,
+                                               double& zt) {
+    uint32_t c[4] = {gidx, (uint32_t)step, (uint32_t)(step >> 32), 0u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    double u1 = u53(c[0], c[1], true), u2 = u53(c[2], c[3], false);
+    double r = sqrt(-2.0 * log(u1));
+    double a = 6.283185307179586 * u2;
+    zd = r * cos(a);
+    zt = r * sin(a);
+}
+__device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t n) {
+    uint32_t c[4] = {(uint32_t)n, (uint32_t)(n >> 32), 0u, 1u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return u53(c[0], c[1], false);
+}
+
+// ---- RayIterator RayIterator.java:65-130 ----
+struct RayIter {
+    int x, y, x_inc, y_inc, n;
+    float dx, dy, error;
+
+    __device__ __forceinline__ void init(float x0, float y0, float x1, float y1, int additional) {
+        dx = fabsf(x1 - x0);
+        dy = fabsf(y1 - y0);
+        const double fx0 = floor((double)x0), fy0 = floor((double)y0);
+        x = java_d2i(fx0);
+        y = java_d2i(fy0);
+        n = 1 + additional;
+        if (dx == 0.0f) {
+            x_inc = 0;
+            error = __int_as_float(0x7f800000);
+        } else if (x1 > x0) {
+            x_inc = 1;
+            n += java_d2i(floor((double)x1) - (double)x);
+            error = (float)((fx0 + 1.0 - (double)x0) * (double)dy);
+        } else {
+            x_inc = -1;
+            n += x - java_d2i(floor((double)x1));
+            error = (float)(((double)x0 - fx0) * (double)dy);
+        }
+        if (dy == 0.0f) {
+            y_inc = 0;
+            error = error - __int_as_float(0x7f800000);
+        } else if (y1 > y0) {
+            y_inc = 1;
+            n += java_d2i(floor((double)y1)) - y;
+            error = (float)((double)error - (fy0 + 1.0 - (double)y0) * (double)dx);
+        } else {
+            y_inc = -1;
+            n += y - java_d2i(floor((double)y1));
+            error = (float)((double)error - ((double)y0 - fy0) * (double)dx);
+        }
+    }
+    __device__ __forceinline__ bool has_next(int W, int H) const {
+        return n > 0 && !(x < 0 || x >= W || y < 0 || y >= H);
+    }
+    __device__ __forceinline__ void advance() {
+        if (error > 0.0f) {
+            y += y_inc;
+            error -= dx;
+        } else {
+            x += x_inc;
+            error += dy;
+        }
+        n -= 1;
+    }
+};
+
+// SensorModel.inverseSensorModel SensorModel.java:31-41 -> 0 prior (+= 0), 1 free, 2 occupied.
+__device__ __forceinline__ int inverse_sensor_class(float current, float measured, bool was_hit,
+                                                    float tol_half) {
+    if (!was_hit) return current < measured ? 1 : 0;
+    if (current < measured - tol_half) return 1;
+    if (current > measured + tol_half) return 0;
+    return 2;
+}
+
+// A map cell: the two integer counters that represent Java's f64 log-odds exactly
+// (every increment is one of L_free, L_occ, 0.0 — GridMap.java:223, SensorModel.java:23-25).
+struct __align__(8) CellCounts {
+    uint32_t n_free, n_occ;
+};
+
+// GridMap.applyMeasurement GridMap.java:194-228 on integer counters.  Integer atomics commute, so the
+// result is independent of the order in which rays (threads) land: deterministic by construction.
+struct CellBox {
+    int x0, y0, x1, y1;
+};
+__device__ __forceinline__ void apply_measurement(CellCounts* __restrict__ map, const Geometry& g, float sx,
+                                                  float sy, float ex, float ey, float meas, bool was_hit,
+                                                  CellBox& box) {
+    RayIter it;
+    it.init(sx + 0.5f, sy + 0.5f, ex + 0.5f, ey + 0.5f, g.extra_steps);
+    box.x0 = box.y0 = 0x7fffffff;
+    box.x1 = box.y1 = -1;
+    if (!it.has_next(g.W, g.H)) return;
+    box.x0 = box.x1 = it.x;
+    box.y0 = box.y1 = it.y;
+    int lx = it.x, ly = it.y;
+    while (it.has_next(g.W, g.H)) {
+        lx = it.x;
+        ly = it.y;
+        const float dX = sx - ((float)lx + 0.5f);
+        const float dY = sy - ((float)ly + 0.5f);
+        const float dist = __fsqrt_rn(dX * dX + dY * dY);  // (float) Math.sqrt((double) f32) == sqrt.rn.f32
+        const int cls = inverse_sensor_class(dist, meas, was_hit, g.tol_half);
+        if (cls != 0) {
+            uint32_t* p = reinterpret_cast<uint32_t*>(map + ((size_t)lx + (size_t)ly * g.W)) + (cls - 1);
+            atomicAdd(p, 1u);  // result unused -> RED.E.ADD
+        }
+        it.advance();
+    }
+    // the walk is monotone in x and in y: its bounding box is spanned by the first and last cell
+    box.x0 = min(box.x0, lx); box.x1 = max(box.x1, lx);
+    box.y0 = min(box.y0, ly); box.y1 = max(box.y1, ly);
+}
+
+// ---- warp helpers ----
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace gms

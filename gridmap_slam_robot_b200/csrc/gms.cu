@@ -1,0 +1,958 @@
+// gms.cu — libgms.so: the CUDA (sm_100a) implementation of include/gms.h.
+// No CPU fallback: every entry point runs the kernels of kernels.cuh or fails with an error code.
+// Host-side arithmetic here is limited to what the reference does once per GridMap / Odometry
+// construction (grid size, Gaussian taps, log-odds constants, noise sigmas), with the same
+// promotions as the Java source (cited inline).
+#include "../../include/gms.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace gms;
+
+#define EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+thread_local std::string g_create_err;
+
+struct PhaseSpan {
+    int phase;
+    cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct gms_handle {
+    gms_config cfg{};
+    Geometry g{};
+    int W = 0, H = 0, P = 0, lo = 0, cnt = 0, S = 0, dev = 0, resample_mode = 0;
+    size_t cells = 0;
+    float world_w = 0, world_h = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // particle state (double buffered for resampling)
+    float4* pose[2] = {nullptr, nullptr};
+    double* w[2] = {nullptr, nullptr};
+    double* lw[2] = {nullptr, nullptr};
+    int* slot[2] = {nullptr, nullptr};
+    int cur = 0, slot_cur = 0;
+    int* parents = nullptr;
+    void* cdf = nullptr;
+    // maps
+    CellCounts* counts = nullptr;
+    double* lik = nullptr;
+    int4* rect = nullptr;
+    int4* tile_desc = nullptr;
+    int* tile_off = nullptr;
+    int *dup_src = nullptr, *dup_dst = nullptr, *scratch2p = nullptr;
+    // beams
+    int bcap = 0;
+    double2 *in_xy = nullptr, *all_xy = nullptr, *hit_xy = nullptr;
+    double* in_dist = nullptr;
+    uint8_t *in_hit = nullptr, *all_hit = nullptr;
+    float* meas = nullptr;
+    double* d_normals = nullptr;
+    // exchange, scratch, stats
+    ExchangeRec *xlocal = nullptr, *xglobal = nullptr;
+    void* d_tmp = nullptr;  // max(cells*8, P*24) bytes
+    size_t d_tmp_bytes = 0;
+    float4* tmp_pose = nullptr;
+    int* tmp_slot = nullptr;
+    double* tmp_lw = nullptr;
+    Stats* st = nullptr;
+    Stats* h_st = nullptr;  // pinned
+    unsigned char* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    bool stats_valid = false;
+    // step bookkeeping
+    uint64_t step = 0, resample_count = 0;
+    bool have_update = false, pending = false;
+    double pend_dtheta = 0;
+    int pend_B = 0;
+    // profiling
+    bool profile = false;
+    std::vector<PhaseSpan> spans;
+    std::vector<cudaEvent_t> pool;
+    double phase_ms[GMS_PHASE_COUNT] = {0};
+    int64_t phase_launches[GMS_PHASE_COUNT] = {0};
+    int64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(gms_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_err = msg;
+    return code;
+}
+int cuda_fail(gms_handle* h, cudaError_t e, const char* what) {
+    std::string m = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    (void)cudaGetLastError();
+    return fail(h, e == cudaErrorMemoryAllocation ? GMS_ERR_OOM : GMS_ERR_CUDA, m);
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return cuda_fail(h, e_, #call);     \
+    } while (0)
+#define ENTER(h)                                                   \
+    if (!(h)) return GMS_ERR_INVALID_ARG;                          \
+    CK(cudaSetDevice((h)->dev))
+
+struct Phase {  // RAII: CUDA events around one phase when profiling is on
+    gms_handle* h;
+    int phase;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Phase(gms_handle* h_, int p) : h(h_), phase(p) {
+        if (!h->profile) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!h->pool.empty()) { e = h->pool.back(); h->pool.pop_back(); }
+            else cudaEventCreate(&e);
+            return e;
+        };
+        a = get(); b = get();
+        cudaEventRecord(a, h->stream);
+    }
+    ~Phase() {
+        if (!a) return;
+        cudaEventRecord(b, h->stream);
+        h->spans.push_back({phase, a, b});
+    }
+};
+inline void count_launch(gms_handle* h, int phase) {
+    h->launches++;
+    h->phase_launches[phase]++;
+}
+#define LAUNCH(phase, ...)                                         \
+    do {                                                           \
+        __VA_ARGS__;                                               \
+        count_launch(h, phase);                                    \
+        CK(cudaGetLastError());                                    \
+    } while (0)
+
+int flush_profile(gms_handle* h) {
+    if (h->spans.empty()) return GMS_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    for (auto& s : h->spans) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, s.a, s.b));
+        h->phase_ms[s.phase] += ms;
+        h->pool.push_back(s.a);
+        h->pool.push_back(s.b);
+    }
+    h->spans.clear();
+    return GMS_OK;
+}
+
+inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// Util.generateGaussianKernel Util.java:428-455 (host, once per GridMap: GridMap.java:94-95)
+void gaussian_kernel(double sigma, int size, double* values) {
+    const double norm = 1.0 / (std::sqrt(2 * M_PI) * sigma);
+    const double coeff = 2 * sigma * sigma;
+    double total = 0;
+    for (int x = -size; x <= size; x++) {
+        const double gv = norm * std::exp((double)(-x * x) / coeff);
+        values[x + size] = gv;
+        total += gv;
+    }
+    for (int i = 0; i < 2 * size + 1; i++) values[i] /= total;
+}
+double log_odds(double p) { return std::log(p / (1.0 - p)); }  // Util.java:35-37 (1.0f - odds promotes)
+int java_d2i_host(double d) {
+    if (d != d) return 0;
+    if (d >= 2147483647.0) return 2147483647;
+    if (d <= -2147483648.0) return -2147483647 - 1;
+    return (int)d;
+}
+
+void free_all(gms_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->dev);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < 2; i++) { cudaFree(h->pose[i]); cudaFree(h->w[i]); cudaFree(h->lw[i]); cudaFree(h->slot[i]); }
+    cudaFree(h->parents); cudaFree(h->cdf); cudaFree(h->counts); cudaFree(h->lik); cudaFree(h->rect);
+    cudaFree(h->tile_desc); cudaFree(h->tile_off); cudaFree(h->dup_src); cudaFree(h->dup_dst); cudaFree(h->scratch2p);
+    cudaFree(h->in_xy); cudaFree(h->all_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
+    cudaFree(h->all_hit); cudaFree(h->meas); cudaFree(h->d_normals); cudaFree(h->xlocal); cudaFree(h->xglobal);
+    cudaFree(h->d_tmp); cudaFree(h->tmp_pose); cudaFree(h->tmp_slot); cudaFree(h->tmp_lw); cudaFree(h->st);
+    if (h->h_st) cudaFreeHost(h->h_st);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    for (auto& s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto e : h->pool) cudaEventDestroy(e);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int ensure_stage(gms_handle* h, size_t bytes) {
+    if (bytes <= h->h_stage_bytes) return GMS_OK;
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    h->h_stage = nullptr;
+    h->h_stage_bytes = 0;
+    size_t n = bytes + bytes / 2 + 4096;
+    CK(cudaMallocHost((void**)&h->h_stage, n));
+    h->h_stage_bytes = n;
+    return GMS_OK;
+}
+
+int ensure_beams(gms_handle* h, int B) {
+    if (B <= h->bcap) return GMS_OK;
+    if ((size_t)B * 16 > 200 * 1024) return fail(h, GMS_ERR_INVALID_ARG, "too many beams (max 12800)");
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->in_xy); cudaFree(h->all_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
+    cudaFree(h->all_hit); cudaFree(h->meas);
+    h->in_xy = h->all_xy = h->hit_xy = nullptr; h->in_dist = nullptr; h->in_hit = h->all_hit = nullptr; h->meas = nullptr;
+    h->bcap = 0;
+    const int cap = ((B + 255) / 256) * 256;
+    CK(cudaMalloc((void**)&h->in_xy, (size_t)cap * 16));
+    CK(cudaMalloc((void**)&h->all_xy, (size_t)cap * 16));
+    CK(cudaMalloc((void**)&h->hit_xy, (size_t)cap * 16));
+    CK(cudaMalloc((void**)&h->in_dist, (size_t)cap * 8));
+    CK(cudaMalloc((void**)&h->in_hit, (size_t)cap));
+    CK(cudaMalloc((void**)&h->all_hit, (size_t)cap));
+    CK(cudaMalloc((void**)&h->meas, (size_t)cap * 4));
+    h->bcap = cap;
+    return GMS_OK;
+}
+
+int fetch_stats(gms_handle* h) {
+    if (h->stats_valid) return GMS_OK;
+    CK(cudaMemcpyAsync(h->h_st, h->st, sizeof(Stats), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->stats_valid = true;
+    return GMS_OK;
+}
+
+// ---- the step, as stream-ordered launches ---------------------------------------------------------
+int launch_pack(gms_handle* h, const double* d_xy, const double* d_dist, const uint8_t* d_hit, int B) {
+    int rc = ensure_beams(h, B);
+    if (rc) return rc;
+    if (B > 0) {
+        if ((const void*)d_xy != (const void*)h->all_xy)
+            CK(cudaMemcpyAsync(h->all_xy, d_xy, (size_t)B * 16, cudaMemcpyDeviceToDevice, h->stream));
+        if ((const void*)d_hit != (const void*)h->all_hit)
+            CK(cudaMemcpyAsync(h->all_hit, d_hit, (size_t)B, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    LAUNCH(GMS_PHASE_SCORE, k_pack_beams<<<1, 256, 0, h->stream>>>(h->all_xy, d_dist, h->all_hit, B, h->g.res_f,
+                                                                   h->hit_xy, h->meas, h->st));
+    return GMS_OK;
+}
+
+int launch_likelihood(gms_handle* h) {
+    Phase ph(h, GMS_PHASE_LIKELIHOOD);
+    LAUNCH(GMS_PHASE_LIKELIHOOD,
+           k_lik_worklist<<<1, 1024, 0, h->stream>>>(h->rect, h->S, h->W, h->H, h->g.khalf, h->tile_desc,
+                                                      h->tile_off, h->st));
+    const int k = h->g.khalf, th = kTileH + 2 * k, tw = kTileW + 2 * k;
+    const size_t smem = (size_t)th * kTileW * 8 + (size_t)th * tw * 4;
+    const long long max_tiles = (long long)h->S * ((h->W + kTileW - 1) / kTileW) * ((h->H + kTileH - 1) / kTileH);
+    const unsigned grid = (unsigned)std::min<long long>(max_tiles, 148 * 6);
+    LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<<<grid, 256, smem, h->stream>>>(h->counts, h->lik, h->tile_desc,
+                                                                               h->tile_off, h->S, h->st, h->g));
+    return GMS_OK;
+}
+
+int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* slot, double* lw,
+                 ExchangeRec* xlocal, int B) {
+    Phase ph(h, GMS_PHASE_SCORE);
+    const unsigned grid = std::min<unsigned>(blocks_for(cnt, 8), 148 * 8);
+    const size_t smem = std::max<size_t>(16, (size_t)B * 16);
+    LAUNCH(GMS_PHASE_SCORE, k_score<<<grid, 256, smem, h->stream>>>(pose, lo, cnt, h->hit_xy, h->st, h->lik, slot,
+                                                                     lw, xlocal, h->g));
+    return GMS_OK;
+}
+
+int launch_map_update(gms_handle* h, const float4* pose, int lo, int cnt, const int* slot, int B, int shared) {
+    if (B <= 0) return GMS_OK;
+    Phase ph(h, GMS_PHASE_MAP_UPDATE);
+    const long long total = shared ? (long long)B : (long long)cnt * B;
+    LAUNCH(GMS_PHASE_MAP_UPDATE,
+           k_map_update<<<blocks_for(total, 128), 128, 0, h->stream>>>(pose, lo, cnt, h->all_xy, h->meas, h->all_hit,
+                                                                       B, h->counts, slot, h->rect, h->st, shared,
+                                                                       h->g));
+    return GMS_OK;
+}
+
+int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const uint8_t* d_hit, int B, double d_center,
+               double d_theta, const double* d_normals) {
+    const gms_config& c = h->cfg;
+    h->stats_valid = false;
+    int rc = launch_pack(h, d_xy, d_dist, d_hit, B);
+    if (rc) return rc;
+    {
+        Phase ph(h, GMS_PHASE_MOTION);
+        // Odometry.recalculateStdDev Odometry.java:60-69
+        const double sd_c = (c.noise_center_base + std::fabs(d_center) * c.noise_center_gain) / 2;
+        const double sd_t = c.noise_theta_base_deg * (M_PI / 180.0) + c.noise_theta_gain * std::fabs(d_theta);
+        LAUNCH(GMS_PHASE_MOTION, k_motion<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(
+                                     h->pose[h->cur], h->lo, h->cnt, d_normals, c.seed, h->step, d_center, d_theta,
+                                     sd_c, sd_t));
+    }
+    rc = launch_likelihood(h);
+    if (rc) return rc;
+    const bool shared = c.map_mode == GMS_MAP_SHARED;
+    rc = launch_score(h, h->pose[h->cur], h->lo, h->cnt, shared ? nullptr : h->slot[h->slot_cur], h->lw[h->cur],
+                      c.nranks > 1 ? h->xlocal : nullptr, B);
+    if (rc) return rc;
+    const bool skip = std::fabs(d_theta) > (M_PI / 180.0) * c.skip_update_deg;  // SLAM.java:82
+    if (!shared && !skip) {
+        rc = launch_map_update(h, h->pose[h->cur], h->lo, h->cnt, h->slot[h->slot_cur], B, 0);
+        if (rc) return rc;
+    }
+    h->pending = true;
+    h->pend_dtheta = d_theta;
+    h->pend_B = B;
+    return GMS_OK;
+}
+
+int launch_resample(gms_handle* h, double u01) {
+    const int P = h->P;
+    {
+        Phase ph(h, GMS_PHASE_RESAMPLE);
+        if (h->resample_mode == GMS_RESAMPLE_FIXED) {
+            LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_fixed<<<1, 1024, 0, h->stream>>>(h->w[h->cur], P,
+                                                                              (unsigned long long*)h->cdf, h->st));
+            LAUNCH(GMS_PHASE_RESAMPLE, k_select<true><<<blocks_for(P, 256), 256, 0, h->stream>>>(
+                                           h->cdf, P, u01, h->cfg.seed, h->resample_count, h->parents, h->st));
+        } else {
+            LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_literal<<<1, 32, 0, h->stream>>>(h->w[h->cur], P, (double*)h->cdf, h->st));
+            LAUNCH(GMS_PHASE_RESAMPLE, k_select<false><<<blocks_for(P, 256), 256, 0, h->stream>>>(
+                                           h->cdf, P, u01, h->cfg.seed, h->resample_count, h->parents, h->st));
+        }
+        const int nxt = h->cur ^ 1;
+        LAUNCH(GMS_PHASE_RESAMPLE, k_gather<<<blocks_for(P, 256), 256, 0, h->stream>>>(
+                                       h->parents, P, h->pose[h->cur], h->w[h->cur], h->lw[h->cur], h->pose[nxt],
+                                       h->w[nxt], h->lw[nxt]));
+        h->cur = nxt;
+    }
+    h->resample_count++;
+    if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE) {
+        if (h->cfg.nranks != 1)
+            return fail(h, GMS_ERR_UNSUPPORTED, "per-particle maps across ranks: use the migration entry points");
+        Phase ph(h, GMS_PHASE_MAP_COPY);
+        const int nxt = h->slot_cur ^ 1;
+        LAUNCH(GMS_PHASE_MAP_COPY, k_assign_slots<<<1, 1024, 0, h->stream>>>(h->parents, P, h->slot[h->slot_cur],
+                                                                              h->slot[nxt], h->dup_src, h->dup_dst,
+                                                                              h->scratch2p, h->st));
+        h->slot_cur = nxt;
+        const size_t bytes = h->cells * 16;
+        const int chunks = (int)std::max<size_t>(1, std::min<size_t>(1024, bytes / (64 * 1024)));
+        LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps<<<(unsigned)((long long)chunks * P), 256, 0, h->stream>>>(
+                                       h->counts, h->lik, h->rect, h->dup_src, h->dup_dst, h->st, h->cells, chunks));
+    }
+    return GMS_OK;
+}
+
+__global__ void k_set_resample_flag(Stats* st, int v) { st->do_resample = v; }
+
+int step_end(gms_handle* h, int policy, double u01) {
+    if (!h->pending) return fail(h, GMS_ERR_STATE, "update_end without update_begin");
+    const gms_config& c = h->cfg;
+    h->stats_valid = false;
+    if (c.nranks > 1)
+        LAUNCH(GMS_PHASE_NORMALISE, k_import_exchange<<<blocks_for(h->P, 256), 256, 0, h->stream>>>(
+                                        h->xglobal, h->P, h->lw[h->cur], h->pose[h->cur]));
+    {
+        Phase ph(h, GMS_PHASE_NORMALISE);
+        LAUNCH(GMS_PHASE_NORMALISE, k_normalise<<<1, 1024, 0, h->stream>>>(h->lw[h->cur], h->w[h->cur], h->pose[h->cur],
+                                                                            h->P, policy, h->st));
+    }
+    const bool skip = std::fabs(h->pend_dtheta) > (M_PI / 180.0) * c.skip_update_deg;
+    if (c.map_mode == GMS_MAP_SHARED && !skip) {
+        int rc = launch_map_update(h, h->pose[h->cur], 0, 1, nullptr, h->pend_B, 1);
+        if (rc) return rc;
+    }
+    h->step++;
+    h->have_update = true;
+    h->pending = false;
+    if (policy != GMS_RESAMPLE_NEVER) return launch_resample(h, u01);
+    return GMS_OK;
+}
+
+int slot_of(gms_handle* h, int particle, int* slot) {
+    if (h->cfg.map_mode == GMS_MAP_SHARED) { *slot = 0; return GMS_OK; }
+    if (particle < h->lo || particle >= h->lo + h->cnt)
+        return fail(h, GMS_ERR_INVALID_ARG, "particle index is not held by this handle");
+    CK(cudaMemcpyAsync(slot, h->slot[h->slot_cur] + (particle - h->lo), sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GMS_OK;
+}
+
+int upload_beams(gms_handle* h, const double* xy, const double* dist, const uint8_t* hit, int B) {
+    int rc = ensure_beams(h, B);
+    if (rc) return rc;
+    if (B == 0) return GMS_OK;
+    const size_t need = (size_t)B * 25;
+    rc = ensure_stage(h, need + 64);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));  // the staging buffer may still feed an earlier copy
+    unsigned char* s = h->h_stage;
+    std::memcpy(s, xy, (size_t)B * 16);
+    std::memcpy(s + (size_t)B * 16, dist ? (const void*)dist : (const void*)xy, (size_t)B * 8);
+    std::memcpy(s + (size_t)B * 24, hit, (size_t)B);
+    CK(cudaMemcpyAsync(h->all_xy, s, (size_t)B * 16, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->in_dist, s + (size_t)B * 16, (size_t)B * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->all_hit, s + (size_t)B * 24, (size_t)B, cudaMemcpyHostToDevice, h->stream));
+    return GMS_OK;
+}
+
+int do_reset(gms_handle* h) {
+    const int P = h->P;
+    for (int i = 0; i < 2; i++)
+        LAUNCH(GMS_PHASE_COUNT - 1, k_init_particles<<<blocks_for(P, 256), 256, 0, h->stream>>>(h->pose[i], h->w[i],
+                                                                                               h->lw[i], h->parents, P));
+    if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE)
+        for (int i = 0; i < 2; i++)
+            LAUNCH(GMS_PHASE_COUNT - 1, k_iota<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(h->slot[i], h->cnt));
+    // GridMap.createMapData(null) GridMap.java:106-117: logData = logOdds(0.5) = 0.0 (no counts),
+    // likelihoodData = 0.0 until the first computeLikelihoodMap; the whole map is dirty.
+    CK(cudaMemsetAsync(h->counts, 0, (size_t)h->S * h->cells * sizeof(CellCounts), h->stream));
+    CK(cudaMemsetAsync(h->lik, 0, (size_t)h->S * h->cells * sizeof(double), h->stream));
+    LAUNCH(GMS_PHASE_COUNT - 1, k_fill_rect<<<blocks_for(h->S, 256), 256, 0, h->stream>>>(
+                                    h->rect, h->S, make_int4(0, 0, h->W - 1, h->H - 1)));
+    CK(cudaMemsetAsync(h->st, 0, sizeof(Stats), h->stream));
+    h->cur = 0; h->slot_cur = 0;
+    h->step = 0; h->resample_count = 0;
+    h->have_update = false; h->pending = false; h->stats_valid = false;
+    CK(cudaStreamSynchronize(h->stream));
+    return GMS_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+EXPORT int gms_config_default(gms_config* cfg) {
+    if (!cfg) return GMS_ERR_INVALID_ARG;
+    std::memset(cfg, 0, sizeof *cfg);
+    cfg->struct_size = (uint32_t)sizeof *cfg;
+    cfg->num_particles = 500;        // SLAM.java:50
+    cfg->map_width_m = 6.0f;         // SLAM.java:57
+    cfg->map_height_m = 6.0f;
+    cfg->resolution = 0.05f;
+    cfg->origin_x = -3.0f;
+    cfg->origin_y = -3.0f;
+    cfg->sensor_max_range = 10.0f;   // SensorModel.java:20
+    cfg->z_hit = 0.9;                // GridMap.java:259
+    cfg->hit_tolerance = 2.0f;       // GridMap.java:223
+    cfg->extra_steps = 2;            // GridMap.java:210
+    cfg->p_free = 0.30f;             // SensorModel.java:23-24
+    cfg->p_occ = 0.9f;
+    cfg->noise_center_base = 0.01;   // Odometry.java:63-64
+    cfg->noise_center_gain = 0.05;
+    cfg->noise_theta_base_deg = 5;
+    cfg->noise_theta_gain = 0.1;
+    cfg->skip_update_deg = 30;       // SLAM.java:82
+    cfg->likelihood_sigma_num = 0.05;  // GridMap.java:94
+    cfg->map_mode = GMS_MAP_PER_PARTICLE;
+    cfg->resample_mode = GMS_RESAMPLE_AUTO;
+    cfg->device = 0;
+    cfg->rank = 0;
+    cfg->nranks = 1;
+    cfg->seed = 0x5EEDull;
+    return GMS_OK;
+}
+
+EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
+    gms_handle* h = nullptr;  // for the CK / fail macros before the handle exists
+    if (!cfg || !out) return fail(nullptr, GMS_ERR_INVALID_ARG, "gms_create: NULL argument");
+    if (cfg->struct_size != sizeof(gms_config))
+        return fail(nullptr, GMS_ERR_INVALID_ARG, "gms_create: gms_config.struct_size mismatch");
+    if (cfg->num_particles < 1 || !(cfg->resolution > 0) || !(cfg->map_width_m > 0) || !(cfg->map_height_m > 0) ||
+        cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks || cfg->extra_steps < 0 ||
+        (cfg->map_mode != GMS_MAP_PER_PARTICLE && cfg->map_mode != GMS_MAP_SHARED) || cfg->resample_mode < 0 ||
+        cfg->resample_mode > 2 || cfg->num_particles % cfg->nranks != 0)
+        return fail(nullptr, GMS_ERR_INVALID_ARG, "gms_create: invalid configuration");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1 || cfg->device < 0 || cfg->device >= ndev) {
+        (void)cudaGetLastError();
+        return fail(nullptr, GMS_ERR_CUDA,
+                    std::string("gms_create: no usable CUDA device (libgms has no CPU fallback): ") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range"));
+    }
+    h = new (std::nothrow) gms_handle();
+    if (!h) return fail(nullptr, GMS_ERR_OOM, "gms_create: out of host memory");
+    h->cfg = *cfg;
+    h->dev = cfg->device;
+    // GridMap ctor GridMap.java:80-100
+    h->W = java_d2i_host(std::ceil((double)(cfg->map_width_m / cfg->resolution)));
+    h->H = java_d2i_host(std::ceil((double)(cfg->map_height_m / cfg->resolution)));
+    h->world_w = (float)h->W * cfg->resolution;
+    h->world_h = (float)h->H * cfg->resolution;
+    const double sigma = std::sqrt(cfg->likelihood_sigma_num / (double)cfg->resolution);
+    const int half = java_d2i_host(std::ceil(sigma * 3));
+    if (2 * half + 1 > 31 || h->W < 1 || h->H < 1 || (long long)h->W * h->H > (1LL << 31) - 1) {
+        delete h;
+        return fail(nullptr, GMS_ERR_INVALID_ARG, "gms_create: kernel too wide or grid size out of range");
+    }
+    Geometry& g = h->g;
+    g.W = h->W; g.H = h->H;
+    g.extra_steps = cfg->extra_steps;
+    g.khalf = half; g.ktaps = 2 * half + 1;
+    g.res_f = cfg->resolution;
+    g.tol_half = cfg->hit_tolerance / 2;
+    g.res = (double)cfg->resolution; g.posx = (double)cfg->origin_x; g.posy = (double)cfg->origin_y;
+    g.z_hit = cfg->z_hit;
+    g.uniform_term = 1.0 / (double)cfg->sensor_max_range;                          // GridMap.java:286
+    g.random_term = (1 - cfg->z_hit) * 1.0 / (double)cfg->sensor_max_range;        // GridMap.java:288
+    g.l_free = log_odds((double)cfg->p_free);
+    g.l_occ = log_odds((double)cfg->p_occ);
+    gaussian_kernel(sigma, half, g.kernel);
+    h->P = cfg->num_particles;
+    h->cnt = h->P / cfg->nranks;
+    h->lo = cfg->rank * h->cnt;
+    h->S = cfg->map_mode == GMS_MAP_SHARED ? 1 : h->cnt;
+    h->cells = (size_t)h->W * h->H;
+    h->resample_mode = cfg->resample_mode == GMS_RESAMPLE_AUTO
+                           ? (h->P <= 16384 ? GMS_RESAMPLE_LITERAL : GMS_RESAMPLE_FIXED)
+                           : cfg->resample_mode;
+    auto bail = [&](int rc) {
+        std::string m = h->err;
+        free_all(h);
+        g_create_err = m;
+        return rc;
+    };
+#define CKC(call)                                                                \
+    do {                                                                         \
+        cudaError_t e_ = (call);                                                 \
+        if (e_ != cudaSuccess) return bail(cuda_fail(h, e_, #call));             \
+    } while (0)
+    CKC(cudaSetDevice(h->dev));
+    CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    const size_t P = (size_t)h->P;
+    for (int i = 0; i < 2; i++) {
+        CKC(cudaMalloc((void**)&h->pose[i], P * sizeof(float4)));
+        CKC(cudaMalloc((void**)&h->w[i], P * 8));
+        CKC(cudaMalloc((void**)&h->lw[i], P * 8));
+        CKC(cudaMalloc((void**)&h->slot[i], (size_t)h->cnt * 4));
+    }
+    CKC(cudaMalloc((void**)&h->parents, P * 4));
+    CKC(cudaMalloc((void**)&h->cdf, P * 8));
+    CKC(cudaMalloc((void**)&h->counts, (size_t)h->S * h->cells * sizeof(CellCounts)));
+    CKC(cudaMalloc((void**)&h->lik, (size_t)h->S * h->cells * sizeof(double)));
+    CKC(cudaMalloc((void**)&h->rect, (size_t)h->S * sizeof(int4)));
+    CKC(cudaMalloc((void**)&h->tile_desc, (size_t)h->S * sizeof(int4)));
+    CKC(cudaMalloc((void**)&h->tile_off, ((size_t)h->S + 1) * 4));
+    CKC(cudaMalloc((void**)&h->dup_src, P * 4));
+    CKC(cudaMalloc((void**)&h->dup_dst, P * 4));
+    CKC(cudaMalloc((void**)&h->scratch2p, 2 * P * 4));
+    CKC(cudaMalloc((void**)&h->d_normals, (size_t)h->cnt * 16));
+    CKC(cudaMalloc((void**)&h->xlocal, (size_t)h->cnt * sizeof(ExchangeRec)));
+    CKC(cudaMalloc((void**)&h->xglobal, P * sizeof(ExchangeRec)));
+    h->d_tmp_bytes = std::max(h->cells * 8, P * 24);
+    CKC(cudaMalloc(&h->d_tmp, h->d_tmp_bytes));
+    CKC(cudaMalloc((void**)&h->tmp_pose, sizeof(float4)));
+    CKC(cudaMalloc((void**)&h->tmp_slot, sizeof(int)));
+    CKC(cudaMalloc((void**)&h->tmp_lw, sizeof(double)));
+    CKC(cudaMalloc((void**)&h->st, sizeof(Stats)));
+    CKC(cudaMallocHost((void**)&h->h_st, sizeof(Stats)));
+    CKC(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKC(cudaFuncSetAttribute(k_likelihood, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    int rc = ensure_beams(h, 1024);
+    if (rc) return bail(rc);
+    rc = ensure_stage(h, 1 << 20);
+    if (rc) return bail(rc);
+    rc = do_reset(h);
+    if (rc) return bail(rc);
+    *out = h;
+    return GMS_OK;
+}
+
+EXPORT int gms_destroy(gms_handle* h) {
+    free_all(h);
+    return GMS_OK;
+}
+
+EXPORT const char* gms_last_error(const gms_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+EXPORT int gms_get_info(const gms_handle* h, gms_info* info) {
+    if (!h || !info) return GMS_ERR_INVALID_ARG;
+    std::memset(info, 0, sizeof *info);
+    info->abi_version = GMS_ABI_VERSION;
+    info->is_cuda = 1;
+    info->grid_w = h->W; info->grid_h = h->H;
+    info->num_particles = h->P; info->local_begin = h->lo; info->local_count = h->cnt;
+    info->num_slots = h->S; info->kernel_taps = h->g.ktaps; info->resample_mode = h->resample_mode;
+    std::memcpy(info->kernel, h->g.kernel, sizeof(double) * h->g.ktaps);
+    info->l_free = h->g.l_free; info->l_occ = h->g.l_occ;
+    info->world_w = h->world_w; info->world_h = h->world_h;
+    return GMS_OK;
+}
+
+EXPORT int gms_reset(gms_handle* h) {
+    ENTER(h);
+    return do_reset(h);
+}
+
+EXPORT int gms_update(gms_handle* h, const double* beam_xy, const double* beam_dist, const uint8_t* beam_hit,
+                      int32_t B, double d_center, double d_theta, const double* normals, double* neff_out) {
+    ENTER(h);
+    if (B < 0 || (B > 0 && (!beam_xy || !beam_dist || !beam_hit)))
+        return fail(h, GMS_ERR_INVALID_ARG, "gms_update: bad beam arrays");
+    if (h->cfg.nranks != 1) return fail(h, GMS_ERR_STATE, "gms_update: multi-rank handles use update_begin/end");
+    // staging layout: [beams | pad to 64 | normals]; size it once so upload_beams never re-allocates
+    const size_t off = (((size_t)B * 25 + 63) / 64) * 64;
+    int rc = ensure_stage(h, off + (normals ? (size_t)h->cnt * 16 : 0) + 64);
+    if (rc) return rc;
+    if ((rc = upload_beams(h, beam_xy, beam_dist, beam_hit, B))) return rc;
+    const double* d_normals = nullptr;
+    if (normals) {
+        std::memcpy(h->h_stage + off, normals, (size_t)h->cnt * 16);
+        CK(cudaMemcpyAsync(h->d_normals, h->h_stage + off, (size_t)h->cnt * 16, cudaMemcpyHostToDevice, h->stream));
+        d_normals = h->d_normals;
+    }
+    rc = step_begin(h, (const double*)h->all_xy, h->in_dist, h->all_hit, B, d_center, d_theta, d_normals);
+    if (rc) return rc;
+    rc = step_end(h, GMS_RESAMPLE_NEVER, 0.0);
+    if (rc) return rc;
+    rc = fetch_stats(h);
+    if (rc) return rc;
+    if (neff_out) *neff_out = h->h_st->neff;
+    return GMS_OK;
+}
+
+EXPORT int gms_resample(gms_handle* h, double u01) {
+    ENTER(h);
+    if (u01 >= 1.0) return fail(h, GMS_ERR_INVALID_ARG, "gms_resample: u01 must be < 1");
+    LAUNCH(GMS_PHASE_RESAMPLE, k_set_resample_flag<<<1, 1, 0, h->stream>>>(h->st, 1));
+    int rc = launch_resample(h, u01);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return GMS_OK;
+}
+
+EXPORT int gms_calculate_neff(gms_handle* h, double* neff_out) {
+    ENTER(h);
+    if (!neff_out) return GMS_ERR_INVALID_ARG;
+    LAUNCH(GMS_PHASE_NORMALISE, k_neff<<<1, 1024, 0, h->stream>>>(h->w[h->cur], h->P, h->st));
+    h->stats_valid = false;
+    int rc = fetch_stats(h);
+    if (rc) return rc;
+    *neff_out = h->h_st->neff_query;
+    return GMS_OK;
+}
+
+EXPORT int gms_get_weighted_pose(gms_handle* h, float pose[3]) {
+    ENTER(h);
+    if (!pose) return GMS_ERR_INVALID_ARG;
+    LAUNCH(GMS_PHASE_NORMALISE, k_weighted_pose<<<1, 1024, 0, h->stream>>>(h->w[h->cur], h->pose[h->cur], h->P, h->st));
+    h->stats_valid = false;
+    int rc = fetch_stats(h);
+    if (rc) return rc;
+    std::memcpy(pose, h->h_st->weighted_pose, 3 * sizeof(float));
+    return GMS_OK;
+}
+
+EXPORT int gms_get_strongest(gms_handle* h, int32_t* index, float pose[3], double* weight) {
+    ENTER(h);
+    int rc = fetch_stats(h);
+    if (rc) return rc;
+    if (!h->have_update) {  // SLAM.reset: strongestParticle = particles.get(0) (SLAM.java:75)
+        if (index) *index = -1;
+        if (pose) pose[0] = pose[1] = pose[2] = 0.f;
+        if (weight) *weight = 1.0 / h->P;
+        return GMS_OK;
+    }
+    if (index) *index = h->h_st->strongest;
+    if (pose) std::memcpy(pose, h->h_st->strongest_pose, 3 * sizeof(float));
+    if (weight) *weight = h->h_st->strongest_w;
+    return GMS_OK;
+}
+
+EXPORT int gms_get_poses(gms_handle* h, float* xyt) {
+    ENTER(h);
+    if (!xyt) return GMS_ERR_INVALID_ARG;
+    LAUNCH(GMS_PHASE_COUNT - 1,
+           k_pose_unpack<<<blocks_for(h->P, 256), 256, 0, h->stream>>>(h->pose[h->cur], (float*)h->d_tmp, h->P));
+    CK(cudaMemcpyAsync(xyt, h->d_tmp, (size_t)h->P * 12, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GMS_OK;
+}
+
+static int copy_out(gms_handle* h, void* dst, const void* src, size_t bytes) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GMS_OK;
+}
+EXPORT int gms_get_weights(gms_handle* h, double* w) {
+    ENTER(h);
+    if (!w) return GMS_ERR_INVALID_ARG;
+    return copy_out(h, w, h->w[h->cur], (size_t)h->P * 8);
+}
+EXPORT int gms_get_log_weights(gms_handle* h, double* lw) {
+    ENTER(h);
+    if (!lw) return GMS_ERR_INVALID_ARG;
+    return copy_out(h, lw, h->lw[h->cur], (size_t)h->P * 8);
+}
+EXPORT int gms_get_parents(gms_handle* h, int32_t* parents) {
+    ENTER(h);
+    if (!parents) return GMS_ERR_INVALID_ARG;
+    return copy_out(h, parents, h->parents, (size_t)h->P * 4);
+}
+
+EXPORT int gms_get_map(gms_handle* h, int32_t particle, int32_t kind, void* dst, size_t bytes) {
+    ENTER(h);
+    if (!dst) return GMS_ERR_INVALID_ARG;
+    if (kind < GMS_MAP_LOG || kind > GMS_MAP_OCC_COUNT) return fail(h, GMS_ERR_INVALID_ARG, "gms_get_map: unknown kind");
+    const size_t esz = (kind == GMS_MAP_LOG || kind == GMS_MAP_LIKELIHOOD) ? 8 : 4;
+    if (bytes != h->cells * esz) return fail(h, GMS_ERR_INVALID_ARG, "gms_get_map: size mismatch");
+    int s;
+    int rc = slot_of(h, particle, &s);
+    if (rc) return rc;
+    const CellCounts* c = h->counts + (size_t)s * h->cells;
+    const unsigned nb = blocks_for((long long)h->cells, 256);
+    if (kind == GMS_MAP_LIKELIHOOD) return copy_out(h, dst, h->lik + (size_t)s * h->cells, bytes);
+    if (kind == GMS_MAP_LOG)
+        LAUNCH(GMS_PHASE_COUNT - 1,
+               k_counts_to_log<<<nb, 256, 0, h->stream>>>(c, (double*)h->d_tmp, h->cells, h->g.l_free, h->g.l_occ));
+    else
+        LAUNCH(GMS_PHASE_COUNT - 1, k_counts_split<<<nb, 256, 0, h->stream>>>(c, (uint32_t*)h->d_tmp, h->cells,
+                                                                             kind == GMS_MAP_OCC_COUNT));
+    return copy_out(h, dst, h->d_tmp, bytes);
+}
+
+EXPORT int gms_set_poses(gms_handle* h, const float* xyt) {
+    ENTER(h);
+    if (!xyt) return GMS_ERR_INVALID_ARG;
+    CK(cudaMemcpyAsync(h->d_tmp, xyt, (size_t)h->P * 12, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(GMS_PHASE_COUNT - 1,
+           k_pose_pack<<<blocks_for(h->P, 256), 256, 0, h->stream>>>((const float*)h->d_tmp, h->pose[h->cur], h->P));
+    CK(cudaStreamSynchronize(h->stream));
+    return GMS_OK;
+}
+EXPORT int gms_set_weights(gms_handle* h, const double* w) {
+    ENTER(h);
+    if (!w) return GMS_ERR_INVALID_ARG;
+    CK(cudaMemcpyAsync(h->w[h->cur], w, (size_t)h->P * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GMS_OK;
+}
+EXPORT int gms_set_map_counts(gms_handle* h, int32_t particle, const uint32_t* nf, const uint32_t* no) {
+    ENTER(h);
+    if (!nf || !no) return GMS_ERR_INVALID_ARG;
+    int s;
+    int rc = slot_of(h, particle, &s);
+    if (rc) return rc;
+    uint32_t* tmp = (uint32_t*)h->d_tmp;  // cells*8 bytes: two u32 planes
+    CK(cudaMemcpyAsync(tmp, nf, h->cells * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(tmp + h->cells, no, h->cells * 4, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(GMS_PHASE_COUNT - 1, k_counts_join<<<blocks_for((long long)h->cells, 256), 256, 0, h->stream>>>(
+                                    h->counts + (size_t)s * h->cells, tmp, tmp + h->cells, h->cells));
+    LAUNCH(GMS_PHASE_COUNT - 1, k_fill_rect<<<1, 1, 0, h->stream>>>(h->rect + s, 1, make_int4(0, 0, h->W - 1, h->H - 1)));
+    CK(cudaStreamSynchronize(h->stream));
+    return GMS_OK;
+}
+
+// ---- GridMap operators on one map ---------------------------------------------------------------
+EXPORT int gms_map_apply_measurement(gms_handle* h, int32_t particle, float sx, float sy, float ex, float ey,
+                                     float meas, int32_t was_hit) {
+    ENTER(h);
+    int s;
+    int rc = slot_of(h, particle, &s);
+    if (rc) return rc;
+    LAUNCH(GMS_PHASE_MAP_UPDATE, k_apply_one<<<1, 1, 0, h->stream>>>(h->counts + (size_t)s * h->cells, h->rect + s, sx,
+                                                                     sy, ex, ey, meas, was_hit, h->g));
+    CK(cudaStreamSynchronize(h->stream));
+    return GMS_OK;
+}
+
+static int stage_pose_slot(gms_handle* h, const float pose[3], int s) {
+    const float4 p = make_float4(pose[0], pose[1], pose[2], 0.f);
+    CK(cudaMemcpyAsync(h->tmp_pose, &p, sizeof p, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->tmp_slot, &s, sizeof s, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));  // the sources are stack variables
+    return GMS_OK;
+}
+
+EXPORT int gms_map_integrate_observation(gms_handle* h, int32_t particle, const float pose[3], const double* bxy,
+                                         const double* bdist, const uint8_t* bhit, int32_t B) {
+    ENTER(h);
+    if (!pose || B < 0 || (B > 0 && (!bxy || !bdist || !bhit))) return GMS_ERR_INVALID_ARG;
+    int s;
+    int rc = slot_of(h, particle, &s);
+    if (rc) return rc;
+    if ((rc = upload_beams(h, bxy, bdist, bhit, B))) return rc;
+    if ((rc = launch_pack(h, (const double*)h->all_xy, h->in_dist, h->all_hit, B))) return rc;
+    if ((rc = stage_pose_slot(h, pose, s))) return rc;
+    if ((rc = launch_map_update(h, h->tmp_pose, 0, 1, h->tmp_slot, B, 0))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return GMS_OK;
+}
+
+EXPORT int gms_map_compute_likelihood(gms_handle* h, int32_t particle) {
+    ENTER(h);
+    int s;
+    int rc = slot_of(h, particle, &s);
+    if (rc) return rc;
+    // the whole map of this slot (GridMap.computeLikelihoodMap has no notion of a dirty region);
+    // other slots keep whatever is pending for them: the work-list pass is per slot.
+    LAUNCH(GMS_PHASE_LIKELIHOOD, k_fill_rect<<<1, 1, 0, h->stream>>>(h->rect + s, 1, make_int4(0, 0, h->W - 1, h->H - 1)));
+    // run the work list on this slot only
+    {
+        Phase ph(h, GMS_PHASE_LIKELIHOOD);
+        LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_worklist<<<1, 1024, 0, h->stream>>>(h->rect + s, 1, h->W, h->H, h->g.khalf,
+                                                                                h->tile_desc, h->tile_off, h->st));
+        const int k = h->g.khalf, th = kTileH + 2 * k, tw = kTileW + 2 * k;
+        const size_t smem = (size_t)th * kTileW * 8 + (size_t)th * tw * 4;
+        LAUNCH(GMS_PHASE_LIKELIHOOD,
+               k_likelihood<<<148 * 6, 256, smem, h->stream>>>(h->counts + (size_t)s * h->cells,
+                                                               h->lik + (size_t)s * h->cells, h->tile_desc,
+                                                               h->tile_off, 1, h->st, h->g));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return GMS_OK;
+}
+
+EXPORT int gms_map_probability_of(gms_handle* h, int32_t particle, const float pose[3], const double* bxy,
+                                  const uint8_t* bhit, int32_t B, double* log_prob, double* prob) {
+    ENTER(h);
+    if (!pose || B < 0 || (B > 0 && (!bxy || !bhit))) return GMS_ERR_INVALID_ARG;
+    int s;
+    int rc = slot_of(h, particle, &s);
+    if (rc) return rc;
+    if ((rc = upload_beams(h, bxy, nullptr, bhit, B))) return rc;
+    if ((rc = launch_pack(h, (const double*)h->all_xy, h->in_dist, h->all_hit, B))) return rc;
+    if ((rc = stage_pose_slot(h, pose, s))) return rc;
+    if ((rc = launch_score(h, h->tmp_pose, 0, 1, h->tmp_slot, h->tmp_lw, nullptr, B))) return rc;
+    double lw = 0;
+    if ((rc = copy_out(h, &lw, h->tmp_lw, 8))) return rc;
+    if (log_prob) *log_prob = lw;
+    if (prob) *prob = std::exp(lw);
+    return GMS_OK;
+}
+
+EXPORT int gms_trace_rays(gms_handle* h, const float* rays, int32_t n, int32_t extra, int32_t* cells_xy, int32_t cap,
+                          int32_t* counts) {
+    ENTER(h);
+    if (!rays || !counts || n < 0 || cap < 0 || extra < 0 || (cap > 0 && !cells_xy)) return GMS_ERR_INVALID_ARG;
+    if (n == 0) return GMS_OK;
+    float4* d_rays = nullptr;
+    int2* d_cells = nullptr;
+    int* d_counts = nullptr;
+    auto cleanup = [&]() { cudaFree(d_rays); cudaFree(d_cells); cudaFree(d_counts); };
+    const size_t cb = (size_t)n * std::max(cap, 1) * sizeof(int2);
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&d_rays, (size_t)n * 16)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&d_cells, cb)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&d_counts, (size_t)n * 4)) != cudaSuccess) {
+        cleanup();
+        return cuda_fail(h, e, "gms_trace_rays: cudaMalloc");
+    }
+    int rc = GMS_OK;
+    do {
+        if ((e = cudaMemcpyAsync(d_rays, rays, (size_t)n * 16, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) break;
+        if ((e = cudaMemsetAsync(d_cells, 0xff, cb, h->stream)) != cudaSuccess) break;
+        k_trace_rays<<<blocks_for(n, 128), 128, 0, h->stream>>>(d_rays, n, extra, h->W, h->H, d_cells, cap, d_counts);
+        count_launch(h, GMS_PHASE_MAP_UPDATE);
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if (cap > 0 &&
+            (e = cudaMemcpyAsync(cells_xy, d_cells, (size_t)n * cap * 8, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess)
+            break;
+        if ((e = cudaMemcpyAsync(counts, d_counts, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream)) != cudaSuccess) break;
+        e = cudaStreamSynchronize(h->stream);
+    } while (0);
+    if (e != cudaSuccess) rc = cuda_fail(h, e, "gms_trace_rays");
+    cleanup();
+    return rc;
+}
+
+// Odometry(int,int) Odometry.java:41-55; MathUtil.PI is float pi (MathUtil.java:21); Robot.java:8-14
+EXPORT int gms_odometry_from_counts(int32_t left, int32_t right, double* d_center, double* d_theta) {
+    if (!d_center || !d_theta) return GMS_ERR_INVALID_ARG;
+    const double pif = (double)(float)M_PI;
+    const double dl = (double)left / 960 * pif * 0.063;
+    const double dr = (double)right / 960 * pif * 0.063;
+    *d_center = (dl + dr) / 2;
+    *d_theta = (dr - dl) / 0.22;
+    return GMS_OK;
+}
+
+// ---- device-resident / multi-rank -----------------------------------------------------------------
+EXPORT int gms_update_begin_dev(gms_handle* h, const double* d_xy, const double* d_dist, const uint8_t* d_hit,
+                                int32_t B, double d_center, double d_theta, const double* d_normals) {
+    ENTER(h);
+    if (B < 0 || (B > 0 && (!d_xy || !d_dist || !d_hit))) return fail(h, GMS_ERR_INVALID_ARG, "bad beam arrays");
+    if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE && h->cfg.nranks != 1)
+        return fail(h, GMS_ERR_UNSUPPORTED, "per-particle maps across ranks are not implemented yet");
+    return step_begin(h, d_xy, d_dist, d_hit, B, d_center, d_theta, d_normals);
+}
+EXPORT int gms_update_end_dev(gms_handle* h, int32_t policy, double u01) {
+    ENTER(h);
+    if (policy < 0 || policy > 2 || u01 >= 1.0) return fail(h, GMS_ERR_INVALID_ARG, "bad resample policy / u01");
+    return step_end(h, policy, u01);
+}
+EXPORT int gms_step_dev(gms_handle* h, const double* d_xy, const double* d_dist, const uint8_t* d_hit, int32_t B,
+                        double d_center, double d_theta, const double* d_normals, int32_t policy, double u01) {
+    ENTER(h);
+    if (h->cfg.nranks != 1) return fail(h, GMS_ERR_STATE, "gms_step_dev: multi-rank handles use update_begin/end");
+    if (B < 0 || (B > 0 && (!d_xy || !d_dist || !d_hit))) return fail(h, GMS_ERR_INVALID_ARG, "bad beam arrays");
+    if (policy < 0 || policy > 2 || u01 >= 1.0) return fail(h, GMS_ERR_INVALID_ARG, "bad resample policy / u01");
+    int rc = step_begin(h, d_xy, d_dist, d_hit, B, d_center, d_theta, d_normals);
+    if (rc) return rc;
+    return step_end(h, policy, u01);
+}
+EXPORT int gms_exchange_buffers(gms_handle* h, void** dl, size_t* lb, void** dg, size_t* gb) {
+    if (!h) return GMS_ERR_INVALID_ARG;
+    if (dl) *dl = h->xlocal;
+    if (lb) *lb = (size_t)h->cnt * sizeof(ExchangeRec);
+    if (dg) *dg = h->xglobal;
+    if (gb) *gb = (size_t)h->P * sizeof(ExchangeRec);
+    return GMS_OK;
+}
+EXPORT int gms_read_neff(gms_handle* h, double* neff) {
+    ENTER(h);
+    if (!neff) return GMS_ERR_INVALID_ARG;
+    int rc = fetch_stats(h);
+    if (rc) return rc;
+    *neff = h->h_st->neff;
+    return GMS_OK;
+}
+EXPORT int gms_sync(gms_handle* h) {
+    ENTER(h);
+    CK(cudaStreamSynchronize(h->stream));
+    return GMS_OK;
+}
+EXPORT int gms_set_stream(gms_handle* h, void* s) {
+    ENTER(h);
+    CK(cudaStreamSynchronize(h->stream));
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return GMS_OK;
+}
+EXPORT int gms_profile_enable(gms_handle* h, int32_t on) {
+    ENTER(h);
+    int rc = flush_profile(h);
+    h->profile = on != 0;
+    return rc;
+}
+EXPORT int gms_profile_read(gms_handle* h, double* ms, int64_t* launches) {
+    ENTER(h);
+    int rc = flush_profile(h);
+    if (rc) return rc;
+    for (int i = 0; i < GMS_PHASE_COUNT; i++) {
+        if (ms) ms[i] = h->phase_ms[i];
+        if (launches) launches[i] = h->phase_launches[i];
+    }
+    return GMS_OK;
+}
+EXPORT int gms_profile_reset(gms_handle* h) {
+    ENTER(h);
+    int rc = flush_profile(h);
+    for (int i = 0; i < GMS_PHASE_COUNT; i++) { h->phase_ms[i] = 0; h->phase_launches[i] = 0; }
+    return rc;
+}
+EXPORT int gms_launch_count(gms_handle* h, int64_t* n) {
+    if (!h || !n) return GMS_ERR_INVALID_ARG;
+    *n = h->launches;
+    return GMS_OK;
+}

@@ -255,3 +255,46 @@ def check_errors(lib):
     assert abs(neff - 2.0) < 1e-12
     assert np.array_equal(h.weights(), [0.5, 0.5])
     h.close()
+
+
+# ---------------------------------------------------------------- CUDA vs oracle replay ----------
+def replay_compare(cuda, oracle, P, beams, steps, grid_m, mode, max_range=10.0, resample_every=2,
+                   resample_mode=B.RESAMPLE_LITERAL, map_particles=(0,), via_dev=None, seed=7):
+    """Same seeded synthetic-room scans and injected draws through both libraries, compared after
+    every step.  Bit-exact: poses, per-cell counts, likelihood field, parents, strongest index.
+    Toleranced: log-weights 1e-9 abs, weights/Neff 1e-9 rel, weighted pose 2e-6 abs."""
+    from gridmap_slam_robot_b200 import synth
+
+    scans = synth.make_scans(steps, beams, max_range=max_range)
+    normals, uniforms = synth.make_draws(steps, P, seed=seed)
+    kw = dict(num_particles=P, map_width_m=grid_m, map_height_m=grid_m, origin_x=-grid_m / 2, origin_y=-grid_m / 2,
+              map_mode=mode, resample_mode=resample_mode)
+    g, o = cuda.create(**kw), oracle.create(**kw)
+    try:
+        for s, sc in enumerate(scans):
+            args = (sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta, normals[s])
+            ng = via_dev(g, *args) if via_dev else g.update(*args)
+            no = o.update(*args)
+            assert np.array_equal(g.poses(), o.poses()), f"step {s}: poses"
+            np.testing.assert_allclose(g.log_weights(), o.log_weights(), rtol=0, atol=LW_TOL, err_msg=f"step {s}")
+            np.testing.assert_allclose(g.weights(), o.weights(), rtol=W_RTOL, atol=1e-300, err_msg=f"step {s}")
+            assert abs(ng / no - 1) < 1e-9, f"step {s}: neff {ng} vs {no}"
+            gi, gp, gw = g.strongest()
+            oi, op, ow = o.strongest()
+            assert gi == oi and np.array_equal(gp, op) and abs(gw / ow - 1) < 1e-9, f"step {s}: strongest"
+            np.testing.assert_allclose(g.weighted_pose(), o.weighted_pose(), rtol=0, atol=2e-6)
+            if resample_every and s % resample_every == resample_every - 1:
+                g.resample(float(uniforms[s]))
+                o.resample(float(uniforms[s]))
+                assert np.array_equal(g.parents(), o.parents()), f"step {s}: parents"
+                assert np.array_equal(g.poses(), o.poses()), f"step {s}: poses after resample"
+                assert np.array_equal(g.weights(), o.weights()[...]) or np.allclose(
+                    g.weights(), o.weights(), rtol=W_RTOL, atol=1e-300)
+            for p in map_particles:
+                for kind in (B.MAP_FREE_COUNT, B.MAP_OCC_COUNT, B.MAP_LIKELIHOOD):
+                    a, b = g.get_map(p, kind), o.get_map(p, kind)
+                    assert np.array_equal(a, b), f"step {s}: map kind {kind} of particle {p}: {np.sum(a != b)} cells"
+        return g.launch_count()
+    finally:
+        g.close()
+        o.close()

@@ -1,0 +1,195 @@
+"""GPU (-m gpu): the CUDA hot path, called through the C-ABI, against
+  (1) the hand-derived Appendix B vectors, (2) the committed pyref golden fixtures,
+  (3) the C oracle on seeded synthetic-room replays, (4) size-independent properties at full size.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import checks
+from gridmap_slam_robot_b200 import binding as B
+
+pytestmark = pytest.mark.gpu
+
+
+def test_no_cpu_fallback_symbols(cuda):
+    h = cuda.create(num_particles=4, map_mode=B.MAP_SHARED)
+    assert h.info.is_cuda == 1
+    h.close()
+
+
+def test_constants(cuda):
+    checks.check_constants(cuda)
+
+
+def test_appendix_b_rays(cuda):
+    checks.check_appendix_b_rays(cuda)
+
+
+def test_appendix_b_resample(cuda):
+    checks.check_appendix_b_resample(cuda)
+
+
+def test_blank_likelihood(cuda):
+    checks.check_blank_likelihood(cuda)
+
+
+def test_golden_rays(cuda):
+    checks.check_rays(cuda)
+
+
+def test_golden_apply(cuda):
+    checks.check_apply(cuda)
+
+
+def test_golden_blur(cuda):
+    checks.check_blur(cuda)
+
+
+def test_golden_resample(cuda):
+    checks.check_resample(cuda)
+
+
+def test_golden_motion(cuda):
+    checks.check_motion(cuda)
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_golden_slam(cuda, shared):
+    checks.check_slam(cuda, shared)
+
+
+def test_errors(cuda):
+    checks.check_errors(cuda)
+
+
+def _via_dev(policy=B.POLICY_NEVER):
+    """Route an update through the device-resident entry point with torch-owned device buffers."""
+    import torch
+
+    def run(h, xy, dist, hit, dc, dth, normals):
+        dev = torch.device("cuda:0")
+        t_xy = torch.from_numpy(np.ascontiguousarray(xy, np.float64)).to(dev)
+        t_d = torch.from_numpy(np.ascontiguousarray(dist, np.float64)).to(dev)
+        t_h = torch.from_numpy(np.ascontiguousarray(hit, np.uint8)).to(dev)
+        t_n = torch.from_numpy(np.ascontiguousarray(normals, np.float64)).to(dev)
+        torch.cuda.synchronize()
+        Bn = int(t_d.numel())
+        h.step_dev(t_xy.data_ptr() if Bn else 0, t_d.data_ptr() if Bn else 0, t_h.data_ptr() if Bn else 0, Bn, dc,
+                   dth, t_n.data_ptr(), policy)
+        return h.read_neff()
+
+    return run
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_golden_slam_device_entry(cuda, shared):
+    checks.check_slam(cuda, shared, via_dev=_via_dev())
+
+
+# ---- CUDA vs oracle on the synthetic room ----
+def test_replay_k1_per_particle(cuda, oracle):
+    """K1 geometry (20 m room, 400^2 cells, 360 beams, 10 m range => misses exercised), fewer particles."""
+    n = checks.replay_compare(cuda, oracle, P=24, beams=360, steps=8, grid_m=20.0, mode=B.MAP_PER_PARTICLE,
+                              map_particles=(0, 11, 23))
+    assert n > 0
+
+
+def test_replay_k1_shared(cuda, oracle):
+    checks.replay_compare(cuda, oracle, P=100, beams=360, steps=10, grid_m=20.0, mode=B.MAP_SHARED)
+
+
+def test_replay_small_map_out_of_bounds(cuda, oracle):
+    """12 m map around an 18 m room: rays leave the grid, end points fall outside (skipped in scoring)."""
+    checks.replay_compare(cuda, oracle, P=16, beams=180, steps=6, grid_m=12.0, mode=B.MAP_PER_PARTICLE,
+                          map_particles=(0, 15))
+
+
+def test_replay_fixed_point_resampling(cuda, oracle):
+    checks.replay_compare(cuda, oracle, P=300, beams=90, steps=6, grid_m=20.0, mode=B.MAP_SHARED,
+                          resample_mode=B.RESAMPLE_FIXED, resample_every=1)
+
+
+def test_replay_720_beams_1024_grid_shared(cuda, oracle):
+    """K2/K3-style: 720 beams underflow Java's product (0.1^720): log-domain weights stay finite."""
+    checks.replay_compare(cuda, oracle, P=64, beams=720, steps=4, grid_m=51.2, mode=B.MAP_SHARED, max_range=12.0)
+
+
+def test_replay_device_entry(cuda, oracle):
+    checks.replay_compare(cuda, oracle, P=32, beams=360, steps=5, grid_m=20.0, mode=B.MAP_PER_PARTICLE,
+                          via_dev=_via_dev(), map_particles=(0, 31))
+
+
+def test_determinism_and_profile(cuda):
+    """Same inputs twice => byte-identical state (integer atomics commute; fixed reduction trees)."""
+    from gridmap_slam_robot_b200 import synth
+
+    P, steps = 256, 4
+    scans = synth.make_scans(steps, 360)
+    normals, uniforms = synth.make_draws(steps, P)
+    outs = []
+    for _ in range(2):
+        h = cuda.create(num_particles=P, map_width_m=20.0, map_height_m=20.0, origin_x=-10.0, origin_y=-10.0)
+        h.profile_enable(True)
+        for s, sc in enumerate(scans):
+            h.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta, normals[s])
+            h.resample(float(uniforms[s]))
+        ms, launches = h.profile_read()
+        assert launches["score"] >= steps and launches["map_update"] >= steps and ms["likelihood"] > 0
+        outs.append((h.poses().tobytes(), h.weights().tobytes(), h.get_map(5, B.MAP_FREE_COUNT).tobytes(),
+                     h.get_map(5, B.MAP_LIKELIHOOD).tobytes(), h.parents().tobytes()))
+        h.close()
+    assert outs[0] == outs[1]
+
+
+def test_device_philox_matches_oracle(cuda, oracle):
+    """normals == NULL: both sides draw from Philox4x32-10 keyed by (seed, global index, step).  The
+    Box-Muller transcendental functions differ by ulps between libm and CUDA, so poses agree to 1e-6."""
+    from gridmap_slam_robot_b200 import synth
+
+    sc = synth.make_scans(1, 90)[0]
+    kw = dict(num_particles=512, map_mode=B.MAP_SHARED, seed=1234)
+    g, o = cuda.create(**kw), oracle.create(**kw)
+    for _ in range(3):
+        g.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, 0.05, 0.01)
+        o.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, 0.05, 0.01)
+    np.testing.assert_allclose(g.poses(), o.poses(), rtol=0, atol=1e-6)
+    p = g.poses()
+    assert 0.1 < p[:, 0].mean() < 0.2 and p[:, 2].std() > 0.05
+    g.resample(-1.0)
+    o.resample(-1.0)
+    assert np.array_equal(g.parents(), o.parents())
+    g.close()
+    o.close()
+
+
+# ---- size-independent properties at BASELINE sizes ----
+def test_full_size_k2_properties(cuda):
+    """K2: 1k particles x 360 beams, 1024^2 shared grid.  Properties: weights sum to 1, Neff in [1, P],
+    parents sorted and in range, counts only grow, every likelihood value in [0, 1], and the map
+    touched only inside the scan's reach."""
+    from gridmap_slam_robot_b200 import synth
+
+    P = 1000
+    h = cuda.create(num_particles=P, map_width_m=51.2, map_height_m=51.2, origin_x=-25.6, origin_y=-25.6,
+                    map_mode=B.MAP_SHARED)
+    assert (h.W, h.H) == (1024, 1024)
+    scans = synth.make_scans(6, 360)
+    prev = np.zeros((1024, 1024), np.uint64)
+    for s, sc in enumerate(scans):
+        neff = h.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta)
+        w = h.weights()
+        assert abs(w.sum() - 1) < 1e-9 and 1.0 <= neff <= P + 1e-6
+        h.resample(-1.0)
+        par = h.parents()
+        assert par.min() >= 0 and par.max() < P and np.all(np.diff(par) >= 0)
+        tot = h.get_map(0, B.MAP_FREE_COUNT).astype(np.uint64) + h.get_map(0, B.MAP_OCC_COUNT)
+        assert np.all(tot >= prev)
+        prev = tot
+    lik = h.get_map(0, B.MAP_LIKELIHOOD)
+    assert lik.min() >= 0.0 and lik.max() <= 1.0 + 1e-12
+    ys, xs = np.nonzero(prev)
+    # room is +-9 m, robot within 6.1 m of the origin, 10 m range (+2 cells): |coord| < 16.2 m
+    assert np.all(np.abs((xs + 0.5) * 0.05 - 25.6) < 16.2) and np.all(np.abs((ys + 0.5) * 0.05 - 25.6) < 16.2)
+    h.close()
