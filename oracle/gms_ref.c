@@ -161,8 +161,13 @@ static void generate_gaussian_kernel(double sigma, int size, double *values) {
  * Util.doGaussianBlurdSeparable Util.java:378-426 (out-of-range taps are skipped, no renormalisation)
  * ------------------------------------------------------------------------------------------- */
 static void blur_separable(const double *in, double *out, double *tmp, int width, int height,
-                           const double *kernel, int ktaps) {
+                           const double *kernel, int ktaps, int threads) {
     int k = (ktaps - 1) / 2;
+    /* rows are independent: the OpenMP split (reference arm only, threads > 1) is bit-identical */
+    (void)threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1 && !omp_in_parallel())
+#endif
     for (int y = 0; y < height; y++) {
         int yi = y * width;
         for (int x = 0; x < width; x++) {
@@ -175,6 +180,9 @@ static void blur_separable(const double *in, double *out, double *tmp, int width
         }
     }
     memcpy(tmp, out, sizeof(double) * (size_t)width * height);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(threads) if (threads > 1 && !omp_in_parallel())
+#endif
     for (int y = 0; y < height; y++) {
         for (int x = 0; x < width; x++) {
             double total = 0;
@@ -196,7 +204,7 @@ static void compute_likelihood(const gms_handle *h, const double *logd, double *
         else if (logd[i] < 0.0) prob[i] = 0;
         else prob[i] = 0.5;
     }
-    blur_separable(prob, lik, tmp, h->W, h->H, h->kernel, h->ktaps);
+    blur_separable(prob, lik, tmp, h->W, h->H, h->kernel, h->ktaps, h->threads);
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -850,7 +858,7 @@ EXPORT int gmsref_set_threads(gms_handle *h, int32_t n) {
 EXPORT int gmsref_blur(const double *in, double *out, int32_t w, int32_t hgt, const double *kernel, int32_t ktaps) {
     double *tmp = malloc(sizeof(double) * (size_t)w * hgt);
     if (!tmp) return GMS_ERR_OOM;
-    blur_separable(in, out, tmp, w, hgt, kernel, ktaps);
+    blur_separable(in, out, tmp, w, hgt, kernel, ktaps, 1);
     free(tmp);
     return GMS_OK;
 }
