@@ -214,7 +214,11 @@ def run_gpu(args, wl):
     P_total = wl["P"] * world if args.scaling == "weak" else wl["P"]
     assert P_total % world == 0
     h = make_handle(lib, wl, P_total, rank=rank, nranks=world, device=local_rank)
-    stream = torch.cuda.current_stream(dev)
+    # a non-default torch stream shared with the library, so torch.cuda.Event brackets the library's
+    # launches (the legacy default stream has handle 0, which gms_set_stream reads as "own stream")
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     h.set_stream(stream.cuda_stream)
     runner = None
     if world > 1:

@@ -20,6 +20,7 @@ struct Geometry {
     float res_f;              // GridMap.resolution
     float tol_half;           // hitTolerance / 2 (SensorModel.java:35-37)
     double res, posx, posy;   // (double) resolution / position: the promotions Java performs
+    double inv_res;           // 1.0 / res — only for the guarded fast path of cell_of()
     double z_hit;             // GridMap.java:259
     double uniform_term;      // 1.0 / SENSOR_MAX_RANGE                (GridMap.java:286)
     double random_term;       // zRandom * 1.0 / SENSOR_MAX_RANGE      (GridMap.java:288)
@@ -29,6 +30,19 @@ struct Geometry {
 
 // JLS 5.1.3 (int) of a double: NaN -> 0, saturating, truncation toward zero == cvt.rzi.s32.f64.
 __device__ __forceinline__ int java_d2i(double d) { return __double2int_rz(d); }
+
+// (int) ((world - position) / resolution) of GridMap.java:273-274 without the f64 division on the fast
+// path.  q = t * (1/res) is within 2 ulp of the correctly rounded quotient t / res, i.e. within
+// 1.4e-6 for every |q| < 2^31; when q is further than 1e-5 from both neighbouring integers no integer
+// lies between q and t / res, so both truncate to the same cell.  Otherwise (probability ~2e-5 per
+// lookup; also NaN / saturating inputs) the exact division decides.  Result is bit-identical to Java.
+__device__ __forceinline__ int cell_of(double t, double res, double inv_res) {
+    const double q = t * inv_res;
+    const int n = __double2int_rz(q);
+    const double fr = fabs(q - (double)n);  // exact (Sterbenz); in [0, 1) for in-range q
+    if (fr > 1e-5 && fr < 1.0 - 1e-5) return n;
+    return __double2int_rz(t / res);
+}
 
 // MathUtil.angleConstrain MathUtil.java:65-72.  The loops are replicated literally (they are NOT the
 // identity on in-range input: +2pi then -2pi rounds).  Deliberate divergence: |a| > 1e6 or

@@ -58,6 +58,11 @@ struct gms_handle {
     uint8_t *in_hit = nullptr, *all_hit = nullptr;
     float* meas = nullptr;
     double* d_normals = nullptr;
+    // shared-map two-pass update: recorded ray cells
+    uint32_t* ray_cells = nullptr;
+    int* ray_count = nullptr;
+    float2* ray_start = nullptr;
+    int ray_cap = 0;
     // exchange, scratch, stats
     ExchangeRec *xlocal = nullptr, *xglobal = nullptr;
     void* d_tmp = nullptr;  // max(cells*8, P*24) bytes
@@ -182,6 +187,7 @@ void free_all(gms_handle* h) {
     cudaFree(h->tile_desc); cudaFree(h->tile_off); cudaFree(h->dup_src); cudaFree(h->dup_dst); cudaFree(h->scratch2p);
     cudaFree(h->in_xy); cudaFree(h->all_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
     cudaFree(h->all_hit); cudaFree(h->meas); cudaFree(h->d_normals); cudaFree(h->xlocal); cudaFree(h->xglobal);
+    cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start);
     cudaFree(h->d_tmp); cudaFree(h->tmp_pose); cudaFree(h->tmp_slot); cudaFree(h->tmp_lw); cudaFree(h->st);
     if (h->h_st) cudaFreeHost(h->h_st);
     if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -208,8 +214,9 @@ int ensure_beams(gms_handle* h, int B) {
     if ((size_t)B * 16 > 200 * 1024) return fail(h, GMS_ERR_INVALID_ARG, "too many beams (max 12800)");
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(h->in_xy); cudaFree(h->all_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
-    cudaFree(h->all_hit); cudaFree(h->meas);
+    cudaFree(h->all_hit); cudaFree(h->meas); cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start);
     h->in_xy = h->all_xy = h->hit_xy = nullptr; h->in_dist = nullptr; h->in_hit = h->all_hit = nullptr; h->meas = nullptr;
+    h->ray_cells = nullptr; h->ray_count = nullptr; h->ray_start = nullptr;
     h->bcap = 0;
     const int cap = ((B + 255) / 256) * 256;
     CK(cudaMalloc((void**)&h->in_xy, (size_t)cap * 16));
@@ -219,6 +226,13 @@ int ensure_beams(gms_handle* h, int B) {
     CK(cudaMalloc((void**)&h->in_hit, (size_t)cap));
     CK(cudaMalloc((void**)&h->all_hit, (size_t)cap));
     CK(cudaMalloc((void**)&h->meas, (size_t)cap * 4));
+    if (h->cfg.map_mode == GMS_MAP_SHARED) {
+        // a ray visits at most W + H - 1 in-bounds cells (4-connected, monotone) + the extra steps
+        h->ray_cap = h->W + h->H + h->cfg.extra_steps + 4;
+        CK(cudaMalloc((void**)&h->ray_cells, (size_t)cap * h->ray_cap * 4));
+        CK(cudaMalloc((void**)&h->ray_count, (size_t)cap * 4));
+        CK(cudaMalloc((void**)&h->ray_start, sizeof(float2)));
+    }
     h->bcap = cap;
     return GMS_OK;
 }
@@ -273,6 +287,16 @@ int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* 
 int launch_map_update(gms_handle* h, const float4* pose, int lo, int cnt, const int* slot, int B, int shared) {
     if (B <= 0) return GMS_OK;
     Phase ph(h, GMS_PHASE_MAP_UPDATE);
+    if (shared) {
+        LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_walk<<<blocks_for(B, 64), 64, 0, h->stream>>>(
+                                         pose, h->all_xy, B, h->st, h->ray_cells, h->ray_cap, h->ray_count,
+                                         h->ray_start, h->rect, h->g));
+        const dim3 grid(blocks_for(h->ray_cap, 256), (unsigned)B);
+        LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_apply<<<grid, 256, 0, h->stream>>>(h->ray_cells, h->ray_cap, h->ray_count,
+                                                                               h->ray_start, h->meas, h->all_hit,
+                                                                               h->counts, h->g));
+        return GMS_OK;
+    }
     const long long total = shared ? (long long)B : (long long)cnt * B;
     LAUNCH(GMS_PHASE_MAP_UPDATE,
            k_map_update<<<blocks_for(total, 128), 128, 0, h->stream>>>(pose, lo, cnt, h->all_xy, h->meas, h->all_hit,
@@ -318,7 +342,7 @@ int launch_resample(gms_handle* h, double u01) {
     {
         Phase ph(h, GMS_PHASE_RESAMPLE);
         if (h->resample_mode == GMS_RESAMPLE_FIXED) {
-            LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_fixed<<<1, 1024, 0, h->stream>>>(h->w[h->cur], P,
+            LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_fixed<<<kClusterCtas, 1024, 0, h->stream>>>(h->w[h->cur], P,
                                                                               (unsigned long long*)h->cdf, h->st));
             LAUNCH(GMS_PHASE_RESAMPLE, k_select<true><<<blocks_for(P, 256), 256, 0, h->stream>>>(
                                            h->cdf, P, u01, h->cfg.seed, h->resample_count, h->parents, h->st));
@@ -362,7 +386,7 @@ int step_end(gms_handle* h, int policy, double u01) {
                                         h->xglobal, h->P, h->lw[h->cur], h->pose[h->cur]));
     {
         Phase ph(h, GMS_PHASE_NORMALISE);
-        LAUNCH(GMS_PHASE_NORMALISE, k_normalise<<<1, 1024, 0, h->stream>>>(h->lw[h->cur], h->w[h->cur], h->pose[h->cur],
+        LAUNCH(GMS_PHASE_NORMALISE, k_normalise<<<kClusterCtas, 1024, 0, h->stream>>>(h->lw[h->cur], h->w[h->cur], h->pose[h->cur],
                                                                             h->P, policy, h->st));
     }
     const bool skip = std::fabs(h->pend_dtheta) > (M_PI / 180.0) * c.skip_update_deg;
@@ -502,6 +526,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     g.res_f = cfg->resolution;
     g.tol_half = cfg->hit_tolerance / 2;
     g.res = (double)cfg->resolution; g.posx = (double)cfg->origin_x; g.posy = (double)cfg->origin_y;
+    g.inv_res = 1.0 / g.res;
     g.z_hit = cfg->z_hit;
     g.uniform_term = 1.0 / (double)cfg->sensor_max_range;                          // GridMap.java:286
     g.random_term = (1 - cfg->z_hit) * 1.0 / (double)cfg->sensor_max_range;        // GridMap.java:288
@@ -514,7 +539,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     h->S = cfg->map_mode == GMS_MAP_SHARED ? 1 : h->cnt;
     h->cells = (size_t)h->W * h->H;
     h->resample_mode = cfg->resample_mode == GMS_RESAMPLE_AUTO
-                           ? (h->P <= 16384 ? GMS_RESAMPLE_LITERAL : GMS_RESAMPLE_FIXED)
+                           ? (h->P <= 2048 ? GMS_RESAMPLE_LITERAL : GMS_RESAMPLE_FIXED)
                            : cfg->resample_mode;
     auto bail = [&](int rc) {
         std::string m = h->err;
@@ -635,7 +660,7 @@ EXPORT int gms_resample(gms_handle* h, double u01) {
 EXPORT int gms_calculate_neff(gms_handle* h, double* neff_out) {
     ENTER(h);
     if (!neff_out) return GMS_ERR_INVALID_ARG;
-    LAUNCH(GMS_PHASE_NORMALISE, k_neff<<<1, 1024, 0, h->stream>>>(h->w[h->cur], h->P, h->st));
+    LAUNCH(GMS_PHASE_NORMALISE, k_neff<<<kClusterCtas, 1024, 0, h->stream>>>(h->w[h->cur], h->P, h->st));
     h->stats_valid = false;
     int rc = fetch_stats(h);
     if (rc) return rc;
@@ -646,7 +671,7 @@ EXPORT int gms_calculate_neff(gms_handle* h, double* neff_out) {
 EXPORT int gms_get_weighted_pose(gms_handle* h, float pose[3]) {
     ENTER(h);
     if (!pose) return GMS_ERR_INVALID_ARG;
-    LAUNCH(GMS_PHASE_NORMALISE, k_weighted_pose<<<1, 1024, 0, h->stream>>>(h->w[h->cur], h->pose[h->cur], h->P, h->st));
+    LAUNCH(GMS_PHASE_NORMALISE, k_weighted_pose<<<kClusterCtas, 1024, 0, h->stream>>>(h->w[h->cur], h->pose[h->cur], h->P, h->st));
     h->stats_valid = false;
     int rc = fetch_stats(h);
     if (rc) return rc;

@@ -6,9 +6,13 @@
 //   lik    f64[S][H][W]              likelihood field (GridMapData.likelihoodData)
 //   rect   int4[S]                   cells modified since the slot's last likelihood rebuild
 #pragma once
+#include <cooperative_groups.h>
+
 #include "device_math.cuh"
 
 namespace gms {
+
+namespace cg = cooperative_groups;
 
 struct Stats {
     double neff;          // SLAM.calculateNeff of the last update
@@ -267,8 +271,8 @@ __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, 
                 f[u] = 1.0;
                 if (b < nh) {
                     const double2 m = s_xy[b];
-                    const int gx = java_d2i((t.tx(m.x, m.y) - g.posx) / g.res);  // (int): toward zero
-                    const int gy = java_d2i((t.ty(m.x, m.y) - g.posy) / g.res);
+                    const int gx = cell_of(t.tx(m.x, m.y) - g.posx, g.res, g.inv_res);  // (int): toward zero
+                    const int gy = cell_of(t.ty(m.x, m.y) - g.posy, g.res, g.inv_res);
                     if (!(gx < 0 || gy < 0 || gx >= g.W || gy >= g.H)) {
                         const double val = __ldg(field + ((size_t)gx + (size_t)gy * g.W));
                         f[u] = val == 0.5 ? g.uniform_term : g.z_hit * val + g.random_term;
@@ -325,6 +329,64 @@ __global__ void __launch_bounds__(128) k_map_update(const float4* __restrict__ p
     }
 }
 
+// Shared map (one scan per step, only B rays): the DDA of a ray is inherently sequential (f32 error
+// term, RayIterator.java:112-130), but the per-cell work (sqrt, inverse sensor model, counter update)
+// is not.  Pass 1 walks each ray once and records its cells {x | y << 16}; pass 2 classifies and
+// accumulates all cells of all rays in parallel.
+__global__ void __launch_bounds__(64) k_ray_walk(const float4* __restrict__ pose,
+                                                 const double2* __restrict__ all_xy, int B,
+                                                 const Stats* __restrict__ st, uint32_t* __restrict__ ray_cells,
+                                                 int cap, int* __restrict__ ray_count,
+                                                 float2* __restrict__ ray_start, int4* __restrict__ rect,
+                                                 Geometry g) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float4 p = pose[st->strongest];
+    const Xform t(p.x, p.y, p.z);
+    const float sx = (float)((t.tx(0.0, 0.0) - g.posx) / g.res);
+    const float sy = (float)((t.ty(0.0, 0.0) - g.posy) / g.res);
+    const double2 m = all_xy[b];
+    const float ex = (float)((t.tx(m.x, m.y) - g.posx) / g.res);
+    const float ey = (float)((t.ty(m.x, m.y) - g.posy) / g.res);
+    if (b == 0) *ray_start = make_float2(sx, sy);
+    RayIter it;
+    it.init(sx + 0.5f, sy + 0.5f, ex + 0.5f, ey + 0.5f, g.extra_steps);
+    uint32_t* out = ray_cells + (size_t)b * cap;
+    int c = 0;
+    int fx = it.x, fy = it.y, lx = it.x, ly = it.y;
+    while (it.has_next(g.W, g.H) && c < cap) {
+        lx = it.x; ly = it.y;
+        out[c++] = (uint32_t)lx | ((uint32_t)ly << 16);
+        it.advance();
+    }
+    ray_count[b] = c;
+    if (c > 0) {
+        int* r = reinterpret_cast<int*>(rect);
+        atomicMin(r + 0, min(fx, lx));
+        atomicMin(r + 1, min(fy, ly));
+        atomicMax(r + 2, max(fx, lx));
+        atomicMax(r + 3, max(fy, ly));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ray_apply(const uint32_t* __restrict__ ray_cells, int cap,
+                                                   const int* __restrict__ ray_count,
+                                                   const float2* __restrict__ ray_start,
+                                                   const float* __restrict__ meas, const uint8_t* __restrict__ hit,
+                                                   CellCounts* __restrict__ counts, Geometry g) {
+    const int b = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ray_count[b]) return;
+    const uint32_t cell = ray_cells[(size_t)b * cap + k];
+    const int cx = (int)(cell & 0xffffu), cy = (int)(cell >> 16);
+    const float2 s = *ray_start;
+    const float dX = s.x - ((float)cx + 0.5f);
+    const float dY = s.y - ((float)cy + 0.5f);
+    const float dist = __fsqrt_rn(dX * dX + dY * dY);
+    const int cls = inverse_sensor_class(dist, meas[b], hit[b] != 0, g.tol_half);
+    if (cls != 0) atomicAdd(reinterpret_cast<uint32_t*>(counts + ((size_t)cx + (size_t)cy * g.W)) + (cls - 1), 1u);
+}
+
 // single ray given in grid coordinates (gms_map_apply_measurement)
 __global__ void k_apply_one(CellCounts* __restrict__ counts, int4* __restrict__ rect, float sx, float sy,
                             float ex, float ey, float meas, int was_hit, Geometry g) {
@@ -354,9 +416,14 @@ __global__ void k_trace_rays(const float4* __restrict__ rays, int n, int extra, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// A6 — normalise (SLAM.java:119-121), Neff (:180-190), strongest (:110-115).  One CTA: P <= ~1e6
-// doubles is latency-, not bandwidth-bound.  Fixed reduction tree => identical on every rank.
+// A6 — normalise (SLAM.java:119-121), Neff (:180-190), strongest (:110-115), weighted pose (:165-178).
+// P <= ~1e6 doubles: latency-bound reductions.  One thread-block CLUSTER of 8 CTAs x 1024 threads;
+// CTA partials are exchanged through distributed shared memory (DSMEM) and combined in rank order, so
+// every CTA — and every rank of a multi-GPU run — obtains bit-identical totals (fixed tree).
 // ------------------------------------------------------------------------------------------------
+constexpr int kClusterCtas = 8;
+constexpr int kClusterThreads = kClusterCtas * 1024;
+
 template <typename T, typename Op>
 __device__ __forceinline__ T block_reduce_1024(T v, Op op, T* s_buf) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -371,17 +438,36 @@ __device__ __forceinline__ T block_reduce_1024(T v, Op op, T* s_buf) {
     return v;
 }
 struct SumOp { __device__ double operator()(double a, double b) const { return a + b; } };
-__global__ void __launch_bounds__(1024) k_normalise(const double* __restrict__ lw, double* __restrict__ w,
-                                                    const float4* __restrict__ pose, int P, int policy,
-                                                    Stats* __restrict__ st) {
+struct SumU64 { __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a + b; } };
+
+// block partial -> cluster total (identical in every thread of every CTA of the cluster)
+__device__ __forceinline__ double cluster_sum(cg::cluster_group& cl, double v, double* s_buf, double* s_slot) {
+    const double b = block_reduce_1024(v, SumOp(), s_buf);
+    if (threadIdx.x == 0) *s_slot = b;
+    cl.sync();
+    double t = 0.0;
+#pragma unroll
+    for (int r = 0; r < kClusterCtas; r++) t += *cl.map_shared_rank(s_slot, r);
+    cl.sync();  // the slot may be rewritten by the next reduction
+    return t;
+}
+
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
+    k_normalise(const double* __restrict__ lw, double* __restrict__ w, const float4* __restrict__ pose, int P,
+                int policy, Stats* __restrict__ st) {
+    cg::cluster_group cl = cg::this_cluster();
     __shared__ double s_d[32];
     __shared__ double s_key[32];
     __shared__ int s_idx[32];
+    __shared__ double s_slot;
+    __shared__ double s_best;
+    __shared__ int s_besti;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    // pass 1: max and its first index
-    double best = -__longlong_as_double(0x7ff0000000000000LL) ;  // -inf
+    const int gt = cl.block_rank() * 1024 + tid;
+    // pass 1: max and its FIRST index (strict > keeps the first maximum, SLAM.java:110-115)
+    double best = __longlong_as_double(0xfff0000000000000LL);  // -inf
     int bi = 0x7fffffff;
-    for (int i = tid; i < P; i += 1024) {
+    for (int i = gt; i < P; i += kClusterThreads) {
         const double v = lw[i];
         if (v > best || (v == best && i < bi)) { best = v; bi = i; }
     }
@@ -400,36 +486,44 @@ __global__ void __launch_bounds__(1024) k_normalise(const double* __restrict__ l
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
+    if (tid == 0) { s_best = best; s_besti = bi; }
+    cl.sync();
+#pragma unroll
+    for (int r = 0; r < kClusterCtas; r++) {
+        const double ov = *cl.map_shared_rank(&s_best, r);
+        const int oi = *cl.map_shared_rank(&s_besti, r);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
     // pass 2: e_i = exp(lw_i - max), S = sum e_i
     double acc = 0.0;
-    for (int i = tid; i < P; i += 1024) {
+    for (int i = gt; i < P; i += kClusterThreads) {
         const double e = exp(lw[i] - best);
         w[i] = e;
         acc += e;
     }
-    const double S = block_reduce_1024(acc, SumOp(), s_d);
+    const double S = cluster_sum(cl, acc, s_d, &s_slot);
     // pass 3: w_i = e_i / S and their sum (SLAM.calculateNeff recomputes it, SLAM.java:181-183)
     acc = 0.0;
-    for (int i = tid; i < P; i += 1024) {
+    for (int i = gt; i < P; i += kClusterThreads) {
         const double v = w[i] / S;
         w[i] = v;
         acc += v;
     }
-    const double ws = block_reduce_1024(acc, SumOp(), s_d);
+    const double ws = cluster_sum(cl, acc, s_d, &s_slot);
     // pass 4: sum (w/ws)^2 (SLAM.java:185-187)
     acc = 0.0;
-    for (int i = tid; i < P; i += 1024) {
+    for (int i = gt; i < P; i += kClusterThreads) {
         const double v = w[i] / ws;
         acc += v * v;
     }
-    const double sq = block_reduce_1024(acc, SumOp(), s_d);
-    if (tid == 0) {
+    const double sq = cluster_sum(cl, acc, s_d, &s_slot);
+    if (gt == 0) {
         const double neff = 1.0 / sq;
         st->neff = neff;
         st->lw_max = best;
         st->sum_exp = S;
         st->strongest = bi;
-        st->strongest_w = w[bi];
+        st->strongest_w = exp(lw[bi] - best) / S;
         const float4 p = pose[bi];
         st->strongest_pose[0] = p.x; st->strongest_pose[1] = p.y; st->strongest_pose[2] = p.z;
         st->do_resample = policy == 2 || (policy == 1 && neff < (double)(P / 2));  // GridMapApp.java:185
@@ -437,27 +531,33 @@ __global__ void __launch_bounds__(1024) k_normalise(const double* __restrict__ l
 }
 
 // SLAM.calculateNeff on the current weights (after set_weights / resample)
-__global__ void __launch_bounds__(1024) k_neff(const double* __restrict__ w, int P, Stats* __restrict__ st) {
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
+    k_neff(const double* __restrict__ w, int P, Stats* __restrict__ st) {
+    cg::cluster_group cl = cg::this_cluster();
     __shared__ double s_d[32];
+    __shared__ double s_slot;
+    const int gt = cl.block_rank() * 1024 + threadIdx.x;
     double acc = 0.0;
-    for (int i = threadIdx.x; i < P; i += 1024) acc += w[i];
-    const double ws = block_reduce_1024(acc, SumOp(), s_d);
+    for (int i = gt; i < P; i += kClusterThreads) acc += w[i];
+    const double ws = cluster_sum(cl, acc, s_d, &s_slot);
     acc = 0.0;
-    for (int i = threadIdx.x; i < P; i += 1024) {
+    for (int i = gt; i < P; i += kClusterThreads) {
         const double v = w[i] / ws;
         acc += v * v;
     }
-    const double sq = block_reduce_1024(acc, SumOp(), s_d);
-    if (threadIdx.x == 0) st->neff_query = 1.0 / sq;
+    const double sq = cluster_sum(cl, acc, s_d, &s_slot);
+    if (gt == 0) st->neff_query = 1.0 / sq;
 }
 
 // SLAM.getWeightedPose SLAM.java:165-178 (plain, not circular, mean of angleConstrain(theta))
-__global__ void __launch_bounds__(1024) k_weighted_pose(const double* __restrict__ w,
-                                                        const float4* __restrict__ pose, int P,
-                                                        Stats* __restrict__ st) {
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
+    k_weighted_pose(const double* __restrict__ w, const float4* __restrict__ pose, int P, Stats* __restrict__ st) {
+    cg::cluster_group cl = cg::this_cluster();
     __shared__ double s_d[32];
+    __shared__ double s_slot;
+    const int gt = cl.block_rank() * 1024 + threadIdx.x;
     double xs = 0, ys = 0, ts = 0, ws = 0;
-    for (int i = threadIdx.x; i < P; i += 1024) {
+    for (int i = gt; i < P; i += kClusterThreads) {
         const float4 p = pose[i];
         const double wi = w[i];
         xs += (double)p.x * wi;
@@ -465,11 +565,11 @@ __global__ void __launch_bounds__(1024) k_weighted_pose(const double* __restrict
         ts += angle_constrain((double)p.z) * wi;
         ws += wi;
     }
-    xs = block_reduce_1024(xs, SumOp(), s_d);
-    ys = block_reduce_1024(ys, SumOp(), s_d);
-    ts = block_reduce_1024(ts, SumOp(), s_d);
-    ws = block_reduce_1024(ws, SumOp(), s_d);
-    if (threadIdx.x == 0) {
+    xs = cluster_sum(cl, xs, s_d, &s_slot);
+    ys = cluster_sum(cl, ys, s_d, &s_slot);
+    ts = cluster_sum(cl, ts, s_d, &s_slot);
+    ws = cluster_sum(cl, ws, s_d, &s_slot);
+    if (gt == 0) {
         st->weighted_pose[0] = (float)(xs / ws);
         st->weighted_pose[1] = (float)(ys / ws);
         st->weighted_pose[2] = (float)(ts / ws);
@@ -509,30 +609,50 @@ __global__ void __launch_bounds__(32) k_cdf_literal(const double* __restrict__ w
     }
 }
 
-// FIXED CDF: u64 fixed point trunc(w * 2^60); integer addition is associative, so the block-wide
-// scan equals the sequential walk bit for bit on any number of threads / ranks.
-__global__ void __launch_bounds__(1024) k_cdf_fixed(const double* __restrict__ w, int P,
-                                                    unsigned long long* __restrict__ cdf,
-                                                    const Stats* __restrict__ st) {
-    if (!st->do_resample) return;
-    __shared__ unsigned long long s_part[1024];
-    const int tid = threadIdx.x;
-    const int per = (P + 1023) / 1024;
-    const int i0 = tid * per, i1 = min(P, i0 + per);
-    unsigned long long sum = 0;
-    for (int i = i0; i < i1; i++) sum += (unsigned long long)(w[i] * 0x1p60);
-    s_part[tid] = sum;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        unsigned long long v = tid >= o ? s_part[tid - o] : 0ull;
+// FIXED CDF: u64 fixed point trunc(w * 2^60); integer addition is associative, so the cluster-wide
+// scan equals the sequential walk bit for bit on any number of threads / CTAs / ranks.  Each CTA of
+// the 8-CTA cluster owns a contiguous chunk: chunk totals travel through DSMEM, then a coalesced
+// tile-by-tile block scan (warp shuffles) writes the inclusive prefix.
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
+    k_cdf_fixed(const double* __restrict__ w, int P, unsigned long long* __restrict__ cdf,
+                const Stats* __restrict__ st) {
+    if (!st->do_resample) return;  // uniform over the cluster
+    cg::cluster_group cl = cg::this_cluster();
+    __shared__ unsigned long long s_u[32];
+    __shared__ unsigned long long s_total;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int rank = (int)cl.block_rank();
+    const int per = (((P + kClusterCtas - 1) / kClusterCtas + 1023) / 1024) * 1024;
+    const int i0 = min(P, rank * per), i1 = min(P, i0 + per);
+    unsigned long long acc = 0;
+    for (int i = i0 + tid; i < i1; i += 1024) acc += (unsigned long long)(w[i] * 0x1p60);
+    const unsigned long long tot = block_reduce_1024(acc, SumU64(), s_u);
+    if (tid == 0) s_total = tot;
+    cl.sync();
+    unsigned long long carry = 0;
+    for (int r = 0; r < rank; r++) carry += *cl.map_shared_rank(&s_total, r);
+    cl.sync();
+    for (int base = i0; base < i1; base += 1024) {
+        const int i = base + tid;
+        unsigned long long v = i < i1 ? (unsigned long long)(w[i] * 0x1p60) : 0ull;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
         __syncthreads();
-        s_part[tid] += v;
+        if (lane == 31) s_u[wid] = v;
         __syncthreads();
-    }
-    unsigned long long run = s_part[tid] - sum;
-    for (int i = i0; i < i1; i++) {
-        run += (unsigned long long)(w[i] * 0x1p60);
-        cdf[i] = run;
+        unsigned long long wsum = s_u[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, wsum, o);
+            if (lane >= o) wsum += u;
+        }
+        const unsigned long long warp_excl = __shfl_sync(0xffffffffu, wsum, max(wid, 1) - 1);
+        const unsigned long long tile_total = __shfl_sync(0xffffffffu, wsum, 31);
+        if (i < i1) cdf[i] = carry + (wid > 0 ? warp_excl : 0ull) + v;
+        carry += tile_total;
     }
 }
 

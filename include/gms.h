@@ -50,7 +50,7 @@ typedef enum gms_status {
 #define GMS_MAP_SHARED 1        /* extension: one map, updated from the strongest pose */
 
 /* resample_mode: how the CDF of SLAM.resample (SLAM.java:137-145) is accumulated */
-#define GMS_RESAMPLE_AUTO 0     /* LITERAL when P <= 16384, FIXED above                            */
+#define GMS_RESAMPLE_AUTO 0     /* LITERAL when P <= 2048, FIXED above                             */
 #define GMS_RESAMPLE_LITERAL 1  /* sequential f64 running sum in particle order: Java's own order  */
 #define GMS_RESAMPLE_FIXED 2    /* u64 fixed point (w * 2^60, truncated): associative, so a block-
                                    wide / multi-rank scan gives identical indices                  */

@@ -452,7 +452,7 @@ EXPORT int gms_create(const gms_config *cfg, gms_handle **out) {
     h->lo = cfg->rank * h->cnt;
     h->S = cfg->map_mode == GMS_MAP_SHARED ? 1 : h->cnt;
     h->resample_mode = cfg->resample_mode == GMS_RESAMPLE_AUTO
-                           ? (h->P <= 16384 ? GMS_RESAMPLE_LITERAL : GMS_RESAMPLE_FIXED)
+                           ? (h->P <= 2048 ? GMS_RESAMPLE_LITERAL : GMS_RESAMPLE_FIXED)
                            : cfg->resample_mode;
     h->threads = 1;
     size_t n = (size_t)h->W * h->H;
