@@ -58,6 +58,16 @@ struct gms_handle {
     uint8_t *in_hit = nullptr, *all_hit = nullptr;
     float* meas = nullptr;
     double* d_normals = nullptr;
+    // heading sort for k_score_sorted
+    unsigned *sort_hist = nullptr, *sort_offs = nullptr, *sort_key = nullptr, *sort_rank = nullptr;
+    int* order = nullptr;
+    // tile partials of normalise / neff / weighted pose
+    int ntiles = 0;
+    NormPartials np{};
+    double* wp_part = nullptr;
+    unsigned* wp_counter = nullptr;
+    bool tile_fx_valid = false;
+    int* ray_maxlen = nullptr;
     // shared-map two-pass update: recorded ray cells
     uint32_t* ray_cells = nullptr;
     int* ray_count = nullptr;
@@ -187,7 +197,10 @@ void free_all(gms_handle* h) {
     cudaFree(h->tile_desc); cudaFree(h->tile_off); cudaFree(h->dup_src); cudaFree(h->dup_dst); cudaFree(h->scratch2p);
     cudaFree(h->in_xy); cudaFree(h->all_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
     cudaFree(h->all_hit); cudaFree(h->meas); cudaFree(h->d_normals); cudaFree(h->xlocal); cudaFree(h->xglobal);
-    cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start);
+    cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start); cudaFree(h->ray_maxlen);
+    cudaFree(h->sort_hist); cudaFree(h->sort_offs); cudaFree(h->sort_key); cudaFree(h->sort_rank); cudaFree(h->order);
+    cudaFree(h->np.m); cudaFree(h->np.idx); cudaFree(h->np.s); cudaFree(h->np.ws); cudaFree(h->np.q); cudaFree(h->np.fx);
+    cudaFree(h->np.counter); cudaFree(h->wp_part); cudaFree(h->wp_counter);
     cudaFree(h->d_tmp); cudaFree(h->tmp_pose); cudaFree(h->tmp_slot); cudaFree(h->tmp_lw); cudaFree(h->st);
     if (h->h_st) cudaFreeHost(h->h_st);
     if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -274,9 +287,19 @@ int launch_likelihood(gms_handle* h) {
     return GMS_OK;
 }
 
+// Thread-per-particle scoring in heading order pays off when one shared field serves many particles
+// (see k_score_sorted); per-particle maps and small particle sets keep one warp per particle.
+bool use_sorted_score(const gms_handle* h) { return h->cfg.map_mode == GMS_MAP_SHARED && h->cnt >= 4096; }
+
 int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* slot, double* lw,
-                 ExchangeRec* xlocal, int B) {
+                 ExchangeRec* xlocal, int B, bool sorted = false) {
     Phase ph(h, GMS_PHASE_SCORE);
+    if (sorted) {
+        const size_t smem_s = std::max<size_t>(16, (size_t)B * 16);
+        LAUNCH(GMS_PHASE_SCORE, k_score_sorted<<<blocks_for(cnt, 128), 128, smem_s, h->stream>>>(
+                                    pose, lo, cnt, h->hit_xy, h->st, h->lik, h->order, lw, xlocal, h->g));
+        return GMS_OK;
+    }
     const unsigned grid = std::min<unsigned>(blocks_for(cnt, 8), 148 * 8);
     const size_t smem = std::max<size_t>(16, (size_t)B * 16);
     LAUNCH(GMS_PHASE_SCORE, k_score<<<grid, 256, smem, h->stream>>>(pose, lo, cnt, h->hit_xy, h->st, h->lik, slot,
@@ -288,13 +311,14 @@ int launch_map_update(gms_handle* h, const float4* pose, int lo, int cnt, const 
     if (B <= 0) return GMS_OK;
     Phase ph(h, GMS_PHASE_MAP_UPDATE);
     if (shared) {
-        LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_walk<<<blocks_for(B, 64), 64, 0, h->stream>>>(
-                                         pose, h->all_xy, B, h->st, h->ray_cells, h->ray_cap, h->ray_count,
-                                         h->ray_start, h->rect, h->g));
-        const dim3 grid(blocks_for(h->ray_cap, 256), (unsigned)B);
-        LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_apply<<<grid, 256, 0, h->stream>>>(h->ray_cells, h->ray_cap, h->ray_count,
-                                                                               h->ray_start, h->meas, h->all_hit,
-                                                                               h->counts, h->g));
+        const int Bpad = ((B + 31) / 32) * 32;
+        LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_walk<<<blocks_for(Bpad, 64), 64, 0, h->stream>>>(
+                                         pose, h->all_xy, B, Bpad, h->st, h->ray_cells, h->ray_cap, h->ray_count,
+                                         h->ray_start, h->ray_maxlen, h->rect, h->g));
+        LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_apply<<<148 * 4, 256, 0, h->stream>>>(
+                                         h->ray_cells, Bpad, h->ray_count, h->ray_maxlen, h->ray_start, h->meas,
+                                         h->all_hit, h->counts, h->g));
+        LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_reset<<<1, 1, 0, h->stream>>>(h->ray_maxlen));
         return GMS_OK;
     }
     const long long total = shared ? (long long)B : (long long)cnt * B;
@@ -316,15 +340,21 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
         // Odometry.recalculateStdDev Odometry.java:60-69
         const double sd_c = (c.noise_center_base + std::fabs(d_center) * c.noise_center_gain) / 2;
         const double sd_t = c.noise_theta_base_deg * (M_PI / 180.0) + c.noise_theta_gain * std::fabs(d_theta);
+        const bool sorted = use_sorted_score(h);
         LAUNCH(GMS_PHASE_MOTION, k_motion<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(
                                      h->pose[h->cur], h->lo, h->cnt, d_normals, c.seed, h->step, d_center, d_theta,
-                                     sd_c, sd_t));
+                                     sd_c, sd_t, sorted ? h->sort_hist : nullptr, h->sort_key, h->sort_rank));
+        if (sorted) {
+            LAUNCH(GMS_PHASE_MOTION, k_sort_scan<<<1, 1024, 0, h->stream>>>(h->sort_hist, h->sort_offs));
+            LAUNCH(GMS_PHASE_MOTION, k_sort_scatter<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(
+                                         h->sort_offs, h->sort_key, h->sort_rank, h->cnt, h->order));
+        }
     }
     rc = launch_likelihood(h);
     if (rc) return rc;
     const bool shared = c.map_mode == GMS_MAP_SHARED;
     rc = launch_score(h, h->pose[h->cur], h->lo, h->cnt, shared ? nullptr : h->slot[h->slot_cur], h->lw[h->cur],
-                      c.nranks > 1 ? h->xlocal : nullptr, B);
+                      c.nranks > 1 ? h->xlocal : nullptr, B, use_sorted_score(h));
     if (rc) return rc;
     const bool skip = std::fabs(d_theta) > (M_PI / 180.0) * c.skip_update_deg;  // SLAM.java:82
     if (!shared && !skip) {
@@ -342,8 +372,10 @@ int launch_resample(gms_handle* h, double u01) {
     {
         Phase ph(h, GMS_PHASE_RESAMPLE);
         if (h->resample_mode == GMS_RESAMPLE_FIXED) {
-            LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_fixed<<<kClusterCtas, 1024, 0, h->stream>>>(h->w[h->cur], P,
-                                                                              (unsigned long long*)h->cdf, h->st));
+            if (!h->tile_fx_valid)  // tile sums of trunc(w * 2^60): by-product of k_normalise / k_neff
+                LAUNCH(GMS_PHASE_RESAMPLE, k_neff<<<h->ntiles, 1024, 0, h->stream>>>(h->w[h->cur], P, h->ntiles, h->np, h->st));
+            LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_fixed<<<h->ntiles, 1024, 0, h->stream>>>(
+                                           h->w[h->cur], P, h->np.fx, (unsigned long long*)h->cdf, h->st));
             LAUNCH(GMS_PHASE_RESAMPLE, k_select<true><<<blocks_for(P, 256), 256, 0, h->stream>>>(
                                            h->cdf, P, u01, h->cfg.seed, h->resample_count, h->parents, h->st));
         } else {
@@ -356,6 +388,7 @@ int launch_resample(gms_handle* h, double u01) {
                                        h->parents, P, h->pose[h->cur], h->w[h->cur], h->lw[h->cur], h->pose[nxt],
                                        h->w[nxt], h->lw[nxt]));
         h->cur = nxt;
+        h->tile_fx_valid = false;
     }
     h->resample_count++;
     if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE) {
@@ -386,8 +419,11 @@ int step_end(gms_handle* h, int policy, double u01) {
                                         h->xglobal, h->P, h->lw[h->cur], h->pose[h->cur]));
     {
         Phase ph(h, GMS_PHASE_NORMALISE);
-        LAUNCH(GMS_PHASE_NORMALISE, k_normalise<<<kClusterCtas, 1024, 0, h->stream>>>(h->lw[h->cur], h->w[h->cur], h->pose[h->cur],
-                                                                            h->P, policy, h->st));
+        LAUNCH(GMS_PHASE_NORMALISE, k_softmax_partials<<<h->ntiles, 1024, 0, h->stream>>>(h->lw[h->cur], h->P, h->np));
+        LAUNCH(GMS_PHASE_NORMALISE, k_normalise<<<h->ntiles, 1024, 0, h->stream>>>(
+                                        h->lw[h->cur], h->w[h->cur], h->pose[h->cur], h->P, h->ntiles, policy, h->np,
+                                        h->st));
+        h->tile_fx_valid = true;
     }
     const bool skip = std::fabs(h->pend_dtheta) > (M_PI / 180.0) * c.skip_update_deg;
     if (c.map_mode == GMS_MAP_SHARED && !skip) {
@@ -445,7 +481,7 @@ int do_reset(gms_handle* h) {
     CK(cudaMemsetAsync(h->st, 0, sizeof(Stats), h->stream));
     h->cur = 0; h->slot_cur = 0;
     h->step = 0; h->resample_count = 0;
-    h->have_update = false; h->pending = false; h->stats_valid = false;
+    h->have_update = false; h->pending = false; h->stats_valid = false; h->tile_fx_valid = false;
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }
@@ -581,8 +617,32 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->tmp_slot, sizeof(int)));
     CKC(cudaMalloc((void**)&h->tmp_lw, sizeof(double)));
     CKC(cudaMalloc((void**)&h->st, sizeof(Stats)));
+    CKC(cudaMalloc((void**)&h->sort_hist, kSortBins * 4));
+    CKC(cudaMalloc((void**)&h->sort_offs, kSortBins * 4));
+    CKC(cudaMemset(h->sort_hist, 0, kSortBins * 4));
+    CKC(cudaMalloc((void**)&h->sort_key, (size_t)h->cnt * 4));
+    CKC(cudaMalloc((void**)&h->sort_rank, (size_t)h->cnt * 4));
+    CKC(cudaMalloc((void**)&h->order, (size_t)h->cnt * 4));
+    h->ntiles = (h->P + 1023) / 1024;
+    {
+        const size_t nt = (size_t)h->ntiles;
+        CKC(cudaMalloc((void**)&h->np.m, nt * 8));
+        CKC(cudaMalloc((void**)&h->np.idx, nt * 4));
+        CKC(cudaMalloc((void**)&h->np.s, nt * 8));
+        CKC(cudaMalloc((void**)&h->np.ws, nt * 8));
+        CKC(cudaMalloc((void**)&h->np.q, nt * 8));
+        CKC(cudaMalloc((void**)&h->np.fx, nt * 8));
+        CKC(cudaMalloc((void**)&h->np.counter, 4));
+        CKC(cudaMemset(h->np.counter, 0, 4));
+        CKC(cudaMalloc((void**)&h->wp_part, nt * 32));
+        CKC(cudaMalloc((void**)&h->wp_counter, 4));
+        CKC(cudaMemset(h->wp_counter, 0, 4));
+        CKC(cudaMalloc((void**)&h->ray_maxlen, 4));
+        CKC(cudaMemset(h->ray_maxlen, 0, 4));
+    }
     CKC(cudaMallocHost((void**)&h->h_st, sizeof(Stats)));
     CKC(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKC(cudaFuncSetAttribute(k_score_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CKC(cudaFuncSetAttribute(k_likelihood, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     int rc = ensure_beams(h, 1024);
     if (rc) return bail(rc);
@@ -660,7 +720,8 @@ EXPORT int gms_resample(gms_handle* h, double u01) {
 EXPORT int gms_calculate_neff(gms_handle* h, double* neff_out) {
     ENTER(h);
     if (!neff_out) return GMS_ERR_INVALID_ARG;
-    LAUNCH(GMS_PHASE_NORMALISE, k_neff<<<kClusterCtas, 1024, 0, h->stream>>>(h->w[h->cur], h->P, h->st));
+    LAUNCH(GMS_PHASE_NORMALISE, k_neff<<<h->ntiles, 1024, 0, h->stream>>>(h->w[h->cur], h->P, h->ntiles, h->np, h->st));
+    h->tile_fx_valid = true;
     h->stats_valid = false;
     int rc = fetch_stats(h);
     if (rc) return rc;
@@ -671,7 +732,8 @@ EXPORT int gms_calculate_neff(gms_handle* h, double* neff_out) {
 EXPORT int gms_get_weighted_pose(gms_handle* h, float pose[3]) {
     ENTER(h);
     if (!pose) return GMS_ERR_INVALID_ARG;
-    LAUNCH(GMS_PHASE_NORMALISE, k_weighted_pose<<<kClusterCtas, 1024, 0, h->stream>>>(h->w[h->cur], h->pose[h->cur], h->P, h->st));
+    LAUNCH(GMS_PHASE_NORMALISE, k_weighted_pose<<<h->ntiles, 1024, 0, h->stream>>>(
+                                    h->w[h->cur], h->pose[h->cur], h->P, h->ntiles, h->wp_part, h->wp_counter, h->st));
     h->stats_valid = false;
     int rc = fetch_stats(h);
     if (rc) return rc;
@@ -761,6 +823,7 @@ EXPORT int gms_set_weights(gms_handle* h, const double* w) {
     if (!w) return GMS_ERR_INVALID_ARG;
     CK(cudaMemcpyAsync(h->w[h->cur], w, (size_t)h->P * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->tile_fx_valid = false;
     return GMS_OK;
 }
 EXPORT int gms_set_map_counts(gms_handle* h, int32_t particle, const uint32_t* nf, const uint32_t* no) {

@@ -6,13 +6,9 @@
 //   lik    f64[S][H][W]              likelihood field (GridMapData.likelihoodData)
 //   rect   int4[S]                   cells modified since the slot's last likelihood rebuild
 #pragma once
-#include <cooperative_groups.h>
-
 #include "device_math.cuh"
 
 namespace gms {
-
-namespace cg = cooperative_groups;
 
 struct Stats {
     double neff;          // SLAM.calculateNeff of the last update
@@ -75,10 +71,13 @@ __global__ void __launch_bounds__(256) k_pack_beams(const double2* __restrict__ 
 // A2 — SLAM.sampleMotionModel SLAM.java:155-163 + Odometry.apply Odometry.java:77-96.
 // One thread per local particle; z = {z_d, z_theta} injected or Philox(seed, global index, step).
 // ------------------------------------------------------------------------------------------------
+constexpr int kSortBins = 65536;  // heading buckets of 2*pi/65536 rad (1 mm of arc at 10 m)
+
 __global__ void __launch_bounds__(256) k_motion(float4* __restrict__ pose, int lo, int cnt,
                                                 const double* __restrict__ normals, uint64_t seed,
                                                 uint64_t step, double d_center, double d_theta, double sd_c,
-                                                double sd_t) {
+                                                double sd_t, unsigned* __restrict__ sort_hist,
+                                                unsigned* __restrict__ sort_key, unsigned* __restrict__ sort_rank) {
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= cnt) return;
     const int i = lo + li;
@@ -96,6 +95,63 @@ __global__ void __launch_bounds__(256) k_motion(float4* __restrict__ pose, int l
     p.x = (float)((double)p.x + (double)cos_f(p.z) * d);
     p.y = (float)((double)p.y + (double)sin_f(p.z) * d);
     pose[i] = p;
+    if (sort_hist) {
+        // processing order for k_score_sorted (not part of the arithmetic): bucket by heading; the rank
+        // inside a bucket is whatever order the atomics land in — any order gives the same weights
+        const unsigned b = min(__float2uint_rz((p.z + 3.14159274f) * (kSortBins / 6.28318548f)), (unsigned)kSortBins - 1u);
+        sort_key[li] = b;
+        sort_rank[li] = atomicAdd(sort_hist + b, 1u);
+    }
+}
+
+// exclusive scan of the heading histogram (one CTA, 64 bins per thread) + re-zero for the next step
+__global__ void __launch_bounds__(1024) k_sort_scan(unsigned* __restrict__ hist, unsigned* __restrict__ offs) {
+    __shared__ unsigned s_w[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int per = kSortBins / 1024;
+    uint4* h4 = reinterpret_cast<uint4*>(hist) + tid * (per / 4);
+    unsigned sum = 0;
+#pragma unroll 4
+    for (int k = 0; k < per / 4; k++) {
+        const uint4 v = h4[k];
+        sum += v.x + v.y + v.z + v.w;
+    }
+    unsigned inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    unsigned wv = s_w[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, wv, o);
+        if (lane >= o) wv += u;
+    }
+    const unsigned wbase = wid > 0 ? __shfl_sync(0xffffffffu, wv, wid - 1) : 0u;
+    unsigned run = wbase + inc - sum;
+    uint4* o4 = reinterpret_cast<uint4*>(offs) + tid * (per / 4);
+#pragma unroll 4
+    for (int k = 0; k < per / 4; k++) {
+        const uint4 v = h4[k];  // second read: L1/L2 hit
+        uint4 o;
+        o.x = run; run += v.x;
+        o.y = run; run += v.y;
+        o.z = run; run += v.z;
+        o.w = run; run += v.w;
+        o4[k] = o;
+        h4[k] = make_uint4(0, 0, 0, 0);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sort_scatter(const unsigned* __restrict__ offs,
+                                                      const unsigned* __restrict__ key,
+                                                      const unsigned* __restrict__ rank, int cnt,
+                                                      int* __restrict__ order) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li < cnt) order[offs[key[li]] + rank[li]] = li;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -294,6 +350,94 @@ __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, 
     }
 }
 
+// Shared map, many particles: ONE THREAD per particle, the 32 lanes of a warp take 32 particles that
+// are neighbours in heading (k_motion / k_sort_*).  Why (ncu, profiles/r01_*): with beams across lanes a
+// warp-wide gather touches ~17-25 different 128-byte lines, and the L1 tag stage retires one line per
+// clock, so scoring sat at ~1 lookup/clk/SM (0.25 ms for 72 M lookups) regardless of instruction
+// count.  Heading-sorted neighbours look up the SAME beam at nearly the same cell, so a warp-wide
+// gather touches 1-3 lines.  The product runs over the beams in Java's order; every 64 factors the
+// exponent is peeled off exactly (power-of-two scaling commutes with rounding), so mant * 2^exp2 is
+// Java's product bit for bit wherever that does not underflow, and ln() is taken once.
+__global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__ pose, int lo, int cnt,
+                                                      const double2* __restrict__ hit_xy,
+                                                      const Stats* __restrict__ st, const double* __restrict__ lik,
+                                                      const int* __restrict__ order, double* __restrict__ lw,
+                                                      ExchangeRec* __restrict__ xlocal, Geometry g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+    double2* s_xy = reinterpret_cast<double2*>(smem_raw);
+    const int nh = st->num_hit;
+    const int tid = threadIdx.x;
+    const uint32_t bar = smem_u32(&s_bar);
+    if (nh > 0) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)nh * 16u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    smem_u32(s_xy)),
+                "l"(hit_xy), "r"(bytes), "r"(bar)
+                : "memory");
+        }
+    }
+    const int t = blockIdx.x * blockDim.x + tid;
+    const int li = t < cnt ? order[t] : -1;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (li >= 0) p = pose[lo + li];
+    const Xform x(p.x, p.y, p.z);
+    if (nh > 0) {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                : "=r"(done)
+                : "r"(bar)
+                : "memory");
+        }
+    }
+    if (li < 0) return;
+    double mant = 1.0;
+    int exp2 = 0;
+    for (int b0 = 0; b0 < nh; b0 += 8) {
+        double f[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int b = b0 + u;
+            f[u] = 1.0;
+            if (b < nh) {
+                const double2 m = s_xy[b];  // same address in every lane: shared-memory broadcast
+                const int gx = cell_of(x.tx(m.x, m.y) - g.posx, g.res, g.inv_res);
+                const int gy = cell_of(x.ty(m.x, m.y) - g.posy, g.res, g.inv_res);
+                if (!(gx < 0 || gy < 0 || gx >= g.W || gy >= g.H)) {
+                    const double val = __ldg(lik + ((size_t)gx + (size_t)gy * g.W));
+                    f[u] = val == 0.5 ? g.uniform_term : g.z_hit * val + g.random_term;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (b0 + u < nh) mant *= f[u];  // skipped beams do not multiply (x * 1.0 == x anyway)
+        if ((b0 & 63) == 56) {  // factors are in [0.01, 0.91]: 64 of them cannot underflow a normalised mantissa
+            const int hi = __double2hiint(mant);
+            const int e = ((hi >> 20) & 0x7ff) - 1023;
+            mant = __hiloint2double(hi - (e << 20), __double2loint(mant));
+            exp2 += e;
+        }
+    }
+    const double l = log(mant) + (double)exp2 * 0.6931471805599453;
+    lw[lo + li] = l;
+    if (xlocal) {
+        ExchangeRec r;
+        r.lw = l; r.x = p.x; r.y = p.y; r.t = p.z; r.pad = 0;
+        xlocal[li] = r;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // A8..A11 — GridMap.integrateObservation GridMap.java:173-191 + applyMeasurement :194-228.
 // One thread per (particle, beam) ray; per-particle maps, or the shared map from the strongest pose.
@@ -334,13 +478,17 @@ __global__ void __launch_bounds__(128) k_map_update(const float4* __restrict__ p
 // is not.  Pass 1 walks each ray once and records its cells {x | y << 16}; pass 2 classifies and
 // accumulates all cells of all rays in parallel.
 __global__ void __launch_bounds__(64) k_ray_walk(const float4* __restrict__ pose,
-                                                 const double2* __restrict__ all_xy, int B,
+                                                 const double2* __restrict__ all_xy, int B, int Bpad,
                                                  const Stats* __restrict__ st, uint32_t* __restrict__ ray_cells,
                                                  int cap, int* __restrict__ ray_count,
-                                                 float2* __restrict__ ray_start, int4* __restrict__ rect,
-                                                 Geometry g) {
+                                                 float2* __restrict__ ray_start, int* __restrict__ ray_maxlen,
+                                                 int4* __restrict__ rect, Geometry g) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    if (b >= Bpad) return;
+    if (b >= B) {
+        ray_count[b] = 0;
+        return;
+    }
     const float4 p = pose[st->strongest];
     const Xform t(p.x, p.y, p.z);
     const float sx = (float)((t.tx(0.0, 0.0) - g.posx) / g.res);
@@ -351,16 +499,21 @@ __global__ void __launch_bounds__(64) k_ray_walk(const float4* __restrict__ pose
     if (b == 0) *ray_start = make_float2(sx, sy);
     RayIter it;
     it.init(sx + 0.5f, sy + 0.5f, ex + 0.5f, ey + 0.5f, g.extra_steps);
-    uint32_t* out = ray_cells + (size_t)b * cap;
+    // cell k of ray b lives at ray_cells[k * Bpad + b]: lanes (consecutive rays) advance in lockstep, so
+    // every store of the walk and every load of k_ray_apply is one coalesced line
+    uint32_t* out = ray_cells + b;
     int c = 0;
-    int fx = it.x, fy = it.y, lx = it.x, ly = it.y;
+    const int fx = it.x, fy = it.y;
+    int lx = it.x, ly = it.y;
     while (it.has_next(g.W, g.H) && c < cap) {
         lx = it.x; ly = it.y;
-        out[c++] = (uint32_t)lx | ((uint32_t)ly << 16);
+        out[(size_t)c * Bpad] = (uint32_t)lx | ((uint32_t)ly << 16);
+        c++;
         it.advance();
     }
     ray_count[b] = c;
     if (c > 0) {
+        atomicMax(ray_maxlen, c);
         int* r = reinterpret_cast<int*>(rect);
         atomicMin(r + 0, min(fx, lx));
         atomicMin(r + 1, min(fy, ly));
@@ -369,23 +522,32 @@ __global__ void __launch_bounds__(64) k_ray_walk(const float4* __restrict__ pose
     }
 }
 
-__global__ void __launch_bounds__(256) k_ray_apply(const uint32_t* __restrict__ ray_cells, int cap,
-                                                   const int* __restrict__ ray_count,
+// persistent grid-stride over the (cell k, ray b) pairs; resets ray_maxlen for the next scan
+__global__ void __launch_bounds__(256) k_ray_apply(const uint32_t* __restrict__ ray_cells, int Bpad,
+                                                   const int* __restrict__ ray_count, int* __restrict__ ray_maxlen,
                                                    const float2* __restrict__ ray_start,
                                                    const float* __restrict__ meas, const uint8_t* __restrict__ hit,
                                                    CellCounts* __restrict__ counts, Geometry g) {
-    const int b = blockIdx.y;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= ray_count[b]) return;
-    const uint32_t cell = ray_cells[(size_t)b * cap + k];
-    const int cx = (int)(cell & 0xffffu), cy = (int)(cell >> 16);
+    const int maxlen = *ray_maxlen;
+    const long long total = (long long)maxlen * Bpad;
     const float2 s = *ray_start;
-    const float dX = s.x - ((float)cx + 0.5f);
-    const float dY = s.y - ((float)cy + 0.5f);
-    const float dist = __fsqrt_rn(dX * dX + dY * dY);
-    const int cls = inverse_sensor_class(dist, meas[b], hit[b] != 0, g.tol_half);
-    if (cls != 0) atomicAdd(reinterpret_cast<uint32_t*>(counts + ((size_t)cx + (size_t)cy * g.W)) + (cls - 1), 1u);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(e / Bpad), b = (int)(e - (long long)k * Bpad);
+        if (k >= ray_count[b]) continue;
+        const uint32_t cell = ray_cells[e];
+        const int cx = (int)(cell & 0xffffu), cy = (int)(cell >> 16);
+        const float dX = s.x - ((float)cx + 0.5f);
+        const float dY = s.y - ((float)cy + 0.5f);
+        const float dist = __fsqrt_rn(dX * dX + dY * dY);
+        const int cls = inverse_sensor_class(dist, meas[b], hit[b] != 0, g.tol_half);
+        if (cls != 0)
+            atomicAdd(reinterpret_cast<uint32_t*>(counts + ((size_t)cx + (size_t)cy * g.W)) + (cls - 1), 1u);
+    }
 }
+
+// runs after k_ray_apply on the same stream
+__global__ void k_ray_reset(int* ray_maxlen) { *ray_maxlen = 0; }
 
 // single ray given in grid coordinates (gms_map_apply_measurement)
 __global__ void k_apply_one(CellCounts* __restrict__ counts, int4* __restrict__ rect, float sx, float sy,
@@ -417,13 +579,11 @@ __global__ void k_trace_rays(const float4* __restrict__ rays, int n, int extra, 
 
 // ------------------------------------------------------------------------------------------------
 // A6 — normalise (SLAM.java:119-121), Neff (:180-190), strongest (:110-115), weighted pose (:165-178).
-// P <= ~1e6 doubles: latency-bound reductions.  One thread-block CLUSTER of 8 CTAs x 1024 threads;
-// CTA partials are exchanged through distributed shared memory (DSMEM) and combined in rank order, so
-// every CTA — and every rank of a multi-GPU run — obtains bit-identical totals (fixed tree).
+// P <= ~1e6 doubles: latency-bound.  ceil(P/1024) CTAs of 1024 threads; per-CTA partials go to global
+// memory and are combined in a FIXED order (by every CTA redundantly, or by the last CTA to finish), so
+// the totals are run-to-run and rank-to-rank bit-identical.  (An 8-CTA cluster/DSMEM version measured
+// 33 us here: it confines the exp/divide work to 8 SMs.)
 // ------------------------------------------------------------------------------------------------
-constexpr int kClusterCtas = 8;
-constexpr int kClusterThreads = kClusterCtas * 1024;
-
 template <typename T, typename Op>
 __device__ __forceinline__ T block_reduce_1024(T v, Op op, T* s_buf) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -440,43 +600,16 @@ __device__ __forceinline__ T block_reduce_1024(T v, Op op, T* s_buf) {
 struct SumOp { __device__ double operator()(double a, double b) const { return a + b; } };
 struct SumU64 { __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a + b; } };
 
-// block partial -> cluster total (identical in every thread of every CTA of the cluster)
-__device__ __forceinline__ double cluster_sum(cg::cluster_group& cl, double v, double* s_buf, double* s_slot) {
-    const double b = block_reduce_1024(v, SumOp(), s_buf);
-    if (threadIdx.x == 0) *s_slot = b;
-    cl.sync();
-    double t = 0.0;
-#pragma unroll
-    for (int r = 0; r < kClusterCtas; r++) t += *cl.map_shared_rank(s_slot, r);
-    cl.sync();  // the slot may be rewritten by the next reduction
-    return t;
-}
-
-__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
-    k_normalise(const double* __restrict__ lw, double* __restrict__ w, const float4* __restrict__ pose, int P,
-                int policy, Stats* __restrict__ st) {
-    cg::cluster_group cl = cg::this_cluster();
-    __shared__ double s_d[32];
-    __shared__ double s_key[32];
-    __shared__ int s_idx[32];
-    __shared__ double s_slot;
-    __shared__ double s_best;
-    __shared__ int s_besti;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int gt = cl.block_rank() * 1024 + tid;
-    // pass 1: max and its FIRST index (strict > keeps the first maximum, SLAM.java:110-115)
-    double best = __longlong_as_double(0xfff0000000000000LL);  // -inf
-    int bi = 0x7fffffff;
-    for (int i = gt; i < P; i += kClusterThreads) {
-        const double v = lw[i];
-        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
-    }
+// (max, first index of the max) over a block; result valid in every thread
+__device__ __forceinline__ void block_argmax_1024(double& best, int& bi, double* s_key, int* s_idx) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
+    __syncthreads();
     if (lane == 0) { s_key[wid] = best; s_idx[wid] = bi; }
     __syncthreads();
     best = s_key[lane]; bi = s_idx[lane];
@@ -486,93 +619,183 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
-    if (tid == 0) { s_best = best; s_besti = bi; }
-    cl.sync();
-#pragma unroll
-    for (int r = 0; r < kClusterCtas; r++) {
-        const double ov = *cl.map_shared_rank(&s_best, r);
-        const int oi = *cl.map_shared_rank(&s_besti, r);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+}
+
+struct NormPartials {   // one entry per CTA (tile of 1024 particles)
+    double* m;          // tile max of lw
+    int* idx;           // first index of the tile max
+    double* s;          // sum exp(lw - tile max)
+    double* ws;         // sum of normalised weights of the tile
+    double* q;          // sum of squared normalised weights of the tile
+    unsigned long long* fx;  // sum of trunc(w * 2^60) of the tile (feeds k_cdf_fixed)
+    unsigned* counter;  // last-block-done ticket
+};
+#define kNegInf (__longlong_as_double((long long)0xfff0000000000000ULL))
+
+// pass 1: per-tile (max, first arg-max, sum exp(lw - tile max))
+__global__ void __launch_bounds__(1024) k_softmax_partials(const double* __restrict__ lw, int P, NormPartials np) {
+    __shared__ double s_key[32];
+    __shared__ int s_idx[32];
+    __shared__ double s_d[32];
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    const double v = i < P ? lw[i] : kNegInf;
+    double best = v;
+    int bi = i < P ? i : 0x7fffffff;
+    block_argmax_1024(best, bi, s_key, s_idx);
+    const double e = i < P ? exp(v - best) : 0.0;
+    const double sum = block_reduce_1024(e, SumOp(), s_d);
+    if (threadIdx.x == 0) {
+        np.m[blockIdx.x] = best;
+        np.idx[blockIdx.x] = bi;
+        np.s[blockIdx.x] = sum;
     }
-    // pass 2: e_i = exp(lw_i - max), S = sum e_i
+}
+
+// pass 2: every CTA combines the tile partials in the same fixed order -> (M, first arg-max, S); then
+// w_i = exp(lw_i - M) / S for its tile, tile sums; the last CTA to finish folds the tile sums (fixed
+// order) into Neff (SLAM.java:180-190: 1 / sum (w / sum w)^2, evaluated as (sum w)^2 / sum w^2) and
+// publishes the step's statistics.
+__global__ void __launch_bounds__(1024) k_normalise(const double* __restrict__ lw, double* __restrict__ w,
+                                                    const float4* __restrict__ pose, int P, int ntiles, int policy,
+                                                    NormPartials np, Stats* __restrict__ st) {
+    __shared__ double s_key[32];
+    __shared__ int s_idx[32];
+    __shared__ double s_d[32];
+    __shared__ unsigned long long s_u[32];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x;
+    double best = kNegInf;
+    int bi = 0x7fffffff;
+    for (int c = tid; c < ntiles; c += 1024) {
+        const double v = np.m[c];
+        const int vi = np.idx[c];
+        if (v > best || (v == best && vi < bi)) { best = v; bi = vi; }
+    }
+    block_argmax_1024(best, bi, s_key, s_idx);
     double acc = 0.0;
-    for (int i = gt; i < P; i += kClusterThreads) {
-        const double e = exp(lw[i] - best);
-        w[i] = e;
-        acc += e;
+    for (int c = tid; c < ntiles; c += 1024) acc += np.s[c] * exp(np.m[c] - best);
+    const double S = block_reduce_1024(acc, SumOp(), s_d);
+    const int i = blockIdx.x * 1024 + tid;
+    double wi = 0.0;
+    if (i < P) {
+        wi = exp(lw[i] - best) / S;
+        w[i] = wi;
     }
-    const double S = cluster_sum(cl, acc, s_d, &s_slot);
-    // pass 3: w_i = e_i / S and their sum (SLAM.calculateNeff recomputes it, SLAM.java:181-183)
-    acc = 0.0;
-    for (int i = gt; i < P; i += kClusterThreads) {
-        const double v = w[i] / S;
-        w[i] = v;
-        acc += v;
+    const double ws = block_reduce_1024(wi, SumOp(), s_d);
+    const double q = block_reduce_1024(wi * wi, SumOp(), s_d);
+    const unsigned long long fx = block_reduce_1024((unsigned long long)(wi * 0x1p60), SumU64(), s_u);
+    if (tid == 0) {
+        np.ws[blockIdx.x] = ws;
+        np.q[blockIdx.x] = q;
+        np.fx[blockIdx.x] = fx;
+        __threadfence();
+        s_last = atomicAdd(np.counter, 1u) == (unsigned)ntiles - 1u;
     }
-    const double ws = cluster_sum(cl, acc, s_d, &s_slot);
-    // pass 4: sum (w/ws)^2 (SLAM.java:185-187)
-    acc = 0.0;
-    for (int i = gt; i < P; i += kClusterThreads) {
-        const double v = w[i] / ws;
-        acc += v * v;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    for (int c = tid; c < ntiles; c += 1024) {
+        a += __ldcg(np.ws + c);
+        b += __ldcg(np.q + c);
     }
-    const double sq = cluster_sum(cl, acc, s_d, &s_slot);
-    if (gt == 0) {
-        const double neff = 1.0 / sq;
+    a = block_reduce_1024(a, SumOp(), s_d);
+    b = block_reduce_1024(b, SumOp(), s_d);
+    if (tid == 0) {
+        const double neff = (a * a) / b;
         st->neff = neff;
         st->lw_max = best;
         st->sum_exp = S;
         st->strongest = bi;
-        st->strongest_w = exp(lw[bi] - best) / S;
+        st->strongest_w = 1.0 / S;
         const float4 p = pose[bi];
         st->strongest_pose[0] = p.x; st->strongest_pose[1] = p.y; st->strongest_pose[2] = p.z;
         st->do_resample = policy == 2 || (policy == 1 && neff < (double)(P / 2));  // GridMapApp.java:185
+        *np.counter = 0u;
     }
 }
 
-// SLAM.calculateNeff on the current weights (after set_weights / resample)
-__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
-    k_neff(const double* __restrict__ w, int P, Stats* __restrict__ st) {
-    cg::cluster_group cl = cg::this_cluster();
+// SLAM.calculateNeff on the current weights (after set_weights / resample); also the fixed-point tile
+// sums k_cdf_fixed needs.  Same last-block pattern.
+__global__ void __launch_bounds__(1024) k_neff(const double* __restrict__ w, int P, int ntiles, NormPartials np,
+                                               Stats* __restrict__ st) {
     __shared__ double s_d[32];
-    __shared__ double s_slot;
-    const int gt = cl.block_rank() * 1024 + threadIdx.x;
-    double acc = 0.0;
-    for (int i = gt; i < P; i += kClusterThreads) acc += w[i];
-    const double ws = cluster_sum(cl, acc, s_d, &s_slot);
-    acc = 0.0;
-    for (int i = gt; i < P; i += kClusterThreads) {
-        const double v = w[i] / ws;
-        acc += v * v;
+    __shared__ unsigned long long s_u[32];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * 1024 + tid;
+    const double wi = i < P ? w[i] : 0.0;
+    const double ws = block_reduce_1024(wi, SumOp(), s_d);
+    const double q = block_reduce_1024(wi * wi, SumOp(), s_d);
+    const unsigned long long fx = block_reduce_1024((unsigned long long)(wi * 0x1p60), SumU64(), s_u);
+    if (tid == 0) {
+        np.ws[blockIdx.x] = ws;
+        np.q[blockIdx.x] = q;
+        np.fx[blockIdx.x] = fx;
+        __threadfence();
+        s_last = atomicAdd(np.counter, 1u) == (unsigned)ntiles - 1u;
     }
-    const double sq = cluster_sum(cl, acc, s_d, &s_slot);
-    if (gt == 0) st->neff_query = 1.0 / sq;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    for (int c = tid; c < ntiles; c += 1024) {
+        a += __ldcg(np.ws + c);
+        b += __ldcg(np.q + c);
+    }
+    a = block_reduce_1024(a, SumOp(), s_d);
+    b = block_reduce_1024(b, SumOp(), s_d);
+    if (tid == 0) {
+        st->neff_query = (a * a) / b;
+        *np.counter = 0u;
+    }
 }
 
 // SLAM.getWeightedPose SLAM.java:165-178 (plain, not circular, mean of angleConstrain(theta))
-__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
-    k_weighted_pose(const double* __restrict__ w, const float4* __restrict__ pose, int P, Stats* __restrict__ st) {
-    cg::cluster_group cl = cg::this_cluster();
+__global__ void __launch_bounds__(1024) k_weighted_pose(const double* __restrict__ w,
+                                                        const float4* __restrict__ pose, int P, int ntiles,
+                                                        double* __restrict__ part /* 4 * ntiles */,
+                                                        unsigned* __restrict__ counter, Stats* __restrict__ st) {
     __shared__ double s_d[32];
-    __shared__ double s_slot;
-    const int gt = cl.block_rank() * 1024 + threadIdx.x;
+    __shared__ bool s_last;
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * 1024 + tid;
     double xs = 0, ys = 0, ts = 0, ws = 0;
-    for (int i = gt; i < P; i += kClusterThreads) {
+    if (i < P) {
         const float4 p = pose[i];
         const double wi = w[i];
-        xs += (double)p.x * wi;
-        ys += (double)p.y * wi;
-        ts += angle_constrain((double)p.z) * wi;
-        ws += wi;
+        xs = (double)p.x * wi;
+        ys = (double)p.y * wi;
+        ts = angle_constrain((double)p.z) * wi;
+        ws = wi;
     }
-    xs = cluster_sum(cl, xs, s_d, &s_slot);
-    ys = cluster_sum(cl, ys, s_d, &s_slot);
-    ts = cluster_sum(cl, ts, s_d, &s_slot);
-    ws = cluster_sum(cl, ws, s_d, &s_slot);
-    if (gt == 0) {
+    xs = block_reduce_1024(xs, SumOp(), s_d);
+    ys = block_reduce_1024(ys, SumOp(), s_d);
+    ts = block_reduce_1024(ts, SumOp(), s_d);
+    ws = block_reduce_1024(ws, SumOp(), s_d);
+    if (tid == 0) {
+        part[4 * blockIdx.x + 0] = xs; part[4 * blockIdx.x + 1] = ys;
+        part[4 * blockIdx.x + 2] = ts; part[4 * blockIdx.x + 3] = ws;
+        __threadfence();
+        s_last = atomicAdd(counter, 1u) == (unsigned)ntiles - 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    xs = ys = ts = ws = 0.0;
+    for (int c = tid; c < ntiles; c += 1024) {
+        xs += __ldcg(part + 4 * c + 0); ys += __ldcg(part + 4 * c + 1);
+        ts += __ldcg(part + 4 * c + 2); ws += __ldcg(part + 4 * c + 3);
+    }
+    xs = block_reduce_1024(xs, SumOp(), s_d);
+    ys = block_reduce_1024(ys, SumOp(), s_d);
+    ts = block_reduce_1024(ts, SumOp(), s_d);
+    ws = block_reduce_1024(ws, SumOp(), s_d);
+    if (tid == 0) {
         st->weighted_pose[0] = (float)(xs / ws);
         st->weighted_pose[1] = (float)(ys / ws);
         st->weighted_pose[2] = (float)(ts / ws);
+        *counter = 0u;
     }
 }
 
@@ -609,51 +832,37 @@ __global__ void __launch_bounds__(32) k_cdf_literal(const double* __restrict__ w
     }
 }
 
-// FIXED CDF: u64 fixed point trunc(w * 2^60); integer addition is associative, so the cluster-wide
-// scan equals the sequential walk bit for bit on any number of threads / CTAs / ranks.  Each CTA of
-// the 8-CTA cluster owns a contiguous chunk: chunk totals travel through DSMEM, then a coalesced
-// tile-by-tile block scan (warp shuffles) writes the inclusive prefix.
-__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(1024)
-    k_cdf_fixed(const double* __restrict__ w, int P, unsigned long long* __restrict__ cdf,
-                const Stats* __restrict__ st) {
-    if (!st->do_resample) return;  // uniform over the cluster
-    cg::cluster_group cl = cg::this_cluster();
+// FIXED CDF: u64 fixed point trunc(w * 2^60); integer addition is associative, so a parallel scan equals
+// the sequential walk bit for bit on any number of threads / CTAs / ranks.  Tile c (1024 particles) adds
+// the fixed-point tile sums of tiles < c (produced by k_normalise / k_neff) to a block-wide scan.
+__global__ void __launch_bounds__(1024) k_cdf_fixed(const double* __restrict__ w, int P,
+                                                    const unsigned long long* __restrict__ tile_fx,
+                                                    unsigned long long* __restrict__ cdf,
+                                                    const Stats* __restrict__ st) {
+    if (!st->do_resample) return;
     __shared__ unsigned long long s_u[32];
-    __shared__ unsigned long long s_total;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int rank = (int)cl.block_rank();
-    const int per = (((P + kClusterCtas - 1) / kClusterCtas + 1023) / 1024) * 1024;
-    const int i0 = min(P, rank * per), i1 = min(P, i0 + per);
     unsigned long long acc = 0;
-    for (int i = i0 + tid; i < i1; i += 1024) acc += (unsigned long long)(w[i] * 0x1p60);
-    const unsigned long long tot = block_reduce_1024(acc, SumU64(), s_u);
-    if (tid == 0) s_total = tot;
-    cl.sync();
-    unsigned long long carry = 0;
-    for (int r = 0; r < rank; r++) carry += *cl.map_shared_rank(&s_total, r);
-    cl.sync();
-    for (int base = i0; base < i1; base += 1024) {
-        const int i = base + tid;
-        unsigned long long v = i < i1 ? (unsigned long long)(w[i] * 0x1p60) : 0ull;
+    for (int c = tid; c < (int)blockIdx.x; c += 1024) acc += tile_fx[c];
+    const unsigned long long carry = block_reduce_1024(acc, SumU64(), s_u);
+    const int i = blockIdx.x * 1024 + tid;
+    unsigned long long v = i < P ? (unsigned long long)(w[i] * 0x1p60) : 0ull;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long u = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane >= o) v += u;
-        }
-        __syncthreads();
-        if (lane == 31) s_u[wid] = v;
-        __syncthreads();
-        unsigned long long wsum = s_u[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long u = __shfl_up_sync(0xffffffffu, wsum, o);
-            if (lane >= o) wsum += u;
-        }
-        const unsigned long long warp_excl = __shfl_sync(0xffffffffu, wsum, max(wid, 1) - 1);
-        const unsigned long long tile_total = __shfl_sync(0xffffffffu, wsum, 31);
-        if (i < i1) cdf[i] = carry + (wid > 0 ? warp_excl : 0ull) + v;
-        carry += tile_total;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
     }
+    __syncthreads();
+    if (lane == 31) s_u[wid] = v;
+    __syncthreads();
+    unsigned long long wsum = s_u[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long u = __shfl_up_sync(0xffffffffu, wsum, o);
+        if (lane >= o) wsum += u;
+    }
+    const unsigned long long warp_excl = __shfl_sync(0xffffffffu, wsum, max(wid, 1) - 1);
+    if (i < P) cdf[i] = carry + (wid > 0 ? warp_excl : 0ull) + v;
 }
 
 // index selection: for m = 1..P, U = r + (m-1)*1.0/P, first i with !(U > c_i), clamped to P-1.
