@@ -21,6 +21,7 @@ struct Geometry {
     float tol_half;           // hitTolerance / 2 (SensorModel.java:35-37)
     double res, posx, posy;   // (double) resolution / position: the promotions Java performs
     double inv_res;           // 1.0 / res — only for the guarded fast path of cell_of()
+    double half_margin;       // 0.5 - 1e-5: fast-path acceptance band of k_score_sorted
     double z_hit;             // GridMap.java:259
     double uniform_term;      // 1.0 / SENSOR_MAX_RANGE                (GridMap.java:286)
     double random_term;       // zRandom * 1.0 / SENSOR_MAX_RANGE      (GridMap.java:288)

@@ -47,6 +47,7 @@ struct gms_handle {
     // maps
     CellCounts* counts = nullptr;
     double* lik = nullptr;
+    double* fac = nullptr;  // shared map only: per-cell scoring factor (GridMap.java:284-288)
     int4* rect = nullptr;
     int4* tile_desc = nullptr;
     int* tile_off = nullptr;
@@ -193,7 +194,7 @@ void free_all(gms_handle* h) {
     cudaSetDevice(h->dev);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (int i = 0; i < 2; i++) { cudaFree(h->pose[i]); cudaFree(h->w[i]); cudaFree(h->lw[i]); cudaFree(h->slot[i]); }
-    cudaFree(h->parents); cudaFree(h->cdf); cudaFree(h->counts); cudaFree(h->lik); cudaFree(h->rect);
+    cudaFree(h->parents); cudaFree(h->cdf); cudaFree(h->counts); cudaFree(h->lik); cudaFree(h->fac); cudaFree(h->rect);
     cudaFree(h->tile_desc); cudaFree(h->tile_off); cudaFree(h->dup_src); cudaFree(h->dup_dst); cudaFree(h->scratch2p);
     cudaFree(h->in_xy); cudaFree(h->all_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
     cudaFree(h->all_hit); cudaFree(h->meas); cudaFree(h->d_normals); cudaFree(h->xlocal); cudaFree(h->xglobal);
@@ -282,7 +283,7 @@ int launch_likelihood(gms_handle* h) {
     const size_t smem = (size_t)th * kTileW * 8 + (size_t)th * tw * 4;
     const long long max_tiles = (long long)h->S * ((h->W + kTileW - 1) / kTileW) * ((h->H + kTileH - 1) / kTileH);
     const unsigned grid = (unsigned)std::min<long long>(max_tiles, 148 * 6);
-    LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<<<grid, 256, smem, h->stream>>>(h->counts, h->lik, h->tile_desc,
+    LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<<<grid, 256, smem, h->stream>>>(h->counts, h->lik, h->fac, h->tile_desc,
                                                                                h->tile_off, h->S, h->st, h->g));
     return GMS_OK;
 }
@@ -297,7 +298,7 @@ int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* 
     if (sorted) {
         const size_t smem_s = std::max<size_t>(16, (size_t)B * 16);
         LAUNCH(GMS_PHASE_SCORE, k_score_sorted<<<blocks_for(cnt, 128), 128, smem_s, h->stream>>>(
-                                    pose, lo, cnt, h->hit_xy, h->st, h->lik, h->order, lw, xlocal, h->g));
+                                    pose, lo, cnt, h->hit_xy, h->st, h->fac, h->order, lw, xlocal, h->g));
         return GMS_OK;
     }
     const unsigned grid = std::min<unsigned>(blocks_for(cnt, 8), 148 * 8);
@@ -563,6 +564,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     g.tol_half = cfg->hit_tolerance / 2;
     g.res = (double)cfg->resolution; g.posx = (double)cfg->origin_x; g.posy = (double)cfg->origin_y;
     g.inv_res = 1.0 / g.res;
+    g.half_margin = 0.5 - 1e-5;
     g.z_hit = cfg->z_hit;
     g.uniform_term = 1.0 / (double)cfg->sensor_max_range;                          // GridMap.java:286
     g.random_term = (1 - cfg->z_hit) * 1.0 / (double)cfg->sensor_max_range;        // GridMap.java:288
@@ -602,6 +604,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->cdf, P * 8));
     CKC(cudaMalloc((void**)&h->counts, (size_t)h->S * h->cells * sizeof(CellCounts)));
     CKC(cudaMalloc((void**)&h->lik, (size_t)h->S * h->cells * sizeof(double)));
+    if (cfg->map_mode == GMS_MAP_SHARED) CKC(cudaMalloc((void**)&h->fac, h->cells * sizeof(double)));
     CKC(cudaMalloc((void**)&h->rect, (size_t)h->S * sizeof(int4)));
     CKC(cudaMalloc((void**)&h->tile_desc, (size_t)h->S * sizeof(int4)));
     CKC(cudaMalloc((void**)&h->tile_off, ((size_t)h->S + 1) * 4));
@@ -895,7 +898,7 @@ EXPORT int gms_map_compute_likelihood(gms_handle* h, int32_t particle) {
         const size_t smem = (size_t)th * kTileW * 8 + (size_t)th * tw * 4;
         LAUNCH(GMS_PHASE_LIKELIHOOD,
                k_likelihood<<<148 * 6, 256, smem, h->stream>>>(h->counts + (size_t)s * h->cells,
-                                                               h->lik + (size_t)s * h->cells, h->tile_desc,
+                                                               h->lik + (size_t)s * h->cells, h->fac, h->tile_desc,
                                                                h->tile_off, 1, h->st, h->g));
     }
     CK(cudaStreamSynchronize(h->stream));

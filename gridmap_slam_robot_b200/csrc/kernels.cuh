@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) k_pack_beams(const double2* __restrict__ 
 // A2 — SLAM.sampleMotionModel SLAM.java:155-163 + Odometry.apply Odometry.java:77-96.
 // One thread per local particle; z = {z_d, z_theta} injected or Philox(seed, global index, step).
 // ------------------------------------------------------------------------------------------------
-constexpr int kSortBins = 65536;  // heading buckets of 2*pi/65536 rad (1 mm of arc at 10 m)
+constexpr int kSortBins = 8192;  // heading buckets of 2*pi/8192 rad (< 8 mm of arc at 10 m: sub-cell)
 
 __global__ void __launch_bounds__(256) k_motion(float4* __restrict__ pose, int lo, int cnt,
                                                 const double* __restrict__ normals, uint64_t seed,
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) k_motion(float4* __restrict__ pose, int l
     }
 }
 
-// exclusive scan of the heading histogram (one CTA, 64 bins per thread) + re-zero for the next step
+// exclusive scan of the heading histogram (one CTA, 8 bins per thread) + re-zero for the next step
 __global__ void __launch_bounds__(1024) k_sort_scan(unsigned* __restrict__ hist, unsigned* __restrict__ offs) {
     __shared__ unsigned s_w[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(1024) k_lik_worklist(int4* __restrict__ rect, 
 // Persistent CTAs walk the work list.  smem: s_t[(TH+2k)][TW+2k] f32 codes {0, .5, 1} (exact in f32),
 // s_h[(TH+2k)][TW] f64 horizontal pass.
 __global__ void __launch_bounds__(256) k_likelihood(const CellCounts* __restrict__ counts,
-                                                    double* __restrict__ lik, const int4* __restrict__ tile_desc,
+                                                    double* __restrict__ lik, double* __restrict__ fac,
+                                                    const int4* __restrict__ tile_desc,
                                                     const int* __restrict__ tile_off, int S,
                                                     const Stats* __restrict__ st, Geometry g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -261,6 +262,9 @@ __global__ void __launch_bounds__(256) k_likelihood(const CellCounts* __restrict
                 double total = 0.0;
                 for (int i = 0; i < g.ktaps; i++) total += g.kernel[i] * col[i * kTileW];
                 out[(size_t)gx + (size_t)gy * g.W] = total;
+                // shared map: the per-lookup factor of GridMap.probabilityOf (GridMap.java:284-288) is a
+                // pure function of the cell, so it is evaluated once per cell here, not once per lookup
+                if (fac) fac[(size_t)gx + (size_t)gy * g.W] = total == 0.5 ? g.uniform_term : g.z_hit * total + g.random_term;
             }
         }
         __syncthreads();
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, 
 // Java's product bit for bit wherever that does not underflow, and ln() is taken once.
 __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__ pose, int lo, int cnt,
                                                       const double2* __restrict__ hit_xy,
-                                                      const Stats* __restrict__ st, const double* __restrict__ lik,
+                                                      const Stats* __restrict__ st, const double* __restrict__ fac,
                                                       const int* __restrict__ order, double* __restrict__ lw,
                                                       ExchangeRec* __restrict__ xlocal, Geometry g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -401,27 +405,35 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
         }
     }
     if (li < 0) return;
+    // Fast path for (int) ((world - position) / resolution), GridMap.java:273-274: q~ = the same quantity
+    // evaluated with two FMAs from per-particle constants.  |q~ - q_java| < 1e-9 for every finite input
+    // with |q| < 2^31, so when q~ is further than 1e-5 from both neighbouring integers the truncation is
+    // the one Java computes; otherwise (or NaN / saturation) the literal expression with the f64 division
+    // decides.  Result: bit-identical cell indices at 2 DFMA instead of 4 DMUL/DADD + subtract + divide.
+    const double cinv = x.c * g.inv_res, sinv = x.s * g.inv_res;
+    const double pqx = (x.px - g.posx) * g.inv_res, pqy = (x.py - g.posy) * g.inv_res;
     double mant = 1.0;
     int exp2 = 0;
-    for (int b0 = 0; b0 < nh; b0 += 8) {
+    auto factor_of = [&](const double2 m) -> double {
+        const double qx = fma(m.x, cinv, fma(-m.y, sinv, pqx));
+        const double qy = fma(m.x, sinv, fma(m.y, cinv, pqy));
+        int gx = __double2int_rz(qx), gy = __double2int_rz(qy);
+        const double ex = fabs(qx - (double)gx) - 0.5, ey = fabs(qy - (double)gy) - 0.5;
+        if (!(fabs(ex) < g.half_margin && fabs(ey) < g.half_margin)) {
+            gx = java_d2i((x.tx(m.x, m.y) - g.posx) / g.res);
+            gy = java_d2i((x.ty(m.x, m.y) - g.posy) / g.res);
+        }
+        double f = 1.0;
+        if ((unsigned)gx < (unsigned)g.W && (unsigned)gy < (unsigned)g.H) f = __ldg(fac + ((size_t)gx + (size_t)gy * g.W));
+        return f;
+    };
+    int b0 = 0;
+    for (; b0 + 8 <= nh; b0 += 8) {
         double f[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int b = b0 + u;
-            f[u] = 1.0;
-            if (b < nh) {
-                const double2 m = s_xy[b];  // same address in every lane: shared-memory broadcast
-                const int gx = cell_of(x.tx(m.x, m.y) - g.posx, g.res, g.inv_res);
-                const int gy = cell_of(x.ty(m.x, m.y) - g.posy, g.res, g.inv_res);
-                if (!(gx < 0 || gy < 0 || gx >= g.W || gy >= g.H)) {
-                    const double val = __ldg(lik + ((size_t)gx + (size_t)gy * g.W));
-                    f[u] = val == 0.5 ? g.uniform_term : g.z_hit * val + g.random_term;
-                }
-            }
-        }
+        for (int u = 0; u < 8; u++) f[u] = factor_of(s_xy[b0 + u]);  // same address in every lane: broadcast
 #pragma unroll
-        for (int u = 0; u < 8; u++)
-            if (b0 + u < nh) mant *= f[u];  // skipped beams do not multiply (x * 1.0 == x anyway)
+        for (int u = 0; u < 8; u++) mant *= f[u];  // Java's order (GridMap.java:286-288)
         if ((b0 & 63) == 56) {  // factors are in [0.01, 0.91]: 64 of them cannot underflow a normalised mantissa
             const int hi = __double2hiint(mant);
             const int e = ((hi >> 20) & 0x7ff) - 1023;
@@ -429,6 +441,7 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
             exp2 += e;
         }
     }
+    for (; b0 < nh; b0++) mant *= factor_of(s_xy[b0]);
     const double l = log(mant) + (double)exp2 * 0.6931471805599453;
     lw[lo + li] = l;
     if (xlocal) {
