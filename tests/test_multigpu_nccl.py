@@ -1,0 +1,101 @@
+"""GPU (-m gpu), needs >= 2 devices: particles sharded over ranks, NCCL all-gather of the exchange
+records on the library's stream.  Rank-count invariance: the R-rank run equals the
+1-rank run on the same inputs — parents, poses and integer map counts bit for bit."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(P):
+    return dict(num_particles=P, map_width_m=51.2, map_height_m=51.2, origin_x=-25.6, origin_y=-25.6, map_mode=1,
+                resample_mode=2, seed=4242)
+
+
+def _steps(h, stepper, scans, normals, uniforms, lo, cnt, dev):
+    import torch
+
+    from gridmap_slam_robot_b200 import binding as B
+
+    out = []
+    for s, sc in enumerate(scans):
+        t_xy = torch.from_numpy(sc.beam_xy).to(dev)
+        t_d = torch.from_numpy(sc.beam_dist).to(dev)
+        t_h = torch.from_numpy(sc.beam_hit).to(dev)
+        t_n = torch.from_numpy(np.ascontiguousarray(normals[s, lo:lo + cnt])).to(dev)
+        torch.cuda.synchronize()
+        args = (t_xy.data_ptr(), t_d.data_ptr(), t_h.data_ptr(), sc.num_beams, sc.d_center, sc.d_theta, t_n.data_ptr())
+        if stepper:
+            stepper.step(*args, policy=B.POLICY_ALWAYS, u01=float(uniforms[s]))
+        else:
+            h.update_begin_dev(*args)
+            h.update_end_dev(B.POLICY_ALWAYS, float(uniforms[s]))
+        out.append((h.read_neff(), h.parents().copy(), h.poses().copy(), h.weights().copy(),
+                    h.get_map(0, B.MAP_FREE_COUNT).copy(), h.get_map(0, B.MAP_OCC_COUNT).copy()))
+    return out
+
+
+def _worker(rank, world, port, P, steps, beams, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from gridmap_slam_robot_b200 import binding as B
+    from gridmap_slam_robot_b200 import parallel, synth
+
+    h = B.load().create(rank=rank, nranks=world, device=rank, **_cfg(P))
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    h.set_stream(stream.cuda_stream)
+    stepper = parallel.ShardedStepper(h, dist, dev)
+    scans = synth.make_scans(steps, beams, max_range=12.0)
+    normals, uniforms = synth.make_draws(steps, P)
+    res = _steps(h, stepper, scans, normals, uniforms, h.info.local_begin, h.info.local_count, dev)
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpus_equal_one_gpu(cuda):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    from gridmap_slam_robot_b200 import synth
+
+    P, steps, beams, world = 8192, 4, 360, 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, P, steps, beams, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    h = cuda.create(**_cfg(P))
+    scans = synth.make_scans(steps, beams, max_range=12.0)
+    normals, uniforms = synth.make_draws(steps, P)
+    single = _steps(h, None, scans, normals, uniforms, 0, P, torch.device("cuda", 0))
+    for r in range(world):
+        for s in range(steps):
+            a, b = results[r][s], single[s]
+            assert abs(a[0] / b[0] - 1) < 1e-12
+            for k in (1, 2, 4, 5):
+                assert np.array_equal(a[k], b[k]), (r, s, k)
+            np.testing.assert_allclose(a[3], b[3], rtol=1e-12, atol=0)
+    h.close()
