@@ -22,6 +22,8 @@ struct Geometry {
     double res, posx, posy;   // (double) resolution / position: the promotions Java performs
     double inv_res;           // 1.0 / res — only for the guarded fast path of cell_of()
     double half_margin;       // 0.5 - 1e-5: fast-path acceptance band of k_score_sorted
+    int tiles_x, tiles_y;     // likelihood tiles (kTileW x kTileH cells) per map
+    int tile_words;           // 32-bit words of one slot's dirty-tile bitmap
     double z_hit;             // GridMap.java:259
     double uniform_term;      // 1.0 / SENSOR_MAX_RANGE                (GridMap.java:286)
     double random_term;       // zRandom * 1.0 / SENSOR_MAX_RANGE      (GridMap.java:288)
@@ -167,14 +169,56 @@ struct __align__(8) CellCounts {
     uint32_t n_free, n_occ;
 };
 
-// GridMap.applyMeasurement GridMap.java:194-228 on integer counters.  Integer atomics commute, so the
-// result is independent of the order in which rays (threads) land: deterministic by construction.
+constexpr int kTileW = 64, kTileH = 32;  // likelihood tile (cells)
+
+// Thresholded code of a cell, GridMap.java:238-245: log-odds > 0 -> 1, < 0 -> 0, == 0 -> 0.5, from the
+// closed form of the counters.  The same expression decides which tiles are rebuilt and what they hold.
+__device__ __forceinline__ double cell_value(uint32_t n_free, uint32_t n_occ, const Geometry& g) {
+    return (double)n_free * g.l_free + (double)n_occ * g.l_occ;
+}
+__device__ __forceinline__ int cell_code(uint32_t n_free, uint32_t n_occ, const Geometry& g) {
+    const double v = cell_value(n_free, n_occ, g);
+    return v > 0.0 ? 2 : (v < 0.0 ? 0 : 1);
+}
+// Does adding one free (cls 1) / occupied (cls 2) increment to (n_free, n_occ) change the code?
+// L_free < 0 < L_occ: a never-occupied cell only flips on its first free hit, a never-freed cell only on
+// its first occupied hit; everything else needs the two evaluations.
+__device__ __forceinline__ bool code_flips(uint32_t n_free, uint32_t n_occ, int cls, const Geometry& g) {
+    if (cls == 1) {
+        if (n_occ == 0) return n_free == 0;
+        return cell_code(n_free, n_occ, g) != cell_code(n_free + 1, n_occ, g);
+    }
+    if (n_free == 0) return n_occ == 0;
+    return cell_code(n_free, n_occ, g) != cell_code(n_free, n_occ + 1, g);
+}
+// The likelihood value of a cell depends on the codes within khalf cells: mark every tile whose output
+// can change when the code of (cx, cy) changes.
+__device__ __forceinline__ void mark_dirty(uint32_t* __restrict__ bitmap, int cx, int cy, const Geometry& g) {
+    const int tx0 = max(cx - g.khalf, 0) / kTileW, tx1 = min(cx + g.khalf, g.W - 1) / kTileW;
+    const int ty0 = max(cy - g.khalf, 0) / kTileH, ty1 = min(cy + g.khalf, g.H - 1) / kTileH;
+    for (int ty = ty0; ty <= ty1; ty++)
+        for (int tx = tx0; tx <= tx1; tx++) {
+            const int t = ty * g.tiles_x + tx;
+            atomicOr(bitmap + (t >> 5), 1u << (t & 31));
+        }
+}
+// One counter increment.  The 64-bit atomic returns the cell as it was, so exactly one thread observes
+// each transition: integer adds commute (deterministic counts), and a tile is queued for a likelihood
+// rebuild only when the thresholded code of one of its cells really changed.
+__device__ __forceinline__ void bump_cell(CellCounts* __restrict__ map, uint32_t* __restrict__ bitmap, int cx, int cy,
+                                          int cls, const Geometry& g) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(map + ((size_t)cx + (size_t)cy * g.W));
+    const unsigned long long old = atomicAdd(p, cls == 1 ? 1ull : (1ull << 32));
+    if (code_flips((uint32_t)old, (uint32_t)(old >> 32), cls, g)) mark_dirty(bitmap, cx, cy, g);
+}
+
+// GridMap.applyMeasurement GridMap.java:194-228 on integer counters.
 struct CellBox {
     int x0, y0, x1, y1;
 };
-__device__ __forceinline__ void apply_measurement(CellCounts* __restrict__ map, const Geometry& g, float sx,
-                                                  float sy, float ex, float ey, float meas, bool was_hit,
-                                                  CellBox& box) {
+__device__ __forceinline__ void apply_measurement(CellCounts* __restrict__ map, uint32_t* __restrict__ bitmap,
+                                                  const Geometry& g, float sx, float sy, float ex, float ey,
+                                                  float meas, bool was_hit, CellBox& box) {
     RayIter it;
     it.init(sx + 0.5f, sy + 0.5f, ex + 0.5f, ey + 0.5f, g.extra_steps);
     box.x0 = box.y0 = 0x7fffffff;
@@ -190,10 +234,7 @@ __device__ __forceinline__ void apply_measurement(CellCounts* __restrict__ map, 
         const float dY = sy - ((float)ly + 0.5f);
         const float dist = __fsqrt_rn(dX * dX + dY * dY);  // (float) Math.sqrt((double) f32) == sqrt.rn.f32
         const int cls = inverse_sensor_class(dist, meas, was_hit, g.tol_half);
-        if (cls != 0) {
-            uint32_t* p = reinterpret_cast<uint32_t*>(map + ((size_t)lx + (size_t)ly * g.W)) + (cls - 1);
-            atomicAdd(p, 1u);  // result unused -> RED.E.ADD
-        }
+        if (cls != 0) bump_cell(map, bitmap, lx, ly, cls, g);
         it.advance();
     }
     // the walk is monotone in x and in y: its bounding box is spanned by the first and last cell

@@ -48,9 +48,12 @@ struct gms_handle {
     CellCounts* counts = nullptr;
     double* lik = nullptr;
     double* fac = nullptr;  // shared map only: per-cell scoring factor (GridMap.java:284-288)
-    int4* rect = nullptr;
-    int4* tile_desc = nullptr;
-    int* tile_off = nullptr;
+    int4* rect = nullptr;        // explored bounding box per slot
+    uint32_t* dirty = nullptr;   // dirty-tile bitmap per slot
+    int* word_off = nullptr;
+    int2* tile_list = nullptr;
+    int tiles_per_map = 0;
+    int4* dup_rect = nullptr;
     int *dup_src = nullptr, *dup_dst = nullptr, *scratch2p = nullptr;
     // beams
     int bcap = 0;
@@ -195,7 +198,7 @@ void free_all(gms_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (int i = 0; i < 2; i++) { cudaFree(h->pose[i]); cudaFree(h->w[i]); cudaFree(h->lw[i]); cudaFree(h->slot[i]); }
     cudaFree(h->parents); cudaFree(h->cdf); cudaFree(h->counts); cudaFree(h->lik); cudaFree(h->fac); cudaFree(h->rect);
-    cudaFree(h->tile_desc); cudaFree(h->tile_off); cudaFree(h->dup_src); cudaFree(h->dup_dst); cudaFree(h->scratch2p);
+    cudaFree(h->dirty); cudaFree(h->word_off); cudaFree(h->tile_list); cudaFree(h->dup_rect); cudaFree(h->dup_src); cudaFree(h->dup_dst); cudaFree(h->scratch2p);
     cudaFree(h->in_xy); cudaFree(h->all_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
     cudaFree(h->all_hit); cudaFree(h->meas); cudaFree(h->d_normals); cudaFree(h->xlocal); cudaFree(h->xglobal);
     cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start); cudaFree(h->ray_maxlen);
@@ -276,15 +279,16 @@ int launch_pack(gms_handle* h, const double* d_xy, const double* d_dist, const u
 
 int launch_likelihood(gms_handle* h) {
     Phase ph(h, GMS_PHASE_LIKELIHOOD);
-    LAUNCH(GMS_PHASE_LIKELIHOOD,
-           k_lik_worklist<<<1, 1024, 0, h->stream>>>(h->rect, h->S, h->W, h->H, h->g.khalf, h->tile_desc,
-                                                      h->tile_off, h->st));
+    const int nwords = h->S * h->g.tile_words;
+    LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_scan<<<1, 1024, 0, h->stream>>>(h->dirty, nwords, h->word_off, h->st));
+    LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_emit<<<blocks_for(nwords, 256), 256, 0, h->stream>>>(
+                                     h->dirty, nwords, h->g.tile_words, h->word_off, h->tile_list));
     const int k = h->g.khalf, th = kTileH + 2 * k, tw = kTileW + 2 * k;
     const size_t smem = (size_t)th * kTileW * 8 + (size_t)th * tw * 4;
-    const long long max_tiles = (long long)h->S * ((h->W + kTileW - 1) / kTileW) * ((h->H + kTileH - 1) / kTileH);
+    const long long max_tiles = (long long)h->S * h->tiles_per_map;
     const unsigned grid = (unsigned)std::min<long long>(max_tiles, 148 * 6);
-    LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<<<grid, 256, smem, h->stream>>>(h->counts, h->lik, h->fac, h->tile_desc,
-                                                                               h->tile_off, h->S, h->st, h->g));
+    LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<<<grid, 256, smem, h->stream>>>(h->counts, h->lik, h->fac, h->tile_list,
+                                                                               h->st, h->g));
     return GMS_OK;
 }
 
@@ -318,15 +322,15 @@ int launch_map_update(gms_handle* h, const float4* pose, int lo, int cnt, const 
                                          h->ray_start, h->ray_maxlen, h->rect, h->g));
         LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_apply<<<148 * 4, 256, 0, h->stream>>>(
                                          h->ray_cells, Bpad, h->ray_count, h->ray_maxlen, h->ray_start, h->meas,
-                                         h->all_hit, h->counts, h->g));
+                                         h->all_hit, h->counts, h->dirty, h->g));
         LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_reset<<<1, 1, 0, h->stream>>>(h->ray_maxlen));
         return GMS_OK;
     }
     const long long total = shared ? (long long)B : (long long)cnt * B;
     LAUNCH(GMS_PHASE_MAP_UPDATE,
            k_map_update<<<blocks_for(total, 128), 128, 0, h->stream>>>(pose, lo, cnt, h->all_xy, h->meas, h->all_hit,
-                                                                       B, h->counts, slot, h->rect, h->st, shared,
-                                                                       h->g));
+                                                                       B, h->counts, slot, h->rect, h->dirty, h->st,
+                                                                       shared, h->g));
     return GMS_OK;
 }
 
@@ -397,14 +401,14 @@ int launch_resample(gms_handle* h, double u01) {
             return fail(h, GMS_ERR_UNSUPPORTED, "per-particle maps across ranks: use the migration entry points");
         Phase ph(h, GMS_PHASE_MAP_COPY);
         const int nxt = h->slot_cur ^ 1;
-        LAUNCH(GMS_PHASE_MAP_COPY, k_assign_slots<<<1, 1024, 0, h->stream>>>(h->parents, P, h->slot[h->slot_cur],
-                                                                              h->slot[nxt], h->dup_src, h->dup_dst,
-                                                                              h->scratch2p, h->st));
+        LAUNCH(GMS_PHASE_MAP_COPY, k_assign_slots<<<1, 1024, 0, h->stream>>>(
+                                       h->parents, P, h->slot[h->slot_cur], h->slot[nxt], h->dup_src, h->dup_dst,
+                                       h->dup_rect, h->rect, h->scratch2p, h->st, h->g));
         h->slot_cur = nxt;
-        const size_t bytes = h->cells * 16;
-        const int chunks = (int)std::max<size_t>(1, std::min<size_t>(1024, bytes / (64 * 1024)));
+        const int chunks = std::max(1, std::min(32, h->H / 16));
         LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps<<<(unsigned)((long long)chunks * P), 256, 0, h->stream>>>(
-                                       h->counts, h->lik, h->rect, h->dup_src, h->dup_dst, h->st, h->cells, chunks));
+                                       h->counts, h->lik, h->dirty, h->dup_src, h->dup_dst, h->dup_rect, h->st,
+                                       h->cells, h->W, h->g.tile_words, chunks));
     }
     return GMS_OK;
 }
@@ -477,8 +481,11 @@ int do_reset(gms_handle* h) {
     // likelihoodData = 0.0 until the first computeLikelihoodMap; the whole map is dirty.
     CK(cudaMemsetAsync(h->counts, 0, (size_t)h->S * h->cells * sizeof(CellCounts), h->stream));
     CK(cudaMemsetAsync(h->lik, 0, (size_t)h->S * h->cells * sizeof(double), h->stream));
+    // nothing explored yet; every tile needs its first likelihood build
     LAUNCH(GMS_PHASE_COUNT - 1, k_fill_rect<<<blocks_for(h->S, 256), 256, 0, h->stream>>>(
-                                    h->rect, h->S, make_int4(0, 0, h->W - 1, h->H - 1)));
+                                    h->rect, h->S, make_int4(0x7fffffff, 0x7fffffff, -1, -1)));
+    LAUNCH(GMS_PHASE_COUNT - 1, k_fill_dirty<<<blocks_for((long long)h->S * h->g.tile_words, 256), 256, 0, h->stream>>>(
+                                    h->dirty, h->S, h->g.tile_words, h->tiles_per_map));
     CK(cudaMemsetAsync(h->st, 0, sizeof(Stats), h->stream));
     h->cur = 0; h->slot_cur = 0;
     h->step = 0; h->resample_count = 0;
@@ -565,6 +572,10 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     g.res = (double)cfg->resolution; g.posx = (double)cfg->origin_x; g.posy = (double)cfg->origin_y;
     g.inv_res = 1.0 / g.res;
     g.half_margin = 0.5 - 1e-5;
+    g.tiles_x = (h->W + kTileW - 1) / kTileW;
+    g.tiles_y = (h->H + kTileH - 1) / kTileH;
+    g.tile_words = (g.tiles_x * g.tiles_y + 31) / 32;
+    h->tiles_per_map = g.tiles_x * g.tiles_y;
     g.z_hit = cfg->z_hit;
     g.uniform_term = 1.0 / (double)cfg->sensor_max_range;                          // GridMap.java:286
     g.random_term = (1 - cfg->z_hit) * 1.0 / (double)cfg->sensor_max_range;        // GridMap.java:288
@@ -606,8 +617,10 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->lik, (size_t)h->S * h->cells * sizeof(double)));
     if (cfg->map_mode == GMS_MAP_SHARED) CKC(cudaMalloc((void**)&h->fac, h->cells * sizeof(double)));
     CKC(cudaMalloc((void**)&h->rect, (size_t)h->S * sizeof(int4)));
-    CKC(cudaMalloc((void**)&h->tile_desc, (size_t)h->S * sizeof(int4)));
-    CKC(cudaMalloc((void**)&h->tile_off, ((size_t)h->S + 1) * 4));
+    CKC(cudaMalloc((void**)&h->dirty, (size_t)h->S * g.tile_words * 4));
+    CKC(cudaMalloc((void**)&h->word_off, (size_t)h->S * g.tile_words * 4));
+    CKC(cudaMalloc((void**)&h->tile_list, (size_t)h->S * h->tiles_per_map * sizeof(int2)));
+    CKC(cudaMalloc((void**)&h->dup_rect, P * sizeof(int4)));
     CKC(cudaMalloc((void**)&h->dup_src, P * 4));
     CKC(cudaMalloc((void**)&h->dup_dst, P * 4));
     CKC(cudaMalloc((void**)&h->scratch2p, 2 * P * 4));
@@ -841,6 +854,8 @@ EXPORT int gms_set_map_counts(gms_handle* h, int32_t particle, const uint32_t* n
     LAUNCH(GMS_PHASE_COUNT - 1, k_counts_join<<<blocks_for((long long)h->cells, 256), 256, 0, h->stream>>>(
                                     h->counts + (size_t)s * h->cells, tmp, tmp + h->cells, h->cells));
     LAUNCH(GMS_PHASE_COUNT - 1, k_fill_rect<<<1, 1, 0, h->stream>>>(h->rect + s, 1, make_int4(0, 0, h->W - 1, h->H - 1)));
+    LAUNCH(GMS_PHASE_COUNT - 1, k_fill_dirty<<<blocks_for(h->g.tile_words, 256), 256, 0, h->stream>>>(
+                                    h->dirty + (size_t)s * h->g.tile_words, 1, h->g.tile_words, h->tiles_per_map));
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }
@@ -852,8 +867,9 @@ EXPORT int gms_map_apply_measurement(gms_handle* h, int32_t particle, float sx, 
     int s;
     int rc = slot_of(h, particle, &s);
     if (rc) return rc;
-    LAUNCH(GMS_PHASE_MAP_UPDATE, k_apply_one<<<1, 1, 0, h->stream>>>(h->counts + (size_t)s * h->cells, h->rect + s, sx,
-                                                                     sy, ex, ey, meas, was_hit, h->g));
+    LAUNCH(GMS_PHASE_MAP_UPDATE, k_apply_one<<<1, 1, 0, h->stream>>>(
+                                     h->counts + (size_t)s * h->cells, h->rect + s,
+                                     h->dirty + (size_t)s * h->g.tile_words, sx, sy, ex, ey, meas, was_hit, h->g));
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }
@@ -886,21 +902,11 @@ EXPORT int gms_map_compute_likelihood(gms_handle* h, int32_t particle) {
     int s;
     int rc = slot_of(h, particle, &s);
     if (rc) return rc;
-    // the whole map of this slot (GridMap.computeLikelihoodMap has no notion of a dirty region);
-    // other slots keep whatever is pending for them: the work-list pass is per slot.
-    LAUNCH(GMS_PHASE_LIKELIHOOD, k_fill_rect<<<1, 1, 0, h->stream>>>(h->rect + s, 1, make_int4(0, 0, h->W - 1, h->H - 1)));
-    // run the work list on this slot only
-    {
-        Phase ph(h, GMS_PHASE_LIKELIHOOD);
-        LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_worklist<<<1, 1024, 0, h->stream>>>(h->rect + s, 1, h->W, h->H, h->g.khalf,
-                                                                                h->tile_desc, h->tile_off, h->st));
-        const int k = h->g.khalf, th = kTileH + 2 * k, tw = kTileW + 2 * k;
-        const size_t smem = (size_t)th * kTileW * 8 + (size_t)th * tw * 4;
-        LAUNCH(GMS_PHASE_LIKELIHOOD,
-               k_likelihood<<<148 * 6, 256, smem, h->stream>>>(h->counts + (size_t)s * h->cells,
-                                                               h->lik + (size_t)s * h->cells, h->fac, h->tile_desc,
-                                                               h->tile_off, 1, h->st, h->g));
-    }
+    // the whole map of this slot (GridMap.computeLikelihoodMap has no notion of dirty tiles); tiles
+    // pending on other slots are rebuilt by the same pass, which only brings them up to date earlier
+    LAUNCH(GMS_PHASE_LIKELIHOOD, k_fill_dirty<<<blocks_for(h->g.tile_words, 256), 256, 0, h->stream>>>(
+                                     h->dirty + (size_t)s * h->g.tile_words, 1, h->g.tile_words, h->tiles_per_map));
+    if ((rc = launch_likelihood(h))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }

@@ -4,7 +4,8 @@
 //   lw, w  f64[P]                    ln(product) of the last update / normalised weight
 //   counts CellCounts[S][H][W]       8 B per cell, row-major idx = x + y*W (GridMap.java:135)
 //   lik    f64[S][H][W]              likelihood field (GridMapData.likelihoodData)
-//   rect   int4[S]                   cells modified since the slot's last likelihood rebuild
+//   rect   int4[S]                   bounding box of every cell touched since reset ("explored")
+//   dirty  u32[S][tile_words]        bitmap of likelihood tiles whose thresholded codes changed
 #pragma once
 #include "device_math.cuh"
 
@@ -161,45 +162,44 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const unsigned* __restrict
 // log-odds within `khalf` cells, so an untouched neighbourhood reproduces itself bit for bit.
 // Same f64 operation order as Java (tap index ascending, mul then add, no FMA) => bit-exact.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTileW = 64, kTileH = 32;
-
-// One CTA: per-slot tile ranges + exclusive scan -> work list; resets the dirty rectangles.
-__global__ void __launch_bounds__(1024) k_lik_worklist(int4* __restrict__ rect, int S, int W, int H, int khalf,
-                                                       int4* __restrict__ tile_desc, int* __restrict__ tile_off,
-                                                       Stats* __restrict__ st) {
+// Work list: every set bit of the per-slot dirty-tile bitmaps becomes one {slot, tile} item.
+// k_lik_scan (one CTA): exclusive scan of the per-word popcounts.  k_lik_emit: expands and clears the words.
+__global__ void __launch_bounds__(1024) k_lik_scan(const uint32_t* __restrict__ dirty, int nwords,
+                                                   int* __restrict__ word_off, Stats* __restrict__ st) {
     __shared__ int s_part[1024];
     const int tid = threadIdx.x;
-    const int per = (S + 1023) / 1024;
-    const int s0 = tid * per, s1 = min(S, s0 + per);
+    const int per = (nwords + 1023) / 1024;
+    const int i0 = min(nwords, tid * per), i1 = min(nwords, i0 + per);
     int sum = 0;
-    for (int s = s0; s < s1; s++) {
-        int4 r = rect[s];
-        int4 d = make_int4(0, 0, 0, 0);
-        if (r.x <= r.z && r.y <= r.w) {
-            const int x0 = max(r.x - khalf, 0) / kTileW, x1 = min(r.z + khalf, W - 1) / kTileW;
-            const int y0 = max(r.y - khalf, 0) / kTileH, y1 = min(r.w + khalf, H - 1) / kTileH;
-            d = make_int4(x0, y0, x1 - x0 + 1, y1 - y0 + 1);
-        }
-        tile_desc[s] = d;
-        sum += d.z * d.w;
-        rect[s] = make_int4(0x7fffffff, 0x7fffffff, -1, -1);
-    }
+    for (int i = i0; i < i1; i++) sum += __popc(dirty[i]);
     s_part[tid] = sum;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
-        int v = tid >= o ? s_part[tid - o] : 0;
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = tid >= o ? s_part[tid - o] : 0;
         __syncthreads();
         s_part[tid] += v;
         __syncthreads();
     }
     int run = s_part[tid] - sum;
-    for (int s = s0; s < s1; s++) {
-        tile_off[s] = run;
-        run += tile_desc[s].z * tile_desc[s].w;
+    for (int i = i0; i < i1; i++) {
+        word_off[i] = run;
+        run += __popc(dirty[i]);
     }
-    if (tid == 1023) {
-        tile_off[S] = s_part[1023];
-        st->num_tiles = s_part[1023];
+    if (tid == 1023) st->num_tiles = s_part[1023];
+}
+__global__ void __launch_bounds__(256) k_lik_emit(uint32_t* __restrict__ dirty, int nwords, int tile_words,
+                                                  const int* __restrict__ word_off, int2* __restrict__ list) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    uint32_t w = dirty[i];
+    if (!w) return;
+    dirty[i] = 0u;
+    const int slot = i / tile_words, base = (i - slot * tile_words) * 32;
+    int o = word_off[i];
+    while (w) {
+        const int bit = __ffs(w) - 1;
+        w &= w - 1;
+        list[o++] = make_int2(slot, base + bit);
     }
 }
 
@@ -207,9 +207,8 @@ __global__ void __launch_bounds__(1024) k_lik_worklist(int4* __restrict__ rect, 
 // s_h[(TH+2k)][TW] f64 horizontal pass.
 __global__ void __launch_bounds__(256) k_likelihood(const CellCounts* __restrict__ counts,
                                                     double* __restrict__ lik, double* __restrict__ fac,
-                                                    const int4* __restrict__ tile_desc,
-                                                    const int* __restrict__ tile_off, int S,
-                                                    const Stats* __restrict__ st, Geometry g) {
+                                                    const int2* __restrict__ list, const Stats* __restrict__ st,
+                                                    Geometry g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int k = g.khalf;
     const int tw = kTileW + 2 * k, th = kTileH + 2 * k;
@@ -219,17 +218,10 @@ __global__ void __launch_bounds__(256) k_likelihood(const CellCounts* __restrict
     const int num_tiles = st->num_tiles;
     const size_t cells = (size_t)g.W * g.H;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        // slot of tile t: last s with tile_off[s] <= t
-        int lo = 0, hi = S - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (tile_off[mid] <= t) lo = mid; else hi = mid - 1;
-        }
-        const int4 d = tile_desc[lo];
-        const int r = t - tile_off[lo];
-        const int ox = (d.x + r % d.z) * kTileW, oy = (d.y + r / d.z) * kTileH;
-        const CellCounts* cmap = counts + (size_t)lo * cells;
-        double* out = lik + (size_t)lo * cells;
+        const int2 item = list[t];
+        const int ox = (item.y % g.tiles_x) * kTileW, oy = (item.y / g.tiles_x) * kTileH;
+        const CellCounts* cmap = counts + (size_t)item.x * cells;
+        double* out = lik + (size_t)item.x * cells;
         // 1. threshold the log-odds against logOdds(0.5) == 0.0 (GridMap.java:238-245); cells outside
         //    the map contribute 0 — Java skips those taps, and total + k*0.0 == total.
         for (int e = tid; e < th * tw; e += 256) {
@@ -238,8 +230,7 @@ __global__ void __launch_bounds__(256) k_likelihood(const CellCounts* __restrict
             float code = 0.0f;
             if (gx >= 0 && gx < g.W && gy >= 0 && gy < g.H) {
                 const CellCounts c = cmap[(size_t)gx + (size_t)gy * g.W];
-                const double v = (double)c.n_free * g.l_free + (double)c.n_occ * g.l_occ;
-                code = v > 0.0 ? 1.0f : (v < 0.0 ? 0.0f : 0.5f);
+                code = 0.5f * (float)cell_code(c.n_free, c.n_occ, g);
             }
             s_t[e] = code;
         }
@@ -460,8 +451,8 @@ __global__ void __launch_bounds__(128) k_map_update(const float4* __restrict__ p
                                                     const float* __restrict__ meas,
                                                     const uint8_t* __restrict__ hit, int B,
                                                     CellCounts* __restrict__ counts, const int* __restrict__ slot,
-                                                    int4* __restrict__ rect, const Stats* __restrict__ st,
-                                                    int shared, Geometry g) {
+                                                    int4* __restrict__ rect, uint32_t* __restrict__ dirty,
+                                                    const Stats* __restrict__ st, int shared, Geometry g) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = shared ? (long long)B : (long long)cnt * B;
     if (gid >= total) return;
@@ -476,7 +467,8 @@ __global__ void __launch_bounds__(128) k_map_update(const float4* __restrict__ p
     const float ex = (float)((t.tx(m.x, m.y) - g.posx) / g.res);
     const float ey = (float)((t.ty(m.x, m.y) - g.posy) / g.res);
     CellBox box;
-    apply_measurement(counts + (size_t)s * ((size_t)g.W * g.H), g, sx, sy, ex, ey, meas[b], hit[b] != 0, box);
+    apply_measurement(counts + (size_t)s * ((size_t)g.W * g.H), dirty + (size_t)s * g.tile_words, g, sx, sy, ex, ey,
+                      meas[b], hit[b] != 0, box);
     if (box.x1 >= 0) {
         int* r = reinterpret_cast<int*>(rect + s);
         atomicMin(r + 0, box.x0);
@@ -540,7 +532,8 @@ __global__ void __launch_bounds__(256) k_ray_apply(const uint32_t* __restrict__ 
                                                    const int* __restrict__ ray_count, int* __restrict__ ray_maxlen,
                                                    const float2* __restrict__ ray_start,
                                                    const float* __restrict__ meas, const uint8_t* __restrict__ hit,
-                                                   CellCounts* __restrict__ counts, Geometry g) {
+                                                   CellCounts* __restrict__ counts, uint32_t* __restrict__ dirty,
+                                                   Geometry g) {
     const int maxlen = *ray_maxlen;
     const long long total = (long long)maxlen * Bpad;
     const float2 s = *ray_start;
@@ -554,8 +547,7 @@ __global__ void __launch_bounds__(256) k_ray_apply(const uint32_t* __restrict__ 
         const float dY = s.y - ((float)cy + 0.5f);
         const float dist = __fsqrt_rn(dX * dX + dY * dY);
         const int cls = inverse_sensor_class(dist, meas[b], hit[b] != 0, g.tol_half);
-        if (cls != 0)
-            atomicAdd(reinterpret_cast<uint32_t*>(counts + ((size_t)cx + (size_t)cy * g.W)) + (cls - 1), 1u);
+        if (cls != 0) bump_cell(counts, dirty, cx, cy, cls, g);
     }
 }
 
@@ -563,10 +555,10 @@ __global__ void __launch_bounds__(256) k_ray_apply(const uint32_t* __restrict__ 
 __global__ void k_ray_reset(int* ray_maxlen) { *ray_maxlen = 0; }
 
 // single ray given in grid coordinates (gms_map_apply_measurement)
-__global__ void k_apply_one(CellCounts* __restrict__ counts, int4* __restrict__ rect, float sx, float sy,
-                            float ex, float ey, float meas, int was_hit, Geometry g) {
+__global__ void k_apply_one(CellCounts* __restrict__ counts, int4* __restrict__ rect, uint32_t* __restrict__ dirty,
+                            float sx, float sy, float ex, float ey, float meas, int was_hit, Geometry g) {
     CellBox box;
-    apply_measurement(counts, g, sx, sy, ex, ey, meas, was_hit != 0, box);
+    apply_measurement(counts, dirty, g, sx, sy, ex, ey, meas, was_hit != 0, box);
     if (box.x1 >= 0) {
         rect->x = min(rect->x, box.x0); rect->y = min(rect->y, box.y0);
         rect->z = max(rect->z, box.x1); rect->w = max(rect->w, box.y1);
@@ -931,7 +923,9 @@ __global__ void __launch_bounds__(256) k_gather(const int* __restrict__ parents,
 __global__ void __launch_bounds__(1024) k_assign_slots(const int* __restrict__ parents, int P,
                                                        const int* __restrict__ slot_in, int* __restrict__ slot_out,
                                                        int* __restrict__ dup_src, int* __restrict__ dup_dst,
-                                                       int* __restrict__ scratch /* 2P */, Stats* __restrict__ st) {
+                                                       int4* __restrict__ dup_rect, int4* __restrict__ rect,
+                                                       int* __restrict__ scratch /* 2P */, Stats* __restrict__ st,
+                                                       Geometry g) {
     __shared__ int s_a[1024], s_b[1024];
     const int tid = threadIdx.x;
     const int per = (P + 1023) / 1024;
@@ -964,10 +958,20 @@ __global__ void __launch_bounds__(1024) k_assign_slots(const int* __restrict__ p
     for (int m = i0; m < i1; m++) {
         const int p = parents[m];
         if (m > 0 && p == parents[m - 1]) {
-            const int d = free_slots[rd];
-            dup_src[rd] = slot_in[p];
+            const int d = free_slots[rd], sp = slot_in[p];
+            dup_src[rd] = sp;
             dup_dst[rd] = d;
             slot_out[m] = d;
+            // Outside the explored boxes both maps are blank (identical), so only the union of the two
+            // boxes (+ the blur half-width for the likelihood field) has to move; the child inherits
+            // the parent's box.  Source slots are never destinations (a parent with a child is not dead).
+            const int4 a = rect[sp], b = rect[d];
+            int4 r = make_int4(min(a.x, b.x), min(a.y, b.y), max(a.z, b.z), max(a.w, b.w));
+            if (r.x <= r.z && r.y <= r.w)
+                r = make_int4(max(r.x - g.khalf, 0), max(r.y - g.khalf, 0), min(r.z + g.khalf, g.W - 1),
+                              min(r.w + g.khalf, g.H - 1));
+            dup_rect[rd] = r;
+            rect[d] = a;
             rd++;
         } else {
             slot_out[m] = slot_in[p];
@@ -976,44 +980,64 @@ __global__ void __launch_bounds__(1024) k_assign_slots(const int* __restrict__ p
     if (tid == 1023) st->num_dup = s_a[1023];
 }
 
-// GridMap.createMapData(other) GridMap.java:118-124: both arrays of the parent are copied (+ the dirty
-// rectangle that travels with them).  grid = chunks_per_map * max_dups; CTAs beyond num_dup exit.
+// GridMap.createMapData(other) GridMap.java:118-124: both arrays of the parent are copied — restricted to
+// the rectangle k_assign_slots computed (identical result, see there) — plus the dirty-tile bitmap.
+// grid = chunks_per_map * max_dups; CTAs beyond num_dup exit.  Rows are moved as 16-byte vectors.
 __global__ void __launch_bounds__(256) k_copy_maps(CellCounts* __restrict__ counts, double* __restrict__ lik,
-                                                   int4* __restrict__ rect, const int* __restrict__ dup_src,
-                                                   const int* __restrict__ dup_dst, const Stats* __restrict__ st,
-                                                   size_t cells, int chunks_per_map) {
+                                                   uint32_t* __restrict__ dirty, const int* __restrict__ dup_src,
+                                                   const int* __restrict__ dup_dst, const int4* __restrict__ dup_rect,
+                                                   const Stats* __restrict__ st, size_t cells, int W, int tile_words,
+                                                   int chunks_per_map) {
     const int k = blockIdx.x / chunks_per_map;
     if (k >= st->num_dup) return;
     const int chunk = blockIdx.x - k * chunks_per_map;
     const int src = dup_src[k], dst = dup_dst[k];
+    if (chunk == 0)
+        for (int i = threadIdx.x; i < tile_words; i += 256)
+            dirty[(size_t)dst * tile_words + i] = dirty[(size_t)src * tile_words + i];
+    const int4 r = dup_rect[k];
+    if (r.x > r.z || r.y > r.w) return;
+    const int rows = r.w - r.y + 1;
+    const int per = (rows + chunks_per_map - 1) / chunks_per_map;
+    const int y0 = r.y + chunk * per, y1 = min(r.w + 1, y0 + per);
     const CellCounts* cs = counts + (size_t)src * cells;
     CellCounts* cd = counts + (size_t)dst * cells;
     const double* ls = lik + (size_t)src * cells;
     double* ld = lik + (size_t)dst * cells;
-    if ((cells & 1) == 0) {  // slot bases are 16-byte aligned: move 2 cells per access
-        const size_t n16 = cells / 2;
-        const size_t per = (n16 + chunks_per_map - 1) / chunks_per_map;
-        const size_t a = (size_t)chunk * per, b = min(n16, a + per);
-        const uint4* cs4 = reinterpret_cast<const uint4*>(cs);
-        uint4* cd4 = reinterpret_cast<uint4*>(cd);
-        const uint4* ls4 = reinterpret_cast<const uint4*>(ls);
-        uint4* ld4 = reinterpret_cast<uint4*>(ld);
-        for (size_t i = a + threadIdx.x; i < b; i += 256) {
-            cd4[i] = cs4[i];
-            ld4[i] = ls4[i];
+    if (((cells | (size_t)W) & 1) == 0) {  // even row length and slot size: rows start 16-byte aligned
+        const int x0 = r.x & ~1, n2 = ((r.z | 1) - x0 + 1) / 2;  // pairs of cells
+        for (int y = y0; y < y1; y++) {
+            const size_t o = ((size_t)y * W + x0) / 2;
+            const uint4* cs4 = reinterpret_cast<const uint4*>(cs) + o;
+            uint4* cd4 = reinterpret_cast<uint4*>(cd) + o;
+            const uint4* ls4 = reinterpret_cast<const uint4*>(ls) + o;
+            uint4* ld4 = reinterpret_cast<uint4*>(ld) + o;
+            for (int i = threadIdx.x; i < n2; i += 256) {
+                cd4[i] = cs4[i];
+                ld4[i] = ls4[i];
+            }
         }
     } else {
-        const size_t per = (cells + chunks_per_map - 1) / chunks_per_map;
-        const size_t a = (size_t)chunk * per, b = min(cells, a + per);
-        for (size_t i = a + threadIdx.x; i < b; i += 256) {
-            cd[i] = cs[i];
-            ld[i] = ls[i];
+        const int n = r.z - r.x + 1;
+        for (int y = y0; y < y1; y++) {
+            const size_t o = (size_t)y * W + r.x;
+            for (int i = threadIdx.x; i < n; i += 256) {
+                cd[o + i] = cs[o + i];
+                ld[o + i] = ls[o + i];
+            }
         }
     }
-    if (chunk == 0 && threadIdx.x == 0) rect[dst] = rect[src];
 }
 
 // ---- small utilities ----
+// mark every tile of `nslots` slots dirty (bits beyond the last tile stay clear)
+__global__ void k_fill_dirty(uint32_t* dirty, int nslots, int tile_words, int ntiles) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslots * tile_words) return;
+    const int wi = i % tile_words;
+    const int left = ntiles - wi * 32;
+    dirty[i] = left >= 32 ? 0xffffffffu : (left > 0 ? (1u << left) - 1u : 0u);
+}
 __global__ void k_fill_rect(int4* rect, int S, int4 v) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < S) rect[s] = v;
