@@ -96,6 +96,8 @@ SYMBOLS = {
     "gms_update_begin_dev": [_vp, _vp, _vp, _vp, _i32, _f64, _f64, _vp],
     "gms_update_end_dev": [_vp, _i32, _f64],
     "gms_read_neff": [_vp, _P(_f64)],
+    "gms_ipc_export": [_vp, _vp],
+    "gms_ipc_import": [_vp, _vp],
 }
 
 
@@ -304,6 +306,15 @@ class Handle:
         v = _f64()
         self._ck(self.dll.gms_read_neff(self.h, C.byref(v)))
         return v.value
+
+    def ipc_export(self) -> bytes:
+        buf = (C.c_ubyte * (4 * 64))()
+        self._ck(self.dll.gms_ipc_export(self.h, C.addressof(buf)))
+        return bytes(buf)
+
+    def ipc_import(self, all_handles: bytes):
+        buf = (C.c_ubyte * len(all_handles)).from_buffer_copy(all_handles)
+        self._ck(self.dll.gms_ipc_import(self.h, C.addressof(buf)))
 
     def sync(self):
         self._ck(self.dll.gms_sync(self.h))

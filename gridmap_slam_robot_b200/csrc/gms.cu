@@ -54,7 +54,11 @@ struct gms_handle {
     int2* tile_list = nullptr;
     int tiles_per_map = 0;
     int4* dup_rect = nullptr;
-    int *dup_src = nullptr, *dup_dst = nullptr, *scratch2p = nullptr;
+    int *dup_src = nullptr, *dup_dst = nullptr, *dup_src_rank = nullptr, *scratch2p = nullptr;
+    // per-particle maps across ranks: peer mappings of every rank's arenas (cudaIpc)
+    PeerTable peers{};
+    bool peers_ready = false;
+    void* ipc_opened[kMaxRanks][4] = {};
     // beams
     int bcap = 0;
     double2 *in_xy = nullptr, *all_xy = nullptr, *hit_xy = nullptr;
@@ -196,9 +200,12 @@ void free_all(gms_handle* h) {
     if (!h) return;
     cudaSetDevice(h->dev);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int q = 0; q < kMaxRanks; q++)
+        for (int k = 0; k < 4; k++)
+            if (h->ipc_opened[q][k]) cudaIpcCloseMemHandle(h->ipc_opened[q][k]);
     for (int i = 0; i < 2; i++) { cudaFree(h->pose[i]); cudaFree(h->w[i]); cudaFree(h->lw[i]); cudaFree(h->slot[i]); }
     cudaFree(h->parents); cudaFree(h->cdf); cudaFree(h->counts); cudaFree(h->lik); cudaFree(h->fac); cudaFree(h->rect);
-    cudaFree(h->dirty); cudaFree(h->word_off); cudaFree(h->tile_list); cudaFree(h->dup_rect); cudaFree(h->dup_src); cudaFree(h->dup_dst); cudaFree(h->scratch2p);
+    cudaFree(h->dirty); cudaFree(h->word_off); cudaFree(h->tile_list); cudaFree(h->dup_rect); cudaFree(h->dup_src_rank); cudaFree(h->dup_src); cudaFree(h->dup_dst); cudaFree(h->scratch2p);
     cudaFree(h->in_xy); cudaFree(h->all_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
     cudaFree(h->all_hit); cudaFree(h->meas); cudaFree(h->d_normals); cudaFree(h->xlocal); cudaFree(h->xglobal);
     cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start); cudaFree(h->ray_maxlen);
@@ -283,12 +290,16 @@ int launch_likelihood(gms_handle* h) {
     LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_scan<<<1, 1024, 0, h->stream>>>(h->dirty, nwords, h->word_off, h->st));
     LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_emit<<<blocks_for(nwords, 256), 256, 0, h->stream>>>(
                                      h->dirty, nwords, h->g.tile_words, h->word_off, h->tile_list));
-    const int k = h->g.khalf, th = kTileH + 2 * k, tw = kTileW + 2 * k;
+    const int k = h->g.khalf, th = kTileH + 2 * k, tw = (kTileW + 2 * k + 3) & ~3;
     const size_t smem = (size_t)th * kTileW * 8 + (size_t)th * tw * 4;
     const long long max_tiles = (long long)h->S * h->tiles_per_map;
     const unsigned grid = (unsigned)std::min<long long>(max_tiles, 148 * 6);
-    LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<<<grid, 256, smem, h->stream>>>(h->counts, h->lik, h->fac, h->tile_list,
-                                                                               h->st, h->g));
+    if (k == 3)
+        LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<3><<<grid, 256, smem, h->stream>>>(h->counts, h->lik, h->fac,
+                                                                                      h->tile_list, h->st, h->g));
+    else
+        LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<0><<<grid, 256, smem, h->stream>>>(h->counts, h->lik, h->fac,
+                                                                                      h->tile_list, h->st, h->g));
     return GMS_OK;
 }
 
@@ -358,12 +369,12 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
     rc = launch_likelihood(h);
     if (rc) return rc;
     const bool shared = c.map_mode == GMS_MAP_SHARED;
-    rc = launch_score(h, h->pose[h->cur], h->lo, h->cnt, shared ? nullptr : h->slot[h->slot_cur], h->lw[h->cur],
+    rc = launch_score(h, h->pose[h->cur], h->lo, h->cnt, shared ? nullptr : h->slot[h->slot_cur] + h->lo, h->lw[h->cur],
                       c.nranks > 1 ? h->xlocal : nullptr, B, use_sorted_score(h));
     if (rc) return rc;
     const bool skip = std::fabs(d_theta) > (M_PI / 180.0) * c.skip_update_deg;  // SLAM.java:82
     if (!shared && !skip) {
-        rc = launch_map_update(h, h->pose[h->cur], h->lo, h->cnt, h->slot[h->slot_cur], B, 0);
+        rc = launch_map_update(h, h->pose[h->cur], h->lo, h->cnt, h->slot[h->slot_cur] + h->lo, B, 0);
         if (rc) return rc;
     }
     h->pending = true;
@@ -396,9 +407,25 @@ int launch_resample(gms_handle* h, double u01) {
         h->tile_fx_valid = false;
     }
     h->resample_count++;
+    if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE && h->cfg.nranks > 1) {
+        if (!h->peers_ready)
+            return fail(h, GMS_ERR_STATE, "per-particle maps across ranks: call gms_ipc_import before resampling");
+        Phase ph(h, GMS_PHASE_MAP_COPY);
+        const int nxt = h->slot_cur ^ 1;
+        LAUNCH(GMS_PHASE_MAP_COPY, k_assign_slots_mr<<<1, 1024, 0, h->stream>>>(
+                                       h->parents, P, h->cnt, h->cfg.nranks, h->S, h->cfg.rank, h->slot[h->slot_cur],
+                                       h->slot[nxt], h->dup_src_rank, h->dup_src, h->dup_dst, h->scratch2p, h->st));
+        h->slot_cur = nxt;
+        LAUNCH(GMS_PHASE_MAP_COPY, k_job_rects<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(
+                                       h->dup_src_rank, h->dup_src, h->dup_dst, h->dup_rect, h->rect, h->st, h->peers,
+                                       h->g));
+        const int chunks = std::max(1, std::min(32, h->H / 16));
+        LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps<<<(unsigned)((long long)chunks * h->cnt), 256, 0, h->stream>>>(
+                                       h->counts, h->lik, h->dirty, h->dup_src, h->dup_dst, h->dup_rect, h->st,
+                                       h->cells, h->W, h->g.tile_words, chunks, h->dup_src_rank, h->peers));
+        return GMS_OK;
+    }
     if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE) {
-        if (h->cfg.nranks != 1)
-            return fail(h, GMS_ERR_UNSUPPORTED, "per-particle maps across ranks: use the migration entry points");
         Phase ph(h, GMS_PHASE_MAP_COPY);
         const int nxt = h->slot_cur ^ 1;
         LAUNCH(GMS_PHASE_MAP_COPY, k_assign_slots<<<1, 1024, 0, h->stream>>>(
@@ -408,7 +435,7 @@ int launch_resample(gms_handle* h, double u01) {
         const int chunks = std::max(1, std::min(32, h->H / 16));
         LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps<<<(unsigned)((long long)chunks * P), 256, 0, h->stream>>>(
                                        h->counts, h->lik, h->dirty, h->dup_src, h->dup_dst, h->dup_rect, h->st,
-                                       h->cells, h->W, h->g.tile_words, chunks));
+                                       h->cells, h->W, h->g.tile_words, chunks, nullptr, h->peers));
     }
     return GMS_OK;
 }
@@ -446,7 +473,7 @@ int slot_of(gms_handle* h, int particle, int* slot) {
     if (h->cfg.map_mode == GMS_MAP_SHARED) { *slot = 0; return GMS_OK; }
     if (particle < h->lo || particle >= h->lo + h->cnt)
         return fail(h, GMS_ERR_INVALID_ARG, "particle index is not held by this handle");
-    CK(cudaMemcpyAsync(slot, h->slot[h->slot_cur] + (particle - h->lo), sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(slot, h->slot[h->slot_cur] + particle, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }
@@ -476,7 +503,7 @@ int do_reset(gms_handle* h) {
                                                                                                h->lw[i], h->parents, P));
     if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE)
         for (int i = 0; i < 2; i++)
-            LAUNCH(GMS_PHASE_COUNT - 1, k_iota<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(h->slot[i], h->cnt));
+            LAUNCH(GMS_PHASE_COUNT - 1, k_iota_mod<<<blocks_for(h->P, 256), 256, 0, h->stream>>>(h->slot[i], h->P, h->cnt));
     // GridMap.createMapData(null) GridMap.java:106-117: logData = logOdds(0.5) = 0.0 (no counts),
     // likelihoodData = 0.0 until the first computeLikelihoodMap; the whole map is dirty.
     CK(cudaMemsetAsync(h->counts, 0, (size_t)h->S * h->cells * sizeof(CellCounts), h->stream));
@@ -535,6 +562,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     if (!cfg || !out) return fail(nullptr, GMS_ERR_INVALID_ARG, "gms_create: NULL argument");
     if (cfg->struct_size != sizeof(gms_config))
         return fail(nullptr, GMS_ERR_INVALID_ARG, "gms_create: gms_config.struct_size mismatch");
+    if (cfg->nranks > kMaxRanks) return fail(nullptr, GMS_ERR_INVALID_ARG, "gms_create: at most 16 ranks");
     if (cfg->num_particles < 1 || !(cfg->resolution > 0) || !(cfg->map_width_m > 0) || !(cfg->map_height_m > 0) ||
         cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks || cfg->extra_steps < 0 ||
         (cfg->map_mode != GMS_MAP_PER_PARTICLE && cfg->map_mode != GMS_MAP_SHARED) || cfg->resample_mode < 0 ||
@@ -585,7 +613,9 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     h->P = cfg->num_particles;
     h->cnt = h->P / cfg->nranks;
     h->lo = cfg->rank * h->cnt;
-    h->S = cfg->map_mode == GMS_MAP_SHARED ? 1 : h->cnt;
+    // per-particle maps across ranks keep cnt spare slots so that a resampling exchange never writes a slot
+    // of the old generation (other ranks may still be pulling from it)
+    h->S = cfg->map_mode == GMS_MAP_SHARED ? 1 : (cfg->nranks > 1 ? 2 * h->cnt : h->cnt);
     h->cells = (size_t)h->W * h->H;
     h->resample_mode = cfg->resample_mode == GMS_RESAMPLE_AUTO
                            ? (h->P <= 2048 ? GMS_RESAMPLE_LITERAL : GMS_RESAMPLE_FIXED)
@@ -609,7 +639,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
         CKC(cudaMalloc((void**)&h->pose[i], P * sizeof(float4)));
         CKC(cudaMalloc((void**)&h->w[i], P * 8));
         CKC(cudaMalloc((void**)&h->lw[i], P * 8));
-        CKC(cudaMalloc((void**)&h->slot[i], (size_t)h->cnt * 4));
+        CKC(cudaMalloc((void**)&h->slot[i], P * 4));  // global table: particle m -> slot in its rank's arena
     }
     CKC(cudaMalloc((void**)&h->parents, P * 4));
     CKC(cudaMalloc((void**)&h->cdf, P * 8));
@@ -623,7 +653,8 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->dup_rect, P * sizeof(int4)));
     CKC(cudaMalloc((void**)&h->dup_src, P * 4));
     CKC(cudaMalloc((void**)&h->dup_dst, P * 4));
-    CKC(cudaMalloc((void**)&h->scratch2p, 2 * P * 4));
+    CKC(cudaMalloc((void**)&h->dup_src_rank, P * 4));
+    CKC(cudaMalloc((void**)&h->scratch2p, std::max(2 * P, (size_t)2 * cfg->nranks * h->S) * 4));
     CKC(cudaMalloc((void**)&h->d_normals, (size_t)h->cnt * 16));
     CKC(cudaMalloc((void**)&h->xlocal, (size_t)h->cnt * sizeof(ExchangeRec)));
     CKC(cudaMalloc((void**)&h->xglobal, P * sizeof(ExchangeRec)));
@@ -659,7 +690,8 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMallocHost((void**)&h->h_st, sizeof(Stats)));
     CKC(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CKC(cudaFuncSetAttribute(k_score_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CKC(cudaFuncSetAttribute(k_likelihood, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CKC(cudaFuncSetAttribute(k_likelihood<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CKC(cudaFuncSetAttribute(k_likelihood<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     int rc = ensure_beams(h, 1024);
     if (rc) return bail(rc);
     rc = ensure_stage(h, 1 << 20);
@@ -980,8 +1012,6 @@ EXPORT int gms_update_begin_dev(gms_handle* h, const double* d_xy, const double*
                                 int32_t B, double d_center, double d_theta, const double* d_normals) {
     ENTER(h);
     if (B < 0 || (B > 0 && (!d_xy || !d_dist || !d_hit))) return fail(h, GMS_ERR_INVALID_ARG, "bad beam arrays");
-    if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE && h->cfg.nranks != 1)
-        return fail(h, GMS_ERR_UNSUPPORTED, "per-particle maps across ranks are not implemented yet");
     return step_begin(h, d_xy, d_dist, d_hit, B, d_center, d_theta, d_normals);
 }
 EXPORT int gms_update_end_dev(gms_handle* h, int32_t policy, double u01) {
@@ -1051,5 +1081,38 @@ EXPORT int gms_profile_reset(gms_handle* h) {
 EXPORT int gms_launch_count(gms_handle* h, int64_t* n) {
     if (!h || !n) return GMS_ERR_INVALID_ARG;
     *n = h->launches;
+    return GMS_OK;
+}
+
+// ---- per-particle maps across ranks: peer mappings (one process per GPU on one node) ----------------
+EXPORT int gms_ipc_export(gms_handle* h, void* handles) {
+    ENTER(h);
+    if (!handles) return GMS_ERR_INVALID_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == GMS_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    cudaIpcMemHandle_t* out = static_cast<cudaIpcMemHandle_t*>(handles);
+    CK(cudaIpcGetMemHandle(&out[0], h->counts));
+    CK(cudaIpcGetMemHandle(&out[1], h->lik));
+    CK(cudaIpcGetMemHandle(&out[2], h->rect));
+    CK(cudaIpcGetMemHandle(&out[3], h->dirty));
+    return GMS_OK;
+}
+EXPORT int gms_ipc_import(gms_handle* h, const void* all_handles) {
+    ENTER(h);
+    if (!all_handles) return GMS_ERR_INVALID_ARG;
+    const cudaIpcMemHandle_t* in = static_cast<const cudaIpcMemHandle_t*>(all_handles);
+    for (int q = 0; q < h->cfg.nranks; q++) {
+        void* ptr[4] = {h->counts, h->lik, h->rect, h->dirty};
+        if (q != h->cfg.rank)
+            for (int k = 0; k < 4; k++) {
+                if (h->ipc_opened[q][k]) { ptr[k] = h->ipc_opened[q][k]; continue; }
+                CK(cudaIpcOpenMemHandle(&ptr[k], in[q * GMS_IPC_NUM_HANDLES + k], cudaIpcMemLazyEnablePeerAccess));
+                h->ipc_opened[q][k] = ptr[k];
+            }
+        h->peers.counts[q] = static_cast<const CellCounts*>(ptr[0]);
+        h->peers.lik[q] = static_cast<const double*>(ptr[1]);
+        h->peers.rect[q] = static_cast<const int4*>(ptr[2]);
+        h->peers.dirty[q] = static_cast<const uint32_t*>(ptr[3]);
+    }
+    h->peers_ready = true;
     return GMS_OK;
 }

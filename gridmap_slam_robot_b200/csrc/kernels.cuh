@@ -33,6 +33,14 @@ struct ExchangeRec {  // 24 B, gms.h "Exchange record"
     uint32_t pad;
 };
 
+constexpr int kMaxRanks = 16;
+struct PeerTable {  // per-particle maps across ranks: every rank's arenas, mapped into this process (cudaIpc)
+    const CellCounts* counts[kMaxRanks];
+    const double* lik[kMaxRanks];
+    const int4* rect[kMaxRanks];
+    const uint32_t* dirty[kMaxRanks];
+};
+
 // ------------------------------------------------------------------------------------------------
 // beam table: compaction of the hit beams (scoring reads only those, GridMap.java:269-270) and the
 // per-beam measured distance in cells, (float) m.distance / resolution (GridMap.java:188).
@@ -203,20 +211,36 @@ __global__ void __launch_bounds__(256) k_lik_emit(uint32_t* __restrict__ dirty, 
     }
 }
 
-// Persistent CTAs walk the work list.  smem: s_t[(TH+2k)][TW+2k] f32 codes {0, .5, 1} (exact in f32),
-// s_h[(TH+2k)][TW] f64 horizontal pass.
+// Thresholded code {0, 1, 2} = {free, unknown, occupied}; the two cheap branches agree with cell_code().
+__device__ __forceinline__ int cell_code_fast(const CellCounts c, const Geometry& g) {
+    if (c.n_occ == 0) return c.n_free ? 0 : 1;
+    if (c.n_free == 0) return 2;
+    return cell_code(c.n_free, c.n_occ, g);
+}
+
+// Persistent CTAs walk the work list; one 64x32-cell tile per iteration.
+//   smem s_t[(TH+2k)][tw_pad] f32 codes {0, .5, 1} (exact in f32), s_h[(TH+2k)][TW] f64 horizontal pass.
+// KH = 3 (the reference's 0.05 m cells: 7 taps) is register-blocked: a thread produces 8 neighbouring
+// outputs of a pass from 14 inputs held in registers, taps fully unrolled, eight independent f64
+// accumulation chains (each in Java's order: tap index ascending, multiply then add, no FMA).
+// KH = 0 is the generic run-time-width version.
+template <int KH>
 __global__ void __launch_bounds__(256) k_likelihood(const CellCounts* __restrict__ counts,
                                                     double* __restrict__ lik, double* __restrict__ fac,
                                                     const int2* __restrict__ list, const Stats* __restrict__ st,
                                                     Geometry g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int k = g.khalf;
-    const int tw = kTileW + 2 * k, th = kTileH + 2 * k;
+    const int k = KH ? KH : g.khalf;
+    const int tw = KH ? ((kTileW + 2 * KH + 3) & ~3) : kTileW + 2 * k;  // KH: rows padded to 16 bytes
+    const int th = kTileH + 2 * k;
     double* s_h = reinterpret_cast<double*>(smem_raw);               // th * kTileW
     float* s_t = reinterpret_cast<float*>(s_h + th * kTileW);        // th * tw
     const int tid = threadIdx.x;
     const int num_tiles = st->num_tiles;
     const size_t cells = (size_t)g.W * g.H;
+    double kr[2 * KH + 1];
+#pragma unroll
+    for (int i = 0; i < 2 * KH + 1; i++) kr[i] = g.kernel[i];
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int2 item = list[t];
         const int ox = (item.y % g.tiles_x) * kTileW, oy = (item.y / g.tiles_x) * kTileH;
@@ -224,38 +248,79 @@ __global__ void __launch_bounds__(256) k_likelihood(const CellCounts* __restrict
         double* out = lik + (size_t)item.x * cells;
         // 1. threshold the log-odds against logOdds(0.5) == 0.0 (GridMap.java:238-245); cells outside
         //    the map contribute 0 — Java skips those taps, and total + k*0.0 == total.
-        for (int e = tid; e < th * tw; e += 256) {
-            const int ly = e / tw, lx = e - ly * tw;
+        const int twu = kTileW + 2 * k;  // used columns
+        for (int e = tid; e < th * twu; e += 256) {
+            const int ly = e / twu, lx = e - ly * twu;
             const int gx = ox + lx - k, gy = oy + ly - k;
             float code = 0.0f;
-            if (gx >= 0 && gx < g.W && gy >= 0 && gy < g.H) {
-                const CellCounts c = cmap[(size_t)gx + (size_t)gy * g.W];
-                code = 0.5f * (float)cell_code(c.n_free, c.n_occ, g);
+            if (gx >= 0 && gx < g.W && gy >= 0 && gy < g.H)
+                code = 0.5f * (float)cell_code_fast(cmap[(size_t)gx + (size_t)gy * g.W], g);
+            s_t[ly * tw + lx] = code;
+        }
+        __syncthreads();
+        if (KH) {
+            // 2. horizontal pass (Util.java:387-403): item = (row, 8-column segment)
+            for (int it = tid; it < th * (kTileW / 8); it += 256) {
+                const int ly = it / (kTileW / 8), x0 = (it - ly * (kTileW / 8)) * 8;
+                const float4* row4 = reinterpret_cast<const float4*>(s_t + ly * tw + x0);
+                double c[16];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float4 v = row4[q];
+                    c[4 * q] = (double)v.x; c[4 * q + 1] = (double)v.y; c[4 * q + 2] = (double)v.z; c[4 * q + 3] = (double)v.w;
+                }
+                double* dst = s_h + ly * kTileW + x0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    double total = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 2 * KH + 1; i++) total += kr[i] * c[j + i];
+                    dst[j] = total;
+                }
             }
-            s_t[e] = code;
-        }
-        __syncthreads();
-        // 2. horizontal pass (Util.java:387-403)
-        for (int e = tid; e < th * kTileW; e += 256) {
-            const int ly = e / kTileW, lx = e - ly * kTileW;
-            const float* row = s_t + ly * tw + lx;
-            double total = 0.0;
-            for (int i = 0; i < g.ktaps; i++) total += g.kernel[i] * (double)row[i];
-            s_h[e] = total;
-        }
-        __syncthreads();
-        // 3. vertical pass (Util.java:409-424)
-        for (int e = tid; e < kTileH * kTileW; e += 256) {
-            const int ly = e / kTileW, lx = e - ly * kTileW;
-            const int gx = ox + lx, gy = oy + ly;
-            if (gx < g.W && gy < g.H) {
-                const double* col = s_h + ly * kTileW + lx;
+            __syncthreads();
+            // 3. vertical pass (Util.java:409-424): thread = (column, group of 8 rows)
+            {
+                const int lx = tid & (kTileW - 1), y0 = (tid / kTileW) * 8;
+                const int gx = ox + lx;
+                double hcol[8 + 2 * KH];
+#pragma unroll
+                for (int i = 0; i < 8 + 2 * KH; i++) hcol[i] = s_h[(y0 + i) * kTileW + lx];
+                if (gx < g.W) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int gy = oy + y0 + j;
+                        double total = 0.0;
+#pragma unroll
+                        for (int i = 0; i < 2 * KH + 1; i++) total += kr[i] * hcol[j + i];
+                        if (gy < g.H) {
+                            out[(size_t)gx + (size_t)gy * g.W] = total;
+                            // shared map: the per-lookup factor of GridMap.probabilityOf (GridMap.java:284-288)
+                            // is a pure function of the cell: evaluated once per cell here, not per lookup
+                            if (fac) fac[(size_t)gx + (size_t)gy * g.W] = total == 0.5 ? g.uniform_term : g.z_hit * total + g.random_term;
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int e = tid; e < th * kTileW; e += 256) {
+                const int ly = e / kTileW, lx = e - ly * kTileW;
+                const float* row = s_t + ly * tw + lx;
                 double total = 0.0;
-                for (int i = 0; i < g.ktaps; i++) total += g.kernel[i] * col[i * kTileW];
-                out[(size_t)gx + (size_t)gy * g.W] = total;
-                // shared map: the per-lookup factor of GridMap.probabilityOf (GridMap.java:284-288) is a
-                // pure function of the cell, so it is evaluated once per cell here, not once per lookup
-                if (fac) fac[(size_t)gx + (size_t)gy * g.W] = total == 0.5 ? g.uniform_term : g.z_hit * total + g.random_term;
+                for (int i = 0; i < g.ktaps; i++) total += g.kernel[i] * (double)row[i];
+                s_h[e] = total;
+            }
+            __syncthreads();
+            for (int e = tid; e < kTileH * kTileW; e += 256) {
+                const int ly = e / kTileW, lx = e - ly * kTileW;
+                const int gx = ox + lx, gy = oy + ly;
+                if (gx < g.W && gy < g.H) {
+                    const double* col = s_h + ly * kTileW + lx;
+                    double total = 0.0;
+                    for (int i = 0; i < g.ktaps; i++) total += g.kernel[i] * col[i * kTileW];
+                    out[(size_t)gx + (size_t)gy * g.W] = total;
+                    if (fac) fac[(size_t)gx + (size_t)gy * g.W] = total == 0.5 ? g.uniform_term : g.z_hit * total + g.random_term;
+                }
             }
         }
         __syncthreads();
@@ -980,29 +1045,134 @@ __global__ void __launch_bounds__(1024) k_assign_slots(const int* __restrict__ p
     if (tid == 1023) st->num_dup = s_a[1023];
 }
 
+// Per-particle maps sharded over R ranks.  Particle m lives on rank m / cnt, in slot
+// gslot[m] of that rank's arena of S = 2*cnt slots.  Every rank runs this kernel on the same inputs and
+// obtains the same global table; it records copy jobs only for its own particles.
+//   keep : the first child that a parent has ON ITS OWN RANK stays in the parent's slot (no copy)
+//   need : every other child takes, in order, a slot of its rank that the OLD generation does not occupy
+//          (there are >= cnt of those), and is filled by a local copy or a pull from the parent's rank.
+// No slot of the old generation is written during the exchange, so concurrent pulls by other ranks read
+// consistent maps; the caller's barrier after the pulls releases the old slots.
+__device__ __forceinline__ int block_excl_scan_1024(int v, int* s_buf, int* total) {
+    const int tid = threadIdx.x;
+    __syncthreads();
+    s_buf[tid] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int u = tid >= o ? s_buf[tid - o] : 0;
+        __syncthreads();
+        s_buf[tid] += u;
+        __syncthreads();
+    }
+    if (total) *total = s_buf[1023];
+    return s_buf[tid] - v;
+}
+
+__global__ void __launch_bounds__(1024) k_assign_slots_mr(const int* __restrict__ parents, int P, int cnt, int R, int S,
+                                                          int myrank, const int* __restrict__ gslot_in,
+                                                          int* __restrict__ gslot_out, int* __restrict__ job_src_rank,
+                                                          int* __restrict__ job_src_slot, int* __restrict__ job_dst,
+                                                          int* __restrict__ scratch /* 2*R*S */, Stats* __restrict__ st) {
+    __shared__ int s_buf[1024];
+    const int tid = threadIdx.x;
+    int* occ = scratch;
+    int* freelist = scratch + R * S;
+    for (int i = tid; i < R * S; i += 1024) occ[i] = 0;
+    __syncthreads();
+    for (int p = tid; p < P; p += 1024) occ[(p / cnt) * S + gslot_in[p]] = 1;
+    __syncthreads();
+    for (int q = 0; q < R; q++) {
+        const int per_s = (S + 1023) / 1024;
+        const int s0 = min(S, tid * per_s), s1 = min(S, s0 + per_s);
+        int nf = 0;
+        for (int x = s0; x < s1; x++) nf += occ[q * S + x] ? 0 : 1;
+        int rf = block_excl_scan_1024(nf, s_buf, nullptr);
+        for (int x = s0; x < s1; x++)
+            if (!occ[q * S + x]) freelist[q * S + rf++] = x;
+        const int per_m = (cnt + 1023) / 1024;
+        const int m0 = q * cnt + min(cnt, tid * per_m), m1 = min((q + 1) * cnt, m0 + per_m);
+        int nn = 0;
+        for (int m = m0; m < m1; m++) {
+            const int p = parents[m];
+            const bool keep = (p / cnt == q) && (m == q * cnt || parents[m - 1] != p);
+            nn += keep ? 0 : 1;
+        }
+        int total = 0;
+        int rn = block_excl_scan_1024(nn, s_buf, &total);  // also orders the freelist writes before the reads
+        for (int m = m0; m < m1; m++) {
+            const int p = parents[m];
+            const bool keep = (p / cnt == q) && (m == q * cnt || parents[m - 1] != p);
+            if (keep) {
+                gslot_out[m] = gslot_in[p];
+            } else {
+                const int d = freelist[q * S + rn];
+                gslot_out[m] = d;
+                if (q == myrank) {
+                    job_src_rank[rn] = p / cnt;
+                    job_src_slot[rn] = gslot_in[p];
+                    job_dst[rn] = d;
+                }
+                rn++;
+            }
+        }
+        if (q == myrank && tid == 0) st->num_dup = total;
+    }
+}
+
+// copy rectangle of every job (union of the two explored boxes + blur half-width); the child inherits the
+// parent's box.  The parent's box is read from the parent's rank.
+__global__ void __launch_bounds__(256) k_job_rects(const int* __restrict__ job_src_rank,
+                                                   const int* __restrict__ job_src_slot,
+                                                   const int* __restrict__ job_dst, int4* __restrict__ job_rect,
+                                                   int4* __restrict__ rect, const Stats* __restrict__ st,
+                                                   PeerTable peers, Geometry g) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= st->num_dup) return;
+    const int4 a = peers.rect[job_src_rank[k]][job_src_slot[k]];
+    const int d = job_dst[k];
+    const int4 b = rect[d];
+    int4 r = make_int4(min(a.x, b.x), min(a.y, b.y), max(a.z, b.z), max(a.w, b.w));
+    if (r.x <= r.z && r.y <= r.w)
+        r = make_int4(max(r.x - g.khalf, 0), max(r.y - g.khalf, 0), min(r.z + g.khalf, g.W - 1), min(r.w + g.khalf, g.H - 1));
+    job_rect[k] = r;
+    rect[d] = a;
+}
+
 // GridMap.createMapData(other) GridMap.java:118-124: both arrays of the parent are copied — restricted to
 // the rectangle k_assign_slots computed (identical result, see there) — plus the dirty-tile bitmap.
 // grid = chunks_per_map * max_dups; CTAs beyond num_dup exit.  Rows are moved as 16-byte vectors.
+// With `dup_src_rank` the source slot lives in another rank's arena: the same kernel then PULLS the rows
+// over NVLink through the peer mappings of PeerTable (cudaIpc), one 16-byte load per lane.
 __global__ void __launch_bounds__(256) k_copy_maps(CellCounts* __restrict__ counts, double* __restrict__ lik,
                                                    uint32_t* __restrict__ dirty, const int* __restrict__ dup_src,
                                                    const int* __restrict__ dup_dst, const int4* __restrict__ dup_rect,
                                                    const Stats* __restrict__ st, size_t cells, int W, int tile_words,
-                                                   int chunks_per_map) {
+                                                   int chunks_per_map, const int* __restrict__ dup_src_rank,
+                                                   PeerTable peers) {
     const int k = blockIdx.x / chunks_per_map;
     if (k >= st->num_dup) return;
     const int chunk = blockIdx.x - k * chunks_per_map;
     const int src = dup_src[k], dst = dup_dst[k];
+    const CellCounts* src_counts = counts;
+    const double* src_lik = lik;
+    const uint32_t* src_dirty = dirty;
+    if (dup_src_rank) {
+        const int q = dup_src_rank[k];
+        src_counts = peers.counts[q];
+        src_lik = peers.lik[q];
+        src_dirty = peers.dirty[q];
+    }
     if (chunk == 0)
         for (int i = threadIdx.x; i < tile_words; i += 256)
-            dirty[(size_t)dst * tile_words + i] = dirty[(size_t)src * tile_words + i];
+            dirty[(size_t)dst * tile_words + i] = src_dirty[(size_t)src * tile_words + i];
     const int4 r = dup_rect[k];
     if (r.x > r.z || r.y > r.w) return;
     const int rows = r.w - r.y + 1;
     const int per = (rows + chunks_per_map - 1) / chunks_per_map;
     const int y0 = r.y + chunk * per, y1 = min(r.w + 1, y0 + per);
-    const CellCounts* cs = counts + (size_t)src * cells;
+    const CellCounts* cs = src_counts + (size_t)src * cells;
     CellCounts* cd = counts + (size_t)dst * cells;
-    const double* ls = lik + (size_t)src * cells;
+    const double* ls = src_lik + (size_t)src * cells;
     double* ld = lik + (size_t)dst * cells;
     if (((cells | (size_t)W) & 1) == 0) {  // even row length and slot size: rows start 16-byte aligned
         const int x0 = r.x & ~1, n2 = ((r.z | 1) - x0 + 1) / 2;  // pairs of cells
@@ -1050,9 +1220,9 @@ __global__ void k_init_particles(float4* pose, double* w, double* lw, int* paren
     lw[i] = 0.0;
     parents[i] = i;
 }
-__global__ void k_iota(int* a, int n) {
+__global__ void k_iota_mod(int* a, int n, int mod) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) a[i] = i;
+    if (i < n) a[i] = i % mod;
 }
 __global__ void k_counts_to_log(const CellCounts* __restrict__ c, double* __restrict__ out, size_t n, double l_free,
                                 double l_occ) {

@@ -41,6 +41,15 @@ class ShardedStepper:
         self.local = wrap_block(dl, lb, device)
         self.glob = wrap_block(dg, gb, device)
         assert gb == lb * dist.get_world_size()
+        # per-particle maps: resampling moves maps between GPUs (SLAM.java:41-45 deep copy); every rank
+        # maps the other ranks' arenas (cudaIpc) so its copy kernel can pull parents' maps over NVLink
+        self.migrates = handle.cfg.map_mode == B.MAP_PER_PARTICLE and dist.get_world_size() > 1
+        if self.migrates:
+            mine = handle.ipc_export()
+            every = [None] * dist.get_world_size()
+            dist.all_gather_object(every, mine)
+            handle.ipc_import(b"".join(every))
+            self._token = torch.zeros(1, dtype=torch.int32, device=device)
 
     def step(self, d_xy, d_dist, d_hit, num_beams, d_center, d_theta, d_normals=None, policy=B.POLICY_NEVER,
              u01=-1.0):
@@ -49,3 +58,6 @@ class ShardedStepper:
         # NCCL: ordered after the begin kernels on the current stream, and the end kernels after it
         self.dist.all_gather_into_tensor(self.glob, self.local)
         self.h.update_end_dev(policy, u01)
+        if self.migrates and policy != B.POLICY_NEVER:
+            # stream-ordered barrier: no rank starts the next map update before every pull has finished
+            self.dist.all_reduce(self._token)

@@ -220,6 +220,17 @@ int gms_update_begin_dev(gms_handle* h, const double* d_beam_xy, const double* d
 int gms_update_end_dev(gms_handle* h, int32_t resample_policy, double u01);
 int gms_read_neff(gms_handle* h, double* neff_out);  /* sync + read Neff of the last *_dev update */
 
+/* Per-particle maps (GMS_MAP_PER_PARTICLE) across ranks — the reference's Particle(Particle) deep copy
+ * (SLAM.java:41-45, GridMap.java:118-124) when parent and child live on different GPUs of one node.
+ * Each rank exports IPC handles of its map arenas, the caller all-gathers them (rank-major) and every
+ * rank imports the lot; resampling then pulls remote parents' maps over NVLink inside
+ * gms_update_end_dev / gms_resample.  The caller must run a barrier across ranks after the resampling
+ * call before the next update (old slots are only released then).  Handles hold 2x the slots. */
+#define GMS_IPC_HANDLE_BYTES 64
+#define GMS_IPC_NUM_HANDLES 4
+int gms_ipc_export(gms_handle* h, void* handles /* GMS_IPC_NUM_HANDLES * GMS_IPC_HANDLE_BYTES */);
+int gms_ipc_import(gms_handle* h, const void* all_handles /* nranks * the above, rank-major */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1004,3 +1004,5 @@ EXPORT int gms_profile_read(gms_handle *h, double *ms, int64_t *launches) {
 }
 EXPORT int gms_profile_reset(gms_handle *h) { return h ? GMS_OK : GMS_ERR_INVALID_ARG; }
 EXPORT int gms_launch_count(gms_handle *h, int64_t *n) { if (!h || !n) return GMS_ERR_INVALID_ARG; *n = 0; return GMS_OK; }
+EXPORT int gms_ipc_export(gms_handle *h, void *handles) { (void)handles; return h ? fail(h, GMS_ERR_UNSUPPORTED, "oracle: no device arenas") : GMS_ERR_INVALID_ARG; }
+EXPORT int gms_ipc_import(gms_handle *h, const void *all) { (void)all; return h ? fail(h, GMS_ERR_UNSUPPORTED, "oracle: no device arenas") : GMS_ERR_INVALID_ARG; }

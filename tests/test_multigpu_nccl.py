@@ -13,12 +13,13 @@ sys.path.insert(0, ROOT)
 pytestmark = pytest.mark.gpu
 
 
-def _cfg(P):
-    return dict(num_particles=P, map_width_m=51.2, map_height_m=51.2, origin_x=-25.6, origin_y=-25.6, map_mode=1,
+def _cfg(P, mode=1):
+    g = 51.2 if mode == 1 else 20.0
+    return dict(num_particles=P, map_width_m=g, map_height_m=g, origin_x=-g / 2, origin_y=-g / 2, map_mode=mode,
                 resample_mode=2, seed=4242)
 
 
-def _steps(h, stepper, scans, normals, uniforms, lo, cnt, dev):
+def _steps(h, stepper, scans, normals, uniforms, lo, cnt, dev, map_particles=(0,)):
     import torch
 
     from gridmap_slam_robot_b200 import binding as B
@@ -36,12 +37,13 @@ def _steps(h, stepper, scans, normals, uniforms, lo, cnt, dev):
         else:
             h.update_begin_dev(*args)
             h.update_end_dev(B.POLICY_ALWAYS, float(uniforms[s]))
-        out.append((h.read_neff(), h.parents().copy(), h.poses().copy(), h.weights().copy(),
-                    h.get_map(0, B.MAP_FREE_COUNT).copy(), h.get_map(0, B.MAP_OCC_COUNT).copy()))
+        maps = {p: (h.get_map(p, B.MAP_FREE_COUNT).copy(), h.get_map(p, B.MAP_OCC_COUNT).copy(),
+                    h.get_map(p, B.MAP_LIKELIHOOD).copy()) for p in map_particles}
+        out.append((h.read_neff(), h.parents().copy(), h.poses().copy(), h.weights().copy(), maps))
     return out
 
 
-def _worker(rank, world, port, P, steps, beams, q):
+def _worker(rank, world, port, P, steps, beams, q, mode=1):
     import torch
     import torch.distributed as dist
 
@@ -53,49 +55,64 @@ def _worker(rank, world, port, P, steps, beams, q):
     from gridmap_slam_robot_b200 import binding as B
     from gridmap_slam_robot_b200 import parallel, synth
 
-    h = B.load().create(rank=rank, nranks=world, device=rank, **_cfg(P))
+    h = B.load().create(rank=rank, nranks=world, device=rank, **_cfg(P, mode))
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     h.set_stream(stream.cuda_stream)
     stepper = parallel.ShardedStepper(h, dist, dev)
     scans = synth.make_scans(steps, beams, max_range=12.0)
     normals, uniforms = synth.make_draws(steps, P)
-    res = _steps(h, stepper, scans, normals, uniforms, h.info.local_begin, h.info.local_count, dev)
+    lo, cnt = h.info.local_begin, h.info.local_count
+    mp_ = (0,) if mode == 1 else tuple(range(lo, lo + cnt))
+    res = _steps(h, stepper, scans, normals, uniforms, lo, cnt, dev, map_particles=mp_)
     q.put((rank, res))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_gpus_equal_one_gpu(cuda):
+def _run(cuda, P, steps, beams, world, mode):
     import torch
     import torch.multiprocessing as mp
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
     from gridmap_slam_robot_b200 import synth
 
-    P, steps, beams, world = 8192, 4, 360, 2
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, P, steps, beams, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, P, steps, beams, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     results = dict(q.get(timeout=300) for _ in range(world))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    h = cuda.create(**_cfg(P))
+    h = cuda.create(**_cfg(P, mode))
     scans = synth.make_scans(steps, beams, max_range=12.0)
     normals, uniforms = synth.make_draws(steps, P)
-    single = _steps(h, None, scans, normals, uniforms, 0, P, torch.device("cuda", 0))
+    single = _steps(h, None, scans, normals, uniforms, 0, P, torch.device("cuda", 0),
+                    map_particles=(0,) if mode == 1 else tuple(range(P)))
     for r in range(world):
         for s in range(steps):
             a, b = results[r][s], single[s]
             assert abs(a[0] / b[0] - 1) < 1e-12
-            for k in (1, 2, 4, 5):
-                assert np.array_equal(a[k], b[k]), (r, s, k)
+            assert np.array_equal(a[1], b[1]), (r, s, "parents")
+            assert np.array_equal(a[2], b[2]), (r, s, "poses")
             np.testing.assert_allclose(a[3], b[3], rtol=1e-12, atol=0)
+            for p, (nf, no, lik) in a[4].items():
+                assert np.array_equal(nf, b[4][p][0]) and np.array_equal(no, b[4][p][1]), (r, s, p, "counts")
+                assert np.array_equal(lik, b[4][p][2]), (r, s, p, "likelihood")
     h.close()
+
+
+def test_two_gpus_equal_one_gpu(cuda):
+    _run(cuda, P=8192, steps=4, beams=360, world=2, mode=1)
+
+
+def test_two_gpus_per_particle_maps_migrate(cuda):
+    """K5-style: every particle owns a map; resampling every step moves maps between the two GPUs
+    (peer pull over NVLink).  Every particle's counts and likelihood field equal the 1-GPU run."""
+    _run(cuda, P=48, steps=5, beams=180, world=2, mode=0)
