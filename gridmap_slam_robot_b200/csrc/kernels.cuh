@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const unsigned* __restrict
 // Work list: every set bit of the per-slot dirty-tile bitmaps becomes one {slot, tile} item.
 // k_lik_scan (one CTA): exclusive scan of the per-word popcounts.  k_lik_emit: expands and clears the words.
 __global__ void __launch_bounds__(1024) k_lik_scan(const uint32_t* __restrict__ dirty, int nwords,
-                                                   int* __restrict__ word_off, Stats* __restrict__ st) {
+                                                   int* __restrict__ word_off, Stats* __restrict__ st,
+                                                   int* __restrict__ ray_maxlen) {
     __shared__ int s_part[1024];
     const int tid = threadIdx.x;
     const int per = (nwords + 1023) / 1024;
@@ -193,7 +194,10 @@ __global__ void __launch_bounds__(1024) k_lik_scan(const uint32_t* __restrict__ 
         word_off[i] = run;
         run += __popc(dirty[i]);
     }
-    if (tid == 1023) st->num_tiles = s_part[1023];
+    if (tid == 1023) {
+        st->num_tiles = s_part[1023];
+        *ray_maxlen = 0;  // consumed by the previous step's k_ray_apply; re-armed for this step's k_ray_walk
+    }
 }
 __global__ void __launch_bounds__(256) k_lik_emit(uint32_t* __restrict__ dirty, int nwords, int tile_words,
                                                   const int* __restrict__ word_off, int2* __restrict__ list) {
@@ -470,24 +474,41 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
     const double pqx = (x.px - g.posx) * g.inv_res, pqy = (x.py - g.posy) * g.inv_res;
     double mant = 1.0;
     int exp2 = 0;
-    auto factor_of = [&](const double2 m) -> double {
-        const double qx = fma(m.x, cinv, fma(-m.y, sinv, pqx));
-        const double qy = fma(m.x, sinv, fma(m.y, cinv, pqy));
-        int gx = __double2int_rz(qx), gy = __double2int_rz(qy);
-        const double ex = fabs(qx - (double)gx) - 0.5, ey = fabs(qy - (double)gy) - 0.5;
-        if (!(fabs(ex) < g.half_margin && fabs(ey) < g.half_margin)) {
-            gx = java_d2i((x.tx(m.x, m.y) - g.posx) / g.res);
-            gy = java_d2i((x.ty(m.x, m.y) - g.posy) / g.res);
-        }
-        double f = 1.0;
-        if ((unsigned)gx < (unsigned)g.W && (unsigned)gy < (unsigned)g.H) f = __ldg(fac + ((size_t)gx + (size_t)gy * g.W));
-        return f;
+    const unsigned uW = (unsigned)g.W, uH = (unsigned)g.H, oob = uW * uH;
+    // exact (slow) evaluation of one beam: the literal Java expression incl. the f64 division
+    auto factor_exact = [&](const double2 m) -> double {
+        const int gx = java_d2i((x.tx(m.x, m.y) - g.posx) / g.res);
+        const int gy = java_d2i((x.ty(m.x, m.y) - g.posy) / g.res);
+        if ((unsigned)gx < uW && (unsigned)gy < uH) return __ldg(fac + ((unsigned)gy * uW + (unsigned)gx));
+        return 1.0;
     };
     int b0 = 0;
     for (; b0 + 8 <= nh; b0 += 8) {
+        unsigned idx[8];
+        unsigned bad = 0;
+        // branch-free fast path for 8 beams (their dependency chains interleave); beams whose q~ is too
+        // close to an integer are only flagged here and redone exactly below.  End points outside the
+        // map read the sentinel fac[W*H] == 1.0 (GridMap.java:276: such beams do not multiply).
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const double2 m = s_xy[b0 + u];  // same address in every lane: shared-memory broadcast
+            const double qx = fma(m.x, cinv, fma(-m.y, sinv, pqx));
+            const double qy = fma(m.x, sinv, fma(m.y, cinv, pqy));
+            const int gx = __double2int_rz(qx), gy = __double2int_rz(qy);
+            const double ex = fabs(qx - (double)gx) - 0.5, ey = fabs(qy - (double)gy) - 0.5;
+            const bool ok = fabs(ex) < g.half_margin && fabs(ey) < g.half_margin;
+            const bool inb = (unsigned)gx < uW && (unsigned)gy < uH;
+            bad |= ok ? 0u : (1u << u);
+            idx[u] = inb ? (unsigned)gy * uW + (unsigned)gx : oob;
+        }
         double f[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) f[u] = factor_of(s_xy[b0 + u]);  // same address in every lane: broadcast
+        for (int u = 0; u < 8; u++) f[u] = __ldg(fac + idx[u]);  // 8 independent gathers in flight
+        if (bad) {
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (bad & (1u << u)) f[u] = factor_exact(s_xy[b0 + u]);
+        }
 #pragma unroll
         for (int u = 0; u < 8; u++) mant *= f[u];  // Java's order (GridMap.java:286-288)
         if ((b0 & 63) == 56) {  // factors are in [0.01, 0.91]: 64 of them cannot underflow a normalised mantissa
@@ -497,7 +518,7 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
             exp2 += e;
         }
     }
-    for (; b0 < nh; b0++) mant *= factor_of(s_xy[b0]);
+    for (; b0 < nh; b0++) mant *= factor_exact(s_xy[b0]);
     const double l = log(mant) + (double)exp2 * 0.6931471805599453;
     lw[lo + li] = l;
     if (xlocal) {
@@ -592,7 +613,7 @@ __global__ void __launch_bounds__(64) k_ray_walk(const float4* __restrict__ pose
     }
 }
 
-// persistent grid-stride over the (cell k, ray b) pairs; resets ray_maxlen for the next scan
+// persistent grid-stride over the (cell k, ray b) pairs (ray_maxlen is re-zeroed by the next k_lik_scan)
 __global__ void __launch_bounds__(256) k_ray_apply(const uint32_t* __restrict__ ray_cells, int Bpad,
                                                    const int* __restrict__ ray_count, int* __restrict__ ray_maxlen,
                                                    const float2* __restrict__ ray_start,
@@ -615,9 +636,6 @@ __global__ void __launch_bounds__(256) k_ray_apply(const uint32_t* __restrict__ 
         if (cls != 0) bump_cell(counts, dirty, cx, cy, cls, g);
     }
 }
-
-// runs after k_ray_apply on the same stream
-__global__ void k_ray_reset(int* ray_maxlen) { *ray_maxlen = 0; }
 
 // single ray given in grid coordinates (gms_map_apply_measurement)
 __global__ void k_apply_one(CellCounts* __restrict__ counts, int4* __restrict__ rect, uint32_t* __restrict__ dirty,
