@@ -98,6 +98,10 @@ SYMBOLS = {
     "gms_read_neff": [_vp, _P(_f64)],
     "gms_ipc_export": [_vp, _vp],
     "gms_ipc_import": [_vp, _vp],
+    "gms_deskew": [_vp, _vp, _vp, _i32, _f64, _f64, _vp, _vp],
+    "gms_update_raw": [_vp, _vp, _vp, _vp, _i32, _f64, _f64, _vp, _P(_f64)],
+    "gms_render_map": [_vp, _i32, _i32, _vp],
+    "gms_combined_map": [_vp, _vp, _vp],
 }
 
 
@@ -284,6 +288,32 @@ class Handle:
         counts = np.zeros(n, np.int32)
         self._ck(self.dll.gms_trace_rays(self.h, _ptr(rays), n, extra, _ptr(cells), cap, _ptr(counts)))
         return cells, counts
+
+    # ---- rows adjacent to the path ----
+    def deskew(self, angle, dist, d_center, d_theta):
+        a, d = _arr(angle, np.float64), _arr(dist, np.float64)
+        xy, od = np.zeros((a.size, 2), np.float64), np.zeros(a.size, np.float64)
+        self._ck(self.dll.gms_deskew(self.h, _ptr(a), _ptr(d), a.size, d_center, d_theta, _ptr(xy), _ptr(od)))
+        return xy, od
+
+    def update_raw(self, angle, dist, hit, d_center, d_theta, normals=None):
+        a = _arr(angle, np.float64)
+        d, hh = _arr(dist, np.float64, a.size), _arr(hit, np.uint8, a.size)
+        nz = None if normals is None else _arr(normals, np.float64, 2 * self.info.local_count)
+        neff = _f64()
+        self._ck(self.dll.gms_update_raw(self.h, _ptr(a), _ptr(d), _ptr(hh), a.size, d_center, d_theta, _ptr(nz),
+                                         C.byref(neff)))
+        return neff.value
+
+    def render_map(self, particle, likelihood=False):
+        out = np.zeros((self.H, self.W), np.uint32)
+        self._ck(self.dll.gms_render_map(self.h, particle, int(likelihood), _ptr(out)))
+        return out
+
+    def combined_map(self):
+        lg, lk = np.zeros((self.H, self.W), np.float64), np.zeros((self.H, self.W), np.float64)
+        self._ck(self.dll.gms_combined_map(self.h, _ptr(lg), _ptr(lk)))
+        return lg, lk
 
     # ---- device-resident / multi-rank ----
     def step_dev(self, d_xy, d_dist, d_hit, B, d_center, d_theta, d_normals=None, policy=POLICY_NEVER, u01=-1.0):

@@ -66,7 +66,14 @@ struct gms_handle {
     double* in_dist = nullptr;
     uint8_t *in_hit = nullptr, *all_hit = nullptr;
     float* meas = nullptr;
+    double *raw_angle = nullptr, *raw_dist = nullptr;  // raw sweep for the fused de-skew
     double* d_normals = nullptr;
+    // combined-map fusion scratch (allocated on first use)
+    double *comb_log = nullptr, *comb_lik = nullptr;
+    CellCounts* comb_sign = nullptr;
+    uint32_t* comb_dirty = nullptr;
+    int* comb_off = nullptr;
+    int2* comb_list = nullptr;
     // heading sort for k_score_sorted
     unsigned *sort_hist = nullptr, *sort_offs = nullptr, *sort_key = nullptr, *sort_rank = nullptr;
     int* order = nullptr;
@@ -212,6 +219,8 @@ void free_all(gms_handle* h) {
     cudaFree(h->in_xy); cudaFree(h->all_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
     cudaFree(h->all_hit); cudaFree(h->meas); cudaFree(h->d_normals); cudaFree(h->xlocal); cudaFree(h->xglobal);
     cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start); cudaFree(h->ray_maxlen);
+    cudaFree(h->raw_angle); cudaFree(h->raw_dist); cudaFree(h->comb_log); cudaFree(h->comb_lik); cudaFree(h->comb_sign);
+    cudaFree(h->comb_dirty); cudaFree(h->comb_off); cudaFree(h->comb_list);
     cudaFree(h->sort_hist); cudaFree(h->sort_offs); cudaFree(h->sort_key); cudaFree(h->sort_rank); cudaFree(h->order);
     cudaFree(h->np.m); cudaFree(h->np.idx); cudaFree(h->np.s); cudaFree(h->np.ws); cudaFree(h->np.q); cudaFree(h->np.fx);
     cudaFree(h->np.counter); cudaFree(h->wp_part); cudaFree(h->wp_counter);
@@ -242,6 +251,8 @@ int ensure_beams(gms_handle* h, int B) {
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(h->in_xy); cudaFree(h->all_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
     cudaFree(h->all_hit); cudaFree(h->meas); cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start);
+    cudaFree(h->raw_angle); cudaFree(h->raw_dist);
+    h->raw_angle = h->raw_dist = nullptr;
     h->in_xy = h->all_xy = h->hit_xy = nullptr; h->in_dist = nullptr; h->in_hit = h->all_hit = nullptr; h->meas = nullptr;
     h->ray_cells = nullptr; h->ray_count = nullptr; h->ray_start = nullptr;
     h->bcap = 0;
@@ -253,6 +264,8 @@ int ensure_beams(gms_handle* h, int B) {
     CK(cudaMalloc((void**)&h->in_hit, (size_t)cap));
     CK(cudaMalloc((void**)&h->all_hit, (size_t)cap));
     CK(cudaMalloc((void**)&h->meas, (size_t)cap * 4));
+    CK(cudaMalloc((void**)&h->raw_angle, (size_t)cap * 8));
+    CK(cudaMalloc((void**)&h->raw_dist, (size_t)cap * 8));
     if (h->cfg.map_mode == GMS_MAP_SHARED) {
         // a ray visits at most W + H - 1 in-bounds cells (4-connected, monotone) + the extra steps
         h->ray_cap = h->W + h->H + h->cfg.extra_steps + 4;
@@ -1124,5 +1137,112 @@ EXPORT int gms_ipc_import(gms_handle* h, const void* all_handles) {
         h->peers.dirty[q] = static_cast<const uint32_t*>(ptr[3]);
     }
     h->peers_ready = true;
+    return GMS_OK;
+}
+
+// ---- rows adjacent to the path ------------------------------------------------------
+namespace {
+// raw sweep -> device (raw_angle, raw_dist, all_hit) -> de-skewed beam table (all_xy, in_dist)
+int upload_raw_and_deskew(gms_handle* h, const double* angle, const double* dist, const uint8_t* hit, int B,
+                          double d_center, double d_theta) {
+    int rc = ensure_beams(h, B);
+    if (rc) return rc;
+    if (B == 0) return GMS_OK;
+    if ((rc = ensure_stage(h, (size_t)B * 17 + 64))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    unsigned char* s = h->h_stage;
+    std::memcpy(s, angle, (size_t)B * 8);
+    std::memcpy(s + (size_t)B * 8, dist, (size_t)B * 8);
+    if (hit) std::memcpy(s + (size_t)B * 16, hit, (size_t)B);
+    CK(cudaMemcpyAsync(h->raw_angle, s, (size_t)B * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->raw_dist, s + (size_t)B * 8, (size_t)B * 8, cudaMemcpyHostToDevice, h->stream));
+    if (hit) CK(cudaMemcpyAsync(h->all_hit, s + (size_t)B * 16, (size_t)B, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(GMS_PHASE_COUNT - 1, k_deskew<<<blocks_for(B, 256), 256, 0, h->stream>>>(h->raw_angle, h->raw_dist, B, d_center,
+                                                                                   d_theta, h->all_xy, h->in_dist));
+    return GMS_OK;
+}
+}  // namespace
+
+EXPORT int gms_deskew(gms_handle* h, const double* angle, const double* dist, int32_t B, double d_center,
+                      double d_theta, double* out_xy, double* out_dist) {
+    ENTER(h);
+    if (B < 0 || (B > 0 && (!angle || !dist || !out_xy || !out_dist))) return fail(h, GMS_ERR_INVALID_ARG, "gms_deskew: bad arrays");
+    int rc = upload_raw_and_deskew(h, angle, dist, nullptr, B, d_center, d_theta);
+    if (rc || B == 0) return rc;
+    CK(cudaMemcpyAsync(out_xy, h->all_xy, (size_t)B * 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out_dist, h->in_dist, (size_t)B * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return GMS_OK;
+}
+
+EXPORT int gms_update_raw(gms_handle* h, const double* angle, const double* dist, const uint8_t* hit, int32_t B,
+                          double d_center, double d_theta, const double* normals, double* neff_out) {
+    ENTER(h);
+    if (B < 0 || (B > 0 && (!angle || !dist || !hit))) return fail(h, GMS_ERR_INVALID_ARG, "gms_update_raw: bad arrays");
+    if (h->cfg.nranks != 1) return fail(h, GMS_ERR_STATE, "gms_update_raw: multi-rank handles use update_begin/end");
+    int rc = upload_raw_and_deskew(h, angle, dist, hit, B, d_center, d_theta);
+    if (rc) return rc;
+    const double* d_normals = nullptr;
+    if (normals) {
+        CK(cudaMemcpyAsync(h->d_normals, normals, (size_t)h->cnt * 16, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));  // pageable source
+        d_normals = h->d_normals;
+    }
+    if ((rc = step_begin(h, (const double*)h->all_xy, h->in_dist, h->all_hit, B, d_center, d_theta, d_normals))) return rc;
+    if ((rc = step_end(h, GMS_RESAMPLE_NEVER, 0.0))) return rc;
+    if ((rc = fetch_stats(h))) return rc;
+    if (neff_out) *neff_out = h->h_st->neff;
+    return GMS_OK;
+}
+
+EXPORT int gms_render_map(gms_handle* h, int32_t particle, int32_t likelihood, uint32_t* abgr_out) {
+    ENTER(h);
+    if (!abgr_out) return GMS_ERR_INVALID_ARG;
+    int s;
+    int rc = slot_of(h, particle, &s);
+    if (rc) return rc;
+    LAUNCH(GMS_PHASE_COUNT - 1, k_render<<<blocks_for((long long)h->cells, 256), 256, 0, h->stream>>>(
+                                    h->counts + (size_t)s * h->cells, h->lik + (size_t)s * h->cells, h->cells, likelihood,
+                                    h->g.l_free, h->g.l_occ, (uint32_t*)h->d_tmp));
+    return copy_out(h, abgr_out, h->d_tmp, h->cells * 4);
+}
+
+EXPORT int gms_combined_map(gms_handle* h, double* log_out, double* lik_out) {
+    ENTER(h);
+    if (h->cfg.map_mode != GMS_MAP_PER_PARTICLE || h->cfg.nranks != 1)
+        return fail(h, GMS_ERR_UNSUPPORTED, "gms_combined_map: single-rank per-particle maps only");
+    if (!h->comb_log) {
+        CK(cudaMalloc((void**)&h->comb_log, h->cells * 8));
+        CK(cudaMalloc((void**)&h->comb_lik, h->cells * 8));
+        CK(cudaMalloc((void**)&h->comb_sign, h->cells * sizeof(CellCounts)));
+        CK(cudaMalloc((void**)&h->comb_dirty, (size_t)h->g.tile_words * 4));
+        CK(cudaMalloc((void**)&h->comb_off, (size_t)h->g.tile_words * 4));
+        CK(cudaMalloc((void**)&h->comb_list, (size_t)h->tiles_per_map * sizeof(int2)));
+    }
+    LAUNCH(GMS_PHASE_COUNT - 1, k_combine<<<blocks_for((long long)h->cells, 256), 256, 0, h->stream>>>(
+                                    h->counts, h->slot[h->slot_cur], h->P, h->cells, h->g.l_free, h->g.l_occ, h->comb_log,
+                                    h->comb_sign));
+    if (log_out) CK(cudaMemcpyAsync(log_out, h->comb_log, h->cells * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (lik_out) {
+        // GridMap.computeLikelihoodMap(combinedGrid): the same tile kernel on the sign map
+        LAUNCH(GMS_PHASE_LIKELIHOOD, k_fill_dirty<<<blocks_for(h->g.tile_words, 256), 256, 0, h->stream>>>(
+                                         h->comb_dirty, 1, h->g.tile_words, h->tiles_per_map));
+        LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_scan<<<1, 1024, 0, h->stream>>>(h->comb_dirty, h->g.tile_words, h->comb_off,
+                                                                           h->st, h->ray_maxlen));
+        LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_emit<<<blocks_for(h->g.tile_words, 256), 256, 0, h->stream>>>(
+                                         h->comb_dirty, h->g.tile_words, h->g.tile_words, h->comb_off, h->comb_list));
+        const int k = h->g.khalf, th = kTileH + 2 * k, tw = (kTileW + 2 * k + 3) & ~3;
+        const size_t smem = (size_t)th * kTileW * 8 + (size_t)th * tw * 4;
+        const unsigned grid = (unsigned)std::min(h->tiles_per_map, 148 * 6);
+        if (k == 3)
+            LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<3><<<grid, 256, smem, h->stream>>>(h->comb_sign, h->comb_lik, nullptr,
+                                                                                          h->comb_list, h->st, h->g));
+        else
+            LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<0><<<grid, 256, smem, h->stream>>>(h->comb_sign, h->comb_lik, nullptr,
+                                                                                          h->comb_list, h->st, h->g));
+        CK(cudaMemcpyAsync(lik_out, h->comb_lik, h->cells * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    h->stats_valid = false;
+    CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }

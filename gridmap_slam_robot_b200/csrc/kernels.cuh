@@ -1217,6 +1217,68 @@ __global__ void __launch_bounds__(256) k_copy_maps(CellCounts* __restrict__ coun
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// rows adjacent to the path
+// ------------------------------------------------------------------------------------------------
+// GridMapApp.onHandleData GridMapApp.java:140-175 + Measurement(double x, double y, boolean, int)
+// Observation.java:69-76.  MathUtil.cos/sin(double) = FastMath (commons-math3) -> CUDA cos/sin: f64
+// results agree to ~1 ulp, not bit for bit.
+__global__ void __launch_bounds__(256) k_deskew(const double* __restrict__ angle, const double* __restrict__ dist,
+                                                int n, double d_center, double d_theta, double2* __restrict__ out_xy,
+                                                double* __restrict__ out_dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d_i = (double)(-(n - i)) / (double)n;
+    const double delta_theta = d_theta * d_i;
+    const double delta_x = d_center * d_i;
+    const double a = angle[i] + delta_theta;
+    const double x_a = dist[i] * cos(a) + delta_x;
+    const double y_a = dist[i] * sin(a);
+    out_xy[i] = make_double2(x_a, y_a);
+    out_dist[i] = sqrt(x_a * x_a + y_a * y_a);
+}
+
+// Util.invLogOdds(double) Util.java:46-48: 1.0f - 1.0f / (1 + Math.exp(log))
+__device__ __forceinline__ double inv_log_odds(double l) { return 1.0 - 1.0 / (1.0 + exp(l)); }
+
+// GridMap.render GridMap.java:371-388: value -> LUT index (int)(value * 255) -> gray (int)(255 * (i / 256f))
+__global__ void __launch_bounds__(256) k_render(const CellCounts* __restrict__ counts, const double* __restrict__ lik,
+                                                size_t n, int likelihood, double l_free, double l_occ,
+                                                uint32_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float value;
+    if (likelihood) value = (float)lik[i];
+    else {
+        const double l = (double)counts[i].n_free * l_free + (double)counts[i].n_occ * l_occ;
+        value = (float)(1.0 - inv_log_odds(l));
+    }
+    int idx = (int)(value * 255.0f);
+    idx = min(max(idx, 0), 255);  // Java would throw outside [0, 255]; values are probabilities
+    const float ratio = (float)idx / 256.0f;
+    const uint32_t c = (uint32_t)(int)(255.0f * ratio);
+    out[i] = ((255u << 24) | (c << 16) | (c << 8) | c) & 0xfeffffffu;  // Color.colorToFloatBits
+}
+
+// GridMapApp.calculateCombined GridMapApp.java:439-458 (product in particle order); also emits the
+// pseudo-counts whose sign equals the combined log-odds' sign, so k_likelihood can blur it.
+__global__ void __launch_bounds__(256) k_combine(const CellCounts* __restrict__ counts, const int* __restrict__ slot,
+                                                 int P, size_t cells, double l_free, double l_occ,
+                                                 double* __restrict__ log_out, CellCounts* __restrict__ sign_out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
+    double product = 1.0;
+    for (int p = 0; p < P; p++) {
+        const CellCounts c = counts[(size_t)slot[p] * cells + i];
+        const double l = (double)c.n_free * l_free + (double)c.n_occ * l_occ;
+        product *= 1.0 - inv_log_odds(l);
+    }
+    const double odds = 1.0 - product;
+    const double v = log(odds / (1.0 - odds));  // Util.logOdds(double)
+    log_out[i] = v;
+    sign_out[i] = v > 0.0 ? CellCounts{0u, 1u} : (v < 0.0 ? CellCounts{1u, 0u} : CellCounts{0u, 0u});
+}
+
 // ---- small utilities ----
 // mark every tile of `nslots` slots dirty (bits beyond the last tile stay clear)
 __global__ void k_fill_dirty(uint32_t* dirty, int nslots, int tile_words, int ntiles) {

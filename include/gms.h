@@ -231,6 +231,25 @@ int gms_read_neff(gms_handle* h, double* neff_out);  /* sync + read Neff of the 
 int gms_ipc_export(gms_handle* h, void* handles /* GMS_IPC_NUM_HANDLES * GMS_IPC_HANDLE_BYTES */);
 int gms_ipc_import(gms_handle* h, const void* all_handles /* nranks * the above, rank-major */);
 
+/* ---- rows adjacent to the path --------------------------------------------------- */
+/* Scan de-skew + beam-table build, GridMapApp.onHandleData GridMapApp.java:140-175 followed by
+ * Measurement(x, y, wasHit, 0) Observation.java:69-76: beam i of n is rotated / shifted back by the
+ * fraction -(n-i)/n of the odometry.  out_xy = {localX, localY} pairs, out_dist = sqrt(x^2+y^2). */
+int gms_deskew(gms_handle* h, const double* angle, const double* dist, int32_t num_beams, double d_center,
+               double d_theta, double* out_xy, double* out_dist);
+/* SLAM.update on a RAW sweep (angle, distance, wasHit as received, ConnectionThread.java:73-81): the
+ * de-skew runs on the device, fused with the beam upload, then the step of gms_update. */
+int gms_update_raw(gms_handle* h, const double* angle, const double* dist, const uint8_t* beam_hit,
+                   int32_t num_beams, double d_center, double d_theta, const double* normals, double* neff_out);
+/* Map hand-off to the renderer, GridMap.render GridMap.java:371-388 + Util.getColorBitsGrayscale
+ * Util.java:106-108 + Color.colorToFloatBits Color.java:62-66: one packed ABGR word per cell
+ * (likelihood != 0: the likelihood field, else 1 - p(occupied)), 4 bytes/cell D2H instead of 8-16. */
+int gms_render_map(gms_handle* h, int32_t particle, int32_t likelihood, uint32_t* abgr_out /* W*H */);
+/* Combined-map fusion, GridMapApp.calculateCombined GridMapApp.java:439-458: per cell
+ * logOdds(1 - prod_p (1 - invLogOdds(logData_p))) over all particles, then computeLikelihoodMap of it.
+ * Either output may be NULL.  Single-rank, per-particle maps. */
+int gms_combined_map(gms_handle* h, double* log_out /* W*H */, double* likelihood_out /* W*H */);
+
 #ifdef __cplusplus
 }
 #endif

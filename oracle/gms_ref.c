@@ -1006,3 +1006,68 @@ EXPORT int gms_profile_reset(gms_handle *h) { return h ? GMS_OK : GMS_ERR_INVALI
 EXPORT int gms_launch_count(gms_handle *h, int64_t *n) { if (!h || !n) return GMS_ERR_INVALID_ARG; *n = 0; return GMS_OK; }
 EXPORT int gms_ipc_export(gms_handle *h, void *handles) { (void)handles; return h ? fail(h, GMS_ERR_UNSUPPORTED, "oracle: no device arenas") : GMS_ERR_INVALID_ARG; }
 EXPORT int gms_ipc_import(gms_handle *h, const void *all) { (void)all; return h ? fail(h, GMS_ERR_UNSUPPORTED, "oracle: no device arenas") : GMS_ERR_INVALID_ARG; }
+
+/* ---- rows adjacent to the path ---------------------------------------------------- */
+/* GridMapApp.onHandleData GridMapApp.java:140-175 + Measurement(x, y, wasHit, 0) Observation.java:69-76 */
+static void deskew(const double *angle, const double *dist, int n, double d_center, double d_theta, double *xy, double *od) {
+    for (int i = 0; i < n; i++) {
+        double d_i = -(n - i) / (double)n;
+        double delta_theta = d_theta * d_i;
+        double delta_x = d_center * d_i;
+        double x_a = dist[i] * cos(angle[i] + delta_theta) + delta_x;
+        double y_a = dist[i] * sin(angle[i] + delta_theta);
+        xy[2 * i] = x_a; xy[2 * i + 1] = y_a;
+        od[i] = sqrt(x_a * x_a + y_a * y_a);
+    }
+}
+EXPORT int gms_deskew(gms_handle *h, const double *angle, const double *dist, int32_t n, double d_center, double d_theta,
+                      double *out_xy, double *out_dist) {
+    if (!h || n < 0 || (n > 0 && (!angle || !dist || !out_xy || !out_dist))) return GMS_ERR_INVALID_ARG;
+    deskew(angle, dist, n, d_center, d_theta, out_xy, out_dist);
+    return GMS_OK;
+}
+EXPORT int gms_update_raw(gms_handle *h, const double *angle, const double *dist, const uint8_t *hit, int32_t n,
+                          double d_center, double d_theta, const double *normals, double *neff_out) {
+    if (!h || n < 0 || (n > 0 && (!angle || !dist || !hit))) return GMS_ERR_INVALID_ARG;
+    double *xy = malloc(sizeof(double) * 2 * (n + 1)), *od = malloc(sizeof(double) * (n + 1));
+    deskew(angle, dist, n, d_center, d_theta, xy, od);
+    int rc = gms_update(h, xy, od, hit, n, d_center, d_theta, normals, neff_out);
+    free(xy); free(od);
+    return rc;
+}
+static double inv_log_odds(double l) { return 1.0 - 1.0 / (1 + exp(l)); } /* Util.java:46-48 */
+/* GridMap.render GridMap.java:371-388, Util.getColorBitsGrayscale Util.java:106-108, Color.java:62-66 */
+EXPORT int gms_render_map(gms_handle *h, int32_t particle, int32_t likelihood, uint32_t *out) {
+    int s;
+    if (!h || !out || !slot_of(h, particle, &s)) return GMS_ERR_INVALID_ARG;
+    size_t n = (size_t)h->W * h->H;
+    for (size_t i = 0; i < n; i++) {
+        float value = likelihood ? (float)h->lik[s][i] : (float)(1.0 - inv_log_odds(h->logd[s][i]));
+        int idx = (int)(value * 255);
+        if (idx < 0) idx = 0;
+        if (idx > 255) idx = 255;
+        float ratio = idx / (float)256;
+        uint32_t c = (uint32_t)(int)(255 * ratio);
+        out[i] = ((255u << 24) | (c << 16) | (c << 8) | c) & 0xfeffffffu;
+    }
+    return GMS_OK;
+}
+/* GridMapApp.calculateCombined GridMapApp.java:439-458 */
+EXPORT int gms_combined_map(gms_handle *h, double *log_out, double *lik_out) {
+    if (!h) return GMS_ERR_INVALID_ARG;
+    if (h->cfg.map_mode != GMS_MAP_PER_PARTICLE || h->cfg.nranks != 1)
+        return fail(h, GMS_ERR_UNSUPPORTED, "gms_combined_map: single-rank per-particle maps only");
+    if (!ensure_scratch(h)) return fail(h, GMS_ERR_OOM, "out of memory (scratch)");
+    size_t n = (size_t)h->W * h->H;
+    double *comb = malloc(n * sizeof(double)), *lik = malloc(n * sizeof(double));
+    for (size_t i = 0; i < n; i++) {
+        double product = 1;
+        for (int p = 0; p < h->P; p++) product *= 1 - inv_log_odds(h->logd[h->slot[p]][i]);
+        comb[i] = log_odds(1 - product);
+    }
+    compute_likelihood(h, comb, lik, h->prob_scratch, h->tmp_scratch);
+    if (log_out) memcpy(log_out, comb, n * sizeof(double));
+    if (lik_out) memcpy(lik_out, lik, n * sizeof(double));
+    free(comb); free(lik);
+    return GMS_OK;
+}

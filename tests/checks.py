@@ -298,3 +298,74 @@ def replay_compare(cuda, oracle, P, beams, steps, grid_m, mode, max_range=10.0, 
     finally:
         g.close()
         o.close()
+
+
+# ---------------------------------------------------------------- rows adjacent to the path (§8f) ----
+def _raw_sweeps(steps, beams):
+    """Raw sweeps the way the robot link delivers them: angle, distance, wasHit (+ odometry)."""
+    from gridmap_slam_robot_b200 import synth
+
+    scans = synth.make_scans(steps, beams)
+    ang = 2.0 * np.pi * np.arange(beams) / beams
+    return [(ang, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta) for sc in scans]
+
+
+def check_deskew_reference_formula(lib):
+    """GridMapApp.java:140-175 restated with numpy (same libm): the oracle must match it bit for bit,
+    the CUDA path to a few ulp (FastMath / CUDA / libm sin and cos are not correctly rounded)."""
+    h = lib.create(num_particles=1, map_width_m=0.5, map_height_m=0.5, map_mode=B.MAP_SHARED)
+    rng = np.random.default_rng(11)
+    n = 97
+    ang, dist = rng.uniform(-np.pi, np.pi, n), rng.uniform(0.05, 11.0, n)
+    dc, dth = 0.07, -0.21
+    d_i = -(n - np.arange(n)) / float(n)
+    x = dist * np.cos(ang + dth * d_i) + dc * d_i
+    y = dist * np.sin(ang + dth * d_i)
+    xy, od = h.deskew(ang, dist, dc, dth)
+    tol = 0 if not h.info.is_cuda else 8 * np.finfo(np.float64).eps * 11.0
+    np.testing.assert_allclose(xy[:, 0], x, rtol=0, atol=tol)
+    np.testing.assert_allclose(xy[:, 1], y, rtol=0, atol=tol)
+    np.testing.assert_allclose(od, np.sqrt(x * x + y * y), rtol=0, atol=tol)
+    h.close()
+
+
+def check_next_rows(cuda, oracle):
+    """CUDA vs oracle: fused de-skew + update on raw sweeps, renderer hand-off, combined-map fusion."""
+    P, beams, steps = 12, 180, 5
+    kw = dict(num_particles=P, map_width_m=20.0, map_height_m=20.0, origin_x=-10.0, origin_y=-10.0)
+    g, o = cuda.create(**kw), oracle.create(**kw)
+    from gridmap_slam_robot_b200 import synth
+
+    normals, uniforms = synth.make_draws(steps, P)
+    for s, (ang, dist, hit, dc, dth) in enumerate(_raw_sweeps(steps, beams)):
+        ng = g.update_raw(ang, dist, hit, dc, dth, normals[s])
+        no = o.update_raw(ang, dist, hit, dc, dth, normals[s])
+        assert abs(ng / no - 1) < 1e-9
+        assert np.array_equal(g.poses(), o.poses())
+        np.testing.assert_allclose(g.log_weights(), o.log_weights(), rtol=0, atol=1e-9)
+        if s % 2:
+            g.resample(float(uniforms[s]))
+            o.resample(float(uniforms[s]))
+            assert np.array_equal(g.parents(), o.parents())
+    # de-skewed beams differ by ulps between libm and CUDA, which can move an end point across a cell
+    # boundary: counts are compared as "almost all cells equal"
+    for p in (0, P - 1):
+        for kind in (B.MAP_FREE_COUNT, B.MAP_OCC_COUNT):
+            a, b = g.get_map(p, kind), o.get_map(p, kind)
+            assert np.mean(a != b) < 1e-4, (p, kind, np.sum(a != b))
+    # renderer hand-off: packed ABGR gray words
+    for lik in (False, True):
+        a, b = g.render_map(0, lik), o.render_map(0, lik)
+        assert a.dtype == np.uint32 and np.all((a >> 24) == 0xFE)  # alpha 255 & 0xfe mask
+        assert np.mean(a != b) < 1e-3
+        lvl = (a & 0xFF).astype(int) - (b & 0xFF).astype(int)
+        assert np.abs(lvl).max() <= 1 or np.mean(a != b) < 1e-4
+    # combined-map fusion
+    lg, lk = g.combined_map()
+    lo, lko = o.combined_map()
+    finite = np.isfinite(lo)
+    assert np.array_equal(np.isfinite(lg), finite)
+    np.testing.assert_allclose(lg[finite], lo[finite], rtol=1e-9, atol=1e-9)
+    assert np.mean(lk != lko) < 1e-3
+    g.close()
+    o.close()
