@@ -55,7 +55,7 @@ struct gms_handle {
     int2* tile_list = nullptr;
     int tiles_per_map = 0;
     int4* dup_rect = nullptr;
-    int *dup_src = nullptr, *dup_dst = nullptr, *dup_src_rank = nullptr, *scratch2p = nullptr;
+    int *dup_src = nullptr, *dup_dst = nullptr, *dup_src_rank = nullptr, *dup_level = nullptr, *scratch2p = nullptr;
     // per-particle maps across ranks: peer mappings of every rank's arenas (cudaIpc)
     PeerTable peers{};
     bool peers_ready = false;
@@ -215,7 +215,7 @@ void free_all(gms_handle* h) {
             if (h->ipc_opened[q][k]) cudaIpcCloseMemHandle(h->ipc_opened[q][k]);
     for (int i = 0; i < 2; i++) { cudaFree(h->pose[i]); cudaFree(h->w[i]); cudaFree(h->lw[i]); cudaFree(h->slot[i]); }
     cudaFree(h->parents); cudaFree(h->cdf); cudaFree(h->counts); cudaFree(h->lik); cudaFree(h->fac); cudaFree(h->rect);
-    cudaFree(h->dirty); cudaFree(h->word_off); cudaFree(h->tile_list); cudaFree(h->dup_rect); cudaFree(h->dup_src_rank); cudaFree(h->dup_src); cudaFree(h->dup_dst); cudaFree(h->scratch2p);
+    cudaFree(h->dirty); cudaFree(h->word_off); cudaFree(h->tile_list); cudaFree(h->dup_rect); cudaFree(h->dup_src_rank); cudaFree(h->dup_level); cudaFree(h->dup_src); cudaFree(h->dup_dst); cudaFree(h->scratch2p);
     cudaFree(h->in_xy); cudaFree(h->all_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
     cudaFree(h->all_hit); cudaFree(h->meas); cudaFree(h->d_normals); cudaFree(h->xlocal); cudaFree(h->xglobal);
     cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start); cudaFree(h->ray_maxlen);
@@ -431,15 +431,19 @@ int launch_resample(gms_handle* h, double u01) {
         const int nxt = h->slot_cur ^ 1;
         LAUNCH(GMS_PHASE_MAP_COPY, k_assign_slots_mr<<<1, 1024, 0, h->stream>>>(
                                        h->parents, P, h->cnt, h->cfg.nranks, h->S, h->cfg.rank, h->slot[h->slot_cur],
-                                       h->slot[nxt], h->dup_src_rank, h->dup_src, h->dup_dst, h->scratch2p, h->st));
+                                       h->slot[nxt], h->dup_src_rank, h->dup_src, h->dup_dst, h->dup_level, h->dirty,
+                                       h->g.tile_words, h->scratch2p, h->st));
         h->slot_cur = nxt;
-        LAUNCH(GMS_PHASE_MAP_COPY, k_job_rects<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(
-                                       h->dup_src_rank, h->dup_src, h->dup_dst, h->dup_rect, h->rect, h->st, h->peers,
-                                       h->g));
         const int chunks = std::max(1, std::min(32, h->H / 16));
-        LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps<<<(unsigned)((long long)chunks * h->cnt), 256, 0, h->stream>>>(
-                                       h->counts, h->lik, h->dirty, h->dup_src, h->dup_dst, h->dup_rect, h->st,
-                                       h->cells, h->W, h->g.tile_words, chunks, h->dup_src_rank, h->peers));
+        for (int level = 0; level < 2; level++) {  // 0: pulls + copies of old-generation maps, 1: copies of pulled replicas
+            LAUNCH(GMS_PHASE_MAP_COPY, k_job_rects<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(
+                                           h->dup_src_rank, h->dup_src, h->dup_dst, h->dup_level, level, h->dup_rect,
+                                           h->rect, h->st, h->peers, h->g));
+            LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps<<<(unsigned)((long long)chunks * h->cnt), 256, 0, h->stream>>>(
+                                           h->counts, h->lik, h->dirty, h->dup_src, h->dup_dst, h->dup_rect, h->st,
+                                           h->cells, h->W, h->g.tile_words, chunks, h->dup_src_rank, h->peers,
+                                           h->dup_level, level));
+        }
         return GMS_OK;
     }
     if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE) {
@@ -452,7 +456,7 @@ int launch_resample(gms_handle* h, double u01) {
         const int chunks = std::max(1, std::min(32, h->H / 16));
         LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps<<<(unsigned)((long long)chunks * P), 256, 0, h->stream>>>(
                                        h->counts, h->lik, h->dirty, h->dup_src, h->dup_dst, h->dup_rect, h->st,
-                                       h->cells, h->W, h->g.tile_words, chunks, nullptr, h->peers));
+                                       h->cells, h->W, h->g.tile_words, chunks, nullptr, h->peers, nullptr, 0));
     }
     return GMS_OK;
 }
@@ -675,6 +679,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->dup_src, P * 4));
     CKC(cudaMalloc((void**)&h->dup_dst, P * 4));
     CKC(cudaMalloc((void**)&h->dup_src_rank, P * 4));
+    CKC(cudaMalloc((void**)&h->dup_level, P * 4));
     CKC(cudaMalloc((void**)&h->scratch2p, std::max(2 * P, (size_t)2 * cfg->nranks * h->S) * 4));
     CKC(cudaMalloc((void**)&h->d_normals, (size_t)h->cnt * 16));
     CKC(cudaMalloc((void**)&h->xlocal, (size_t)h->cnt * sizeof(ExchangeRec)));

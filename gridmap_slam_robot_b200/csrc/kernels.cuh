@@ -1090,7 +1090,9 @@ __global__ void __launch_bounds__(1024) k_assign_slots_mr(const int* __restrict_
                                                           int myrank, const int* __restrict__ gslot_in,
                                                           int* __restrict__ gslot_out, int* __restrict__ job_src_rank,
                                                           int* __restrict__ job_src_slot, int* __restrict__ job_dst,
-                                                          int* __restrict__ scratch /* 2*R*S */, Stats* __restrict__ st) {
+                                                          int* __restrict__ job_level, uint32_t* __restrict__ dirty,
+                                                          int tile_words, int* __restrict__ scratch /* 2*R*S */,
+                                                          Stats* __restrict__ st) {
     __shared__ int s_buf[1024];
     const int tid = threadIdx.x;
     int* occ = scratch;
@@ -1126,8 +1128,22 @@ __global__ void __launch_bounds__(1024) k_assign_slots_mr(const int* __restrict_
                 const int d = freelist[q * S + rn];
                 gslot_out[m] = d;
                 if (q == myrank) {
-                    job_src_rank[rn] = p / cnt;
-                    job_src_slot[rn] = gslot_in[p];
+                    // A remote parent is pulled over NVLink ONCE per rank (by its first child here, level 0);
+                    // its further children on this rank copy that local replica afterwards (level 1).  Without
+                    // this a heavy parent's rank serves every one of its children: an NVLink hot spot.
+                    const bool remote = p / cnt != q;
+                    const bool first_here = m == q * cnt || parents[m - 1] != p;
+                    if (remote && !first_here) {
+                        int mf = m;  // first child of p on this rank, and the slot it was given
+                        while (mf > q * cnt && parents[mf - 1] == p) mf--;
+                        job_src_rank[rn] = q;
+                        job_src_slot[rn] = freelist[q * S + rn - (m - mf)];
+                        job_level[rn] = 1;
+                    } else {
+                        job_src_rank[rn] = p / cnt;
+                        job_src_slot[rn] = gslot_in[p];
+                        job_level[rn] = 0;
+                    }
                     job_dst[rn] = d;
                 }
                 rn++;
@@ -1135,17 +1151,25 @@ __global__ void __launch_bounds__(1024) k_assign_slots_mr(const int* __restrict_
         }
         if (q == myrank && tid == 0) st->num_dup = total;
     }
+    // slots of this rank that the new generation does not occupy: drop their pending likelihood tiles
+    __syncthreads();
+    for (int i = tid; i < S; i += 1024) occ[i] = 0;
+    __syncthreads();
+    for (int m = myrank * cnt + tid; m < (myrank + 1) * cnt; m += 1024) occ[gslot_out[m]] = 1;
+    __syncthreads();
+    for (int i = tid; i < S * tile_words; i += 1024)
+        if (!occ[i / tile_words]) dirty[i] = 0u;
 }
 
 // copy rectangle of every job (union of the two explored boxes + blur half-width); the child inherits the
 // parent's box.  The parent's box is read from the parent's rank.
 __global__ void __launch_bounds__(256) k_job_rects(const int* __restrict__ job_src_rank,
                                                    const int* __restrict__ job_src_slot,
-                                                   const int* __restrict__ job_dst, int4* __restrict__ job_rect,
-                                                   int4* __restrict__ rect, const Stats* __restrict__ st,
-                                                   PeerTable peers, Geometry g) {
+                                                   const int* __restrict__ job_dst, const int* __restrict__ job_level,
+                                                   int level, int4* __restrict__ job_rect, int4* __restrict__ rect,
+                                                   const Stats* __restrict__ st, PeerTable peers, Geometry g) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= st->num_dup) return;
+    if (k >= st->num_dup || job_level[k] != level) return;
     const int4 a = peers.rect[job_src_rank[k]][job_src_slot[k]];
     const int d = job_dst[k];
     const int4 b = rect[d];
@@ -1166,9 +1190,10 @@ __global__ void __launch_bounds__(256) k_copy_maps(CellCounts* __restrict__ coun
                                                    const int* __restrict__ dup_dst, const int4* __restrict__ dup_rect,
                                                    const Stats* __restrict__ st, size_t cells, int W, int tile_words,
                                                    int chunks_per_map, const int* __restrict__ dup_src_rank,
-                                                   PeerTable peers) {
+                                                   PeerTable peers, const int* __restrict__ job_level, int level) {
     const int k = blockIdx.x / chunks_per_map;
     if (k >= st->num_dup) return;
+    if (job_level && job_level[k] != level) return;
     const int chunk = blockIdx.x - k * chunks_per_map;
     const int src = dup_src[k], dst = dup_dst[k];
     const CellCounts* src_counts = counts;
