@@ -37,6 +37,12 @@ struct gms_handle {
     size_t cells = 0;
     float world_w = 0, world_h = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // shared map: two side streams let independent chains of one step overlap (likelihood refresh next to
+    // motion + heading sort; map integration next to resampling); joined back before anything depends on them
+    cudaStream_t side_a = nullptr, side_b = nullptr;
+    cudaEvent_t ev_fork_a = nullptr, ev_done_a = nullptr, ev_fork_b = nullptr, ev_done_b = nullptr;
+    bool overlap = true;  // GMS_NO_OVERLAP=1 serialises everything on one stream
+    bool b_pending = false;  // a map integration is still running on side_b (joined by the next consumer)
     // particle state (double buffered for resampling)
     float4* pose[2] = {nullptr, nullptr};
     double* w[2] = {nullptr, nullptr};
@@ -66,6 +72,12 @@ struct gms_handle {
     double* in_dist = nullptr;
     uint8_t *in_hit = nullptr, *all_hit = nullptr;
     float* meas = nullptr;
+    // two sets of {all_xy, all_hit, meas}: the shared-map integration of step N may still read set N%2 on the
+    // side stream while step N+1 uploads into the other set; all_xy / all_hit / meas point at the current one
+    double2* all_xy2[2] = {nullptr, nullptr};
+    uint8_t* all_hit2[2] = {nullptr, nullptr};
+    float* meas2[2] = {nullptr, nullptr};
+    int bset = 0;
     double *raw_angle = nullptr, *raw_dist = nullptr;  // raw sweep for the fused de-skew
     double* d_normals = nullptr;
     // combined-map fusion scratch (allocated on first use)
@@ -83,7 +95,7 @@ struct gms_handle {
     double* wp_part = nullptr;
     unsigned* wp_counter = nullptr;
     bool tile_fx_valid = false;
-    int score_cta = 128;  // threads per CTA of k_score_sorted (GMS_SCORE_CTA overrides: tuning knob)
+    int score_g = 0;  // sub-threads per particle in k_score_sorted (0 = automatic; GMS_SCORE_G overrides: tuning knob)
     int num_sms = 148;
     int* ray_maxlen = nullptr;
     // shared-map two-pass update: recorded ray cells
@@ -134,9 +146,17 @@ int cuda_fail(gms_handle* h, cudaError_t e, const char* what) {
         cudaError_t e_ = (call);                                   \
         if (e_ != cudaSuccess) return cuda_fail(h, e_, #call);     \
     } while (0)
-#define ENTER(h)                                                   \
+// ENTER: every entry point; joins a map integration still running on the side stream.  ENTER_STEP: the
+// step entry points, which hand that dependency to the likelihood chain instead (step_begin).
+#define ENTER_STEP(h)                                              \
     if (!(h)) return GMS_ERR_INVALID_ARG;                          \
     CK(cudaSetDevice((h)->dev))
+#define ENTER(h)                                                   \
+    ENTER_STEP(h);                                                 \
+    if ((h)->b_pending) {                                          \
+        CK(cudaStreamWaitEvent((h)->stream, (h)->ev_done_b, 0));   \
+        (h)->b_pending = false;                                    \
+    }
 
 struct Phase {  // RAII: CUDA events around one phase when profiling is on
     gms_handle* h;
@@ -210,14 +230,17 @@ void free_all(gms_handle* h) {
     if (!h) return;
     cudaSetDevice(h->dev);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->side_a) cudaStreamSynchronize(h->side_a);
+    if (h->side_b) cudaStreamSynchronize(h->side_b);
     for (int q = 0; q < kMaxRanks; q++)
         for (int k = 0; k < 4; k++)
             if (h->ipc_opened[q][k]) cudaIpcCloseMemHandle(h->ipc_opened[q][k]);
     for (int i = 0; i < 2; i++) { cudaFree(h->pose[i]); cudaFree(h->w[i]); cudaFree(h->lw[i]); cudaFree(h->slot[i]); }
     cudaFree(h->parents); cudaFree(h->cdf); cudaFree(h->counts); cudaFree(h->lik); cudaFree(h->fac); cudaFree(h->rect);
     cudaFree(h->dirty); cudaFree(h->word_off); cudaFree(h->tile_list); cudaFree(h->dup_rect); cudaFree(h->dup_src_rank); cudaFree(h->dup_level); cudaFree(h->dup_src); cudaFree(h->dup_dst); cudaFree(h->scratch2p);
-    cudaFree(h->in_xy); cudaFree(h->all_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
-    cudaFree(h->all_hit); cudaFree(h->meas); cudaFree(h->d_normals); cudaFree(h->xlocal); cudaFree(h->xglobal);
+    cudaFree(h->in_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
+    for (int i = 0; i < 2; i++) { cudaFree(h->all_xy2[i]); cudaFree(h->all_hit2[i]); cudaFree(h->meas2[i]); }
+    cudaFree(h->d_normals); cudaFree(h->xlocal); cudaFree(h->xglobal);
     cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start); cudaFree(h->ray_maxlen);
     cudaFree(h->raw_angle); cudaFree(h->raw_dist); cudaFree(h->comb_log); cudaFree(h->comb_lik); cudaFree(h->comb_sign);
     cudaFree(h->comb_dirty); cudaFree(h->comb_off); cudaFree(h->comb_list);
@@ -230,6 +253,10 @@ void free_all(gms_handle* h) {
     for (auto& s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : h->pool) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->side_a) cudaStreamDestroy(h->side_a);
+    if (h->side_b) cudaStreamDestroy(h->side_b);
+    for (cudaEvent_t e : {h->ev_fork_a, h->ev_done_a, h->ev_fork_b, h->ev_done_b})
+        if (e) cudaEventDestroy(e);
     delete h;
 }
 
@@ -249,8 +276,12 @@ int ensure_beams(gms_handle* h, int B) {
     if (B <= h->bcap) return GMS_OK;
     if ((size_t)B * 16 > 200 * 1024) return fail(h, GMS_ERR_INVALID_ARG, "too many beams (max 12800)");
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(h->in_xy); cudaFree(h->all_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
-    cudaFree(h->all_hit); cudaFree(h->meas); cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start);
+    CK(cudaStreamSynchronize(h->side_a));
+    CK(cudaStreamSynchronize(h->side_b));
+    h->b_pending = false;
+    cudaFree(h->in_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
+    for (int i = 0; i < 2; i++) { cudaFree(h->all_xy2[i]); cudaFree(h->all_hit2[i]); cudaFree(h->meas2[i]); h->all_xy2[i] = nullptr; h->all_hit2[i] = nullptr; h->meas2[i] = nullptr; }
+    cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start);
     cudaFree(h->raw_angle); cudaFree(h->raw_dist);
     h->raw_angle = h->raw_dist = nullptr;
     h->in_xy = h->all_xy = h->hit_xy = nullptr; h->in_dist = nullptr; h->in_hit = h->all_hit = nullptr; h->meas = nullptr;
@@ -258,12 +289,15 @@ int ensure_beams(gms_handle* h, int B) {
     h->bcap = 0;
     const int cap = ((B + 255) / 256) * 256;
     CK(cudaMalloc((void**)&h->in_xy, (size_t)cap * 16));
-    CK(cudaMalloc((void**)&h->all_xy, (size_t)cap * 16));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaMalloc((void**)&h->all_xy2[i], (size_t)cap * 16));
+        CK(cudaMalloc((void**)&h->all_hit2[i], (size_t)cap));
+        CK(cudaMalloc((void**)&h->meas2[i], (size_t)cap * 4));
+    }
+    h->all_xy = h->all_xy2[h->bset]; h->all_hit = h->all_hit2[h->bset]; h->meas = h->meas2[h->bset];
     CK(cudaMalloc((void**)&h->hit_xy, (size_t)cap * 16));
     CK(cudaMalloc((void**)&h->in_dist, (size_t)cap * 8));
     CK(cudaMalloc((void**)&h->in_hit, (size_t)cap));
-    CK(cudaMalloc((void**)&h->all_hit, (size_t)cap));
-    CK(cudaMalloc((void**)&h->meas, (size_t)cap * 4));
     CK(cudaMalloc((void**)&h->raw_angle, (size_t)cap * 8));
     CK(cudaMalloc((void**)&h->raw_dist, (size_t)cap * 8));
     if (h->cfg.map_mode == GMS_MAP_SHARED) {
@@ -275,6 +309,14 @@ int ensure_beams(gms_handle* h, int B) {
     }
     h->bcap = cap;
     return GMS_OK;
+}
+
+// start of a step: switch to the beam-table set the side stream is not reading
+void flip_beams(gms_handle* h) {
+    h->bset ^= 1;
+    h->all_xy = h->all_xy2[h->bset];
+    h->all_hit = h->all_hit2[h->bset];
+    h->meas = h->meas2[h->bset];
 }
 
 int fetch_stats(gms_handle* h) {
@@ -323,15 +365,29 @@ int launch_likelihood(gms_handle* h) {
 // Thread-per-particle scoring in heading order pays off when one shared field serves many particles
 // (see k_score_sorted); per-particle maps and small particle sets keep one warp per particle.
 bool use_sorted_score(const gms_handle* h) { return h->cfg.map_mode == GMS_MAP_SHARED && h->cnt >= 4096; }
+// every shared-map scoring of the step runs k_score_sorted (factor field + FMA cell index)
+bool use_fac_score(const gms_handle* h) { return h->cfg.map_mode == GMS_MAP_SHARED; }
 
 int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* slot, double* lw,
                  ExchangeRec* xlocal, int B, bool sorted = false) {
     Phase ph(h, GMS_PHASE_SCORE);
     if (sorted) {
         const size_t smem_s = std::max<size_t>(16, (size_t)B * 16);
-        // (an SM-balanced partition with 352-thread CTAs measured 10% slower than plain 128-thread CTAs)
-        LAUNCH(GMS_PHASE_SCORE, k_score_sorted<<<blocks_for(cnt, h->score_cta), h->score_cta, smem_s, h->stream>>>(
-                                    pose, lo, cnt, h->hit_xy, h->st, h->fac, h->order, lw, xlocal, h->g));
+        // sub-threads per particle: enough threads to fill the machine (>= ~150k), at most one warp per particle
+        int G = 1;
+        while (G < 32 && (long long)cnt * G < 300000) G *= 2;
+        if (h->score_g) G = h->score_g;
+        const int* order = use_sorted_score(h) ? h->order : nullptr;
+        const unsigned grid = blocks_for((long long)cnt * G, 128);
+#define SCORE_G(GG)                                                                                              \
+    case GG:                                                                                                     \
+        LAUNCH(GMS_PHASE_SCORE, k_score_sorted<GG><<<grid, 128, smem_s, h->stream>>>(pose, lo, cnt, h->hit_xy, h->st, \
+                                                                                      h->fac, order, lw, xlocal, h->g)); \
+        break;
+        switch (G) {
+            SCORE_G(1) SCORE_G(2) SCORE_G(4) SCORE_G(8) SCORE_G(16) SCORE_G(32)
+        }
+#undef SCORE_G
         return GMS_OK;
     }
     const unsigned grid = std::min<unsigned>(blocks_for(cnt, 8), 148 * 8);
@@ -366,7 +422,28 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
                double d_theta, const double* d_normals) {
     const gms_config& c = h->cfg;
     h->stats_valid = false;
-    int rc = launch_pack(h, d_xy, d_dist, d_hit, B);
+    const bool shared = c.map_mode == GMS_MAP_SHARED;
+    const bool fork = shared && h->overlap;
+    int rc;
+    if (fork) {  // likelihood refresh of the shared map: independent of the beams and of the motion update
+        cudaStream_t main = h->stream;
+        CK(cudaEventRecord(h->ev_fork_a, main));
+        CK(cudaStreamWaitEvent(h->side_a, h->ev_fork_a, 0));
+        if (h->b_pending) {  // the previous step's map integration feeds this refresh (and, through it, main)
+            CK(cudaStreamWaitEvent(h->side_a, h->ev_done_b, 0));
+            h->b_pending = false;
+        }
+        h->stream = h->side_a;
+        rc = launch_likelihood(h);
+        h->stream = main;
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev_done_a, h->side_a));
+    }
+    if (h->b_pending) {  // not forking: join the side stream the plain way
+        CK(cudaStreamWaitEvent(h->stream, h->ev_done_b, 0));
+        h->b_pending = false;
+    }
+    rc = launch_pack(h, d_xy, d_dist, d_hit, B);
     if (rc) return rc;
     {
         Phase ph(h, GMS_PHASE_MOTION);
@@ -383,11 +460,14 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
                                          h->sort_offs, h->sort_key, h->sort_rank, h->cnt, h->order));
         }
     }
-    rc = launch_likelihood(h);
-    if (rc) return rc;
-    const bool shared = c.map_mode == GMS_MAP_SHARED;
+    if (fork) {
+        CK(cudaStreamWaitEvent(h->stream, h->ev_done_a, 0));
+    } else {
+        rc = launch_likelihood(h);
+        if (rc) return rc;
+    }
     rc = launch_score(h, h->pose[h->cur], h->lo, h->cnt, shared ? nullptr : h->slot[h->slot_cur] + h->lo, h->lw[h->cur],
-                      c.nranks > 1 ? h->xlocal : nullptr, B, use_sorted_score(h));
+                      c.nranks > 1 ? h->xlocal : nullptr, B, use_fac_score(h));
     if (rc) return rc;
     const bool skip = std::fabs(d_theta) > (M_PI / 180.0) * c.skip_update_deg;  // SLAM.java:82
     if (!shared && !skip) {
@@ -479,15 +559,29 @@ int step_end(gms_handle* h, int policy, double u01) {
         h->tile_fx_valid = true;
     }
     const bool skip = std::fabs(h->pend_dtheta) > (M_PI / 180.0) * c.skip_update_deg;
+    bool forked = false;
     if (c.map_mode == GMS_MAP_SHARED && !skip) {
+        // map integration from the strongest pose: touches the map only, resampling touches the particle
+        // arrays only (it gathers into the other buffer), so the two chains run side by side
+        cudaStream_t main = h->stream;
+        forked = h->overlap;
+        if (forked) {
+            CK(cudaEventRecord(h->ev_fork_b, main));
+            CK(cudaStreamWaitEvent(h->side_b, h->ev_fork_b, 0));
+            h->stream = h->side_b;
+        }
         int rc = launch_map_update(h, h->pose[h->cur], 0, 1, nullptr, h->pend_B, 1);
+        h->stream = main;
         if (rc) return rc;
+        if (forked) CK(cudaEventRecord(h->ev_done_b, h->side_b));
     }
     h->step++;
     h->have_update = true;
     h->pending = false;
-    if (policy != GMS_RESAMPLE_NEVER) return launch_resample(h, u01);
-    return GMS_OK;
+    int rc = GMS_OK;
+    if (policy != GMS_RESAMPLE_NEVER) rc = launch_resample(h, u01);
+    if (forked) h->b_pending = true;  // joined by the next step's likelihood chain or the next other call
+    return rc;
 }
 
 int slot_of(gms_handle* h, int particle, int* slot) {
@@ -655,6 +749,13 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaSetDevice(h->dev));
     CKC(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
+    CKC(cudaStreamCreateWithFlags(&h->side_a, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&h->side_b, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&h->ev_fork_a, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->ev_done_a, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->ev_fork_b, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->ev_done_b, cudaEventDisableTiming));
+    if (const char* e = std::getenv("GMS_NO_OVERLAP")) h->overlap = std::atoi(e) == 0;
     const size_t P = (size_t)h->P;
     for (int i = 0; i < 2; i++) {
         CKC(cudaMalloc((void**)&h->pose[i], P * sizeof(float4)));
@@ -697,7 +798,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->sort_rank, (size_t)h->cnt * 4));
     CKC(cudaMalloc((void**)&h->order, (size_t)h->cnt * 4));
     h->ntiles = (h->P + 1023) / 1024;
-    if (const char* e = std::getenv("GMS_SCORE_CTA")) { const int v = std::atoi(e); if (v == 32 || v == 64 || v == 96 || v == 128) h->score_cta = v; }
+    if (const char* e = std::getenv("GMS_SCORE_G")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) h->score_g = v; }
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, h->dev) == cudaSuccess) h->num_sms = prop.multiProcessorCount; }
     {
         const size_t nt = (size_t)h->ntiles;
@@ -717,7 +818,12 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     }
     CKC(cudaMallocHost((void**)&h->h_st, sizeof(Stats)));
     CKC(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CKC(cudaFuncSetAttribute(k_score_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKC(cudaFuncSetAttribute(k_score_sorted<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKC(cudaFuncSetAttribute(k_score_sorted<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKC(cudaFuncSetAttribute(k_score_sorted<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKC(cudaFuncSetAttribute(k_score_sorted<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKC(cudaFuncSetAttribute(k_score_sorted<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CKC(cudaFuncSetAttribute(k_score_sorted<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CKC(cudaFuncSetAttribute(k_likelihood<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CKC(cudaFuncSetAttribute(k_likelihood<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     int rc = ensure_beams(h, 1024);
@@ -758,7 +864,8 @@ EXPORT int gms_reset(gms_handle* h) {
 
 EXPORT int gms_update(gms_handle* h, const double* beam_xy, const double* beam_dist, const uint8_t* beam_hit,
                       int32_t B, double d_center, double d_theta, const double* normals, double* neff_out) {
-    ENTER(h);
+    ENTER_STEP(h);
+    flip_beams(h);
     if (B < 0 || (B > 0 && (!beam_xy || !beam_dist || !beam_hit)))
         return fail(h, GMS_ERR_INVALID_ARG, "gms_update: bad beam arrays");
     if (h->cfg.nranks != 1) return fail(h, GMS_ERR_STATE, "gms_update: multi-rank handles use update_begin/end");
@@ -1038,7 +1145,8 @@ EXPORT int gms_odometry_from_counts(int32_t left, int32_t right, double* d_cente
 // ---- device-resident / multi-rank -----------------------------------------------------------------
 EXPORT int gms_update_begin_dev(gms_handle* h, const double* d_xy, const double* d_dist, const uint8_t* d_hit,
                                 int32_t B, double d_center, double d_theta, const double* d_normals) {
-    ENTER(h);
+    ENTER_STEP(h);
+    flip_beams(h);
     if (B < 0 || (B > 0 && (!d_xy || !d_dist || !d_hit))) return fail(h, GMS_ERR_INVALID_ARG, "bad beam arrays");
     return step_begin(h, d_xy, d_dist, d_hit, B, d_center, d_theta, d_normals);
 }
@@ -1049,7 +1157,8 @@ EXPORT int gms_update_end_dev(gms_handle* h, int32_t policy, double u01) {
 }
 EXPORT int gms_step_dev(gms_handle* h, const double* d_xy, const double* d_dist, const uint8_t* d_hit, int32_t B,
                         double d_center, double d_theta, const double* d_normals, int32_t policy, double u01) {
-    ENTER(h);
+    ENTER_STEP(h);
+    flip_beams(h);
     if (h->cfg.nranks != 1) return fail(h, GMS_ERR_STATE, "gms_step_dev: multi-rank handles use update_begin/end");
     if (B < 0 || (B > 0 && (!d_xy || !d_dist || !d_hit))) return fail(h, GMS_ERR_INVALID_ARG, "bad beam arrays");
     if (policy < 0 || policy > 2 || u01 >= 1.0) return fail(h, GMS_ERR_INVALID_ARG, "bad resample policy / u01");
@@ -1182,7 +1291,8 @@ EXPORT int gms_deskew(gms_handle* h, const double* angle, const double* dist, in
 
 EXPORT int gms_update_raw(gms_handle* h, const double* angle, const double* dist, const uint8_t* hit, int32_t B,
                           double d_center, double d_theta, const double* normals, double* neff_out) {
-    ENTER(h);
+    ENTER_STEP(h);
+    flip_beams(h);
     if (B < 0 || (B > 0 && (!angle || !dist || !hit))) return fail(h, GMS_ERR_INVALID_ARG, "gms_update_raw: bad arrays");
     if (h->cfg.nranks != 1) return fail(h, GMS_ERR_STATE, "gms_update_raw: multi-rank handles use update_begin/end");
     int rc = upload_raw_and_deskew(h, angle, dist, hit, B, d_center, d_theta);

@@ -422,6 +422,9 @@ __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, 
 // gather touches 1-3 lines.  The product runs over the beams in Java's order; every 64 factors the
 // exponent is peeled off exactly (power-of-two scaling commutes with rounding), so mant * 2^exp2 is
 // Java's product bit for bit wherever that does not underflow, and ln() is taken once.
+// G threads share a particle (beam u*G + gsub goes to sub-thread gsub): G = 1 for ~1e5 particles, up to 32
+// (= one warp per particle) for small sets, so the grid always fills the machine.
+template <int G>
 __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__ pose, int lo, int cnt,
                                                       const double2* __restrict__ hit_xy,
                                                       const Stats* __restrict__ st, const double* __restrict__ fac,
@@ -449,8 +452,8 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
                 : "memory");
         }
     }
-    const int t = blockIdx.x * blockDim.x + tid;
-    const int li = t < cnt ? order[t] : -1;
+    const int t = (blockIdx.x * blockDim.x + tid) / G, gsub = (blockIdx.x * blockDim.x + tid) % G;
+    const int li = t < cnt ? (order ? order[t] : t) : -1;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     if (li >= 0) p = pose[lo + li];
     const Xform x(p.x, p.y, p.z);
@@ -464,7 +467,7 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
                 : "memory");
         }
     }
-    if (li < 0) return;
+    const int nhe = li >= 0 ? nh : 0;  // idle sub-threads still take part in the shuffles below
     // Fast path for (int) ((world - position) / resolution), GridMap.java:273-274: q~ = the same quantity
     // evaluated with two FMAs from per-particle constants.  |q~ - q_java| < 1e-9 for every finite input
     // with |q| < 2^31, so when q~ is further than 1e-5 from both neighbouring integers the truncation is
@@ -482,8 +485,14 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
         if ((unsigned)gx < uW && (unsigned)gy < uH) return __ldg(fac + ((unsigned)gy * uW + (unsigned)gx));
         return 1.0;
     };
-    int b0 = 0;
-    for (; b0 + 8 <= nh; b0 += 8) {
+    auto peel = [&]() {  // move the exponent of mant into exp2: exact (power-of-two scaling)
+        const int hi = __double2hiint(mant);
+        const int e = ((hi >> 20) & 0x7ff) - 1023;
+        mant = __hiloint2double(hi - (e << 20), __double2loint(mant));
+        exp2 += e;
+    };
+    int b0 = 0, it = 0;
+    for (; b0 + 8 * G <= nhe; b0 += 8 * G, it++) {
         unsigned idx[8];
         unsigned bad = 0;
         // branch-free fast path for 8 beams (their dependency chains interleave); beams whose q~ is too
@@ -491,7 +500,7 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
         // map read the sentinel fac[W*H] == 1.0 (GridMap.java:276: such beams do not multiply).
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            const double2 m = s_xy[b0 + u];  // same address in every lane: shared-memory broadcast
+            const double2 m = s_xy[b0 + u * G + gsub];  // G distinct addresses per warp: shared-memory broadcast
             const double qx = fma(m.x, cinv, fma(-m.y, sinv, pqx));
             const double qy = fma(m.x, sinv, fma(m.y, cinv, pqy));
             const int gx = __double2int_rz(qx), gy = __double2int_rz(qy);
@@ -507,18 +516,22 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
         if (bad) {
 #pragma unroll
             for (int u = 0; u < 8; u++)
-                if (bad & (1u << u)) f[u] = factor_exact(s_xy[b0 + u]);
+                if (bad & (1u << u)) f[u] = factor_exact(s_xy[b0 + u * G + gsub]);
         }
 #pragma unroll
-        for (int u = 0; u < 8; u++) mant *= f[u];  // Java's order (GridMap.java:286-288)
-        if ((b0 & 63) == 56) {  // factors are in [0.01, 0.91]: 64 of them cannot underflow a normalised mantissa
-            const int hi = __double2hiint(mant);
-            const int e = ((hi >> 20) & 0x7ff) - 1023;
-            mant = __hiloint2double(hi - (e << 20), __double2loint(mant));
-            exp2 += e;
+        for (int u = 0; u < 8; u++) mant *= f[u];  // G == 1: Java's order (GridMap.java:286-288)
+        if ((it & 7) == 7) peel();  // factors are in [0.01, 0.91]: 64 of them cannot underflow a normalised mantissa
+    }
+    for (int b = b0 + gsub; b < nhe; b += G) mant *= factor_exact(s_xy[b]);
+    peel();
+    if (G > 1) {  // combine the sub-threads' partial products: mantissas in [1, 2), at most 2^5 after the tree
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            mant *= __shfl_xor_sync(0xffffffffu, mant, o);
+            exp2 += __shfl_xor_sync(0xffffffffu, exp2, o);
         }
     }
-    for (; b0 < nh; b0++) mant *= factor_exact(s_xy[b0]);
+    if (li < 0 || gsub != 0) return;
     const double l = log(mant) + (double)exp2 * 0.6931471805599453;
     lw[lo + li] = l;
     if (xlocal) {
