@@ -87,7 +87,7 @@ struct gms_handle {
     int* comb_off = nullptr;
     int2* comb_list = nullptr;
     // heading sort for k_score_sorted
-    unsigned *sort_hist = nullptr, *sort_offs = nullptr, *sort_key = nullptr, *sort_rank = nullptr;
+    unsigned *sort_hist = nullptr, *sort_offs = nullptr, *sort_key = nullptr, *sort_rank = nullptr, *sort_cta = nullptr;
     int* order = nullptr;
     // tile partials of normalise / neff / weighted pose
     int ntiles = 0;
@@ -244,7 +244,7 @@ void free_all(gms_handle* h) {
     cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start); cudaFree(h->ray_maxlen);
     cudaFree(h->raw_angle); cudaFree(h->raw_dist); cudaFree(h->comb_log); cudaFree(h->comb_lik); cudaFree(h->comb_sign);
     cudaFree(h->comb_dirty); cudaFree(h->comb_off); cudaFree(h->comb_list);
-    cudaFree(h->sort_hist); cudaFree(h->sort_offs); cudaFree(h->sort_key); cudaFree(h->sort_rank); cudaFree(h->order);
+    cudaFree(h->sort_hist); cudaFree(h->sort_cta); cudaFree(h->sort_offs); cudaFree(h->sort_key); cudaFree(h->sort_rank); cudaFree(h->order);
     cudaFree(h->np.m); cudaFree(h->np.idx); cudaFree(h->np.s); cudaFree(h->np.ws); cudaFree(h->np.q); cudaFree(h->np.fx);
     cudaFree(h->np.counter); cudaFree(h->wp_part); cudaFree(h->wp_counter);
     cudaFree(h->d_tmp); cudaFree(h->tmp_pose); cudaFree(h->tmp_slot); cudaFree(h->tmp_lw); cudaFree(h->st);
@@ -455,9 +455,9 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
                                      h->pose[h->cur], h->lo, h->cnt, d_normals, c.seed, h->step, d_center, d_theta,
                                      sd_c, sd_t, sorted ? h->sort_hist : nullptr, h->sort_key, h->sort_rank));
         if (sorted) {
-            LAUNCH(GMS_PHASE_MOTION, k_sort_scan<<<1, 1024, 0, h->stream>>>(h->sort_hist, h->sort_offs));
+            LAUNCH(GMS_PHASE_MOTION, k_sort_scan<<<kSortCtas, 1024, 0, h->stream>>>(h->sort_hist, h->sort_offs, h->sort_cta));
             LAUNCH(GMS_PHASE_MOTION, k_sort_scatter<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(
-                                         h->sort_offs, h->sort_key, h->sort_rank, h->cnt, h->order));
+                                         h->sort_offs, h->sort_cta, h->sort_key, h->sort_rank, h->cnt, h->order));
         }
     }
     if (fork) {
@@ -484,22 +484,21 @@ int launch_resample(gms_handle* h, double u01) {
     const int P = h->P;
     {
         Phase ph(h, GMS_PHASE_RESAMPLE);
+        const int nxt = h->cur ^ 1;
         if (h->resample_mode == GMS_RESAMPLE_FIXED) {
             if (!h->tile_fx_valid)  // tile sums of trunc(w * 2^60): by-product of k_normalise / k_neff
                 LAUNCH(GMS_PHASE_RESAMPLE, k_neff<<<h->ntiles, 1024, 0, h->stream>>>(h->w[h->cur], P, h->ntiles, h->np, h->st));
             LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_fixed<<<h->ntiles, 1024, 0, h->stream>>>(
                                            h->w[h->cur], P, h->np.fx, (unsigned long long*)h->cdf, h->st));
             LAUNCH(GMS_PHASE_RESAMPLE, k_select<true><<<blocks_for(P, 256), 256, 0, h->stream>>>(
-                                           h->cdf, P, u01, h->cfg.seed, h->resample_count, h->parents, h->st));
+                                           h->cdf, P, u01, h->cfg.seed, h->resample_count, h->parents, h->st,
+                                           h->pose[h->cur], h->w[h->cur], h->lw[h->cur], h->pose[nxt], h->w[nxt], h->lw[nxt]));
         } else {
             LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_literal<<<1, 32, 0, h->stream>>>(h->w[h->cur], P, (double*)h->cdf, h->st));
             LAUNCH(GMS_PHASE_RESAMPLE, k_select<false><<<blocks_for(P, 256), 256, 0, h->stream>>>(
-                                           h->cdf, P, u01, h->cfg.seed, h->resample_count, h->parents, h->st));
+                                           h->cdf, P, u01, h->cfg.seed, h->resample_count, h->parents, h->st,
+                                           h->pose[h->cur], h->w[h->cur], h->lw[h->cur], h->pose[nxt], h->w[nxt], h->lw[nxt]));
         }
-        const int nxt = h->cur ^ 1;
-        LAUNCH(GMS_PHASE_RESAMPLE, k_gather<<<blocks_for(P, 256), 256, 0, h->stream>>>(
-                                       h->parents, P, h->pose[h->cur], h->w[h->cur], h->lw[h->cur], h->pose[nxt],
-                                       h->w[nxt], h->lw[nxt]));
         h->cur = nxt;
         h->tile_fx_valid = false;
     }
@@ -791,9 +790,10 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->tmp_slot, sizeof(int)));
     CKC(cudaMalloc((void**)&h->tmp_lw, sizeof(double)));
     CKC(cudaMalloc((void**)&h->st, sizeof(Stats)));
-    CKC(cudaMalloc((void**)&h->sort_hist, kSortBins * 4));
+    CKC(cudaMalloc((void**)&h->sort_hist, (size_t)kSortBins * 4));
+    CKC(cudaMalloc((void**)&h->sort_cta, (size_t)kSortCtas * 4));
     CKC(cudaMalloc((void**)&h->sort_offs, kSortBins * 4));
-    CKC(cudaMemset(h->sort_hist, 0, kSortBins * 4));
+    CKC(cudaMemset(h->sort_hist, 0, (size_t)kSortBins * 4));
     CKC(cudaMalloc((void**)&h->sort_key, (size_t)h->cnt * 4));
     CKC(cudaMalloc((void**)&h->sort_rank, (size_t)h->cnt * 4));
     CKC(cudaMalloc((void**)&h->order, (size_t)h->cnt * 4));

@@ -80,7 +80,11 @@ __global__ void __launch_bounds__(256) k_pack_beams(const double2* __restrict__ 
 // A2 — SLAM.sampleMotionModel SLAM.java:155-163 + Odometry.apply Odometry.java:77-96.
 // One thread per local particle; z = {z_d, z_theta} injected or Philox(seed, global index, step).
 // ------------------------------------------------------------------------------------------------
-constexpr int kSortBins = 8192;  // heading buckets of 2*pi/8192 rad (< 8 mm of arc at 10 m: sub-cell)
+// 65536 heading buckets of 2*pi/65536 rad: ~30 particles per bucket at 100k particles spread over +-15 deg.
+// Same-address atomics with a return value serialise at ~70 ns each (ncu: 8192 buckets made k_motion 23 us,
+// 65536 buckets 10 us), so the bucket count is chosen for low contention, not for ordering precision.
+constexpr int kSortBins = 65536;
+constexpr int kSortCtas = kSortBins / 1024;
 
 __global__ void __launch_bounds__(256) k_motion(float4* __restrict__ pose, int lo, int cnt,
                                                 const double* __restrict__ normals, uint64_t seed,
@@ -113,19 +117,16 @@ __global__ void __launch_bounds__(256) k_motion(float4* __restrict__ pose, int l
     }
 }
 
-// exclusive scan of the heading histogram (one CTA, 8 bins per thread) + re-zero for the next step
-__global__ void __launch_bounds__(1024) k_sort_scan(unsigned* __restrict__ hist, unsigned* __restrict__ offs) {
+// exclusive scan of the heading histogram: CTA c scans buckets [1024c, 1024c+1024) (coalesced) and publishes
+// its total; the scatter adds the totals of the CTAs before it.  Re-zeroes the histogram for the next step.
+__global__ void __launch_bounds__(1024) k_sort_scan(unsigned* __restrict__ hist, unsigned* __restrict__ offs,
+                                                    unsigned* __restrict__ cta_total) {
     __shared__ unsigned s_w[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    constexpr int per = kSortBins / 1024;
-    uint4* h4 = reinterpret_cast<uint4*>(hist) + tid * (per / 4);
-    unsigned sum = 0;
-#pragma unroll 4
-    for (int k = 0; k < per / 4; k++) {
-        const uint4 v = h4[k];
-        sum += v.x + v.y + v.z + v.w;
-    }
-    unsigned inc = sum;
+    const int i = blockIdx.x * 1024 + tid;
+    const unsigned v = hist[i];
+    hist[i] = 0u;
+    unsigned inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
@@ -140,27 +141,38 @@ __global__ void __launch_bounds__(1024) k_sort_scan(unsigned* __restrict__ hist,
         if (lane >= o) wv += u;
     }
     const unsigned wbase = wid > 0 ? __shfl_sync(0xffffffffu, wv, wid - 1) : 0u;
-    unsigned run = wbase + inc - sum;
-    uint4* o4 = reinterpret_cast<uint4*>(offs) + tid * (per / 4);
-#pragma unroll 4
-    for (int k = 0; k < per / 4; k++) {
-        const uint4 v = h4[k];  // second read: L1/L2 hit
-        uint4 o;
-        o.x = run; run += v.x;
-        o.y = run; run += v.y;
-        o.z = run; run += v.z;
-        o.w = run; run += v.w;
-        o4[k] = o;
-        h4[k] = make_uint4(0, 0, 0, 0);
-    }
+    offs[i] = wbase + inc - v;
+    if (tid == 1023) cta_total[blockIdx.x] = wbase + inc;
 }
 
 __global__ void __launch_bounds__(256) k_sort_scatter(const unsigned* __restrict__ offs,
+                                                      const unsigned* __restrict__ cta_total,
                                                       const unsigned* __restrict__ key,
                                                       const unsigned* __restrict__ rank, int cnt,
                                                       int* __restrict__ order) {
+    __shared__ unsigned s_base[kSortCtas];
+    if (threadIdx.x < kSortCtas) {  // exclusive prefix of the 64 CTA totals (two warps, shuffle scan)
+        const int lane = threadIdx.x & 31;
+        const unsigned t = cta_total[threadIdx.x];
+        unsigned inc = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        s_base[threadIdx.x] = inc - t;
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32 && threadIdx.x < kSortCtas) {
+        unsigned first_half = s_base[31] + cta_total[31];
+        s_base[threadIdx.x] += first_half;
+    }
+    __syncthreads();
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
-    if (li < cnt) order[offs[key[li]] + rank[li]] = li;
+    if (li < cnt) {
+        const unsigned k = key[li];
+        order[s_base[k >> 10] + offs[k] + rank[li]] = li;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -967,14 +979,22 @@ __global__ void __launch_bounds__(1024) k_cdf_fixed(const double* __restrict__ w
 }
 
 // index selection: for m = 1..P, U = r + (m-1)*1.0/P, first i with !(U > c_i), clamped to P-1.
+// ... and the new generation is gathered right here: copies of the chosen parents (Particle(Particle)
+// SLAM.java:41-45: weight and pose are copied; weights are NOT reset to 1/N).
 template <bool FIXED>
 __global__ void __launch_bounds__(256) k_select(const void* __restrict__ cdf_raw, int P, double u01, uint64_t seed,
                                                 uint64_t resample_count, int* __restrict__ parents,
-                                                const Stats* __restrict__ st) {
+                                                const Stats* __restrict__ st, const float4* __restrict__ pose_in,
+                                                const double* __restrict__ w_in, const double* __restrict__ lw_in,
+                                                float4* __restrict__ pose_out, double* __restrict__ w_out,
+                                                double* __restrict__ lw_out) {
     const int m0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (m0 >= P) return;
     if (!st->do_resample) {
         parents[m0] = m0;
+        pose_out[m0] = pose_in[m0];
+        w_out[m0] = w_in[m0];
+        lw_out[m0] = lw_in[m0];
         return;
     }
     if (u01 < 0.0) u01 = philox_uniform(seed, resample_count);
@@ -996,8 +1016,12 @@ __global__ void __launch_bounds__(256) k_select(const void* __restrict__ cdf_raw
         }
     }
     parents[m0] = lo;
+    pose_out[m0] = pose_in[lo];
+    w_out[m0] = w_in[lo];
+    lw_out[m0] = lw_in[lo];
 }
 
+// (stand-alone gather, kept for callers that already hold parent indices)
 // new generation = copies of the chosen parents (Particle(Particle) SLAM.java:41-45: weight and pose
 // are copied; weights are NOT reset to 1/N)
 __global__ void __launch_bounds__(256) k_gather(const int* __restrict__ parents, int P,
