@@ -21,7 +21,12 @@ struct Geometry {
     float tol_half;           // hitTolerance / 2 (SensorModel.java:35-37)
     double res, posx, posy;   // (double) resolution / position: the promotions Java performs
     double inv_res;           // 1.0 / res — only for the guarded fast path of cell_of()
-    double half_margin;       // 0.5 - 1e-5: fast-path acceptance band of k_score_sorted
+    double half_margin;       // 0.5 - 1e-5: fast-path acceptance band (legacy, unused by the integer path)
+    // fixed-point fast path of k_score_sorted: q + fx_magic puts round(q * 2^fx_k) into the low mantissa word
+    double fx_magic;          // 1.5 * 2^(52 - fx_k)
+    int fx_k;                 // fraction bits: max(W, H) * 2^fx_k < 2^30
+    int fx_hi;                // high word of fx_magic == high word of q + fx_magic for 0 <= q < 2^(31 - fx_k)
+    int fx_margin;            // acceptance margin in units of 2^-fx_k (>= 8 units >> |q~ - q_java| + rounding)
     int tiles_x, tiles_y;     // likelihood tiles (kTileW x kTileH cells) per map
     int tile_words;           // 32-bit words of one slot's dirty-tile bitmap
     double z_hit;             // GridMap.java:259
@@ -31,8 +36,10 @@ struct Geometry {
     double kernel[31];        // Util.generateGaussianKernel           (Util.java:428-455)
 };
 
-// JLS 5.1.3 (int) of a double: NaN -> 0, saturating, truncation toward zero == cvt.rzi.s32.f64.
-__device__ __forceinline__ int java_d2i(double d) { return __double2int_rz(d); }
+// JLS 5.1.3 (int) of a double: NaN -> 0, saturating, truncation toward zero.  cvt.rzi.s32.f64 truncates and
+// saturates, but returns INT_MIN for NaN on sm_100 (measured: tests/test_gpu_parity.py::test_degenerate_scans),
+// so NaN is handled explicitly.
+__device__ __forceinline__ int java_d2i(double d) { return d != d ? 0 : __double2int_rz(d); }
 
 // (int) ((world - position) / resolution) of GridMap.java:273-274 without the f64 division on the fast
 // path.  q = t * (1/res) is within 2 ulp of the correctly rounded quotient t / res, i.e. within
@@ -44,7 +51,7 @@ __device__ __forceinline__ int cell_of(double t, double res, double inv_res) {
     const int n = __double2int_rz(q);
     const double fr = fabs(q - (double)n);  // exact (Sterbenz); in [0, 1) for in-range q
     if (fr > 1e-5 && fr < 1.0 - 1e-5) return n;
-    return __double2int_rz(t / res);
+    return java_d2i(t / res);
 }
 
 // MathUtil.angleConstrain MathUtil.java:65-72.  The loops are replicated literally (they are NOT the

@@ -375,7 +375,7 @@ int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* 
         const size_t smem_s = std::max<size_t>(16, (size_t)B * 16);
         // sub-threads per particle: enough threads to fill the machine (>= ~150k), at most one warp per particle
         int G = 1;
-        while (G < 32 && (long long)cnt * G < 300000) G *= 2;
+        while (G < 32 && (long long)cnt * G < 200000) G *= 2;
         if (h->score_g) G = h->score_g;
         const int* order = use_sorted_score(h) ? h->order : nullptr;
         const unsigned grid = blocks_for((long long)cnt * G, 128);
@@ -714,6 +714,16 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     g.res = (double)cfg->resolution; g.posx = (double)cfg->origin_x; g.posy = (double)cfg->origin_y;
     g.inv_res = 1.0 / g.res;
     g.half_margin = 0.5 - 1e-5;
+    {
+        int bits = 1;
+        while ((1 << bits) <= std::max(h->W, h->H)) bits++;  // max(W, H) < 2^bits
+        g.fx_k = std::min(20, 30 - bits);
+        g.fx_magic = std::ldexp(1.5, 52 - g.fx_k);
+        unsigned long long u;
+        std::memcpy(&u, &g.fx_magic, 8);
+        g.fx_hi = (int)(u >> 32);
+        g.fx_margin = std::max(8, 1 << std::max(0, g.fx_k - 14));
+    }
     g.tiles_x = (h->W + kTileW - 1) / kTileW;
     g.tiles_y = (h->H + kTileH - 1) / kTileH;
     g.tile_words = (g.tiles_x * g.tiles_y + 31) / 32;

@@ -490,8 +490,15 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
     double mant = 1.0;
     int exp2 = 0;
     const unsigned uW = (unsigned)g.W, uH = (unsigned)g.H, oob = uW * uH;
+    const int fk = g.fx_k;
+    const unsigned fmask = (1u << fk) - 1u, fmarg = (unsigned)g.fx_margin, fspan = (1u << fk) - 2u * fmarg;
     // exact (slow) evaluation of one beam: the literal Java expression incl. the f64 division
     auto factor_exact = [&](const double2 m) -> double {
+        {   // far outside the map (more than a cell beyond an edge): no lookup, no division needed
+            const double qx = fma(m.x, cinv, fma(-m.y, sinv, pqx));
+            const double qy = fma(m.x, sinv, fma(m.y, cinv, pqy));
+            if (qx < -2.0 || qy < -2.0 || qx > (double)uW + 1.0 || qy > (double)uH + 1.0) return 1.0;
+        }
         const int gx = java_d2i((x.tx(m.x, m.y) - g.posx) / g.res);
         const int gy = java_d2i((x.ty(m.x, m.y) - g.posy) / g.res);
         if ((unsigned)gx < uW && (unsigned)gy < uH) return __ldg(fac + ((unsigned)gy * uW + (unsigned)gx));
@@ -515,12 +522,19 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
             const double2 m = s_xy[b0 + u * G + gsub];  // G distinct addresses per warp: shared-memory broadcast
             const double qx = fma(m.x, cinv, fma(-m.y, sinv, pqx));
             const double qy = fma(m.x, sinv, fma(m.y, cinv, pqy));
-            const int gx = __double2int_rz(qx), gy = __double2int_rz(qy);
-            const double ex = fabs(qx - (double)gx) - 0.5, ey = fabs(qy - (double)gy) - 0.5;
-            const bool ok = fabs(ex) < g.half_margin && fabs(ey) < g.half_margin;
-            const bool inb = (unsigned)gx < uW && (unsigned)gy < uH;
+            // q + 1.5*2^(52-k): the low mantissa word now holds round(q * 2^k) as an integer, the high word
+            // is a known constant exactly when 0 <= q < 2^(31-k).  Cell = I >> k, fraction = I & (2^k - 1).
+            const double tx = qx + g.fx_magic, ty = qy + g.fx_magic;
+            const int ix = __double2loint(tx), iy = __double2loint(ty);
+            const bool inrange = __double2hiint(tx) == g.fx_hi && __double2hiint(ty) == g.fx_hi;
+            const unsigned gx = (unsigned)ix >> fk, gy = (unsigned)iy >> fk;
+            const unsigned frx = (unsigned)ix & fmask, fry = (unsigned)iy & fmask;
+            // accepted when both fractions are >= margin away from 0 and 1: no integer lies between q~ and
+            // Java's quotient, so both truncate to the same cell
+            const bool ok = inrange && (frx - fmarg) < fspan && (fry - fmarg) < fspan;
+            const bool inb = gx < uW && gy < uH;
             bad |= ok ? 0u : (1u << u);
-            idx[u] = inb ? (unsigned)gy * uW + (unsigned)gx : oob;
+            idx[u] = (ok && inb) ? gy * uW + gx : oob;
         }
         double f[8];
 #pragma unroll

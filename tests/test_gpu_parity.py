@@ -193,3 +193,94 @@ def test_full_size_k2_properties(cuda):
     # room is +-9 m, robot within 6.1 m of the origin, 10 m range (+2 cells): |coord| < 16.2 m
     assert np.all(np.abs((xs + 0.5) * 0.05 - 25.6) < 16.2) and np.all(np.abs((ys + 0.5) * 0.05 - 25.6) < 16.2)
     h.close()
+
+
+# ---- paths that only large particle sets / unusual geometry reach ----
+def test_replay_sorted_scoring_path(cuda, oracle):
+    """>= 4096 particles on a shared map: heading-sorted k_score_sorted<G> with the fixed-point cell index,
+    717 beams (not a multiple of 8: remainder loop) and a 12 m map (end points outside: sentinel + exact path)."""
+    checks.replay_compare(cuda, oracle, P=6000, beams=717, steps=4, grid_m=12.0, mode=B.MAP_SHARED, max_range=30.0,
+                          resample_mode=B.RESAMPLE_FIXED, resample_every=1)
+    checks.replay_compare(cuda, oracle, P=5000, beams=360, steps=3, grid_m=51.2, mode=B.MAP_SHARED, max_range=30.0,
+                          resample_mode=B.RESAMPLE_FIXED, resample_every=2)
+
+
+def test_replay_other_resolution_generic_blur(cuda, oracle):
+    """0.02 m cells: sigma = sqrt(0.05/0.02) -> 11 taps: the generic (run-time width) likelihood kernel; odd,
+    non-square grid (scalar copy path)."""
+    from gridmap_slam_robot_b200 import synth
+
+    P, steps = 10, 4
+    kw = dict(num_particles=P, map_width_m=7.0 + 0.02, map_height_m=5.0 + 3 * 0.02, resolution=0.02, origin_x=-3.5,
+              origin_y=-2.5, resample_mode=B.RESAMPLE_LITERAL)
+    g, o = cuda.create(**kw), oracle.create(**kw)
+    assert g.info.kernel_taps == o.info.kernel_taps == 11 and (g.W * g.H) % 2 == 1
+    scans = synth.make_scans(steps, 120, max_range=3.0)
+    normals, uniforms = synth.make_draws(steps, P)
+    for s, sc in enumerate(scans):
+        a = (sc.beam_xy * 0.3, sc.beam_dist * 0.3, sc.beam_hit, sc.d_center, sc.d_theta, normals[s])
+        ng, no = g.update(*a), o.update(*a)
+        assert abs(ng / no - 1) < 1e-9 and np.array_equal(g.poses(), o.poses())
+        np.testing.assert_allclose(g.log_weights(), o.log_weights(), rtol=0, atol=1e-9)
+        g.resample(float(uniforms[s]))
+        o.resample(float(uniforms[s]))
+        assert np.array_equal(g.parents(), o.parents())
+        for p in (0, P - 1):
+            for kind in (B.MAP_FREE_COUNT, B.MAP_OCC_COUNT, B.MAP_LIKELIHOOD):
+                assert np.array_equal(g.get_map(p, kind), o.get_map(p, kind)), (s, p, kind)
+    g.close()
+    o.close()
+
+
+def test_degenerate_scans(cuda, oracle):
+    """All-miss scan (no scoring factors: uniform weights), zero-length and NaN/huge beams, particles far
+    outside the map: both sides agree, nothing crashes."""
+    P = 64
+    kw = dict(num_particles=P, map_width_m=6.0, map_height_m=6.0, origin_x=-3.0, origin_y=-3.0, map_mode=B.MAP_SHARED)
+    g, o = cuda.create(**kw), oracle.create(**kw)
+    rng = np.random.default_rng(2)
+    z = rng.standard_normal((P, 2))
+    n = 40
+    ang = 2 * np.pi * np.arange(n) / n
+    dist = np.full(n, 10.0)
+    xy = np.stack([dist * np.cos(ang), dist * np.sin(ang)], 1)
+    for hit in (np.zeros(n, np.uint8), np.ones(n, np.uint8)):
+        ng, no = g.update(xy, dist, hit, 0.0, 0.0, z), o.update(xy, dist, hit, 0.0, 0.0, z)
+        assert abs(ng / no - 1) < 1e-9
+        np.testing.assert_allclose(g.log_weights(), o.log_weights(), rtol=0, atol=1e-9)
+    xy2, d2 = xy.copy(), dist.copy()
+    xy2[0] = (0.0, 0.0); d2[0] = 0.0              # zero-length ray: start cell three times
+    xy2[1] = (1e30, -1e30); d2[1] = 1e30          # saturating (int) casts
+    xy2[2] = (np.nan, 1.0); d2[2] = np.nan        # NaN -> (int) 0
+    hit = np.ones(n, np.uint8)
+    ng, no = g.update(xy2, d2, hit, 0.05, 0.0, z), o.update(xy2, d2, hit, 0.05, 0.0, z)
+    assert np.array_equal(np.isnan(g.log_weights()), np.isnan(o.log_weights()))
+    fin = np.isfinite(o.log_weights())
+    np.testing.assert_allclose(g.log_weights()[fin], o.log_weights()[fin], rtol=0, atol=1e-9)
+    for kind in (B.MAP_FREE_COUNT, B.MAP_OCC_COUNT):
+        assert np.array_equal(g.get_map(0, kind), o.get_map(0, kind))
+    far = np.tile(np.asarray([[500.0, -500.0, 0.3]], np.float32), (P, 1))
+    g.set_poses(far); o.set_poses(far)
+    ng, no = g.update(xy, dist, hit, 0.0, 0.0, z), o.update(xy, dist, hit, 0.0, 0.0, z)
+    assert abs(ng / no - 1) < 1e-9 and np.array_equal(g.poses(), o.poses())
+    g.close()
+    o.close()
+
+
+def test_literal_vs_fixed_resampling_agree(cuda):
+    """The associative fixed-point CDF picks the same parents as Java's sequential f64 sum on random weights
+    (a disagreement needs U within ~1e-16 of a CDF step); the count is reported, and must be 0 here."""
+    rng = np.random.default_rng(9)
+    bad = 0
+    for n in (500, 2048, 20000):
+        w = rng.random(n) ** 6
+        w /= w.sum()
+        par = []
+        for mode in (B.RESAMPLE_LITERAL, B.RESAMPLE_FIXED):
+            h = cuda.create(num_particles=n, map_width_m=0.5, map_height_m=0.5, map_mode=B.MAP_SHARED, resample_mode=mode)
+            h.set_weights(w)
+            h.resample(0.123456789)
+            par.append(h.parents())
+            h.close()
+        bad += int(np.sum(par[0] != par[1]))
+    assert bad == 0
