@@ -310,6 +310,39 @@ def run_gpu(args, wl):
                "h2d_bytes_per_step": Bn * 25, "d2h_bytes_per_step": 2 * stats_bytes,
                "calls": "gms_update + gms_resample + gms_get_strongest + gms_get_weighted_pose "
                         "(GridMapApp.java:178-192), host beam arrays in pinned memory"}
+    if world > 1:
+        # e2e at N ranks: every rank stages the scan from pinned host memory each step (H2D inside the timed
+        # region), steps through the all-gather, and reads Neff back (D2H + sync) like SLAM.update's caller
+        pinned = [(torch.from_numpy(s.beam_xy).pin_memory(), torch.from_numpy(s.beam_dist).pin_memory(),
+                   torch.from_numpy(s.beam_hit).pin_memory()) for s in scans]
+        d_xy, d_d, d_h = torch.empty_like(t_xy[0]), torch.empty_like(t_d[0]), torch.empty_like(t_h[0])
+        n_e2e = max(3, min(args.steps, 200))
+
+        def e2e_step_mr(i):
+            k = i % nscan
+            d_xy.copy_(pinned[k][0], non_blocking=True)
+            d_d.copy_(pinned[k][1], non_blocking=True)
+            d_h.copy_(pinned[k][2], non_blocking=True)
+            runner.step(d_xy.data_ptr(), d_d.data_ptr(), d_h.data_ptr(), Bn, scans[k].d_center, scans[k].d_theta,
+                        policy=B.POLICY_ALWAYS)
+            return h.read_neff()
+
+        for i in range(3):
+            e2e_step_mr(i)
+        barrier()
+        t0 = time.perf_counter()
+        sc = 0
+        for i in range(n_e2e):
+            e2e_step_mr(3 + i)
+            sc += P_total * hits[(3 + i) % nscan]
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        te = float(te.item())
+        e2e = {"value": sc / te, "unit": "scores/s", "ms_per_step": 1e3 * te / n_e2e, "steps": n_e2e,
+               "h2d_bytes_per_step": Bn * 25 * world, "d2h_bytes_per_step": 104 * world,
+               "calls": "per rank: H2D of the scan from pinned memory + gms_update_begin_dev + ncclAllGather + "
+                        "gms_update_end_dev(resample) + gms_read_neff"}
     if rank != 0:
         return
     peak, peak_src = peaks()

@@ -234,15 +234,39 @@ __device__ __forceinline__ void apply_measurement(CellCounts* __restrict__ map, 
     box.x0 = box.x1 = it.x;
     box.y0 = box.y1 = it.y;
     int lx = it.x, ly = it.y;
+    // The returned counters are only needed for the (rare) dirty-tile marking.  Four increments are issued
+    // back to back before the first result is inspected, so four atomics are in flight per thread instead
+    // of one (a branch on the returned value would otherwise stall the warp for a full L2 round trip).
     while (it.has_next(g.W, g.H)) {
-        lx = it.x;
-        ly = it.y;
-        const float dX = sx - ((float)lx + 0.5f);
-        const float dY = sy - ((float)ly + 0.5f);
-        const float dist = __fsqrt_rn(dX * dX + dY * dY);  // (float) Math.sqrt((double) f32) == sqrt.rn.f32
-        const int cls = inverse_sensor_class(dist, meas, was_hit, g.tol_half);
-        if (cls != 0) bump_cell(map, bitmap, lx, ly, cls, g);
-        it.advance();
+        int cx[4], cy[4], cl[4];
+        int n = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) cl[j] = 0;
+        while (n < 4 && it.has_next(g.W, g.H)) {
+            lx = it.x;
+            ly = it.y;
+            const float dX = sx - ((float)lx + 0.5f);
+            const float dY = sy - ((float)ly + 0.5f);
+            const float dist = __fsqrt_rn(dX * dX + dY * dY);  // (float) Math.sqrt((double) f32) == sqrt.rn.f32
+            const int cls = inverse_sensor_class(dist, meas, was_hit, g.tol_half);
+            if (cls != 0) {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (j == n) { cx[j] = lx; cy[j] = ly; cl[j] = cls; }
+                n++;
+            }
+            it.advance();
+        }
+        unsigned long long old[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (cl[j] != 0)
+                old[j] = atomicAdd(reinterpret_cast<unsigned long long*>(map + ((size_t)cx[j] + (size_t)cy[j] * g.W)),
+                                   cl[j] == 1 ? 1ull : (1ull << 32));
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (cl[j] != 0 && code_flips((uint32_t)old[j], (uint32_t)(old[j] >> 32), cl[j], g))
+                mark_dirty(bitmap, cx[j], cy[j], g);
     }
     // the walk is monotone in x and in y: its bounding box is spanned by the first and last cell
     box.x0 = min(box.x0, lx); box.x1 = max(box.x1, lx);

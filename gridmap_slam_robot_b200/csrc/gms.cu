@@ -39,8 +39,8 @@ struct gms_handle {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // shared map: two side streams let independent chains of one step overlap (likelihood refresh next to
     // motion + heading sort; map integration next to resampling); joined back before anything depends on them
-    cudaStream_t side_a = nullptr, side_b = nullptr;
-    cudaEvent_t ev_fork_a = nullptr, ev_done_a = nullptr, ev_fork_b = nullptr, ev_done_b = nullptr;
+    cudaStream_t side_a = nullptr, side_b = nullptr, side_c = nullptr;
+    cudaEvent_t ev_fork_a = nullptr, ev_done_a = nullptr, ev_fork_b = nullptr, ev_done_b = nullptr, ev_done_c = nullptr;
     bool overlap = true;  // GMS_NO_OVERLAP=1 serialises everything on one stream
     bool b_pending = false;  // a map integration is still running on side_b (joined by the next consumer)
     // particle state (double buffered for resampling)
@@ -232,6 +232,7 @@ void free_all(gms_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->side_a) cudaStreamSynchronize(h->side_a);
     if (h->side_b) cudaStreamSynchronize(h->side_b);
+    if (h->side_c) cudaStreamSynchronize(h->side_c);
     for (int q = 0; q < kMaxRanks; q++)
         for (int k = 0; k < 4; k++)
             if (h->ipc_opened[q][k]) cudaIpcCloseMemHandle(h->ipc_opened[q][k]);
@@ -255,7 +256,8 @@ void free_all(gms_handle* h) {
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->side_a) cudaStreamDestroy(h->side_a);
     if (h->side_b) cudaStreamDestroy(h->side_b);
-    for (cudaEvent_t e : {h->ev_fork_a, h->ev_done_a, h->ev_fork_b, h->ev_done_b})
+    if (h->side_c) cudaStreamDestroy(h->side_c);
+    for (cudaEvent_t e : {h->ev_fork_a, h->ev_done_a, h->ev_fork_b, h->ev_done_b, h->ev_done_c})
         if (e) cudaEventDestroy(e);
     delete h;
 }
@@ -278,6 +280,7 @@ int ensure_beams(gms_handle* h, int B) {
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaStreamSynchronize(h->side_a));
     CK(cudaStreamSynchronize(h->side_b));
+    CK(cudaStreamSynchronize(h->side_c));
     h->b_pending = false;
     cudaFree(h->in_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
     for (int i = 0; i < 2; i++) { cudaFree(h->all_xy2[i]); cudaFree(h->all_hit2[i]); cudaFree(h->meas2[i]); h->all_xy2[i] = nullptr; h->all_hit2[i] = nullptr; h->meas2[i] = nullptr; }
@@ -331,14 +334,8 @@ int fetch_stats(gms_handle* h) {
 int launch_pack(gms_handle* h, const double* d_xy, const double* d_dist, const uint8_t* d_hit, int B) {
     int rc = ensure_beams(h, B);
     if (rc) return rc;
-    if (B > 0) {
-        if ((const void*)d_xy != (const void*)h->all_xy)
-            CK(cudaMemcpyAsync(h->all_xy, d_xy, (size_t)B * 16, cudaMemcpyDeviceToDevice, h->stream));
-        if ((const void*)d_hit != (const void*)h->all_hit)
-            CK(cudaMemcpyAsync(h->all_hit, d_hit, (size_t)B, cudaMemcpyDeviceToDevice, h->stream));
-    }
-    LAUNCH(GMS_PHASE_SCORE, k_pack_beams<<<1, 256, 0, h->stream>>>(h->all_xy, d_dist, h->all_hit, B, h->g.res_f,
-                                                                   h->hit_xy, h->meas, h->st));
+    LAUNCH(GMS_PHASE_SCORE, k_pack_beams<<<1, 256, 0, h->stream>>>((const double2*)d_xy, d_dist, d_hit, B, h->g.res_f,
+                                                                   h->hit_xy, h->meas, h->all_xy, h->all_hit, h->st));
     return GMS_OK;
 }
 
@@ -443,8 +440,18 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
         CK(cudaStreamWaitEvent(h->stream, h->ev_done_b, 0));
         h->b_pending = false;
     }
-    rc = launch_pack(h, d_xy, d_dist, d_hit, B);
-    if (rc) return rc;
+    if (fork) {  // the beam table is only needed by the scoring: build it next to the motion update
+        cudaStream_t main = h->stream;
+        CK(cudaStreamWaitEvent(h->side_c, h->ev_fork_a, 0));
+        h->stream = h->side_c;
+        rc = launch_pack(h, d_xy, d_dist, d_hit, B);
+        h->stream = main;
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev_done_c, h->side_c));
+    } else {
+        rc = launch_pack(h, d_xy, d_dist, d_hit, B);
+        if (rc) return rc;
+    }
     {
         Phase ph(h, GMS_PHASE_MOTION);
         // Odometry.recalculateStdDev Odometry.java:60-69
@@ -462,6 +469,7 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
     }
     if (fork) {
         CK(cudaStreamWaitEvent(h->stream, h->ev_done_a, 0));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_done_c, 0));
     } else {
         rc = launch_likelihood(h);
         if (rc) return rc;
@@ -760,6 +768,8 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     h->stream = h->own_stream;
     CKC(cudaStreamCreateWithFlags(&h->side_a, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&h->side_b, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&h->side_c, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&h->ev_done_c, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_fork_a, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_done_a, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_fork_b, cudaEventDisableTiming));

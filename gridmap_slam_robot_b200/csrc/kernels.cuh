@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(256) k_pack_beams(const double2* __restrict__ 
                                                     const double* __restrict__ in_dist,
                                                     const uint8_t* __restrict__ in_hit, int B, float res_f,
                                                     double2* __restrict__ hit_xy, float* __restrict__ meas,
+                                                    double2* __restrict__ all_xy, uint8_t* __restrict__ all_hit,
                                                     Stats* __restrict__ st) {
     __shared__ int s_warp[8];
     __shared__ int s_base;
@@ -58,7 +59,11 @@ __global__ void __launch_bounds__(256) k_pack_beams(const double2* __restrict__ 
     for (int b0 = 0; b0 < B; b0 += 256) {
         const int b = b0 + tid;
         const bool hit = b < B && in_hit[b] != 0;
-        if (b < B) meas[b] = (float)in_dist[b] / res_f;
+        if (b < B) {
+            meas[b] = (float)in_dist[b] / res_f;
+            if (all_xy != in_xy) all_xy[b] = in_xy[b];  // private copy: the map integration reads it later
+            if (all_hit != in_hit) all_hit[b] = in_hit[b];
+        }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (lane == 0) s_warp[wid] = __popc(m);
         __syncthreads();
@@ -265,13 +270,38 @@ __global__ void __launch_bounds__(256) k_likelihood(const CellCounts* __restrict
         // 1. threshold the log-odds against logOdds(0.5) == 0.0 (GridMap.java:238-245); cells outside
         //    the map contribute 0 — Java skips those taps, and total + k*0.0 == total.
         const int twu = kTileW + 2 * k;  // used columns
-        for (int e = tid; e < th * twu; e += 256) {
-            const int ly = e / twu, lx = e - ly * twu;
-            const int gx = ox + lx - k, gy = oy + ly - k;
-            float code = 0.0f;
-            if (gx >= 0 && gx < g.W && gy >= 0 && gy < g.H)
-                code = 0.5f * (float)cell_code_fast(cmap[(size_t)gx + (size_t)gy * g.W], g);
-            s_t[ly * tw + lx] = code;
+        if (KH) {
+            // all global loads of the tile + halo are issued before the first one is consumed
+            constexpr int kPer = ((kTileH + 2 * KH) * (kTileW + 2 * KH) + 255) / 256;
+            CellCounts c[kPer];
+            int where[kPer];  // smem offset, or -1 outside the tile list / -2 outside the map
+#pragma unroll
+            for (int j = 0; j < kPer; j++) {
+                const int e = tid + j * 256;
+                where[j] = -1;
+                c[j] = CellCounts{0u, 0u};
+                if (e < th * twu) {
+                    const int ly = e / twu, lx = e - ly * twu;
+                    const int gx = ox + lx - k, gy = oy + ly - k;
+                    where[j] = ly * tw + lx;
+                    if (gx >= 0 && gx < g.W && gy >= 0 && gy < g.H) c[j] = cmap[(size_t)gx + (size_t)gy * g.W];
+                    else where[j] = -2 - where[j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kPer; j++) {
+                if (where[j] >= 0) s_t[where[j]] = 0.5f * (float)cell_code_fast(c[j], g);
+                else if (where[j] <= -2) s_t[-2 - where[j]] = 0.0f;
+            }
+        } else {
+            for (int e = tid; e < th * twu; e += 256) {
+                const int ly = e / twu, lx = e - ly * twu;
+                const int gx = ox + lx - k, gy = oy + ly - k;
+                float code = 0.0f;
+                if (gx >= 0 && gx < g.W && gy >= 0 && gy < g.H)
+                    code = 0.5f * (float)cell_code_fast(cmap[(size_t)gx + (size_t)gy * g.W], g);
+                s_t[ly * tw + lx] = code;
+            }
         }
         __syncthreads();
         if (KH) {
@@ -1269,17 +1299,25 @@ __global__ void __launch_bounds__(256) k_copy_maps(CellCounts* __restrict__ coun
     const double* ls = src_lik + (size_t)src * cells;
     double* ld = lik + (size_t)dst * cells;
     if (((cells | (size_t)W) & 1) == 0) {  // even row length and slot size: rows start 16-byte aligned
-        const int x0 = r.x & ~1, n2 = ((r.z | 1) - x0 + 1) / 2;  // pairs of cells
-        for (int y = y0; y < y1; y++) {
-            const size_t o = ((size_t)y * W + x0) / 2;
-            const uint4* cs4 = reinterpret_cast<const uint4*>(cs) + o;
-            uint4* cd4 = reinterpret_cast<uint4*>(cd) + o;
-            const uint4* ls4 = reinterpret_cast<const uint4*>(ls) + o;
-            uint4* ld4 = reinterpret_cast<uint4*>(ld) + o;
-            for (int i = threadIdx.x; i < n2; i += 256) {
-                cd4[i] = cs4[i];
-                ld4[i] = ls4[i];
+        const int x0 = r.x & ~1, n2 = ((r.z | 1) - x0 + 1) / 2;  // pairs of cells per row
+        const uint4* cs4 = reinterpret_cast<const uint4*>(cs);
+        uint4* cd4 = reinterpret_cast<uint4*>(cd);
+        const uint4* ls4 = reinterpret_cast<const uint4*>(ls);
+        uint4* ld4 = reinterpret_cast<uint4*>(ld);
+        const int total = (y1 - y0) * n2;  // (row, pair) flattened: 4 independent 16-byte loads per array in flight
+        for (int e0 = threadIdx.x; e0 < total; e0 += 4 * 256) {
+            size_t o[4];
+            uint4 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = e0 + u * 256;
+                const int yy = e / n2, xx = e - yy * n2;
+                o[u] = ((size_t)(y0 + yy) * W + x0) / 2 + xx;
+                if (e < total) { a[u] = cs4[o[u]]; b[u] = ls4[o[u]]; }
             }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (e0 + u * 256 < total) { cd4[o[u]] = a[u]; ld4[o[u]] = b[u]; }
         }
     } else {
         const int n = r.z - r.x + 1;
