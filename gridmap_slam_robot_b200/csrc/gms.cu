@@ -193,6 +193,9 @@ inline void count_launch(gms_handle* h, int phase) {
 int flush_profile(gms_handle* h) {
     if (h->spans.empty()) return GMS_OK;
     CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->side_a));  // phases of the shared-map step are timed on the stream they run on
+    CK(cudaStreamSynchronize(h->side_b));
+    CK(cudaStreamSynchronize(h->side_c));
     for (auto& s : h->spans) {
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, s.a, s.b));
@@ -1203,7 +1206,7 @@ EXPORT int gms_read_neff(gms_handle* h, double* neff) {
     return GMS_OK;
 }
 EXPORT int gms_sync(gms_handle* h) {
-    ENTER(h);
+    ENTER(h);  // joins a pending map integration into the main stream first
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }
