@@ -525,7 +525,8 @@ EXPORT int gms_reset(gms_handle *h) {
 
 static int ensure_scratch(gms_handle *h) {
     if (h->prob_scratch) return 1;
-    size_t n = (size_t)h->W * h->H * (size_t)h->threads;
+    /* per-thread scratch only where threads blur different maps (per-particle mode) */
+    size_t n = (size_t)h->W * h->H * (size_t)(h->cfg.map_mode == GMS_MAP_SHARED ? 1 : h->threads);
     h->prob_scratch = malloc(n * sizeof(double));
     h->tmp_scratch = malloc(n * sizeof(double));
     return h->prob_scratch && h->tmp_scratch;
