@@ -239,23 +239,21 @@ __device__ __forceinline__ void apply_measurement(CellCounts* __restrict__ map, 
     // of one (a branch on the returned value would otherwise stall the warp for a full L2 round trip).
     while (it.has_next(g.W, g.H)) {
         int cx[4], cy[4], cl[4];
-        int n = 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) cl[j] = 0;
-        while (n < 4 && it.has_next(g.W, g.H)) {
-            lx = it.x;
-            ly = it.y;
-            const float dX = sx - ((float)lx + 0.5f);
-            const float dY = sy - ((float)ly + 0.5f);
-            const float dist = __fsqrt_rn(dX * dX + dY * dY);  // (float) Math.sqrt((double) f32) == sqrt.rn.f32
-            const int cls = inverse_sensor_class(dist, meas, was_hit, g.tol_half);
-            if (cls != 0) {
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (j == n) { cx[j] = lx; cy[j] = ly; cl[j] = cls; }
-                n++;
+        for (int j = 0; j < 4; j++) {  // four DDA steps (statically indexed registers, predicated past the end)
+            const bool live = it.has_next(g.W, g.H);
+            cx[j] = it.x;
+            cy[j] = it.y;
+            cl[j] = 0;
+            if (live) {
+                lx = it.x;
+                ly = it.y;
+                const float dX = sx - ((float)lx + 0.5f);
+                const float dY = sy - ((float)ly + 0.5f);
+                const float dist = __fsqrt_rn(dX * dX + dY * dY);  // (float) Math.sqrt((double) f32) == sqrt.rn.f32
+                cl[j] = inverse_sensor_class(dist, meas, was_hit, g.tol_half);
+                it.advance();
             }
-            it.advance();
         }
         unsigned long long old[4];
 #pragma unroll

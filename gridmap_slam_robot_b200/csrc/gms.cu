@@ -917,10 +917,8 @@ EXPORT int gms_resample(gms_handle* h, double u01) {
     ENTER(h);
     if (u01 >= 1.0) return fail(h, GMS_ERR_INVALID_ARG, "gms_resample: u01 must be < 1");
     LAUNCH(GMS_PHASE_RESAMPLE, k_set_resample_flag<<<1, 1, 0, h->stream>>>(h->st, 1));
-    int rc = launch_resample(h, u01);
-    if (rc) return rc;
-    CK(cudaStreamSynchronize(h->stream));
-    return GMS_OK;
+    // SLAM.resample() returns nothing: the work is only enqueued; every getter synchronises before it reads
+    return launch_resample(h, u01);
 }
 
 EXPORT int gms_calculate_neff(gms_handle* h, double* neff_out) {

@@ -127,7 +127,8 @@ int gms_update(gms_handle* h, const double* beam_xy, const double* beam_dist, co
                double* neff_out);
 
 /* SLAM.resample() SLAM.java:133-153.  u01 in [0,1) replaces Math.random() (SLAM.java:136);
- * u01 < 0 draws it from the handle's Philox stream. */
+ * u01 < 0 draws it from the handle's Philox stream.  Like the Java method it returns nothing to wait for:
+ * the work is enqueued on the handle's stream and observed through the getters (which synchronise). */
 int gms_resample(gms_handle* h, double u01);
 
 int gms_calculate_neff(gms_handle* h, double* neff_out);    /* SLAM.calculateNeff SLAM.java:180-190 */
