@@ -21,7 +21,6 @@ struct Geometry {
     float tol_half;           // hitTolerance / 2 (SensorModel.java:35-37)
     double res, posx, posy;   // (double) resolution / position: the promotions Java performs
     double inv_res;           // 1.0 / res — only for the guarded fast path of cell_of()
-    double half_margin;       // 0.5 - 1e-5: fast-path acceptance band (legacy, unused by the integer path)
     // fixed-point fast path of k_score_sorted: q + fx_magic puts round(q * 2^fx_k) into the low mantissa word
     double fx_magic;          // 1.5 * 2^(52 - fx_k)
     int fx_k;                 // fraction bits: max(W, H) * 2^fx_k < 2^30

@@ -724,7 +724,6 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     g.tol_half = cfg->hit_tolerance / 2;
     g.res = (double)cfg->resolution; g.posx = (double)cfg->origin_x; g.posy = (double)cfg->origin_y;
     g.inv_res = 1.0 / g.res;
-    g.half_margin = 0.5 - 1e-5;
     {
         int bits = 1;
         while ((1 << bits) <= std::max(h->W, h->H)) bits++;  // max(W, H) < 2^bits

@@ -1066,21 +1066,6 @@ __global__ void __launch_bounds__(256) k_select(const void* __restrict__ cdf_raw
     lw_out[m0] = lw_in[lo];
 }
 
-// (stand-alone gather, kept for callers that already hold parent indices)
-// new generation = copies of the chosen parents (Particle(Particle) SLAM.java:41-45: weight and pose
-// are copied; weights are NOT reset to 1/N)
-__global__ void __launch_bounds__(256) k_gather(const int* __restrict__ parents, int P,
-                                                const float4* __restrict__ pose_in, const double* __restrict__ w_in,
-                                                const double* __restrict__ lw_in, float4* __restrict__ pose_out,
-                                                double* __restrict__ w_out, double* __restrict__ lw_out) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= P) return;
-    const int p = parents[m];
-    pose_out[m] = pose_in[p];
-    w_out[m] = w_in[p];
-    lw_out[m] = lw_in[p];
-}
-
 // Per-particle maps: slot assignment.  parents[] is non-decreasing, so the first child of a parent is
 // where parents[m] != parents[m-1]; it keeps the parent's slot (no copy).  Every further child
 // ("duplicate") takes, in order, the slot of a parent that has no child at all.  One CTA; two

@@ -284,3 +284,61 @@ def test_literal_vs_fixed_resampling_agree(cuda):
             h.close()
         bad += int(np.sum(par[0] != par[1]))
     assert bad == 0
+
+
+def test_device_side_resample_policy(cuda, oracle):
+    """GMS_RESAMPLE_IF_NEFF_LOW decides on the device (no host round trip) what GridMapApp.java:185 decides
+    on the host: resample iff neff < P/2.  The device-policy run must equal a run where the host applies
+    the same rule with gms_update + gms_resample, and the oracle doing the same."""
+    import torch
+
+    from gridmap_slam_robot_b200 import synth
+
+    P, steps, beams = 512, 10, 180
+    kw = dict(num_particles=P, map_width_m=20.0, map_height_m=20.0, origin_x=-10.0, origin_y=-10.0,
+              map_mode=B.MAP_SHARED, resample_mode=B.RESAMPLE_LITERAL)
+    scans = synth.make_scans(steps, beams)
+    normals, uniforms = synth.make_draws(steps, P)
+    dev = torch.device("cuda:0")
+    gd, gh, o = cuda.create(**kw), cuda.create(**kw), oracle.create(**kw)
+    resampled = 0
+    for s, sc in enumerate(scans):
+        t = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (sc.beam_xy, sc.beam_dist, sc.beam_hit, normals[s])]
+        torch.cuda.synchronize()
+        gd.step_dev(t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), beams, sc.d_center, sc.d_theta, t[3].data_ptr(),
+                    B.POLICY_IF_NEFF_LOW, float(uniforms[s]))
+        neff_d = gd.read_neff()
+        for h in (gh, o):
+            neff = h.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta, normals[s])
+            if neff < P // 2:
+                h.resample(float(uniforms[s]))
+                resampled += h is gh
+        assert abs(neff_d / neff - 1) < 1e-9
+        assert np.array_equal(gd.poses(), gh.poses()) and np.array_equal(gd.poses(), o.poses()), s
+        np.testing.assert_allclose(gd.weights(), o.weights(), rtol=1e-9, atol=1e-300)
+        assert np.array_equal(gd.get_map(0, B.MAP_FREE_COUNT), o.get_map(0, B.MAP_FREE_COUNT))
+    assert 0 < resampled < steps  # the schedule exercised both branches
+    for h in (gd, gh, o):
+        h.close()
+
+
+def test_strongest_survives_resampling_like_the_reference(cuda, oracle):
+    """GridMapApp keeps `strongestParticle` across the resample (GridMapApp.java:188-190): its pose and weight are
+    those of the last update even though the particle list was replaced."""
+    from gridmap_slam_robot_b200 import synth
+
+    P = 200
+    kw = dict(num_particles=P, map_width_m=20.0, map_height_m=20.0, origin_x=-10.0, origin_y=-10.0)
+    sc = synth.make_scans(2, 90)
+    z = synth.make_draws(2, P)[0]
+    for lib in (cuda, oracle):
+        h = lib.create(**kw)
+        h.update(sc[0].beam_xy, sc[0].beam_dist, sc[0].beam_hit, 0.05, 0.01, z[0])
+        h.update(sc[1].beam_xy, sc[1].beam_dist, sc[1].beam_hit, 0.05, 0.01, z[1])
+        idx, pose, w = h.strongest()
+        assert np.array_equal(pose, h.poses()[idx]) and w == h.weights()[idx] == h.weights().max()
+        h.resample(0.77)
+        idx2, pose2, w2 = h.strongest()
+        assert idx2 == idx and np.array_equal(pose2, pose) and w2 == w
+        assert any(np.array_equal(pose, p) for p in h.poses())  # the strongest particle always survives
+        h.close()
