@@ -95,6 +95,8 @@ struct gms_handle {
     double* wp_part = nullptr;
     unsigned* wp_counter = nullptr;
     bool tile_fx_valid = false;
+    int np_cap = 0;
+    int score_parts = 0;  // > 0: the last scoring launch already wrote that many (m, idx, s) partials
     int score_g = 0;  // sub-threads per particle in k_score_sorted (0 = automatic; GMS_SCORE_G overrides: tuning knob)
     int num_sms = 148;
     int* ray_maxlen = nullptr;
@@ -379,10 +381,13 @@ int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* 
         if (h->score_g) G = h->score_g;
         const int* order = use_sorted_score(h) ? h->order : nullptr;
         const unsigned grid = blocks_for((long long)cnt * G, 128);
+        const int emit = h->cfg.nranks == 1 && (int)grid <= h->np_cap;  // normalise consumes the CTA partials directly
+        h->score_parts = emit ? (int)grid : 0;
 #define SCORE_G(GG)                                                                                              \
     case GG:                                                                                                     \
         LAUNCH(GMS_PHASE_SCORE, k_score_sorted<GG><<<grid, 128, smem_s, h->stream>>>(pose, lo, cnt, h->hit_xy, h->st, \
-                                                                                      h->fac, order, lw, xlocal, h->g)); \
+                                                                                      h->fac, order, lw, xlocal, h->np, \
+                                                                                      emit, h->g));              \
         break;
         switch (G) {
             SCORE_G(1) SCORE_G(2) SCORE_G(4) SCORE_G(8) SCORE_G(16) SCORE_G(32)
@@ -562,10 +567,15 @@ int step_end(gms_handle* h, int policy, double u01) {
                                         h->xglobal, h->P, h->lw[h->cur], h->pose[h->cur]));
     {
         Phase ph(h, GMS_PHASE_NORMALISE);
-        LAUNCH(GMS_PHASE_NORMALISE, k_softmax_partials<<<h->ntiles, 1024, 0, h->stream>>>(h->lw[h->cur], h->P, h->np));
+        int nparts = h->score_parts;
+        h->score_parts = 0;
+        if (nparts == 0) {
+            nparts = h->ntiles;
+            LAUNCH(GMS_PHASE_NORMALISE, k_softmax_partials<<<h->ntiles, 1024, 0, h->stream>>>(h->lw[h->cur], h->P, h->np));
+        }
         LAUNCH(GMS_PHASE_NORMALISE, k_normalise<<<h->ntiles, 1024, 0, h->stream>>>(
-                                        h->lw[h->cur], h->w[h->cur], h->pose[h->cur], h->P, h->ntiles, policy, h->np,
-                                        h->st));
+                                        h->lw[h->cur], h->w[h->cur], h->pose[h->cur], h->P, h->ntiles, nparts, policy,
+                                        h->np, h->st));
         h->tile_fx_valid = true;
     }
     const bool skip = std::fabs(h->pend_dtheta) > (M_PI / 180.0) * c.skip_update_deg;
@@ -824,9 +834,10 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, h->dev) == cudaSuccess) h->num_sms = prop.multiProcessorCount; }
     {
         const size_t nt = (size_t)h->ntiles;
-        CKC(cudaMalloc((void**)&h->np.m, nt * 8));
-        CKC(cudaMalloc((void**)&h->np.idx, nt * 4));
-        CKC(cudaMalloc((void**)&h->np.s, nt * 8));
+        h->np_cap = std::max(h->ntiles, std::max(3200, (h->cnt + 127) / 128));  // score CTAs may outnumber the tiles
+        CKC(cudaMalloc((void**)&h->np.m, (size_t)h->np_cap * 8));
+        CKC(cudaMalloc((void**)&h->np.idx, (size_t)h->np_cap * 4));
+        CKC(cudaMalloc((void**)&h->np.s, (size_t)h->np_cap * 8));
         CKC(cudaMalloc((void**)&h->np.ws, nt * 8));
         CKC(cudaMalloc((void**)&h->np.q, nt * 8));
         CKC(cudaMalloc((void**)&h->np.fx, nt * 8));

@@ -7,6 +7,7 @@
 //   rect   int4[S]                   bounding box of every cell touched since reset ("explored")
 //   dirty  u32[S][tile_words]        bitmap of likelihood tiles whose thresholded codes changed
 #pragma once
+#include <type_traits>
 #include "device_math.cuh"
 
 namespace gms {
@@ -32,6 +33,17 @@ struct ExchangeRec {  // 24 B, gms.h "Exchange record"
     float x, y, t;
     uint32_t pad;
 };
+
+struct NormPartials {   // partial results of normalise: per score CTA (m, idx, s) and per 1024-particle tile (ws, q, fx)
+    double* m;          // tile max of lw
+    int* idx;           // first index of the tile max
+    double* s;          // sum exp(lw - tile max)
+    double* ws;         // sum of normalised weights of the tile
+    double* q;          // sum of squared normalised weights of the tile
+    unsigned long long* fx;  // sum of trunc(w * 2^60) of the tile (feeds k_cdf_fixed)
+    unsigned* counter;  // last-block-done ticket
+};
+#define kNegInf (__longlong_as_double((long long)0xfff0000000000000ULL))
 
 constexpr int kMaxRanks = 16;
 struct PeerTable {  // per-particle maps across ranks: every rank's arenas, mapped into this process (cudaIpc)
@@ -471,9 +483,12 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
                                                       const double2* __restrict__ hit_xy,
                                                       const Stats* __restrict__ st, const double* __restrict__ fac,
                                                       const int* __restrict__ order, double* __restrict__ lw,
-                                                      ExchangeRec* __restrict__ xlocal, Geometry g) {
+                                                      ExchangeRec* __restrict__ xlocal, NormPartials np,
+                                                      int emit_partials, Geometry g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ double s_red[4];
+    __shared__ int s_redi[4];
     double2* s_xy = reinterpret_cast<double2*>(smem_raw);
     const int nh = st->num_hit;
     const int tid = threadIdx.x;
@@ -588,13 +603,46 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
             exp2 += __shfl_xor_sync(0xffffffffu, exp2, o);
         }
     }
-    if (li < 0 || gsub != 0) return;
+    const bool writer = li >= 0 && gsub == 0;
     const double l = log(mant) + (double)exp2 * 0.6931471805599453;
-    lw[lo + li] = l;
-    if (xlocal) {
-        ExchangeRec r;
-        r.lw = l; r.x = p.x; r.y = p.y; r.t = p.z; r.pad = 0;
-        xlocal[li] = r;
+    if (writer) {
+        lw[lo + li] = l;
+        if (xlocal) {
+            ExchangeRec r;
+            r.lw = l; r.x = p.x; r.y = p.y; r.t = p.z; r.pad = 0;
+            xlocal[li] = r;
+        }
+    }
+    if (!emit_partials) return;
+    // epilogue (single-rank shared map): this CTA's (max, first arg-max, sum exp(lw - max)) for k_normalise,
+    // which saves the separate pass over lw.  The combination in k_normalise is order-independent.
+    const int lane = tid & 31, wid = tid >> 5;
+    double best = writer ? l : kNegInf;
+    int bi = writer ? lo + li : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { s_red[wid] = best; s_redi[wid] = bi; }
+    __syncthreads();
+    best = s_red[0]; bi = s_redi[0];
+#pragma unroll
+    for (int k = 1; k < 4; k++)
+        if (k < (int)(blockDim.x >> 5) && (s_red[k] > best || (s_red[k] == best && s_redi[k] < bi))) { best = s_red[k]; bi = s_redi[k]; }
+    double e = writer ? exp(l - best) : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    __syncthreads();
+    if (lane == 0) s_red[wid] = e;
+    __syncthreads();
+    if (tid == 0) {
+        double sum = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) sum += s_red[k];
+        np.m[blockIdx.x] = best;
+        np.idx[blockIdx.x] = bi;
+        np.s[blockIdx.x] = sum;
     }
 }
 
@@ -779,17 +827,6 @@ __device__ __forceinline__ void block_argmax_1024(double& best, int& bi, double*
     }
 }
 
-struct NormPartials {   // one entry per CTA (tile of 1024 particles)
-    double* m;          // tile max of lw
-    int* idx;           // first index of the tile max
-    double* s;          // sum exp(lw - tile max)
-    double* ws;         // sum of normalised weights of the tile
-    double* q;          // sum of squared normalised weights of the tile
-    unsigned long long* fx;  // sum of trunc(w * 2^60) of the tile (feeds k_cdf_fixed)
-    unsigned* counter;  // last-block-done ticket
-};
-#define kNegInf (__longlong_as_double((long long)0xfff0000000000000ULL))
-
 // pass 1: per-tile (max, first arg-max, sum exp(lw - tile max))
 __global__ void __launch_bounds__(1024) k_softmax_partials(const double* __restrict__ lw, int P, NormPartials np) {
     __shared__ double s_key[32];
@@ -814,8 +851,8 @@ __global__ void __launch_bounds__(1024) k_softmax_partials(const double* __restr
 // order) into Neff (SLAM.java:180-190: 1 / sum (w / sum w)^2, evaluated as (sum w)^2 / sum w^2) and
 // publishes the step's statistics.
 __global__ void __launch_bounds__(1024) k_normalise(const double* __restrict__ lw, double* __restrict__ w,
-                                                    const float4* __restrict__ pose, int P, int ntiles, int policy,
-                                                    NormPartials np, Stats* __restrict__ st) {
+                                                    const float4* __restrict__ pose, int P, int ntiles, int nparts,
+                                                    int policy, NormPartials np, Stats* __restrict__ st) {
     __shared__ double s_key[32];
     __shared__ int s_idx[32];
     __shared__ double s_d[32];
@@ -824,14 +861,14 @@ __global__ void __launch_bounds__(1024) k_normalise(const double* __restrict__ l
     const int tid = threadIdx.x;
     double best = kNegInf;
     int bi = 0x7fffffff;
-    for (int c = tid; c < ntiles; c += 1024) {
+    for (int c = tid; c < nparts; c += 1024) {
         const double v = np.m[c];
         const int vi = np.idx[c];
         if (v > best || (v == best && vi < bi)) { best = v; bi = vi; }
     }
     block_argmax_1024(best, bi, s_key, s_idx);
     double acc = 0.0;
-    for (int c = tid; c < ntiles; c += 1024) acc += np.s[c] * exp(np.m[c] - best);
+    for (int c = tid; c < nparts; c += 1024) acc += np.s[c] * exp(np.m[c] - best);
     const double S = block_reduce_1024(acc, SumOp(), s_d);
     const int i = blockIdx.x * 1024 + tid;
     double wi = 0.0;
@@ -1033,9 +1070,19 @@ __global__ void __launch_bounds__(256) k_select(const void* __restrict__ cdf_raw
                                                 const double* __restrict__ w_in, const double* __restrict__ lw_in,
                                                 float4* __restrict__ pose_out, double* __restrict__ w_out,
                                                 double* __restrict__ lw_out) {
+    __shared__ unsigned long long s_coarse[2048];
     const int m0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool resample = st->do_resample != 0;  // uniform over the grid
+    int stride = 32;
+    while ((P + stride - 1) / stride > 2048) stride <<= 1;
+    const int ncoarse = (P + stride - 1) / stride;
+    if (resample) {
+        const unsigned long long* raw = static_cast<const unsigned long long*>(cdf_raw);  // 8-byte keys either way
+        for (int j = threadIdx.x; j < ncoarse; j += 256) s_coarse[j] = raw[min(P - 1, (j + 1) * stride - 1)];
+        __syncthreads();
+    }
     if (m0 >= P) return;
-    if (!st->do_resample) {
+    if (!resample) {
         parents[m0] = m0;
         pose_out[m0] = pose_in[m0];
         w_out[m0] = w_in[m0];
@@ -1045,20 +1092,22 @@ __global__ void __launch_bounds__(256) k_select(const void* __restrict__ cdf_raw
     if (u01 < 0.0) u01 = philox_uniform(seed, resample_count);
     const double r = u01 * 1.0 / (double)P;
     const double U = r + (double)m0 * 1.0 / (double)P;
-    int lo = 0, hi = P - 1;
-    if (FIXED) {
-        const unsigned long long* cdf = static_cast<const unsigned long long*>(cdf_raw);
-        const unsigned long long Uq = (unsigned long long)(U * 0x1p60);
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (Uq > cdf[mid]) lo = mid + 1; else hi = mid;
-        }
-    } else {
-        const double* cdf = static_cast<const double*>(cdf_raw);
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (U > cdf[mid]) lo = mid + 1; else hi = mid;
-        }
+    // two-level search: every `stride`-th CDF value (<= 2048 of them) is staged in shared memory with one
+    // round of independent loads, which replaces the top ~11 dependent global probes of a plain bisection
+    using Key = typename std::conditional<FIXED, unsigned long long, double>::type;
+    const Key* cdf = static_cast<const Key*>(cdf_raw);
+    const Key key = FIXED ? (Key)(unsigned long long)(U * 0x1p60) : (Key)U;
+    Key* coarse = reinterpret_cast<Key*>(s_coarse);
+    int lo = 0, hi = ncoarse - 1;
+    while (lo < hi) {  // first segment whose last CDF value is not below the key
+        const int mid = (lo + hi) >> 1;
+        if (key > coarse[mid]) lo = mid + 1; else hi = mid;
+    }
+    hi = min(P - 1, (lo + 1) * stride - 1);
+    lo = lo * stride;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (key > cdf[mid]) lo = mid + 1; else hi = mid;
     }
     parents[m0] = lo;
     pose_out[m0] = pose_in[lo];
