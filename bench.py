@@ -103,13 +103,16 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+UPDATE_MODE = 0  # --update-mode sorted: the atomic-free sort + run-length scatter (measured alternative)
+
+
 def make_handle(lib, wl, P, rank=0, nranks=1, device=0):
     from gridmap_slam_robot_b200 import binding as B
 
     g = wl["grid_m"]
     return lib.create(num_particles=P, map_width_m=g, map_height_m=g, origin_x=-g / 2, origin_y=-g / 2,
                       map_mode=B.MAP_SHARED if wl["mode"] == "shared" else B.MAP_PER_PARTICLE,
-                      rank=rank, nranks=nranks, device=device, seed=20260101)
+                      rank=rank, nranks=nranks, device=device, seed=20260101, update_mode=UPDATE_MODE)
 
 
 def score_bytes(P, B, s=8):
@@ -368,7 +371,7 @@ def run_gpu(args, wl):
         "config": {"workload": f"{args.workload}: {wl['desc']}", "particles_total": P_total,
                    "particles_per_gpu": P_local, "beams": Bn, "beams_scored": float(np.mean(hits)),
                    "grid": f"{h.W}x{h.H}", "map_mode": wl["mode"], "resample": "every step (GMS_RESAMPLE_ALWAYS)",
-                   "motion_noise": "device Philox", "l2": "flushed between timed steps (256 MiB memset, untimed)",
+                   "motion_noise": "device Philox", "map_update": args.update_mode, "l2": "flushed between timed steps (256 MiB memset, untimed)",
                    "scan_ring": nscan, "parallelism": f"particles sharded over {world} rank(s)"},
         "ms_per_step_wall": 1e3 * t_wall / args.steps,
         "phases_ms_per_step": {k: v / args.steps for k, v in phase_ms.items() if v > 0},
@@ -399,7 +402,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-particles", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--update-mode", default="atomic", choices=["atomic", "sorted"])
     args = ap.parse_args()
+    global UPDATE_MODE
+    UPDATE_MODE = 1 if args.update_mode == "sorted" else 0
     args.warmup = max(args.warmup, 3)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

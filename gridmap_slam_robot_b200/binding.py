@@ -20,6 +20,7 @@ MAP_PER_PARTICLE, MAP_SHARED = 0, 1
 RESAMPLE_AUTO, RESAMPLE_LITERAL, RESAMPLE_FIXED = 0, 1, 2
 MAP_LOG, MAP_LIKELIHOOD, MAP_FREE_COUNT, MAP_OCC_COUNT = 0, 1, 2, 3
 POLICY_NEVER, POLICY_IF_NEFF_LOW, POLICY_ALWAYS = 0, 1, 2
+UPDATE_ATOMIC, UPDATE_SORTED = 0, 1
 PHASES = ("motion", "likelihood", "score", "normalise", "map_update", "resample", "map_copy", "other")
 
 
@@ -40,7 +41,7 @@ class Config(C.Structure):
         ("noise_theta_base_deg", C.c_double), ("noise_theta_gain", C.c_double),
         ("skip_update_deg", C.c_double), ("likelihood_sigma_num", C.c_double),
         ("map_mode", C.c_int32), ("resample_mode", C.c_int32), ("device", C.c_int32),
-        ("rank", C.c_int32), ("nranks", C.c_int32), ("reserved0", C.c_int32),
+        ("rank", C.c_int32), ("nranks", C.c_int32), ("update_mode", C.c_int32),
         ("seed", C.c_uint64),
     ]
 

@@ -13,6 +13,9 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_run_length_encode.cuh>
+
 #include "kernels.cuh"
 
 using namespace gms;
@@ -100,6 +103,11 @@ struct gms_handle {
     int score_g = 0;  // sub-threads per particle in k_score_sorted (0 = automatic; GMS_SCORE_G overrides: tuning knob)
     int num_sms = 148;
     int* ray_maxlen = nullptr;
+    // GMS_UPDATE_SORTED scratch (allocated on first use)
+    uint32_t *sk_keys = nullptr, *sk_sorted = nullptr, *sk_unique = nullptr;
+    int *sk_runlen = nullptr, *sk_nruns = nullptr;
+    void* sk_temp = nullptr;
+    size_t sk_temp_bytes = 0, sk_cap = 0;
     // shared-map two-pass update: recorded ray cells
     uint32_t* ray_cells = nullptr;
     int* ray_count = nullptr;
@@ -248,6 +256,8 @@ void free_all(gms_handle* h) {
     for (int i = 0; i < 2; i++) { cudaFree(h->all_xy2[i]); cudaFree(h->all_hit2[i]); cudaFree(h->meas2[i]); }
     cudaFree(h->d_normals); cudaFree(h->xlocal); cudaFree(h->xglobal);
     cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start); cudaFree(h->ray_maxlen);
+    cudaFree(h->sk_keys); cudaFree(h->sk_sorted); cudaFree(h->sk_unique); cudaFree(h->sk_runlen); cudaFree(h->sk_nruns);
+    cudaFree(h->sk_temp);
     cudaFree(h->raw_angle); cudaFree(h->raw_dist); cudaFree(h->comb_log); cudaFree(h->comb_lik); cudaFree(h->comb_sign);
     cudaFree(h->comb_dirty); cudaFree(h->comb_off); cudaFree(h->comb_list);
     cudaFree(h->sort_hist); cudaFree(h->sort_cta); cudaFree(h->sort_offs); cudaFree(h->sort_key); cudaFree(h->sort_rank); cudaFree(h->order);
@@ -402,6 +412,44 @@ int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* 
     return GMS_OK;
 }
 
+// GMS_UPDATE_SORTED: the atomic-free scatter.  The key count is read back (one 4-byte D2H + sync) so the sort
+// covers only the cells the scan produced; the mode exists to be measured against the default.
+int launch_sorted_update(gms_handle* h, int Bpad) {
+    int maxlen = 0;
+    CK(cudaMemcpyAsync(&maxlen, h->ray_maxlen, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const size_t n = (size_t)maxlen * Bpad;
+    if (n == 0) return GMS_OK;
+    if (n > h->sk_cap) {
+        cudaFree(h->sk_keys); cudaFree(h->sk_sorted); cudaFree(h->sk_unique); cudaFree(h->sk_runlen); cudaFree(h->sk_temp);
+        h->sk_keys = h->sk_sorted = h->sk_unique = nullptr; h->sk_runlen = nullptr; h->sk_temp = nullptr; h->sk_cap = 0;
+        const size_t cap = n + n / 2;
+        CK(cudaMalloc((void**)&h->sk_keys, cap * 4));
+        CK(cudaMalloc((void**)&h->sk_sorted, cap * 4));
+        CK(cudaMalloc((void**)&h->sk_unique, cap * 4));
+        CK(cudaMalloc((void**)&h->sk_runlen, cap * 4));
+        if (!h->sk_nruns) CK(cudaMalloc((void**)&h->sk_nruns, 4));
+        size_t t1 = 0, t2 = 0;
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, t1, h->sk_keys, h->sk_sorted, (int)cap, 0, 32, h->stream));
+        CK(cub::DeviceRunLengthEncode::Encode(nullptr, t2, h->sk_sorted, h->sk_unique, h->sk_runlen, h->sk_nruns, (int)cap, h->stream));
+        h->sk_temp_bytes = std::max(t1, t2);
+        CK(cudaMalloc(&h->sk_temp, h->sk_temp_bytes));
+        h->sk_cap = cap;
+    }
+    LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_keys<<<148 * 4, 256, 0, h->stream>>>(h->ray_cells, Bpad, maxlen, h->ray_count,
+                                                                            h->ray_start, h->meas, h->all_hit, h->sk_keys,
+                                                                            h->g));
+    size_t tb = h->sk_temp_bytes;
+    CK(cub::DeviceRadixSort::SortKeys(h->sk_temp, tb, h->sk_keys, h->sk_sorted, (int)n, 0, 32, h->stream));
+    tb = h->sk_temp_bytes;
+    CK(cub::DeviceRunLengthEncode::Encode(h->sk_temp, tb, h->sk_sorted, h->sk_unique, h->sk_runlen, h->sk_nruns, (int)n,
+                                          h->stream));
+    h->launches += 8;  // CUB: 3-4 kernels per call
+    LAUNCH(GMS_PHASE_MAP_UPDATE, k_apply_runs<<<148 * 4, 256, 0, h->stream>>>(h->sk_unique, h->sk_runlen, h->sk_nruns,
+                                                                              h->counts, h->dirty, h->g));
+    return GMS_OK;
+}
+
 int launch_map_update(gms_handle* h, const float4* pose, int lo, int cnt, const int* slot, int B, int shared) {
     if (B <= 0) return GMS_OK;
     Phase ph(h, GMS_PHASE_MAP_UPDATE);
@@ -410,6 +458,7 @@ int launch_map_update(gms_handle* h, const float4* pose, int lo, int cnt, const 
         LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_walk<<<blocks_for(Bpad, 64), 64, 0, h->stream>>>(
                                          pose, h->all_xy, B, Bpad, h->st, h->ray_cells, h->ray_cap, h->ray_count,
                                          h->ray_start, h->ray_maxlen, h->rect, h->g));
+        if (h->cfg.update_mode == GMS_UPDATE_SORTED) return launch_sorted_update(h, Bpad);
         LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_apply<<<148 * 4, 256, 0, h->stream>>>(
                                          h->ray_cells, Bpad, h->ray_count, h->ray_maxlen, h->ray_start, h->meas,
                                          h->all_hit, h->counts, h->dirty, h->g));
@@ -701,7 +750,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     if (cfg->num_particles < 1 || !(cfg->resolution > 0) || !(cfg->map_width_m > 0) || !(cfg->map_height_m > 0) ||
         cfg->nranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->nranks || cfg->extra_steps < 0 ||
         (cfg->map_mode != GMS_MAP_PER_PARTICLE && cfg->map_mode != GMS_MAP_SHARED) || cfg->resample_mode < 0 ||
-        cfg->resample_mode > 2 || cfg->num_particles % cfg->nranks != 0)
+        cfg->resample_mode > 2 || cfg->num_particles % cfg->nranks != 0 || cfg->update_mode < 0 || cfg->update_mode > 1)
         return fail(nullptr, GMS_ERR_INVALID_ARG, "gms_create: invalid configuration");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);

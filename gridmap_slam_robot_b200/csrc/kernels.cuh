@@ -755,6 +755,50 @@ __global__ void __launch_bounds__(256) k_ray_apply(const uint32_t* __restrict__ 
     }
 }
 
+// ---- atomic-free alternative (GMS_UPDATE_SORTED): keys -> sort -> run lengths -> one writer per cell ----
+// key = cell index << 2 | class (1 free, 2 occupied); class-0 cells and padding get the sentinel 0xFFFFFFFF.
+__global__ void __launch_bounds__(256) k_ray_keys(const uint32_t* __restrict__ ray_cells, int Bpad, int maxlen,
+                                                  const int* __restrict__ ray_count,
+                                                  const float2* __restrict__ ray_start,
+                                                  const float* __restrict__ meas, const uint8_t* __restrict__ hit,
+                                                  uint32_t* __restrict__ keys, Geometry g) {
+    const long long total = (long long)maxlen * Bpad;
+    const float2 s = *ray_start;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(e / Bpad), b = (int)(e - (long long)k * Bpad);
+        uint32_t key = 0xffffffffu;
+        if (k < ray_count[b]) {
+            const uint32_t cell = ray_cells[e];
+            const int cx = (int)(cell & 0xffffu), cy = (int)(cell >> 16);
+            const float dX = s.x - ((float)cx + 0.5f);
+            const float dY = s.y - ((float)cy + 0.5f);
+            const float dist = __fsqrt_rn(dX * dX + dY * dY);
+            const int cls = inverse_sensor_class(dist, meas[b], hit[b] != 0, g.tol_half);
+            if (cls != 0) key = ((uint32_t)(cx + cy * g.W) << 2) | (uint32_t)cls;
+        }
+        keys[e] = key;
+    }
+}
+// one thread per run; the thread of a cell's FIRST run applies all (<= 2) runs of that cell with plain stores
+__global__ void __launch_bounds__(256) k_apply_runs(const uint32_t* __restrict__ ukeys, const int* __restrict__ runlen,
+                                                    const int* __restrict__ num_runs, CellCounts* __restrict__ counts,
+                                                    uint32_t* __restrict__ dirty, Geometry g) {
+    const int n = *num_runs;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t key = ukeys[i];
+        if (key == 0xffffffffu) continue;
+        const uint32_t cell = key >> 2;
+        if (i > 0 && (ukeys[i - 1] >> 2) == cell) continue;  // second run of this cell: applied by the first
+        CellCounts c = counts[cell];
+        const int before = cell_code(c.n_free, c.n_occ, g);
+        if ((key & 3u) == 1u) c.n_free += (uint32_t)runlen[i]; else c.n_occ += (uint32_t)runlen[i];
+        if (i + 1 < n && (ukeys[i + 1] >> 2) == cell && ukeys[i + 1] != 0xffffffffu) c.n_occ += (uint32_t)runlen[i + 1];
+        counts[cell] = c;
+        if (cell_code(c.n_free, c.n_occ, g) != before) mark_dirty(dirty, (int)(cell % (uint32_t)g.W), (int)(cell / (uint32_t)g.W), g);
+    }
+}
+
 // single ray given in grid coordinates (gms_map_apply_measurement)
 __global__ void k_apply_one(CellCounts* __restrict__ counts, int4* __restrict__ rect, uint32_t* __restrict__ dirty,
                             float sx, float sy, float ex, float ey, float meas, int was_hit, Geometry g) {

@@ -55,6 +55,11 @@ typedef enum gms_status {
 #define GMS_RESAMPLE_FIXED 2    /* u64 fixed point (w * 2^60, truncated): associative, so a block-
                                    wide / multi-rank scan gives identical indices                  */
 
+/* update_mode: how the ray cells of one scan are accumulated into the shared map */
+#define GMS_UPDATE_ATOMIC 0     /* integer atomics on the counters (default; order-independent => deterministic) */
+#define GMS_UPDATE_SORTED 1     /* atomic-free: key sort of the ray cells + run-length accumulation, one writer
+                                   per cell (the scatter north_star sketches; kept as a measured alternative) */
+
 /* kinds for gms_get_map */
 #define GMS_MAP_LOG 0           /* f64[W*H]: nFree*L_free + nOcc*L_occ   (GridMapData.logData)       */
 #define GMS_MAP_LIKELIHOOD 1    /* f64[W*H]: thresholded + blurred field (GridMapData.likelihoodData) */
@@ -88,7 +93,7 @@ typedef struct gms_config {
     int32_t device;             /* CUDA device ordinal (ignored by the oracle)                     */
     int32_t rank;               /* this process' rank / number of ranks sharing the particle set   */
     int32_t nranks;
-    int32_t reserved0;
+    int32_t update_mode;        /* GMS_UPDATE_* (shared map only)                                  */
     uint64_t seed;              /* Philox key for device-generated motion noise / resample draws   */
 } gms_config;
 

@@ -342,3 +342,24 @@ def test_strongest_survives_resampling_like_the_reference(cuda, oracle):
         assert idx2 == idx and np.array_equal(pose2, pose) and w2 == w
         assert any(np.array_equal(pose, p) for p in h.poses())  # the strongest particle always survives
         h.close()
+
+
+def test_sorted_update_mode_equals_atomic(cuda, oracle):
+    """GMS_UPDATE_SORTED (atomic-free: key sort + run lengths + one writer per cell) produces the same counts,
+    dirty tiles and likelihood field as the default integer atomics — and as the oracle."""
+    from gridmap_slam_robot_b200 import synth
+
+    P, steps = 64, 5
+    kw = dict(num_particles=P, map_width_m=20.0, map_height_m=20.0, origin_x=-10.0, origin_y=-10.0, map_mode=B.MAP_SHARED)
+    a, s_, o = cuda.create(**kw), cuda.create(update_mode=B.UPDATE_SORTED, **kw), oracle.create(**kw)
+    scans = synth.make_scans(steps, 360)
+    normals, uniforms = synth.make_draws(steps, P)
+    for i, sc in enumerate(scans):
+        for h in (a, s_, o):
+            h.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta, normals[i])
+            h.resample(float(uniforms[i]))
+        for kind in (B.MAP_FREE_COUNT, B.MAP_OCC_COUNT, B.MAP_LIKELIHOOD):
+            m = a.get_map(0, kind)
+            assert np.array_equal(m, s_.get_map(0, kind)) and np.array_equal(m, o.get_map(0, kind)), (i, kind)
+    for h in (a, s_, o):
+        h.close()
