@@ -21,6 +21,7 @@ RESAMPLE_AUTO, RESAMPLE_LITERAL, RESAMPLE_FIXED = 0, 1, 2
 MAP_LOG, MAP_LIKELIHOOD, MAP_FREE_COUNT, MAP_OCC_COUNT = 0, 1, 2, 3
 POLICY_NEVER, POLICY_IF_NEFF_LOW, POLICY_ALWAYS = 0, 1, 2
 UPDATE_ATOMIC, UPDATE_SORTED = 0, 1
+IPC_NUM_HANDLES = 7
 PHASES = ("motion", "likelihood", "score", "normalise", "map_update", "resample", "map_copy", "other")
 
 
@@ -339,7 +340,7 @@ class Handle:
         return v.value
 
     def ipc_export(self) -> bytes:
-        buf = (C.c_ubyte * (4 * 64))()
+        buf = (C.c_ubyte * (IPC_NUM_HANDLES * 64))()
         self._ck(self.dll.gms_ipc_export(self.h, C.addressof(buf)))
         return bytes(buf)
 

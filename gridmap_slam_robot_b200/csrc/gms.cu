@@ -68,7 +68,14 @@ struct gms_handle {
     // per-particle maps across ranks: peer mappings of every rank's arenas (cudaIpc)
     PeerTable peers{};
     bool peers_ready = false;
-    void* ipc_opened[kMaxRanks][4] = {};
+    void* ipc_opened[kMaxRanks][GMS_IPC_NUM_HANDLES] = {};
+    // fused exchange: double-buffered receive buffers + arrival flags, peer-mapped after gms_ipc_import
+    ExchangeRec* xg2[2] = {nullptr, nullptr};
+    unsigned long long* xflags = nullptr;
+    ExchangeRec* peer_xg[2][kMaxRanks] = {};
+    XFlags peer_flags{};
+    unsigned long long xseq = 0;
+    bool direct = false;
     // beams
     int bcap = 0;
     double2 *in_xy = nullptr, *all_xy = nullptr, *hit_xy = nullptr;
@@ -247,8 +254,9 @@ void free_all(gms_handle* h) {
     if (h->side_b) cudaStreamSynchronize(h->side_b);
     if (h->side_c) cudaStreamSynchronize(h->side_c);
     for (int q = 0; q < kMaxRanks; q++)
-        for (int k = 0; k < 4; k++)
+        for (int k = 0; k < GMS_IPC_NUM_HANDLES; k++)
             if (h->ipc_opened[q][k]) cudaIpcCloseMemHandle(h->ipc_opened[q][k]);
+    cudaFree(h->xg2[0]); cudaFree(h->xg2[1]); cudaFree(h->xflags);
     for (int i = 0; i < 2; i++) { cudaFree(h->pose[i]); cudaFree(h->w[i]); cudaFree(h->lw[i]); cudaFree(h->slot[i]); }
     cudaFree(h->parents); cudaFree(h->cdf); cudaFree(h->counts); cudaFree(h->lik); cudaFree(h->fac); cudaFree(h->rect);
     cudaFree(h->dirty); cudaFree(h->word_off); cudaFree(h->tile_list); cudaFree(h->dup_rect); cudaFree(h->dup_src_rank); cudaFree(h->dup_level); cudaFree(h->dup_src); cudaFree(h->dup_dst); cudaFree(h->scratch2p);
@@ -341,6 +349,7 @@ int fetch_stats(gms_handle* h) {
     if (h->stats_valid) return GMS_OK;
     CK(cudaMemcpyAsync(h->h_st, h->st, sizeof(Stats), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->h_st->xerror) return fail(h, GMS_ERR_STATE, "fused exchange: a peer's records did not arrive (rank out of step?)");
     h->stats_valid = true;
     return GMS_OK;
 }
@@ -381,8 +390,14 @@ bool use_sorted_score(const gms_handle* h) { return h->cfg.map_mode == GMS_MAP_S
 bool use_fac_score(const gms_handle* h) { return h->cfg.map_mode == GMS_MAP_SHARED; }
 
 int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* slot, double* lw,
-                 ExchangeRec* xlocal, int B, bool sorted = false) {
+                 ExchangeRec* xlocal, int B, bool sorted = false, bool push = false) {
     Phase ph(h, GMS_PHASE_SCORE);
+    XPush xp{};
+    if (push) {
+        xp.nranks = h->cfg.nranks;
+        for (int q = 0; q < xp.nranks; q++) xp.dst[q] = h->peer_xg[h->xseq & 1][q];
+        xlocal = nullptr;
+    }
     if (sorted) {
         const size_t smem_s = std::max<size_t>(16, (size_t)B * 16);
         // sub-threads per particle: enough threads to fill the machine (>= ~150k), at most one warp per particle
@@ -396,8 +411,8 @@ int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* 
 #define SCORE_G(GG)                                                                                              \
     case GG:                                                                                                     \
         LAUNCH(GMS_PHASE_SCORE, k_score_sorted<GG><<<grid, 128, smem_s, h->stream>>>(pose, lo, cnt, h->hit_xy, h->st, \
-                                                                                      h->fac, order, lw, xlocal, h->np, \
-                                                                                      emit, h->g));              \
+                                                                                      h->fac, order, lw, xlocal, xp,   \
+                                                                                      h->np, emit, h->g));       \
         break;
         switch (G) {
             SCORE_G(1) SCORE_G(2) SCORE_G(4) SCORE_G(8) SCORE_G(16) SCORE_G(32)
@@ -408,7 +423,7 @@ int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* 
     const unsigned grid = std::min<unsigned>(blocks_for(cnt, 8), 148 * 8);
     const size_t smem = std::max<size_t>(16, (size_t)B * 16);
     LAUNCH(GMS_PHASE_SCORE, k_score<<<grid, 256, smem, h->stream>>>(pose, lo, cnt, h->hit_xy, h->st, h->lik, slot,
-                                                                     lw, xlocal, h->g));
+                                                                     lw, xlocal, xp, h->g));
     return GMS_OK;
 }
 
@@ -532,8 +547,10 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
         if (rc) return rc;
     }
     rc = launch_score(h, h->pose[h->cur], h->lo, h->cnt, shared ? nullptr : h->slot[h->slot_cur] + h->lo, h->lw[h->cur],
-                      c.nranks > 1 ? h->xlocal : nullptr, B, use_fac_score(h));
+                      c.nranks > 1 ? h->xlocal : nullptr, B, use_fac_score(h), c.nranks > 1 && h->direct);
     if (rc) return rc;
+    if (c.nranks > 1 && h->direct)  // tell every rank that this rank's records of step xseq+1 have landed
+        LAUNCH(GMS_PHASE_SCORE, k_xsignal<<<1, 32, 0, h->stream>>>(h->peer_flags, c.nranks, c.rank, h->xseq + 1));
     const bool skip = std::fabs(d_theta) > (M_PI / 180.0) * c.skip_update_deg;  // SLAM.java:82
     if (!shared && !skip) {
         rc = launch_map_update(h, h->pose[h->cur], h->lo, h->cnt, h->slot[h->slot_cur] + h->lo, B, 0);
@@ -611,9 +628,16 @@ int step_end(gms_handle* h, int policy, double u01) {
     if (!h->pending) return fail(h, GMS_ERR_STATE, "update_end without update_begin");
     const gms_config& c = h->cfg;
     h->stats_valid = false;
-    if (c.nranks > 1)
+    if (c.nranks > 1) {
+        const ExchangeRec* src = h->xglobal;  // filled by the caller's all-gather ...
+        if (h->direct) {                      // ... or pushed by the peers' scoring kernels
+            LAUNCH(GMS_PHASE_NORMALISE, k_xwait<<<1, 32, 0, h->stream>>>(h->xflags, c.nranks, h->xseq + 1, h->st));
+            src = h->xg2[h->xseq & 1];
+            h->xseq++;
+        }
         LAUNCH(GMS_PHASE_NORMALISE, k_import_exchange<<<blocks_for(h->P, 256), 256, 0, h->stream>>>(
-                                        h->xglobal, h->P, h->lw[h->cur], h->pose[h->cur]));
+                                        src, h->P, h->lw[h->cur], h->pose[h->cur]));
+    }
     {
         Phase ph(h, GMS_PHASE_NORMALISE);
         int nparts = h->score_parts;
@@ -865,6 +889,12 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->d_normals, (size_t)h->cnt * 16));
     CKC(cudaMalloc((void**)&h->xlocal, (size_t)h->cnt * sizeof(ExchangeRec)));
     CKC(cudaMalloc((void**)&h->xglobal, P * sizeof(ExchangeRec)));
+    if (cfg->nranks > 1) {
+        CKC(cudaMalloc((void**)&h->xg2[0], P * sizeof(ExchangeRec)));
+        CKC(cudaMalloc((void**)&h->xg2[1], P * sizeof(ExchangeRec)));
+        CKC(cudaMalloc((void**)&h->xflags, kMaxRanks * 8));
+        CKC(cudaMemset(h->xflags, 0, kMaxRanks * 8));
+    }
     h->d_tmp_bytes = std::max(h->cells * 8, P * 24);
     CKC(cudaMalloc(&h->d_tmp, h->d_tmp_bytes));
     CKC(cudaMalloc((void**)&h->tmp_pose, sizeof(float4)));
@@ -1305,22 +1335,22 @@ EXPORT int gms_launch_count(gms_handle* h, int64_t* n) {
 EXPORT int gms_ipc_export(gms_handle* h, void* handles) {
     ENTER(h);
     if (!handles) return GMS_ERR_INVALID_ARG;
+    if (h->cfg.nranks < 2) return fail(h, GMS_ERR_STATE, "gms_ipc_export: single-rank handle");
     static_assert(sizeof(cudaIpcMemHandle_t) == GMS_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
     cudaIpcMemHandle_t* out = static_cast<cudaIpcMemHandle_t*>(handles);
-    CK(cudaIpcGetMemHandle(&out[0], h->counts));
-    CK(cudaIpcGetMemHandle(&out[1], h->lik));
-    CK(cudaIpcGetMemHandle(&out[2], h->rect));
-    CK(cudaIpcGetMemHandle(&out[3], h->dirty));
+    void* ptr[GMS_IPC_NUM_HANDLES] = {h->counts, h->lik, h->rect, h->dirty, h->xg2[0], h->xg2[1], h->xflags};
+    for (int k = 0; k < GMS_IPC_NUM_HANDLES; k++) CK(cudaIpcGetMemHandle(&out[k], ptr[k]));
     return GMS_OK;
 }
 EXPORT int gms_ipc_import(gms_handle* h, const void* all_handles) {
     ENTER(h);
     if (!all_handles) return GMS_ERR_INVALID_ARG;
+    if (h->cfg.nranks < 2) return fail(h, GMS_ERR_STATE, "gms_ipc_import: single-rank handle");
     const cudaIpcMemHandle_t* in = static_cast<const cudaIpcMemHandle_t*>(all_handles);
     for (int q = 0; q < h->cfg.nranks; q++) {
-        void* ptr[4] = {h->counts, h->lik, h->rect, h->dirty};
+        void* ptr[GMS_IPC_NUM_HANDLES] = {h->counts, h->lik, h->rect, h->dirty, h->xg2[0], h->xg2[1], h->xflags};
         if (q != h->cfg.rank)
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < GMS_IPC_NUM_HANDLES; k++) {
                 if (h->ipc_opened[q][k]) { ptr[k] = h->ipc_opened[q][k]; continue; }
                 CK(cudaIpcOpenMemHandle(&ptr[k], in[q * GMS_IPC_NUM_HANDLES + k], cudaIpcMemLazyEnablePeerAccess));
                 h->ipc_opened[q][k] = ptr[k];
@@ -1329,8 +1359,12 @@ EXPORT int gms_ipc_import(gms_handle* h, const void* all_handles) {
         h->peers.lik[q] = static_cast<const double*>(ptr[1]);
         h->peers.rect[q] = static_cast<const int4*>(ptr[2]);
         h->peers.dirty[q] = static_cast<const uint32_t*>(ptr[3]);
+        h->peer_xg[0][q] = static_cast<ExchangeRec*>(ptr[4]);
+        h->peer_xg[1][q] = static_cast<ExchangeRec*>(ptr[5]);
+        h->peer_flags.flag[q] = static_cast<unsigned long long*>(ptr[6]);
     }
     h->peers_ready = true;
+    h->direct = true;
     return GMS_OK;
 }
 

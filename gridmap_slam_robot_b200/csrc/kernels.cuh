@@ -25,7 +25,8 @@ struct Stats {
     int num_hit;          // beams with wasHit (GridMap.java:269-270)
     int num_dup;          // map copies of the last resample
     int num_tiles;        // likelihood work-list length
-    int pad[3];
+    int xerror;           // fused exchange: a peer's records did not arrive in time
+    int pad[2];
 };
 
 struct ExchangeRec {  // 24 B, gms.h "Exchange record"
@@ -52,6 +53,36 @@ struct PeerTable {  // per-particle maps across ranks: every rank's arenas, mapp
     const int4* rect[kMaxRanks];
     const uint32_t* dirty[kMaxRanks];
 };
+
+// Fused exchange (multi-rank): the scoring kernel stores each particle's 24-byte record straight into EVERY
+// rank's receive buffer (peer-mapped, NVLink), so the all-gather rides on the scoring kernel's own stores;
+// a flag per (receiver, sender) carries the step sequence number (k_xsignal / k_xwait).
+struct XPush {
+    int nranks;  // 0: disabled
+    ExchangeRec* dst[kMaxRanks];
+};
+struct XFlags {
+    unsigned long long* flag[kMaxRanks];  // flag[q] = rank q's flag array (one u64 per sender)
+};
+__global__ void k_xsignal(XFlags f, int R, int myrank, unsigned long long seq) {
+    const int q = threadIdx.x;
+    if (q < R) {
+        __threadfence_system();  // the records written by the preceding kernel are visible before the flag
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.flag[q] + myrank), "l"(seq) : "memory");
+    }
+}
+__global__ void k_xwait(const unsigned long long* __restrict__ my_flags, int R, unsigned long long seq,
+                        Stats* __restrict__ st) {
+    const int q = threadIdx.x;
+    if (q >= R) return;
+    unsigned long long v = 0;
+    for (long long spins = 0; spins < 8000000; spins++) {  // ~4 s with the sleeps: never hang the device
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(my_flags + q) : "memory");
+        if (v >= seq) return;
+        __nanosleep(500);
+    }
+    st->xerror = 1;
+}
 
 // ------------------------------------------------------------------------------------------------
 // beam table: compaction of the hit beams (scoring reads only those, GridMap.java:269-270) and the
@@ -397,7 +428,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, int lo, int cnt,
                                                const double2* __restrict__ hit_xy, const Stats* __restrict__ st,
                                                const double* __restrict__ lik, const int* __restrict__ slot,
-                                               double* __restrict__ lw, ExchangeRec* __restrict__ xlocal,
+                                               double* __restrict__ lw, ExchangeRec* __restrict__ xlocal, XPush xp,
                                                Geometry g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -459,10 +490,11 @@ __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, 
         const double l = warp_sum(log(prod));
         if (lane == 0) {
             lw[i] = l;
-            if (xlocal) {
+            if (xlocal || xp.nranks) {
                 ExchangeRec r;
                 r.lw = l; r.x = p.x; r.y = p.y; r.t = p.z; r.pad = 0;
-                xlocal[li] = r;
+                if (xlocal) xlocal[li] = r;
+                for (int q = 0; q < xp.nranks; q++) xp.dst[q][i] = r;
             }
         }
     }
@@ -483,7 +515,7 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
                                                       const double2* __restrict__ hit_xy,
                                                       const Stats* __restrict__ st, const double* __restrict__ fac,
                                                       const int* __restrict__ order, double* __restrict__ lw,
-                                                      ExchangeRec* __restrict__ xlocal, NormPartials np,
+                                                      ExchangeRec* __restrict__ xlocal, XPush xp, NormPartials np,
                                                       int emit_partials, Geometry g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -607,10 +639,11 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
     const double l = log(mant) + (double)exp2 * 0.6931471805599453;
     if (writer) {
         lw[lo + li] = l;
-        if (xlocal) {
+        if (xlocal || xp.nranks) {
             ExchangeRec r;
             r.lw = l; r.x = p.x; r.y = p.y; r.t = p.z; r.pad = 0;
-            xlocal[li] = r;
+            if (xlocal) xlocal[li] = r;
+            for (int q = 0; q < xp.nranks; q++) xp.dst[q][lo + li] = r;  // push to every rank (NVLink)
         }
     }
     if (!emit_partials) return;

@@ -35,7 +35,7 @@ def wrap_block(ptr, nbytes, device):
 
 
 class ShardedStepper:
-    def __init__(self, handle: B.Handle, dist, device):
+    def __init__(self, handle: B.Handle, dist, device, use_peer_memory=True):
         self.h, self.dist, self.device = handle, dist, device
         dl, lb, dg, gb = handle.exchange_buffers()
         self.local = wrap_block(dl, lb, device)
@@ -44,19 +44,26 @@ class ShardedStepper:
         # per-particle maps: resampling moves maps between GPUs (SLAM.java:41-45 deep copy); every rank
         # maps the other ranks' arenas (cudaIpc) so its copy kernel can pull parents' maps over NVLink
         self.migrates = handle.cfg.map_mode == B.MAP_PER_PARTICLE and dist.get_world_size() > 1
-        if self.migrates:
+        # CUDA handles map each other's buffers (cudaIpc): the exchange then rides on the scoring kernel's own
+        # stores over NVLink (fused compute + all-gather, gms.h "FUSED path") and per-particle maps can migrate.
+        # The oracle (CPU tests, gloo) has no device arenas: it keeps the explicit all-gather.
+        self.direct = False
+        if handle.info.is_cuda and dist.get_world_size() > 1 and use_peer_memory:
             mine = handle.ipc_export()
             every = [None] * dist.get_world_size()
             dist.all_gather_object(every, mine)
             handle.ipc_import(b"".join(every))
+            self.direct = True
+        if self.migrates:
             self._token = torch.zeros(1, dtype=torch.int32, device=device)
 
     def step(self, d_xy, d_dist, d_hit, num_beams, d_center, d_theta, d_normals=None, policy=B.POLICY_NEVER,
              u01=-1.0):
         """One SLAM step across all ranks.  Pointers are device pointers (host pointers for the oracle)."""
         self.h.update_begin_dev(d_xy, d_dist, d_hit, num_beams, d_center, d_theta, d_normals)
-        # NCCL: ordered after the begin kernels on the current stream, and the end kernels after it
-        self.dist.all_gather_into_tensor(self.glob, self.local)
+        if not self.direct:
+            # NCCL / gloo: ordered after the begin kernels on the current stream, and the end kernels after it
+            self.dist.all_gather_into_tensor(self.glob, self.local)
         self.h.update_end_dev(policy, u01)
         if self.migrates and policy != B.POLICY_NEVER:
             # stream-ordered barrier: no rank starts the next map update before every pull has finished

@@ -43,7 +43,7 @@ def _steps(h, stepper, scans, normals, uniforms, lo, cnt, dev, map_particles=(0,
     return out
 
 
-def _worker(rank, world, port, P, steps, beams, q, mode=1):
+def _worker(rank, world, port, P, steps, beams, q, mode=1, peer=True):
     import torch
     import torch.distributed as dist
 
@@ -59,7 +59,8 @@ def _worker(rank, world, port, P, steps, beams, q, mode=1):
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     h.set_stream(stream.cuda_stream)
-    stepper = parallel.ShardedStepper(h, dist, dev)
+    stepper = parallel.ShardedStepper(h, dist, dev, use_peer_memory=peer or mode == 0)
+    assert stepper.direct == (peer or mode == 0)
     scans = synth.make_scans(steps, beams, max_range=12.0)
     normals, uniforms = synth.make_draws(steps, P)
     lo, cnt = h.info.local_begin, h.info.local_count
@@ -70,7 +71,7 @@ def _worker(rank, world, port, P, steps, beams, q, mode=1):
     dist.destroy_process_group()
 
 
-def _run(cuda, P, steps, beams, world, mode):
+def _run(cuda, P, steps, beams, world, mode, peer=True):
     import torch
     import torch.multiprocessing as mp
 
@@ -83,7 +84,7 @@ def _run(cuda, P, steps, beams, world, mode):
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, P, steps, beams, q, mode)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, P, steps, beams, q, mode, peer)) for r in range(world)]
     for p in procs:
         p.start()
     results = dict(q.get(timeout=300) for _ in range(world))
@@ -109,7 +110,13 @@ def _run(cuda, P, steps, beams, world, mode):
 
 
 def test_two_gpus_equal_one_gpu(cuda):
-    _run(cuda, P=8192, steps=4, beams=360, world=2, mode=1)
+    """Fused exchange: the scoring kernels push the records into both ranks' receive buffers (NVLink)."""
+    _run(cuda, P=8192, steps=6, beams=360, world=2, mode=1)
+
+
+def test_two_gpus_equal_one_gpu_nccl_all_gather(cuda):
+    """Same run with the explicit NCCL all-gather between begin and end."""
+    _run(cuda, P=8192, steps=4, beams=360, world=2, mode=1, peer=False)
 
 
 def test_two_gpus_per_particle_maps_migrate(cuda):
