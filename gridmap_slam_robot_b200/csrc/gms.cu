@@ -549,13 +549,17 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
     rc = launch_score(h, h->pose[h->cur], h->lo, h->cnt, shared ? nullptr : h->slot[h->slot_cur] + h->lo, h->lw[h->cur],
                       c.nranks > 1 ? h->xlocal : nullptr, B, use_fac_score(h), c.nranks > 1 && h->direct);
     if (rc) return rc;
-    if (c.nranks > 1 && h->direct)  // tell every rank that this rank's records of step xseq+1 have landed
-        LAUNCH(GMS_PHASE_SCORE, k_xsignal<<<1, 32, 0, h->stream>>>(h->peer_flags, c.nranks, c.rank, h->xseq + 1));
+
     const bool skip = std::fabs(d_theta) > (M_PI / 180.0) * c.skip_update_deg;  // SLAM.java:82
     if (!shared && !skip) {
         rc = launch_map_update(h, h->pose[h->cur], h->lo, h->cnt, h->slot[h->slot_cur] + h->lo, B, 0);
         if (rc) return rc;
     }
+    // Tell every rank that this rank's records of exchange xseq+1 have landed.  With per-particle maps the flag
+    // also certifies that this rank's maps are final for the step (peers may pull them when resampling), so it
+    // is raised after the map integration.
+    if (c.nranks > 1 && h->direct)
+        LAUNCH(GMS_PHASE_SCORE, k_xsignal<<<1, 32, 0, h->stream>>>(h->peer_flags, c.nranks, c.rank, h->xseq + 1));
     h->pending = true;
     h->pend_dtheta = d_theta;
     h->pend_B = B;
