@@ -390,14 +390,8 @@ bool use_sorted_score(const gms_handle* h) { return h->cfg.map_mode == GMS_MAP_S
 bool use_fac_score(const gms_handle* h) { return h->cfg.map_mode == GMS_MAP_SHARED; }
 
 int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* slot, double* lw,
-                 ExchangeRec* xlocal, int B, bool sorted = false, bool push = false) {
+                 ExchangeRec* xlocal, int B, bool sorted = false) {
     Phase ph(h, GMS_PHASE_SCORE);
-    XPush xp{};
-    if (push) {
-        xp.nranks = h->cfg.nranks;
-        for (int q = 0; q < xp.nranks; q++) xp.dst[q] = h->peer_xg[h->xseq & 1][q];
-        xlocal = nullptr;
-    }
     if (sorted) {
         const size_t smem_s = std::max<size_t>(16, (size_t)B * 16);
         // sub-threads per particle: enough threads to fill the machine (>= ~150k), at most one warp per particle
@@ -411,8 +405,8 @@ int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* 
 #define SCORE_G(GG)                                                                                              \
     case GG:                                                                                                     \
         LAUNCH(GMS_PHASE_SCORE, k_score_sorted<GG><<<grid, 128, smem_s, h->stream>>>(pose, lo, cnt, h->hit_xy, h->st, \
-                                                                                      h->fac, order, lw, xlocal, xp,   \
-                                                                                      h->np, emit, h->g));       \
+                                                                                      h->fac, order, lw, xlocal, h->np, \
+                                                                                      emit, h->g));              \
         break;
         switch (G) {
             SCORE_G(1) SCORE_G(2) SCORE_G(4) SCORE_G(8) SCORE_G(16) SCORE_G(32)
@@ -423,7 +417,7 @@ int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* 
     const unsigned grid = std::min<unsigned>(blocks_for(cnt, 8), 148 * 8);
     const size_t smem = std::max<size_t>(16, (size_t)B * 16);
     LAUNCH(GMS_PHASE_SCORE, k_score<<<grid, 256, smem, h->stream>>>(pose, lo, cnt, h->hit_xy, h->st, h->lik, slot,
-                                                                     lw, xlocal, xp, h->g));
+                                                                     lw, xlocal, h->g));
     return GMS_OK;
 }
 
@@ -547,8 +541,15 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
         if (rc) return rc;
     }
     rc = launch_score(h, h->pose[h->cur], h->lo, h->cnt, shared ? nullptr : h->slot[h->slot_cur] + h->lo, h->lw[h->cur],
-                      c.nranks > 1 ? h->xlocal : nullptr, B, use_fac_score(h), c.nranks > 1 && h->direct);
+                      (c.nranks > 1 && !h->direct) ? h->xlocal : nullptr, B, use_fac_score(h));
     if (rc) return rc;
+    if (c.nranks > 1 && h->direct) {  // this rank's {lw, pose} block -> every rank's receive buffer (NVLink stores)
+        XPush xp{};
+        xp.nranks = c.nranks;
+        for (int q = 0; q < xp.nranks; q++) xp.dst[q] = reinterpret_cast<unsigned char*>(h->peer_xg[h->xseq & 1][q]);
+        const unsigned grid = std::min<unsigned>(blocks_for((long long)c.nranks * h->cnt, 256), 148 * 8);
+        LAUNCH(GMS_PHASE_SCORE, k_xpush<<<grid, 256, 0, h->stream>>>(h->lw[h->cur], h->pose[h->cur], h->lo, h->cnt, h->P, xp));
+    }
 
     const bool skip = std::fabs(d_theta) > (M_PI / 180.0) * c.skip_update_deg;  // SLAM.java:82
     if (!shared && !skip) {
@@ -633,14 +634,16 @@ int step_end(gms_handle* h, int policy, double u01) {
     const gms_config& c = h->cfg;
     h->stats_valid = false;
     if (c.nranks > 1) {
-        const ExchangeRec* src = h->xglobal;  // filled by the caller's all-gather ...
-        if (h->direct) {                      // ... or pushed by the peers' scoring kernels
+        if (h->direct) {  // pushed by the peers (k_xpush): wait for every sender's flag, then unpack
             LAUNCH(GMS_PHASE_NORMALISE, k_xwait<<<1, 32, 0, h->stream>>>(h->xflags, c.nranks, h->xseq + 1, h->st));
-            src = h->xg2[h->xseq & 1];
+            LAUNCH(GMS_PHASE_NORMALISE, k_import_soa<<<blocks_for(h->P, 256), 256, 0, h->stream>>>(
+                                            reinterpret_cast<const unsigned char*>(h->xg2[h->xseq & 1]), h->P, h->lo,
+                                            h->cnt, h->lw[h->cur], h->pose[h->cur]));
             h->xseq++;
+        } else {  // filled by the caller's all-gather
+            LAUNCH(GMS_PHASE_NORMALISE, k_import_exchange<<<blocks_for(h->P, 256), 256, 0, h->stream>>>(
+                                            h->xglobal, h->P, h->lw[h->cur], h->pose[h->cur]));
         }
-        LAUNCH(GMS_PHASE_NORMALISE, k_import_exchange<<<blocks_for(h->P, 256), 256, 0, h->stream>>>(
-                                        src, h->P, h->lw[h->cur], h->pose[h->cur]));
     }
     {
         Phase ph(h, GMS_PHASE_NORMALISE);

@@ -54,13 +54,37 @@ struct PeerTable {  // per-particle maps across ranks: every rank's arenas, mapp
     const uint32_t* dirty[kMaxRanks];
 };
 
-// Fused exchange (multi-rank): the scoring kernel stores each particle's 24-byte record straight into EVERY
-// rank's receive buffer (peer-mapped, NVLink), so the all-gather rides on the scoring kernel's own stores;
-// a flag per (receiver, sender) carries the step sequence number (k_xsignal / k_xwait).
+// Peer exchange (multi-rank, replaces the NCCL all-gather): after scoring, k_xpush stores this rank's block of
+// {log-weight, pose} straight into EVERY rank's receive buffer (peer-mapped, NVLink) with coalesced 8/16-byte
+// stores; a flag per (receiver, sender) carries the step sequence number (k_xsignal / k_xwait).  Receive
+// buffer layout: f64 lw[P] followed by float4 pose[P].  (Pushing the 24-byte records from inside the scoring
+// kernel was tried first: fine on 2-4 GPUs, but 7 x 100k scattered 24-byte NVLink writes per rank doubled the
+// scoring time on 8.)
 struct XPush {
-    int nranks;  // 0: disabled
-    ExchangeRec* dst[kMaxRanks];
+    int nranks;
+    unsigned char* dst[kMaxRanks];
 };
+__global__ void __launch_bounds__(256) k_xpush(const double* __restrict__ lw, const float4* __restrict__ pose, int lo,
+                                               int cnt, int P, XPush xp) {
+    const long long total = (long long)xp.nranks * cnt;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(e / cnt), i = lo + (int)(e - (long long)q * cnt);
+        double* dl = reinterpret_cast<double*>(xp.dst[q]);
+        float4* dp = reinterpret_cast<float4*>(dl + P);
+        dl[i] = lw[i];
+        dp[i] = pose[i];
+    }
+}
+__global__ void __launch_bounds__(256) k_import_soa(const unsigned char* __restrict__ xg, int P, int lo, int cnt,
+                                                    double* __restrict__ lw, float4* __restrict__ pose) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P || (i >= lo && i < lo + cnt)) return;  // the local block is already in place
+    const double* sl = reinterpret_cast<const double*>(xg);
+    const float4* sp = reinterpret_cast<const float4*>(sl + P);
+    lw[i] = sl[i];
+    pose[i] = sp[i];
+}
 struct XFlags {
     unsigned long long* flag[kMaxRanks];  // flag[q] = rank q's flag array (one u64 per sender)
 };
@@ -428,7 +452,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, int lo, int cnt,
                                                const double2* __restrict__ hit_xy, const Stats* __restrict__ st,
                                                const double* __restrict__ lik, const int* __restrict__ slot,
-                                               double* __restrict__ lw, ExchangeRec* __restrict__ xlocal, XPush xp,
+                                               double* __restrict__ lw, ExchangeRec* __restrict__ xlocal,
                                                Geometry g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -490,11 +514,10 @@ __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, 
         const double l = warp_sum(log(prod));
         if (lane == 0) {
             lw[i] = l;
-            if (xlocal || xp.nranks) {
+            if (xlocal) {
                 ExchangeRec r;
                 r.lw = l; r.x = p.x; r.y = p.y; r.t = p.z; r.pad = 0;
-                if (xlocal) xlocal[li] = r;
-                for (int q = 0; q < xp.nranks; q++) xp.dst[q][i] = r;
+                xlocal[li] = r;
             }
         }
     }
@@ -515,7 +538,7 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
                                                       const double2* __restrict__ hit_xy,
                                                       const Stats* __restrict__ st, const double* __restrict__ fac,
                                                       const int* __restrict__ order, double* __restrict__ lw,
-                                                      ExchangeRec* __restrict__ xlocal, XPush xp, NormPartials np,
+                                                      ExchangeRec* __restrict__ xlocal, NormPartials np,
                                                       int emit_partials, Geometry g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -639,11 +662,10 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
     const double l = log(mant) + (double)exp2 * 0.6931471805599453;
     if (writer) {
         lw[lo + li] = l;
-        if (xlocal || xp.nranks) {
+        if (xlocal) {
             ExchangeRec r;
             r.lw = l; r.x = p.x; r.y = p.y; r.t = p.z; r.pad = 0;
-            if (xlocal) xlocal[li] = r;
-            for (int q = 0; q < xp.nranks; q++) xp.dst[q][lo + li] = r;  // push to every rank (NVLink)
+            xlocal[li] = r;
         }
     }
     if (!emit_partials) return;

@@ -232,8 +232,8 @@ int gms_read_neff(gms_handle* h, double* neff_out);  /* sync + read Neff of the 
  * rank imports the lot; resampling then pulls remote parents' maps over NVLink inside
  * gms_update_end_dev / gms_resample.  The caller must run a barrier across ranks after the resampling
  * call before the next update (old slots are only released then).  Handles hold 2x the slots.
- * The same import also switches the {log-weight, pose} exchange of every multi-rank handle to the FUSED path:
- * the scoring kernel stores each record directly into every rank's receive buffer over NVLink and a flag
+ * The same import also switches the {log-weight, pose} exchange of every multi-rank handle to the PEER path:
+ * after scoring each rank stores its block directly into every rank's receive buffer over NVLink and a flag
  * per sender replaces the collective, so the caller skips its all-gather between begin and end. */
 #define GMS_IPC_HANDLE_BYTES 64
 #define GMS_IPC_NUM_HANDLES 7
