@@ -132,7 +132,8 @@ def run_reference(args, wl):
 
     lib = B.Library(b.build_oracle())
     cores = os.cpu_count() or 1
-    P = wl["P"]
+    # same configuration as the GPU arm at this N: weak scaling multiplies the particle count
+    P = wl["P"] * max(1, args.gpus) if args.scaling == "weak" else wl["P"]
     # bounded sample: shared-map workloads run at full size for a few steps; per-particle-map workloads
     # (cost linear in particles: each owns a map) time a slice of the particles at full beam count/map size
     P_s = min(P, args.ref_particles if args.ref_particles else (P if wl["mode"] == "shared" else 64))
@@ -159,7 +160,8 @@ def run_reference(args, wl):
         "impl": "reference", "metric": "particle_beam_scores_per_s", "value": value, "unit": "scores/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * t_total / steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {wl['desc']}", "map_mode": wl["mode"], "resample": "every step"},
+        "config": {"workload": f"{args.workload}: {wl['desc']}", "particles_total": P, "map_mode": wl["mode"],
+                   "resample": "every step"},
         "cpu_baseline": {"value": value, "unit": "scores/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "scores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
