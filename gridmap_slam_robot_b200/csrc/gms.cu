@@ -58,6 +58,8 @@ struct gms_handle {
     CellCounts* counts = nullptr;
     double* lik = nullptr;
     double* fac = nullptr;  // shared map only: per-cell scoring factor (GridMap.java:284-288)
+    alignas(64) CUtensorMap lik_tmap{};  // 3-D tensor map of the counter arena {W, H, S} for k_likelihood_tma
+    bool lik_tma = false;
     int4* rect = nullptr;        // explored bounding box per slot
     uint32_t* dirty = nullptr;   // dirty-tile bitmap per slot
     int* word_off = nullptr;
@@ -374,7 +376,11 @@ int launch_likelihood(gms_handle* h) {
     const size_t smem = (size_t)th * kTileW * 8 + (size_t)th * tw * 4;
     const long long max_tiles = (long long)h->S * h->tiles_per_map;
     const unsigned grid = (unsigned)std::min<long long>(max_tiles, 148 * 6);
-    if (k == 3)
+    if (h->lik_tma) {
+        const size_t smem_t = 2 * (((size_t)kTmaTileW * kTmaTileH * 8 + 127) / 128 * 128) + (size_t)th * kTileW * 8 + (size_t)th * tw * 4;
+        LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood_tma<<<grid, 256, smem_t, h->stream>>>(h->lik_tmap, h->lik, h->fac,
+                                                                                         h->tile_list, h->st, h->g));
+    } else if (k == 3)
         LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<3><<<grid, 256, smem, h->stream>>>(h->counts, h->lik, h->fac,
                                                                                       h->tile_list, h->st, h->g));
     else
@@ -945,6 +951,27 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaFuncSetAttribute(k_score_sorted<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CKC(cudaFuncSetAttribute(k_likelihood<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CKC(cudaFuncSetAttribute(k_likelihood<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CKC(cudaFuncSetAttribute(k_likelihood_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    if (g.khalf == 3 && (h->W & 1) == 0 && !(std::getenv("GMS_LIK_TMA") && std::atoi(std::getenv("GMS_LIK_TMA")) == 0)) {
+        // TMA descriptor of counts[S][H][W] (8-byte cells); box = one tile + halo.  Any failure keeps the plain kernel.
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+            qres == cudaDriverEntryPointSuccess) {
+            const cuuint64_t dims[3] = {(cuuint64_t)h->W, (cuuint64_t)h->H, (cuuint64_t)h->S};
+            const cuuint64_t strides[2] = {(cuuint64_t)h->W * 8, (cuuint64_t)h->cells * 8};
+            const cuuint32_t box[3] = {(cuuint32_t)kTmaTileW, (cuuint32_t)kTmaTileH, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            const CUresult r = ((EncodeFn)fn)(&h->lik_tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, h->counts, dims, strides, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            h->lik_tma = r == CUDA_SUCCESS;
+        }
+        (void)cudaGetLastError();
+    }
     int rc = ensure_beams(h, 1024);
     if (rc) return bail(rc);
     rc = ensure_stage(h, 1 << 20);

@@ -7,6 +7,7 @@
 //   rect   int4[S]                   bounding box of every cell touched since reset ("explored")
 //   dirty  u32[S][tile_words]        bitmap of likelihood tiles whose thresholded codes changed
 #pragma once
+#include <cuda.h>  // CUtensorMap
 #include <type_traits>
 #include "device_math.cuh"
 
@@ -45,6 +46,8 @@ struct NormPartials {   // partial results of normalise: per score CTA (m, idx, 
     unsigned* counter;  // last-block-done ticket
 };
 #define kNegInf (__longlong_as_double((long long)0xfff0000000000000ULL))
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 constexpr int kMaxRanks = 16;
 struct PeerTable {  // per-particle maps across ranks: every rank's arenas, mapped into this process (cudaIpc)
@@ -440,6 +443,126 @@ __global__ void __launch_bounds__(256) k_likelihood(const CellCounts* __restrict
     }
 }
 
+// TMA variant of k_likelihood<3> (KH = 3, even W): the tile + halo of the counter map is fetched by ONE
+// cp.async.bulk.tensor.3d request ({x, y, slot} box of the 3-D tensor counts[S][H][W], 8-byte elements;
+// out-of-map coordinates are zero-filled by the TMA unit) that completes on an mbarrier, instead of 2660
+// per-thread loads with their address arithmetic.  The innermost start coordinate must be 16-byte aligned
+// (measured: an odd cell offset raises "illegal instruction"), so the box starts at x0 - 4 and is 72 cells
+// wide; the 3-cell halo is columns 1..70 of it.  Passes 2 and 3 are those of k_likelihood<3>.
+constexpr int kTmaTileW = kTileW + 8, kTmaTileH = kTileH + 6, kTmaPadX = 4;
+__global__ void __launch_bounds__(256) k_likelihood_tma(const __grid_constant__ CUtensorMap tmap,
+                                                        double* __restrict__ lik, double* __restrict__ fac,
+                                                        const int2* __restrict__ list, const Stats* __restrict__ st,
+                                                        Geometry g) {
+    constexpr int KH = 3;
+    constexpr int tw = (kTileW + 2 * KH + 3) & ~3, th = kTileH + 2 * KH;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    constexpr int kRawBytes = (kTmaTileW * kTmaTileH * 8 + 127) & ~127;
+    // two raw buffers: the TMA request of the NEXT tile is in flight while this tile is blurred
+    double* s_h = reinterpret_cast<double*>(smem_raw + 2 * kRawBytes);  // th * kTileW
+    float* s_t = reinterpret_cast<float*>(s_h + th * kTileW);           // th * tw
+    const int tid = threadIdx.x;
+    const int num_tiles = st->num_tiles;
+    const size_t cells = (size_t)g.W * g.H;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    double kr[2 * KH + 1];
+#pragma unroll
+    for (int i = 0; i < 2 * KH + 1; i++) kr[i] = g.kernel[i];
+    auto fetch = [&](int t, int buf) {  // one elected thread: arm the barrier, issue the 3-D box load
+        const int2 item = list[t];
+        const int ox = (item.y % g.tiles_x) * kTileW, oy = (item.y / g.tiles_x) * kTileH;
+        const uint32_t bar = smem_u32(&s_bar[buf]);
+        const uint32_t bytes = kTmaTileW * kTmaTileH * 8;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the buffer are done
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(smem_u32(smem_raw + buf * kRawBytes)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(ox - kTmaPadX),
+              "r"(oy - KH), "r"(item.x), "r"(bar)
+            : "memory");
+    };
+    if (tid == 0 && (int)blockIdx.x < num_tiles) fetch(blockIdx.x, 0);
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, it++) {
+        const int buf = it & 1;
+        const int2 item = list[t];
+        const int ox = (item.y % g.tiles_x) * kTileW, oy = (item.y / g.tiles_x) * kTileH;
+        double* out = lik + (size_t)item.x * cells;
+        if (tid == 0 && t + (int)gridDim.x < num_tiles) fetch(t + gridDim.x, buf ^ 1);
+        const CellCounts* s_c = reinterpret_cast<const CellCounts*>(smem_raw + buf * kRawBytes);
+        const uint32_t bar = smem_u32(&s_bar[buf]);
+        const uint32_t phase = (uint32_t)(it >> 1) & 1u;
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                : "=r"(done)
+                : "r"(bar), "r"(phase)
+                : "memory");
+        }
+        // 1. threshold (GridMap.java:238-245); cells outside the map contribute 0, not the "unknown" 0.5 that
+        //    the zero-filled counters would threshold to
+        constexpr int twu = kTileW + 2 * KH;
+        for (int e = tid; e < th * twu; e += 256) {
+            const int ly = e / twu, lx = e - ly * twu;
+            const int gx = ox + lx - KH, gy = oy + ly - KH;
+            float code = 0.0f;
+            if (gx >= 0 && gx < g.W && gy >= 0 && gy < g.H)
+                code = 0.5f * (float)cell_code_fast(s_c[ly * kTmaTileW + lx + (kTmaPadX - KH)], g);
+            s_t[ly * tw + lx] = code;
+        }
+        __syncthreads();
+        // 2. horizontal pass (Util.java:387-403): item = (row, 8-column segment)
+        for (int seg = tid; seg < th * (kTileW / 8); seg += 256) {
+            const int ly = seg / (kTileW / 8), x0 = (seg - ly * (kTileW / 8)) * 8;
+            const float4* row4 = reinterpret_cast<const float4*>(s_t + ly * tw + x0);
+            double c[16];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float4 v = row4[q];
+                c[4 * q] = (double)v.x; c[4 * q + 1] = (double)v.y; c[4 * q + 2] = (double)v.z; c[4 * q + 3] = (double)v.w;
+            }
+            double* dst = s_h + ly * kTileW + x0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                double total = 0.0;
+#pragma unroll
+                for (int i = 0; i < 2 * KH + 1; i++) total += kr[i] * c[j + i];
+                dst[j] = total;
+            }
+        }
+        __syncthreads();
+        // 3. vertical pass (Util.java:409-424): thread = (column, group of 8 rows)
+        {
+            const int lx = tid & (kTileW - 1), y0 = (tid / kTileW) * 8;
+            const int gx = ox + lx;
+            double hcol[8 + 2 * KH];
+#pragma unroll
+            for (int i = 0; i < 8 + 2 * KH; i++) hcol[i] = s_h[(y0 + i) * kTileW + lx];
+            if (gx < g.W) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int gy = oy + y0 + j;
+                    double total = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 2 * KH + 1; i++) total += kr[i] * hcol[j + i];
+                    if (gy < g.H) {
+                        out[(size_t)gx + (size_t)gy * g.W] = total;
+                        if (fac) fac[(size_t)gx + (size_t)gy * g.W] = total == 0.5 ? g.uniform_term : g.z_hit * total + g.random_term;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // A5 — GridMap.probabilityOf GridMap.java:261-294.  One warp per particle, hit beams across lanes.
 // The beam table is staged once per CTA with a 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) and
@@ -447,7 +570,6 @@ __global__ void __launch_bounds__(256) k_likelihood(const CellCounts* __restrict
 // Each lane multiplies its factors (<= ceil(B/32) of them, each in [0.01, 0.91]: no underflow), takes
 // one log, and the 32 logs are summed with a fixed xor-shuffle tree (deterministic).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, int lo, int cnt,
                                                const double2* __restrict__ hit_xy, const Stats* __restrict__ st,
