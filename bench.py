@@ -365,6 +365,28 @@ def run_gpu(args, wl):
         except Exception:
             traffic = None
     value = scored / t_dev
+    roofline = {"kernel": "k_score_sorted", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": sb, "sector_bytes_per_launch": P_local * int(np.mean(hits)) * 32,
+                "launch_ms": score_ms, "launches": n_score}
+    if wl["mode"] == "per_particle":
+        # per-particle maps: the scatter (k_map_update) dominates.  SURVEY.md §8d: C * 2 * s_log bytes with
+        # s_log = 4 (one counter of the 8-byte pair is read and written per ray cell); C from the true poses
+        # (n_r = 3 + |dfloor x| + |dfloor y| per ray, RayIterator.java:65-104), so approximate per particle.
+        cells_per_scan = []
+        for k, sc in enumerate(scans):
+            x, y, th = synth.true_pose(k + 1)
+            a = 2.0 * np.pi * np.arange(Bn) / Bn + th
+            ex, ey = x + sc.beam_dist * np.cos(a), y + sc.beam_dist * np.sin(a)
+            res = 0.05
+            cells_per_scan.append(float(np.sum(3 + np.abs(np.floor(ex / res) - np.floor(x / res)) +
+                                               np.abs(np.floor(ey / res) - np.floor(y / res)))))
+        ub = P_local * float(np.mean(cells_per_scan)) * 8.0
+        upd_ms = phase_ms["map_update"] / max(1, args.steps)
+        roofline = {"kernel": "k_map_update", "bound": "hbm", "achieved": ub / (upd_ms * 1e-3) / 1e9, "peak": peak,
+                    "unit": "GB/s", "frac": ub / (upd_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": ub, "launch_ms": upd_ms,
+                    "note": "scatter of 64-bit counter atomics: bound by L2 atomic throughput, not by HBM bandwidth"}
     line = {
         "metric": "particle_beam_scores_per_s", "value": value, "unit": "scores/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
@@ -378,10 +400,7 @@ def run_gpu(args, wl):
         "ms_per_step_wall": 1e3 * t_wall / args.steps,
         "phases_ms_per_step": {k: v / args.steps for k, v in phase_ms.items() if v > 0},
         "neff_last": neff,
-        "roofline": {"kernel": "k_score", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": sb, "sector_bytes_per_launch": P_local * int(np.mean(hits)) * 32,
-                     "launch_ms": score_ms, "launches": n_score},
+        "roofline": roofline,
         "clocks": sampler.result(),
         "gpu_launches": int(launches),
     }
