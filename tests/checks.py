@@ -369,3 +369,36 @@ def check_next_rows(cuda, oracle):
     assert np.mean(lk != lko) < 1e-3
     g.close()
     o.close()
+
+
+def check_truncation_toward_zero(lib):
+    """GridMap.java:273-274: gridX = (int) ((x - position.x) / resolution) truncates TOWARD ZERO, so an end point
+    up to one cell left of / below the map still reads column / row 0 (it is not skipped).  Both scoring
+    kernels (one warp per particle; heading-sorted fixed-point path) must reproduce that."""
+    for P in (1, 5000):  # 5000 particles on a shared map take the k_score_sorted path inside gms_update
+        h = lib.create(num_particles=P, map_width_m=3.0, map_height_m=2.5, resolution=0.05, origin_x=-1.5,
+                       origin_y=-1.25, map_mode=B.MAP_SHARED)
+        nf, no = np.zeros((h.H, h.W), np.uint32), np.zeros((h.H, h.W), np.uint32)
+        no[:, 0] = 1  # column 0 occupied -> likelihood > 0.5 there
+        no[0, :] = 1
+        h.set_map_counts(0, nf, no)
+        # robot at the origin, heading 0: beam end points at world (-1.5 - 0.02, 0.3) and (0.4, -1.25 - 0.03):
+        # (x - pos)/res = -0.4 and -0.6 -> (int) 0 in Java; a floor() would give -1 and skip the beam
+        xy = np.asarray([[-1.52, 0.3], [0.4, -1.28], [-1.5 - 0.051, 0.3]], np.float64)
+        dist = np.hypot(xy[:, 0], xy[:, 1])
+        hit = np.ones(3, np.uint8)
+        h.map_compute_likelihood(0)
+        lik = h.get_map(0, B.MAP_LIKELIHOOD)
+        expect = 0.0
+        for gx, gy in ((0, int((0.3 + 1.25) / 0.05)), (int((0.4 + 1.5) / 0.05), 0)):
+            v = lik[gy, gx]
+            assert v != 0.5
+            expect += np.log(0.9 * v + (1 - 0.9) * 1.0 / 10.0)
+        # third beam: (x - pos)/res = -1.02 -> (int) -1 -> out of the map -> skipped
+        lp, _ = h.map_probability_of(0, (0.0, 0.0, 0.0), xy, hit)
+        assert abs(lp - expect) < 1e-12, (lp, expect)
+        h.set_poses(np.zeros((P, 3), np.float32))
+        # zero motion: sd*z + mean with z = 0 and dCenter = dTheta = 0 leaves every pose at the origin
+        h.update(xy, dist, hit, 0.0, 0.0, np.zeros((P, 2)))
+        np.testing.assert_allclose(h.log_weights(), expect, rtol=0, atol=1e-12)
+        h.close()

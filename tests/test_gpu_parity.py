@@ -363,3 +363,7 @@ def test_sorted_update_mode_equals_atomic(cuda, oracle):
             assert np.array_equal(m, s_.get_map(0, kind)) and np.array_equal(m, o.get_map(0, kind)), (i, kind)
     for h in (a, s_, o):
         h.close()
+
+
+def test_truncation_toward_zero(cuda):
+    checks.check_truncation_toward_zero(cuda)

@@ -62,3 +62,7 @@ def test_sign_of_count_form_is_robust():
     v = np.abs(nf * AB.L_FREE + no * AB.L_OCC)
     v[0, 0] = np.inf
     assert v.min() > 1e-4
+
+
+def test_truncation_toward_zero(oracle):
+    checks.check_truncation_toward_zero(oracle)
