@@ -107,6 +107,11 @@ struct gms_handle {
     double* wp_part = nullptr;
     unsigned* wp_counter = nullptr;
     bool tile_fx_valid = false;
+    // multi-rank shared map: the step's resampling selects only this rank's children; the rest is selected
+    // lazily if a getter asks for the full arrays before the next step (which overwrites them anyway)
+    bool resample_partial = false;
+    double partial_u01 = 0;
+    unsigned long long partial_count = 0;
     int np_cap = 0;
     int score_parts = 0;  // > 0: the last scoring launch already wrote that many (m, idx, s) partials
     int score_g = 0;  // sub-threads per particle in k_score_sorted (0 = automatic; GMS_SCORE_G overrides: tuning knob)
@@ -491,6 +496,7 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
                double d_theta, const double* d_normals) {
     const gms_config& c = h->cfg;
     h->stats_valid = false;
+    h->resample_partial = false;  // the exchange of this step overwrites every non-local particle anyway
     const bool shared = c.map_mode == GMS_MAP_SHARED;
     const bool fork = shared && h->overlap;
     int rc;
@@ -573,7 +579,32 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
     return GMS_OK;
 }
 
-int launch_resample(gms_handle* h, double u01) {
+// children [m_begin, m_begin + m_count) of the resampling whose CDF is in h->cdf; in = buffers `from`, out = `to`
+int launch_select(gms_handle* h, int from, int to, double u01, unsigned long long count, int m_begin, int m_count) {
+    if (m_count <= 0) return GMS_OK;
+    const int P = h->P;
+    if (h->resample_mode == GMS_RESAMPLE_FIXED)
+        LAUNCH(GMS_PHASE_RESAMPLE, k_select<true><<<blocks_for(m_count, 256), 256, 0, h->stream>>>(
+                                       h->cdf, P, u01, h->cfg.seed, count, h->parents, h->st, h->pose[from], h->w[from],
+                                       h->lw[from], h->pose[to], h->w[to], h->lw[to], m_begin, m_count));
+    else
+        LAUNCH(GMS_PHASE_RESAMPLE, k_select<false><<<blocks_for(m_count, 256), 256, 0, h->stream>>>(
+                                       h->cdf, P, u01, h->cfg.seed, count, h->parents, h->st, h->pose[from], h->w[from],
+                                       h->lw[from], h->pose[to], h->w[to], h->lw[to], m_begin, m_count));
+    return GMS_OK;
+}
+
+// the part of a local-only resampling that was skipped (see resample_partial)
+int complete_resample(gms_handle* h) {
+    if (!h->resample_partial) return GMS_OK;
+    h->resample_partial = false;
+    const int from = h->cur ^ 1, to = h->cur;
+    int rc = launch_select(h, from, to, h->partial_u01, h->partial_count, 0, h->lo);
+    if (rc) return rc;
+    return launch_select(h, from, to, h->partial_u01, h->partial_count, h->lo + h->cnt, h->P - h->lo - h->cnt);
+}
+
+int launch_resample(gms_handle* h, double u01, bool local_only = false) {
     const int P = h->P;
     {
         Phase ph(h, GMS_PHASE_RESAMPLE);
@@ -583,15 +614,20 @@ int launch_resample(gms_handle* h, double u01) {
                 LAUNCH(GMS_PHASE_RESAMPLE, k_neff<<<h->ntiles, 1024, 0, h->stream>>>(h->w[h->cur], P, h->ntiles, h->np, h->st));
             LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_fixed<<<h->ntiles, 1024, 0, h->stream>>>(
                                            h->w[h->cur], P, h->np.fx, (unsigned long long*)h->cdf, h->st));
-            LAUNCH(GMS_PHASE_RESAMPLE, k_select<true><<<blocks_for(P, 256), 256, 0, h->stream>>>(
-                                           h->cdf, P, u01, h->cfg.seed, h->resample_count, h->parents, h->st,
-                                           h->pose[h->cur], h->w[h->cur], h->lw[h->cur], h->pose[nxt], h->w[nxt], h->lw[nxt]));
         } else {
             LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_literal<<<1, 32, 0, h->stream>>>(h->w[h->cur], P, (double*)h->cdf, h->st));
-            LAUNCH(GMS_PHASE_RESAMPLE, k_select<false><<<blocks_for(P, 256), 256, 0, h->stream>>>(
-                                           h->cdf, P, u01, h->cfg.seed, h->resample_count, h->parents, h->st,
-                                           h->pose[h->cur], h->w[h->cur], h->lw[h->cur], h->pose[nxt], h->w[nxt], h->lw[nxt]));
         }
+        int rc;
+        if (local_only) {
+            rc = launch_select(h, h->cur, nxt, u01, h->resample_count, h->lo, h->cnt);
+            h->resample_partial = true;
+            h->partial_u01 = u01;
+            h->partial_count = h->resample_count;
+        } else {
+            rc = launch_select(h, h->cur, nxt, u01, h->resample_count, 0, P);
+            h->resample_partial = false;
+        }
+        if (rc) return rc;
         h->cur = nxt;
         h->tile_fx_valid = false;
     }
@@ -685,7 +721,8 @@ int step_end(gms_handle* h, int policy, double u01) {
     h->have_update = true;
     h->pending = false;
     int rc = GMS_OK;
-    if (policy != GMS_RESAMPLE_NEVER) rc = launch_resample(h, u01);
+    if (policy != GMS_RESAMPLE_NEVER)
+        rc = launch_resample(h, u01, c.nranks > 1 && c.map_mode == GMS_MAP_SHARED);
     if (forked) h->b_pending = true;  // joined by the next step's likelihood chain or the next other call
     return rc;
 }
@@ -1038,6 +1075,7 @@ EXPORT int gms_update(gms_handle* h, const double* beam_xy, const double* beam_d
 
 EXPORT int gms_resample(gms_handle* h, double u01) {
     ENTER(h);
+    { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (u01 >= 1.0) return fail(h, GMS_ERR_INVALID_ARG, "gms_resample: u01 must be < 1");
     LAUNCH(GMS_PHASE_RESAMPLE, k_set_resample_flag<<<1, 1, 0, h->stream>>>(h->st, 1));
     // SLAM.resample() returns nothing: the work is only enqueued; every getter synchronises before it reads
@@ -1046,6 +1084,7 @@ EXPORT int gms_resample(gms_handle* h, double u01) {
 
 EXPORT int gms_calculate_neff(gms_handle* h, double* neff_out) {
     ENTER(h);
+    { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!neff_out) return GMS_ERR_INVALID_ARG;
     LAUNCH(GMS_PHASE_NORMALISE, k_neff<<<h->ntiles, 1024, 0, h->stream>>>(h->w[h->cur], h->P, h->ntiles, h->np, h->st));
     h->tile_fx_valid = true;
@@ -1058,6 +1097,7 @@ EXPORT int gms_calculate_neff(gms_handle* h, double* neff_out) {
 
 EXPORT int gms_get_weighted_pose(gms_handle* h, float pose[3]) {
     ENTER(h);
+    { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!pose) return GMS_ERR_INVALID_ARG;
     LAUNCH(GMS_PHASE_NORMALISE, k_weighted_pose<<<h->ntiles, 1024, 0, h->stream>>>(
                                     h->w[h->cur], h->pose[h->cur], h->P, h->ntiles, h->wp_part, h->wp_counter, h->st));
@@ -1086,6 +1126,7 @@ EXPORT int gms_get_strongest(gms_handle* h, int32_t* index, float pose[3], doubl
 
 EXPORT int gms_get_poses(gms_handle* h, float* xyt) {
     ENTER(h);
+    { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!xyt) return GMS_ERR_INVALID_ARG;
     LAUNCH(GMS_PHASE_COUNT - 1,
            k_pose_unpack<<<blocks_for(h->P, 256), 256, 0, h->stream>>>(h->pose[h->cur], (float*)h->d_tmp, h->P));
@@ -1101,16 +1142,19 @@ static int copy_out(gms_handle* h, void* dst, const void* src, size_t bytes) {
 }
 EXPORT int gms_get_weights(gms_handle* h, double* w) {
     ENTER(h);
+    { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!w) return GMS_ERR_INVALID_ARG;
     return copy_out(h, w, h->w[h->cur], (size_t)h->P * 8);
 }
 EXPORT int gms_get_log_weights(gms_handle* h, double* lw) {
     ENTER(h);
+    { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!lw) return GMS_ERR_INVALID_ARG;
     return copy_out(h, lw, h->lw[h->cur], (size_t)h->P * 8);
 }
 EXPORT int gms_get_parents(gms_handle* h, int32_t* parents) {
     ENTER(h);
+    { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!parents) return GMS_ERR_INVALID_ARG;
     return copy_out(h, parents, h->parents, (size_t)h->P * 4);
 }
@@ -1138,6 +1182,7 @@ EXPORT int gms_get_map(gms_handle* h, int32_t particle, int32_t kind, void* dst,
 
 EXPORT int gms_set_poses(gms_handle* h, const float* xyt) {
     ENTER(h);
+    { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!xyt) return GMS_ERR_INVALID_ARG;
     CK(cudaMemcpyAsync(h->d_tmp, xyt, (size_t)h->P * 12, cudaMemcpyHostToDevice, h->stream));
     LAUNCH(GMS_PHASE_COUNT - 1,
@@ -1147,6 +1192,7 @@ EXPORT int gms_set_poses(gms_handle* h, const float* xyt) {
 }
 EXPORT int gms_set_weights(gms_handle* h, const double* w) {
     ENTER(h);
+    { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!w) return GMS_ERR_INVALID_ARG;
     CK(cudaMemcpyAsync(h->w[h->cur], w, (size_t)h->P * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));

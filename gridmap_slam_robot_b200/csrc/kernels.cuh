@@ -1290,9 +1290,9 @@ __global__ void __launch_bounds__(256) k_select(const void* __restrict__ cdf_raw
                                                 const Stats* __restrict__ st, const float4* __restrict__ pose_in,
                                                 const double* __restrict__ w_in, const double* __restrict__ lw_in,
                                                 float4* __restrict__ pose_out, double* __restrict__ w_out,
-                                                double* __restrict__ lw_out) {
+                                                double* __restrict__ lw_out, int m_begin, int m_count) {
     __shared__ unsigned long long s_coarse[2048];
-    const int m0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m0 = m_begin + blockIdx.x * blockDim.x + threadIdx.x;  // children [m_begin, m_begin + m_count)
     const bool resample = st->do_resample != 0;  // uniform over the grid
     int stride = 32;
     while ((P + stride - 1) / stride > 2048) stride <<= 1;
@@ -1302,7 +1302,7 @@ __global__ void __launch_bounds__(256) k_select(const void* __restrict__ cdf_raw
         for (int j = threadIdx.x; j < ncoarse; j += 256) s_coarse[j] = raw[min(P - 1, (j + 1) * stride - 1)];
         __syncthreads();
     }
-    if (m0 >= P) return;
+    if (m0 >= m_begin + m_count) return;
     if (!resample) {
         parents[m0] = m0;
         pose_out[m0] = pose_in[m0];
