@@ -93,3 +93,22 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(B.GmsError) as e:
         lib.create(num_particles=4)
     assert e.value.code == B.ERR_CUDA
+
+
+def test_product_library_is_independent_of_the_oracle():
+    """libgms.so neither links nor names the oracle: no DT_NEEDED on libgms_ref, no gmsref_* symbols, and no
+    dependency beyond libc/libstdc++/libm/libdl/librt/libpthread (+ the CUDA driver at run time)."""
+    import subprocess
+
+    so = B.LIBGMS_PATH
+    if not os.path.exists(so):
+        from gridmap_slam_robot_b200 import build
+
+        build.build_libgms()
+    needed = subprocess.run(["readelf", "-d", so], capture_output=True, text=True).stdout
+    libs = re.findall(r"NEEDED.*\[(.+?)\]", needed)
+    assert libs and all(re.match(r"lib(c|m|dl|rt|pthread|stdc\+\+|gcc_s)\.so", l) or l.startswith("ld-linux") for l in libs), libs
+    syms = subprocess.run(["nm", "-D", so], capture_output=True, text=True).stdout
+    assert "gmsref_" not in syms and "gms_update" in syms
+    src = open(os.path.join(ROOT, "gridmap_slam_robot_b200", "csrc", "gms.cu")).read()
+    assert "oracle" not in src.lower().replace("oracle/", "")  # the product source never refers to the checker
