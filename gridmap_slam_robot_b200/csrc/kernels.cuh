@@ -875,7 +875,10 @@ __global__ void __launch_bounds__(64) k_ray_walk(const float4* __restrict__ pose
         ray_count[b] = 0;
         return;
     }
-    const float4 p = pose[st->strongest];
+    // the strongest pose as k_normalise snapshotted it: this kernel may run on a side stream while the next
+    // step's motion update already rewrites the pose array
+    (void)pose;
+    const float4 p = make_float4(st->strongest_pose[0], st->strongest_pose[1], st->strongest_pose[2], 0.f);
     const Xform t(p.x, p.y, p.z);
     const float sx = (float)((t.tx(0.0, 0.0) - g.posx) / g.res);
     const float sy = (float)((t.ty(0.0, 0.0) - g.posy) / g.res);
