@@ -499,7 +499,8 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
     h->resample_partial = false;  // the exchange of this step overwrites every non-local particle anyway
     const bool shared = c.map_mode == GMS_MAP_SHARED;
     const bool fork = shared && h->overlap;
-    int rc;
+    int rc = ensure_beams(h, B);  // grow the beam tables (if needed) while every stream can still be drained from here
+    if (rc) return rc;
     if (fork) {  // likelihood refresh of the shared map: independent of the beams and of the motion update
         cudaStream_t main = h->stream;
         CK(cudaEventRecord(h->ev_fork_a, main));
