@@ -180,6 +180,25 @@ def gen_slam(shared):
     np.savez_compressed(os.path.join(OUT, "pyref_slam_shared.npz" if shared else "pyref_slam_pp.npz"), **out)
 
 
+def gen_underflow():
+    """400 hit beams on a blank map: Java's product 0.1^400 underflows to 0 -> weightSum 0 -> NaN weights
+    (SLAM.java:121); the log-domain weights stay finite and uniform."""
+    rng = np.random.Generator(np.random.PCG64(808))
+    gm = small_map()
+    P, B = 3, 400
+    slam = pyref.PySLAM(P, gm, shared=True)
+    ang = 2 * math.pi * np.arange(B) / B
+    dist = rng.uniform(0.4, 1.0, B)
+    xy = np.stack([dist * np.cos(ang), dist * np.sin(ang)], 1)
+    hit = np.ones(B, np.uint8)
+    beams = [(float(xy[b, 0]), float(xy[b, 1]), float(dist[b]), True) for b in range(B)]
+    normals = np.zeros((P, 2))
+    ne = slam.update(beams, 0.0, 0.0, [0.0] * (2 * P))
+    np.savez_compressed(os.path.join(OUT, "pyref_underflow.npz"), xy=xy, dist=dist, hit=hit, normals=normals,
+                        neff=np.float64(ne), lw=np.asarray(slam.lw, np.float64), w=np.asarray(slam.w, np.float64),
+                        wlit=np.asarray(slam.wlit, np.float64))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_rays()
@@ -189,4 +208,5 @@ if __name__ == "__main__":
     gen_resample()
     gen_slam(False)
     gen_slam(True)
+    gen_underflow()
     print("golden fixtures written to", os.path.normpath(OUT))

@@ -402,3 +402,16 @@ def check_truncation_toward_zero(lib):
         h.update(xy, dist, hit, 0.0, 0.0, np.zeros((P, 2)))
         np.testing.assert_allclose(h.log_weights(), expect, rtol=0, atol=1e-12)
         h.close()
+
+
+def check_underflow(lib):
+    """Java's product weights underflow (NaN after normalisation); the build's log-domain weights do not."""
+    g = golden("pyref_underflow.npz")
+    assert np.isnan(g["wlit"]).all()  # what the reference itself would produce (SLAM.java:121)
+    h = small_handle(lib, P=3, mode=B.MAP_SHARED)
+    neff = h.update(g["xy"], g["dist"], g["hit"], 0.0, 0.0, g["normals"])
+    np.testing.assert_allclose(h.log_weights(), g["lw"], rtol=0, atol=LW_TOL)
+    assert np.all(g["lw"] < -700)  # below ln(DBL_MIN): exp() of it is 0
+    np.testing.assert_allclose(h.weights(), g["w"], rtol=W_RTOL, atol=0)
+    assert abs(neff - float(g["neff"])) < 1e-9 and abs(neff - 3.0) < 1e-9
+    h.close()

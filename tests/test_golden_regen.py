@@ -17,6 +17,7 @@ def test_golden_fixtures_are_reproducible(tmp_path):
         fn()
     mg.gen_slam(False)
     mg.gen_slam(True)
+    mg.gen_underflow()
     committed = os.path.join(ROOT, "tests", "golden")
     names = sorted(f for f in os.listdir(committed) if f.endswith(".npz"))
     assert names == sorted(os.listdir(tmp_path))

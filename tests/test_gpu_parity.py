@@ -367,3 +367,7 @@ def test_sorted_update_mode_equals_atomic(cuda, oracle):
 
 def test_truncation_toward_zero(cuda):
     checks.check_truncation_toward_zero(cuda)
+
+
+def test_weight_underflow_log_domain(cuda):
+    checks.check_underflow(cuda)

@@ -66,3 +66,7 @@ def test_sign_of_count_form_is_robust():
 
 def test_truncation_toward_zero(oracle):
     checks.check_truncation_toward_zero(oracle)
+
+
+def test_weight_underflow_log_domain(oracle):
+    checks.check_underflow(oracle)
