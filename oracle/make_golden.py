@@ -1,8 +1,8 @@
 """make_golden.py — writes tests/golden/*.npz from the pure-Python restatement (oracle/pyref.py).
 
 Run from the repo root:  python oracle/make_golden.py
-The fixtures pin the C oracle (tests/test_oracle_golden.py, CPU) and the CUDA path
-(tests/test_gpu_golden.py, -m gpu).  They are NOT outputs of the reference itself — the Java
+The fixtures pin the C oracle (tests/test_oracle.py, CPU) and the CUDA path
+(tests/test_gpu_parity.py, -m gpu).  They are NOT outputs of the reference itself — the Java
 reference cannot run in this image (no JDK); see the header of oracle/gms_ref.c.
 Inputs are drawn from numpy PCG64 with fixed seeds; every float32-typed input is stored as float32
 and every double as float64, so the files are exact.
