@@ -169,33 +169,60 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(wl, workload_name):
+PHASES = ("motion", "likelihood_field", "scoring", "map_update", "normalise", "resample")
+
+
+def cpu_baseline(wl, workload_name, steps=2, warm=1):
     """Oracle on ONE host core (the reference is single threaded: SLAM.java:88 on the GL render thread),
-    a bounded sample of the same workload."""
+    a bounded sample of the same workload, with the per-phase split SURVEY.md §8d asks for."""
+    import ctypes
+
     from gridmap_slam_robot_b200 import binding as B
     from gridmap_slam_robot_b200 import build as b
     from gridmap_slam_robot_b200 import synth
 
     lib = B.Library(b.build_oracle())
+    lib.dll.gmsref_phase_seconds.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.c_int32]
     P = wl["P"]
-    P_s = min(P, P if wl["mode"] == "shared" else 8)
+    P_s = min(P, P if wl["mode"] == "shared" or P <= 100 else 8)
     h = make_handle(lib, wl, P_s)
-    scans = synth.make_scans(3, wl["B"], max_range=wl["max_range"])
-    t_total, scored = 0.0, 0
+    scans = synth.make_scans(warm + steps, wl["B"], max_range=wl["max_range"])
+    t_total, scored, per_step = 0.0, 0, []
+    ph = (ctypes.c_double * 6)()
     for s, sc in enumerate(scans):
+        if s == warm:
+            lib.dll.gmsref_phase_seconds(h.h, ph, 1)
         t0 = time.perf_counter()
         h.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta)
         h.resample(-1.0)
         h.weighted_pose()
         dt = time.perf_counter() - t0
-        if s >= 1:
+        if s >= warm:
             t_total += dt
+            per_step.append(dt)
             scored += P_s * sc.num_hits
+    lib.dll.gmsref_phase_seconds(h.h, ph, 0)
     h.close()
+    per_step.sort()
     return {"value": scored / t_total, "unit": "scores/s", "cores": 1, "kind": "port",
-            "ms_per_step_sample": 1e3 * t_total / 2,
-            "sample": f"{P_s} of {P} particles x {wl['B']} beams, full {wl['grid_m']} m grid, 2 steps after 1 warm-up; "
-                      f"C restatement of the Java path (not JVM), single thread"}
+            "ms_per_step_sample": 1e3 * t_total / steps,
+            "ms_per_step_median": 1e3 * per_step[len(per_step) // 2],
+            "ms_per_step_p95": 1e3 * per_step[min(len(per_step) - 1, int(0.95 * len(per_step)))],
+            "phase_ms_per_step": {k: 1e3 * ph[i] / steps for i, k in enumerate(PHASES)},
+            "host": {"nproc": os.cpu_count(), "cpu": cpu_model()},
+            "sample": f"{P_s} of {P} particles x {wl['B']} beams, full {wl['grid_m']} m grid, {steps} steps after {warm} "
+                      f"warm-up; C restatement of the Java path (not JVM), single thread"}
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def run_gpu(args, wl):
@@ -424,7 +451,15 @@ def main():
     ap.add_argument("--ref-particles", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--update-mode", default="atomic", choices=["atomic", "sorted"])
+    ap.add_argument("--cpu-replay", type=int, default=0, metavar="STEPS",
+                    help="only time the single-thread CPU restatement for STEPS steps of the workload (per-phase "
+                         "split; SURVEY.md 8d asks for K1 x 500) and print its cpu_baseline object")
     args = ap.parse_args()
+    if args.cpu_replay:
+        wl = WORKLOADS[args.workload]
+        print(json.dumps({"workload": f"{args.workload}: {wl['desc']}",
+                          "cpu_baseline": cpu_baseline(wl, args.workload, steps=args.cpu_replay, warm=1)}), flush=True)
+        return
     global UPDATE_MODE
     UPDATE_MODE = 1 if args.update_mode == "sorted" else 0
     args.warmup = max(args.warmup, 3)

@@ -27,6 +27,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -65,8 +66,26 @@ struct gms_handle {
     double *pend_xy, *pend_dist;
     uint8_t *pend_hit;
     double pend_dtheta;
+    /* wall-clock seconds per phase of the step, accumulated when threads == 1 (the per-phase
+     * split of the CPU path): motion, likelihood field, scoring, map integration, normalise, resample */
+    double phase[6];
     char err[256];
 };
+
+static inline double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+#define PHASE_T0(h) double t0__ = (h)->threads == 1 ? now_s() : 0.0
+#define PHASE_ADD(h, k)                                  \
+    do {                                                 \
+        if ((h)->threads == 1) {                         \
+            double t1__ = now_s();                       \
+            (h)->phase[k] += t1__ - t0__;                \
+            t0__ = t1__;                                 \
+        }                                                \
+    } while (0)
 
 static __thread char g_create_err[256];
 
@@ -617,7 +636,11 @@ static int update_local(gms_handle *h, const double *bxy, const double *bdist, c
     int skip = fabs(d_theta) > (M_PI / 180.0) * h->cfg.skip_update_deg; /* SLAM.java:82 */
     size_t n = (size_t)h->W * h->H;
     int shared = h->cfg.map_mode == GMS_MAP_SHARED;
-    if (shared) compute_likelihood(h, h->logd[0], h->lik[0], h->prob_scratch, h->tmp_scratch);
+    if (shared) {
+        PHASE_T0(h);
+        compute_likelihood(h, h->logd[0], h->lik[0], h->prob_scratch, h->tmp_scratch);
+        PHASE_ADD(h, 1);
+    }
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 1) num_threads(h->threads)
 #endif
@@ -629,20 +652,25 @@ static int update_local(gms_handle *h, const double *bxy, const double *bdist, c
         int tid = 0;
 #endif
         double zd, zt;
+        PHASE_T0(h);
         if (normals) { zd = normals[2 * li]; zt = normals[2 * li + 1]; }
         else philox_normals(h->cfg.seed, (uint32_t)i, h->step, &zd, &zt);
         motion_sample(h, &h->px[i], &h->py[i], &h->pt[i], d_center, d_theta, zd, zt); /* SLAM.java:90 */
+        PHASE_ADD(h, 0);
         int s = h->slot[li];
         if (!shared)
             compute_likelihood(h, h->logd[s], h->lik[s], h->prob_scratch + n * tid,
                                h->tmp_scratch + n * tid);                               /* SLAM.java:93 */
+        PHASE_ADD(h, 1);
         /* SLAM.java:97 findBestPoseOptim: objective == 0 -> start pose (identity) */
         double lw;
         h->wlit[i] = probability_of(h, h->lik[s], h->px[i], h->py[i], h->pt[i], bxy, bhit, B, &lw); /* :99 */
         h->lw[i] = lw;
+        PHASE_ADD(h, 2);
         if (!shared && !skip)
             integrate_observation(h, h->logd[s], h->nfree[s], h->nocc[s], h->px[i], h->py[i], h->pt[i],
                                   bxy, bdist, bhit, B);                                 /* SLAM.java:102-107 */
+        PHASE_ADD(h, 3);
     }
     struct xrec *xl = (struct xrec *)h->xlocal;
     for (int li = 0; li < h->cnt; li++) {
@@ -663,12 +691,15 @@ static int update_global(gms_handle *h, const double *bxy, const double *bdist, 
         h->lw[i] = xg[i].lw; h->px[i] = xg[i].x; h->py[i] = xg[i].y; h->pt[i] = xg[i].t;
         h->wlit[i] = exp(xg[i].lw); /* literal products of remote particles are not exchanged */
     }
+    PHASE_T0(h);
     normalise(h);
+    PHASE_ADD(h, 4);
     int skip = fabs(d_theta) > (M_PI / 180.0) * h->cfg.skip_update_deg;
     if (h->cfg.map_mode == GMS_MAP_SHARED && !skip) {
         int b = h->strongest;
         integrate_observation(h, h->logd[0], h->nfree[0], h->nocc[0], h->px[b], h->py[b], h->pt[b], bxy,
                               bdist, bhit, B);
+        PHASE_ADD(h, 3);
     }
     h->step++;
     h->have_update = 1;
@@ -695,6 +726,7 @@ EXPORT int gms_update(gms_handle *h, const double *beam_xy, const double *beam_d
 /* SLAM.resample SLAM.java:133-153 incl. the deep copy Particle(Particle) SLAM.java:41-45 */
 static void do_resample(gms_handle *h, double u01) {
     int P = h->P;
+    PHASE_T0(h);
     if (u01 < 0) u01 = philox_uniform(h->cfg.seed, h->resample_count);
     h->resample_count++;
     gmsref_resample_indices(h->w, P, u01, h->resample_mode, h->parents);
@@ -735,6 +767,7 @@ static void do_resample(gms_handle *h, double u01) {
     memcpy(h->px, nx, sizeof(float) * P); memcpy(h->py, ny, sizeof(float) * P); memcpy(h->pt, nt, sizeof(float) * P);
     memcpy(h->w, nw, sizeof(double) * P); memcpy(h->lw, nl, sizeof(double) * P); memcpy(h->wlit, nwl, sizeof(double) * P);
     free(nx); free(ny); free(nt); free(nw); free(nl); free(nwl);
+    PHASE_ADD(h, 5);
 }
 
 EXPORT int gms_resample(gms_handle *h, double u01) {
@@ -846,6 +879,13 @@ EXPORT int gmsref_get_literal_weights(gms_handle *h, double *w, double *neff, in
     if (w) memcpy(w, h->wlit, sizeof(double) * h->P);
     if (neff) *neff = h->neff_lit;
     if (strongest) *strongest = h->strongest_lit;
+    return GMS_OK;
+}
+/* seconds spent per phase since the last call with reset != 0 (threads == 1 only; see struct gms_handle) */
+EXPORT int gmsref_phase_seconds(gms_handle *h, double out[6], int32_t reset) {
+    if (!h) return GMS_ERR_INVALID_ARG;
+    if (out) memcpy(out, h->phase, sizeof h->phase);
+    if (reset) memset(h->phase, 0, sizeof h->phase);
     return GMS_OK;
 }
 EXPORT int gmsref_set_threads(gms_handle *h, int32_t n) {
