@@ -415,3 +415,72 @@ def check_underflow(lib):
     np.testing.assert_allclose(h.weights(), g["w"], rtol=W_RTOL, atol=0)
     assert abs(neff - float(g["neff"])) < 1e-9 and abs(neff - 3.0) < 1e-9
     h.close()
+
+
+# ---------------------------------------------------------------- full BASELINE sizes, sampled --------
+def check_full_size_sampled(lib, oracle, P, beams, grid_m, max_range=10.0, steps=3, sample=48, seed=11):
+    """Shared-map step at sizes where a whole oracle replay would take minutes, checked piecewise against the
+    oracle's per-map operators (which finish in seconds):
+      motion      a random sample of particles against Odometry.apply on the previous pose, bit for bit
+      field       the ONE shared likelihood field, bit for bit (GridMap.computeLikelihoodMap on the oracle's map)
+      scoring     the sample's log-weights against GridMap.probabilityOf on that field, |d| <= 1e-9
+      normalise   weights / Neff / strongest recomputed in numpy from the library's own log-weights
+      integration per-cell counts bit for bit: the oracle integrates the same scan from the library's strongest pose
+      resampling  parents against the oracle's resampler fed the library's weights; children's poses and weights
+    """
+    import ctypes as C
+
+    from gridmap_slam_robot_b200 import synth
+
+    scans = synth.make_scans(steps, beams, max_range=max_range)
+    normals, uniforms = synth.make_draws(steps, P, seed=seed)
+    kw = dict(map_width_m=grid_m, map_height_m=grid_m, origin_x=-grid_m / 2, origin_y=-grid_m / 2,
+              map_mode=B.MAP_SHARED)
+    g = lib.create(num_particles=P, **kw)
+    o = oracle.create(num_particles=1, **kw)
+    r = oracle.create(num_particles=P, map_width_m=0.5, map_height_m=0.5, map_mode=B.MAP_SHARED)
+    assert g.info.resample_mode == r.info.resample_mode
+    motion = oracle.dll.gmsref_motion
+    motion.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_double, C.c_double, C.c_double, C.c_double]
+    rng = np.random.default_rng(seed)
+    try:
+        prev = g.poses()
+        for s, sc in enumerate(scans):
+            neff = g.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta, normals[s])
+            poses, lw, w = g.poses(), g.log_weights(), g.weights()
+            pick = np.unique(np.concatenate([rng.choice(P, size=min(sample, P), replace=False),
+                                             [0, P - 1, int(np.argmax(lw)), int(np.argmin(lw))]]))
+            for i in pick:
+                p = (C.c_float * 3)(*prev[i])
+                assert motion(o.h, p, sc.d_center, sc.d_theta, float(normals[s][i, 0]), float(normals[s][i, 1])) == 0
+                assert np.array_equal(np.asarray(p[:], np.float32), poses[i]), f"step {s}: motion of particle {i}"
+            o.map_compute_likelihood(0)
+            assert np.array_equal(g.get_map(0, B.MAP_LIKELIHOOD), o.get_map(0, B.MAP_LIKELIHOOD)), f"step {s}: field"
+            for i in pick:
+                lp, _ = o.map_probability_of(0, poses[i], sc.beam_xy, sc.beam_hit)
+                assert abs(lp - lw[i]) <= LW_TOL, f"step {s}: log-weight of particle {i}: {lw[i]} vs {lp}"
+            e = np.exp(lw - lw.max())
+            wn = e / e.sum()
+            np.testing.assert_allclose(w, wn, rtol=1e-9, atol=1e-300, err_msg=f"step {s}: weights")
+            assert abs(neff * np.sum(wn * wn) - 1) < 1e-9, f"step {s}: neff"
+            si, sp, sw = g.strongest()
+            assert si == int(np.argmax(lw)) and np.array_equal(sp, poses[si]) and abs(sw / wn[si] - 1) < 1e-9
+            wp = g.weighted_pose()
+            assert abs(wp[0] - np.dot(wn, poses[:, 0].astype(np.float64))) < 2e-6
+            assert abs(wp[1] - np.dot(wn, poses[:, 1].astype(np.float64))) < 2e-6
+            o.map_integrate_observation(0, sp, sc.beam_xy, sc.beam_dist, sc.beam_hit)
+            for kind in (B.MAP_FREE_COUNT, B.MAP_OCC_COUNT):
+                a, b = g.get_map(0, kind), o.get_map(0, kind)
+                assert np.array_equal(a, b), f"step {s}: counts kind {kind}: {np.sum(a != b)} cells differ"
+            u = float(uniforms[s])
+            r.set_weights(w)
+            r.resample(u)
+            g.resample(u)
+            par = g.parents()
+            assert np.array_equal(par, r.parents()), f"step {s}: parents"
+            assert np.array_equal(g.poses(), poses[par]) and np.array_equal(g.weights(), w[par])
+            prev = g.poses()
+    finally:
+        g.close()
+        o.close()
+        r.close()

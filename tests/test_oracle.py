@@ -70,3 +70,9 @@ def test_truncation_toward_zero(oracle):
 
 def test_weight_underflow_log_domain(oracle):
     checks.check_underflow(oracle)
+
+
+def test_full_size_sampled_check_is_self_consistent(oracle):
+    """The piecewise full-size check of the GPU suite (checks.check_full_size_sampled), run here on the oracle
+    itself at a size a CPU finishes in seconds: the per-map operators compose to exactly the step."""
+    checks.check_full_size_sampled(oracle, oracle, P=3000, beams=90, grid_m=25.6, steps=3, sample=16)
