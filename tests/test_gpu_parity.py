@@ -371,3 +371,14 @@ def test_truncation_toward_zero(cuda):
 
 def test_weight_underflow_log_domain(cuda):
     checks.check_underflow(cuda)
+
+
+# ---- BASELINE configs 2 and 3 at their full sizes, piecewise against the oracle's per-map operators ----
+def test_full_size_k3_sampled_parity(cuda, oracle):
+    """K3: 10k particles x 720 beams, 2048^2 shared grid, 12 m range."""
+    checks.check_full_size_sampled(cuda, oracle, P=10000, beams=720, grid_m=102.4, max_range=12.0)
+
+
+def test_full_size_k4_sampled_parity(cuda, oracle):
+    """K4: 100k particles x 720 beams, 4096^2 shared grid, every beam hits (the bench workload)."""
+    checks.check_full_size_sampled(cuda, oracle, P=100000, beams=720, grid_m=204.8, max_range=30.0)
