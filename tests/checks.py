@@ -484,3 +484,57 @@ def check_full_size_sampled(lib, oracle, P, beams, grid_m, max_range=10.0, steps
         g.close()
         o.close()
         r.close()
+
+
+def check_full_size_sampled_pp(lib, oracle, P, beams, grid_m, max_range=10.0, steps=3, sample=6, seed=13):
+    """Per-particle maps (the reference's mode) at full size, a sample of particles per step against the
+    oracle's per-map operators: each sampled particle's field, log-weight and integrated counts are reproduced
+    from its own counts before the step; after resampling every sampled child's map equals its parent's."""
+    from gridmap_slam_robot_b200 import synth
+
+    scans = synth.make_scans(steps, beams, max_range=max_range)
+    normals, uniforms = synth.make_draws(steps, P, seed=seed)
+    kw = dict(map_width_m=grid_m, map_height_m=grid_m, origin_x=-grid_m / 2, origin_y=-grid_m / 2)
+    g = lib.create(num_particles=P, map_mode=B.MAP_PER_PARTICLE, **kw)
+    o = oracle.create(num_particles=1, map_mode=B.MAP_SHARED, **kw)
+    r = oracle.create(num_particles=P, map_width_m=0.5, map_height_m=0.5, map_mode=B.MAP_SHARED)
+    assert g.info.resample_mode == r.info.resample_mode
+    rng = np.random.default_rng(seed)
+    counts = lambda h, i: (h.get_map(i, B.MAP_FREE_COUNT), h.get_map(i, B.MAP_OCC_COUNT))  # noqa: E731
+    try:
+        for s, sc in enumerate(scans):
+            pick = np.unique(np.concatenate([rng.choice(P, size=min(sample, P), replace=False), [0, P - 1]]))
+            before = {int(i): counts(g, int(i)) for i in pick}
+            neff = g.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta, normals[s])
+            poses, lw, w = g.poses(), g.log_weights(), g.weights()
+            for i in before:
+                o.set_map_counts(0, *before[i])
+                o.map_compute_likelihood(0)
+                assert np.array_equal(g.get_map(i, B.MAP_LIKELIHOOD), o.get_map(0, B.MAP_LIKELIHOOD)), (s, i, "field")
+                lp, _ = o.map_probability_of(0, poses[i], sc.beam_xy, sc.beam_hit)
+                assert abs(lp - lw[i]) <= LW_TOL, (s, i, lw[i], lp)
+                o.map_integrate_observation(0, poses[i], sc.beam_xy, sc.beam_dist, sc.beam_hit)
+                for a, b in zip(counts(g, i), counts(o, 0)):
+                    assert np.array_equal(a, b), (s, i, "counts", int(np.sum(a != b)))
+            e = np.exp(lw - lw.max())
+            wn = e / e.sum()
+            np.testing.assert_allclose(w, wn, rtol=1e-9, atol=1e-300)
+            assert abs(neff * np.sum(wn * wn) - 1) < 1e-9
+            assert g.strongest()[0] == int(np.argmax(lw))
+            u = float(uniforms[s])
+            r.set_weights(w)
+            r.resample(u)
+            rpar = r.parents()
+            kids = np.unique(np.concatenate([rng.choice(P, size=min(sample, P), replace=False), [0, P - 1]]))
+            parent_maps = {int(m): counts(g, int(rpar[m])) + (g.get_map(int(rpar[m]), B.MAP_LIKELIHOOD),) for m in kids}
+            g.resample(u)
+            assert np.array_equal(g.parents(), rpar), f"step {s}: parents"
+            assert np.array_equal(g.poses(), poses[rpar])
+            for m, (pf, po, pl) in parent_maps.items():  # deep copy of both arrays: GridMap.java:106-124
+                cf, co = counts(g, m)
+                assert np.array_equal(cf, pf) and np.array_equal(co, po), (s, m, "child counts")
+                assert np.array_equal(g.get_map(m, B.MAP_LIKELIHOOD), pl), (s, m, "child field")
+    finally:
+        g.close()
+        o.close()
+        r.close()

@@ -382,3 +382,9 @@ def test_full_size_k3_sampled_parity(cuda, oracle):
 def test_full_size_k4_sampled_parity(cuda, oracle):
     """K4: 100k particles x 720 beams, 4096^2 shared grid, every beam hits (the bench workload)."""
     checks.check_full_size_sampled(cuda, oracle, P=100000, beams=720, grid_m=204.8, max_range=30.0)
+
+
+def test_full_size_per_particle_maps_sampled_parity(cuda, oracle):
+    """BASELINE config 1 with the reference's own map semantics (and config 4's per-GPU share): 1k particles x 360
+    beams, each particle with its own 1024^2 map."""
+    checks.check_full_size_sampled_pp(cuda, oracle, P=1000, beams=360, grid_m=51.2)

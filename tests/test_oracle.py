@@ -76,3 +76,7 @@ def test_full_size_sampled_check_is_self_consistent(oracle):
     """The piecewise full-size check of the GPU suite (checks.check_full_size_sampled), run here on the oracle
     itself at a size a CPU finishes in seconds: the per-map operators compose to exactly the step."""
     checks.check_full_size_sampled(oracle, oracle, P=3000, beams=90, grid_m=25.6, steps=3, sample=16)
+
+
+def test_full_size_sampled_pp_check_is_self_consistent(oracle):
+    checks.check_full_size_sampled_pp(oracle, oracle, P=24, beams=90, grid_m=25.6, steps=3, sample=4)
