@@ -115,6 +115,7 @@ struct gms_handle {
     int np_cap = 0;
     int score_parts = 0;  // > 0: the last scoring launch already wrote that many (m, idx, s) partials
     int score_g = 0;  // sub-threads per particle in k_score_sorted (0 = automatic; GMS_SCORE_G overrides: tuning knob)
+    int score_v = 0;  // index-validation variant of k_score_sorted (GMS_SCORE_V=1: ALU-lean form, same results)
     int num_sms = 148;
     int* ray_maxlen = nullptr;
     // GMS_UPDATE_SORTED scratch (allocated on first use)
@@ -415,9 +416,12 @@ int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* 
         h->score_parts = emit ? (int)grid : 0;
 #define SCORE_G(GG)                                                                                              \
     case GG:                                                                                                     \
-        LAUNCH(GMS_PHASE_SCORE, k_score_sorted<GG><<<grid, 128, smem_s, h->stream>>>(pose, lo, cnt, h->hit_xy, h->st, \
-                                                                                      h->fac, order, lw, xlocal, h->np, \
-                                                                                      emit, h->g));              \
+        if (h->score_v == 1)                                                                                     \
+            LAUNCH(GMS_PHASE_SCORE, (k_score_sorted<GG, 1><<<grid, 128, smem_s, h->stream>>>(                    \
+                                        pose, lo, cnt, h->hit_xy, h->st, h->fac, order, lw, xlocal, h->np, emit, h->g))); \
+        else                                                                                                     \
+            LAUNCH(GMS_PHASE_SCORE, (k_score_sorted<GG, 0><<<grid, 128, smem_s, h->stream>>>(                    \
+                                        pose, lo, cnt, h->hit_xy, h->st, h->fac, order, lw, xlocal, h->np, emit, h->g))); \
         break;
         switch (G) {
             SCORE_G(1) SCORE_G(2) SCORE_G(4) SCORE_G(8) SCORE_G(16) SCORE_G(32)
@@ -960,6 +964,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->sort_rank, (size_t)h->cnt * 4));
     CKC(cudaMalloc((void**)&h->order, (size_t)h->cnt * 4));
     h->ntiles = (h->P + 1023) / 1024;
+    if (const char* e = std::getenv("GMS_SCORE_V")) h->score_v = std::atoi(e) == 1 ? 1 : 0;
     if (const char* e = std::getenv("GMS_SCORE_G")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) h->score_g = v; }
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, h->dev) == cudaSuccess) h->num_sms = prop.multiProcessorCount; }
     {

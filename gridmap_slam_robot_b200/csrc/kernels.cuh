@@ -655,7 +655,11 @@ __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, 
 // Java's product bit for bit wherever that does not underflow, and ln() is taken once.
 // G threads share a particle (beam u*G + gsub goes to sub-thread gsub): G = 1 for ~1e5 particles, up to 32
 // (= one warp per particle) for small sets, so the grid always fills the machine.
-template <int G>
+// V selects how the fast path validates its fixed-point cell index (same accepted set, same results):
+// 0 = mask / subtract / compare per coordinate (measured, default); 1 = ALU-lean form — the margin is a power
+// of two, so "fraction within margin of an integer" is ((i + margin) & M) == 0, x and y share one unsigned min
+// and one LOP3 covers both high-word tests (GMS_SCORE_V=1; the ALU pipe is this kernel's busiest).
+template <int G, int V = 0>
 __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__ pose, int lo, int cnt,
                                                       const double2* __restrict__ hit_xy,
                                                       const Stats* __restrict__ st, const double* __restrict__ fac,
@@ -714,6 +718,7 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
     const unsigned uW = (unsigned)g.W, uH = (unsigned)g.H, oob = uW * uH;
     const int fk = g.fx_k;
     const unsigned fmask = (1u << fk) - 1u, fmarg = (unsigned)g.fx_margin, fspan = (1u << fk) - 2u * fmarg;
+    const unsigned fnear = fmask & ~(2u * fmarg - 1u);  // V == 1: the fraction bits above the 2*margin window
     // exact (slow) evaluation of one beam: the literal Java expression incl. the f64 division
     auto factor_exact = [&](const double2 m) -> double {
         {   // far outside the map (more than a cell beyond an edge): no lookup, no division needed
@@ -748,12 +753,21 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
             // is a known constant exactly when 0 <= q < 2^(31-k).  Cell = I >> k, fraction = I & (2^k - 1).
             const double tx = qx + g.fx_magic, ty = qy + g.fx_magic;
             const int ix = __double2loint(tx), iy = __double2loint(ty);
-            const bool inrange = __double2hiint(tx) == g.fx_hi && __double2hiint(ty) == g.fx_hi;
             const unsigned gx = (unsigned)ix >> fk, gy = (unsigned)iy >> fk;
-            const unsigned frx = (unsigned)ix & fmask, fry = (unsigned)iy & fmask;
-            // accepted when both fractions are >= margin away from 0 and 1: no integer lies between q~ and
-            // Java's quotient, so both truncate to the same cell
-            const bool ok = inrange && (frx - fmarg) < fspan && (fry - fmarg) < fspan;
+            bool ok;
+            if constexpr (V == 1) {
+                // fmarg is a power of two (Geometry): frac in [fmarg, 2^k - fmarg)  <=>  ((i + fmarg) & fnear) != 0
+                const unsigned hi = ((unsigned)__double2hiint(tx) ^ (unsigned)g.fx_hi) |
+                                    ((unsigned)__double2hiint(ty) ^ (unsigned)g.fx_hi);
+                const unsigned nx = ((unsigned)ix + fmarg) & fnear, ny = ((unsigned)iy + fmarg) & fnear;
+                ok = hi == 0u && min(nx, ny) != 0u;
+            } else {
+                const bool inrange = __double2hiint(tx) == g.fx_hi && __double2hiint(ty) == g.fx_hi;
+                const unsigned frx = (unsigned)ix & fmask, fry = (unsigned)iy & fmask;
+                // accepted when both fractions are >= margin away from 0 and 1: no integer lies between q~ and
+                // Java's quotient, so both truncate to the same cell
+                ok = inrange && (frx - fmarg) < fspan && (fry - fmarg) < fspan;
+            }
             const bool inb = gx < uW && gy < uH;
             bad |= ok ? 0u : (1u << u);
             idx[u] = (ok && inb) ? gy * uW + gx : oob;
