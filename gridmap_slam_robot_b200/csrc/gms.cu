@@ -307,7 +307,7 @@ int ensure_stage(gms_handle* h, size_t bytes) {
 
 int ensure_beams(gms_handle* h, int B) {
     if (B <= h->bcap) return GMS_OK;
-    if ((size_t)B * 16 > 200 * 1024) return fail(h, GMS_ERR_INVALID_ARG, "too many beams (max 12800)");
+    if (B > GMS_MAX_BEAMS) return fail(h, GMS_ERR_INVALID_ARG, "too many beams (GMS_MAX_BEAMS)");
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaStreamSynchronize(h->side_a));
     CK(cudaStreamSynchronize(h->side_b));
@@ -342,6 +342,14 @@ int ensure_beams(gms_handle* h, int B) {
         CK(cudaMalloc((void**)&h->ray_start, sizeof(float2)));
     }
     h->bcap = cap;
+    return GMS_OK;
+}
+
+// argument check shared by the step entry points; runs BEFORE flip_beams so that a rejected call leaves the
+// beam-table parity (and with it the side stream's read set) untouched
+int check_beams(gms_handle* h, int B, const void* a, const void* b, const void* c, const char* who) {
+    if (B < 0 || (B > 0 && (!a || !b || !c))) return fail(h, GMS_ERR_INVALID_ARG, std::string(who) + ": bad beam arrays");
+    if (B > GMS_MAX_BEAMS) return fail(h, GMS_ERR_INVALID_ARG, std::string(who) + ": too many beams (GMS_MAX_BEAMS)");
     return GMS_OK;
 }
 
@@ -1054,10 +1062,9 @@ EXPORT int gms_reset(gms_handle* h) {
 EXPORT int gms_update(gms_handle* h, const double* beam_xy, const double* beam_dist, const uint8_t* beam_hit,
                       int32_t B, double d_center, double d_theta, const double* normals, double* neff_out) {
     ENTER_STEP(h);
-    flip_beams(h);
-    if (B < 0 || (B > 0 && (!beam_xy || !beam_dist || !beam_hit)))
-        return fail(h, GMS_ERR_INVALID_ARG, "gms_update: bad beam arrays");
+    if (int rc_ = check_beams(h, B, beam_xy, beam_dist, beam_hit, "gms_update")) return rc_;
     if (h->cfg.nranks != 1) return fail(h, GMS_ERR_STATE, "gms_update: multi-rank handles use update_begin/end");
+    flip_beams(h);
     // staging layout: [beams | pad to 64 | normals]; size it once so upload_beams never re-allocates
     const size_t off = (((size_t)B * 25 + 63) / 64) * 64;
     int rc = ensure_stage(h, off + (normals ? (size_t)h->cnt * 16 : 0) + 64);
@@ -1342,8 +1349,8 @@ EXPORT int gms_odometry_from_counts(int32_t left, int32_t right, double* d_cente
 EXPORT int gms_update_begin_dev(gms_handle* h, const double* d_xy, const double* d_dist, const uint8_t* d_hit,
                                 int32_t B, double d_center, double d_theta, const double* d_normals) {
     ENTER_STEP(h);
+    if (int rc_ = check_beams(h, B, d_xy, d_dist, d_hit, "gms_update_begin_dev")) return rc_;
     flip_beams(h);
-    if (B < 0 || (B > 0 && (!d_xy || !d_dist || !d_hit))) return fail(h, GMS_ERR_INVALID_ARG, "bad beam arrays");
     return step_begin(h, d_xy, d_dist, d_hit, B, d_center, d_theta, d_normals);
 }
 EXPORT int gms_update_end_dev(gms_handle* h, int32_t policy, double u01) {
@@ -1354,10 +1361,10 @@ EXPORT int gms_update_end_dev(gms_handle* h, int32_t policy, double u01) {
 EXPORT int gms_step_dev(gms_handle* h, const double* d_xy, const double* d_dist, const uint8_t* d_hit, int32_t B,
                         double d_center, double d_theta, const double* d_normals, int32_t policy, double u01) {
     ENTER_STEP(h);
-    flip_beams(h);
     if (h->cfg.nranks != 1) return fail(h, GMS_ERR_STATE, "gms_step_dev: multi-rank handles use update_begin/end");
-    if (B < 0 || (B > 0 && (!d_xy || !d_dist || !d_hit))) return fail(h, GMS_ERR_INVALID_ARG, "bad beam arrays");
+    if (int rc_ = check_beams(h, B, d_xy, d_dist, d_hit, "gms_step_dev")) return rc_;
     if (policy < 0 || policy > 2 || u01 >= 1.0) return fail(h, GMS_ERR_INVALID_ARG, "bad resample policy / u01");
+    flip_beams(h);
     int rc = step_begin(h, d_xy, d_dist, d_hit, B, d_center, d_theta, d_normals);
     if (rc) return rc;
     return step_end(h, policy, u01);
@@ -1492,9 +1499,9 @@ EXPORT int gms_deskew(gms_handle* h, const double* angle, const double* dist, in
 EXPORT int gms_update_raw(gms_handle* h, const double* angle, const double* dist, const uint8_t* hit, int32_t B,
                           double d_center, double d_theta, const double* normals, double* neff_out) {
     ENTER_STEP(h);
-    flip_beams(h);
-    if (B < 0 || (B > 0 && (!angle || !dist || !hit))) return fail(h, GMS_ERR_INVALID_ARG, "gms_update_raw: bad arrays");
+    if (int rc_ = check_beams(h, B, angle, dist, hit, "gms_update_raw")) return rc_;
     if (h->cfg.nranks != 1) return fail(h, GMS_ERR_STATE, "gms_update_raw: multi-rank handles use update_begin/end");
+    flip_beams(h);
     int rc = upload_raw_and_deskew(h, angle, dist, hit, B, d_center, d_theta);
     if (rc) return rc;
     const double* d_normals = nullptr;

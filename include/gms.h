@@ -123,6 +123,11 @@ int gms_get_info(const gms_handle* h, gms_info* info);
 int gms_reset(gms_handle* h);                               /* SLAM.reset SLAM.java:65-77          */
 
 /* ---- the SLAM step -------------------------------------------------------------------------- */
+/* Largest scan any entry point accepts (the hit-beam table of the scoring kernels is staged in one
+ * CTA's shared memory: 12800 * 16 B = 200 KB); more beams -> GMS_ERR_INVALID_ARG, no state change.
+ * The reference's sweeps have 360 (ConnectionThread.java) .. 720 beams. */
+#define GMS_MAX_BEAMS 12800
+
 /* SLAM.update(Observation, Odometry) SLAM.java:80-131.  `normals` = 2*local_count standard normal
  * draws, particle-major {z_d, z_theta} (the two NormalDistribution.sample() calls of
  * Odometry.apply, Odometry.java:80-81, d first), or NULL to draw them on the device (Philox keyed

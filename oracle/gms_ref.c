@@ -714,6 +714,7 @@ EXPORT int gms_update(gms_handle *h, const double *beam_xy, const double *beam_d
     if (!h) return GMS_ERR_INVALID_ARG;
     if (B < 0 || (B > 0 && (!beam_xy || !beam_dist || !beam_hit)))
         return fail(h, GMS_ERR_INVALID_ARG, "gms_update: bad beam arrays");
+    if (B > GMS_MAX_BEAMS) return fail(h, GMS_ERR_INVALID_ARG, "gms_update: too many beams (GMS_MAX_BEAMS)");
     if (h->cfg.nranks != 1) return fail(h, GMS_ERR_STATE, "gms_update: multi-rank handles use begin/end");
     int rc = update_local(h, beam_xy, beam_dist, beam_hit, B, d_center, d_theta, normals);
     if (rc) return rc;
@@ -1008,7 +1009,9 @@ EXPORT int gms_exchange_buffers(gms_handle *h, void **dl, size_t *lb, void **dg,
 }
 EXPORT int gms_update_begin_dev(gms_handle *h, const double *bxy, const double *bdist, const uint8_t *bhit,
                                 int32_t B, double d_center, double d_theta, const double *normals) {
-    if (!h || B < 0) return GMS_ERR_INVALID_ARG;
+    if (!h) return GMS_ERR_INVALID_ARG;
+    if (B < 0 || (B > 0 && (!bxy || !bdist || !bhit))) return fail(h, GMS_ERR_INVALID_ARG, "bad beam arrays");
+    if (B > GMS_MAX_BEAMS) return fail(h, GMS_ERR_INVALID_ARG, "too many beams (GMS_MAX_BEAMS)");
     if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE && h->cfg.nranks != 1)
         return fail(h, GMS_ERR_UNSUPPORTED, "oracle: per-particle maps are single-rank only");
     free(h->pend_xy); free(h->pend_dist); free(h->pend_hit);
@@ -1069,7 +1072,9 @@ EXPORT int gms_deskew(gms_handle *h, const double *angle, const double *dist, in
 }
 EXPORT int gms_update_raw(gms_handle *h, const double *angle, const double *dist, const uint8_t *hit, int32_t n,
                           double d_center, double d_theta, const double *normals, double *neff_out) {
-    if (!h || n < 0 || (n > 0 && (!angle || !dist || !hit))) return GMS_ERR_INVALID_ARG;
+    if (!h) return GMS_ERR_INVALID_ARG;
+    if (n < 0 || (n > 0 && (!angle || !dist || !hit))) return fail(h, GMS_ERR_INVALID_ARG, "gms_update_raw: bad arrays");
+    if (n > GMS_MAX_BEAMS) return fail(h, GMS_ERR_INVALID_ARG, "gms_update_raw: too many beams (GMS_MAX_BEAMS)");
     double *xy = malloc(sizeof(double) * 2 * (n + 1)), *od = malloc(sizeof(double) * (n + 1));
     deskew(angle, dist, n, d_center, d_theta, xy, od);
     int rc = gms_update(h, xy, od, hit, n, d_center, d_theta, normals, neff_out);

@@ -250,6 +250,15 @@ def check_errors(lib):
         raise AssertionError("u01 >= 1 accepted")
     except B.GmsError as e:
         assert e.code == B.ERR_INVALID_ARG
+    # a scan longer than GMS_MAX_BEAMS is rejected and leaves the state alone
+    n = B.MAX_BEAMS + 1
+    poses_before = h.poses()
+    try:
+        h.update(np.zeros((n, 2)), np.ones(n), np.ones(n, np.uint8), 0.0, 0.0, np.zeros(4))
+        raise AssertionError("GMS_MAX_BEAMS + 1 beams accepted")
+    except B.GmsError as e:
+        assert e.code == B.ERR_INVALID_ARG
+    assert np.array_equal(h.poses(), poses_before)
     # empty scan: every weight is the empty product 1 -> uniform weights, Neff = P
     neff = h.update(np.zeros((0, 2)), np.zeros(0), np.zeros(0, np.uint8), 0.0, 0.0, np.zeros(4))
     assert abs(neff - 2.0) < 1e-12

@@ -112,3 +112,34 @@ def test_product_library_is_independent_of_the_oracle():
     assert "gmsref_" not in syms and "gms_update" in syms
     src = open(os.path.join(ROOT, "gridmap_slam_robot_b200", "csrc", "gms.cu")).read()
     assert "oracle" not in src.lower().replace("oracle/", "")  # the product source never refers to the checker
+
+
+def test_binding_constants_match_the_header():
+    """Every integer constant of include/gms.h (#define GMS_* and enum gms_status) has the same value in the
+    Python binding, and the ctypes structs have the sizes the C compiler gives them."""
+    import subprocess
+    import tempfile
+
+    hdr = open(os.path.join(ROOT, "include", "gms.h")).read()
+    consts = {k: int(v) for k, v in re.findall(r"#define\s+GMS_([A-Z_0-9]+)\s+(-?\d+)\b", hdr)}
+    consts.update({k: int(v) for k, v in re.findall(r"\bGMS_((?:OK|ERR_[A-Z_]+))\s*=\s*(-?\d+)", hdr)})
+    alias = {"RESAMPLE_NEVER": "POLICY_NEVER", "RESAMPLE_IF_NEFF_LOW": "POLICY_IF_NEFF_LOW",
+             "RESAMPLE_ALWAYS": "POLICY_ALWAYS"}
+    checked = 0
+    for name, value in consts.items():
+        if name.startswith("PHASE_") or name in ("H_", "ABI_VERSION", "IPC_HANDLE_BYTES"):
+            continue
+        py = alias.get(name, name)
+        assert hasattr(B, py), f"binding.py lacks {py} (GMS_{name})"
+        assert getattr(B, py) == value, (name, getattr(B, py), value)
+        checked += 1
+    assert checked >= 20
+    assert len(B.PHASES) == consts["PHASE_COUNT"]
+    src = '#include <stdio.h>\n#include "gms.h"\nint main(void){printf("%zu %zu\\n", sizeof(gms_config), sizeof(gms_info));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    assert [int(v) for v in out] == [ctypes.sizeof(B.Config), ctypes.sizeof(B.Info)]
