@@ -456,11 +456,11 @@ __global__ void __launch_bounds__(256) k_likelihood_tma(const __grid_constant__ 
                                                         Geometry g) {
     constexpr int KH = 3;
     constexpr int tw = (kTileW + 2 * KH + 3) & ~3, th = kTileH + 2 * KH;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_tma[];
     __shared__ __align__(8) uint64_t s_bar[2];
     constexpr int kRawBytes = (kTmaTileW * kTmaTileH * 8 + 127) & ~127;
     // two raw buffers: the TMA request of the NEXT tile is in flight while this tile is blurred
-    double* s_h = reinterpret_cast<double*>(smem_raw + 2 * kRawBytes);  // th * kTileW
+    double* s_h = reinterpret_cast<double*>(smem_tma + 2 * kRawBytes);  // th * kTileW
     float* s_t = reinterpret_cast<float*>(s_h + th * kTileW);           // th * tw
     const int tid = threadIdx.x;
     const int num_tiles = st->num_tiles;
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(256) k_likelihood_tma(const __grid_constant__ 
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            ::"r"(smem_u32(smem_raw + buf * kRawBytes)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(ox - kTmaPadX),
+            ::"r"(smem_u32(smem_tma + buf * kRawBytes)), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(ox - kTmaPadX),
               "r"(oy - KH), "r"(item.x), "r"(bar)
             : "memory");
     };
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(256) k_likelihood_tma(const __grid_constant__ 
         const int ox = (item.y % g.tiles_x) * kTileW, oy = (item.y / g.tiles_x) * kTileH;
         double* out = lik + (size_t)item.x * cells;
         if (tid == 0 && t + (int)gridDim.x < num_tiles) fetch(t + gridDim.x, buf ^ 1);
-        const CellCounts* s_c = reinterpret_cast<const CellCounts*>(smem_raw + buf * kRawBytes);
+        const CellCounts* s_c = reinterpret_cast<const CellCounts*>(smem_tma + buf * kRawBytes);
         const uint32_t bar = smem_u32(&s_bar[buf]);
         const uint32_t phase = (uint32_t)(it >> 1) & 1u;
         uint32_t done = 0;
