@@ -85,3 +85,26 @@ def test_accepted_fast_index_equals_java(W):
     assert worst < 1e-9, worst
     assert worst * 1000 < marg / (1 << k)
     assert accepted > 2000 and rejected > 200, (accepted, rejected)  # both branches exercised
+
+
+def test_guarded_reciprocal_cell_of():
+    """cell_of() of csrc/device_math.cuh (k_score, per-particle maps): trunc(t * (1/res)) is used only when it lies
+    more than 1e-5 from both neighbouring integers; then it must equal Java's (int) (t / res)."""
+    rng = np.random.default_rng(77)
+    for res in (f32(0.05), f32(0.025), f32(0.1), f32(0.03)):
+        inv = 1.0 / res
+        fast = slow = 0
+        for n in range(20000):
+            t = float(rng.uniform(-20, 250))
+            if n % 2:  # next to a cell boundary, on either side, down to a few ulps
+                cell = float(rng.integers(-50, 5000))
+                t = cell * res + float(rng.choice([0.0, 1e-16, -1e-16, 1e-13, -1e-13, 1e-9, -1e-9, 4e-7, -4e-7, 6e-7, -6e-7]))
+            q = t * inv
+            nq = int(q)
+            fr = abs(q - nq)
+            if 1e-5 < fr < 1.0 - 1e-5:
+                fast += 1
+                assert nq == d2i(t / res), (res, t)
+            else:
+                slow += 1
+        assert fast > 9000 and slow > 2000, (fast, slow)
