@@ -425,11 +425,11 @@ int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* 
 #define SCORE_G(GG)                                                                                              \
     case GG:                                                                                                     \
         if (h->score_v == 1)                                                                                     \
-            LAUNCH(GMS_PHASE_SCORE, (k_score_sorted<GG, 1><<<grid, 128, smem_s, h->stream>>>(                    \
-                                        pose, lo, cnt, h->hit_xy, h->st, h->fac, order, lw, xlocal, h->np, emit, h->g))); \
+            LAUNCH(GMS_PHASE_SCORE, k_score_sorted<GG, 1><<<grid, 128, smem_s, h->stream>>>(                     \
+                                        pose, lo, cnt, h->hit_xy, h->st, h->fac, order, lw, xlocal, h->np, emit, h->g)); \
         else                                                                                                     \
-            LAUNCH(GMS_PHASE_SCORE, (k_score_sorted<GG, 0><<<grid, 128, smem_s, h->stream>>>(                    \
-                                        pose, lo, cnt, h->hit_xy, h->st, h->fac, order, lw, xlocal, h->np, emit, h->g))); \
+            LAUNCH(GMS_PHASE_SCORE, k_score_sorted<GG, 0><<<grid, 128, smem_s, h->stream>>>(                     \
+                                        pose, lo, cnt, h->hit_xy, h->st, h->fac, order, lw, xlocal, h->np, emit, h->g)); \
         break;
         switch (G) {
             SCORE_G(1) SCORE_G(2) SCORE_G(4) SCORE_G(8) SCORE_G(16) SCORE_G(32)
