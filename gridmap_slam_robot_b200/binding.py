@@ -21,9 +21,9 @@ RESAMPLE_AUTO, RESAMPLE_LITERAL, RESAMPLE_FIXED = 0, 1, 2
 MAP_LOG, MAP_LIKELIHOOD, MAP_FREE_COUNT, MAP_OCC_COUNT = 0, 1, 2, 3
 POLICY_NEVER, POLICY_IF_NEFF_LOW, POLICY_ALWAYS = 0, 1, 2
 UPDATE_ATOMIC, UPDATE_SORTED = 0, 1
-IPC_NUM_HANDLES = 7
+IPC_NUM_HANDLES = 9
 MAX_BEAMS = 12800  # GMS_MAX_BEAMS
-PHASES = ("motion", "likelihood", "score", "normalise", "map_update", "resample", "map_copy", "other")
+PHASES = ("motion", "likelihood", "score", "normalise", "map_update", "resample", "map_copy", "exchange", "other")
 
 
 class GmsError(RuntimeError):
@@ -60,6 +60,7 @@ class Info(C.Structure):
 
 _vp, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 _P = C.POINTER
+POSE_OPTIMIZER_FN = C.CFUNCTYPE(C.c_int, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _f64, _f64)
 
 # every symbol include/gms.h declares: name -> argtypes (restype is int unless noted)
 SYMBOLS = {
@@ -90,6 +91,8 @@ SYMBOLS = {
     "gms_odometry_from_counts": [_i32, _i32, _P(_f64), _P(_f64)],
     "gms_step_dev": [_vp, _vp, _vp, _vp, _i32, _f64, _f64, _vp, _i32, _f64],
     "gms_sync": [_vp],
+    "gms_join_streams": [_vp],
+    "gms_set_pose_optimizer": [_vp, _vp, _vp],
     "gms_set_stream": [_vp, _vp],
     "gms_profile_enable": [_vp, _i32],
     "gms_profile_read": [_vp, _vp, _vp],
@@ -351,6 +354,34 @@ class Handle:
 
     def sync(self):
         self._ck(self.dll.gms_sync(self.h))
+
+    def join_streams(self):
+        self._ck(self.dll.gms_join_streams(self.h))
+
+    def set_pose_optimizer(self, fn=None):
+        """A4 hook (GridMap.findBestPoseOptim): fn(first_particle, poses[count,3] f32 in/out, beam_xy[B,2], beam_dist[B],
+        beam_hit[B], d_center, d_theta) -> None, or None to restore the identity default."""
+        if fn is None:
+            self._opt_cb = None
+            self._ck(self.dll.gms_set_pose_optimizer(self.h, None, None))
+            return
+
+        def tramp(user, hptr, first, count, poses, bxy, bdist, bhit, nb, dc, dt):
+            try:
+                p = np.ctypeslib.as_array(C.cast(poses, C.POINTER(C.c_float)), shape=(count, 3))
+                xy = np.ctypeslib.as_array(C.cast(bxy, C.POINTER(C.c_double)), shape=(nb, 2)) if nb else np.zeros((0, 2))
+                d = np.ctypeslib.as_array(C.cast(bdist, C.POINTER(C.c_double)), shape=(nb,)) if nb else np.zeros(0)
+                hh = np.ctypeslib.as_array(C.cast(bhit, C.POINTER(C.c_uint8)), shape=(nb,)) if nb else np.zeros(0, np.uint8)
+                fn(first, p, xy, d, hh, dc, dt)
+                return 0
+            except Exception:  # a Python exception must not unwind through the C frames
+                import traceback
+
+                traceback.print_exc()
+                return 1
+
+        self._opt_cb = POSE_OPTIMIZER_FN(tramp)
+        self._ck(self.dll.gms_set_pose_optimizer(self.h, C.cast(self._opt_cb, _vp), None))
 
     def set_stream(self, stream_ptr):
         self._ck(self.dll.gms_set_stream(self.h, stream_ptr))

@@ -31,6 +31,16 @@ struct PhaseSpan {
     cudaEvent_t a, b;
 };
 
+// one scan on the device: the table as uploaded + what k_pack_beams derives from it
+struct BeamSet {
+    double2* xy = nullptr;     // {localX, localY} of every beam (private copy: the map integration reads it later)
+    double* dist = nullptr;    // Measurement.distance (metres)
+    uint8_t* hit = nullptr;    // wasHit
+    float* meas = nullptr;     // (float) distance / resolution (GridMap.java:188)
+    double2* hit_xy = nullptr; // compacted hit beams (scoring reads only those, GridMap.java:269-270)
+    int* num_hit = nullptr;
+};
+
 }  // namespace
 
 struct gms_handle {
@@ -40,12 +50,13 @@ struct gms_handle {
     size_t cells = 0;
     float world_w = 0, world_h = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    // shared map: two side streams let independent chains of one step overlap (likelihood refresh next to
+    // shared map: side streams let independent chains of one step overlap (likelihood refresh next to
     // motion + heading sort; map integration next to resampling); joined back before anything depends on them
-    cudaStream_t side_a = nullptr, side_b = nullptr, side_c = nullptr;
-    cudaEvent_t ev_fork_a = nullptr, ev_done_a = nullptr, ev_fork_b = nullptr, ev_done_b = nullptr, ev_done_c = nullptr;
+    cudaStream_t side_a = nullptr, side_b = nullptr;
+    cudaEvent_t ev_fork_a = nullptr, ev_done_a = nullptr, ev_fork_b = nullptr, ev_done_b = nullptr;
     bool overlap = true;  // GMS_NO_OVERLAP=1 serialises everything on one stream
     bool b_pending = false;  // a map integration is still running on side_b (joined by the next consumer)
+    bool coop = true;     // cooperative launches available (always on sm_100; GMS_NO_COOP=1 is a debugging aid)
     // particle state (double buffered for resampling)
     float4* pose[2] = {nullptr, nullptr};
     double* w[2] = {nullptr, nullptr};
@@ -61,34 +72,32 @@ struct gms_handle {
     alignas(64) CUtensorMap lik_tmap{};  // 3-D tensor map of the counter arena {W, H, S} for k_likelihood_tma
     bool lik_tma = false;
     int4* rect = nullptr;        // explored bounding box per slot
-    uint32_t* dirty = nullptr;   // dirty-tile bitmap per slot
+    uint32_t* dirty = nullptr;   // dirty-tile bitmap per slot: the PENDING set (read by the next likelihood refresh)
+    uint32_t* dirty_alt = nullptr;  // shared map with the self-listing refresh: the buffer the last refresh consumed
+    bool alt_needs_clear = false;
+    bool self_list = false;      // shared map, bitmap small enough: the refresh builds its own work list
     int* word_off = nullptr;
     int2* tile_list = nullptr;
     int tiles_per_map = 0;
     int4* dup_rect = nullptr;
     int *dup_src = nullptr, *dup_dst = nullptr, *dup_src_rank = nullptr, *dup_level = nullptr, *scratch2p = nullptr;
-    // per-particle maps across ranks: peer mappings of every rank's arenas (cudaIpc)
+    // peer mappings of every rank's arenas (cudaIpc; one process per GPU on one node)
     PeerTable peers{};
     bool peers_ready = false;
     void* ipc_opened[kMaxRanks][GMS_IPC_NUM_HANDLES] = {};
-    // fused exchange: double-buffered receive buffers + arrival flags, peer-mapped after gms_ipc_import
-    ExchangeRec* xg2[2] = {nullptr, nullptr};
+    // peer exchange of the log-weights: double-buffered receive buffers + arrival flags + peer pose arrays
+    double* xlw[2] = {nullptr, nullptr};
     unsigned long long* xflags = nullptr;
-    ExchangeRec* peer_xg[2][kMaxRanks] = {};
-    XFlags peer_flags{};
+    unsigned* xticket = nullptr;
+    double* peer_xlw[2][kMaxRanks] = {};
+    unsigned long long* peer_flags[kMaxRanks] = {};
+    const float4* peer_pose[2][kMaxRanks] = {};
     unsigned long long xseq = 0;
     bool direct = false;
-    // beams
+    // beams: two step sets (the shared-map integration of step N may still read set N%2 on the side stream while
+    // step N+1 uploads into the other) + one set for the GridMap operator entry points / the pose-optimiser hook
     int bcap = 0;
-    double2 *in_xy = nullptr, *all_xy = nullptr, *hit_xy = nullptr;
-    double* in_dist = nullptr;
-    uint8_t *in_hit = nullptr, *all_hit = nullptr;
-    float* meas = nullptr;
-    // two sets of {all_xy, all_hit, meas}: the shared-map integration of step N may still read set N%2 on the
-    // side stream while step N+1 uploads into the other set; all_xy / all_hit / meas point at the current one
-    double2* all_xy2[2] = {nullptr, nullptr};
-    uint8_t* all_hit2[2] = {nullptr, nullptr};
-    float* meas2[2] = {nullptr, nullptr};
+    BeamSet bs[2], ops;
     int bset = 0;
     double *raw_angle = nullptr, *raw_dist = nullptr;  // raw sweep for the fused de-skew
     double* d_normals = nullptr;
@@ -99,8 +108,7 @@ struct gms_handle {
     int* comb_off = nullptr;
     int2* comb_list = nullptr;
     // heading sort for k_score_sorted
-    unsigned *sort_hist = nullptr, *sort_offs = nullptr, *sort_key = nullptr, *sort_rank = nullptr, *sort_cta = nullptr;
-    int* order = nullptr;
+    SortBufs sort{};
     // tile partials of normalise / neff / weighted pose
     int ntiles = 0;
     NormPartials np{};
@@ -112,8 +120,6 @@ struct gms_handle {
     bool resample_partial = false;
     double partial_u01 = 0;
     unsigned long long partial_count = 0;
-    int np_cap = 0;
-    int score_parts = 0;  // > 0: the last scoring launch already wrote that many (m, idx, s) partials
     int score_g = 0;  // sub-threads per particle in k_score_sorted (0 = automatic; GMS_SCORE_G overrides: tuning knob)
     int score_v = 0;  // index-validation variant of k_score_sorted (GMS_SCORE_V=1: ALU-lean form, same results)
     int num_sms = 148;
@@ -123,12 +129,12 @@ struct gms_handle {
     int *sk_runlen = nullptr, *sk_nruns = nullptr;
     void* sk_temp = nullptr;
     size_t sk_temp_bytes = 0, sk_cap = 0;
-    // shared-map two-pass update: recorded ray cells
+    // shared-map update: recorded ray cells
     uint32_t* ray_cells = nullptr;
     int* ray_count = nullptr;
     float2* ray_start = nullptr;
     int ray_cap = 0;
-    // exchange, scratch, stats
+    // exchange (collective path), scratch, stats
     ExchangeRec *xlocal = nullptr, *xglobal = nullptr;
     void* d_tmp = nullptr;  // max(cells*8, P*24) bytes
     size_t d_tmp_bytes = 0;
@@ -137,9 +143,18 @@ struct gms_handle {
     double* tmp_lw = nullptr;
     Stats* st = nullptr;
     Stats* h_st = nullptr;  // pinned
-    unsigned char* h_stage = nullptr;
-    size_t h_stage_bytes = 0;
+    // pinned staging ring for the host-buffer entry points: slot k is reused only after the copy enqueued from
+    // it has completed (one event per slot), so an upload never synchronises the stream
+    static constexpr int kStageSlots = 4;
+    unsigned char* h_stage[kStageSlots] = {};
+    size_t h_stage_bytes[kStageSlots] = {};
+    cudaEvent_t h_stage_ev[kStageSlots] = {};
+    int stage_next = 0;
     bool stats_valid = false;
+    // A4: optional CPU pose optimiser between motion and scoring (GridMap.findBestPoseOptim); default none = identity
+    gms_pose_optimizer_fn opt_fn = nullptr;
+    void* opt_user = nullptr;
+    float* h_opt_poses = nullptr;  // pinned, 3 * cnt
     // step bookkeeping
     uint64_t step = 0, resample_count = 0;
     bool have_update = false, pending = false;
@@ -214,13 +229,19 @@ inline void count_launch(gms_handle* h, int phase) {
         count_launch(h, phase);                                    \
         CK(cudaGetLastError());                                    \
     } while (0)
+// cooperative launch (grid-wide barriers inside the kernel): every CTA of the grid is co-resident
+#define LAUNCH_COOP(phase, kernel, grid, block, smem, ...)                                               \
+    do {                                                                                                 \
+        void* args_[] = {__VA_ARGS__};                                                                   \
+        CK(cudaLaunchCooperativeKernel((const void*)(kernel), dim3(grid), dim3(block), args_, smem, h->stream)); \
+        count_launch(h, phase);                                                                          \
+    } while (0)
 
 int flush_profile(gms_handle* h) {
     if (h->spans.empty()) return GMS_OK;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaStreamSynchronize(h->side_a));  // phases of the shared-map step are timed on the stream they run on
     CK(cudaStreamSynchronize(h->side_b));
-    CK(cudaStreamSynchronize(h->side_c));
     for (auto& s : h->spans) {
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, s.a, s.b));
@@ -254,54 +275,85 @@ int java_d2i_host(double d) {
     return (int)d;
 }
 
+void free_beamset(BeamSet& b) {
+    cudaFree(b.xy); cudaFree(b.dist); cudaFree(b.hit); cudaFree(b.meas); cudaFree(b.hit_xy); cudaFree(b.num_hit);
+    b = BeamSet{};
+}
+
 void free_all(gms_handle* h) {
     if (!h) return;
     cudaSetDevice(h->dev);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->side_a) cudaStreamSynchronize(h->side_a);
     if (h->side_b) cudaStreamSynchronize(h->side_b);
-    if (h->side_c) cudaStreamSynchronize(h->side_c);
     for (int q = 0; q < kMaxRanks; q++)
         for (int k = 0; k < GMS_IPC_NUM_HANDLES; k++)
             if (h->ipc_opened[q][k]) cudaIpcCloseMemHandle(h->ipc_opened[q][k]);
-    cudaFree(h->xg2[0]); cudaFree(h->xg2[1]); cudaFree(h->xflags);
+    cudaFree(h->xlw[0]); cudaFree(h->xlw[1]); cudaFree(h->xflags); cudaFree(h->xticket);
     for (int i = 0; i < 2; i++) { cudaFree(h->pose[i]); cudaFree(h->w[i]); cudaFree(h->lw[i]); cudaFree(h->slot[i]); }
     cudaFree(h->parents); cudaFree(h->cdf); cudaFree(h->counts); cudaFree(h->lik); cudaFree(h->fac); cudaFree(h->rect);
-    cudaFree(h->dirty); cudaFree(h->word_off); cudaFree(h->tile_list); cudaFree(h->dup_rect); cudaFree(h->dup_src_rank); cudaFree(h->dup_level); cudaFree(h->dup_src); cudaFree(h->dup_dst); cudaFree(h->scratch2p);
-    cudaFree(h->in_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
-    for (int i = 0; i < 2; i++) { cudaFree(h->all_xy2[i]); cudaFree(h->all_hit2[i]); cudaFree(h->meas2[i]); }
+    cudaFree(h->dirty); cudaFree(h->dirty_alt); cudaFree(h->word_off); cudaFree(h->tile_list); cudaFree(h->dup_rect);
+    cudaFree(h->dup_src_rank); cudaFree(h->dup_level); cudaFree(h->dup_src); cudaFree(h->dup_dst); cudaFree(h->scratch2p);
+    free_beamset(h->bs[0]); free_beamset(h->bs[1]); free_beamset(h->ops);
     cudaFree(h->d_normals); cudaFree(h->xlocal); cudaFree(h->xglobal);
     cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start); cudaFree(h->ray_maxlen);
     cudaFree(h->sk_keys); cudaFree(h->sk_sorted); cudaFree(h->sk_unique); cudaFree(h->sk_runlen); cudaFree(h->sk_nruns);
     cudaFree(h->sk_temp);
     cudaFree(h->raw_angle); cudaFree(h->raw_dist); cudaFree(h->comb_log); cudaFree(h->comb_lik); cudaFree(h->comb_sign);
     cudaFree(h->comb_dirty); cudaFree(h->comb_off); cudaFree(h->comb_list);
-    cudaFree(h->sort_hist); cudaFree(h->sort_cta); cudaFree(h->sort_offs); cudaFree(h->sort_key); cudaFree(h->sort_rank); cudaFree(h->order);
+    cudaFree(h->sort.hist); cudaFree(h->sort.chunk_total); cudaFree(h->sort.offs); cudaFree(h->sort.key);
+    cudaFree(h->sort.rank); cudaFree(h->sort.order);
     cudaFree(h->np.m); cudaFree(h->np.idx); cudaFree(h->np.s); cudaFree(h->np.ws); cudaFree(h->np.q); cudaFree(h->np.fx);
     cudaFree(h->np.counter); cudaFree(h->wp_part); cudaFree(h->wp_counter);
     cudaFree(h->d_tmp); cudaFree(h->tmp_pose); cudaFree(h->tmp_slot); cudaFree(h->tmp_lw); cudaFree(h->st);
     if (h->h_st) cudaFreeHost(h->h_st);
-    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->h_opt_poses) cudaFreeHost(h->h_opt_poses);
+    for (int k = 0; k < gms_handle::kStageSlots; k++) {
+        if (h->h_stage[k]) cudaFreeHost(h->h_stage[k]);
+        if (h->h_stage_ev[k]) cudaEventDestroy(h->h_stage_ev[k]);
+    }
     for (auto& s : h->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : h->pool) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->side_a) cudaStreamDestroy(h->side_a);
     if (h->side_b) cudaStreamDestroy(h->side_b);
-    if (h->side_c) cudaStreamDestroy(h->side_c);
-    for (cudaEvent_t e : {h->ev_fork_a, h->ev_done_a, h->ev_fork_b, h->ev_done_b, h->ev_done_c})
+    for (cudaEvent_t e : {h->ev_fork_a, h->ev_done_a, h->ev_fork_b, h->ev_done_b})
         if (e) cudaEventDestroy(e);
     delete h;
 }
 
-int ensure_stage(gms_handle* h, size_t bytes) {
-    if (bytes <= h->h_stage_bytes) return GMS_OK;
-    CK(cudaStreamSynchronize(h->stream));
-    if (h->h_stage) cudaFreeHost(h->h_stage);
-    h->h_stage = nullptr;
-    h->h_stage_bytes = 0;
-    size_t n = bytes + bytes / 2 + 4096;
-    CK(cudaMallocHost((void**)&h->h_stage, n));
-    h->h_stage_bytes = n;
+// Next slot of the pinned staging ring, at least `bytes` large.  Blocks only if the copy enqueued from this
+// slot kStageSlots uploads ago has not finished yet (it has: a step lies in between).
+int stage_acquire(gms_handle* h, size_t bytes, unsigned char** out, int* slot) {
+    const int k = h->stage_next;
+    h->stage_next = (k + 1) % gms_handle::kStageSlots;
+    if (!h->h_stage_ev[k]) CK(cudaEventCreateWithFlags(&h->h_stage_ev[k], cudaEventDisableTiming));
+    else CK(cudaEventSynchronize(h->h_stage_ev[k]));
+    if (bytes > h->h_stage_bytes[k]) {
+        if (h->h_stage[k]) cudaFreeHost(h->h_stage[k]);
+        h->h_stage[k] = nullptr;
+        h->h_stage_bytes[k] = 0;
+        const size_t n = bytes + bytes / 2 + 4096;
+        CK(cudaMallocHost((void**)&h->h_stage[k], n));
+        h->h_stage_bytes[k] = n;
+    }
+    *out = h->h_stage[k];
+    *slot = k;
+    return GMS_OK;
+}
+int stage_release(gms_handle* h, int slot) {  // after the last copy from the slot has been enqueued
+    CK(cudaEventRecord(h->h_stage_ev[slot], h->stream));
+    return GMS_OK;
+}
+
+int alloc_beamset(gms_handle* h, BeamSet& b, int cap) {
+    CK(cudaMalloc((void**)&b.xy, (size_t)cap * 16));
+    CK(cudaMalloc((void**)&b.dist, (size_t)cap * 8));
+    CK(cudaMalloc((void**)&b.hit, (size_t)cap));
+    CK(cudaMalloc((void**)&b.meas, (size_t)cap * 4));
+    CK(cudaMalloc((void**)&b.hit_xy, (size_t)cap * 16));
+    CK(cudaMalloc((void**)&b.num_hit, 4));
+    CK(cudaMemset(b.num_hit, 0, 4));
     return GMS_OK;
 }
 
@@ -311,27 +363,17 @@ int ensure_beams(gms_handle* h, int B) {
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaStreamSynchronize(h->side_a));
     CK(cudaStreamSynchronize(h->side_b));
-    CK(cudaStreamSynchronize(h->side_c));
     h->b_pending = false;
-    cudaFree(h->in_xy); cudaFree(h->hit_xy); cudaFree(h->in_dist); cudaFree(h->in_hit);
-    for (int i = 0; i < 2; i++) { cudaFree(h->all_xy2[i]); cudaFree(h->all_hit2[i]); cudaFree(h->meas2[i]); h->all_xy2[i] = nullptr; h->all_hit2[i] = nullptr; h->meas2[i] = nullptr; }
+    free_beamset(h->bs[0]); free_beamset(h->bs[1]); free_beamset(h->ops);
     cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start);
     cudaFree(h->raw_angle); cudaFree(h->raw_dist);
     h->raw_angle = h->raw_dist = nullptr;
-    h->in_xy = h->all_xy = h->hit_xy = nullptr; h->in_dist = nullptr; h->in_hit = h->all_hit = nullptr; h->meas = nullptr;
     h->ray_cells = nullptr; h->ray_count = nullptr; h->ray_start = nullptr;
     h->bcap = 0;
     const int cap = ((B + 255) / 256) * 256;
-    CK(cudaMalloc((void**)&h->in_xy, (size_t)cap * 16));
-    for (int i = 0; i < 2; i++) {
-        CK(cudaMalloc((void**)&h->all_xy2[i], (size_t)cap * 16));
-        CK(cudaMalloc((void**)&h->all_hit2[i], (size_t)cap));
-        CK(cudaMalloc((void**)&h->meas2[i], (size_t)cap * 4));
-    }
-    h->all_xy = h->all_xy2[h->bset]; h->all_hit = h->all_hit2[h->bset]; h->meas = h->meas2[h->bset];
-    CK(cudaMalloc((void**)&h->hit_xy, (size_t)cap * 16));
-    CK(cudaMalloc((void**)&h->in_dist, (size_t)cap * 8));
-    CK(cudaMalloc((void**)&h->in_hit, (size_t)cap));
+    int rc;
+    for (BeamSet* b : {&h->bs[0], &h->bs[1], &h->ops})
+        if ((rc = alloc_beamset(h, *b, cap))) return rc;
     CK(cudaMalloc((void**)&h->raw_angle, (size_t)cap * 8));
     CK(cudaMalloc((void**)&h->raw_dist, (size_t)cap * 8));
     if (h->cfg.map_mode == GMS_MAP_SHARED) {
@@ -354,99 +396,120 @@ int check_beams(gms_handle* h, int B, const void* a, const void* b, const void* 
 }
 
 // start of a step: switch to the beam-table set the side stream is not reading
-void flip_beams(gms_handle* h) {
-    h->bset ^= 1;
-    h->all_xy = h->all_xy2[h->bset];
-    h->all_hit = h->all_hit2[h->bset];
-    h->meas = h->meas2[h->bset];
-}
+void flip_beams(gms_handle* h) { h->bset ^= 1; }
+inline BeamSet& cur_beams(gms_handle* h) { return h->bs[h->bset]; }
 
 int fetch_stats(gms_handle* h) {
     if (h->stats_valid) return GMS_OK;
     CK(cudaMemcpyAsync(h->h_st, h->st, sizeof(Stats), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (h->h_st->xerror) return fail(h, GMS_ERR_STATE, "fused exchange: a peer's records did not arrive (rank out of step?)");
+    if (h->h_st->xerror)
+        return fail(h, GMS_ERR_STATE, "peer exchange: a rank's log-weights did not arrive (rank out of step?); the "
+                                      "step was abandoned before it changed any state");
     h->stats_valid = true;
     return GMS_OK;
 }
 
+PoseTable pose_table(const gms_handle* h, int buf) {
+    PoseTable t{};
+    t.cnt = h->cnt;
+    for (int q = 0; q < h->cfg.nranks; q++)
+        t.p[q] = (h->direct && q != h->cfg.rank) ? h->peer_pose[buf][q] : h->pose[buf];
+    return t;
+}
+
 // ---- the step, as stream-ordered launches ---------------------------------------------------------
-int launch_pack(gms_handle* h, const double* d_xy, const double* d_dist, const uint8_t* d_hit, int B) {
-    int rc = ensure_beams(h, B);
-    if (rc) return rc;
+int launch_pack(gms_handle* h, BeamSet& b, const double* d_xy, const double* d_dist, const uint8_t* d_hit, int B) {
     LAUNCH(GMS_PHASE_SCORE, k_pack_beams<<<1, 256, 0, h->stream>>>((const double2*)d_xy, d_dist, d_hit, B, h->g.res_f,
-                                                                   h->hit_xy, h->meas, h->all_xy, h->all_hit, h->st));
+                                                                   b.hit_xy, b.meas, b.xy, b.hit, b.num_hit));
+    return GMS_OK;
+}
+
+// blur launch over a work list (k_lik_scan / k_lik_emit) or, with `sl.bitmap`, over the bitmap itself
+int launch_blur(gms_handle* h, const CellCounts* counts, double* lik, double* fac, const int2* list, SelfList sl,
+                long long max_tiles, bool allow_tma) {
+    const int k = h->g.khalf, th = kTileH + 2 * k, tw = (kTileW + 2 * k + 3) & ~3;
+    const size_t smem = (size_t)th * kTileW * 8 + (size_t)th * tw * 4;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(max_tiles, (long long)h->num_sms * 6));
+    if (allow_tma && h->lik_tma) {
+        const size_t smem_t = 2 * (((size_t)kTmaTileW * kTmaTileH * 8 + 127) / 128 * 128) + smem;
+        LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood_tma<<<grid, 256, smem_t, h->stream>>>(h->lik_tmap, lik, fac, list, h->st, sl, h->g));
+    } else if (k == 3)
+        LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<3><<<grid, 256, smem, h->stream>>>(counts, lik, fac, list, h->st, sl, h->g));
+    else
+        LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<0><<<grid, 256, smem, h->stream>>>(counts, lik, fac, list, h->st, sl, h->g));
     return GMS_OK;
 }
 
 int launch_likelihood(gms_handle* h) {
     Phase ph(h, GMS_PHASE_LIKELIHOOD);
+    if (h->self_list) {
+        // shared map: ONE launch; the refresh reads the pending bitmap, new marks go to the other buffer
+        if (h->alt_needs_clear) CK(cudaMemsetAsync(h->dirty_alt, 0, (size_t)h->g.tile_words * 4, h->stream));
+        const SelfList sl{h->dirty, h->g.tile_words};
+        int rc = launch_blur(h, h->counts, h->lik, h->fac, nullptr, sl, h->tiles_per_map, true);
+        if (rc) return rc;
+        std::swap(h->dirty, h->dirty_alt);
+        h->alt_needs_clear = true;
+        return GMS_OK;
+    }
     const int nwords = h->S * h->g.tile_words;
-    LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_scan<<<1, 1024, 0, h->stream>>>(h->dirty, nwords, h->word_off, h->st,
-                                                                       h->ray_maxlen));
+    LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_scan<<<1, 1024, 0, h->stream>>>(h->dirty, nwords, h->word_off, h->st));
     LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_emit<<<blocks_for(nwords, 256), 256, 0, h->stream>>>(
                                      h->dirty, nwords, h->g.tile_words, h->word_off, h->tile_list));
-    const int k = h->g.khalf, th = kTileH + 2 * k, tw = (kTileW + 2 * k + 3) & ~3;
-    const size_t smem = (size_t)th * kTileW * 8 + (size_t)th * tw * 4;
-    const long long max_tiles = (long long)h->S * h->tiles_per_map;
-    const unsigned grid = (unsigned)std::min<long long>(max_tiles, 148 * 6);
-    if (h->lik_tma) {
-        const size_t smem_t = 2 * (((size_t)kTmaTileW * kTmaTileH * 8 + 127) / 128 * 128) + (size_t)th * kTileW * 8 + (size_t)th * tw * 4;
-        LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood_tma<<<grid, 256, smem_t, h->stream>>>(h->lik_tmap, h->lik, h->fac,
-                                                                                         h->tile_list, h->st, h->g));
-    } else if (k == 3)
-        LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<3><<<grid, 256, smem, h->stream>>>(h->counts, h->lik, h->fac,
-                                                                                      h->tile_list, h->st, h->g));
-    else
-        LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<0><<<grid, 256, smem, h->stream>>>(h->counts, h->lik, h->fac,
-                                                                                      h->tile_list, h->st, h->g));
-    return GMS_OK;
+    return launch_blur(h, h->counts, h->lik, h->fac, h->tile_list, SelfList{nullptr, 0},
+                       (long long)h->S * h->tiles_per_map, true);
 }
 
 // Thread-per-particle scoring in heading order pays off when one shared field serves many particles
 // (see k_score_sorted); per-particle maps and small particle sets keep one warp per particle.
-bool use_sorted_score(const gms_handle* h) { return h->cfg.map_mode == GMS_MAP_SHARED && h->cnt >= 4096; }
+bool use_sorted_score(const gms_handle* h) { return h->cfg.map_mode == GMS_MAP_SHARED && h->cnt >= 4096 && h->coop; }
 // every shared-map scoring of the step runs k_score_sorted (factor field + FMA cell index)
 bool use_fac_score(const gms_handle* h) { return h->cfg.map_mode == GMS_MAP_SHARED; }
 
-int launch_score(gms_handle* h, const float4* pose, int lo, int cnt, const int* slot, double* lw,
+template <int G, int V>
+int launch_score_sorted(gms_handle* h, unsigned grid, size_t smem, const float4* pose, int lo, int cnt, const BeamSet& b,
+                        const int* order, double* lw, ExchangeRec* xlocal) {
+    static bool attr_done = false;  // per instantiation: scans above 3072 beams need more than the default 48 KB
+    if (!attr_done) {
+        CK(cudaFuncSetAttribute(k_score_sorted<G, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    LAUNCH(GMS_PHASE_SCORE, k_score_sorted<G, V><<<grid, 128, smem, h->stream>>>(pose, lo, cnt, b.hit_xy, b.num_hit, h->fac,
+                                                                                 order, lw, xlocal, h->g));
+    return GMS_OK;
+}
+
+int launch_score(gms_handle* h, const BeamSet& b, const float4* pose, int lo, int cnt, const int* slot, double* lw,
                  ExchangeRec* xlocal, int B, bool sorted = false) {
     Phase ph(h, GMS_PHASE_SCORE);
+    const size_t smem = std::max<size_t>(16, (size_t)B * 16);
     if (sorted) {
-        const size_t smem_s = std::max<size_t>(16, (size_t)B * 16);
         // sub-threads per particle: enough threads to fill the machine (>= ~150k), at most one warp per particle
         int G = 1;
         while (G < 32 && (long long)cnt * G < 200000) G *= 2;
         if (h->score_g) G = h->score_g;
-        const int* order = use_sorted_score(h) ? h->order : nullptr;
+        const int* order = use_sorted_score(h) ? h->sort.order : nullptr;
         const unsigned grid = blocks_for((long long)cnt * G, 128);
-        const int emit = h->cfg.nranks == 1 && (int)grid <= h->np_cap;  // normalise consumes the CTA partials directly
-        h->score_parts = emit ? (int)grid : 0;
-#define SCORE_G(GG)                                                                                              \
-    case GG:                                                                                                     \
-        if (h->score_v == 1)                                                                                     \
-            LAUNCH(GMS_PHASE_SCORE, k_score_sorted<GG, 1><<<grid, 128, smem_s, h->stream>>>(                     \
-                                        pose, lo, cnt, h->hit_xy, h->st, h->fac, order, lw, xlocal, h->np, emit, h->g)); \
-        else                                                                                                     \
-            LAUNCH(GMS_PHASE_SCORE, k_score_sorted<GG, 0><<<grid, 128, smem_s, h->stream>>>(                     \
-                                        pose, lo, cnt, h->hit_xy, h->st, h->fac, order, lw, xlocal, h->np, emit, h->g)); \
-        break;
+#define SCORE_G(GG)                                                                                            \
+    case GG:                                                                                                   \
+        return h->score_v == 1 ? launch_score_sorted<GG, 1>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
+                               : launch_score_sorted<GG, 0>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal);
         switch (G) {
             SCORE_G(1) SCORE_G(2) SCORE_G(4) SCORE_G(8) SCORE_G(16) SCORE_G(32)
         }
 #undef SCORE_G
-        return GMS_OK;
+        return fail(h, GMS_ERR_STATE, "launch_score: bad sub-thread count");
     }
-    const unsigned grid = std::min<unsigned>(blocks_for(cnt, 8), 148 * 8);
-    const size_t smem = std::max<size_t>(16, (size_t)B * 16);
-    LAUNCH(GMS_PHASE_SCORE, k_score<<<grid, 256, smem, h->stream>>>(pose, lo, cnt, h->hit_xy, h->st, h->lik, slot,
-                                                                     lw, xlocal, h->g));
+    const unsigned grid = std::min<unsigned>(blocks_for(cnt, 8), (unsigned)h->num_sms * 8);
+    LAUNCH(GMS_PHASE_SCORE, k_score<<<grid, 256, smem, h->stream>>>(pose, lo, cnt, b.hit_xy, b.num_hit, h->lik, slot, lw,
+                                                                     xlocal, h->g));
     return GMS_OK;
 }
 
 // GMS_UPDATE_SORTED: the atomic-free scatter.  The key count is read back (one 4-byte D2H + sync) so the sort
 // covers only the cells the scan produced; the mode exists to be measured against the default.
-int launch_sorted_update(gms_handle* h, int Bpad) {
+int launch_sorted_update(gms_handle* h, const BeamSet& b, int Bpad) {
     int maxlen = 0;
     CK(cudaMemcpyAsync(&maxlen, h->ray_maxlen, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -469,8 +532,7 @@ int launch_sorted_update(gms_handle* h, int Bpad) {
         h->sk_cap = cap;
     }
     LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_keys<<<148 * 4, 256, 0, h->stream>>>(h->ray_cells, Bpad, maxlen, h->ray_count,
-                                                                            h->ray_start, h->meas, h->all_hit, h->sk_keys,
-                                                                            h->g));
+                                                                            h->ray_start, b.meas, b.hit, h->sk_keys, h->g));
     size_t tb = h->sk_temp_bytes;
     CK(cub::DeviceRadixSort::SortKeys(h->sk_temp, tb, h->sk_keys, h->sk_sorted, (int)n, 0, 32, h->stream));
     tb = h->sk_temp_bytes;
@@ -482,25 +544,56 @@ int launch_sorted_update(gms_handle* h, int Bpad) {
     return GMS_OK;
 }
 
-int launch_map_update(gms_handle* h, const float4* pose, int lo, int cnt, const int* slot, int B, int shared) {
+// shared map: integrate the scan from the strongest pose (Stats.strongest_pose, snapshotted by the normalise kernel)
+int launch_shared_update(gms_handle* h, const BeamSet& b, int B) {
     if (B <= 0) return GMS_OK;
     Phase ph(h, GMS_PHASE_MAP_UPDATE);
-    if (shared) {
-        const int Bpad = ((B + 31) / 32) * 32;
-        LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_walk<<<blocks_for(Bpad, 64), 64, 0, h->stream>>>(
-                                         pose, h->all_xy, B, Bpad, h->st, h->ray_cells, h->ray_cap, h->ray_count,
-                                         h->ray_start, h->ray_maxlen, h->rect, h->g));
-        if (h->cfg.update_mode == GMS_UPDATE_SORTED) return launch_sorted_update(h, Bpad);
-        LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_apply<<<148 * 4, 256, 0, h->stream>>>(
-                                         h->ray_cells, Bpad, h->ray_count, h->ray_maxlen, h->ray_start, h->meas,
-                                         h->all_hit, h->counts, h->dirty, h->g));
-        return GMS_OK;
+    const int Bpad = ((B + 31) / 32) * 32;
+    const bool sorted = h->cfg.update_mode == GMS_UPDATE_SORTED;
+    if (sorted) CK(cudaMemsetAsync(h->ray_maxlen, 0, 4, h->stream));
+    uint32_t* stale = h->alt_needs_clear ? h->dirty_alt : nullptr;
+    LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_integrate<<<Bpad / 32, 256, 0, h->stream>>>(
+                                     b.xy, B, Bpad, h->st, h->ray_cells, h->ray_cap, h->ray_count, h->ray_start,
+                                     h->ray_maxlen, h->rect, b.meas, b.hit, h->counts, h->dirty, stale,
+                                     stale ? h->g.tile_words : 0, sorted ? 1 : 0, h->g));
+    h->alt_needs_clear = false;
+    if (sorted) return launch_sorted_update(h, b, Bpad);
+    return GMS_OK;
+}
+
+// per-particle maps (or one explicit {pose, slot} pair): one thread per (particle, beam) ray
+int launch_map_update(gms_handle* h, const BeamSet& b, const float4* pose, int lo, int cnt, const int* slot, int B) {
+    if (B <= 0) return GMS_OK;
+    Phase ph(h, GMS_PHASE_MAP_UPDATE);
+    const long long total = (long long)cnt * B;
+    LAUNCH(GMS_PHASE_MAP_UPDATE, k_map_update<<<blocks_for(total, 128), 128, 0, h->stream>>>(
+                                     pose, lo, cnt, b.xy, b.meas, b.hit, B, h->counts, slot, h->rect, h->dirty, h->g));
+    return GMS_OK;
+}
+
+// A4 — GridMap.findBestPoseOptim GridMap.java:348-369 as a CPU hook between motion and scoring: the local
+// particles' poses go to the host, the callback may replace them, they come back.  Default: no hook (the
+// reference's optimiser returns its start pose), nothing of this runs.
+int run_pose_optimizer(gms_handle* h, const double* d_xy, const double* d_dist, const uint8_t* d_hit, int B,
+                       double d_center, double d_theta) {
+    if (!h->h_opt_poses) CK(cudaMallocHost((void**)&h->h_opt_poses, (size_t)h->cnt * 12));
+    float* tmp = (float*)h->d_tmp;
+    LAUNCH(GMS_PHASE_COUNT - 1, k_pose_unpack<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(h->pose[h->cur] + h->lo, tmp, h->cnt));
+    CK(cudaMemcpyAsync(h->h_opt_poses, tmp, (size_t)h->cnt * 12, cudaMemcpyDeviceToHost, h->stream));
+    // the hook sees host copies of the scan (the *_dev entry points hold it on the device)
+    std::vector<double> xy((size_t)2 * B), dist((size_t)B);
+    std::vector<uint8_t> hit((size_t)B);
+    if (B > 0) {
+        CK(cudaMemcpyAsync(xy.data(), d_xy, (size_t)B * 16, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(dist.data(), d_dist, (size_t)B * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(hit.data(), d_hit, (size_t)B, cudaMemcpyDeviceToHost, h->stream));
     }
-    const long long total = shared ? (long long)B : (long long)cnt * B;
-    LAUNCH(GMS_PHASE_MAP_UPDATE,
-           k_map_update<<<blocks_for(total, 128), 128, 0, h->stream>>>(pose, lo, cnt, h->all_xy, h->meas, h->all_hit,
-                                                                       B, h->counts, slot, h->rect, h->dirty, h->st,
-                                                                       shared, h->g));
+    CK(cudaStreamSynchronize(h->stream));
+    const int rc = h->opt_fn(h->opt_user, h, h->lo, h->cnt, h->h_opt_poses, xy.data(), dist.data(), hit.data(), B, d_center,
+                             d_theta);
+    if (rc != 0) return fail(h, GMS_ERR_STATE, "pose optimiser hook returned " + std::to_string(rc));
+    CK(cudaMemcpyAsync(tmp, h->h_opt_poses, (size_t)h->cnt * 12, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(GMS_PHASE_COUNT - 1, k_pose_pack<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(tmp, h->pose[h->cur] + h->lo, h->cnt));
     return GMS_OK;
 }
 
@@ -508,11 +601,13 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
                double d_theta, const double* d_normals) {
     const gms_config& c = h->cfg;
     h->stats_valid = false;
-    h->resample_partial = false;  // the exchange of this step overwrites every non-local particle anyway
+    h->resample_partial = false;  // this step overwrites every non-local particle of the gathered arrays anyway
     const bool shared = c.map_mode == GMS_MAP_SHARED;
-    const bool fork = shared && h->overlap;
+    const bool hook = h->opt_fn != nullptr;
+    const bool fork = shared && h->overlap && !hook;
     int rc = ensure_beams(h, B);  // grow the beam tables (if needed) while every stream can still be drained from here
     if (rc) return rc;
+    BeamSet& bs = cur_beams(h);
     if (fork) {  // likelihood refresh of the shared map: independent of the beams and of the motion update
         cudaStream_t main = h->stream;
         CK(cudaEventRecord(h->ev_fork_a, main));
@@ -531,79 +626,87 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
         CK(cudaStreamWaitEvent(h->stream, h->ev_done_b, 0));
         h->b_pending = false;
     }
-    if (fork) {  // the beam table is only needed by the scoring: build it next to the motion update
-        cudaStream_t main = h->stream;
-        CK(cudaStreamWaitEvent(h->side_c, h->ev_fork_a, 0));
-        h->stream = h->side_c;
-        rc = launch_pack(h, d_xy, d_dist, d_hit, B);
-        h->stream = main;
-        if (rc) return rc;
-        CK(cudaEventRecord(h->ev_done_c, h->side_c));
-    } else {
-        rc = launch_pack(h, d_xy, d_dist, d_hit, B);
-        if (rc) return rc;
-    }
+    // Odometry.recalculateStdDev Odometry.java:60-69
+    MotionArgs ma{};
+    ma.pose = h->pose[h->cur]; ma.lo = h->lo; ma.cnt = h->cnt; ma.normals = d_normals; ma.seed = c.seed; ma.step = h->step;
+    ma.d_center = d_center; ma.d_theta = d_theta;
+    ma.sd_c = (c.noise_center_base + std::fabs(d_center) * c.noise_center_gain) / 2;
+    ma.sd_t = c.noise_theta_base_deg * (M_PI / 180.0) + c.noise_theta_gain * std::fabs(d_theta);
+    const bool sorted = use_sorted_score(h);
+    bool packed = false;
     {
         Phase ph(h, GMS_PHASE_MOTION);
-        // Odometry.recalculateStdDev Odometry.java:60-69
-        const double sd_c = (c.noise_center_base + std::fabs(d_center) * c.noise_center_gain) / 2;
-        const double sd_t = c.noise_theta_base_deg * (M_PI / 180.0) + c.noise_theta_gain * std::fabs(d_theta);
-        const bool sorted = use_sorted_score(h);
-        LAUNCH(GMS_PHASE_MOTION, k_motion<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(
-                                     h->pose[h->cur], h->lo, h->cnt, d_normals, c.seed, h->step, d_center, d_theta,
-                                     sd_c, sd_t, sorted ? h->sort_hist : nullptr, h->sort_key, h->sort_rank));
-        if (sorted) {
-            LAUNCH(GMS_PHASE_MOTION, k_sort_scan<<<kSortCtas, 1024, 0, h->stream>>>(h->sort_hist, h->sort_offs, h->sort_cta));
-            LAUNCH(GMS_PHASE_MOTION, k_sort_scatter<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(
-                                         h->sort_offs, h->sort_cta, h->sort_key, h->sort_rank, h->cnt, h->order));
+        if (sorted) {  // motion + heading sort + beam packing: one cooperative launch
+            PackArgs pk{(const double2*)d_xy, d_dist, d_hit, B, h->g.res_f, bs.hit_xy, bs.meas, bs.xy, bs.hit, bs.num_hit};
+            int do_pack = hook ? 0 : 1;
+            const unsigned grid = std::min<unsigned>(blocks_for(h->cnt, 1024), (unsigned)h->num_sms);
+            LAUNCH_COOP(GMS_PHASE_MOTION, k_motion_sort, grid, 1024, 0, &ma, &h->sort, &pk, &do_pack);
+            packed = do_pack != 0;
+        } else {
+            LAUNCH(GMS_PHASE_MOTION, k_motion<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(ma));
         }
     }
-    if (fork) {
-        CK(cudaStreamWaitEvent(h->stream, h->ev_done_a, 0));
-        CK(cudaStreamWaitEvent(h->stream, h->ev_done_c, 0));
-    } else {
+    if (!fork) {  // computeLikelihoodMap precedes findBestPoseOptim and probabilityOf (SLAM.java:93-99)
         rc = launch_likelihood(h);
         if (rc) return rc;
     }
-    rc = launch_score(h, h->pose[h->cur], h->lo, h->cnt, shared ? nullptr : h->slot[h->slot_cur] + h->lo, h->lw[h->cur],
+    if (hook) {
+        rc = run_pose_optimizer(h, d_xy, d_dist, d_hit, B, d_center, d_theta);
+        if (rc) return rc;
+    }
+    if (!packed) {
+        rc = launch_pack(h, bs, d_xy, d_dist, d_hit, B);
+        if (rc) return rc;
+    }
+    if (fork) CK(cudaStreamWaitEvent(h->stream, h->ev_done_a, 0));
+    rc = launch_score(h, bs, h->pose[h->cur], h->lo, h->cnt, shared ? nullptr : h->slot[h->slot_cur] + h->lo, h->lw[h->cur],
                       (c.nranks > 1 && !h->direct) ? h->xlocal : nullptr, B, use_fac_score(h));
     if (rc) return rc;
-    if (c.nranks > 1 && h->direct) {  // this rank's {lw, pose} block -> every rank's receive buffer (NVLink stores)
-        XPush xp{};
-        xp.nranks = c.nranks;
-        for (int q = 0; q < xp.nranks; q++) xp.dst[q] = reinterpret_cast<unsigned char*>(h->peer_xg[h->xseq & 1][q]);
-        const unsigned grid = std::min<unsigned>(blocks_for((long long)c.nranks * h->cnt, 256), 148 * 8);
-        LAUNCH(GMS_PHASE_SCORE, k_xpush<<<grid, 256, 0, h->stream>>>(h->lw[h->cur], h->pose[h->cur], h->lo, h->cnt, h->P, xp));
-    }
 
     const bool skip = std::fabs(d_theta) > (M_PI / 180.0) * c.skip_update_deg;  // SLAM.java:82
     if (!shared && !skip) {
-        rc = launch_map_update(h, h->pose[h->cur], h->lo, h->cnt, h->slot[h->slot_cur] + h->lo, B, 0);
+        rc = launch_map_update(h, bs, h->pose[h->cur], h->lo, h->cnt, h->slot[h->slot_cur] + h->lo, B);
         if (rc) return rc;
     }
-    // Tell every rank that this rank's records of exchange xseq+1 have landed.  With per-particle maps the flag
-    // also certifies that this rank's maps are final for the step (peers may pull them when resampling), so it
-    // is raised after the map integration.
-    if (c.nranks > 1 && h->direct)
-        LAUNCH(GMS_PHASE_SCORE, k_xsignal<<<1, 32, 0, h->stream>>>(h->peer_flags, c.nranks, c.rank, h->xseq + 1));
+    if (c.nranks > 1 && h->direct) {
+        // this rank's log-weights -> every rank's receive buffer (NVLink stores), then one flag per receiver.  With
+        // per-particle maps the flag also certifies that this rank's maps are final for the step (peers may pull
+        // them when resampling), so the push is enqueued after the map integration.
+        Phase ph(h, GMS_PHASE_EXCHANGE);
+        XPush xp{};
+        xp.nranks = c.nranks;
+        for (int q = 0; q < xp.nranks; q++) {
+            xp.dst[q] = q == c.rank ? h->xlw[(h->xseq + 1) & 1] : h->peer_xlw[(h->xseq + 1) & 1][q];
+            xp.flag[q] = q == c.rank ? h->xflags : h->peer_flags[q];
+        }
+        const unsigned grid = std::min<unsigned>(blocks_for((long long)c.nranks * h->cnt, 256), (unsigned)h->num_sms * 4);
+        LAUNCH(GMS_PHASE_EXCHANGE, k_xpush_lw<<<grid, 256, 0, h->stream>>>(h->lw[h->cur], h->lo, h->cnt, xp, c.rank,
+                                                                          h->xseq + 1, h->xticket));
+    }
     h->pending = true;
     h->pend_dtheta = d_theta;
     h->pend_B = B;
     return GMS_OK;
 }
 
+SelectArgs select_args(gms_handle* h, int from, int to, double u01, unsigned long long count, int m_begin, int m_count) {
+    SelectArgs a{};
+    a.cdf = h->cdf; a.P = h->P; a.u01 = u01; a.seed = h->cfg.seed; a.resample_count = count;
+    a.parents = h->parents; a.st = h->st; a.poses_in = pose_table(h, from);
+    a.w_in = h->w[from]; a.lw_in = h->lw[from];
+    a.pose_out = h->pose[to]; a.w_out = h->w[to]; a.lw_out = h->lw[to];
+    a.m_begin = m_begin; a.m_count = m_count;
+    return a;
+}
+
 // children [m_begin, m_begin + m_count) of the resampling whose CDF is in h->cdf; in = buffers `from`, out = `to`
 int launch_select(gms_handle* h, int from, int to, double u01, unsigned long long count, int m_begin, int m_count) {
     if (m_count <= 0) return GMS_OK;
-    const int P = h->P;
+    const SelectArgs a = select_args(h, from, to, u01, count, m_begin, m_count);
     if (h->resample_mode == GMS_RESAMPLE_FIXED)
-        LAUNCH(GMS_PHASE_RESAMPLE, k_select<true><<<blocks_for(m_count, 256), 256, 0, h->stream>>>(
-                                       h->cdf, P, u01, h->cfg.seed, count, h->parents, h->st, h->pose[from], h->w[from],
-                                       h->lw[from], h->pose[to], h->w[to], h->lw[to], m_begin, m_count));
+        LAUNCH(GMS_PHASE_RESAMPLE, k_select<true><<<blocks_for(m_count, 256), 256, 0, h->stream>>>(a));
     else
-        LAUNCH(GMS_PHASE_RESAMPLE, k_select<false><<<blocks_for(m_count, 256), 256, 0, h->stream>>>(
-                                       h->cdf, P, u01, h->cfg.seed, count, h->parents, h->st, h->pose[from], h->w[from],
-                                       h->lw[from], h->pose[to], h->w[to], h->lw[to], m_begin, m_count));
+        LAUNCH(GMS_PHASE_RESAMPLE, k_select<false><<<blocks_for(m_count, 256), 256, 0, h->stream>>>(a));
     return GMS_OK;
 }
 
@@ -622,25 +725,23 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
     {
         Phase ph(h, GMS_PHASE_RESAMPLE);
         const int nxt = h->cur ^ 1;
+        const int m_begin = local_only ? h->lo : 0, m_count = local_only ? h->cnt : P;
         if (h->resample_mode == GMS_RESAMPLE_FIXED) {
-            if (!h->tile_fx_valid)  // tile sums of trunc(w * 2^60): by-product of k_normalise / k_neff
+            if (!h->tile_fx_valid)  // tile sums of trunc(w * 2^60): by-product of k_norm_coop / k_neff
                 LAUNCH(GMS_PHASE_RESAMPLE, k_neff<<<h->ntiles, 1024, 0, h->stream>>>(h->w[h->cur], P, h->ntiles, h->np, h->st));
-            LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_fixed<<<h->ntiles, 1024, 0, h->stream>>>(
-                                           h->w[h->cur], P, h->np.fx, (unsigned long long*)h->cdf, h->st));
+            SelectArgs a = select_args(h, h->cur, nxt, u01, h->resample_count, m_begin, m_count);
+            const unsigned long long* fx = h->np.fx;
+            int ntiles = h->ntiles;
+            const unsigned grid = (unsigned)std::max(1, std::min(h->num_sms, std::max(ntiles, (m_count + 1023) / 1024)));
+            LAUNCH_COOP(GMS_PHASE_RESAMPLE, k_resample_coop, grid, 1024, 0, &a, &fx, &ntiles);
         } else {
             LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_literal<<<1, 32, 0, h->stream>>>(h->w[h->cur], P, (double*)h->cdf, h->st));
+            int rc = launch_select(h, h->cur, nxt, u01, h->resample_count, m_begin, m_count);
+            if (rc) return rc;
         }
-        int rc;
-        if (local_only) {
-            rc = launch_select(h, h->cur, nxt, u01, h->resample_count, h->lo, h->cnt);
-            h->resample_partial = true;
-            h->partial_u01 = u01;
-            h->partial_count = h->resample_count;
-        } else {
-            rc = launch_select(h, h->cur, nxt, u01, h->resample_count, 0, P);
-            h->resample_partial = false;
-        }
-        if (rc) return rc;
+        h->resample_partial = local_only;
+        h->partial_u01 = u01;
+        h->partial_count = h->resample_count;
         h->cur = nxt;
         h->tile_fx_valid = false;
     }
@@ -688,29 +789,26 @@ int step_end(gms_handle* h, int policy, double u01) {
     if (!h->pending) return fail(h, GMS_ERR_STATE, "update_end without update_begin");
     const gms_config& c = h->cfg;
     h->stats_valid = false;
+    const double* lw_src = h->lw[h->cur];
+    const unsigned long long* xflags = nullptr;
     if (c.nranks > 1) {
-        if (h->direct) {  // pushed by the peers (k_xpush): wait for every sender's flag, then unpack
-            LAUNCH(GMS_PHASE_NORMALISE, k_xwait<<<1, 32, 0, h->stream>>>(h->xflags, c.nranks, h->xseq + 1, h->st));
-            LAUNCH(GMS_PHASE_NORMALISE, k_import_soa<<<blocks_for(h->P, 256), 256, 0, h->stream>>>(
-                                            reinterpret_cast<const unsigned char*>(h->xg2[h->xseq & 1]), h->P, h->lo,
-                                            h->cnt, h->lw[h->cur], h->pose[h->cur]));
+        if (h->direct) {  // pushed by the peers (k_xpush_lw): the normalise kernel waits for every sender's flag
             h->xseq++;
+            lw_src = h->xlw[h->xseq & 1];
+            xflags = h->xflags;
         } else {  // filled by the caller's all-gather
-            LAUNCH(GMS_PHASE_NORMALISE, k_import_exchange<<<blocks_for(h->P, 256), 256, 0, h->stream>>>(
-                                            h->xglobal, h->P, h->lw[h->cur], h->pose[h->cur]));
+            LAUNCH(GMS_PHASE_EXCHANGE, k_import_exchange<<<blocks_for(h->P, 256), 256, 0, h->stream>>>(
+                                           h->xglobal, h->P, h->lw[h->cur], h->pose[h->cur]));
         }
     }
     {
         Phase ph(h, GMS_PHASE_NORMALISE);
-        int nparts = h->score_parts;
-        h->score_parts = 0;
-        if (nparts == 0) {
-            nparts = h->ntiles;
-            LAUNCH(GMS_PHASE_NORMALISE, k_softmax_partials<<<h->ntiles, 1024, 0, h->stream>>>(h->lw[h->cur], h->P, h->np));
-        }
-        LAUNCH(GMS_PHASE_NORMALISE, k_normalise<<<h->ntiles, 1024, 0, h->stream>>>(
-                                        h->lw[h->cur], h->w[h->cur], h->pose[h->cur], h->P, h->ntiles, nparts, policy,
-                                        h->np, h->st));
+        NormArgs a{};
+        a.lw = lw_src; a.lw_store = lw_src == h->lw[h->cur] ? nullptr : h->lw[h->cur];
+        a.w = h->w[h->cur]; a.poses = pose_table(h, h->cur); a.P = h->P; a.ntiles = h->ntiles; a.policy = policy;
+        a.np = h->np; a.st = h->st; a.xflags = xflags; a.nranks = c.nranks; a.seq = h->xseq;
+        const unsigned grid = (unsigned)std::max(1, std::min(h->ntiles, h->num_sms));
+        LAUNCH_COOP(GMS_PHASE_NORMALISE, k_norm_coop, grid, 1024, 0, &a);
         h->tile_fx_valid = true;
     }
     const bool skip = std::fabs(h->pend_dtheta) > (M_PI / 180.0) * c.skip_update_deg;
@@ -725,7 +823,7 @@ int step_end(gms_handle* h, int policy, double u01) {
             CK(cudaStreamWaitEvent(h->side_b, h->ev_fork_b, 0));
             h->stream = h->side_b;
         }
-        int rc = launch_map_update(h, h->pose[h->cur], 0, 1, nullptr, h->pend_B, 1);
+        int rc = launch_shared_update(h, cur_beams(h), h->pend_B);
         h->stream = main;
         if (rc) return rc;
         if (forked) CK(cudaEventRecord(h->ev_done_b, h->side_b));
@@ -749,22 +847,29 @@ int slot_of(gms_handle* h, int particle, int* slot) {
     return GMS_OK;
 }
 
-int upload_beams(gms_handle* h, const double* xy, const double* dist, const uint8_t* hit, int B) {
+// host scan -> device beam set `b` through the pinned staging ring: one packed block, no stream synchronisation
+int upload_beams(gms_handle* h, BeamSet& b, const double* xy, const double* dist, const uint8_t* hit, int B,
+                 const double* normals = nullptr) {
     int rc = ensure_beams(h, B);
     if (rc) return rc;
-    if (B == 0) return GMS_OK;
-    const size_t need = (size_t)B * 25;
-    rc = ensure_stage(h, need + 64);
-    if (rc) return rc;
-    CK(cudaStreamSynchronize(h->stream));  // the staging buffer may still feed an earlier copy
-    unsigned char* s = h->h_stage;
-    std::memcpy(s, xy, (size_t)B * 16);
-    std::memcpy(s + (size_t)B * 16, dist ? (const void*)dist : (const void*)xy, (size_t)B * 8);
-    std::memcpy(s + (size_t)B * 24, hit, (size_t)B);
-    CK(cudaMemcpyAsync(h->all_xy, s, (size_t)B * 16, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->in_dist, s + (size_t)B * 16, (size_t)B * 8, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->all_hit, s + (size_t)B * 24, (size_t)B, cudaMemcpyHostToDevice, h->stream));
-    return GMS_OK;
+    if (B == 0 && !normals) return GMS_OK;
+    const size_t off_n = (((size_t)B * 25 + 63) / 64) * 64;
+    unsigned char* s = nullptr;
+    int slot = 0;
+    if ((rc = stage_acquire(h, off_n + (normals ? (size_t)h->cnt * 16 : 0) + 64, &s, &slot))) return rc;
+    if (B > 0) {
+        std::memcpy(s, xy, (size_t)B * 16);
+        std::memcpy(s + (size_t)B * 16, dist ? (const void*)dist : (const void*)xy, (size_t)B * 8);
+        std::memcpy(s + (size_t)B * 24, hit, (size_t)B);
+        CK(cudaMemcpyAsync(b.xy, s, (size_t)B * 16, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(b.dist, s + (size_t)B * 16, (size_t)B * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(b.hit, s + (size_t)B * 24, (size_t)B, cudaMemcpyHostToDevice, h->stream));
+    }
+    if (normals) {
+        std::memcpy(s + off_n, normals, (size_t)h->cnt * 16);
+        CK(cudaMemcpyAsync(h->d_normals, s + off_n, (size_t)h->cnt * 16, cudaMemcpyHostToDevice, h->stream));
+    }
+    return stage_release(h, slot);
 }
 
 int do_reset(gms_handle* h) {
@@ -784,10 +889,13 @@ int do_reset(gms_handle* h) {
                                     h->rect, h->S, make_int4(0x7fffffff, 0x7fffffff, -1, -1)));
     LAUNCH(GMS_PHASE_COUNT - 1, k_fill_dirty<<<blocks_for((long long)h->S * h->g.tile_words, 256), 256, 0, h->stream>>>(
                                     h->dirty, h->S, h->g.tile_words, h->tiles_per_map));
+    if (h->dirty_alt) CK(cudaMemsetAsync(h->dirty_alt, 0, (size_t)h->g.tile_words * 4, h->stream));
+    h->alt_needs_clear = false;
     CK(cudaMemsetAsync(h->st, 0, sizeof(Stats), h->stream));
     h->cur = 0; h->slot_cur = 0;
     h->step = 0; h->resample_count = 0;
     h->have_update = false; h->pending = false; h->stats_valid = false; h->tile_fx_valid = false;
+    h->resample_partial = false;
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }
@@ -862,6 +970,14 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
         delete h;
         return fail(nullptr, GMS_ERR_INVALID_ARG, "gms_create: kernel too wide or grid size out of range");
     }
+    // the shared-map ray kernels pack a cell as x | y << 16, the sorted update keys a cell as index << 2
+    if (cfg->map_mode == GMS_MAP_SHARED &&
+        (h->W > 65535 || h->H > 65535 ||
+         (cfg->update_mode == GMS_UPDATE_SORTED && (long long)h->W * h->H >= (1LL << 30)))) {
+        delete h;
+        return fail(nullptr, GMS_ERR_INVALID_ARG,
+                    "gms_create: a shared map is limited to 65535 cells per side (2^30 cells with GMS_UPDATE_SORTED)");
+    }
     Geometry& g = h->g;
     g.W = h->W; g.H = h->H;
     g.extra_steps = cfg->extra_steps;
@@ -916,13 +1032,17 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     h->stream = h->own_stream;
     CKC(cudaStreamCreateWithFlags(&h->side_a, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&h->side_b, cudaStreamNonBlocking));
-    CKC(cudaStreamCreateWithFlags(&h->side_c, cudaStreamNonBlocking));
-    CKC(cudaEventCreateWithFlags(&h->ev_done_c, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_fork_a, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_done_a, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_fork_b, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->ev_done_b, cudaEventDisableTiming));
     if (const char* e = std::getenv("GMS_NO_OVERLAP")) h->overlap = std::atoi(e) == 0;
+    if (const char* e = std::getenv("GMS_NO_COOP")) h->coop = std::atoi(e) == 0;
+    {
+        int coop_ok = 0;
+        CKC(cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, h->dev));
+        if (!coop_ok) return bail(fail(h, GMS_ERR_CUDA, "gms_create: the device does not support cooperative launches"));
+    }
     const size_t P = (size_t)h->P;
     for (int i = 0; i < 2; i++) {
         CKC(cudaMalloc((void**)&h->pose[i], P * sizeof(float4)));
@@ -941,6 +1061,11 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     }
     CKC(cudaMalloc((void**)&h->rect, (size_t)h->S * sizeof(int4)));
     CKC(cudaMalloc((void**)&h->dirty, (size_t)h->S * g.tile_words * 4));
+    if (cfg->map_mode == GMS_MAP_SHARED && g.tile_words <= kSelfListWords &&
+        !(std::getenv("GMS_SELF_LIST") && std::atoi(std::getenv("GMS_SELF_LIST")) == 0)) {
+        CKC(cudaMalloc((void**)&h->dirty_alt, (size_t)g.tile_words * 4));
+        h->self_list = true;
+    }
     CKC(cudaMalloc((void**)&h->word_off, (size_t)h->S * g.tile_words * 4));
     CKC(cudaMalloc((void**)&h->tile_list, (size_t)h->S * h->tiles_per_map * sizeof(int2)));
     CKC(cudaMalloc((void**)&h->dup_rect, P * sizeof(int4)));
@@ -953,10 +1078,12 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->xlocal, (size_t)h->cnt * sizeof(ExchangeRec)));
     CKC(cudaMalloc((void**)&h->xglobal, P * sizeof(ExchangeRec)));
     if (cfg->nranks > 1) {
-        CKC(cudaMalloc((void**)&h->xg2[0], P * sizeof(ExchangeRec)));
-        CKC(cudaMalloc((void**)&h->xg2[1], P * sizeof(ExchangeRec)));
+        CKC(cudaMalloc((void**)&h->xlw[0], P * 8));
+        CKC(cudaMalloc((void**)&h->xlw[1], P * 8));
         CKC(cudaMalloc((void**)&h->xflags, kMaxRanks * 8));
         CKC(cudaMemset(h->xflags, 0, kMaxRanks * 8));
+        CKC(cudaMalloc((void**)&h->xticket, 4));
+        CKC(cudaMemset(h->xticket, 0, 4));
     }
     h->d_tmp_bytes = std::max(h->cells * 8, P * 24);
     CKC(cudaMalloc(&h->d_tmp, h->d_tmp_bytes));
@@ -964,23 +1091,23 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->tmp_slot, sizeof(int)));
     CKC(cudaMalloc((void**)&h->tmp_lw, sizeof(double)));
     CKC(cudaMalloc((void**)&h->st, sizeof(Stats)));
-    CKC(cudaMalloc((void**)&h->sort_hist, (size_t)kSortBins * 4));
-    CKC(cudaMalloc((void**)&h->sort_cta, (size_t)kSortCtas * 4));
-    CKC(cudaMalloc((void**)&h->sort_offs, kSortBins * 4));
-    CKC(cudaMemset(h->sort_hist, 0, (size_t)kSortBins * 4));
-    CKC(cudaMalloc((void**)&h->sort_key, (size_t)h->cnt * 4));
-    CKC(cudaMalloc((void**)&h->sort_rank, (size_t)h->cnt * 4));
-    CKC(cudaMalloc((void**)&h->order, (size_t)h->cnt * 4));
+    CKC(cudaMalloc((void**)&h->sort.hist, (size_t)kSortBins * 4));
+    CKC(cudaMalloc((void**)&h->sort.chunk_total, (size_t)kSortChunks * 4));
+    CKC(cudaMalloc((void**)&h->sort.offs, kSortBins * 4));
+    CKC(cudaMemset(h->sort.hist, 0, (size_t)kSortBins * 4));
+    CKC(cudaMalloc((void**)&h->sort.key, (size_t)h->cnt * 4));
+    CKC(cudaMalloc((void**)&h->sort.rank, (size_t)h->cnt * 4));
+    CKC(cudaMalloc((void**)&h->sort.order, (size_t)h->cnt * 4));
     h->ntiles = (h->P + 1023) / 1024;
     if (const char* e = std::getenv("GMS_SCORE_V")) h->score_v = std::atoi(e) == 1 ? 1 : 0;
     if (const char* e = std::getenv("GMS_SCORE_G")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) h->score_g = v; }
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, h->dev) == cudaSuccess) h->num_sms = prop.multiProcessorCount; }
     {
         const size_t nt = (size_t)h->ntiles;
-        h->np_cap = std::max(h->ntiles, std::max(3200, (h->cnt + 127) / 128));  // score CTAs may outnumber the tiles
-        CKC(cudaMalloc((void**)&h->np.m, (size_t)h->np_cap * 8));
-        CKC(cudaMalloc((void**)&h->np.idx, (size_t)h->np_cap * 4));
-        CKC(cudaMalloc((void**)&h->np.s, (size_t)h->np_cap * 8));
+        const size_t np_cap = std::max<size_t>(nt, 1024);  // (m, idx): one entry per CTA of k_norm_coop; s: per tile
+        CKC(cudaMalloc((void**)&h->np.m, np_cap * 8));
+        CKC(cudaMalloc((void**)&h->np.idx, np_cap * 4));
+        CKC(cudaMalloc((void**)&h->np.s, np_cap * 8));
         CKC(cudaMalloc((void**)&h->np.ws, nt * 8));
         CKC(cudaMalloc((void**)&h->np.q, nt * 8));
         CKC(cudaMalloc((void**)&h->np.fx, nt * 8));
@@ -994,12 +1121,6 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     }
     CKC(cudaMallocHost((void**)&h->h_st, sizeof(Stats)));
     CKC(cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CKC(cudaFuncSetAttribute(k_score_sorted<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CKC(cudaFuncSetAttribute(k_score_sorted<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CKC(cudaFuncSetAttribute(k_score_sorted<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CKC(cudaFuncSetAttribute(k_score_sorted<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CKC(cudaFuncSetAttribute(k_score_sorted<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CKC(cudaFuncSetAttribute(k_score_sorted<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CKC(cudaFuncSetAttribute(k_likelihood<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CKC(cudaFuncSetAttribute(k_likelihood<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CKC(cudaFuncSetAttribute(k_likelihood_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -1024,8 +1145,6 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
         (void)cudaGetLastError();
     }
     int rc = ensure_beams(h, 1024);
-    if (rc) return bail(rc);
-    rc = ensure_stage(h, 1 << 20);
     if (rc) return bail(rc);
     rc = do_reset(h);
     if (rc) return bail(rc);
@@ -1065,18 +1184,10 @@ EXPORT int gms_update(gms_handle* h, const double* beam_xy, const double* beam_d
     if (int rc_ = check_beams(h, B, beam_xy, beam_dist, beam_hit, "gms_update")) return rc_;
     if (h->cfg.nranks != 1) return fail(h, GMS_ERR_STATE, "gms_update: multi-rank handles use update_begin/end");
     flip_beams(h);
-    // staging layout: [beams | pad to 64 | normals]; size it once so upload_beams never re-allocates
-    const size_t off = (((size_t)B * 25 + 63) / 64) * 64;
-    int rc = ensure_stage(h, off + (normals ? (size_t)h->cnt * 16 : 0) + 64);
+    BeamSet& bs = cur_beams(h);
+    int rc = upload_beams(h, bs, beam_xy, beam_dist, beam_hit, B, normals);
     if (rc) return rc;
-    if ((rc = upload_beams(h, beam_xy, beam_dist, beam_hit, B))) return rc;
-    const double* d_normals = nullptr;
-    if (normals) {
-        std::memcpy(h->h_stage + off, normals, (size_t)h->cnt * 16);
-        CK(cudaMemcpyAsync(h->d_normals, h->h_stage + off, (size_t)h->cnt * 16, cudaMemcpyHostToDevice, h->stream));
-        d_normals = h->d_normals;
-    }
-    rc = step_begin(h, (const double*)h->all_xy, h->in_dist, h->all_hit, B, d_center, d_theta, d_normals);
+    rc = step_begin(h, (const double*)bs.xy, bs.dist, bs.hit, B, d_center, d_theta, normals ? h->d_normals : nullptr);
     if (rc) return rc;
     rc = step_end(h, GMS_RESAMPLE_NEVER, 0.0);
     if (rc) return rc;
@@ -1123,6 +1234,7 @@ EXPORT int gms_get_weighted_pose(gms_handle* h, float pose[3]) {
 
 EXPORT int gms_get_strongest(gms_handle* h, int32_t* index, float pose[3], double* weight) {
     ENTER(h);
+    { int rc_ = complete_resample(h); if (rc_) return rc_; }  // the first child may belong to another rank's block
     int rc = fetch_stats(h);
     if (rc) return rc;
     if (!h->have_update) {  // SLAM.reset: strongestParticle = particles.get(0) (SLAM.java:75)
@@ -1131,7 +1243,9 @@ EXPORT int gms_get_strongest(gms_handle* h, int32_t* index, float pose[3], doubl
         if (weight) *weight = 1.0 / h->P;
         return GMS_OK;
     }
-    if (index) *index = h->h_st->strongest;
+    // Java keeps referencing the Particle object that was strongest at the last update; after a resampling that
+    // object lives on as its first child (its map slot is inherited), so that is the index reported here
+    if (index) *index = h->h_st->strongest_now;
     if (pose) std::memcpy(pose, h->h_st->strongest_pose, 3 * sizeof(float));
     if (weight) *weight = h->h_st->strongest_w;
     return GMS_OK;
@@ -1259,10 +1373,10 @@ EXPORT int gms_map_integrate_observation(gms_handle* h, int32_t particle, const 
     int s;
     int rc = slot_of(h, particle, &s);
     if (rc) return rc;
-    if ((rc = upload_beams(h, bxy, bdist, bhit, B))) return rc;
-    if ((rc = launch_pack(h, (const double*)h->all_xy, h->in_dist, h->all_hit, B))) return rc;
+    if ((rc = upload_beams(h, h->ops, bxy, bdist, bhit, B))) return rc;
+    if ((rc = launch_pack(h, h->ops, (const double*)h->ops.xy, h->ops.dist, h->ops.hit, B))) return rc;
     if ((rc = stage_pose_slot(h, pose, s))) return rc;
-    if ((rc = launch_map_update(h, h->tmp_pose, 0, 1, h->tmp_slot, B, 0))) return rc;
+    if ((rc = launch_map_update(h, h->ops, h->tmp_pose, 0, 1, h->tmp_slot, B))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }
@@ -1288,10 +1402,10 @@ EXPORT int gms_map_probability_of(gms_handle* h, int32_t particle, const float p
     int s;
     int rc = slot_of(h, particle, &s);
     if (rc) return rc;
-    if ((rc = upload_beams(h, bxy, nullptr, bhit, B))) return rc;
-    if ((rc = launch_pack(h, (const double*)h->all_xy, h->in_dist, h->all_hit, B))) return rc;
+    if ((rc = upload_beams(h, h->ops, bxy, nullptr, bhit, B))) return rc;
+    if ((rc = launch_pack(h, h->ops, (const double*)h->ops.xy, h->ops.dist, h->ops.hit, B))) return rc;
     if ((rc = stage_pose_slot(h, pose, s))) return rc;
-    if ((rc = launch_score(h, h->tmp_pose, 0, 1, h->tmp_slot, h->tmp_lw, nullptr, B))) return rc;
+    if ((rc = launch_score(h, h->ops, h->tmp_pose, 0, 1, h->tmp_slot, h->tmp_lw, nullptr, B))) return rc;
     double lw = 0;
     if ((rc = copy_out(h, &lw, h->tmp_lw, 8))) return rc;
     if (log_prob) *log_prob = lw;
@@ -1352,6 +1466,16 @@ EXPORT int gms_update_begin_dev(gms_handle* h, const double* d_xy, const double*
     if (int rc_ = check_beams(h, B, d_xy, d_dist, d_hit, "gms_update_begin_dev")) return rc_;
     flip_beams(h);
     return step_begin(h, d_xy, d_dist, d_hit, B, d_center, d_theta, d_normals);
+}
+EXPORT int gms_join_streams(gms_handle* h) {
+    ENTER(h);  // the main stream now waits for the map integration running on the side stream
+    return GMS_OK;
+}
+EXPORT int gms_set_pose_optimizer(gms_handle* h, gms_pose_optimizer_fn fn, void* user) {
+    ENTER(h);
+    h->opt_fn = fn;
+    h->opt_user = user;
+    return GMS_OK;
 }
 EXPORT int gms_update_end_dev(gms_handle* h, int32_t policy, double u01) {
     ENTER(h);
@@ -1431,7 +1555,8 @@ EXPORT int gms_ipc_export(gms_handle* h, void* handles) {
     if (h->cfg.nranks < 2) return fail(h, GMS_ERR_STATE, "gms_ipc_export: single-rank handle");
     static_assert(sizeof(cudaIpcMemHandle_t) == GMS_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
     cudaIpcMemHandle_t* out = static_cast<cudaIpcMemHandle_t*>(handles);
-    void* ptr[GMS_IPC_NUM_HANDLES] = {h->counts, h->lik, h->rect, h->dirty, h->xg2[0], h->xg2[1], h->xflags};
+    void* ptr[GMS_IPC_NUM_HANDLES] = {h->counts, h->lik, h->rect, h->dirty, h->xlw[0], h->xlw[1], h->xflags,
+                                      h->pose[0], h->pose[1]};
     for (int k = 0; k < GMS_IPC_NUM_HANDLES; k++) CK(cudaIpcGetMemHandle(&out[k], ptr[k]));
     return GMS_OK;
 }
@@ -1441,7 +1566,8 @@ EXPORT int gms_ipc_import(gms_handle* h, const void* all_handles) {
     if (h->cfg.nranks < 2) return fail(h, GMS_ERR_STATE, "gms_ipc_import: single-rank handle");
     const cudaIpcMemHandle_t* in = static_cast<const cudaIpcMemHandle_t*>(all_handles);
     for (int q = 0; q < h->cfg.nranks; q++) {
-        void* ptr[GMS_IPC_NUM_HANDLES] = {h->counts, h->lik, h->rect, h->dirty, h->xg2[0], h->xg2[1], h->xflags};
+        void* ptr[GMS_IPC_NUM_HANDLES] = {h->counts, h->lik, h->rect, h->dirty, h->xlw[0], h->xlw[1], h->xflags,
+                                          h->pose[0], h->pose[1]};
         if (q != h->cfg.rank)
             for (int k = 0; k < GMS_IPC_NUM_HANDLES; k++) {
                 if (h->ipc_opened[q][k]) { ptr[k] = h->ipc_opened[q][k]; continue; }
@@ -1452,9 +1578,11 @@ EXPORT int gms_ipc_import(gms_handle* h, const void* all_handles) {
         h->peers.lik[q] = static_cast<const double*>(ptr[1]);
         h->peers.rect[q] = static_cast<const int4*>(ptr[2]);
         h->peers.dirty[q] = static_cast<const uint32_t*>(ptr[3]);
-        h->peer_xg[0][q] = static_cast<ExchangeRec*>(ptr[4]);
-        h->peer_xg[1][q] = static_cast<ExchangeRec*>(ptr[5]);
-        h->peer_flags.flag[q] = static_cast<unsigned long long*>(ptr[6]);
+        h->peer_xlw[0][q] = static_cast<double*>(ptr[4]);
+        h->peer_xlw[1][q] = static_cast<double*>(ptr[5]);
+        h->peer_flags[q] = static_cast<unsigned long long*>(ptr[6]);
+        h->peer_pose[0][q] = static_cast<const float4*>(ptr[7]);
+        h->peer_pose[1][q] = static_cast<const float4*>(ptr[8]);
     }
     h->peers_ready = true;
     h->direct = true;
@@ -1464,23 +1592,30 @@ EXPORT int gms_ipc_import(gms_handle* h, const void* all_handles) {
 // ---- rows adjacent to the path ------------------------------------------------------
 namespace {
 // raw sweep -> device (raw_angle, raw_dist, all_hit) -> de-skewed beam table (all_xy, in_dist)
-int upload_raw_and_deskew(gms_handle* h, const double* angle, const double* dist, const uint8_t* hit, int B,
-                          double d_center, double d_theta) {
+int upload_raw_and_deskew(gms_handle* h, BeamSet& b, const double* angle, const double* dist, const uint8_t* hit, int B,
+                          double d_center, double d_theta, const double* normals = nullptr) {
     int rc = ensure_beams(h, B);
     if (rc) return rc;
-    if (B == 0) return GMS_OK;
-    if ((rc = ensure_stage(h, (size_t)B * 17 + 64))) return rc;
-    CK(cudaStreamSynchronize(h->stream));
-    unsigned char* s = h->h_stage;
-    std::memcpy(s, angle, (size_t)B * 8);
-    std::memcpy(s + (size_t)B * 8, dist, (size_t)B * 8);
-    if (hit) std::memcpy(s + (size_t)B * 16, hit, (size_t)B);
-    CK(cudaMemcpyAsync(h->raw_angle, s, (size_t)B * 8, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->raw_dist, s + (size_t)B * 8, (size_t)B * 8, cudaMemcpyHostToDevice, h->stream));
-    if (hit) CK(cudaMemcpyAsync(h->all_hit, s + (size_t)B * 16, (size_t)B, cudaMemcpyHostToDevice, h->stream));
-    LAUNCH(GMS_PHASE_COUNT - 1, k_deskew<<<blocks_for(B, 256), 256, 0, h->stream>>>(h->raw_angle, h->raw_dist, B, d_center,
-                                                                                   d_theta, h->all_xy, h->in_dist));
-    return GMS_OK;
+    if (B == 0 && !normals) return GMS_OK;
+    const size_t off_n = (((size_t)B * 17 + 63) / 64) * 64;
+    unsigned char* s = nullptr;
+    int slot = 0;
+    if ((rc = stage_acquire(h, off_n + (normals ? (size_t)h->cnt * 16 : 0) + 64, &s, &slot))) return rc;
+    if (B > 0) {
+        std::memcpy(s, angle, (size_t)B * 8);
+        std::memcpy(s + (size_t)B * 8, dist, (size_t)B * 8);
+        if (hit) std::memcpy(s + (size_t)B * 16, hit, (size_t)B);
+        CK(cudaMemcpyAsync(h->raw_angle, s, (size_t)B * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->raw_dist, s + (size_t)B * 8, (size_t)B * 8, cudaMemcpyHostToDevice, h->stream));
+        if (hit) CK(cudaMemcpyAsync(b.hit, s + (size_t)B * 16, (size_t)B, cudaMemcpyHostToDevice, h->stream));
+        LAUNCH(GMS_PHASE_COUNT - 1, k_deskew<<<blocks_for(B, 256), 256, 0, h->stream>>>(h->raw_angle, h->raw_dist, B, d_center,
+                                                                                       d_theta, b.xy, b.dist));
+    }
+    if (normals) {
+        std::memcpy(s + off_n, normals, (size_t)h->cnt * 16);
+        CK(cudaMemcpyAsync(h->d_normals, s + off_n, (size_t)h->cnt * 16, cudaMemcpyHostToDevice, h->stream));
+    }
+    return stage_release(h, slot);
 }
 }  // namespace
 
@@ -1488,10 +1623,10 @@ EXPORT int gms_deskew(gms_handle* h, const double* angle, const double* dist, in
                       double d_theta, double* out_xy, double* out_dist) {
     ENTER(h);
     if (B < 0 || (B > 0 && (!angle || !dist || !out_xy || !out_dist))) return fail(h, GMS_ERR_INVALID_ARG, "gms_deskew: bad arrays");
-    int rc = upload_raw_and_deskew(h, angle, dist, nullptr, B, d_center, d_theta);
+    int rc = upload_raw_and_deskew(h, h->ops, angle, dist, nullptr, B, d_center, d_theta);
     if (rc || B == 0) return rc;
-    CK(cudaMemcpyAsync(out_xy, h->all_xy, (size_t)B * 16, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(out_dist, h->in_dist, (size_t)B * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out_xy, h->ops.xy, (size_t)B * 16, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out_dist, h->ops.dist, (size_t)B * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }
@@ -1502,15 +1637,10 @@ EXPORT int gms_update_raw(gms_handle* h, const double* angle, const double* dist
     if (int rc_ = check_beams(h, B, angle, dist, hit, "gms_update_raw")) return rc_;
     if (h->cfg.nranks != 1) return fail(h, GMS_ERR_STATE, "gms_update_raw: multi-rank handles use update_begin/end");
     flip_beams(h);
-    int rc = upload_raw_and_deskew(h, angle, dist, hit, B, d_center, d_theta);
+    BeamSet& bs = cur_beams(h);
+    int rc = upload_raw_and_deskew(h, bs, angle, dist, hit, B, d_center, d_theta, normals);
     if (rc) return rc;
-    const double* d_normals = nullptr;
-    if (normals) {
-        CK(cudaMemcpyAsync(h->d_normals, normals, (size_t)h->cnt * 16, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaStreamSynchronize(h->stream));  // pageable source
-        d_normals = h->d_normals;
-    }
-    if ((rc = step_begin(h, (const double*)h->all_xy, h->in_dist, h->all_hit, B, d_center, d_theta, d_normals))) return rc;
+    if ((rc = step_begin(h, (const double*)bs.xy, bs.dist, bs.hit, B, d_center, d_theta, normals ? h->d_normals : nullptr))) return rc;
     if ((rc = step_end(h, GMS_RESAMPLE_NEVER, 0.0))) return rc;
     if ((rc = fetch_stats(h))) return rc;
     if (neff_out) *neff_out = h->h_st->neff;
@@ -1550,18 +1680,11 @@ EXPORT int gms_combined_map(gms_handle* h, double* log_out, double* lik_out) {
         LAUNCH(GMS_PHASE_LIKELIHOOD, k_fill_dirty<<<blocks_for(h->g.tile_words, 256), 256, 0, h->stream>>>(
                                          h->comb_dirty, 1, h->g.tile_words, h->tiles_per_map));
         LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_scan<<<1, 1024, 0, h->stream>>>(h->comb_dirty, h->g.tile_words, h->comb_off,
-                                                                           h->st, h->ray_maxlen));
+                                                                           h->st));
         LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_emit<<<blocks_for(h->g.tile_words, 256), 256, 0, h->stream>>>(
                                          h->comb_dirty, h->g.tile_words, h->g.tile_words, h->comb_off, h->comb_list));
-        const int k = h->g.khalf, th = kTileH + 2 * k, tw = (kTileW + 2 * k + 3) & ~3;
-        const size_t smem = (size_t)th * kTileW * 8 + (size_t)th * tw * 4;
-        const unsigned grid = (unsigned)std::min(h->tiles_per_map, 148 * 6);
-        if (k == 3)
-            LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<3><<<grid, 256, smem, h->stream>>>(h->comb_sign, h->comb_lik, nullptr,
-                                                                                          h->comb_list, h->st, h->g));
-        else
-            LAUNCH(GMS_PHASE_LIKELIHOOD, k_likelihood<0><<<grid, 256, smem, h->stream>>>(h->comb_sign, h->comb_lik, nullptr,
-                                                                                          h->comb_list, h->st, h->g));
+        int rc = launch_blur(h, h->comb_sign, h->comb_lik, nullptr, h->comb_list, SelfList{nullptr, 0}, h->tiles_per_map, false);
+        if (rc) return rc;
         CK(cudaMemcpyAsync(lik_out, h->comb_lik, h->cells * 8, cudaMemcpyDeviceToHost, h->stream));
     }
     h->stats_valid = false;

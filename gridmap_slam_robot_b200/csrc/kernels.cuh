@@ -8,10 +8,12 @@
 //   dirty  u32[S][tile_words]        bitmap of likelihood tiles whose thresholded codes changed
 #pragma once
 #include <cuda.h>  // CUtensorMap
+#include <cooperative_groups.h>
 #include <type_traits>
 #include "device_math.cuh"
 
 namespace gms {
+namespace cg = cooperative_groups;
 
 struct Stats {
     double neff;          // SLAM.calculateNeff of the last update
@@ -26,8 +28,11 @@ struct Stats {
     int num_hit;          // beams with wasHit (GridMap.java:269-270)
     int num_dup;          // map copies of the last resample
     int num_tiles;        // likelihood work-list length
-    int xerror;           // fused exchange: a peer's records did not arrive in time
-    int pad[2];
+    int xerror;           // peer exchange: a peer's log-weights did not arrive in time (every later kernel of the
+                          // step returns early, so no state is mutated from stale records)
+    int strongest_now;    // current index of the particle that was strongest at the last update: after a
+                          // resampling its first child (GridMapApp keeps drawing strongestParticle.m), -1 if none
+    int pad[1];
 };
 
 struct ExchangeRec {  // 24 B, gms.h "Exchange record"
@@ -57,76 +62,65 @@ struct PeerTable {  // per-particle maps across ranks: every rank's arenas, mapp
     const uint32_t* dirty[kMaxRanks];
 };
 
-// Peer exchange (multi-rank, replaces the NCCL all-gather): after scoring, k_xpush stores this rank's block of
-// {log-weight, pose} straight into EVERY rank's receive buffer (peer-mapped, NVLink) with coalesced 8/16-byte
-// stores; a flag per (receiver, sender) carries the step sequence number (k_xsignal / k_xwait).  Receive
-// buffer layout: f64 lw[P] followed by float4 pose[P].  (Pushing the 24-byte records from inside the scoring
-// kernel was tried first: fine on 2-4 GPUs, but 7 x 100k scattered 24-byte NVLink writes per rank doubled the
-// scoring time on 8.)
+// Peer exchange (multi-rank, replaces the NCCL all-gather).  Only the f64 log-weights travel: after scoring,
+// k_xpush_lw stores this rank's block of lw straight into EVERY rank's receive buffer (peer-mapped, NVLink) with
+// coalesced 8-byte stores — 8 B per particle and peer instead of the 24-byte {lw, pose} record — and the last
+// CTA to finish raises one flag per receiver carrying the exchange sequence number (st.release.sys after
+// __threadfence_system).  The consumer (k_norm_coop) polls the flags itself (ld.acquire.sys, bounded spin), so
+// no separate wait / import kernels run.  Poses are NOT exchanged: the resampling reads a remote parent's
+// 16-byte pose through the peer mapping of that rank's pose array (PoseTable) — one dependent NVLink read per
+// child whose parent lives elsewhere, and only for this rank's own children.
+// (History: pushing 24-byte records from inside the scoring kernel doubled the scoring time on 8 GPUs; pushing
+// whole {lw, pose} blocks + an import pass cost 19 MB of NVLink stores per rank and step at 8 x 100k.)
 struct XPush {
     int nranks;
-    unsigned char* dst[kMaxRanks];
+    double* dst[kMaxRanks];               // receive buffer (f64[P]) of every rank for this exchange parity
+    unsigned long long* flag[kMaxRanks];  // flag[q] = rank q's flag array (one u64 per sender)
 };
-__global__ void __launch_bounds__(256) k_xpush(const double* __restrict__ lw, const float4* __restrict__ pose, int lo,
-                                               int cnt, int P, XPush xp) {
+__global__ void __launch_bounds__(256) k_xpush_lw(const double* __restrict__ lw, int lo, int cnt, XPush xp,
+                                                  int myrank, unsigned long long seq,
+                                                  unsigned* __restrict__ ticket) {
+    __shared__ bool s_last;
     const long long total = (long long)xp.nranks * cnt;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
         const int q = (int)(e / cnt), i = lo + (int)(e - (long long)q * cnt);
-        double* dl = reinterpret_cast<double*>(xp.dst[q]);
-        float4* dp = reinterpret_cast<float4*>(dl + P);
-        dl[i] = lw[i];
-        dp[i] = pose[i];
+        xp.dst[q][i] = lw[i];
     }
+    __threadfence_system();  // this thread's stores are visible system-wide before anything it does next
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if (threadIdx.x == 0) *ticket = 0u;
+    if ((int)threadIdx.x < xp.nranks)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(xp.flag[threadIdx.x] + myrank), "l"(seq) : "memory");
 }
-__global__ void __launch_bounds__(256) k_import_soa(const unsigned char* __restrict__ xg, int P, int lo, int cnt,
-                                                    double* __restrict__ lw, float4* __restrict__ pose) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P || (i >= lo && i < lo + cnt)) return;  // the local block is already in place
-    const double* sl = reinterpret_cast<const double*>(xg);
-    const float4* sp = reinterpret_cast<const float4*>(sl + P);
-    lw[i] = sl[i];
-    pose[i] = sp[i];
-}
-struct XFlags {
-    unsigned long long* flag[kMaxRanks];  // flag[q] = rank q's flag array (one u64 per sender)
+// every rank's pose array of the current generation, indexable by GLOBAL particle index (single rank, or
+// records imported by an all-gather: every entry is the local array)
+struct PoseTable {
+    const float4* p[kMaxRanks];
+    int cnt;  // particles per rank
+    __device__ __forceinline__ float4 at(int i) const { return p[i / cnt][i]; }
 };
-__global__ void k_xsignal(XFlags f, int R, int myrank, unsigned long long seq) {
-    const int q = threadIdx.x;
-    if (q < R) {
-        __threadfence_system();  // the records written by the preceding kernel are visible before the flag
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.flag[q] + myrank), "l"(seq) : "memory");
-    }
-}
-__global__ void k_xwait(const unsigned long long* __restrict__ my_flags, int R, unsigned long long seq,
-                        Stats* __restrict__ st) {
-    const int q = threadIdx.x;
-    if (q >= R) return;
-    unsigned long long v = 0;
-    for (long long spins = 0; spins < 8000000; spins++) {  // ~4 s with the sleeps: never hang the device
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(my_flags + q) : "memory");
-        if (v >= seq) return;
-        __nanosleep(500);
-    }
-    st->xerror = 1;
-}
 
 // ------------------------------------------------------------------------------------------------
 // beam table: compaction of the hit beams (scoring reads only those, GridMap.java:269-270) and the
 // per-beam measured distance in cells, (float) m.distance / resolution (GridMap.java:188).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pack_beams(const double2* __restrict__ in_xy,
-                                                    const double* __restrict__ in_dist,
-                                                    const uint8_t* __restrict__ in_hit, int B, float res_f,
-                                                    double2* __restrict__ hit_xy, float* __restrict__ meas,
-                                                    double2* __restrict__ all_xy, uint8_t* __restrict__ all_hit,
-                                                    Stats* __restrict__ st) {
-    __shared__ int s_warp[8];
+// Executed by ONE whole CTA (any block size that is a multiple of 32, <= 1024).
+__device__ __forceinline__ void pack_beams_cta(const double2* __restrict__ in_xy, const double* __restrict__ in_dist,
+                                               const uint8_t* __restrict__ in_hit, int B, float res_f,
+                                               double2* __restrict__ hit_xy, float* __restrict__ meas,
+                                               double2* __restrict__ all_xy, uint8_t* __restrict__ all_hit,
+                                               int* __restrict__ num_hit) {
+    __shared__ int s_warp[32];
     __shared__ int s_base;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
     if (tid == 0) s_base = 0;
     __syncthreads();
-    for (int b0 = 0; b0 < B; b0 += 256) {
+    for (int b0 = 0; b0 < B; b0 += blockDim.x) {
         const int b = b0 + tid;
         const bool hit = b < B && in_hit[b] != 0;
         if (b < B) {
@@ -143,12 +137,20 @@ __global__ void __launch_bounds__(256) k_pack_beams(const double2* __restrict__ 
         __syncthreads();
         if (tid == 0) {
             int t = 0;
-            for (int k = 0; k < 8; k++) t += s_warp[k];
+            for (int k = 0; k < nw; k++) t += s_warp[k];
             s_base += t;
         }
         __syncthreads();
     }
-    if (tid == 0) st->num_hit = s_base;
+    if (tid == 0) *num_hit = s_base;
+}
+__global__ void __launch_bounds__(256) k_pack_beams(const double2* __restrict__ in_xy,
+                                                    const double* __restrict__ in_dist,
+                                                    const uint8_t* __restrict__ in_hit, int B, float res_f,
+                                                    double2* __restrict__ hit_xy, float* __restrict__ meas,
+                                                    double2* __restrict__ all_xy, uint8_t* __restrict__ all_hit,
+                                                    int* __restrict__ num_hit) {
+    pack_beams_cta(in_xy, in_dist, in_hit, B, res_f, hit_xy, meas, all_xy, all_hit, num_hit);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -159,94 +161,117 @@ __global__ void __launch_bounds__(256) k_pack_beams(const double2* __restrict__ 
 // Same-address atomics with a return value serialise at ~70 ns each (ncu: 8192 buckets made k_motion 23 us,
 // 65536 buckets 10 us), so the bucket count is chosen for low contention, not for ordering precision.
 constexpr int kSortBins = 65536;
-constexpr int kSortCtas = kSortBins / 1024;
+constexpr int kSortChunks = kSortBins / 1024;
 
-__global__ void __launch_bounds__(256) k_motion(float4* __restrict__ pose, int lo, int cnt,
-                                                const double* __restrict__ normals, uint64_t seed,
-                                                uint64_t step, double d_center, double d_theta, double sd_c,
-                                                double sd_t, unsigned* __restrict__ sort_hist,
-                                                unsigned* __restrict__ sort_key, unsigned* __restrict__ sort_rank) {
-    const int li = blockIdx.x * blockDim.x + threadIdx.x;
-    if (li >= cnt) return;
-    const int i = lo + li;
+struct MotionArgs {
+    float4* pose;
+    int lo, cnt;
+    const double* normals;
+    uint64_t seed, step;
+    double d_center, d_theta, sd_c, sd_t;
+};
+__device__ __forceinline__ float4 motion_one(const MotionArgs& a, int li) {
+    const int i = a.lo + li;
     double zd, zt;
-    if (normals) {
-        zd = normals[2 * li];
-        zt = normals[2 * li + 1];
+    if (a.normals) {
+        zd = a.normals[2 * li];
+        zt = a.normals[2 * li + 1];
     } else {
-        philox_normals(seed, (uint32_t)i, step, zd, zt);
+        philox_normals(a.seed, (uint32_t)i, a.step, zd, zt);
     }
-    const double d = sd_c * zd + d_center;   // NormalDistribution.sample(): sd * z + mean
-    const double th = sd_t * zt + d_theta;
-    float4 p = pose[i];
+    const double d = a.sd_c * zd + a.d_center;   // NormalDistribution.sample(): sd * z + mean
+    const double th = a.sd_t * zt + a.d_theta;
+    float4 p = a.pose[i];
     p.z = (float)angle_constrain((double)p.z + th);
     p.x = (float)((double)p.x + (double)cos_f(p.z) * d);
     p.y = (float)((double)p.y + (double)sin_f(p.z) * d);
-    pose[i] = p;
-    if (sort_hist) {
-        // processing order for k_score_sorted (not part of the arithmetic): bucket by heading; the rank
-        // inside a bucket is whatever order the atomics land in — any order gives the same weights
-        const unsigned b = min(__float2uint_rz((p.z + 3.14159274f) * (kSortBins / 6.28318548f)), (unsigned)kSortBins - 1u);
-        sort_key[li] = b;
-        sort_rank[li] = atomicAdd(sort_hist + b, 1u);
-    }
+    a.pose[i] = p;
+    return p;
+}
+__global__ void __launch_bounds__(256) k_motion(MotionArgs a) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li < a.cnt) motion_one(a, li);
 }
 
-// exclusive scan of the heading histogram: CTA c scans buckets [1024c, 1024c+1024) (coalesced) and publishes
-// its total; the scatter adds the totals of the CTAs before it.  Re-zeroes the histogram for the next step.
-__global__ void __launch_bounds__(1024) k_sort_scan(unsigned* __restrict__ hist, unsigned* __restrict__ offs,
-                                                    unsigned* __restrict__ cta_total) {
+// Motion + heading sort + beam packing in ONE cooperative launch (shared map, many particles).  The sort only
+// fixes a PROCESSING ORDER for k_score_sorted (which thread computes which particle): the rank inside a bucket
+// is whatever order the atomics land in, and nothing downstream depends on it — the scoring kernel performs
+// no reduction across particles, and every sum over particles (normalise, Neff, CDF) runs over fixed
+// 1024-particle tiles of the particle index, so results are run-to-run bit-identical.
+//   phase 1: motion update, bucket histogram (atomic with return = rank in bucket); last CTA packs the beams
+//   phase 2: exclusive scan of the histogram, 1024 buckets per chunk, chunks strided over the CTAs
+//   phase 3: scatter: order[chunk base + bucket offset + rank] = particle
+struct SortBufs {
+    unsigned *hist, *offs, *chunk_total, *key, *rank;
+    int* order;
+};
+struct PackArgs {
+    const double2* in_xy;
+    const double* in_dist;
+    const uint8_t* in_hit;
+    int B;
+    float res_f;
+    double2* hit_xy;
+    float* meas;
+    double2* all_xy;
+    uint8_t* all_hit;
+    int* num_hit;
+};
+__global__ void __launch_bounds__(1024) k_motion_sort(MotionArgs a, SortBufs sb, PackArgs pk, int do_pack) {
+    cg::grid_group grid = cg::this_grid();
     __shared__ unsigned s_w[32];
+    __shared__ unsigned s_base[kSortChunks];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int i = blockIdx.x * 1024 + tid;
-    const unsigned v = hist[i];
-    hist[i] = 0u;
-    unsigned inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += u;
+    const int stride = gridDim.x * blockDim.x;
+    for (int li = blockIdx.x * blockDim.x + tid; li < a.cnt; li += stride) {
+        const float4 p = motion_one(a, li);
+        const unsigned b = min(__float2uint_rz((p.z + 3.14159274f) * (kSortBins / 6.28318548f)), (unsigned)kSortBins - 1u);
+        sb.key[li] = b;
+        sb.rank[li] = atomicAdd(sb.hist + b, 1u);
     }
-    if (lane == 31) s_w[wid] = inc;
-    __syncthreads();
-    unsigned wv = s_w[lane];
+    if (do_pack && blockIdx.x == gridDim.x - 1)
+        pack_beams_cta(pk.in_xy, pk.in_dist, pk.in_hit, pk.B, pk.res_f, pk.hit_xy, pk.meas, pk.all_xy, pk.all_hit, pk.num_hit);
+    grid.sync();
+    for (int c = blockIdx.x; c < kSortChunks; c += gridDim.x) {
+        const int i = c * 1024 + tid;
+        const unsigned v = sb.hist[i];
+        sb.hist[i] = 0u;  // re-armed for the next step
+        unsigned inc = v;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned u = __shfl_up_sync(0xffffffffu, wv, o);
-        if (lane >= o) wv += u;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        __syncthreads();
+        if (lane == 31) s_w[wid] = inc;
+        __syncthreads();
+        unsigned wv = s_w[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, wv, o);
+            if (lane >= o) wv += u;
+        }
+        const unsigned wbase = wid > 0 ? __shfl_sync(0xffffffffu, wv, wid - 1) : 0u;
+        sb.offs[i] = wbase + inc - v;
+        if (tid == 1023) sb.chunk_total[c] = wbase + inc;
     }
-    const unsigned wbase = wid > 0 ? __shfl_sync(0xffffffffu, wv, wid - 1) : 0u;
-    offs[i] = wbase + inc - v;
-    if (tid == 1023) cta_total[blockIdx.x] = wbase + inc;
-}
-
-__global__ void __launch_bounds__(256) k_sort_scatter(const unsigned* __restrict__ offs,
-                                                      const unsigned* __restrict__ cta_total,
-                                                      const unsigned* __restrict__ key,
-                                                      const unsigned* __restrict__ rank, int cnt,
-                                                      int* __restrict__ order) {
-    __shared__ unsigned s_base[kSortCtas];
-    if (threadIdx.x < kSortCtas) {  // exclusive prefix of the 64 CTA totals (two warps, shuffle scan)
-        const int lane = threadIdx.x & 31;
-        const unsigned t = cta_total[threadIdx.x];
+    grid.sync();
+    if (tid < kSortChunks) {  // exclusive prefix of the 64 chunk totals (two warps, shuffle scan)
+        const unsigned t = sb.chunk_total[tid];
         unsigned inc = t;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += u;
         }
-        s_base[threadIdx.x] = inc - t;
+        s_base[tid] = inc - t;
     }
     __syncthreads();
-    if (threadIdx.x >= 32 && threadIdx.x < kSortCtas) {
-        unsigned first_half = s_base[31] + cta_total[31];
-        s_base[threadIdx.x] += first_half;
-    }
+    if (tid >= 32 && tid < kSortChunks) s_base[tid] += s_base[31] + sb.chunk_total[31];
     __syncthreads();
-    const int li = blockIdx.x * blockDim.x + threadIdx.x;
-    if (li < cnt) {
-        const unsigned k = key[li];
-        order[s_base[k >> 10] + offs[k] + rank[li]] = li;
+    for (int li = blockIdx.x * blockDim.x + tid; li < a.cnt; li += stride) {
+        const unsigned k = sb.key[li];
+        sb.order[s_base[k >> 10] + sb.offs[k] + sb.rank[li]] = li;
     }
 }
 
@@ -260,8 +285,7 @@ __global__ void __launch_bounds__(256) k_sort_scatter(const unsigned* __restrict
 // Work list: every set bit of the per-slot dirty-tile bitmaps becomes one {slot, tile} item.
 // k_lik_scan (one CTA): exclusive scan of the per-word popcounts.  k_lik_emit: expands and clears the words.
 __global__ void __launch_bounds__(1024) k_lik_scan(const uint32_t* __restrict__ dirty, int nwords,
-                                                   int* __restrict__ word_off, Stats* __restrict__ st,
-                                                   int* __restrict__ ray_maxlen) {
+                                                   int* __restrict__ word_off, Stats* __restrict__ st) {
     __shared__ int s_part[1024];
     const int tid = threadIdx.x;
     const int per = (nwords + 1023) / 1024;
@@ -281,10 +305,7 @@ __global__ void __launch_bounds__(1024) k_lik_scan(const uint32_t* __restrict__ 
         word_off[i] = run;
         run += __popc(dirty[i]);
     }
-    if (tid == 1023) {
-        st->num_tiles = s_part[1023];
-        *ray_maxlen = 0;  // consumed by the previous step's k_ray_apply; re-armed for this step's k_ray_walk
-    }
+    if (tid == 1023) st->num_tiles = s_part[1023];
 }
 __global__ void __launch_bounds__(256) k_lik_emit(uint32_t* __restrict__ dirty, int nwords, int tile_words,
                                                   const int* __restrict__ word_off, int2* __restrict__ list) {
@@ -300,6 +321,60 @@ __global__ void __launch_bounds__(256) k_lik_emit(uint32_t* __restrict__ dirty, 
         w &= w - 1;
         list[o++] = make_int2(slot, base + bit);
     }
+}
+
+// Shared map (one slot, <= kSelfListWords bitmap words): the blur kernels build the work list themselves —
+// every CTA scans the (tiny) dirty bitmap into a shared-memory prefix of popcounts and picks its tiles from
+// it, so the likelihood refresh is ONE launch on the critical path map update -> refresh -> scoring instead of
+// three.  The bitmap is double buffered by the host: nobody clears the buffer a refresh is reading.
+constexpr int kSelfListWords = 2048;
+struct SelfList {
+    const uint32_t* bitmap;  // nullptr: use the {slot, tile} list built by k_lik_scan / k_lik_emit
+    int nwords;
+};
+// all threads of the CTA; returns the number of dirty tiles, fills s_pref[0..nwords] (exclusive prefix)
+__device__ __forceinline__ int self_list_build(const SelfList& sl, int* s_pref) {
+    __shared__ int s_wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nthreads = blockDim.x;
+    int carry = 0;
+    for (int base = 0; base < sl.nwords; base += nthreads) {
+        const int i = base + tid;
+        const int v = i < sl.nwords ? __popc(sl.bitmap[i]) : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        __syncthreads();
+        if (lane == 31) s_wsum[wid] = inc;
+        __syncthreads();
+        int wv = lane < (nthreads >> 5) ? s_wsum[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, wv, o);
+            if (lane >= o) wv += u;
+        }
+        const int wbase = wid > 0 ? __shfl_sync(0xffffffffu, wv, wid - 1) : 0;
+        const int total = __shfl_sync(0xffffffffu, wv, 31);
+        if (i < sl.nwords) s_pref[i] = carry + wbase + inc - v;
+        carry += total;
+    }
+    __syncthreads();
+    if (tid == 0) s_pref[sl.nwords] = carry;
+    __syncthreads();
+    return carry;
+}
+// the t-th dirty tile (t < total): binary search over the prefix, then the n-th set bit of that word
+__device__ __forceinline__ int2 self_list_item(const SelfList& sl, const int* s_pref, int t) {
+    int lo = 0, hi = sl.nwords - 1;
+    while (lo < hi) {  // last word whose exclusive prefix is <= t
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_pref[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const uint32_t w = sl.bitmap[lo];
+    const int bit = __fns(w, 0, t - s_pref[lo] + 1);
+    return make_int2(0, lo * 32 + bit);
 }
 
 // Thresholded code {0, 1, 2} = {free, unknown, occupied}; the two cheap branches agree with cell_code().
@@ -319,21 +394,22 @@ template <int KH>
 __global__ void __launch_bounds__(256) k_likelihood(const CellCounts* __restrict__ counts,
                                                     double* __restrict__ lik, double* __restrict__ fac,
                                                     const int2* __restrict__ list, const Stats* __restrict__ st,
-                                                    Geometry g) {
+                                                    SelfList sl, Geometry g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_pref[kSelfListWords + 1];
     const int k = KH ? KH : g.khalf;
     const int tw = KH ? ((kTileW + 2 * KH + 3) & ~3) : kTileW + 2 * k;  // KH: rows padded to 16 bytes
     const int th = kTileH + 2 * k;
     double* s_h = reinterpret_cast<double*>(smem_raw);               // th * kTileW
     float* s_t = reinterpret_cast<float*>(s_h + th * kTileW);        // th * tw
     const int tid = threadIdx.x;
-    const int num_tiles = st->num_tiles;
+    const int num_tiles = sl.bitmap ? self_list_build(sl, s_pref) : st->num_tiles;
     const size_t cells = (size_t)g.W * g.H;
     double kr[2 * KH + 1];
 #pragma unroll
     for (int i = 0; i < 2 * KH + 1; i++) kr[i] = g.kernel[i];
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int2 item = list[t];
+        const int2 item = sl.bitmap ? self_list_item(sl, s_pref, t) : list[t];
         const int ox = (item.y % g.tiles_x) * kTileW, oy = (item.y / g.tiles_x) * kTileH;
         const CellCounts* cmap = counts + (size_t)item.x * cells;
         double* out = lik + (size_t)item.x * cells;
@@ -453,18 +529,20 @@ constexpr int kTmaTileW = kTileW + 8, kTmaTileH = kTileH + 6, kTmaPadX = 4;
 __global__ void __launch_bounds__(256) k_likelihood_tma(const __grid_constant__ CUtensorMap tmap,
                                                         double* __restrict__ lik, double* __restrict__ fac,
                                                         const int2* __restrict__ list, const Stats* __restrict__ st,
-                                                        Geometry g) {
+                                                        SelfList sl, Geometry g) {
     constexpr int KH = 3;
     constexpr int tw = (kTileW + 2 * KH + 3) & ~3, th = kTileH + 2 * KH;
     extern __shared__ __align__(128) unsigned char smem_tma[];
     __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ int s_pref[kSelfListWords + 1];
     constexpr int kRawBytes = (kTmaTileW * kTmaTileH * 8 + 127) & ~127;
     // two raw buffers: the TMA request of the NEXT tile is in flight while this tile is blurred
     double* s_h = reinterpret_cast<double*>(smem_tma + 2 * kRawBytes);  // th * kTileW
     float* s_t = reinterpret_cast<float*>(s_h + th * kTileW);           // th * tw
     const int tid = threadIdx.x;
-    const int num_tiles = st->num_tiles;
+    const int num_tiles = sl.bitmap ? self_list_build(sl, s_pref) : st->num_tiles;
     const size_t cells = (size_t)g.W * g.H;
+    auto item_of = [&](int t) -> int2 { return sl.bitmap ? self_list_item(sl, s_pref, t) : list[t]; };
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[1])));
@@ -475,7 +553,7 @@ __global__ void __launch_bounds__(256) k_likelihood_tma(const __grid_constant__ 
 #pragma unroll
     for (int i = 0; i < 2 * KH + 1; i++) kr[i] = g.kernel[i];
     auto fetch = [&](int t, int buf) {  // one elected thread: arm the barrier, issue the 3-D box load
-        const int2 item = list[t];
+        const int2 item = item_of(t);
         const int ox = (item.y % g.tiles_x) * kTileW, oy = (item.y / g.tiles_x) * kTileH;
         const uint32_t bar = smem_u32(&s_bar[buf]);
         const uint32_t bytes = kTmaTileW * kTmaTileH * 8;
@@ -491,7 +569,7 @@ __global__ void __launch_bounds__(256) k_likelihood_tma(const __grid_constant__ 
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, it++) {
         const int buf = it & 1;
-        const int2 item = list[t];
+        const int2 item = item_of(t);
         const int ox = (item.y % g.tiles_x) * kTileW, oy = (item.y / g.tiles_x) * kTileH;
         double* out = lik + (size_t)item.x * cells;
         if (tid == 0 && t + (int)gridDim.x < num_tiles) fetch(t + gridDim.x, buf ^ 1);
@@ -567,19 +645,29 @@ __global__ void __launch_bounds__(256) k_likelihood_tma(const __grid_constant__ 
 // A5 — GridMap.probabilityOf GridMap.java:261-294.  One warp per particle, hit beams across lanes.
 // The beam table is staged once per CTA with a 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) and
 // completion is signalled on an mbarrier; persistent CTAs then stride over particles.
-// Each lane multiplies its factors (<= ceil(B/32) of them, each in [0.01, 0.91]: no underflow), takes
-// one log, and the 32 logs are summed with a fixed xor-shuffle tree (deterministic).
+// Each lane multiplies its factors (<= ceil(B/32) of them, each in [0.01, 0.91]; the exponent is peeled off
+// every 64 factors so the product never underflows), takes one log, and the 32 logs are summed with a fixed
+// xor-shuffle tree (deterministic).
 // ------------------------------------------------------------------------------------------------
 
+// move the binary exponent of a positive normal double into `exp2`: exact (power-of-two scaling)
+__device__ __forceinline__ void peel_exponent(double& mant, int& exp2) {
+    const int hi = __double2hiint(mant);
+    const int e = ((hi >> 20) & 0x7ff) - 1023;
+    if (e == -1023) return;  // zero / subnormal (only reachable with z_hit == 1 configurations): ln() handles it
+    mant = __hiloint2double(hi - (e << 20), __double2loint(mant));
+    exp2 += e;
+}
+
 __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, int lo, int cnt,
-                                               const double2* __restrict__ hit_xy, const Stats* __restrict__ st,
+                                               const double2* __restrict__ hit_xy, const int* __restrict__ num_hit,
                                                const double* __restrict__ lik, const int* __restrict__ slot,
                                                double* __restrict__ lw, ExchangeRec* __restrict__ xlocal,
                                                Geometry g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
     double2* s_xy = reinterpret_cast<double2*>(smem_raw);
-    const int nh = st->num_hit;
+    const int nh = *num_hit;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t bar = smem_u32(&s_bar);
     if (nh > 0) {
@@ -614,7 +702,8 @@ __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, 
         const Xform t(p.x, p.y, p.z);
         const double* field = lik + (slot ? (size_t)slot[li] * cells : 0);
         double prod = 1.0;
-        for (int b0 = 0; b0 < nh; b0 += 128) {
+        int exp2 = 0, it = 0;
+        for (int b0 = 0; b0 < nh; b0 += 128, it++) {
             double f[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -632,8 +721,12 @@ __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, 
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) prod *= f[u];
+            // factors are in [0.01, 0.91]: 64 of them cannot underflow a normalised mantissa, more can (a lane
+            // takes up to GMS_MAX_BEAMS / 32 = 400) — peel the exponent off exactly every 16 rounds
+            if ((it & 15) == 15) peel_exponent(prod, exp2);
         }
-        const double l = warp_sum(log(prod));
+        peel_exponent(prod, exp2);
+        const double l = warp_sum(log(prod) + (double)exp2 * 0.6931471805599453);
         if (lane == 0) {
             lw[i] = l;
             if (xlocal) {
@@ -662,16 +755,13 @@ __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, 
 template <int G, int V = 0>
 __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__ pose, int lo, int cnt,
                                                       const double2* __restrict__ hit_xy,
-                                                      const Stats* __restrict__ st, const double* __restrict__ fac,
+                                                      const int* __restrict__ num_hit, const double* __restrict__ fac,
                                                       const int* __restrict__ order, double* __restrict__ lw,
-                                                      ExchangeRec* __restrict__ xlocal, NormPartials np,
-                                                      int emit_partials, Geometry g) {
+                                                      ExchangeRec* __restrict__ xlocal, Geometry g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ double s_red[4];
-    __shared__ int s_redi[4];
     double2* s_xy = reinterpret_cast<double2*>(smem_raw);
-    const int nh = st->num_hit;
+    const int nh = *num_hit;
     const int tid = threadIdx.x;
     const uint32_t bar = smem_u32(&s_bar);
     if (nh > 0) {
@@ -731,12 +821,7 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
         if ((unsigned)gx < uW && (unsigned)gy < uH) return __ldg(fac + ((unsigned)gy * uW + (unsigned)gx));
         return 1.0;
     };
-    auto peel = [&]() {  // move the exponent of mant into exp2: exact (power-of-two scaling)
-        const int hi = __double2hiint(mant);
-        const int e = ((hi >> 20) & 0x7ff) - 1023;
-        mant = __hiloint2double(hi - (e << 20), __double2loint(mant));
-        exp2 += e;
-    };
+    auto peel = [&]() { peel_exponent(mant, exp2); };
     int b0 = 0, it = 0;
     for (; b0 + 8 * G <= nhe; b0 += 8 * G, it++) {
         unsigned idx[8];
@@ -804,57 +889,24 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
             xlocal[li] = r;
         }
     }
-    if (!emit_partials) return;
-    // epilogue (single-rank shared map): this CTA's (max, first arg-max, sum exp(lw - max)) for k_normalise,
-    // which saves the separate pass over lw.  The combination in k_normalise is order-independent.
-    const int lane = tid & 31, wid = tid >> 5;
-    double best = writer ? l : kNegInf;
-    int bi = writer ? lo + li : 0x7fffffff;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    if (lane == 0) { s_red[wid] = best; s_redi[wid] = bi; }
-    __syncthreads();
-    best = s_red[0]; bi = s_redi[0];
-#pragma unroll
-    for (int k = 1; k < 4; k++)
-        if (k < (int)(blockDim.x >> 5) && (s_red[k] > best || (s_red[k] == best && s_redi[k] < bi))) { best = s_red[k]; bi = s_redi[k]; }
-    double e = writer ? exp(l - best) : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-    __syncthreads();
-    if (lane == 0) s_red[wid] = e;
-    __syncthreads();
-    if (tid == 0) {
-        double sum = 0.0;
-        for (int k = 0; k < (int)(blockDim.x >> 5); k++) sum += s_red[k];
-        np.m[blockIdx.x] = best;
-        np.idx[blockIdx.x] = bi;
-        np.s[blockIdx.x] = sum;
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
 // A8..A11 — GridMap.integrateObservation GridMap.java:173-191 + applyMeasurement :194-228.
-// One thread per (particle, beam) ray; per-particle maps, or the shared map from the strongest pose.
+// Per-particle maps: one thread per (particle, beam) ray.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_map_update(const float4* __restrict__ pose, int lo, int cnt,
                                                     const double2* __restrict__ all_xy,
                                                     const float* __restrict__ meas,
                                                     const uint8_t* __restrict__ hit, int B,
                                                     CellCounts* __restrict__ counts, const int* __restrict__ slot,
-                                                    int4* __restrict__ rect, uint32_t* __restrict__ dirty,
-                                                    const Stats* __restrict__ st, int shared, Geometry g) {
+                                                    int4* __restrict__ rect, uint32_t* __restrict__ dirty, Geometry g) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = shared ? (long long)B : (long long)cnt * B;
-    if (gid >= total) return;
-    const int li = shared ? 0 : (int)(gid / B);
+    if (gid >= (long long)cnt * B) return;
+    const int li = (int)(gid / B);
     const int b = (int)(gid - (long long)li * B);
-    const int s = shared ? 0 : slot[li];
-    const float4 p = pose[shared ? st->strongest : lo + li];
+    const int s = slot[li];
+    const float4 p = pose[lo + li];
     const Xform t(p.x, p.y, p.z);
     const float sx = (float)((t.tx(0.0, 0.0) - g.posx) / g.res);
     const float sy = (float)((t.ty(0.0, 0.0) - g.posy) / g.res);
@@ -873,76 +925,103 @@ __global__ void __launch_bounds__(128) k_map_update(const float4* __restrict__ p
     }
 }
 
-// Shared map (one scan per step, only B rays): the DDA of a ray is inherently sequential (f32 error
-// term, RayIterator.java:112-130), but the per-cell work (sqrt, inverse sensor model, counter update)
-// is not.  Pass 1 walks each ray once and records its cells {x | y << 16}; pass 2 classifies and
-// accumulates all cells of all rays in parallel.
-__global__ void __launch_bounds__(64) k_ray_walk(const float4* __restrict__ pose,
-                                                 const double2* __restrict__ all_xy, int B, int Bpad,
-                                                 const Stats* __restrict__ st, uint32_t* __restrict__ ray_cells,
-                                                 int cap, int* __restrict__ ray_count,
-                                                 float2* __restrict__ ray_start, int* __restrict__ ray_maxlen,
-                                                 int4* __restrict__ rect, Geometry g) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= Bpad) return;
-    if (b >= B) {
-        ray_count[b] = 0;
-        return;
-    }
-    // the strongest pose as k_normalise snapshotted it: this kernel may run on a side stream while the next
+// Shared map (one scan per step, only B rays): the DDA of a ray is inherently sequential (f32 error term,
+// RayIterator.java:112-130), but the per-cell work (sqrt, inverse sensor model, counter update) is not.
+// k_ray_integrate does both in ONE launch: a CTA owns 32 consecutive rays; warp 0 walks them in lockstep and
+// records the cells {x | y << 16} (cell k of ray b at ray_cells[k * Bpad + b]: one coalesced line per step),
+// then all 8 warps classify and accumulate the CTA's (cell, ray) pairs in parallel.
+// The walk loop keeps everything in registers (grid size, increments) and steps four cells per iteration:
+// the round-1 loop re-loaded W/H from the constant bank inside a predicate chain and took ~130 cycles per
+// cell (24 us for 720 rays); this one is bounded by the f32 add -> compare dependency of the error term.
+// `walk_only` (GMS_UPDATE_SORTED) stops after the walk: k_ray_keys + sort + k_apply_runs take over.
+__global__ void __launch_bounds__(256) k_ray_integrate(const double2* __restrict__ all_xy, int B, int Bpad,
+                                                       const Stats* __restrict__ st,
+                                                       uint32_t* __restrict__ ray_cells, int cap,
+                                                       int* __restrict__ ray_count, float2* __restrict__ ray_start,
+                                                       int* __restrict__ ray_maxlen, int4* __restrict__ rect,
+                                                       const float* __restrict__ meas,
+                                                       const uint8_t* __restrict__ hit,
+                                                       CellCounts* __restrict__ counts, uint32_t* __restrict__ dirty,
+                                                       uint32_t* __restrict__ stale_bitmap, int stale_words,
+                                                       int walk_only, Geometry g) {
+    __shared__ int s_len[32];
+    __shared__ int s_max;
+    const int tid = threadIdx.x;
+    // the dirty-tile buffer the refresh of THIS step consumed (host double buffering) is re-armed here: this
+    // kernel is ordered after that refresh and before the next writer of the buffer
+    for (int i = blockIdx.x * blockDim.x + tid; i < stale_words; i += gridDim.x * blockDim.x) stale_bitmap[i] = 0u;
+    if (st->xerror) return;
+    // the strongest pose as k_norm_coop snapshotted it: this kernel may run on a side stream while the next
     // step's motion update already rewrites the pose array
-    (void)pose;
     const float4 p = make_float4(st->strongest_pose[0], st->strongest_pose[1], st->strongest_pose[2], 0.f);
     const Xform t(p.x, p.y, p.z);
     const float sx = (float)((t.tx(0.0, 0.0) - g.posx) / g.res);
     const float sy = (float)((t.ty(0.0, 0.0) - g.posy) / g.res);
-    const double2 m = all_xy[b];
-    const float ex = (float)((t.tx(m.x, m.y) - g.posx) / g.res);
-    const float ey = (float)((t.ty(m.x, m.y) - g.posy) / g.res);
-    if (b == 0) *ray_start = make_float2(sx, sy);
-    RayIter it;
-    it.init(sx + 0.5f, sy + 0.5f, ex + 0.5f, ey + 0.5f, g.extra_steps);
-    // cell k of ray b lives at ray_cells[k * Bpad + b]: lanes (consecutive rays) advance in lockstep, so
-    // every store of the walk and every load of k_ray_apply is one coalesced line
-    uint32_t* out = ray_cells + b;
-    int c = 0;
-    const int fx = it.x, fy = it.y;
-    int lx = it.x, ly = it.y;
-    while (it.has_next(g.W, g.H) && c < cap) {
-        lx = it.x; ly = it.y;
-        out[(size_t)c * Bpad] = (uint32_t)lx | ((uint32_t)ly << 16);
-        c++;
-        it.advance();
+    const int b0 = blockIdx.x * 32;
+    if (tid < 32) {
+        const int b = b0 + tid;
+        int c = 0;
+        if (b < B) {
+            const double2 m = all_xy[b];
+            const float ex = (float)((t.tx(m.x, m.y) - g.posx) / g.res);
+            const float ey = (float)((t.ty(m.x, m.y) - g.posy) / g.res);
+            if (b == 0) *ray_start = make_float2(sx, sy);
+            RayIter it;
+            it.init(sx + 0.5f, sy + 0.5f, ex + 0.5f, ey + 0.5f, g.extra_steps);
+            const unsigned uW = (unsigned)g.W, uH = (unsigned)g.H;
+            int x = it.x, y = it.y, n = min(it.n, cap);
+            const int xi = it.x_inc, yi = it.y_inc;
+            const float dx = it.dx, dy = it.dy;
+            float err = it.error;
+            const int fx = x, fy = y;
+            int lx = x, ly = y;
+            uint32_t* out = ray_cells + b;
+            bool live = n > 0;
+            while (live) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    live = live && n > 0 && (unsigned)x < uW && (unsigned)y < uH;  // RayIterator.hasNext
+                    if (live) {
+                        out[(size_t)c * Bpad] = (uint32_t)x | ((uint32_t)y << 16);
+                        lx = x; ly = y;
+                        c++;
+                        const bool up = err > 0.0f;  // RayIterator.next
+                        y += up ? yi : 0;
+                        x += up ? 0 : xi;
+                        err += up ? -dx : dy;
+                        n--;
+                    }
+                }
+            }
+            if (c > 0) {
+                int* r = reinterpret_cast<int*>(rect);
+                atomicMin(r + 0, min(fx, lx));
+                atomicMin(r + 1, min(fy, ly));
+                atomicMax(r + 2, max(fx, lx));
+                atomicMax(r + 3, max(fy, ly));
+            }
+        }
+        if (b < Bpad) ray_count[b] = c;
+        s_len[tid] = c;
+        int mx = c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (tid == 0) {
+            s_max = mx;
+            if (mx > 0) atomicMax(ray_maxlen, mx);
+        }
     }
-    ray_count[b] = c;
-    if (c > 0) {
-        atomicMax(ray_maxlen, c);
-        int* r = reinterpret_cast<int*>(rect);
-        atomicMin(r + 0, min(fx, lx));
-        atomicMin(r + 1, min(fy, ly));
-        atomicMax(r + 2, max(fx, lx));
-        atomicMax(r + 3, max(fy, ly));
-    }
-}
-
-// persistent grid-stride over the (cell k, ray b) pairs (ray_maxlen is re-zeroed by the next k_lik_scan)
-__global__ void __launch_bounds__(256) k_ray_apply(const uint32_t* __restrict__ ray_cells, int Bpad,
-                                                   const int* __restrict__ ray_count, int* __restrict__ ray_maxlen,
-                                                   const float2* __restrict__ ray_start,
-                                                   const float* __restrict__ meas, const uint8_t* __restrict__ hit,
-                                                   CellCounts* __restrict__ counts, uint32_t* __restrict__ dirty,
-                                                   Geometry g) {
-    const int maxlen = *ray_maxlen;
-    const long long total = (long long)maxlen * Bpad;
-    const float2 s = *ray_start;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(e / Bpad), b = (int)(e - (long long)k * Bpad);
-        if (k >= ray_count[b]) continue;
-        const uint32_t cell = ray_cells[e];
+    __syncthreads();  // also orders warp 0's global stores before the other warps' loads (same CTA)
+    if (walk_only) return;
+    const int total = s_max * 32;
+    for (int e = tid; e < total; e += 256) {
+        const int k = e >> 5, j = e & 31;
+        if (k >= s_len[j]) continue;
+        const int b = b0 + j;
+        const uint32_t cell = ray_cells[(size_t)k * Bpad + b];
         const int cx = (int)(cell & 0xffffu), cy = (int)(cell >> 16);
-        const float dX = s.x - ((float)cx + 0.5f);
-        const float dY = s.y - ((float)cy + 0.5f);
+        const float dX = sx - ((float)cx + 0.5f);
+        const float dY = sy - ((float)cy + 0.5f);
         const float dist = __fsqrt_rn(dX * dX + dY * dY);
         const int cls = inverse_sensor_class(dist, meas[b], hit[b] != 0, g.tol_half);
         if (cls != 0) bump_cell(counts, dirty, cx, cy, cls, g);
@@ -1065,86 +1144,122 @@ __device__ __forceinline__ void block_argmax_1024(double& best, int& bi, double*
     }
 }
 
-// pass 1: per-tile (max, first arg-max, sum exp(lw - tile max))
-__global__ void __launch_bounds__(1024) k_softmax_partials(const double* __restrict__ lw, int P, NormPartials np) {
-    __shared__ double s_key[32];
-    __shared__ int s_idx[32];
-    __shared__ double s_d[32];
-    const int i = blockIdx.x * 1024 + threadIdx.x;
-    const double v = i < P ? lw[i] : kNegInf;
-    double best = v;
-    int bi = i < P ? i : 0x7fffffff;
-    block_argmax_1024(best, bi, s_key, s_idx);
-    const double e = i < P ? exp(v - best) : 0.0;
-    const double sum = block_reduce_1024(e, SumOp(), s_d);
-    if (threadIdx.x == 0) {
-        np.m[blockIdx.x] = best;
-        np.idx[blockIdx.x] = bi;
-        np.s[blockIdx.x] = sum;
-    }
-}
-
-// pass 2: every CTA combines the tile partials in the same fixed order -> (M, first arg-max, S); then
-// w_i = exp(lw_i - M) / S for its tile, tile sums; the last CTA to finish folds the tile sums (fixed
-// order) into Neff (SLAM.java:180-190: 1 / sum (w / sum w)^2, evaluated as (sum w)^2 / sum w^2) and
-// publishes the step's statistics.
-__global__ void __launch_bounds__(1024) k_normalise(const double* __restrict__ lw, double* __restrict__ w,
-                                                    const float4* __restrict__ pose, int P, int ntiles, int nparts,
-                                                    int policy, NormPartials np, Stats* __restrict__ st) {
+// Normalise + Neff + strongest in ONE cooperative launch (grid <= one CTA per SM, grid-wide barriers).
+// Every sum over particles runs over FIXED tiles of 1024 consecutive particle indices, each reduced by a fixed
+// shuffle tree, and the tile results are combined in tile order: the results do not depend on the grid
+// size, on which CTA handled a tile, on the scoring kernel's processing order, or on how many ranks share the
+// particle set (run-to-run, rank-to-rank bit-identical).
+//   phase 0  (multi-rank peer exchange) wait until every rank's log-weights of exchange `seq` have landed
+//   phase 1  M = max lw, first arg-max (SLAM.java:110-115 keeps the first maximum: strict >)
+//   phase 2  e_i = exp(lw_i - M), tile sums s_t                      -> S = sum_t s_t
+//   phase 3  w_i = e_i / S (SLAM.java:119-121), tile sums of w, w^2, trunc(w * 2^60)
+//   final    Neff = (sum w)^2 / sum w^2 (SLAM.java:180-190), strongest pose snapshot, resample decision
+struct NormArgs {
+    const double* lw;    // all P log-weights (own array, or the peer-exchange receive buffer)
+    double* lw_store;    // peer exchange: the received values are also filed in the handle's own lw array (else null)
+    double* w;
+    PoseTable poses;
+    int P, ntiles, policy;
+    NormPartials np;
+    Stats* st;
+    const unsigned long long* xflags;  // nullptr unless the peer exchange is active
+    int nranks;
+    unsigned long long seq;
+};
+__global__ void __launch_bounds__(1024) k_norm_coop(NormArgs a) {
+    cg::grid_group grid = cg::this_grid();
     __shared__ double s_key[32];
     __shared__ int s_idx[32];
     __shared__ double s_d[32];
     __shared__ unsigned long long s_u[32];
-    __shared__ bool s_last;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, G = gridDim.x;
+    if (a.xflags) {
+        if (blockIdx.x == 0 && tid < a.nranks) {
+            unsigned long long v = 0;
+            long long spins = 0;
+            for (; spins < 8000000; spins++) {  // ~4 s with the sleeps: never hang the device
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.xflags + tid) : "memory");
+                if (v >= a.seq) break;
+                __nanosleep(500);
+            }
+            if (v < a.seq) a.st->xerror = 1;
+        }
+        __threadfence();
+        grid.sync();
+        // the flag acquire of CTA 0 + the grid barrier order every CTA's loads after the peers' stores
+        if (*(volatile int*)&a.st->xerror) return;
+    }
+    // phase 1
     double best = kNegInf;
     int bi = 0x7fffffff;
-    for (int c = tid; c < nparts; c += 1024) {
-        const double v = np.m[c];
-        const int vi = np.idx[c];
+    for (int t = blockIdx.x; t < a.ntiles; t += G) {
+        const int i = t * 1024 + tid;
+        if (i < a.P) {
+            const double v = __ldcg(a.lw + i);
+            if (v > best) { best = v; bi = i; }  // tiles ascend: a later equal value never replaces
+        }
+    }
+    block_argmax_1024(best, bi, s_key, s_idx);
+    if (tid == 0) { a.np.m[blockIdx.x] = best; a.np.idx[blockIdx.x] = bi; }
+    grid.sync();
+    best = kNegInf; bi = 0x7fffffff;
+    for (int c = tid; c < G; c += 1024) {
+        const double v = __ldcg(a.np.m + c);
+        const int vi = __ldcg(a.np.idx + c);
         if (v > best || (v == best && vi < bi)) { best = v; bi = vi; }
     }
     block_argmax_1024(best, bi, s_key, s_idx);
+    // phase 2
+    for (int t = blockIdx.x; t < a.ntiles; t += G) {
+        const int i = t * 1024 + tid;
+        double e = 0.0;
+        if (i < a.P) {
+            const double v = __ldcg(a.lw + i);
+            if (a.lw_store) a.lw_store[i] = v;
+            e = exp(v - best);
+            a.w[i] = e;
+        }
+        const double sum = block_reduce_1024(e, SumOp(), s_d);
+        if (tid == 0) a.np.s[t] = sum;
+    }
+    grid.sync();
     double acc = 0.0;
-    for (int c = tid; c < nparts; c += 1024) acc += np.s[c] * exp(np.m[c] - best);
+    for (int c = tid; c < a.ntiles; c += 1024) acc += __ldcg(a.np.s + c);
     const double S = block_reduce_1024(acc, SumOp(), s_d);
-    const int i = blockIdx.x * 1024 + tid;
-    double wi = 0.0;
-    if (i < P) {
-        wi = exp(lw[i] - best) / S;
-        w[i] = wi;
+    // phase 3
+    for (int t = blockIdx.x; t < a.ntiles; t += G) {
+        const int i = t * 1024 + tid;
+        double wi = 0.0;
+        if (i < a.P) {
+            wi = a.w[i] / S;
+            a.w[i] = wi;
+        }
+        const double ws = block_reduce_1024(wi, SumOp(), s_d);
+        const double q = block_reduce_1024(wi * wi, SumOp(), s_d);
+        const unsigned long long fx = block_reduce_1024((unsigned long long)(wi * 0x1p60), SumU64(), s_u);
+        if (tid == 0) { a.np.ws[t] = ws; a.np.q[t] = q; a.np.fx[t] = fx; }
     }
-    const double ws = block_reduce_1024(wi, SumOp(), s_d);
-    const double q = block_reduce_1024(wi * wi, SumOp(), s_d);
-    const unsigned long long fx = block_reduce_1024((unsigned long long)(wi * 0x1p60), SumU64(), s_u);
+    grid.sync();
+    if (blockIdx.x != 0) return;
+    double sa = 0.0, sq = 0.0;
+    for (int c = tid; c < a.ntiles; c += 1024) {
+        sa += __ldcg(a.np.ws + c);
+        sq += __ldcg(a.np.q + c);
+    }
+    sa = block_reduce_1024(sa, SumOp(), s_d);
+    sq = block_reduce_1024(sq, SumOp(), s_d);
     if (tid == 0) {
-        np.ws[blockIdx.x] = ws;
-        np.q[blockIdx.x] = q;
-        np.fx[blockIdx.x] = fx;
-        __threadfence();
-        s_last = atomicAdd(np.counter, 1u) == (unsigned)ntiles - 1u;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    double a = 0.0, b = 0.0;
-    for (int c = tid; c < ntiles; c += 1024) {
-        a += __ldcg(np.ws + c);
-        b += __ldcg(np.q + c);
-    }
-    a = block_reduce_1024(a, SumOp(), s_d);
-    b = block_reduce_1024(b, SumOp(), s_d);
-    if (tid == 0) {
-        const double neff = (a * a) / b;
+        Stats* st = a.st;
+        const double neff = (sa * sa) / sq;
         st->neff = neff;
         st->lw_max = best;
         st->sum_exp = S;
         st->strongest = bi;
+        st->strongest_now = bi;
         st->strongest_w = 1.0 / S;
-        const float4 p = pose[bi];
+        const float4 p = a.poses.at(bi);
         st->strongest_pose[0] = p.x; st->strongest_pose[1] = p.y; st->strongest_pose[2] = p.z;
-        st->do_resample = policy == 2 || (policy == 1 && neff < (double)(P / 2));  // GridMapApp.java:185
-        *np.counter = 0u;
+        st->do_resample = a.policy == 2 || (a.policy == 1 && neff < (double)(a.P / 2));  // GridMapApp.java:185
     }
 }
 
@@ -1248,9 +1363,10 @@ __global__ void __launch_bounds__(256) k_import_exchange(const ExchangeRec* __re
 // LITERAL CDF: Java's sequential f64 running sum, c_i = c_{i-1} + w_i in particle order.  One warp:
 // coalesced 32-wide loads, the dependent add chain is replayed through shuffles.
 __global__ void __launch_bounds__(32) k_cdf_literal(const double* __restrict__ w, int P, double* __restrict__ cdf,
-                                                    const Stats* __restrict__ st) {
-    if (!st->do_resample) return;
+                                                    Stats* __restrict__ st) {
+    if (!st->do_resample || st->xerror) return;
     const int lane = threadIdx.x;
+    if (lane == 0) st->strongest_now = -1;
     double c = 0.0;  // 0.0 + w[0] == w[0]: same as Java's c = particles.get(0).weight (SLAM.java:137)
     for (int base = 0; base < P; base += 32) {
         const double v = base + lane < P ? w[base + lane] : 0.0;
@@ -1265,77 +1381,45 @@ __global__ void __launch_bounds__(32) k_cdf_literal(const double* __restrict__ w
     }
 }
 
-// FIXED CDF: u64 fixed point trunc(w * 2^60); integer addition is associative, so a parallel scan equals
-// the sequential walk bit for bit on any number of threads / CTAs / ranks.  Tile c (1024 particles) adds
-// the fixed-point tile sums of tiles < c (produced by k_normalise / k_neff) to a block-wide scan.
-__global__ void __launch_bounds__(1024) k_cdf_fixed(const double* __restrict__ w, int P,
-                                                    const unsigned long long* __restrict__ tile_fx,
-                                                    unsigned long long* __restrict__ cdf,
-                                                    const Stats* __restrict__ st) {
-    if (!st->do_resample) return;
-    __shared__ unsigned long long s_u[32];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    unsigned long long acc = 0;
-    for (int c = tid; c < (int)blockIdx.x; c += 1024) acc += tile_fx[c];
-    const unsigned long long carry = block_reduce_1024(acc, SumU64(), s_u);
-    const int i = blockIdx.x * 1024 + tid;
-    unsigned long long v = i < P ? (unsigned long long)(w[i] * 0x1p60) : 0ull;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long u = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += u;
-    }
-    __syncthreads();
-    if (lane == 31) s_u[wid] = v;
-    __syncthreads();
-    unsigned long long wsum = s_u[lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long u = __shfl_up_sync(0xffffffffu, wsum, o);
-        if (lane >= o) wsum += u;
-    }
-    const unsigned long long warp_excl = __shfl_sync(0xffffffffu, wsum, max(wid, 1) - 1);
-    if (i < P) cdf[i] = carry + (wid > 0 ? warp_excl : 0ull) + v;
-}
-
 // index selection: for m = 1..P, U = r + (m-1)*1.0/P, first i with !(U > c_i), clamped to P-1.
 // ... and the new generation is gathered right here: copies of the chosen parents (Particle(Particle)
-// SLAM.java:41-45: weight and pose are copied; weights are NOT reset to 1/N).
-template <bool FIXED>
-__global__ void __launch_bounds__(256) k_select(const void* __restrict__ cdf_raw, int P, double u01, uint64_t seed,
-                                                uint64_t resample_count, int* __restrict__ parents,
-                                                const Stats* __restrict__ st, const float4* __restrict__ pose_in,
-                                                const double* __restrict__ w_in, const double* __restrict__ lw_in,
-                                                float4* __restrict__ pose_out, double* __restrict__ w_out,
-                                                double* __restrict__ lw_out, int m_begin, int m_count) {
-    __shared__ unsigned long long s_coarse[2048];
-    const int m0 = m_begin + blockIdx.x * blockDim.x + threadIdx.x;  // children [m_begin, m_begin + m_count)
-    const bool resample = st->do_resample != 0;  // uniform over the grid
+// SLAM.java:41-45: weight and pose are copied; weights are NOT reset to 1/N).  A parent's pose is read through
+// the PoseTable: with the peer exchange it may live in another rank's pose array (one 16-byte NVLink read).
+struct SelectArgs {
+    const void* cdf;     // f64 (LITERAL) or u64 fixed point (FIXED), P entries
+    int P;
+    double u01;
+    uint64_t seed, resample_count;
+    int* parents;
+    Stats* st;
+    PoseTable poses_in;
+    const double* w_in;
+    const double* lw_in;
+    float4* pose_out;
+    double* w_out;
+    double* lw_out;
+    int m_begin, m_count;  // children [m_begin, m_begin + m_count)
+};
+__device__ __forceinline__ int select_stride(int P) {
     int stride = 32;
     while ((P + stride - 1) / stride > 2048) stride <<= 1;
-    const int ncoarse = (P + stride - 1) / stride;
-    if (resample) {
-        const unsigned long long* raw = static_cast<const unsigned long long*>(cdf_raw);  // 8-byte keys either way
-        for (int j = threadIdx.x; j < ncoarse; j += 256) s_coarse[j] = raw[min(P - 1, (j + 1) * stride - 1)];
-        __syncthreads();
-    }
-    if (m0 >= m_begin + m_count) return;
-    if (!resample) {
-        parents[m0] = m0;
-        pose_out[m0] = pose_in[m0];
-        w_out[m0] = w_in[m0];
-        lw_out[m0] = lw_in[m0];
-        return;
-    }
-    if (u01 < 0.0) u01 = philox_uniform(seed, resample_count);
+    return stride;
+}
+template <bool FIXED>
+__device__ __forceinline__ void select_child(const SelectArgs& a, int m0, const unsigned long long* s_coarse, int stride,
+                                             int ncoarse, double u01) {
+    using Key = typename std::conditional<FIXED, unsigned long long, double>::type;
+    const int P = a.P;
     const double r = u01 * 1.0 / (double)P;
-    const double U = r + (double)m0 * 1.0 / (double)P;
+    auto key_of = [&](int m) -> Key {
+        const double U = r + (double)m * 1.0 / (double)P;
+        return FIXED ? (Key)(unsigned long long)(U * 0x1p60) : (Key)U;
+    };
     // two-level search: every `stride`-th CDF value (<= 2048 of them) is staged in shared memory with one
     // round of independent loads, which replaces the top ~11 dependent global probes of a plain bisection
-    using Key = typename std::conditional<FIXED, unsigned long long, double>::type;
-    const Key* cdf = static_cast<const Key*>(cdf_raw);
-    const Key key = FIXED ? (Key)(unsigned long long)(U * 0x1p60) : (Key)U;
-    Key* coarse = reinterpret_cast<Key*>(s_coarse);
+    const Key* cdf = static_cast<const Key*>(a.cdf);
+    const Key key = key_of(m0);
+    const Key* coarse = reinterpret_cast<const Key*>(s_coarse);
     int lo = 0, hi = ncoarse - 1;
     while (lo < hi) {  // first segment whose last CDF value is not below the key
         const int mid = (lo + hi) >> 1;
@@ -1345,12 +1429,97 @@ __global__ void __launch_bounds__(256) k_select(const void* __restrict__ cdf_raw
     lo = lo * stride;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (key > cdf[mid]) lo = mid + 1; else hi = mid;
+        if (key > __ldcg(cdf + mid)) lo = mid + 1; else hi = mid;
     }
-    parents[m0] = lo;
-    pose_out[m0] = pose_in[lo];
-    w_out[m0] = w_in[lo];
-    lw_out[m0] = lw_in[lo];
+    a.parents[m0] = lo;
+    a.pose_out[m0] = a.poses_in.at(lo);
+    a.w_out[m0] = a.w_in[lo];
+    a.lw_out[m0] = __ldcg(a.lw_in + lo);
+    // the strongest particle of the last update lives on as its FIRST child (slam.py / gms_get_strongest)
+    const int sb = a.st->strongest;
+    if (lo == sb && (m0 == 0 || sb == 0 ? m0 == 0 : !(key_of(m0 - 1) > __ldcg(cdf + sb - 1)))) a.st->strongest_now = m0;
+}
+
+// LITERAL mode (P <= 2048 by default): Java's sequential f64 CDF (k_cdf_literal) + this selection kernel.
+// Also used to complete a local-only FIXED selection (multi-rank: the children other ranks own).
+template <bool FIXED>
+__global__ void __launch_bounds__(256) k_select(SelectArgs a) {
+    __shared__ unsigned long long s_coarse[2048];
+    const int m0 = a.m_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.st->xerror) return;
+    const bool resample = a.st->do_resample != 0;  // uniform over the grid
+    const int stride = select_stride(a.P), ncoarse = (a.P + stride - 1) / stride;
+    if (resample) {
+        const unsigned long long* raw = static_cast<const unsigned long long*>(a.cdf);  // 8-byte keys either way
+        for (int j = threadIdx.x; j < ncoarse; j += 256) s_coarse[j] = __ldcg(raw + min(a.P - 1, (j + 1) * stride - 1));
+        __syncthreads();
+    }
+    if (m0 >= a.m_begin + a.m_count) return;
+    if (!resample) {
+        a.parents[m0] = m0;
+        a.pose_out[m0] = a.poses_in.at(m0);
+        a.w_out[m0] = a.w_in[m0];
+        a.lw_out[m0] = __ldcg(a.lw_in + m0);
+        return;
+    }
+    const double u01 = a.u01 < 0.0 ? philox_uniform(a.seed, a.resample_count) : a.u01;
+    select_child<FIXED>(a, m0, s_coarse, stride, ncoarse, u01);
+}
+
+// FIXED mode: CDF + selection in ONE cooperative launch.
+//   phase 1  u64 fixed-point CDF, c_i = sum_{j<=i} trunc(w_j * 2^60): integer addition is associative, so the
+//            parallel scan (fixed-point tile sums of k_norm_coop / k_neff + a block-wide scan per tile) equals
+//            the sequential walk bit for bit on any number of threads / CTAs / ranks
+//   phase 2  selection + gather of the children [m_begin, m_begin + m_count)
+__global__ void __launch_bounds__(1024) k_resample_coop(SelectArgs a, const unsigned long long* __restrict__ tile_fx,
+                                                        int ntiles) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned long long s_coarse[2048];
+    __shared__ unsigned long long s_u[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, G = gridDim.x;
+    if (a.st->xerror) return;        // uniform over the grid
+    if (!a.st->do_resample) {        // uniform over the grid: the generation is carried over unchanged
+        for (int m0 = a.m_begin + blockIdx.x * 1024 + tid; m0 < a.m_begin + a.m_count; m0 += G * 1024) {
+            a.parents[m0] = m0;
+            a.pose_out[m0] = a.poses_in.at(m0);
+            a.w_out[m0] = a.w_in[m0];
+            a.lw_out[m0] = __ldcg(a.lw_in + m0);
+        }
+        return;
+    }
+    unsigned long long* cdf = static_cast<unsigned long long*>(const_cast<void*>(a.cdf));
+    for (int t = blockIdx.x; t < ntiles; t += G) {
+        unsigned long long acc = 0;
+        for (int c = tid; c < t; c += 1024) acc += __ldcg(tile_fx + c);
+        const unsigned long long carry = block_reduce_1024(acc, SumU64(), s_u);
+        const int i = t * 1024 + tid;
+        unsigned long long v = i < a.P ? (unsigned long long)(a.w_in[i] * 0x1p60) : 0ull;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        __syncthreads();
+        if (lane == 31) s_u[wid] = v;
+        __syncthreads();
+        unsigned long long wsum = s_u[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, wsum, o);
+            if (lane >= o) wsum += u;
+        }
+        const unsigned long long warp_excl = __shfl_sync(0xffffffffu, wsum, max(wid, 1) - 1);
+        if (i < a.P) cdf[i] = carry + (wid > 0 ? warp_excl : 0ull) + v;
+    }
+    if (blockIdx.x == 0 && tid == 0) a.st->strongest_now = -1;
+    __threadfence();
+    grid.sync();
+    const int stride = select_stride(a.P), ncoarse = (a.P + stride - 1) / stride;
+    for (int j = tid; j < ncoarse; j += 1024) s_coarse[j] = __ldcg(cdf + min(a.P - 1, (j + 1) * stride - 1));
+    __syncthreads();
+    const double u01 = a.u01 < 0.0 ? philox_uniform(a.seed, a.resample_count) : a.u01;
+    for (int m0 = a.m_begin + blockIdx.x * 1024 + tid; m0 < a.m_begin + a.m_count; m0 += G * 1024)
+        select_child<true>(a, m0, s_coarse, stride, ncoarse, u01);
 }
 
 // Per-particle maps: slot assignment.  parents[] is non-decreasing, so the first child of a parent is

@@ -1,12 +1,18 @@
 """Multi-rank stepping: one process per GPU, particles block-partitioned over ranks.
 
-The only data-path collective is the all-gather of the 24-byte exchange records
-{f64 log-weight, f32 x, y, theta, u32 pad} (100k particles = 2.4 MB).  Everything after it
-(normalise, Neff, strongest, CDF, parent indices, shared-map integration) is computed redundantly and
-bit-identically on every rank from the gathered array, so no broadcast follows.
+Two data planes for the one exchange a step needs (the weights, before resampling):
 
-The stepper is backend-agnostic: with libgms the exchange blocks are device memory and the collective
-is NCCL on the handle's stream; the CPU tests drive the same code with the oracle library and gloo.
+* PEER path (CUDA handles, default): every rank maps the others' receive buffers, flags and pose arrays with
+  cudaIpc.  After scoring, each rank stores its block of f64 log-weights (8 B per particle) into every rank's
+  receive buffer over NVLink and raises a flag; the normalise kernel of every rank waits for the flags itself.
+  Poses are not exchanged at all: the resampling reads a remote parent's 16-byte pose through the peer mapping.
+  No collective, no host synchronisation, no import pass.
+* COLLECTIVE path (the oracle under gloo in the CPU tests, or `use_peer_memory=False`): all-gather of 24-byte
+  records {f64 log-weight, f32 x, y, theta, u32 pad} between begin and end.
+
+Everything after the exchange (normalise, Neff, strongest, CDF, parent indices, shared-map integration) is
+computed redundantly and bit-identically on every rank over fixed 1024-particle tiles of the global particle
+index, so no broadcast follows and the results do not depend on the number of ranks.
 """
 from __future__ import annotations
 
@@ -44,8 +50,7 @@ class ShardedStepper:
         # per-particle maps: resampling moves maps between GPUs (SLAM.java:41-45 deep copy); every rank
         # maps the other ranks' arenas (cudaIpc) so its copy kernel can pull parents' maps over NVLink
         self.migrates = handle.cfg.map_mode == B.MAP_PER_PARTICLE and dist.get_world_size() > 1
-        # CUDA handles map each other's buffers (cudaIpc): the exchange then rides on the scoring kernel's own
-        # stores over NVLink (fused compute + all-gather, gms.h "FUSED path") and per-particle maps can migrate.
+        # CUDA handles map each other's buffers (cudaIpc): PEER path, and per-particle maps can migrate.
         # The oracle (CPU tests, gloo) has no device arenas: it keeps the explicit all-gather.
         self.direct = False
         if handle.info.is_cuda and dist.get_world_size() > 1 and use_peer_memory:

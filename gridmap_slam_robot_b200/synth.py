@@ -71,14 +71,16 @@ class Scan:
         return int(self.beam_hit.sum())
 
 
-def make_scans(num_steps, num_beams, max_range=10.0, seed=20260101, noise_sd=0.01):
-    """`num_steps` consecutive scans along the trajectory (scan k is taken at true_pose(k + 1))."""
+def make_scans(num_steps, num_beams, max_range=10.0, seed=20260101, noise_sd=0.01, room_scale=1.0):
+    """`num_steps` consecutive scans along the trajectory (scan k is taken at true_pose(k + 1)).
+    `room_scale` enlarges the room and its boxes about the origin (bench.py's gather-stress workload); the
+    trajectory stays the 3 m circle."""
     rng = np.random.Generator(np.random.PCG64(seed))
     rel = 2.0 * np.pi * np.arange(num_beams, dtype=np.float64) / num_beams
     scans = []
     for k in range(num_steps):
         x, y, th = true_pose(k + 1)
-        dist = raycast(x, y, rel + th) + rng.normal(0.0, noise_sd, size=num_beams)
+        dist = room_scale * raycast(x / room_scale, y / room_scale, rel + th) + rng.normal(0.0, noise_sd, size=num_beams)
         hit = dist <= max_range
         dist = np.where(hit, np.maximum(dist, 0.02), max_range)
         xy = np.stack([dist * np.cos(rel), dist * np.sin(rel)], axis=1)

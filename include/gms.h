@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GMS_ABI_VERSION 1
+#define GMS_ABI_VERSION 2
 
 typedef enum gms_status {
     GMS_OK = 0,
@@ -141,10 +141,27 @@ int gms_update(gms_handle* h, const double* beam_xy, const double* beam_dist, co
  * the work is enqueued on the handle's stream and observed through the getters (which synchronise). */
 int gms_resample(gms_handle* h, double u01);
 
+/* A4 — GridMap.findBestPoseOptim GridMap.java:348-369 (called per particle between the motion sample and the
+ * weight, SLAM.java:97) as an optional CPU hook.  The reference's own optimiser is the identity (its objective
+ * is multiplied by Odometry.probabiliyOf == 0, Odometry.java:99-103), so the default is NO hook and nothing of
+ * this runs.  With a hook installed every update calls it once, after the motion update and the likelihood
+ * refresh and before the scoring, with the poses of the handle's local particles [first, first + count) in a
+ * host array it may modify in place; beam_* are host copies of the scan.  The hook may call the GridMap
+ * operators of this header on `h` (gms_map_probability_of is the reference's objective) but no step entry
+ * point.  A non-zero return aborts the update with GMS_ERR_STATE. */
+typedef int (*gms_pose_optimizer_fn)(void* user, gms_handle* h, int32_t first_particle, int32_t count,
+                                     float* poses_xyt /* 3*count, in/out */, const double* beam_xy,
+                                     const double* beam_dist, const uint8_t* beam_hit, int32_t num_beams,
+                                     double d_center, double d_theta);
+int gms_set_pose_optimizer(gms_handle* h, gms_pose_optimizer_fn fn /* NULL: identity */, void* user);
+
 int gms_calculate_neff(gms_handle* h, double* neff_out);    /* SLAM.calculateNeff SLAM.java:180-190 */
 int gms_get_weighted_pose(gms_handle* h, float pose_xyt[3]);/* SLAM.getWeightedPose SLAM.java:165-178 */
-/* SLAM.getStrongestParticle SLAM.java:196-198 (+ public fields weight, pose SLAM.java:31-32).
- * index = global particle index at the time of the last update (-1 before any). */
+/* SLAM.getStrongestParticle SLAM.java:196-198 (+ public fields weight, pose SLAM.java:31-32): the particle
+ * that was strongest at the last update.  pose / weight are its values at that update (Java keeps referencing
+ * that Particle object, which a later resample() does not modify).  index = where it lives NOW: its global
+ * index after the update; after a resampling the index of its first child, which inherits its map slot
+ * (GridMapApp.java:376-393 keeps drawing strongestParticle.m); -1 before any update or if it left no child. */
 int gms_get_strongest(gms_handle* h, int32_t* index, float pose_xyt[3], double* weight);
 int gms_get_poses(gms_handle* h, float* xyt /* 3*P */);     /* getParticles().get(i).pose          */
 int gms_get_weights(gms_handle* h, double* w /* P */);      /* getParticles().get(i).weight        */
@@ -197,6 +214,10 @@ int gms_step_dev(gms_handle* h, const double* d_beam_xy, const double* d_beam_di
                  const uint8_t* d_beam_hit, int32_t num_beams, double d_center, double d_theta,
                  const double* d_normals, int32_t resample_policy, double u01);
 int gms_sync(gms_handle* h);
+/* Stream-level join (no host synchronisation): everything the last step enqueued on the handle's internal side
+ * streams (the shared-map integration runs next to the resampling) is ordered before whatever is enqueued on
+ * the handle's stream next — e.g. an event that closes a timed region. */
+int gms_join_streams(gms_handle* h);
 /* Use an existing cudaStream_t for all work of this handle (NULL = the handle's own stream). */
 int gms_set_stream(gms_handle* h, void* cuda_stream);
 /* Per-phase device timing (CUDA events on the handle's stream).  Phases: see GMS_PHASE_*. */
@@ -207,7 +228,8 @@ int gms_set_stream(gms_handle* h, void* cuda_stream);
 #define GMS_PHASE_MAP_UPDATE 4
 #define GMS_PHASE_RESAMPLE 5
 #define GMS_PHASE_MAP_COPY 6
-#define GMS_PHASE_COUNT 8
+#define GMS_PHASE_EXCHANGE 7    /* multi-rank: push of the log-weights / import of all-gathered records */
+#define GMS_PHASE_COUNT 9       /* the last slot collects everything else (getters, resets, rows of §8f) */
 int gms_profile_enable(gms_handle* h, int32_t on);
 /* ms[GMS_PHASE_COUNT], launches[GMS_PHASE_COUNT]: accumulated since the last gms_profile_reset. */
 int gms_profile_read(gms_handle* h, double* ms, int64_t* launches);
@@ -237,11 +259,12 @@ int gms_read_neff(gms_handle* h, double* neff_out);  /* sync + read Neff of the 
  * rank imports the lot; resampling then pulls remote parents' maps over NVLink inside
  * gms_update_end_dev / gms_resample.  The caller must run a barrier across ranks after the resampling
  * call before the next update (old slots are only released then).  Handles hold 2x the slots.
- * The same import also switches the {log-weight, pose} exchange of every multi-rank handle to the PEER path:
- * after scoring each rank stores its block directly into every rank's receive buffer over NVLink and a flag
- * per sender replaces the collective, so the caller skips its all-gather between begin and end. */
+ * The same import also switches the exchange of every multi-rank handle to the PEER path: after scoring each
+ * rank stores its block of f64 log-weights (8 bytes per particle) directly into every rank's receive buffer
+ * over NVLink, a flag per sender replaces the collective (the caller skips its all-gather between begin and
+ * end), and the resampling reads a remote parent's pose through the peer mapping of that rank's pose array. */
 #define GMS_IPC_HANDLE_BYTES 64
-#define GMS_IPC_NUM_HANDLES 7
+#define GMS_IPC_NUM_HANDLES 9
 int gms_ipc_export(gms_handle* h, void* handles /* GMS_IPC_NUM_HANDLES * GMS_IPC_HANDLE_BYTES */);
 int gms_ipc_import(gms_handle* h, const void* all_handles /* nranks * the above, rank-major */);
 

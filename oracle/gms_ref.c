@@ -57,6 +57,11 @@ struct gms_handle {
     /* scalars */
     double neff, neff_lit;
     int32_t strongest, strongest_lit;
+    int32_t strongest_now;        /* where the strongest particle of the last update lives now (first child) */
+    float strongest_pose[3];      /* its pose / weight at that update (Java keeps the Particle object) */
+    double strongest_w;
+    gms_pose_optimizer_fn opt_fn; /* A4 hook: GridMap.findBestPoseOptim (default NULL = identity) */
+    void *opt_user;
     uint64_t step, resample_count;
     int have_update;
     /* exchange blocks for the begin/end split ("device" == host for the oracle) */
@@ -585,6 +590,9 @@ static void normalise(gms_handle *h) {
     }
     for (int i = 0; i < P; i++) h->w[i] /= s;
     h->strongest = cb;
+    h->strongest_now = cb;
+    h->strongest_pose[0] = h->px[cb]; h->strongest_pose[1] = h->py[cb]; h->strongest_pose[2] = h->pt[cb];
+    h->strongest_w = h->w[cb];
     h->neff = neff_of(h->w, P);
 }
 
@@ -641,6 +649,30 @@ static int update_local(gms_handle *h, const double *bxy, const double *bdist, c
         compute_likelihood(h, h->logd[0], h->lik[0], h->prob_scratch, h->tmp_scratch);
         PHASE_ADD(h, 1);
     }
+    if (h->opt_fn) {
+        /* A4 hook installed: the loop of SLAM.java:88 is run in two sweeps — motion sample + likelihood field of
+         * every particle, then the hook (findBestPoseOptim, SLAM.java:97) on all poses, then the weights.  The
+         * particles are independent, so the split changes nothing else. */
+        float *xyt = malloc(sizeof(float) * 3 * (size_t)(h->cnt > 0 ? h->cnt : 1));
+        for (int li = 0; li < h->cnt; li++) {
+            int i = h->lo + li;
+            double zd, zt;
+            if (normals) { zd = normals[2 * li]; zt = normals[2 * li + 1]; }
+            else philox_normals(h->cfg.seed, (uint32_t)i, h->step, &zd, &zt);
+            motion_sample(h, &h->px[i], &h->py[i], &h->pt[i], d_center, d_theta, zd, zt);
+            if (!shared) compute_likelihood(h, h->logd[h->slot[li]], h->lik[h->slot[li]], h->prob_scratch, h->tmp_scratch);
+            xyt[3 * li] = h->px[i]; xyt[3 * li + 1] = h->py[i]; xyt[3 * li + 2] = h->pt[i];
+        }
+        int rc = h->opt_fn(h->opt_user, h, h->lo, h->cnt, xyt, bxy, bdist, bhit, B, d_center, d_theta);
+        if (rc == 0)
+            for (int li = 0; li < h->cnt; li++) {
+                int i = h->lo + li;
+                h->px[i] = xyt[3 * li]; h->py[i] = xyt[3 * li + 1]; h->pt[i] = xyt[3 * li + 2];
+            }
+        free(xyt);
+        if (rc != 0) return fail(h, GMS_ERR_STATE, "pose optimiser hook failed");
+    }
+    const int hooked = h->opt_fn != NULL;
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 1) num_threads(h->threads)
 #endif
@@ -653,16 +685,18 @@ static int update_local(gms_handle *h, const double *bxy, const double *bdist, c
 #endif
         double zd, zt;
         PHASE_T0(h);
-        if (normals) { zd = normals[2 * li]; zt = normals[2 * li + 1]; }
-        else philox_normals(h->cfg.seed, (uint32_t)i, h->step, &zd, &zt);
-        motion_sample(h, &h->px[i], &h->py[i], &h->pt[i], d_center, d_theta, zd, zt); /* SLAM.java:90 */
-        PHASE_ADD(h, 0);
         int s = h->slot[li];
-        if (!shared)
-            compute_likelihood(h, h->logd[s], h->lik[s], h->prob_scratch + n * tid,
-                               h->tmp_scratch + n * tid);                               /* SLAM.java:93 */
-        PHASE_ADD(h, 1);
-        /* SLAM.java:97 findBestPoseOptim: objective == 0 -> start pose (identity) */
+        if (!hooked) {
+            if (normals) { zd = normals[2 * li]; zt = normals[2 * li + 1]; }
+            else philox_normals(h->cfg.seed, (uint32_t)i, h->step, &zd, &zt);
+            motion_sample(h, &h->px[i], &h->py[i], &h->pt[i], d_center, d_theta, zd, zt); /* SLAM.java:90 */
+            PHASE_ADD(h, 0);
+            if (!shared)
+                compute_likelihood(h, h->logd[s], h->lik[s], h->prob_scratch + n * tid,
+                                   h->tmp_scratch + n * tid);                               /* SLAM.java:93 */
+            PHASE_ADD(h, 1);
+        }
+        /* SLAM.java:97 findBestPoseOptim: objective == 0 -> start pose (identity) unless a hook replaced it */
         double lw;
         h->wlit[i] = probability_of(h, h->lik[s], h->px[i], h->py[i], h->pt[i], bxy, bhit, B, &lw); /* :99 */
         h->lw[i] = lw;
@@ -731,6 +765,10 @@ static void do_resample(gms_handle *h, double u01) {
     if (u01 < 0) u01 = philox_uniform(h->cfg.seed, h->resample_count);
     h->resample_count++;
     gmsref_resample_indices(h->w, P, u01, h->resample_mode, h->parents);
+    /* the Particle object GridMapApp holds as strongestParticle lives on as its first child (same map slot) */
+    h->strongest_now = -1;
+    for (int m = 0; m < P; m++)
+        if (h->parents[m] == h->strongest) { h->strongest_now = m; break; }
     float *nx = malloc(sizeof(float) * P), *ny = malloc(sizeof(float) * P), *nt = malloc(sizeof(float) * P);
     double *nw = malloc(sizeof(double) * P), *nl = malloc(sizeof(double) * P), *nwl = malloc(sizeof(double) * P);
     for (int m = 0; m < P; m++) {
@@ -804,10 +842,15 @@ EXPORT int gms_get_weighted_pose(gms_handle *h, float pose[3]) {
 }
 EXPORT int gms_get_strongest(gms_handle *h, int32_t *index, float pose[3], double *weight) {
     if (!h) return GMS_ERR_INVALID_ARG;
-    int b = h->strongest;
-    if (index) *index = h->have_update ? b : -1;
-    if (pose) { pose[0] = h->px[b]; pose[1] = h->py[b]; pose[2] = h->pt[b]; }
-    if (weight) *weight = h->w[b];
+    if (!h->have_update) { /* SLAM.reset: strongestParticle = particles.get(0) (SLAM.java:75) */
+        if (index) *index = -1;
+        if (pose) { pose[0] = pose[1] = pose[2] = 0.f; }
+        if (weight) *weight = 1.0 / h->P;
+        return GMS_OK;
+    }
+    if (index) *index = h->strongest_now;
+    if (pose) { pose[0] = h->strongest_pose[0]; pose[1] = h->strongest_pose[1]; pose[2] = h->strongest_pose[2]; }
+    if (weight) *weight = h->strongest_w;
     return GMS_OK;
 }
 EXPORT int gms_get_poses(gms_handle *h, float *xyt) {
@@ -1039,6 +1082,13 @@ EXPORT int gms_read_neff(gms_handle *h, double *neff) {
     return GMS_OK;
 }
 EXPORT int gms_sync(gms_handle *h) { return h ? GMS_OK : GMS_ERR_INVALID_ARG; }
+EXPORT int gms_join_streams(gms_handle *h) { return h ? GMS_OK : GMS_ERR_INVALID_ARG; }
+EXPORT int gms_set_pose_optimizer(gms_handle *h, gms_pose_optimizer_fn fn, void *user) {
+    if (!h) return GMS_ERR_INVALID_ARG;
+    h->opt_fn = fn;
+    h->opt_user = user;
+    return GMS_OK;
+}
 EXPORT int gms_set_stream(gms_handle *h, void *s) { (void)s; return h ? GMS_OK : GMS_ERR_INVALID_ARG; }
 EXPORT int gms_profile_enable(gms_handle *h, int32_t on) { (void)on; return h ? GMS_OK : GMS_ERR_INVALID_ARG; }
 EXPORT int gms_profile_read(gms_handle *h, double *ms, int64_t *launches) {

@@ -324,24 +324,187 @@ def test_device_side_resample_policy(cuda, oracle):
 
 def test_strongest_survives_resampling_like_the_reference(cuda, oracle):
     """GridMapApp keeps `strongestParticle` across the resample (GridMapApp.java:188-190): its pose and weight are
-    those of the last update even though the particle list was replaced."""
+    those of the last update even though the particle list was replaced, and its map (GridMapApp.java:376-393
+    draws strongestParticle.m) is the one its FIRST CHILD inherits — so the reported index follows it there."""
     from gridmap_slam_robot_b200 import synth
 
     P = 200
     kw = dict(num_particles=P, map_width_m=20.0, map_height_m=20.0, origin_x=-10.0, origin_y=-10.0)
     sc = synth.make_scans(2, 90)
     z = synth.make_draws(2, P)[0]
+    seen = []
     for lib in (cuda, oracle):
         h = lib.create(**kw)
         h.update(sc[0].beam_xy, sc[0].beam_dist, sc[0].beam_hit, 0.05, 0.01, z[0])
         h.update(sc[1].beam_xy, sc[1].beam_dist, sc[1].beam_hit, 0.05, 0.01, z[1])
         idx, pose, w = h.strongest()
         assert np.array_equal(pose, h.poses()[idx]) and w == h.weights()[idx] == h.weights().max()
+        occ_before = h.get_map(idx, B.MAP_OCC_COUNT).copy()
         h.resample(0.77)
         idx2, pose2, w2 = h.strongest()
-        assert idx2 == idx and np.array_equal(pose2, pose) and w2 == w
-        assert any(np.array_equal(pose, p) for p in h.poses())  # the strongest particle always survives
+        parents = h.parents()
+        assert idx2 == int(np.flatnonzero(parents == idx)[0])  # the strongest particle always survives
+        assert np.array_equal(pose2, pose) and w2 == w
+        assert np.array_equal(h.poses()[idx2], pose)
+        assert np.array_equal(h.get_map(idx2, B.MAP_OCC_COUNT), occ_before)
+        seen.append((idx, idx2))
         h.close()
+    assert seen[0] == seen[1]
+
+
+def _halfway_hook(first, poses, xy, dist, hit, dc, dth):
+    """A deterministic stand-in for GridMap.findBestPoseOptim: pulls every pose 25 % towards the origin heading."""
+    poses[:, 2] = (poses[:, 2] * np.float32(0.75)).astype(np.float32)
+    poses[:, 0] = (poses[:, 0] + np.float32(0.01)).astype(np.float32)
+
+
+@pytest.mark.parametrize("mode", [B.MAP_PER_PARTICLE, B.MAP_SHARED])
+def test_pose_optimizer_hook_matches_oracle(cuda, oracle, mode):
+    """A4 (GridMap.findBestPoseOptim, SLAM.java:97) as a CPU hook between motion and scoring: same hook on both
+    libraries => same poses (bit-exact), weights and maps; removing the hook restores the identity default."""
+    from gridmap_slam_robot_b200 import synth
+
+    P, steps = 48, 4
+    scans = synth.make_scans(steps, 180)
+    normals, uniforms = synth.make_draws(steps, P)
+    kw = dict(num_particles=P, map_width_m=20.0, map_height_m=20.0, origin_x=-10.0, origin_y=-10.0, map_mode=mode,
+              resample_mode=B.RESAMPLE_LITERAL)
+    g, o = cuda.create(**kw), oracle.create(**kw)
+    calls = []
+    for h in (g, o):
+        h.set_pose_optimizer(lambda first, poses, *a, _h=h: (calls.append((first, len(poses))), _halfway_hook(first, poses, *a)))
+    for s, sc in enumerate(scans):
+        if s == steps - 1:  # last step without the hook
+            g.set_pose_optimizer(None)
+            o.set_pose_optimizer(None)
+        ng = g.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta, normals[s])
+        no = o.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta, normals[s])
+        assert np.array_equal(g.poses(), o.poses()), f"step {s}"
+        np.testing.assert_allclose(g.log_weights(), o.log_weights(), rtol=0, atol=checks.LW_TOL)
+        assert abs(ng / no - 1) < 1e-9
+        g.resample(float(uniforms[s]))
+        o.resample(float(uniforms[s]))
+        assert np.array_equal(g.parents(), o.parents())
+    for kind in (B.MAP_FREE_COUNT, B.MAP_OCC_COUNT, B.MAP_LIKELIHOOD):
+        assert np.array_equal(g.get_map(0, kind), o.get_map(0, kind))
+    assert len(calls) == 2 * (steps - 1) and all(c == (0, P) for c in calls)
+    g.close()
+    o.close()
+
+
+def test_pose_optimizer_hook_may_call_the_objective(cuda, oracle):
+    """The hook may evaluate GridMap.probabilityOf (the reference's objective, GridMap.java:355-359) on the handle:
+    a two-candidate search per particle gives the same choice on both libraries."""
+    from gridmap_slam_robot_b200 import synth
+
+    P = 12
+    scans = synth.make_scans(3, 90)
+    normals, _ = synth.make_draws(3, P)
+    kw = dict(num_particles=P, map_width_m=20.0, map_height_m=20.0, origin_x=-10.0, origin_y=-10.0)
+    res = []
+    for lib in (cuda, oracle):
+        h = lib.create(**kw)
+
+        def hook(first, poses, xy, dist, hit, dc, dth, _h=h):
+            for k in range(len(poses)):
+                cand = poses[k].copy()
+                cand[2] += np.float32(0.02)
+                a = _h.map_probability_of(first + k, poses[k], xy, hit)[0]
+                b = _h.map_probability_of(first + k, cand, xy, hit)[0]
+                if b > a + 1e-6:
+                    poses[k] = cand
+
+        h.set_pose_optimizer(hook)
+        for s, sc in enumerate(scans):
+            h.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta, normals[s])
+        res.append((h.poses().copy(), h.log_weights().copy(), h.get_map(3, B.MAP_OCC_COUNT).copy()))
+        h.close()
+    assert np.array_equal(res[0][0], res[1][0])
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=0, atol=checks.LW_TOL)
+    assert np.array_equal(res[0][2], res[1][2])
+
+
+def test_scoring_many_beams_does_not_underflow(cuda, oracle):
+    """Per-particle scoring near GMS_MAX_BEAMS on an explored map: a lane multiplies ~390 factors of 0.01..0.91;
+    the running product must not underflow (the oracle sums ln per beam)."""
+    rng = np.random.default_rng(11)
+    Bn = 12500
+    ang = rng.uniform(-np.pi, np.pi, Bn)
+    dist = rng.uniform(1.0, 8.0, Bn)
+    xy = np.stack([dist * np.cos(ang), dist * np.sin(ang)], 1)
+    hit = np.ones(Bn, np.uint8)
+    kw = dict(num_particles=2, map_width_m=20.0, map_height_m=20.0, origin_x=-10.0, origin_y=-10.0)
+    out = []
+    for lib in (cuda, oracle):
+        h = lib.create(**kw)
+        pose = np.array([0.1, -0.2, 0.3], np.float32)
+        sub = slice(0, 2000)
+        h.map_integrate_observation(0, pose, xy[sub], dist[sub], hit[sub])
+        h.map_compute_likelihood(0)
+        out.append(h.map_probability_of(0, pose, xy, hit))
+        h.close()
+    assert np.isfinite(out[0][0]) and out[0][0] < -2000.0  # far below ln(DBL_MIN) = -708
+    assert abs(out[0][0] - out[1][0]) <= 1e-9 * abs(out[1][0])
+
+
+def test_sorted_scoring_validation_variant_many_beams(cuda, oracle, monkeypatch):
+    """GMS_SCORE_V=1 (ALU-lean index validation) with more than 3072 hit beams needs > 48 KB of dynamic shared
+    memory in every instantiation; results equal the default variant's and the oracle's."""
+    from gridmap_slam_robot_b200 import synth
+
+    P, Bn = 4200, 3600
+    scans = synth.make_scans(2, Bn, max_range=30.0)
+    normals, _ = synth.make_draws(2, P)
+    kw = dict(num_particles=P, map_width_m=51.2, map_height_m=51.2, origin_x=-25.6, origin_y=-25.6, map_mode=B.MAP_SHARED)
+    lws = []
+    for v in ("0", "1"):
+        monkeypatch.setenv("GMS_SCORE_V", v)
+        h = cuda.create(**kw)
+        for s, sc in enumerate(scans):
+            h.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta, normals[s])
+        lws.append(h.log_weights().copy())
+        h.close()
+    assert np.array_equal(lws[0], lws[1])
+    o = oracle.create(**kw)
+    for s, sc in enumerate(scans):
+        o.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta, normals[s])
+    np.testing.assert_allclose(lws[0], o.log_weights(), rtol=0, atol=checks.LW_TOL)
+    o.close()
+
+
+def test_determinism_large_shared_sorted_path(cuda):
+    """>= 8k particles on a shared map, device Philox, resampling every step: the heading-sorted scoring, the
+    cooperative normalise / resample kernels and the side streams give byte-identical results run to run."""
+    import torch
+
+    from gridmap_slam_robot_b200 import synth
+
+    P, steps = 16384, 6
+    scans = synth.make_scans(steps, 360, max_range=30.0)
+    dev = torch.device("cuda:0")
+    outs = []
+    for _ in range(3):
+        h = cuda.create(num_particles=P, map_width_m=51.2, map_height_m=51.2, origin_x=-25.6, origin_y=-25.6,
+                        map_mode=B.MAP_SHARED, seed=99)
+        neffs = []
+        for s, sc in enumerate(scans):
+            t_xy, t_d, t_h = (torch.from_numpy(a).to(dev) for a in (sc.beam_xy, sc.beam_dist, sc.beam_hit))
+            torch.cuda.synchronize()
+            h.step_dev(t_xy.data_ptr(), t_d.data_ptr(), t_h.data_ptr(), sc.num_beams, sc.d_center, sc.d_theta, None,
+                       B.POLICY_ALWAYS, -1.0)
+            neffs.append(h.read_neff())
+        outs.append((np.array(neffs).tobytes(), h.poses().tobytes(), h.weights().tobytes(), h.log_weights().tobytes(),
+                     h.parents().tobytes(), h.get_map(0, B.MAP_FREE_COUNT).tobytes(),
+                     h.get_map(0, B.MAP_LIKELIHOOD).tobytes(), h.weighted_pose().tobytes()))
+        h.close()
+    assert outs[0] == outs[1] == outs[2]
+
+
+def test_shared_map_side_limit(cuda):
+    """The shared-map ray kernels pack a cell as x | y << 16: wider grids are rejected at creation."""
+    with pytest.raises(B.GmsError) as e:
+        cuda.create(num_particles=4, map_mode=B.MAP_SHARED, map_width_m=3400.0, map_height_m=1.0, resolution=0.05)
+    assert e.value.code == B.ERR_INVALID_ARG
 
 
 def test_sorted_update_mode_equals_atomic(cuda, oracle):

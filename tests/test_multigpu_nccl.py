@@ -109,9 +109,13 @@ def _run(cuda, P, steps, beams, world, mode, peer=True):
     h.close()
 
 
-def test_two_gpus_equal_one_gpu(cuda):
-    """Fused exchange: the scoring kernels push the records into both ranks' receive buffers (NVLink)."""
-    _run(cuda, P=8192, steps=6, beams=360, world=2, mode=1)
+WORLDS = [2, 4, 8]
+
+
+@pytest.mark.parametrize("world", WORLDS)
+def test_ranks_equal_one_gpu(cuda, world):
+    """Peer exchange: log-weights pushed into every rank's receive buffer (NVLink), poses read through peer maps."""
+    _run(cuda, P=8192, steps=6, beams=360, world=world, mode=1)
 
 
 def test_two_gpus_equal_one_gpu_nccl_all_gather(cuda):
@@ -119,7 +123,55 @@ def test_two_gpus_equal_one_gpu_nccl_all_gather(cuda):
     _run(cuda, P=8192, steps=4, beams=360, world=2, mode=1, peer=False)
 
 
-def test_two_gpus_per_particle_maps_migrate(cuda):
-    """K5-style: every particle owns a map; resampling every step moves maps between the two GPUs
-    (peer pull over NVLink).  Every particle's counts and likelihood field equal the 1-GPU run."""
-    _run(cuda, P=48, steps=5, beams=180, world=2, mode=0)
+@pytest.mark.parametrize("world", WORLDS)
+def test_per_particle_maps_migrate(cuda, world):
+    """K5-style: every particle owns a map; resampling every step moves maps between the GPUs (peer pull over
+    NVLink).  Every particle's counts and likelihood field equal the 1-GPU run."""
+    _run(cuda, P=24 * world, steps=5, beams=180, world=world, mode=0)
+
+
+def _rankcheck_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from gridmap_slam_robot_b200 import binding as B
+    from gridmap_slam_robot_b200 import rankcheck
+
+    lib = B.load()
+    out = []
+    out.append(rankcheck.check(lib, dist, dev, rank, world, per_particle=False, P=16384, beams=360, steps=6, grid_m=51.2))
+    out.append(rankcheck.check(lib, dist, dev, rank, world, per_particle=True, P=64 * world, beams=180, steps=5, grid_m=20.0))
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", WORLDS)
+def test_bench_parity_check(cuda, world):
+    """The check bench.py runs before timing at N > 1 (device Philox keyed by the global particle index,
+    resampling every step): N ranks == 1 rank for parents, pose bytes, weights and every map."""
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rankcheck_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for r in range(world):
+        for ok, detail in results[r]:
+            assert ok, (r, detail)

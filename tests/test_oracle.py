@@ -80,3 +80,44 @@ def test_full_size_sampled_check_is_self_consistent(oracle):
 
 def test_full_size_sampled_pp_check_is_self_consistent(oracle):
     checks.check_full_size_sampled_pp(oracle, oracle, P=24, beams=90, grid_m=25.6, steps=3, sample=4)
+
+
+def test_pose_optimizer_hook_default_is_identity(oracle):
+    """A4 (GridMap.findBestPoseOptim, SLAM.java:97): a hook that changes nothing gives the results of no hook, bit
+    for bit; a hook that moves the poses is what gets scored and integrated."""
+    from gridmap_slam_robot_b200 import binding as B
+    from gridmap_slam_robot_b200 import synth
+
+    P = 20
+    scans = synth.make_scans(3, 90)
+    normals, _ = synth.make_draws(3, P)
+    kw = dict(num_particles=P, map_width_m=20.0, map_height_m=20.0, origin_x=-10.0, origin_y=-10.0)
+    outs = []
+    for hook in (None, lambda first, poses, *a: None, lambda first, poses, *a: poses.__setitem__(slice(None), poses + np.float32(0.05))):
+        h = oracle.create(**kw)
+        if hook:
+            h.set_pose_optimizer(hook)
+        for s, sc in enumerate(scans):
+            h.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta, normals[s])
+        outs.append((h.poses().copy(), h.log_weights().copy(), h.get_map(2, B.MAP_FREE_COUNT).copy()))
+        h.close()
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0], outs[1]))
+    assert not np.array_equal(outs[0][0], outs[2][0]) and not np.array_equal(outs[0][2], outs[2][2])
+
+
+def test_strongest_index_follows_its_first_child(oracle):
+    from gridmap_slam_robot_b200 import synth
+
+    P = 64
+    sc = synth.make_scans(2, 90)
+    z = synth.make_draws(2, P)[0]
+    h = oracle.create(num_particles=P, map_width_m=20.0, map_height_m=20.0, origin_x=-10.0, origin_y=-10.0)
+    assert h.strongest()[0] == -1
+    for s in range(2):
+        h.update(sc[s].beam_xy, sc[s].beam_dist, sc[s].beam_hit, 0.05, 0.01, z[s])
+    idx, pose, w = h.strongest()
+    h.resample(0.31)
+    idx2, pose2, w2 = h.strongest()
+    assert idx2 == int(np.flatnonzero(h.parents() == idx)[0]) and np.array_equal(pose, pose2) and w == w2
+    assert np.array_equal(h.poses()[idx2], pose)
+    h.close()
