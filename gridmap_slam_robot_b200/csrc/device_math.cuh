@@ -26,6 +26,8 @@ struct Geometry {
     int fx_k;                 // fraction bits: max(W, H) * 2^fx_k < 2^30
     int fx_hi;                // high word of fx_magic == high word of q + fx_magic for 0 <= q < 2^(31 - fx_k)
     int fx_margin;            // acceptance margin in units of 2^-fx_k (>= 8 units >> |q~ - q_java| + rounding)
+    int fac_pitch, fac_lp;    // shared map: the factor field is a padded square of side fac_pitch = 2^fac_lp >= max(W, H)
+                              // (1.0 outside the map: such end points do not multiply, GridMap.java:276)
     int tiles_x, tiles_y;     // likelihood tiles (kTileW x kTileH cells) per map
     int tile_words;           // 32-bit words of one slot's dirty-tile bitmap
     double z_hit;             // GridMap.java:259

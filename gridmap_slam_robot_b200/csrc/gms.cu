@@ -39,6 +39,7 @@ struct BeamSet {
     float* meas = nullptr;     // (float) distance / resolution (GridMap.java:188)
     double2* hit_xy = nullptr; // compacted hit beams (scoring reads only those, GridMap.java:269-270)
     int* num_hit = nullptr;
+    double* rmax2 = nullptr;   // squared length of the longest hit beam (range guard of k_score_sorted<G, 2>)
 };
 
 }  // namespace
@@ -120,6 +121,8 @@ struct gms_handle {
     bool resample_partial = false;
     double partial_u01 = 0;
     unsigned long long partial_count = 0;
+    int map_win_words = 26000;  // per-particle map update: cells of the shared-memory window (GMS_MAP_WIN_WORDS; 0 =
+                                // the global-atomic kernel).  26000 x 4 B = 104 KB: two CTAs per SM
     int score_g = 0;  // sub-threads per particle in k_score_sorted (0 = automatic; GMS_SCORE_G overrides: tuning knob)
     int score_v = 0;  // index-validation variant of k_score_sorted (GMS_SCORE_V=1: ALU-lean form, same results)
     int num_sms = 148;
@@ -277,6 +280,7 @@ int java_d2i_host(double d) {
 
 void free_beamset(BeamSet& b) {
     cudaFree(b.xy); cudaFree(b.dist); cudaFree(b.hit); cudaFree(b.meas); cudaFree(b.hit_xy); cudaFree(b.num_hit);
+    cudaFree(b.rmax2);
     b = BeamSet{};
 }
 
@@ -354,6 +358,8 @@ int alloc_beamset(gms_handle* h, BeamSet& b, int cap) {
     CK(cudaMalloc((void**)&b.hit_xy, (size_t)cap * 16));
     CK(cudaMalloc((void**)&b.num_hit, 4));
     CK(cudaMemset(b.num_hit, 0, 4));
+    CK(cudaMalloc((void**)&b.rmax2, 8));
+    CK(cudaMemset(b.rmax2, 0, 8));
     return GMS_OK;
 }
 
@@ -421,7 +427,7 @@ PoseTable pose_table(const gms_handle* h, int buf) {
 // ---- the step, as stream-ordered launches ---------------------------------------------------------
 int launch_pack(gms_handle* h, BeamSet& b, const double* d_xy, const double* d_dist, const uint8_t* d_hit, int B) {
     LAUNCH(GMS_PHASE_SCORE, k_pack_beams<<<1, 256, 0, h->stream>>>((const double2*)d_xy, d_dist, d_hit, B, h->g.res_f,
-                                                                   b.hit_xy, b.meas, b.xy, b.hit, b.num_hit));
+                                                                   b.hit_xy, b.meas, b.xy, b.hit, b.num_hit, b.rmax2));
     return GMS_OK;
 }
 
@@ -470,13 +476,13 @@ bool use_fac_score(const gms_handle* h) { return h->cfg.map_mode == GMS_MAP_SHAR
 template <int G, int V>
 int launch_score_sorted(gms_handle* h, unsigned grid, size_t smem, const float4* pose, int lo, int cnt, const BeamSet& b,
                         const int* order, double* lw, ExchangeRec* xlocal) {
-    static bool attr_done = false;  // per instantiation: scans above 3072 beams need more than the default 48 KB
-    if (!attr_done) {
+    static bool attr_done[64] = {};  // per instantiation and device: scans above 3072 beams need more than 48 KB
+    if (!attr_done[h->dev & 63]) {
         CK(cudaFuncSetAttribute(k_score_sorted<G, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
+        attr_done[h->dev & 63] = true;
     }
     LAUNCH(GMS_PHASE_SCORE, k_score_sorted<G, V><<<grid, 128, smem, h->stream>>>(pose, lo, cnt, b.hit_xy, b.num_hit, h->fac,
-                                                                                 order, lw, xlocal, h->g));
+                                                                                 order, lw, xlocal, b.rmax2, h->g));
     return GMS_OK;
 }
 
@@ -493,8 +499,9 @@ int launch_score(gms_handle* h, const BeamSet& b, const float4* pose, int lo, in
         const unsigned grid = blocks_for((long long)cnt * G, 128);
 #define SCORE_G(GG)                                                                                            \
     case GG:                                                                                                   \
-        return h->score_v == 1 ? launch_score_sorted<GG, 1>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
-                               : launch_score_sorted<GG, 0>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal);
+        return h->score_v == 2   ? launch_score_sorted<GG, 2>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
+               : h->score_v == 1 ? launch_score_sorted<GG, 1>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
+                                 : launch_score_sorted<GG, 0>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal);
         switch (G) {
             SCORE_G(1) SCORE_G(2) SCORE_G(4) SCORE_G(8) SCORE_G(16) SCORE_G(32)
         }
@@ -552,7 +559,7 @@ int launch_shared_update(gms_handle* h, const BeamSet& b, int B) {
     const bool sorted = h->cfg.update_mode == GMS_UPDATE_SORTED;
     if (sorted) CK(cudaMemsetAsync(h->ray_maxlen, 0, 4, h->stream));
     uint32_t* stale = h->alt_needs_clear ? h->dirty_alt : nullptr;
-    LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_integrate<<<Bpad / 32, 256, 0, h->stream>>>(
+    LAUNCH(GMS_PHASE_MAP_UPDATE, k_ray_integrate<<<Bpad / kRaysPerCta, 256, 0, h->stream>>>(
                                      b.xy, B, Bpad, h->st, h->ray_cells, h->ray_cap, h->ray_count, h->ray_start,
                                      h->ray_maxlen, h->rect, b.meas, b.hit, h->counts, h->dirty, stale,
                                      stale ? h->g.tile_words : 0, sorted ? 1 : 0, h->g));
@@ -565,6 +572,12 @@ int launch_shared_update(gms_handle* h, const BeamSet& b, int B) {
 int launch_map_update(gms_handle* h, const BeamSet& b, const float4* pose, int lo, int cnt, const int* slot, int B) {
     if (B <= 0) return GMS_OK;
     Phase ph(h, GMS_PHASE_MAP_UPDATE);
+    if (h->map_win_words > 0) {  // one CTA per (particle, quadrant): shared-memory accumulation + coalesced flush
+        LAUNCH(GMS_PHASE_MAP_UPDATE, k_map_update_win<<<(unsigned)cnt * 4u, 128, (size_t)h->map_win_words * 4, h->stream>>>(
+                                         pose, lo, cnt, b.xy, b.meas, b.hit, B, h->counts, slot, h->rect, h->dirty,
+                                         h->map_win_words, h->g));
+        return GMS_OK;
+    }
     const long long total = (long long)cnt * B;
     LAUNCH(GMS_PHASE_MAP_UPDATE, k_map_update<<<blocks_for(total, 128), 128, 0, h->stream>>>(
                                      pose, lo, cnt, b.xy, b.meas, b.hit, B, h->counts, slot, h->rect, h->dirty, h->g));
@@ -637,7 +650,7 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
     {
         Phase ph(h, GMS_PHASE_MOTION);
         if (sorted) {  // motion + heading sort + beam packing: one cooperative launch
-            PackArgs pk{(const double2*)d_xy, d_dist, d_hit, B, h->g.res_f, bs.hit_xy, bs.meas, bs.xy, bs.hit, bs.num_hit};
+            PackArgs pk{(const double2*)d_xy, d_dist, d_hit, B, h->g.res_f, bs.hit_xy, bs.meas, bs.xy, bs.hit, bs.num_hit, bs.rmax2};
             int do_pack = hook ? 0 : 1;
             const unsigned grid = std::min<unsigned>(blocks_for(h->cnt, 1024), (unsigned)h->num_sms);
             LAUNCH_COOP(GMS_PHASE_MOTION, k_motion_sort, grid, 1024, 0, &ma, &h->sort, &pk, &do_pack);
@@ -722,6 +735,7 @@ int complete_resample(gms_handle* h) {
 
 int launch_resample(gms_handle* h, double u01, bool local_only = false) {
     const int P = h->P;
+    h->stats_valid = false;  // Stats.strongest_now changes
     {
         Phase ph(h, GMS_PHASE_RESAMPLE);
         const int nxt = h->cur ^ 1;
@@ -995,6 +1009,9 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
         std::memcpy(&u, &g.fx_magic, 8);
         g.fx_hi = (int)(u >> 32);
         g.fx_margin = std::max(8, 1 << std::max(0, g.fx_k - 14));
+        g.fac_lp = bits;  // 2^bits > max(W, H) - 1 ... the padded side of the factor field
+        while (g.fac_lp > 0 && (1 << (g.fac_lp - 1)) >= std::max(h->W, h->H)) g.fac_lp--;
+        g.fac_pitch = 1 << g.fac_lp;
     }
     g.tiles_x = (h->W + kTileW - 1) / kTileW;
     g.tiles_y = (h->H + kTileH - 1) / kTileH;
@@ -1055,9 +1072,11 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->counts, (size_t)h->S * h->cells * sizeof(CellCounts)));
     CKC(cudaMalloc((void**)&h->lik, (size_t)h->S * h->cells * sizeof(double)));
     if (cfg->map_mode == GMS_MAP_SHARED) {  // + one sentinel element holding 1.0 for out-of-map end points
-        CKC(cudaMalloc((void**)&h->fac, (h->cells + 1) * sizeof(double)));
-        const double one = 1.0;
-        CKC(cudaMemcpy(h->fac + h->cells, &one, sizeof one, cudaMemcpyHostToDevice));
+        // padded square (side 2^fac_lp) + one sentinel element, all 1.0 until the first refresh writes the map's cells
+        const size_t nfac = (size_t)g.fac_pitch * g.fac_pitch + 1;
+        CKC(cudaMalloc((void**)&h->fac, nfac * sizeof(double)));
+        k_fill_f64<<<(unsigned)std::min<size_t>((nfac + 255) / 256, 148 * 16), 256, 0, h->stream>>>(h->fac, nfac, 1.0);
+        CKC(cudaGetLastError());
     }
     CKC(cudaMalloc((void**)&h->rect, (size_t)h->S * sizeof(int4)));
     CKC(cudaMalloc((void**)&h->dirty, (size_t)h->S * g.tile_words * 4));
@@ -1099,7 +1118,9 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->sort.rank, (size_t)h->cnt * 4));
     CKC(cudaMalloc((void**)&h->sort.order, (size_t)h->cnt * 4));
     h->ntiles = (h->P + 1023) / 1024;
-    if (const char* e = std::getenv("GMS_SCORE_V")) h->score_v = std::atoi(e) == 1 ? 1 : 0;
+    if (const char* e = std::getenv("GMS_SCORE_V")) h->score_v = std::max(0, std::min(2, std::atoi(e)));
+    if (const char* e = std::getenv("GMS_MAP_WIN_WORDS")) h->map_win_words = std::max(0, std::min(56000, std::atoi(e)));
+    CKC(cudaFuncSetAttribute(k_map_update_win, cudaFuncAttributeMaxDynamicSharedMemorySize, 56000 * 4));
     if (const char* e = std::getenv("GMS_SCORE_G")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) h->score_g = v; }
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, h->dev) == cudaSuccess) h->num_sms = prop.multiProcessorCount; }
     {

@@ -114,15 +114,22 @@ __device__ __forceinline__ void pack_beams_cta(const double2* __restrict__ in_xy
                                                const uint8_t* __restrict__ in_hit, int B, float res_f,
                                                double2* __restrict__ hit_xy, float* __restrict__ meas,
                                                double2* __restrict__ all_xy, uint8_t* __restrict__ all_hit,
-                                               int* __restrict__ num_hit) {
+                                               int* __restrict__ num_hit, double* __restrict__ rmax2) {
     __shared__ int s_warp[32];
+    __shared__ double s_r[32];
     __shared__ int s_base;
+    double r2 = 0.0;  // longest hit beam (squared length, metres): range guard of k_score_sorted<G, 2>
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
     if (tid == 0) s_base = 0;
     __syncthreads();
     for (int b0 = 0; b0 < B; b0 += blockDim.x) {
         const int b = b0 + tid;
         const bool hit = b < B && in_hit[b] != 0;
+        if (hit) {
+            const double2 v = in_xy[b];
+            const double d2 = v.x * v.x + v.y * v.y;
+            r2 = d2 > r2 || d2 != d2 ? d2 : r2;  // a NaN beam poisons the guard: exact path
+        }
         if (b < B) {
             meas[b] = (float)in_dist[b] / res_f;
             if (all_xy != in_xy) all_xy[b] = in_xy[b];  // private copy: the map integration reads it later
@@ -143,14 +150,25 @@ __device__ __forceinline__ void pack_beams_cta(const double2* __restrict__ in_xy
         __syncthreads();
     }
     if (tid == 0) *num_hit = s_base;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v = __shfl_xor_sync(0xffffffffu, r2, o);
+        r2 = v > r2 || v != v ? v : r2;
+    }
+    if (lane == 0) s_r[wid] = r2;
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 1; k < nw; k++) r2 = s_r[k] > r2 || s_r[k] != s_r[k] ? s_r[k] : r2;
+        *rmax2 = r2;
+    }
 }
 __global__ void __launch_bounds__(256) k_pack_beams(const double2* __restrict__ in_xy,
                                                     const double* __restrict__ in_dist,
                                                     const uint8_t* __restrict__ in_hit, int B, float res_f,
                                                     double2* __restrict__ hit_xy, float* __restrict__ meas,
                                                     double2* __restrict__ all_xy, uint8_t* __restrict__ all_hit,
-                                                    int* __restrict__ num_hit) {
-    pack_beams_cta(in_xy, in_dist, in_hit, B, res_f, hit_xy, meas, all_xy, all_hit, num_hit);
+                                                    int* __restrict__ num_hit, double* __restrict__ rmax2) {
+    pack_beams_cta(in_xy, in_dist, in_hit, B, res_f, hit_xy, meas, all_xy, all_hit, num_hit, rmax2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -216,6 +234,7 @@ struct PackArgs {
     double2* all_xy;
     uint8_t* all_hit;
     int* num_hit;
+    double* rmax2;
 };
 __global__ void __launch_bounds__(1024) k_motion_sort(MotionArgs a, SortBufs sb, PackArgs pk, int do_pack) {
     cg::grid_group grid = cg::this_grid();
@@ -230,7 +249,7 @@ __global__ void __launch_bounds__(1024) k_motion_sort(MotionArgs a, SortBufs sb,
         sb.rank[li] = atomicAdd(sb.hist + b, 1u);
     }
     if (do_pack && blockIdx.x == gridDim.x - 1)
-        pack_beams_cta(pk.in_xy, pk.in_dist, pk.in_hit, pk.B, pk.res_f, pk.hit_xy, pk.meas, pk.all_xy, pk.all_hit, pk.num_hit);
+        pack_beams_cta(pk.in_xy, pk.in_dist, pk.in_hit, pk.B, pk.res_f, pk.hit_xy, pk.meas, pk.all_xy, pk.all_hit, pk.num_hit, pk.rmax2);
     grid.sync();
     for (int c = blockIdx.x; c < kSortChunks; c += gridDim.x) {
         const int i = c * 1024 + tid;
@@ -489,7 +508,7 @@ __global__ void __launch_bounds__(256) k_likelihood(const CellCounts* __restrict
                             out[(size_t)gx + (size_t)gy * g.W] = total;
                             // shared map: the per-lookup factor of GridMap.probabilityOf (GridMap.java:284-288)
                             // is a pure function of the cell: evaluated once per cell here, not per lookup
-                            if (fac) fac[(size_t)gx + (size_t)gy * g.W] = total == 0.5 ? g.uniform_term : g.z_hit * total + g.random_term;
+                            if (fac) fac[(size_t)gx + (size_t)gy * g.fac_pitch] = total == 0.5 ? g.uniform_term : g.z_hit * total + g.random_term;
                         }
                     }
                 }
@@ -511,7 +530,7 @@ __global__ void __launch_bounds__(256) k_likelihood(const CellCounts* __restrict
                     double total = 0.0;
                     for (int i = 0; i < g.ktaps; i++) total += g.kernel[i] * col[i * kTileW];
                     out[(size_t)gx + (size_t)gy * g.W] = total;
-                    if (fac) fac[(size_t)gx + (size_t)gy * g.W] = total == 0.5 ? g.uniform_term : g.z_hit * total + g.random_term;
+                    if (fac) fac[(size_t)gx + (size_t)gy * g.fac_pitch] = total == 0.5 ? g.uniform_term : g.z_hit * total + g.random_term;
                 }
             }
         }
@@ -632,7 +651,7 @@ __global__ void __launch_bounds__(256) k_likelihood_tma(const __grid_constant__ 
                     for (int i = 0; i < 2 * KH + 1; i++) total += kr[i] * hcol[j + i];
                     if (gy < g.H) {
                         out[(size_t)gx + (size_t)gy * g.W] = total;
-                        if (fac) fac[(size_t)gx + (size_t)gy * g.W] = total == 0.5 ? g.uniform_term : g.z_hit * total + g.random_term;
+                        if (fac) fac[(size_t)gx + (size_t)gy * g.fac_pitch] = total == 0.5 ? g.uniform_term : g.z_hit * total + g.random_term;
                     }
                 }
             }
@@ -757,7 +776,8 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
                                                       const double2* __restrict__ hit_xy,
                                                       const int* __restrict__ num_hit, const double* __restrict__ fac,
                                                       const int* __restrict__ order, double* __restrict__ lw,
-                                                      ExchangeRec* __restrict__ xlocal, Geometry g) {
+                                                      ExchangeRec* __restrict__ xlocal,
+                                                      const double* __restrict__ rmax2, Geometry g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
     double2* s_xy = reinterpret_cast<double2*>(smem_raw);
@@ -805,7 +825,8 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
     const double pqx = (x.px - g.posx) * g.inv_res, pqy = (x.py - g.posy) * g.inv_res;
     double mant = 1.0;
     int exp2 = 0;
-    const unsigned uW = (unsigned)g.W, uH = (unsigned)g.H, oob = uW * uH;
+    const unsigned uW = (unsigned)g.W, uH = (unsigned)g.H, pitch = (unsigned)g.fac_pitch;
+    const unsigned oob = pitch * pitch;  // sentinel element (1.0) behind the padded square
     const int fk = g.fx_k;
     const unsigned fmask = (1u << fk) - 1u, fmarg = (unsigned)g.fx_margin, fspan = (1u << fk) - 2u * fmarg;
     const unsigned fnear = fmask & ~(2u * fmarg - 1u);  // V == 1: the fraction bits above the 2*margin window
@@ -818,17 +839,50 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
         }
         const int gx = java_d2i((x.tx(m.x, m.y) - g.posx) / g.res);
         const int gy = java_d2i((x.ty(m.x, m.y) - g.posy) / g.res);
-        if ((unsigned)gx < uW && (unsigned)gy < uH) return __ldg(fac + ((unsigned)gy * uW + (unsigned)gx));
+        if ((unsigned)gx < uW && (unsigned)gy < uH) return __ldg(fac + ((unsigned)gy * pitch + (unsigned)gx));
         return 1.0;
     };
+    // V == 2 only.  The magic constant is folded into the per-particle offsets (q~ + magic comes out of the two
+    // FMAs directly: 5 instead of 7 FP64-pipe instructions per lookup); that adds at most one more unit of
+    // 2^-k of rounding, far inside the acceptance margin of >= 8 units (tests/test_fastpath_bound.py).
+    // The high-word test of the other variants (|q| within the fixed-point range) is hoisted out of the beam
+    // loop: with R = the longest hit beam of the scan in cells, every q of this particle lies within
+    // |pq| + R * 1.000001 + 2, so one per-particle comparison covers all beams; a particle that fails it
+    // (poses thousands of cells outside the map) takes the exact path for every beam.
+    const double pqxm = pqx + g.fx_magic, pqym = pqy + g.fx_magic;
+    bool fast_ok = true;
+    if constexpr (V == 2) {
+        const double R = sqrt(*rmax2) * g.inv_res * 1.000001 + 2.0;
+        const double lim = (double)(1u << (31 - fk)) - 2.0;
+        fast_ok = fabs(pqx) + R < lim && fabs(pqy) + R < lim;  // NaN poses fail too
+    }
+    const unsigned fshift = 32u - (unsigned)fk;
+    const unsigned fmul = 1u << fshift, fadd = fmarg << fshift, fthr = (2u * fmarg) << fshift;
+    const unsigned bound = 1u << (fk + g.fac_lp);  // (ix | iy) below it  <=>  both cells inside the padded square
     auto peel = [&]() { peel_exponent(mant, exp2); };
     int b0 = 0, it = 0;
-    for (; b0 + 8 * G <= nhe; b0 += 8 * G, it++) {
+    const int nfast = (V == 2 && !fast_ok) ? 0 : nhe;
+    for (; b0 + 8 * G <= nfast; b0 += 8 * G, it++) {
         unsigned idx[8];
         unsigned bad = 0;
         // branch-free fast path for 8 beams (their dependency chains interleave); beams whose q~ is too
         // close to an integer are only flagged here and redone exactly below.  End points outside the
         // map read the sentinel fac[W*H] == 1.0 (GridMap.java:276: such beams do not multiply).
+        if constexpr (V == 2) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const double2 m = s_xy[b0 + u * G + gsub];
+                const double tx = fma(m.x, cinv, fma(-m.y, sinv, pqxm));
+                const double ty = fma(m.x, sinv, fma(m.y, cinv, pqym));
+                const unsigned ix = (unsigned)__double2loint(tx), iy = (unsigned)__double2loint(ty);
+                // fraction test on the FMA pipe: (i + margin) * 2^(32-k) keeps only the fraction bits, shifted to
+                // the top; it is >= 2*margin * 2^(32-k)  <=>  the fraction lies in [margin, 2^k - margin)
+                const unsigned ux = ix * fmul + fadd, uy = iy * fmul + fadd;
+                const bool ok = min(ux, uy) >= fthr && (ix | iy) < bound;
+                bad |= ok ? 0u : (1u << u);
+                idx[u] = ok ? __umulhi(iy, fmul) * pitch + __umulhi(ix, fmul) : oob;  // cell = i >> k
+            }
+        } else
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             const double2 m = s_xy[b0 + u * G + gsub];  // G distinct addresses per warp: shared-memory broadcast
@@ -855,7 +909,7 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
             }
             const bool inb = gx < uW && gy < uH;
             bad |= ok ? 0u : (1u << u);
-            idx[u] = (ok && inb) ? gy * uW + gx : oob;
+            idx[u] = (ok && inb) ? gy * pitch + gx : oob;
         }
         double f[8];
 #pragma unroll
@@ -870,7 +924,10 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
         mant *= ((f[0] * f[1]) * (f[2] * f[3])) * ((f[4] * f[5]) * (f[6] * f[7]));
         if ((it & 7) == 7) peel();  // factors are in [0.01, 0.91]: 64 of them cannot underflow a normalised mantissa
     }
-    for (int b = b0 + gsub; b < nhe; b += G) mant *= factor_exact(s_xy[b]);
+    for (int b = b0 + gsub, j = 0; b < nhe; b += G, j++) {
+        mant *= factor_exact(s_xy[b]);
+        if ((j & 31) == 31) peel();
+    }
     peel();
     if (G > 1) {  // combine the sub-threads' partial products: mantissas in [1, 2), at most 2^5 after the tree
 #pragma unroll
@@ -925,15 +982,160 @@ __global__ void __launch_bounds__(128) k_map_update(const float4* __restrict__ p
     }
 }
 
+// Per-particle maps, windowed: ONE CTA per (particle, quadrant of the ray fan).  The atomic kernel above is bound
+// by the L2 atomic unit (ncu, K2pp: 7.8e7 64-bit ATOMG in 1.05 ms = ~40 atomics/clk chip-wide, 9 % of the HBM
+// roofline, DRAM traffic 2.3x the algorithmic bytes because every non-horizontal DDA step lands in a new 32-byte
+// sector).  A map is only ever written by its own particle, so the increments of one scan can be combined on
+// chip first: the rays of one quadrant all start in the same cell and move monotonically away from it, so they
+// live in a rectangle anchored at the start cell.  The CTA keeps that rectangle in shared memory as one u32
+// per cell (low half: free increments, high half: occupied increments; a ray visits a cell at most 3 times,
+// 3 * GMS_MAX_BEAMS < 65536), walks its rays with shared-memory atomics, and then flushes the rectangle with
+// plain, coalesced 8-byte read-modify-writes (old pair in, new pair out, dirty-tile marking from the two
+// thresholded codes).  Cells beyond the rectangle (window capacity: `win_words` cells) fall back to the global
+// atomic.  Integer accumulation: the result is independent of the order => deterministic, identical to the
+// atomic kernel's.
+__global__ void __launch_bounds__(128) k_map_update_win(const float4* __restrict__ pose, int lo, int cnt,
+                                                        const double2* __restrict__ all_xy,
+                                                        const float* __restrict__ meas,
+                                                        const uint8_t* __restrict__ hit, int B,
+                                                        CellCounts* __restrict__ counts, const int* __restrict__ slot,
+                                                        int4* __restrict__ rect, uint32_t* __restrict__ dirty,
+                                                        int win_words, Geometry g) {
+    extern __shared__ __align__(16) uint32_t s_win[];
+    __shared__ int s_reach[2];
+    __shared__ int s_box[4];
+    const int tid = threadIdx.x;
+    const int li = blockIdx.x >> 2, quad = blockIdx.x & 3;
+    if (li >= cnt) return;
+    const int qx = (quad & 1) ? -1 : 1, qy = (quad & 2) ? -1 : 1;  // direction of travel of this CTA's rays
+    const int s = slot[li];
+    CellCounts* map = counts + (size_t)s * ((size_t)g.W * g.H);
+    uint32_t* bitmap = dirty + (size_t)s * g.tile_words;
+    const float4 p = pose[lo + li];
+    const Xform t(p.x, p.y, p.z);
+    const float sx = (float)((t.tx(0.0, 0.0) - g.posx) / g.res);
+    const float sy = (float)((t.ty(0.0, 0.0) - g.posy) / g.res);
+    const int x0 = java_d2i(floor((double)(sx + 0.5f))), y0 = java_d2i(floor((double)(sy + 0.5f)));  // RayIter.init
+    if (tid == 0) {
+        s_reach[0] = 0; s_reach[1] = 0;
+        s_box[0] = 0x7fffffff; s_box[1] = 0x7fffffff; s_box[2] = -1; s_box[3] = -1;
+    }
+    __syncthreads();
+    int rx = 0, ry = 0;  // of the last ray_of(): |dfloor x|, |dfloor y| between the ray's first and last cell
+    auto ray_of = [&](int b, RayIter& it) -> bool {  // true if beam b belongs to this quadrant
+        const double2 m = all_xy[b];
+        const float ex = (float)((t.tx(m.x, m.y) - g.posx) / g.res);
+        const float ey = (float)((t.ty(m.x, m.y) - g.posy) / g.res);
+        it.init(sx + 0.5f, sy + 0.5f, ex + 0.5f, ey + 0.5f, g.extra_steps);
+        rx = abs(java_d2i(floor((double)(ex + 0.5f))) - x0);
+        ry = abs(java_d2i(floor((double)(ey + 0.5f))) - y0);
+        return ((it.x_inc < 0) ? -1 : 1) == qx && ((it.y_inc < 0) ? -1 : 1) == qy;
+    };
+    // pass A: how far do this quadrant's rays reach (cells, clipped to the map)?  A ray makes |dfloor x| steps in
+    // x and |dfloor y| in y to its end point, plus at most `extra_steps` more in either axis.
+    for (int b = tid; b < B; b += 128) {
+        RayIter it;
+        if (!ray_of(b, it) || !it.has_next(g.W, g.H)) continue;
+        const int lim_x = qx > 0 ? g.W - 1 - x0 : x0, lim_y = qy > 0 ? g.H - 1 - y0 : y0;
+        atomicMax(&s_reach[0], min(rx + g.extra_steps, lim_x));
+        atomicMax(&s_reach[1], min(ry + g.extra_steps, lim_y));
+    }
+    __syncthreads();
+    // window: [0, WX) x [0, WY) cells in the quadrant's own coordinates (lx = (x - x0) * qx, ly likewise)
+    int WX = s_reach[0] + 1, WY = s_reach[1] + 1;
+    if ((long long)WX * WY > win_words) {
+        int sq = 1;
+        while ((sq + 1) * (sq + 1) <= win_words) sq++;
+        if (WX <= sq) WY = win_words / WX;
+        else if (WY <= sq) WX = win_words / WY;
+        else { WX = sq; WY = win_words / sq; }
+    }
+    const int nwin = WX * WY;
+    for (int i = tid; i < nwin; i += 128) s_win[i] = 0u;
+    __syncthreads();
+    // pass B: walk, accumulate on chip
+    for (int b = tid; b < B; b += 128) {
+        RayIter it;
+        if (!ray_of(b, it) || !it.has_next(g.W, g.H)) continue;
+        const float ms = meas[b];
+        const bool wh = hit[b] != 0;
+        const int fx = it.x, fy = it.y;
+        int lx_ = it.x, ly_ = it.y;
+        while (it.has_next(g.W, g.H)) {
+            lx_ = it.x; ly_ = it.y;
+            const float dX = sx - ((float)lx_ + 0.5f);
+            const float dY = sy - ((float)ly_ + 0.5f);
+            const float dist = __fsqrt_rn(dX * dX + dY * dY);
+            const int cls = inverse_sensor_class(dist, ms, wh, g.tol_half);
+            if (cls != 0) {
+                const int wx = (lx_ - x0) * qx, wy = (ly_ - y0) * qy;
+                if ((unsigned)wx < (unsigned)WX && (unsigned)wy < (unsigned)WY)
+                    atomicAdd(&s_win[wy * WX + wx], cls == 1 ? 1u : 65536u);
+                else
+                    bump_cell(map, bitmap, lx_, ly_, cls, g);
+            }
+            it.advance();
+        }
+        atomicMin(&s_box[0], min(fx, lx_)); atomicMin(&s_box[1], min(fy, ly_));
+        atomicMax(&s_box[2], max(fx, lx_)); atomicMax(&s_box[3], max(fy, ly_));
+    }
+    __syncthreads();
+    // flush: plain coalesced read-modify-write of the cells this scan touched (rows of the window are
+    // contiguous in the map, forwards or backwards).  The start row and column (wx == 0 or wy == 0) are shared
+    // with the neighbouring quadrants' CTAs, which flush concurrently: those cells take one 64-bit atomic each.
+    for (int i0 = tid; i0 < nwin; i0 += 4 * 128) {
+        uint32_t inc[4];
+        size_t idx[4];
+        unsigned long long old[4];
+        bool axis[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + u * 128;
+            inc[u] = i < nwin ? s_win[i] : 0u;
+            axis[u] = false;
+            if (inc[u]) {
+                const int wy = i / WX, wx = i - wy * WX;
+                idx[u] = (size_t)(x0 + wx * qx) + (size_t)(y0 + wy * qy) * g.W;
+                axis[u] = wx == 0 || wy == 0;
+                const unsigned long long add = (unsigned long long)(inc[u] & 0xffffu) | ((unsigned long long)(inc[u] >> 16) << 32);
+                if (axis[u]) old[u] = atomicAdd(reinterpret_cast<unsigned long long*>(map + idx[u]), add);
+                else old[u] = __ldcg(reinterpret_cast<const unsigned long long*>(map + idx[u]));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (!inc[u]) continue;
+            const uint32_t of = (uint32_t)old[u], oo = (uint32_t)(old[u] >> 32);
+            const uint32_t nf = of + (inc[u] & 0xffffu), no = oo + (inc[u] >> 16);
+            if (!axis[u])
+                __stcg(reinterpret_cast<unsigned long long*>(map + idx[u]), (unsigned long long)nf | ((unsigned long long)no << 32));
+            bool flip;
+            if (oo == 0 && no == 0) flip = of == 0;                 // never occupied: flips on its first free hit
+            else if (of == 0 && nf == 0) flip = oo == 0;            // never freed: flips on its first occupied hit
+            else flip = cell_code(of, oo, g) != cell_code(nf, no, g);
+            if (flip) {
+                const int wy = (i0 + u * 128) / WX, wx = (i0 + u * 128) - wy * WX;
+                mark_dirty(bitmap, x0 + wx * qx, y0 + wy * qy, g);
+            }
+        }
+    }
+    if (tid == 0 && s_box[2] >= 0) {
+        int* r = reinterpret_cast<int*>(rect + s);
+        atomicMin(r + 0, s_box[0]); atomicMin(r + 1, s_box[1]);
+        atomicMax(r + 2, s_box[2]); atomicMax(r + 3, s_box[3]);
+    }
+}
+
 // Shared map (one scan per step, only B rays): the DDA of a ray is inherently sequential (f32 error term,
 // RayIterator.java:112-130), but the per-cell work (sqrt, inverse sensor model, counter update) is not.
-// k_ray_integrate does both in ONE launch: a CTA owns 32 consecutive rays; warp 0 walks them in lockstep and
-// records the cells {x | y << 16} (cell k of ray b at ray_cells[k * Bpad + b]: one coalesced line per step),
-// then all 8 warps classify and accumulate the CTA's (cell, ray) pairs in parallel.
+// k_ray_integrate does both in ONE launch: a CTA owns 8 consecutive rays (90 CTAs for 720 beams); 8 lanes of warp 0
+// walk them in lockstep and record the cells {x | y << 16} (cell k of ray b at ray_cells[k * Bpad + b]), then all 8
+// warps classify and accumulate the CTA's (cell, ray) pairs in parallel, four independent loads per thread.
 // The walk loop keeps everything in registers (grid size, increments) and steps four cells per iteration:
 // the round-1 loop re-loaded W/H from the constant bank inside a predicate chain and took ~130 cycles per
 // cell (24 us for 720 rays); this one is bounded by the f32 add -> compare dependency of the error term.
 // `walk_only` (GMS_UPDATE_SORTED) stops after the walk: k_ray_keys + sort + k_apply_runs take over.
+constexpr int kRaysPerCta = 8;
 __global__ void __launch_bounds__(256) k_ray_integrate(const double2* __restrict__ all_xy, int B, int Bpad,
                                                        const Stats* __restrict__ st,
                                                        uint32_t* __restrict__ ray_cells, int cap,
@@ -944,7 +1146,7 @@ __global__ void __launch_bounds__(256) k_ray_integrate(const double2* __restrict
                                                        CellCounts* __restrict__ counts, uint32_t* __restrict__ dirty,
                                                        uint32_t* __restrict__ stale_bitmap, int stale_words,
                                                        int walk_only, Geometry g) {
-    __shared__ int s_len[32];
+    __shared__ int s_len[kRaysPerCta];
     __shared__ int s_max;
     const int tid = threadIdx.x;
     // the dirty-tile buffer the refresh of THIS step consumed (host double buffering) is re-armed here: this
@@ -957,43 +1159,54 @@ __global__ void __launch_bounds__(256) k_ray_integrate(const double2* __restrict
     const Xform t(p.x, p.y, p.z);
     const float sx = (float)((t.tx(0.0, 0.0) - g.posx) / g.res);
     const float sy = (float)((t.ty(0.0, 0.0) - g.posy) / g.res);
-    const int b0 = blockIdx.x * 32;
+    const int b0 = blockIdx.x * kRaysPerCta;
     if (tid < 32) {
         const int b = b0 + tid;
         int c = 0;
-        if (b < B) {
+        if (tid < kRaysPerCta && b < B) {
             const double2 m = all_xy[b];
             const float ex = (float)((t.tx(m.x, m.y) - g.posx) / g.res);
             const float ey = (float)((t.ty(m.x, m.y) - g.posy) / g.res);
             if (b == 0) *ray_start = make_float2(sx, sy);
             RayIter it;
             it.init(sx + 0.5f, sy + 0.5f, ex + 0.5f, ey + 0.5f, g.extra_steps);
-            const unsigned uW = (unsigned)g.W, uH = (unsigned)g.H;
             int x = it.x, y = it.y, n = min(it.n, cap);
             const int xi = it.x_inc, yi = it.y_inc;
             const float dx = it.dx, dy = it.dy;
             float err = it.error;
             const int fx = x, fy = y;
-            int lx = x, ly = y;
             uint32_t* out = ray_cells + b;
-            bool live = n > 0;
-            while (live) {
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    live = live && n > 0 && (unsigned)x < uW && (unsigned)y < uH;  // RayIterator.hasNext
-                    if (live) {
-                        out[(size_t)c * Bpad] = (uint32_t)x | ((uint32_t)y << 16);
-                        lx = x; ly = y;
-                        c++;
-                        const bool up = err > 0.0f;  // RayIterator.next
-                        y += up ? yi : 0;
-                        x += up ? 0 : xi;
-                        err += up ? -dx : dy;
-                        n--;
-                    }
-                }
+            // A step moves one cell along one axis, so the first min(room to the map border) + 1 cells cannot be
+            // out of bounds: they are walked without the bounds test (RayIterator.hasNext reduces to n > 0), the
+            // loop is then bounded by the f32 compare -> select -> add chain of the error term alone.
+            int n_fast = 0;
+            if ((unsigned)x < (unsigned)g.W && (unsigned)y < (unsigned)g.H) {
+                const int room_x = xi > 0 ? g.W - 1 - x : (xi < 0 ? x : 0x3fffffff);
+                const int room_y = yi > 0 ? g.H - 1 - y : (yi < 0 ? y : 0x3fffffff);
+                n_fast = min(n, min(room_x, room_y) + 1);
             }
-            if (c > 0) {
+#pragma unroll 4
+            for (int k = 0; k < n_fast; k++) {
+                out[(size_t)k * Bpad] = (uint32_t)x | ((uint32_t)y << 16);
+                const bool up = err > 0.0f;  // RayIterator.next
+                y += up ? yi : 0;
+                x += up ? 0 : xi;
+                err += up ? -dx : dy;
+            }
+            c = n_fast;
+            n -= n_fast;
+            while (n > 0 && (unsigned)x < (unsigned)g.W && (unsigned)y < (unsigned)g.H) {  // RayIterator.hasNext
+                out[(size_t)c * Bpad] = (uint32_t)x | ((uint32_t)y << 16);
+                c++;
+                const bool up = err > 0.0f;
+                y += up ? yi : 0;
+                x += up ? 0 : xi;
+                err += up ? -dx : dy;
+                n--;
+            }
+            if (c > 0) {  // the walk is monotone in x and y: its box is spanned by the first and the last cell
+                const uint32_t last = out[(size_t)(c - 1) * Bpad];
+                const int lx = (int)(last & 0xffffu), ly = (int)(last >> 16);
                 int* r = reinterpret_cast<int*>(rect);
                 atomicMin(r + 0, min(fx, lx));
                 atomicMin(r + 1, min(fy, ly));
@@ -1001,8 +1214,10 @@ __global__ void __launch_bounds__(256) k_ray_integrate(const double2* __restrict
                 atomicMax(r + 3, max(fy, ly));
             }
         }
-        if (b < Bpad) ray_count[b] = c;
-        s_len[tid] = c;
+        if (tid < kRaysPerCta) {
+            if (b < Bpad) ray_count[b] = c;
+            s_len[tid] = c;
+        }
         int mx = c;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -1013,18 +1228,30 @@ __global__ void __launch_bounds__(256) k_ray_integrate(const double2* __restrict
     }
     __syncthreads();  // also orders warp 0's global stores before the other warps' loads (same CTA)
     if (walk_only) return;
-    const int total = s_max * 32;
-    for (int e = tid; e < total; e += 256) {
-        const int k = e >> 5, j = e & 31;
-        if (k >= s_len[j]) continue;
-        const int b = b0 + j;
-        const uint32_t cell = ray_cells[(size_t)k * Bpad + b];
-        const int cx = (int)(cell & 0xffffu), cy = (int)(cell >> 16);
-        const float dX = sx - ((float)cx + 0.5f);
-        const float dY = sy - ((float)cy + 0.5f);
-        const float dist = __fsqrt_rn(dX * dX + dY * dY);
-        const int cls = inverse_sensor_class(dist, meas[b], hit[b] != 0, g.tol_half);
-        if (cls != 0) bump_cell(counts, dirty, cx, cy, cls, g);
+    const int total = s_max * kRaysPerCta;
+    for (int e0 = tid; e0 < total; e0 += 4 * 256) {
+        uint32_t cell[4];
+        int bb[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {  // four independent loads in flight per thread
+            const int e = e0 + u * 256;
+            const int k = e / kRaysPerCta, j = e % kRaysPerCta;
+            bb[u] = -1;
+            if (e < total && k < s_len[j]) {
+                bb[u] = b0 + j;
+                cell[u] = __ldcg(ray_cells + (size_t)k * Bpad + bb[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (bb[u] < 0) continue;
+            const int cx = (int)(cell[u] & 0xffffu), cy = (int)(cell[u] >> 16);
+            const float dX = sx - ((float)cx + 0.5f);
+            const float dY = sy - ((float)cy + 0.5f);
+            const float dist = __fsqrt_rn(dX * dX + dY * dY);
+            const int cls = inverse_sensor_class(dist, meas[bb[u]], hit[bb[u]] != 0, g.tol_half);
+            if (cls != 0) bump_cell(counts, dirty, cx, cy, cls, g);
+        }
     }
 }
 
@@ -1150,10 +1377,12 @@ __device__ __forceinline__ void block_argmax_1024(double& best, int& bi, double*
 // size, on which CTA handled a tile, on the scoring kernel's processing order, or on how many ranks share the
 // particle set (run-to-run, rank-to-rank bit-identical).
 //   phase 0  (multi-rank peer exchange) wait until every rank's log-weights of exchange `seq` have landed
-//   phase 1  M = max lw, first arg-max (SLAM.java:110-115 keeps the first maximum: strict >)
-//   phase 2  e_i = exp(lw_i - M), tile sums s_t                      -> S = sum_t s_t
-//   phase 3  w_i = e_i / S (SLAM.java:119-121), tile sums of w, w^2, trunc(w * 2^60)
-//   final    Neff = (sum w)^2 / sum w^2 (SLAM.java:180-190), strongest pose snapshot, resample decision
+//   phase 1  per tile: (max, first arg-max, sum exp(lw - tile max)); ONE grid barrier; every CTA then folds the
+//            tile partials in tile order -> M (SLAM.java:110-115 keeps the first maximum: strict >) and
+//            S = sum_t s_t * exp(m_t - M)
+//   phase 2  w_i = exp(lw_i - M) / S (SLAM.java:119-121), tile sums of w, w^2, trunc(w * 2^60)
+//   final    (last CTA to finish) Neff = (sum w)^2 / sum w^2 (SLAM.java:180-190), strongest pose snapshot,
+//            resample decision
 struct NormArgs {
     const double* lw;    // all P log-weights (own array, or the peer-exchange receive buffer)
     double* lw_store;    // peer exchange: the received values are also filed in the handle's own lw array (else null)
@@ -1172,66 +1401,54 @@ __global__ void __launch_bounds__(1024) k_norm_coop(NormArgs a) {
     __shared__ int s_idx[32];
     __shared__ double s_d[32];
     __shared__ unsigned long long s_u[32];
+    __shared__ bool s_last;
     const int tid = threadIdx.x, G = gridDim.x;
     if (a.xflags) {
-        if (blockIdx.x == 0 && tid < a.nranks) {
+        if (tid < a.nranks) {  // every CTA polls for itself: no extra grid barrier
             unsigned long long v = 0;
             long long spins = 0;
             for (; spins < 8000000; spins++) {  // ~4 s with the sleeps: never hang the device
                 asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.xflags + tid) : "memory");
                 if (v >= a.seq) break;
-                __nanosleep(500);
+                __nanosleep(200);
             }
             if (v < a.seq) a.st->xerror = 1;
         }
-        __threadfence();
-        grid.sync();
-        // the flag acquire of CTA 0 + the grid barrier order every CTA's loads after the peers' stores
-        if (*(volatile int*)&a.st->xerror) return;
+        __syncthreads();  // the acquiring threads' view is handed to the whole CTA
     }
-    // phase 1
-    double best = kNegInf;
-    int bi = 0x7fffffff;
+    // phase 1: per fixed tile, (max, first arg-max, sum exp(lw - tile max))
     for (int t = blockIdx.x; t < a.ntiles; t += G) {
         const int i = t * 1024 + tid;
-        if (i < a.P) {
-            const double v = __ldcg(a.lw + i);
-            if (v > best) { best = v; bi = i; }  // tiles ascend: a later equal value never replaces
-        }
+        const double v = i < a.P ? __ldcg(a.lw + i) : kNegInf;
+        if (a.lw_store && i < a.P) a.lw_store[i] = v;
+        double best = v;
+        int bi = i < a.P ? i : 0x7fffffff;
+        block_argmax_1024(best, bi, s_key, s_idx);
+        const double e = i < a.P ? exp(v - best) : 0.0;
+        const double sum = block_reduce_1024(e, SumOp(), s_d);
+        if (tid == 0) { a.np.m[t] = best; a.np.idx[t] = bi; a.np.s[t] = sum; }
     }
-    block_argmax_1024(best, bi, s_key, s_idx);
-    if (tid == 0) { a.np.m[blockIdx.x] = best; a.np.idx[blockIdx.x] = bi; }
+    __threadfence();
     grid.sync();
-    best = kNegInf; bi = 0x7fffffff;
-    for (int c = tid; c < G; c += 1024) {
+    if (*(volatile int*)&a.st->xerror) return;  // uniform: set (if at all) before the barrier
+    // every CTA combines the tile partials in the same fixed order -> (M, first arg-max, S)
+    double best = kNegInf;
+    int bi = 0x7fffffff;
+    for (int c = tid; c < a.ntiles; c += 1024) {
         const double v = __ldcg(a.np.m + c);
         const int vi = __ldcg(a.np.idx + c);
         if (v > best || (v == best && vi < bi)) { best = v; bi = vi; }
     }
     block_argmax_1024(best, bi, s_key, s_idx);
-    // phase 2
-    for (int t = blockIdx.x; t < a.ntiles; t += G) {
-        const int i = t * 1024 + tid;
-        double e = 0.0;
-        if (i < a.P) {
-            const double v = __ldcg(a.lw + i);
-            if (a.lw_store) a.lw_store[i] = v;
-            e = exp(v - best);
-            a.w[i] = e;
-        }
-        const double sum = block_reduce_1024(e, SumOp(), s_d);
-        if (tid == 0) a.np.s[t] = sum;
-    }
-    grid.sync();
     double acc = 0.0;
-    for (int c = tid; c < a.ntiles; c += 1024) acc += __ldcg(a.np.s + c);
+    for (int c = tid; c < a.ntiles; c += 1024) acc += __ldcg(a.np.s + c) * exp(__ldcg(a.np.m + c) - best);
     const double S = block_reduce_1024(acc, SumOp(), s_d);
-    // phase 3
+    // phase 2: w_i = exp(lw_i - M) / S, tile sums of w, w^2, trunc(w * 2^60)
     for (int t = blockIdx.x; t < a.ntiles; t += G) {
         const int i = t * 1024 + tid;
         double wi = 0.0;
         if (i < a.P) {
-            wi = a.w[i] / S;
+            wi = exp(__ldcg(a.lw + i) - best) / S;
             a.w[i] = wi;
         }
         const double ws = block_reduce_1024(wi, SumOp(), s_d);
@@ -1239,8 +1456,14 @@ __global__ void __launch_bounds__(1024) k_norm_coop(NormArgs a) {
         const unsigned long long fx = block_reduce_1024((unsigned long long)(wi * 0x1p60), SumU64(), s_u);
         if (tid == 0) { a.np.ws[t] = ws; a.np.q[t] = q; a.np.fx[t] = fx; }
     }
-    grid.sync();
-    if (blockIdx.x != 0) return;
+    // the last CTA to finish folds the tile sums (fixed order) and publishes the step's statistics
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(a.np.counter, 1u) == (unsigned)G - 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
     double sa = 0.0, sq = 0.0;
     for (int c = tid; c < a.ntiles; c += 1024) {
         sa += __ldcg(a.np.ws + c);
@@ -1260,6 +1483,7 @@ __global__ void __launch_bounds__(1024) k_norm_coop(NormArgs a) {
         const float4 p = a.poses.at(bi);
         st->strongest_pose[0] = p.x; st->strongest_pose[1] = p.y; st->strongest_pose[2] = p.z;
         st->do_resample = a.policy == 2 || (a.policy == 1 && neff < (double)(a.P / 2));  // GridMapApp.java:185
+        *a.np.counter = 0u;
     }
 }
 
@@ -1843,6 +2067,9 @@ __global__ void k_fill_dirty(uint32_t* dirty, int nslots, int tile_words, int nt
     const int wi = i % tile_words;
     const int left = ntiles - wi * 32;
     dirty[i] = left >= 32 ? 0xffffffffu : (left > 0 ? (1u << left) - 1u : 0u);
+}
+__global__ void k_fill_f64(double* a, size_t n, double v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = v;
 }
 __global__ void k_fill_rect(int4* rect, int S, int4 v) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;

@@ -87,6 +87,59 @@ def test_accepted_fast_index_equals_java(W):
     assert accepted > 2000 and rejected > 200, (accepted, rejected)  # both branches exercised
 
 
+def fast_index_v2(m, cinv, sinv, pq, k, magic, marg, sign, lp):
+    """One coordinate of k_score_sorted<G, 2>: the magic constant is folded into the per-particle offset, the
+    fraction test runs on (i + margin) * 2^(32-k) mod 2^32, the range test is one compare of the low word."""
+    pqm = pq + magic  # rounded to a multiple of 2^-k once per particle
+    t = fma(m[0], cinv, fma(-m[1], sinv, pqm)) if sign > 0 else fma(m[0], sinv, fma(m[1], cinv, pqm))
+    i = struct.unpack("<Q", struct.pack("<d", t))[0] & 0xFFFFFFFF
+    u = (i * (1 << (32 - k)) + (marg << (32 - k))) & 0xFFFFFFFF
+    ok = u >= ((2 * marg) << (32 - k)) and i < (1 << (k + lp))
+    return ok, i >> k
+
+
+@pytest.mark.parametrize("W", [120, 400, 1024, 2048, 4096, 16384])
+def test_accepted_fast_index_v2_equals_java(W):
+    """The ALU-lean variant: an accepted index equals Java's truncation, inside or outside the map (cells of the
+    padded square beyond the map hold 1.0), for every pose the per-particle range guard lets through."""
+    rng = np.random.default_rng(1000 + W)
+    res = f32(0.05)
+    inv_res = 1.0 / res
+    posx = f32(-W * 0.05 / 2)
+    k, magic, hi, marg = geometry(W)
+    lp = max(1, (W - 1).bit_length())
+    lim = float(1 << (31 - k)) - 2.0
+    accepted = rejected = guarded = 0
+    for n in range(3000):
+        theta = f32(rng.uniform(-math.pi, math.pi))
+        c, s = f32(math.cos(theta)), f32(math.sin(theta))
+        px = f32(rng.uniform(-0.7, 0.7) * W * 0.05)  # poses well outside the map too
+        reach = min(30.0, 0.6 * W * 0.05)
+        m = [float(rng.uniform(-reach, reach)), float(rng.uniform(-reach, reach))]
+        for sign in (+1, -1):
+            def java_q(mm):
+                t = mm[0] * c - mm[1] * s + px if sign > 0 else mm[0] * s + mm[1] * c + px
+                return (t - posx) / res
+            if n % 2 and abs(c if sign > 0 else s) > 0.2:
+                target = round(java_q(m)) + float(rng.choice([0.0, 1e-13, -1e-13, 1e-10, -1e-10, 1e-7, -1e-7, 5e-5, -5e-5,
+                                                               7e-5, -7e-5, 2e-5, -2e-5]))
+                m[0] += (target - java_q(m)) * res / (c if sign > 0 else s)
+            qj = java_q(m)
+            cinv, sinv, pq = c * inv_res, s * inv_res, (px - posx) * inv_res
+            R = math.sqrt(m[0] * m[0] + m[1] * m[1]) * inv_res * 1.000001 + 2.0
+            if not (abs(pq) + R < lim):
+                guarded += 1  # the kernel takes the exact path for every beam of such a particle
+                continue
+            ok, cell = fast_index_v2(m, cinv, sinv, pq, k, magic, marg, sign, lp)
+            if ok:
+                accepted += 1
+                assert cell == d2i(qj) and 0 <= qj, (W, theta, px, m, qj)
+                assert cell < (1 << lp)
+            else:
+                rejected += 1
+    assert accepted > 1500 and rejected > 200, (accepted, rejected, guarded)
+
+
 def test_guarded_reciprocal_cell_of():
     """cell_of() of csrc/device_math.cuh (k_score, per-particle maps): trunc(t * (1/res)) is used only when it lies
     more than 1e-5 from both neighbouring integers; then it must equal Java's (int) (t / res)."""
