@@ -121,8 +121,9 @@ struct gms_handle {
     bool resample_partial = false;
     double partial_u01 = 0;
     unsigned long long partial_count = 0;
-    int map_win_words = 26000;  // per-particle map update: cells of the shared-memory window (GMS_MAP_WIN_WORDS; 0 =
-                                // the global-atomic kernel).  26000 x 4 B = 104 KB: two CTAs per SM
+    int map_win_words = 0;      // per-particle map update: cells of the shared-memory window of k_map_update_win
+                                // (GMS_MAP_WIN_WORDS, e.g. 13000 = 52 KB: four CTAs per SM); 0 = the global-atomic
+                                // kernel (default: see DESIGN.md for the measurements)
     int score_g = 0;  // sub-threads per particle in k_score_sorted (0 = automatic; GMS_SCORE_G overrides: tuning knob)
     int score_v = 0;  // index-validation variant of k_score_sorted (GMS_SCORE_V=1: ALU-lean form, same results)
     int num_sms = 148;
@@ -435,7 +436,7 @@ int launch_pack(gms_handle* h, BeamSet& b, const double* d_xy, const double* d_d
 int launch_blur(gms_handle* h, const CellCounts* counts, double* lik, double* fac, const int2* list, SelfList sl,
                 long long max_tiles, bool allow_tma) {
     const int k = h->g.khalf, th = kTileH + 2 * k, tw = (kTileW + 2 * k + 3) & ~3;
-    const size_t smem = (size_t)th * kTileW * 8 + (size_t)th * tw * 4;
+    const size_t smem = (size_t)th * kTileW * 8 + (size_t)th * tw * 4 + (sl.bitmap ? (size_t)(sl.nwords + 1) * 4 : 0);
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(max_tiles, (long long)h->num_sms * 6));
     if (allow_tma && h->lik_tma) {
         const size_t smem_t = 2 * (((size_t)kTmaTileW * kTmaTileH * 8 + 127) / 128 * 128) + smem;
@@ -499,7 +500,9 @@ int launch_score(gms_handle* h, const BeamSet& b, const float4* pose, int lo, in
         const unsigned grid = blocks_for((long long)cnt * G, 128);
 #define SCORE_G(GG)                                                                                            \
     case GG:                                                                                                   \
-        return h->score_v == 2   ? launch_score_sorted<GG, 2>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
+        return h->score_v == 4   ? launch_score_sorted<GG, 4>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
+               : h->score_v == 3 ? launch_score_sorted<GG, 3>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
+               : h->score_v == 2 ? launch_score_sorted<GG, 2>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
                : h->score_v == 1 ? launch_score_sorted<GG, 1>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
                                  : launch_score_sorted<GG, 0>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal);
         switch (G) {
@@ -573,7 +576,7 @@ int launch_map_update(gms_handle* h, const BeamSet& b, const float4* pose, int l
     if (B <= 0) return GMS_OK;
     Phase ph(h, GMS_PHASE_MAP_UPDATE);
     if (h->map_win_words > 0) {  // one CTA per (particle, quadrant): shared-memory accumulation + coalesced flush
-        LAUNCH(GMS_PHASE_MAP_UPDATE, k_map_update_win<<<(unsigned)cnt * 4u, 128, (size_t)h->map_win_words * 4, h->stream>>>(
+        LAUNCH(GMS_PHASE_MAP_UPDATE, k_map_update_win<<<(unsigned)cnt * 4u, kWinThreads, (size_t)h->map_win_words * 4, h->stream>>>(
                                          pose, lo, cnt, b.xy, b.meas, b.hit, B, h->counts, slot, h->rect, h->dirty,
                                          h->map_win_words, h->g));
         return GMS_OK;
@@ -1118,7 +1121,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->sort.rank, (size_t)h->cnt * 4));
     CKC(cudaMalloc((void**)&h->sort.order, (size_t)h->cnt * 4));
     h->ntiles = (h->P + 1023) / 1024;
-    if (const char* e = std::getenv("GMS_SCORE_V")) h->score_v = std::max(0, std::min(2, std::atoi(e)));
+    if (const char* e = std::getenv("GMS_SCORE_V")) h->score_v = std::max(0, std::min(4, std::atoi(e)));
     if (const char* e = std::getenv("GMS_MAP_WIN_WORDS")) h->map_win_words = std::max(0, std::min(56000, std::atoi(e)));
     CKC(cudaFuncSetAttribute(k_map_update_win, cudaFuncAttributeMaxDynamicSharedMemorySize, 56000 * 4));
     if (const char* e = std::getenv("GMS_SCORE_G")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) h->score_g = v; }

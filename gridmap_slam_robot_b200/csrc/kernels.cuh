@@ -415,12 +415,13 @@ __global__ void __launch_bounds__(256) k_likelihood(const CellCounts* __restrict
                                                     const int2* __restrict__ list, const Stats* __restrict__ st,
                                                     SelfList sl, Geometry g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_pref[kSelfListWords + 1];
     const int k = KH ? KH : g.khalf;
     const int tw = KH ? ((kTileW + 2 * KH + 3) & ~3) : kTileW + 2 * k;  // KH: rows padded to 16 bytes
     const int th = kTileH + 2 * k;
     double* s_h = reinterpret_cast<double*>(smem_raw);               // th * kTileW
     float* s_t = reinterpret_cast<float*>(s_h + th * kTileW);        // th * tw
+    int* s_pref = reinterpret_cast<int*>(s_t + th * tw);             // self-list launches only: nwords + 1 (the host
+                                                                     // adds the bytes; keeps 3 CTAs/SM otherwise)
     const int tid = threadIdx.x;
     const int num_tiles = sl.bitmap ? self_list_build(sl, s_pref) : st->num_tiles;
     const size_t cells = (size_t)g.W * g.H;
@@ -553,11 +554,11 @@ __global__ void __launch_bounds__(256) k_likelihood_tma(const __grid_constant__ 
     constexpr int tw = (kTileW + 2 * KH + 3) & ~3, th = kTileH + 2 * KH;
     extern __shared__ __align__(128) unsigned char smem_tma[];
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ int s_pref[kSelfListWords + 1];
     constexpr int kRawBytes = (kTmaTileW * kTmaTileH * 8 + 127) & ~127;
     // two raw buffers: the TMA request of the NEXT tile is in flight while this tile is blurred
     double* s_h = reinterpret_cast<double*>(smem_tma + 2 * kRawBytes);  // th * kTileW
     float* s_t = reinterpret_cast<float*>(s_h + th * kTileW);           // th * tw
+    int* s_pref = reinterpret_cast<int*>(s_t + th * tw);                // self-list launches only (host adds the bytes)
     const int tid = threadIdx.x;
     const int num_tiles = sl.bitmap ? self_list_build(sl, s_pref) : st->num_tiles;
     const size_t cells = (size_t)g.W * g.H;
@@ -771,13 +772,15 @@ __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, 
 // 0 = mask / subtract / compare per coordinate (measured, default); 1 = ALU-lean form — the margin is a power
 // of two, so "fraction within margin of an integer" is ((i + margin) & M) == 0, x and y share one unsigned min
 // and one LOP3 covers both high-word tests (GMS_SCORE_V=1; the ALU pipe is this kernel's busiest).
+// V = 3 / 4: the code of V = 2 / 0 compiled for 8 resident CTAs per SM (<= 64 registers) instead of 5-6.
 template <int G, int V = 0>
-__global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__ pose, int lo, int cnt,
+__global__ void __launch_bounds__(128, V >= 3 ? 8 : 1) k_score_sorted(const float4* __restrict__ pose, int lo, int cnt,
                                                       const double2* __restrict__ hit_xy,
                                                       const int* __restrict__ num_hit, const double* __restrict__ fac,
                                                       const int* __restrict__ order, double* __restrict__ lw,
                                                       ExchangeRec* __restrict__ xlocal,
                                                       const double* __restrict__ rmax2, Geometry g) {
+    constexpr int K = V == 3 ? 2 : (V == 4 ? 0 : V);  // which index-validation code
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
     double2* s_xy = reinterpret_cast<double2*>(smem_raw);
@@ -851,7 +854,7 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
     // (poses thousands of cells outside the map) takes the exact path for every beam.
     const double pqxm = pqx + g.fx_magic, pqym = pqy + g.fx_magic;
     bool fast_ok = true;
-    if constexpr (V == 2) {
+    if constexpr (K == 2) {
         const double R = sqrt(*rmax2) * g.inv_res * 1.000001 + 2.0;
         const double lim = (double)(1u << (31 - fk)) - 2.0;
         fast_ok = fabs(pqx) + R < lim && fabs(pqy) + R < lim;  // NaN poses fail too
@@ -861,14 +864,14 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
     const unsigned bound = 1u << (fk + g.fac_lp);  // (ix | iy) below it  <=>  both cells inside the padded square
     auto peel = [&]() { peel_exponent(mant, exp2); };
     int b0 = 0, it = 0;
-    const int nfast = (V == 2 && !fast_ok) ? 0 : nhe;
+    const int nfast = (K == 2 && !fast_ok) ? 0 : nhe;
     for (; b0 + 8 * G <= nfast; b0 += 8 * G, it++) {
         unsigned idx[8];
         unsigned bad = 0;
         // branch-free fast path for 8 beams (their dependency chains interleave); beams whose q~ is too
         // close to an integer are only flagged here and redone exactly below.  End points outside the
         // map read the sentinel fac[W*H] == 1.0 (GridMap.java:276: such beams do not multiply).
-        if constexpr (V == 2) {
+        if constexpr (K == 2) {
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const double2 m = s_xy[b0 + u * G + gsub];
@@ -894,7 +897,7 @@ __global__ void __launch_bounds__(128) k_score_sorted(const float4* __restrict__
             const int ix = __double2loint(tx), iy = __double2loint(ty);
             const unsigned gx = (unsigned)ix >> fk, gy = (unsigned)iy >> fk;
             bool ok;
-            if constexpr (V == 1) {
+            if constexpr (K == 1) {
                 // fmarg is a power of two (Geometry): frac in [fmarg, 2^k - fmarg)  <=>  ((i + fmarg) & fnear) != 0
                 const unsigned hi = ((unsigned)__double2hiint(tx) ^ (unsigned)g.fx_hi) |
                                     ((unsigned)__double2hiint(ty) ^ (unsigned)g.fx_hi);
@@ -987,20 +990,23 @@ __global__ void __launch_bounds__(128) k_map_update(const float4* __restrict__ p
 // roofline, DRAM traffic 2.3x the algorithmic bytes because every non-horizontal DDA step lands in a new 32-byte
 // sector).  A map is only ever written by its own particle, so the increments of one scan can be combined on
 // chip first: the rays of one quadrant all start in the same cell and move monotonically away from it, so they
-// live in a rectangle anchored at the start cell.  The CTA keeps that rectangle in shared memory as one u32
-// per cell (low half: free increments, high half: occupied increments; a ray visits a cell at most 3 times,
-// 3 * GMS_MAX_BEAMS < 65536), walks its rays with shared-memory atomics, and then flushes the rectangle with
-// plain, coalesced 8-byte read-modify-writes (old pair in, new pair out, dirty-tile marking from the two
-// thresholded codes).  Cells beyond the rectangle (window capacity: `win_words` cells) fall back to the global
-// atomic.  Integer accumulation: the result is independent of the order => deterministic, identical to the
-// atomic kernel's.
-__global__ void __launch_bounds__(128) k_map_update_win(const float4* __restrict__ pose, int lo, int cnt,
-                                                        const double2* __restrict__ all_xy,
-                                                        const float* __restrict__ meas,
-                                                        const uint8_t* __restrict__ hit, int B,
-                                                        CellCounts* __restrict__ counts, const int* __restrict__ slot,
-                                                        int4* __restrict__ rect, uint32_t* __restrict__ dirty,
-                                                        int win_words, Geometry g) {
+// live in a rectangle anchored at the start cell.  The CTA tiles that rectangle into windows of `win_words`
+// cells; per window it zeroes a shared-memory array of one u32 per cell (low half: free increments, high half:
+// occupied increments; a ray visits a cell at most 3 times, 3 * GMS_MAX_BEAMS < 65536), re-walks its rays (the
+// DDA is a handful of instructions per cell; a ray leaves the loop as soon as it is past the window in either
+// axis) accumulating with shared-memory atomics, and flushes the window with plain, coalesced 8-byte
+// read-modify-writes (old pair in, new pair out, dirty-tile marking from the two thresholded codes).  No global
+// atomics except on the start row / column, which neighbouring quadrants share.  Integer accumulation: the
+// result is independent of the order => deterministic, identical to the atomic kernel's.
+constexpr int kWinThreads = 256;
+__global__ void __launch_bounds__(kWinThreads, 4) k_map_update_win(const float4* __restrict__ pose, int lo, int cnt,
+                                                                const double2* __restrict__ all_xy,
+                                                                const float* __restrict__ meas,
+                                                                const uint8_t* __restrict__ hit, int B,
+                                                                CellCounts* __restrict__ counts,
+                                                                const int* __restrict__ slot, int4* __restrict__ rect,
+                                                                uint32_t* __restrict__ dirty, int win_words,
+                                                                Geometry g) {
     extern __shared__ __align__(16) uint32_t s_win[];
     __shared__ int s_reach[2];
     __shared__ int s_box[4];
@@ -1017,7 +1023,7 @@ __global__ void __launch_bounds__(128) k_map_update_win(const float4* __restrict
     const float sy = (float)((t.ty(0.0, 0.0) - g.posy) / g.res);
     const int x0 = java_d2i(floor((double)(sx + 0.5f))), y0 = java_d2i(floor((double)(sy + 0.5f)));  // RayIter.init
     if (tid == 0) {
-        s_reach[0] = 0; s_reach[1] = 0;
+        s_reach[0] = -1; s_reach[1] = -1;
         s_box[0] = 0x7fffffff; s_box[1] = 0x7fffffff; s_box[2] = -1; s_box[3] = -1;
     }
     __syncthreads();
@@ -1033,7 +1039,7 @@ __global__ void __launch_bounds__(128) k_map_update_win(const float4* __restrict
     };
     // pass A: how far do this quadrant's rays reach (cells, clipped to the map)?  A ray makes |dfloor x| steps in
     // x and |dfloor y| in y to its end point, plus at most `extra_steps` more in either axis.
-    for (int b = tid; b < B; b += 128) {
+    for (int b = tid; b < B; b += kWinThreads) {
         RayIter it;
         if (!ray_of(b, it) || !it.has_next(g.W, g.H)) continue;
         const int lim_x = qx > 0 ? g.W - 1 - x0 : x0, lim_y = qy > 0 ? g.H - 1 - y0 : y0;
@@ -1041,84 +1047,94 @@ __global__ void __launch_bounds__(128) k_map_update_win(const float4* __restrict
         atomicMax(&s_reach[1], min(ry + g.extra_steps, lim_y));
     }
     __syncthreads();
-    // window: [0, WX) x [0, WY) cells in the quadrant's own coordinates (lx = (x - x0) * qx, ly likewise)
-    int WX = s_reach[0] + 1, WY = s_reach[1] + 1;
-    if ((long long)WX * WY > win_words) {
+    const int RX = s_reach[0] + 1, RY = s_reach[1] + 1;  // the quadrant's rectangle: [0, RX) x [0, RY) in (wx, wy)
+    if (RX <= 0) return;                                  // no ray of this quadrant starts inside the map
+    // window shape: as square as the rectangle allows
+    int WX, WY;
+    {
         int sq = 1;
         while ((sq + 1) * (sq + 1) <= win_words) sq++;
-        if (WX <= sq) WY = win_words / WX;
-        else if (WY <= sq) WX = win_words / WY;
-        else { WX = sq; WY = win_words / sq; }
+        if (RX <= sq) { WX = RX; WY = min(RY, win_words / WX); }
+        else if (RY <= sq) { WY = RY; WX = min(RX, win_words / WY); }
+        else { WX = sq; WY = sq; }
     }
-    const int nwin = WX * WY;
-    for (int i = tid; i < nwin; i += 128) s_win[i] = 0u;
-    __syncthreads();
-    // pass B: walk, accumulate on chip
-    for (int b = tid; b < B; b += 128) {
-        RayIter it;
-        if (!ray_of(b, it) || !it.has_next(g.W, g.H)) continue;
-        const float ms = meas[b];
-        const bool wh = hit[b] != 0;
-        const int fx = it.x, fy = it.y;
-        int lx_ = it.x, ly_ = it.y;
-        while (it.has_next(g.W, g.H)) {
-            lx_ = it.x; ly_ = it.y;
-            const float dX = sx - ((float)lx_ + 0.5f);
-            const float dY = sy - ((float)ly_ + 0.5f);
-            const float dist = __fsqrt_rn(dX * dX + dY * dY);
-            const int cls = inverse_sensor_class(dist, ms, wh, g.tol_half);
-            if (cls != 0) {
-                const int wx = (lx_ - x0) * qx, wy = (ly_ - y0) * qy;
-                if ((unsigned)wx < (unsigned)WX && (unsigned)wy < (unsigned)WY)
-                    atomicAdd(&s_win[wy * WX + wx], cls == 1 ? 1u : 65536u);
-                else
-                    bump_cell(map, bitmap, lx_, ly_, cls, g);
+    for (int oy = 0; oy < RY; oy += WY)
+        for (int ox = 0; ox < RX; ox += WX) {
+            const int wxe = min(ox + WX, RX), wye = min(oy + WY, RY);  // window = [ox, wxe) x [oy, wye)
+            const int ww = wxe - ox, nwin = ww * (wye - oy);
+            for (int i = tid; i < nwin; i += kWinThreads) s_win[i] = 0u;
+            __syncthreads();
+            for (int b = tid; b < B; b += kWinThreads) {
+                RayIter it;
+                if (!ray_of(b, it)) continue;
+                if (rx + g.extra_steps < ox || ry + g.extra_steps < oy) continue;  // ends before this window begins
+                const float ms = meas[b];
+                const bool wh = hit[b] != 0;
+                int lx_ = it.x, ly_ = it.y;
+                bool finished = true, any = false;
+                while (it.has_next(g.W, g.H)) {
+                    lx_ = it.x; ly_ = it.y;
+                    any = true;
+                    const int wx = (lx_ - x0) * qx, wy = (ly_ - y0) * qy;
+                    if (wx >= wxe || wy >= wye) { finished = false; break; }  // past the window for good (monotone walk)
+                    if (wx >= ox && wy >= oy) {
+                        const float dX = sx - ((float)lx_ + 0.5f);
+                        const float dY = sy - ((float)ly_ + 0.5f);
+                        const float dist = __fsqrt_rn(dX * dX + dY * dY);
+                        const int cls = inverse_sensor_class(dist, ms, wh, g.tol_half);
+                        if (cls != 0) atomicAdd(&s_win[(wy - oy) * ww + (wx - ox)], cls == 1 ? 1u : 65536u);
+                    }
+                    it.advance();
+                }
+                if (finished && any) {  // this window holds the ray's last cell: its box for the explored rectangle
+                    atomicMin(&s_box[0], min(x0, lx_)); atomicMin(&s_box[1], min(y0, ly_));
+                    atomicMax(&s_box[2], max(x0, lx_)); atomicMax(&s_box[3], max(y0, ly_));
+                }
             }
-            it.advance();
-        }
-        atomicMin(&s_box[0], min(fx, lx_)); atomicMin(&s_box[1], min(fy, ly_));
-        atomicMax(&s_box[2], max(fx, lx_)); atomicMax(&s_box[3], max(fy, ly_));
-    }
-    __syncthreads();
-    // flush: plain coalesced read-modify-write of the cells this scan touched (rows of the window are
-    // contiguous in the map, forwards or backwards).  The start row and column (wx == 0 or wy == 0) are shared
-    // with the neighbouring quadrants' CTAs, which flush concurrently: those cells take one 64-bit atomic each.
-    for (int i0 = tid; i0 < nwin; i0 += 4 * 128) {
-        uint32_t inc[4];
-        size_t idx[4];
-        unsigned long long old[4];
-        bool axis[4];
+            __syncthreads();
+            // flush: plain coalesced read-modify-write of the cells this scan touched (rows of the window are
+            // contiguous in the map, forwards or backwards).  The start row and column (wx == 0 or wy == 0) are
+            // shared with the neighbouring quadrants' CTAs, which flush concurrently: one 64-bit atomic each.
+            for (int i0 = tid; i0 < nwin; i0 += 8 * kWinThreads) {
+                uint32_t inc[8];
+                int cx[8], cy[8];
+                unsigned long long old[8];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int i = i0 + u * 128;
-            inc[u] = i < nwin ? s_win[i] : 0u;
-            axis[u] = false;
-            if (inc[u]) {
-                const int wy = i / WX, wx = i - wy * WX;
-                idx[u] = (size_t)(x0 + wx * qx) + (size_t)(y0 + wy * qy) * g.W;
-                axis[u] = wx == 0 || wy == 0;
-                const unsigned long long add = (unsigned long long)(inc[u] & 0xffffu) | ((unsigned long long)(inc[u] >> 16) << 32);
-                if (axis[u]) old[u] = atomicAdd(reinterpret_cast<unsigned long long*>(map + idx[u]), add);
-                else old[u] = __ldcg(reinterpret_cast<const unsigned long long*>(map + idx[u]));
-            }
-        }
+                for (int u = 0; u < 8; u++) {
+                    const int i = i0 + u * kWinThreads;
+                    inc[u] = i < nwin ? s_win[i] : 0u;
+                    if (inc[u]) {
+                        const int yy = i / ww, xx = i - yy * ww;
+                        const int wx = ox + xx, wy = oy + yy;
+                        cx[u] = x0 + wx * qx; cy[u] = y0 + wy * qy;
+                        unsigned long long* cell = reinterpret_cast<unsigned long long*>(map + ((size_t)cx[u] + (size_t)cy[u] * g.W));
+                        if (wx == 0 || wy == 0) {
+                            old[u] = atomicAdd(cell, (unsigned long long)(inc[u] & 0xffffu) | ((unsigned long long)(inc[u] >> 16) << 32));
+                            cx[u] |= 0x40000000;  // already stored
+                        } else {
+                            old[u] = __ldcg(cell);
+                        }
+                    }
+                }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (!inc[u]) continue;
-            const uint32_t of = (uint32_t)old[u], oo = (uint32_t)(old[u] >> 32);
-            const uint32_t nf = of + (inc[u] & 0xffffu), no = oo + (inc[u] >> 16);
-            if (!axis[u])
-                __stcg(reinterpret_cast<unsigned long long*>(map + idx[u]), (unsigned long long)nf | ((unsigned long long)no << 32));
-            bool flip;
-            if (oo == 0 && no == 0) flip = of == 0;                 // never occupied: flips on its first free hit
-            else if (of == 0 && nf == 0) flip = oo == 0;            // never freed: flips on its first occupied hit
-            else flip = cell_code(of, oo, g) != cell_code(nf, no, g);
-            if (flip) {
-                const int wy = (i0 + u * 128) / WX, wx = (i0 + u * 128) - wy * WX;
-                mark_dirty(bitmap, x0 + wx * qx, y0 + wy * qy, g);
+                for (int u = 0; u < 8; u++) {
+                    if (!inc[u]) continue;
+                    const bool stored = (cx[u] & 0x40000000) != 0;
+                    const int x = cx[u] & 0x3fffffff, y = cy[u];
+                    const uint32_t of = (uint32_t)old[u], oo = (uint32_t)(old[u] >> 32);
+                    const uint32_t nf = of + (inc[u] & 0xffffu), no = oo + (inc[u] >> 16);
+                    if (!stored)
+                        __stcg(reinterpret_cast<unsigned long long*>(map + ((size_t)x + (size_t)y * g.W)),
+                               (unsigned long long)nf | ((unsigned long long)no << 32));
+                    bool flip;
+                    if (oo == 0 && no == 0) flip = of == 0;       // never occupied: flips on its first free hit
+                    else if (of == 0 && nf == 0) flip = oo == 0;  // never freed: flips on its first occupied hit
+                    else flip = cell_code(of, oo, g) != cell_code(nf, no, g);
+                    if (flip) mark_dirty(bitmap, x, y, g);
+                }
             }
+            __syncthreads();
         }
-    }
     if (tid == 0 && s_box[2] >= 0) {
         int* r = reinterpret_cast<int*>(rect + s);
         atomicMin(r + 0, s_box[0]); atomicMin(r + 1, s_box[1]);
