@@ -33,9 +33,17 @@ struct PhaseSpan {
 
 // one scan on the device: the table as uploaded + what k_pack_beams derives from it
 struct BeamSet {
+    unsigned char* blob = nullptr;  // one allocation [xy | dist | hit]: a host scan arrives with ONE H2D copy
+    int cap = 0;
     double2* xy = nullptr;     // {localX, localY} of every beam (private copy: the map integration reads it later)
     double* dist = nullptr;    // Measurement.distance (metres)
-    uint8_t* hit = nullptr;    // wasHit
+    uint8_t* hit = nullptr;    // wasHit     (xy / dist / hit are views into blob: packed for B beams after an
+                               //             upload, at the capacity offsets otherwise)
+    void view(int B) {
+        xy = reinterpret_cast<double2*>(blob);
+        dist = reinterpret_cast<double*>(blob + (size_t)B * 16);
+        hit = blob + (size_t)B * 24;
+    }
     float* meas = nullptr;     // (float) distance / resolution (GridMap.java:188)
     double2* hit_xy = nullptr; // compacted hit beams (scoring reads only those, GridMap.java:269-270)
     int* num_hit = nullptr;
@@ -116,6 +124,7 @@ struct gms_handle {
     double* wp_part = nullptr;
     unsigned* wp_counter = nullptr;
     bool tile_fx_valid = false;
+    bool wpose_valid = false;  // Stats.weighted_pose is current (computed inside the normalise / resample kernels)
     // multi-rank shared map: the step's resampling selects only this rank's children; the rest is selected
     // lazily if a getter asks for the full arrays before the next step (which overwrites them anyway)
     bool resample_partial = false;
@@ -280,7 +289,7 @@ int java_d2i_host(double d) {
 }
 
 void free_beamset(BeamSet& b) {
-    cudaFree(b.xy); cudaFree(b.dist); cudaFree(b.hit); cudaFree(b.meas); cudaFree(b.hit_xy); cudaFree(b.num_hit);
+    cudaFree(b.blob); cudaFree(b.meas); cudaFree(b.hit_xy); cudaFree(b.num_hit);
     cudaFree(b.rmax2);
     b = BeamSet{};
 }
@@ -352,9 +361,9 @@ int stage_release(gms_handle* h, int slot) {  // after the last copy from the sl
 }
 
 int alloc_beamset(gms_handle* h, BeamSet& b, int cap) {
-    CK(cudaMalloc((void**)&b.xy, (size_t)cap * 16));
-    CK(cudaMalloc((void**)&b.dist, (size_t)cap * 8));
-    CK(cudaMalloc((void**)&b.hit, (size_t)cap));
+    CK(cudaMalloc((void**)&b.blob, (size_t)cap * 25));
+    b.cap = cap;
+    b.view(cap);
     CK(cudaMalloc((void**)&b.meas, (size_t)cap * 4));
     CK(cudaMalloc((void**)&b.hit_xy, (size_t)cap * 16));
     CK(cudaMalloc((void**)&b.num_hit, 4));
@@ -624,6 +633,7 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
     int rc = ensure_beams(h, B);  // grow the beam tables (if needed) while every stream can still be drained from here
     if (rc) return rc;
     BeamSet& bs = cur_beams(h);
+    if (d_xy != (const double*)bs.xy) bs.view(bs.cap);  // device-resident scan: private copies at the capacity offsets
     if (fork) {  // likelihood refresh of the shared map: independent of the beams and of the motion update
         cudaStream_t main = h->stream;
         CK(cudaEventRecord(h->ev_fork_a, main));
@@ -712,6 +722,7 @@ SelectArgs select_args(gms_handle* h, int from, int to, double u01, unsigned lon
     a.w_in = h->w[from]; a.lw_in = h->lw[from];
     a.pose_out = h->pose[to]; a.w_out = h->w[to]; a.lw_out = h->lw[to];
     a.m_begin = m_begin; a.m_count = m_count;
+    a.wp_part = nullptr; a.wp_counter = nullptr;
     return a;
 }
 
@@ -747,11 +758,17 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
             if (!h->tile_fx_valid)  // tile sums of trunc(w * 2^60): by-product of k_norm_coop / k_neff
                 LAUNCH(GMS_PHASE_RESAMPLE, k_neff<<<h->ntiles, 1024, 0, h->stream>>>(h->w[h->cur], P, h->ntiles, h->np, h->st));
             SelectArgs a = select_args(h, h->cur, nxt, u01, h->resample_count, m_begin, m_count);
+            if (!local_only) {  // the whole new generation passes through this launch: weighted pose for free
+                a.wp_part = h->wp_part;
+                a.wp_counter = h->wp_counter;
+            }
+            h->wpose_valid = !local_only;
             const unsigned long long* fx = h->np.fx;
             int ntiles = h->ntiles;
             const unsigned grid = (unsigned)std::max(1, std::min(h->num_sms, std::max(ntiles, (m_count + 1023) / 1024)));
             LAUNCH_COOP(GMS_PHASE_RESAMPLE, k_resample_coop, grid, 1024, 0, &a, &fx, &ntiles);
         } else {
+            h->wpose_valid = false;
             LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_literal<<<1, 32, 0, h->stream>>>(h->w[h->cur], P, (double*)h->cdf, h->st));
             int rc = launch_select(h, h->cur, nxt, u01, h->resample_count, m_begin, m_count);
             if (rc) return rc;
@@ -824,6 +841,9 @@ int step_end(gms_handle* h, int policy, double u01) {
         a.lw = lw_src; a.lw_store = lw_src == h->lw[h->cur] ? nullptr : h->lw[h->cur];
         a.w = h->w[h->cur]; a.poses = pose_table(h, h->cur); a.P = h->P; a.ntiles = h->ntiles; a.policy = policy;
         a.np = h->np; a.st = h->st; a.xflags = xflags; a.nranks = c.nranks; a.seq = h->xseq;
+        a.pose_local = (c.nranks == 1 || !h->direct) ? h->pose[h->cur] : nullptr;
+        a.wp_part = h->wp_part;
+        h->wpose_valid = a.pose_local != nullptr;
         const unsigned grid = (unsigned)std::max(1, std::min(h->ntiles, h->num_sms));
         LAUNCH_COOP(GMS_PHASE_NORMALISE, k_norm_coop, grid, 1024, 0, &a);
         h->tile_fx_valid = true;
@@ -878,9 +898,8 @@ int upload_beams(gms_handle* h, BeamSet& b, const double* xy, const double* dist
         std::memcpy(s, xy, (size_t)B * 16);
         std::memcpy(s + (size_t)B * 16, dist ? (const void*)dist : (const void*)xy, (size_t)B * 8);
         std::memcpy(s + (size_t)B * 24, hit, (size_t)B);
-        CK(cudaMemcpyAsync(b.xy, s, (size_t)B * 16, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(b.dist, s + (size_t)B * 16, (size_t)B * 8, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(b.hit, s + (size_t)B * 24, (size_t)B, cudaMemcpyHostToDevice, h->stream));
+        b.view(B);  // [xy | dist | hit] packed for B beams: one copy
+        CK(cudaMemcpyAsync(b.blob, s, (size_t)B * 25, cudaMemcpyHostToDevice, h->stream));
     }
     if (normals) {
         std::memcpy(s + off_n, normals, (size_t)h->cnt * 16);
@@ -912,7 +931,7 @@ int do_reset(gms_handle* h) {
     h->cur = 0; h->slot_cur = 0;
     h->step = 0; h->resample_count = 0;
     h->have_update = false; h->pending = false; h->stats_valid = false; h->tile_fx_valid = false;
-    h->resample_partial = false;
+    h->resample_partial = false; h->wpose_valid = false;
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }
@@ -1247,9 +1266,12 @@ EXPORT int gms_get_weighted_pose(gms_handle* h, float pose[3]) {
     ENTER(h);
     { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!pose) return GMS_ERR_INVALID_ARG;
-    LAUNCH(GMS_PHASE_NORMALISE, k_weighted_pose<<<h->ntiles, 1024, 0, h->stream>>>(
-                                    h->w[h->cur], h->pose[h->cur], h->P, h->ntiles, h->wp_part, h->wp_counter, h->st));
-    h->stats_valid = false;
+    if (!h->wpose_valid) {  // otherwise the last normalise / resample launch already produced it
+        LAUNCH(GMS_PHASE_NORMALISE, k_weighted_pose<<<h->ntiles, 1024, 0, h->stream>>>(
+                                        h->w[h->cur], h->pose[h->cur], h->P, h->ntiles, h->wp_part, h->wp_counter, h->st));
+        h->stats_valid = false;
+        h->wpose_valid = true;
+    }
     int rc = fetch_stats(h);
     if (rc) return rc;
     std::memcpy(pose, h->h_st->weighted_pose, 3 * sizeof(float));
@@ -1339,6 +1361,7 @@ EXPORT int gms_set_poses(gms_handle* h, const float* xyt) {
     LAUNCH(GMS_PHASE_COUNT - 1,
            k_pose_pack<<<blocks_for(h->P, 256), 256, 0, h->stream>>>((const float*)h->d_tmp, h->pose[h->cur], h->P));
     CK(cudaStreamSynchronize(h->stream));
+    h->wpose_valid = false;
     return GMS_OK;
 }
 EXPORT int gms_set_weights(gms_handle* h, const double* w) {
@@ -1348,6 +1371,7 @@ EXPORT int gms_set_weights(gms_handle* h, const double* w) {
     CK(cudaMemcpyAsync(h->w[h->cur], w, (size_t)h->P * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->tile_fx_valid = false;
+    h->wpose_valid = false;
     return GMS_OK;
 }
 EXPORT int gms_set_map_counts(gms_handle* h, int32_t particle, const uint32_t* nf, const uint32_t* no) {
@@ -1625,6 +1649,7 @@ int upload_raw_and_deskew(gms_handle* h, BeamSet& b, const double* angle, const 
     unsigned char* s = nullptr;
     int slot = 0;
     if ((rc = stage_acquire(h, off_n + (normals ? (size_t)h->cnt * 16 : 0) + 64, &s, &slot))) return rc;
+    b.view(b.cap);
     if (B > 0) {
         std::memcpy(s, angle, (size_t)B * 8);
         std::memcpy(s + (size_t)B * 8, dist, (size_t)B * 8);

@@ -1144,14 +1144,14 @@ __global__ void __launch_bounds__(kWinThreads, 4) k_map_update_win(const float4*
 
 // Shared map (one scan per step, only B rays): the DDA of a ray is inherently sequential (f32 error term,
 // RayIterator.java:112-130), but the per-cell work (sqrt, inverse sensor model, counter update) is not.
-// k_ray_integrate does both in ONE launch: a CTA owns 8 consecutive rays (90 CTAs for 720 beams); 8 lanes of warp 0
+// k_ray_integrate does both in ONE launch: a CTA owns 4 consecutive rays (180 CTAs for 720 beams); 4 lanes of warp 0
 // walk them in lockstep and record the cells {x | y << 16} (cell k of ray b at ray_cells[k * Bpad + b]), then all 8
 // warps classify and accumulate the CTA's (cell, ray) pairs in parallel, four independent loads per thread.
 // The walk loop keeps everything in registers (grid size, increments) and steps four cells per iteration:
 // the round-1 loop re-loaded W/H from the constant bank inside a predicate chain and took ~130 cycles per
 // cell (24 us for 720 rays); this one is bounded by the f32 add -> compare dependency of the error term.
 // `walk_only` (GMS_UPDATE_SORTED) stops after the walk: k_ray_keys + sort + k_apply_runs take over.
-constexpr int kRaysPerCta = 8;
+constexpr int kRaysPerCta = 4;
 __global__ void __launch_bounds__(256) k_ray_integrate(const double2* __restrict__ all_xy, int B, int Bpad,
                                                        const Stats* __restrict__ st,
                                                        uint32_t* __restrict__ ray_cells, int cap,
@@ -1247,7 +1247,8 @@ __global__ void __launch_bounds__(256) k_ray_integrate(const double2* __restrict
     const int total = s_max * kRaysPerCta;
     for (int e0 = tid; e0 < total; e0 += 4 * 256) {
         uint32_t cell[4];
-        int bb[4];
+        int bb[4], cls[4];
+        unsigned long long old[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {  // four independent loads in flight per thread
             const int e = e0 + u * 256;
@@ -1259,15 +1260,22 @@ __global__ void __launch_bounds__(256) k_ray_integrate(const double2* __restrict
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 4; u++) {  // ... then four independent atomics (the returned pair is only needed below)
+            cls[u] = 0;
             if (bb[u] < 0) continue;
             const int cx = (int)(cell[u] & 0xffffu), cy = (int)(cell[u] >> 16);
             const float dX = sx - ((float)cx + 0.5f);
             const float dY = sy - ((float)cy + 0.5f);
             const float dist = __fsqrt_rn(dX * dX + dY * dY);
-            const int cls = inverse_sensor_class(dist, meas[bb[u]], hit[bb[u]] != 0, g.tol_half);
-            if (cls != 0) bump_cell(counts, dirty, cx, cy, cls, g);
+            cls[u] = inverse_sensor_class(dist, meas[bb[u]], hit[bb[u]] != 0, g.tol_half);
+            if (cls[u] != 0)
+                old[u] = atomicAdd(reinterpret_cast<unsigned long long*>(counts + ((size_t)cx + (size_t)cy * g.W)),
+                                   cls[u] == 1 ? 1ull : (1ull << 32));
         }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (cls[u] != 0 && code_flips((uint32_t)old[u], (uint32_t)(old[u] >> 32), cls[u], g))
+                mark_dirty(dirty, (int)(cell[u] & 0xffffu), (int)(cell[u] >> 16), g);
     }
 }
 
@@ -1363,6 +1371,26 @@ __device__ __forceinline__ T block_reduce_1024(T v, Op op, T* s_buf) {
     for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// N sums at once over a 1024-thread block (one shared-memory exchange instead of N): fixed tree, result in every thread
+template <int N>
+__device__ __forceinline__ void block_sum_vec_1024(double (&v)[N], double* s_buf /* 32 * N */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; k++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < N; k++) s_buf[k * 32 + wid] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        v[k] = s_buf[k * 32 + lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+}
 struct SumOp { __device__ double operator()(double a, double b) const { return a + b; } };
 struct SumU64 { __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a + b; } };
 
@@ -1410,12 +1438,15 @@ struct NormArgs {
     const unsigned long long* xflags;  // nullptr unless the peer exchange is active
     int nranks;
     unsigned long long seq;
+    const float4* pose_local;  // all P poses in local memory (single rank / imported records), else nullptr: the
+    double* wp_part;           // weighted pose (SLAM.getWeightedPose) then comes out of this kernel too
 };
 __global__ void __launch_bounds__(1024) k_norm_coop(NormArgs a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double s_key[32];
     __shared__ int s_idx[32];
     __shared__ double s_d[32];
+    __shared__ double s_v[5 * 32];
     __shared__ unsigned long long s_u[32];
     __shared__ bool s_last;
     const int tid = threadIdx.x, G = gridDim.x;
@@ -1463,14 +1494,22 @@ __global__ void __launch_bounds__(1024) k_norm_coop(NormArgs a) {
     for (int t = blockIdx.x; t < a.ntiles; t += G) {
         const int i = t * 1024 + tid;
         double wi = 0.0;
+        double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // w, w^2, w*x, w*y, w*angleConstrain(theta)
         if (i < a.P) {
             wi = exp(__ldcg(a.lw + i) - best) / S;
             a.w[i] = wi;
+            v[0] = wi; v[1] = wi * wi;
+            if (a.pose_local) {  // SLAM.getWeightedPose SLAM.java:165-178
+                const float4 p = a.pose_local[i];
+                v[2] = (double)p.x * wi; v[3] = (double)p.y * wi; v[4] = angle_constrain((double)p.z) * wi;
+            }
         }
-        const double ws = block_reduce_1024(wi, SumOp(), s_d);
-        const double q = block_reduce_1024(wi * wi, SumOp(), s_d);
+        block_sum_vec_1024<5>(v, s_v);
         const unsigned long long fx = block_reduce_1024((unsigned long long)(wi * 0x1p60), SumU64(), s_u);
-        if (tid == 0) { a.np.ws[t] = ws; a.np.q[t] = q; a.np.fx[t] = fx; }
+        if (tid == 0) {
+            a.np.ws[t] = v[0]; a.np.q[t] = v[1]; a.np.fx[t] = fx;
+            if (a.pose_local) { a.wp_part[4 * t] = v[2]; a.wp_part[4 * t + 1] = v[3]; a.wp_part[4 * t + 2] = v[4]; }
+        }
     }
     // the last CTA to finish folds the tile sums (fixed order) and publishes the step's statistics
     if (tid == 0) {
@@ -1480,15 +1519,23 @@ __global__ void __launch_bounds__(1024) k_norm_coop(NormArgs a) {
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    double sa = 0.0, sq = 0.0;
+    double f[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     for (int c = tid; c < a.ntiles; c += 1024) {
-        sa += __ldcg(a.np.ws + c);
-        sq += __ldcg(a.np.q + c);
+        f[0] += __ldcg(a.np.ws + c);
+        f[1] += __ldcg(a.np.q + c);
+        if (a.pose_local) {
+            f[2] += __ldcg(a.wp_part + 4 * c); f[3] += __ldcg(a.wp_part + 4 * c + 1); f[4] += __ldcg(a.wp_part + 4 * c + 2);
+        }
     }
-    sa = block_reduce_1024(sa, SumOp(), s_d);
-    sq = block_reduce_1024(sq, SumOp(), s_d);
+    block_sum_vec_1024<5>(f, s_v);
+    const double sa = f[0], sq = f[1];
     if (tid == 0) {
         Stats* st = a.st;
+        if (a.pose_local) {
+            st->weighted_pose[0] = (float)(f[2] / sa);
+            st->weighted_pose[1] = (float)(f[3] / sa);
+            st->weighted_pose[2] = (float)(f[4] / sa);
+        }
         const double neff = (sa * sa) / sq;
         st->neff = neff;
         st->lw_max = best;
@@ -1639,6 +1686,8 @@ struct SelectArgs {
     double* w_out;
     double* lw_out;
     int m_begin, m_count;  // children [m_begin, m_begin + m_count)
+    double* wp_part;       // k_resample_coop selecting ALL children: SLAM.getWeightedPose of the new generation comes
+    unsigned* wp_counter;  // out of the same kernel (tile partials + last-CTA ticket); nullptr otherwise
 };
 __device__ __forceinline__ int select_stride(int P) {
     int stride = 32;
@@ -1647,7 +1696,7 @@ __device__ __forceinline__ int select_stride(int P) {
 }
 template <bool FIXED>
 __device__ __forceinline__ void select_child(const SelectArgs& a, int m0, const unsigned long long* s_coarse, int stride,
-                                             int ncoarse, double u01) {
+                                             int ncoarse, double u01, float4& pose_o, double& w_o) {
     using Key = typename std::conditional<FIXED, unsigned long long, double>::type;
     const int P = a.P;
     const double r = u01 * 1.0 / (double)P;
@@ -1672,8 +1721,10 @@ __device__ __forceinline__ void select_child(const SelectArgs& a, int m0, const 
         if (key > __ldcg(cdf + mid)) lo = mid + 1; else hi = mid;
     }
     a.parents[m0] = lo;
-    a.pose_out[m0] = a.poses_in.at(lo);
-    a.w_out[m0] = a.w_in[lo];
+    pose_o = a.poses_in.at(lo);
+    w_o = a.w_in[lo];
+    a.pose_out[m0] = pose_o;
+    a.w_out[m0] = w_o;
     a.lw_out[m0] = __ldcg(a.lw_in + lo);
     // the strongest particle of the last update lives on as its FIRST child (slam.py / gms_get_strongest)
     const int sb = a.st->strongest;
@@ -1703,7 +1754,9 @@ __global__ void __launch_bounds__(256) k_select(SelectArgs a) {
         return;
     }
     const double u01 = a.u01 < 0.0 ? philox_uniform(a.seed, a.resample_count) : a.u01;
-    select_child<FIXED>(a, m0, s_coarse, stride, ncoarse, u01);
+    float4 po;
+    double wo;
+    select_child<FIXED>(a, m0, s_coarse, stride, ncoarse, u01, po, wo);
 }
 
 // FIXED mode: CDF + selection in ONE cooperative launch.
@@ -1716,6 +1769,8 @@ __global__ void __launch_bounds__(1024) k_resample_coop(SelectArgs a, const unsi
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned long long s_coarse[2048];
     __shared__ unsigned long long s_u[32];
+    __shared__ double s_v[4 * 32];
+    __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, G = gridDim.x;
     if (a.st->xerror) return;        // uniform over the grid
     if (!a.st->do_resample) {        // uniform over the grid: the generation is carried over unchanged
@@ -1758,8 +1813,41 @@ __global__ void __launch_bounds__(1024) k_resample_coop(SelectArgs a, const unsi
     for (int j = tid; j < ncoarse; j += 1024) s_coarse[j] = __ldcg(cdf + min(a.P - 1, (j + 1) * stride - 1));
     __syncthreads();
     const double u01 = a.u01 < 0.0 ? philox_uniform(a.seed, a.resample_count) : a.u01;
-    for (int m0 = a.m_begin + blockIdx.x * 1024 + tid; m0 < a.m_begin + a.m_count; m0 += G * 1024)
-        select_child<true>(a, m0, s_coarse, stride, ncoarse, u01);
+    const int nchunks = (a.m_count + 1023) / 1024;
+    for (int c = blockIdx.x; c < nchunks; c += G) {  // fixed chunks of 1024 children (fixed reduction order)
+        const int m0 = a.m_begin + c * 1024 + tid;
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        if (m0 < a.m_begin + a.m_count) {
+            float4 po;
+            double wo;
+            select_child<true>(a, m0, s_coarse, stride, ncoarse, u01, po, wo);
+            v[0] = (double)po.x * wo; v[1] = (double)po.y * wo; v[2] = angle_constrain((double)po.z) * wo; v[3] = wo;
+        }
+        if (a.wp_part) {
+            block_sum_vec_1024<4>(v, s_v);
+            if (tid == 0) { a.wp_part[4 * c] = v[0]; a.wp_part[4 * c + 1] = v[1]; a.wp_part[4 * c + 2] = v[2]; a.wp_part[4 * c + 3] = v[3]; }
+        }
+    }
+    if (!a.wp_part) return;
+    // SLAM.getWeightedPose of the new generation: the last CTA to finish folds the chunk sums in chunk order
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(a.wp_counter, 1u) == (unsigned)G - 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double f[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int c = tid; c < nchunks; c += 1024)
+#pragma unroll
+        for (int k = 0; k < 4; k++) f[k] += __ldcg(a.wp_part + 4 * c + k);
+    block_sum_vec_1024<4>(f, s_v);
+    if (tid == 0) {
+        a.st->weighted_pose[0] = (float)(f[0] / f[3]);
+        a.st->weighted_pose[1] = (float)(f[1] / f[3]);
+        a.st->weighted_pose[2] = (float)(f[2] / f[3]);
+        *a.wp_counter = 0u;
+    }
 }
 
 // Per-particle maps: slot assignment.  parents[] is non-decreasing, so the first child of a parent is
