@@ -108,6 +108,8 @@ SYMBOLS = {
     "gms_update_raw": [_vp, _vp, _vp, _vp, _i32, _f64, _f64, _vp, _P(_f64)],
     "gms_render_map": [_vp, _i32, _i32, _vp],
     "gms_combined_map": [_vp, _vp, _vp],
+    "gms_combined_map_begin_dev": [_vp, _P(_vp), _P(C.c_size_t)],
+    "gms_combined_map_end": [_vp, _vp, _vp],
 }
 
 
@@ -319,6 +321,16 @@ class Handle:
     def combined_map(self):
         lg, lk = np.zeros((self.H, self.W), np.float64), np.zeros((self.H, self.W), np.float64)
         self._ck(self.dll.gms_combined_map(self.h, _ptr(lg), _ptr(lk)))
+        return lg, lk
+
+    def combined_map_begin(self):
+        ptr, nb = _vp(), C.c_size_t()
+        self._ck(self.dll.gms_combined_map_begin_dev(self.h, C.byref(ptr), C.byref(nb)))
+        return ptr.value, nb.value
+
+    def combined_map_end(self):
+        lg, lk = np.zeros((self.H, self.W), np.float64), np.zeros((self.H, self.W), np.float64)
+        self._ck(self.dll.gms_combined_map_end(self.h, _ptr(lg), _ptr(lk)))
         return lg, lk
 
     # ---- device-resident / multi-rank ----

@@ -111,7 +111,7 @@ struct gms_handle {
     double *raw_angle = nullptr, *raw_dist = nullptr;  // raw sweep for the fused de-skew
     double* d_normals = nullptr;
     // combined-map fusion scratch (allocated on first use)
-    double *comb_log = nullptr, *comb_lik = nullptr;
+    double *comb_prod = nullptr, *comb_log = nullptr, *comb_lik = nullptr;
     CellCounts* comb_sign = nullptr;
     uint32_t* comb_dirty = nullptr;
     int* comb_off = nullptr;
@@ -313,7 +313,7 @@ void free_all(gms_handle* h) {
     cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start); cudaFree(h->ray_maxlen);
     cudaFree(h->sk_keys); cudaFree(h->sk_sorted); cudaFree(h->sk_unique); cudaFree(h->sk_runlen); cudaFree(h->sk_nruns);
     cudaFree(h->sk_temp);
-    cudaFree(h->raw_angle); cudaFree(h->raw_dist); cudaFree(h->comb_log); cudaFree(h->comb_lik); cudaFree(h->comb_sign);
+    cudaFree(h->raw_angle); cudaFree(h->raw_dist); cudaFree(h->comb_prod); cudaFree(h->comb_log); cudaFree(h->comb_lik); cudaFree(h->comb_sign);
     cudaFree(h->comb_dirty); cudaFree(h->comb_off); cudaFree(h->comb_list);
     cudaFree(h->sort.hist); cudaFree(h->sort.chunk_total); cudaFree(h->sort.offs); cudaFree(h->sort.key);
     cudaFree(h->sort.rank); cudaFree(h->sort.order);
@@ -1708,21 +1708,39 @@ EXPORT int gms_render_map(gms_handle* h, int32_t particle, int32_t likelihood, u
     return copy_out(h, abgr_out, h->d_tmp, h->cells * 4);
 }
 
-EXPORT int gms_combined_map(gms_handle* h, double* log_out, double* lik_out) {
+namespace {
+int ensure_combined(gms_handle* h) {
+    if (h->comb_log) return GMS_OK;
+    CK(cudaMalloc((void**)&h->comb_prod, h->cells * 8));
+    CK(cudaMalloc((void**)&h->comb_log, h->cells * 8));
+    CK(cudaMalloc((void**)&h->comb_lik, h->cells * 8));
+    CK(cudaMalloc((void**)&h->comb_sign, h->cells * sizeof(CellCounts)));
+    CK(cudaMalloc((void**)&h->comb_dirty, (size_t)h->g.tile_words * 4));
+    CK(cudaMalloc((void**)&h->comb_off, (size_t)h->g.tile_words * 4));
+    CK(cudaMalloc((void**)&h->comb_list, (size_t)h->tiles_per_map * sizeof(int2)));
+    return GMS_OK;
+}
+}  // namespace
+
+EXPORT int gms_combined_map_begin_dev(gms_handle* h, void** d_product, size_t* bytes) {
     ENTER(h);
-    if (h->cfg.map_mode != GMS_MAP_PER_PARTICLE || h->cfg.nranks != 1)
-        return fail(h, GMS_ERR_UNSUPPORTED, "gms_combined_map: single-rank per-particle maps only");
-    if (!h->comb_log) {
-        CK(cudaMalloc((void**)&h->comb_log, h->cells * 8));
-        CK(cudaMalloc((void**)&h->comb_lik, h->cells * 8));
-        CK(cudaMalloc((void**)&h->comb_sign, h->cells * sizeof(CellCounts)));
-        CK(cudaMalloc((void**)&h->comb_dirty, (size_t)h->g.tile_words * 4));
-        CK(cudaMalloc((void**)&h->comb_off, (size_t)h->g.tile_words * 4));
-        CK(cudaMalloc((void**)&h->comb_list, (size_t)h->tiles_per_map * sizeof(int2)));
-    }
-    LAUNCH(GMS_PHASE_COUNT - 1, k_combine<<<blocks_for((long long)h->cells, 256), 256, 0, h->stream>>>(
-                                    h->counts, h->slot[h->slot_cur], h->P, h->cells, h->g.l_free, h->g.l_occ, h->comb_log,
-                                    h->comb_sign));
+    if (h->cfg.map_mode != GMS_MAP_PER_PARTICLE)
+        return fail(h, GMS_ERR_UNSUPPORTED, "gms_combined_map: per-particle maps only (a shared map is its own fusion)");
+    int rc = ensure_combined(h);
+    if (rc) return rc;
+    LAUNCH(GMS_PHASE_COUNT - 1, k_combine_product<<<blocks_for((long long)h->cells, 256), 256, 0, h->stream>>>(
+                                    h->counts, h->slot[h->slot_cur] + h->lo, h->cnt, h->cells, h->g.l_free, h->g.l_occ,
+                                    h->comb_prod));
+    if (d_product) *d_product = h->comb_prod;
+    if (bytes) *bytes = h->cells * 8;
+    return GMS_OK;
+}
+
+EXPORT int gms_combined_map_end(gms_handle* h, double* log_out, double* lik_out) {
+    ENTER(h);
+    if (!h->comb_prod) return fail(h, GMS_ERR_STATE, "gms_combined_map_end without gms_combined_map_begin_dev");
+    LAUNCH(GMS_PHASE_COUNT - 1, k_combine_finish<<<blocks_for((long long)h->cells, 256), 256, 0, h->stream>>>(
+                                    h->comb_prod, h->cells, h->comb_log, h->comb_sign));
     if (log_out) CK(cudaMemcpyAsync(log_out, h->comb_log, h->cells * 8, cudaMemcpyDeviceToHost, h->stream));
     if (lik_out) {
         // GridMap.computeLikelihoodMap(combinedGrid): the same tile kernel on the sign map
@@ -1739,4 +1757,14 @@ EXPORT int gms_combined_map(gms_handle* h, double* log_out, double* lik_out) {
     h->stats_valid = false;
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
+}
+
+EXPORT int gms_combined_map(gms_handle* h, double* log_out, double* lik_out) {
+    if (!h) return GMS_ERR_INVALID_ARG;
+    if (h->cfg.nranks != 1)
+        return fail(h, GMS_ERR_STATE, "gms_combined_map: multi-rank handles use gms_combined_map_begin_dev, a PRODUCT "
+                                      "all-reduce of the returned buffer over the ranks, gms_combined_map_end");
+    int rc = gms_combined_map_begin_dev(h, nullptr, nullptr);
+    if (rc) return rc;
+    return gms_combined_map_end(h, log_out, lik_out);
 }

@@ -2144,20 +2144,29 @@ __global__ void __launch_bounds__(256) k_render(const CellCounts* __restrict__ c
     out[i] = ((255u << 24) | (c << 16) | (c << 8) | c) & 0xfeffffffu;  // Color.colorToFloatBits
 }
 
-// GridMapApp.calculateCombined GridMapApp.java:439-458 (product in particle order); also emits the
-// pseudo-counts whose sign equals the combined log-odds' sign, so k_likelihood can blur it.
-__global__ void __launch_bounds__(256) k_combine(const CellCounts* __restrict__ counts, const int* __restrict__ slot,
-                                                 int P, size_t cells, double l_free, double l_occ,
-                                                 double* __restrict__ log_out, CellCounts* __restrict__ sign_out) {
+// GridMapApp.calculateCombined GridMapApp.java:439-458 in two steps, so that ranks can multiply their partial
+// products in between (multi-rank: one PRODUCT all-reduce of W*H doubles):
+//   k_combine_product: prod_p (1 - invLogOdds(logData_p)) over the handle's local particles, in particle order
+//   k_combine_finish : logOdds(1 - product) and the pseudo-counts whose sign equals the combined log-odds' sign,
+//                      so the likelihood tile kernel can blur it (GridMap.computeLikelihoodMap(combinedGrid))
+__global__ void __launch_bounds__(256) k_combine_product(const CellCounts* __restrict__ counts, const int* __restrict__ slot,
+                                                         int n_local, size_t cells, double l_free, double l_occ,
+                                                         double* __restrict__ prod_out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cells) return;
     double product = 1.0;
-    for (int p = 0; p < P; p++) {
+    for (int p = 0; p < n_local; p++) {
         const CellCounts c = counts[(size_t)slot[p] * cells + i];
         const double l = (double)c.n_free * l_free + (double)c.n_occ * l_occ;
         product *= 1.0 - inv_log_odds(l);
     }
-    const double odds = 1.0 - product;
+    prod_out[i] = product;
+}
+__global__ void __launch_bounds__(256) k_combine_finish(const double* __restrict__ prod, size_t cells,
+                                                        double* __restrict__ log_out, CellCounts* __restrict__ sign_out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells) return;
+    const double odds = 1.0 - prod[i];
     const double v = log(odds / (1.0 - odds));  // Util.logOdds(double)
     log_out[i] = v;
     sign_out[i] = v > 0.0 ? CellCounts{0u, 1u} : (v < 0.0 ? CellCounts{1u, 0u} : CellCounts{0u, 0u});

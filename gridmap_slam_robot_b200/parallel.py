@@ -73,3 +73,11 @@ class ShardedStepper:
         if self.migrates and policy != B.POLICY_NEVER:
             # stream-ordered barrier: no rank starts the next map update before every pull has finished
             self.dist.all_reduce(self._token)
+
+    def combined_map(self):
+        """GridMapApp.calculateCombined (GridMapApp.java:439-458) over the particles of ALL ranks: every rank
+        multiplies its own particles' factors, one PRODUCT all-reduce of W*H doubles joins them."""
+        ptr, nbytes = self.h.combined_map_begin()
+        prod = wrap_block(ptr, nbytes, self.device).view(torch.float64)
+        self.dist.all_reduce(prod, op=self.dist.ReduceOp.PRODUCT)
+        return self.h.combined_map_end()

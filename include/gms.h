@@ -284,8 +284,15 @@ int gms_update_raw(gms_handle* h, const double* angle, const double* dist, const
 int gms_render_map(gms_handle* h, int32_t particle, int32_t likelihood, uint32_t* abgr_out /* W*H */);
 /* Combined-map fusion, GridMapApp.calculateCombined GridMapApp.java:439-458: per cell
  * logOdds(1 - prod_p (1 - invLogOdds(logData_p))) over all particles, then computeLikelihoodMap of it.
- * Either output may be NULL.  Single-rank, per-particle maps. */
+ * Either output may be NULL.  Per-particle maps. */
 int gms_combined_map(gms_handle* h, double* log_out /* W*H */, double* likelihood_out /* W*H */);
+/* The same fusion when the particles (and their maps) are sharded over ranks: begin leaves the product over the
+ * handle's LOCAL particles, prod_p (1 - invLogOdds(logData_p)), in a device buffer of W*H doubles and returns its
+ * address; the caller multiplies the ranks' buffers element-wise (one PRODUCT all-reduce, e.g. ncclAllReduce with
+ * ncclProd on the handle's stream); end turns the product into the combined log-odds and its likelihood field.
+ * gms_combined_map() is begin + end on a single-rank handle. */
+int gms_combined_map_begin_dev(gms_handle* h, void** d_product, size_t* bytes);
+int gms_combined_map_end(gms_handle* h, double* log_out /* W*H */, double* likelihood_out /* W*H */);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -105,8 +106,24 @@ class SLAM {  // SLAM.java:26-204
     friend struct GridMapData;
     friend class GridMap;
 
+    std::function<void(int, std::vector<Pose>&)> optimizer;
+
     void ck(int rc) const {
         if (rc) throw Error(rc, gms_last_error(h));
+    }
+    static int optimizerTrampoline(void* user, gms_handle*, int32_t first, int32_t count, float* xyt, const double*,
+                                   const double*, const uint8_t*, int32_t, double, double) {
+        SLAM* self = static_cast<SLAM*>(user);
+        try {
+            std::vector<Pose> poses;
+            poses.reserve(count);
+            for (int i = 0; i < count; i++) poses.emplace_back(xyt[3 * i], xyt[3 * i + 1], xyt[3 * i + 2]);
+            self->optimizer(first, poses);
+            for (int i = 0; i < count; i++) { xyt[3 * i] = poses[i].x; xyt[3 * i + 1] = poses[i].y; xyt[3 * i + 2] = poses[i].theta; }
+            return 0;
+        } catch (...) {
+            return 1;  // no C++ exception may unwind through the C frames
+        }
     }
     static void pack(const Observation& z, std::vector<double>& xy, std::vector<double>& d, std::vector<uint8_t>& hit) {
         for (const Measurement& m : z.getMeasurements()) {
@@ -174,6 +191,13 @@ class SLAM {  // SLAM.java:26-204
         return out;
     }
     GridMap& getGridMap() { return gridMap; }  // SLAM.java:200-202
+    // GridMap.findBestPoseOptim (GridMap.java:348-369, called per particle at SLAM.java:97) as a batch hook: `f(first,
+    // poses)` may replace the poses of the particles [first, first + poses.size()) between the motion sample and the
+    // weight.  The reference's own optimiser returns its start pose, so no hook (the default) is the identity.
+    void setPoseOptimizer(std::function<void(int, std::vector<Pose>&)> f) {
+        optimizer = std::move(f);
+        ck(gms_set_pose_optimizer(h, optimizer ? &SLAM::optimizerTrampoline : nullptr, this));
+    }
     std::vector<int32_t> getParents() {        // the index i chosen for each m (SLAM.java:147)
         std::vector<int32_t> p(info.num_particles);
         ck(gms_get_parents(h, p.data()));

@@ -60,6 +60,7 @@ struct gms_handle {
     int32_t strongest_now;        /* where the strongest particle of the last update lives now (first child) */
     float strongest_pose[3];      /* its pose / weight at that update (Java keeps the Particle object) */
     double strongest_w;
+    double *comb_prod;            /* combined-map fusion: product over the local particles */
     gms_pose_optimizer_fn opt_fn; /* A4 hook: GridMap.findBestPoseOptim (default NULL = identity) */
     void *opt_user;
     uint64_t step, resample_count;
@@ -436,7 +437,7 @@ static void free_handle(gms_handle *h) {
         if (h->nocc) free(h->nocc[s]);
     }
     free(h->logd); free(h->lik); free(h->nfree); free(h->nocc);
-    free(h->prob_scratch); free(h->tmp_scratch);
+    free(h->prob_scratch); free(h->tmp_scratch); free(h->comb_prod);
     free(h->xlocal); free(h->xglobal);
     free(h->pend_xy); free(h->pend_dist); free(h->pend_hit);
     free(h);
@@ -1149,21 +1150,39 @@ EXPORT int gms_render_map(gms_handle *h, int32_t particle, int32_t likelihood, u
     return GMS_OK;
 }
 /* GridMapApp.calculateCombined GridMapApp.java:439-458 */
-EXPORT int gms_combined_map(gms_handle *h, double *log_out, double *lik_out) {
+EXPORT int gms_combined_map_begin_dev(gms_handle *h, void **d_product, size_t *bytes) {
     if (!h) return GMS_ERR_INVALID_ARG;
-    if (h->cfg.map_mode != GMS_MAP_PER_PARTICLE || h->cfg.nranks != 1)
-        return fail(h, GMS_ERR_UNSUPPORTED, "gms_combined_map: single-rank per-particle maps only");
+    if (h->cfg.map_mode != GMS_MAP_PER_PARTICLE)
+        return fail(h, GMS_ERR_UNSUPPORTED, "gms_combined_map: per-particle maps only");
+    size_t n = (size_t)h->W * h->H;
+    if (!h->comb_prod) h->comb_prod = malloc(n * sizeof(double));
+    if (!h->comb_prod) return fail(h, GMS_ERR_OOM, "out of memory (combined map)");
+    for (size_t i = 0; i < n; i++) { /* GridMapApp.java:447-452, particle order */
+        double product = 1;
+        for (int p = 0; p < h->cnt; p++) product *= 1 - inv_log_odds(h->logd[h->slot[p]][i]);
+        h->comb_prod[i] = product;
+    }
+    if (d_product) *d_product = h->comb_prod;
+    if (bytes) *bytes = n * sizeof(double);
+    return GMS_OK;
+}
+EXPORT int gms_combined_map_end(gms_handle *h, double *log_out, double *lik_out) {
+    if (!h) return GMS_ERR_INVALID_ARG;
+    if (!h->comb_prod) return fail(h, GMS_ERR_STATE, "gms_combined_map_end without begin");
     if (!ensure_scratch(h)) return fail(h, GMS_ERR_OOM, "out of memory (scratch)");
     size_t n = (size_t)h->W * h->H;
     double *comb = malloc(n * sizeof(double)), *lik = malloc(n * sizeof(double));
-    for (size_t i = 0; i < n; i++) {
-        double product = 1;
-        for (int p = 0; p < h->P; p++) product *= 1 - inv_log_odds(h->logd[h->slot[p]][i]);
-        comb[i] = log_odds(1 - product);
-    }
-    compute_likelihood(h, comb, lik, h->prob_scratch, h->tmp_scratch);
+    for (size_t i = 0; i < n; i++) comb[i] = log_odds(1 - h->comb_prod[i]); /* GridMapApp.java:454 */
+    compute_likelihood(h, comb, lik, h->prob_scratch, h->tmp_scratch);     /* GridMapApp.java:457 */
     if (log_out) memcpy(log_out, comb, n * sizeof(double));
     if (lik_out) memcpy(lik_out, lik, n * sizeof(double));
     free(comb); free(lik);
     return GMS_OK;
+}
+EXPORT int gms_combined_map(gms_handle *h, double *log_out, double *lik_out) {
+    if (!h) return GMS_ERR_INVALID_ARG;
+    if (h->cfg.nranks != 1) return fail(h, GMS_ERR_STATE, "gms_combined_map: multi-rank handles use begin / all-reduce / end");
+    int rc = gms_combined_map_begin_dev(h, NULL, NULL);
+    if (rc) return rc;
+    return gms_combined_map_end(h, log_out, lik_out);
 }

@@ -14,6 +14,11 @@
         }                                                                \
     } while (0)
 
+#define CHECK_VOID(c)                                                    \
+    do {                                                                 \
+        if (!(c)) std::fprintf(stderr, "%s:%d: CHECK failed: %s\n", __FILE__, __LINE__, #c); \
+    } while (0)
+
 int main() {
     // ray (1,1)->(4,2) on a 10x10 grid, hit: F F O O O 0 0
     {
@@ -61,6 +66,24 @@ int main() {
         CHECK(mx > 0.5 && mx <= 1.0 + 1e-12);  // walls have been integrated and blurred
         slam.reset();
         CHECK(std::fabs(slam.calculateNeff() - 40.0) < 1e-9);
+    }
+    // A4: GridMap.findBestPoseOptim (SLAM.java:97) as a hook between the motion sample and the weight
+    {
+        gms::SLAM slam([](gms_config& c) { c.num_particles = 8; });
+        int calls = 0;
+        slam.setPoseOptimizer([&](int first, std::vector<gms::Pose>& poses) {
+            calls++;
+            CHECK_VOID(first == 0 && poses.size() == 8);
+            for (gms::Pose& p : poses) p.x = 0.25f;  // what the hook returns is what gets weighted and integrated
+        });
+        gms::Observation z;
+        for (int b = 0; b < 30; b++) z.addMeasurement(gms::Measurement(2 * M_PI * b / 30, 1.0, true));
+        slam.update(z, gms::Odometry(0.01, 0.0));
+        CHECK(calls == 1);
+        for (const gms::Particle& p : slam.getParticles()) CHECK(p.pose.x == 0.25f);
+        slam.setPoseOptimizer(nullptr);  // back to the identity default
+        slam.update(z, gms::Odometry(0.0, 0.0));
+        CHECK(calls == 1);
     }
     // error behaviour: bad configuration is reported, not aborted on
     try {

@@ -66,7 +66,8 @@ def _worker(rank, world, port, P, steps, beams, q, mode=1, peer=True):
     lo, cnt = h.info.local_begin, h.info.local_count
     mp_ = (0,) if mode == 1 else tuple(range(lo, lo + cnt))
     res = _steps(h, stepper, scans, normals, uniforms, lo, cnt, dev, map_particles=mp_)
-    q.put((rank, res))
+    comb = stepper.combined_map() if mode == 0 else None  # fusion over the particles of all ranks
+    q.put((rank, res, comb))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -87,7 +88,9 @@ def _run(cuda, P, steps, beams, world, mode, peer=True):
     procs = [ctx.Process(target=_worker, args=(r, world, port, P, steps, beams, q, mode, peer)) for r in range(world)]
     for p in procs:
         p.start()
-    results = dict(q.get(timeout=300) for _ in range(world))
+    got = [q.get(timeout=300) for _ in range(world)]
+    results = {r: res for r, res, _ in got}
+    combined = {r: c for r, _, c in got}
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -106,6 +109,12 @@ def _run(cuda, P, steps, beams, world, mode, peer=True):
             for p, (nf, no, lik) in a[4].items():
                 assert np.array_equal(nf, b[4][p][0]) and np.array_equal(no, b[4][p][1]), (r, s, p, "counts")
                 assert np.array_equal(lik, b[4][p][2]), (r, s, p, "likelihood")
+    if mode == 0:  # GridMapApp.calculateCombined over all ranks == over one rank (product order differs: tolerance)
+        lg1, lk1 = h.combined_map()
+        for r in range(world):
+            lg, lk = combined[r]
+            np.testing.assert_allclose(lg, lg1, rtol=1e-9, atol=1e-12)
+            assert np.mean(lk == lk1) > 0.999
     h.close()
 
 
