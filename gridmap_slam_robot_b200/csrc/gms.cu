@@ -509,7 +509,9 @@ int launch_score(gms_handle* h, const BeamSet& b, const float4* pose, int lo, in
         const unsigned grid = blocks_for((long long)cnt * G, 128);
 #define SCORE_G(GG)                                                                                            \
     case GG:                                                                                                   \
-        return h->score_v == 4   ? launch_score_sorted<GG, 4>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
+        return h->score_v == 6   ? launch_score_sorted<GG, 6>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
+               : h->score_v == 5 ? launch_score_sorted<GG, 5>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
+               : h->score_v == 4 ? launch_score_sorted<GG, 4>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
                : h->score_v == 3 ? launch_score_sorted<GG, 3>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
                : h->score_v == 2 ? launch_score_sorted<GG, 2>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
                : h->score_v == 1 ? launch_score_sorted<GG, 1>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
@@ -1140,7 +1142,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->sort.rank, (size_t)h->cnt * 4));
     CKC(cudaMalloc((void**)&h->sort.order, (size_t)h->cnt * 4));
     h->ntiles = (h->P + 1023) / 1024;
-    if (const char* e = std::getenv("GMS_SCORE_V")) h->score_v = std::max(0, std::min(4, std::atoi(e)));
+    if (const char* e = std::getenv("GMS_SCORE_V")) h->score_v = std::max(0, std::min(6, std::atoi(e)));
     if (const char* e = std::getenv("GMS_MAP_WIN_WORDS")) h->map_win_words = std::max(0, std::min(56000, std::atoi(e)));
     CKC(cudaFuncSetAttribute(k_map_update_win, cudaFuncAttributeMaxDynamicSharedMemorySize, 56000 * 4));
     if (const char* e = std::getenv("GMS_SCORE_G")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) h->score_g = v; }

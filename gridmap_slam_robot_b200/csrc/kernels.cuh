@@ -772,15 +772,16 @@ __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, 
 // 0 = mask / subtract / compare per coordinate (measured, default); 1 = ALU-lean form — the margin is a power
 // of two, so "fraction within margin of an integer" is ((i + margin) & M) == 0, x and y share one unsigned min
 // and one LOP3 covers both high-word tests (GMS_SCORE_V=1; the ALU pipe is this kernel's busiest).
-// V = 3 / 4: the code of V = 2 / 0 compiled for 8 resident CTAs per SM (<= 64 registers) instead of 5-6.
+// V = 3 / 4: the code of V = 2 / 0 compiled for 8 resident CTAs per SM (<= 64 registers) instead of 5-6 (measured
+// slower: the spills land in the beam loop).  V = 5: V = 2 with a software-pipelined beam loop.
 template <int G, int V = 0>
-__global__ void __launch_bounds__(128, V >= 3 ? 8 : 1) k_score_sorted(const float4* __restrict__ pose, int lo, int cnt,
+__global__ void __launch_bounds__(128, (V == 3 || V == 4) ? 8 : 1) k_score_sorted(const float4* __restrict__ pose, int lo, int cnt,
                                                       const double2* __restrict__ hit_xy,
                                                       const int* __restrict__ num_hit, const double* __restrict__ fac,
                                                       const int* __restrict__ order, double* __restrict__ lw,
                                                       ExchangeRec* __restrict__ xlocal,
                                                       const double* __restrict__ rmax2, Geometry g) {
-    constexpr int K = V == 3 ? 2 : (V == 4 ? 0 : V);  // which index-validation code
+    constexpr int K = (V == 3 || V == 5 || V == 6) ? 2 : (V == 4 ? 0 : V);  // which index-validation code
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
     double2* s_xy = reinterpret_cast<double2*>(smem_raw);
@@ -865,6 +866,61 @@ __global__ void __launch_bounds__(128, V >= 3 ? 8 : 1) k_score_sorted(const floa
     auto peel = [&]() { peel_exponent(mant, exp2); };
     int b0 = 0, it = 0;
     const int nfast = (K == 2 && !fast_ok) ? 0 : nhe;
+    if constexpr (V == 5 || V == 6) {
+        constexpr int NB = V == 6 ? 4 : 8;  // beams per batch
+        // Software-pipelined form of the K == 2 loop: the eight gathers of batch i+1 are issued BEFORE the products
+        // of batch i are formed, so a warp always has a batch of loads in flight (ncu on the plain loop: 22 %
+        // occupancy at 98 registers, long_scoreboard + wait the top stalls; the loop body is index math ->
+        // 8 loads -> wait -> multiply tree, serialised per warp).
+        auto index8 = [&](int base, unsigned (&idx)[NB]) -> unsigned {
+            unsigned bad = 0;
+#pragma unroll
+            for (int u = 0; u < NB; u++) {
+                const double2 m = s_xy[base + u * G + gsub];
+                const double tx = fma(m.x, cinv, fma(-m.y, sinv, pqxm));
+                const double ty = fma(m.x, sinv, fma(m.y, cinv, pqym));
+                const unsigned ix = (unsigned)__double2loint(tx), iy = (unsigned)__double2loint(ty);
+                const unsigned ux = ix * fmul + fadd, uy = iy * fmul + fadd;
+                const bool ok = min(ux, uy) >= fthr && (ix | iy) < bound;
+                bad |= ok ? 0u : (1u << u);
+                idx[u] = ok ? __umulhi(iy, fmul) * pitch + __umulhi(ix, fmul) : oob;
+            }
+            return bad;
+        };
+        double f[NB];
+        unsigned bad = 0;
+        if (NB * G <= nfast) {
+            unsigned idx[NB];
+            bad = index8(0, idx);
+#pragma unroll
+            for (int u = 0; u < NB; u++) f[u] = __ldg(fac + idx[u]);
+        }
+#pragma unroll 2
+        for (; b0 + NB * G <= nfast; b0 += NB * G, it++) {
+            double fn[NB];
+            unsigned badn = 0;
+            const bool more = b0 + 2 * NB * G <= nfast;
+            if (more) {
+                unsigned idx[NB];
+                badn = index8(b0 + NB * G, idx);
+#pragma unroll
+                for (int u = 0; u < NB; u++) fn[u] = __ldg(fac + idx[u]);
+            }
+            if (bad) {
+#pragma unroll
+                for (int u = 0; u < NB; u++)
+                    if (bad & (1u << u)) f[u] = factor_exact(s_xy[b0 + u * G + gsub]);
+            }
+            if constexpr (NB == 8) mant *= ((f[0] * f[1]) * (f[2] * f[3])) * ((f[4] * f[5]) * (f[6] * f[7]));
+            else mant *= (f[0] * f[1]) * (f[2] * f[3]);
+            if ((it & (64 / NB - 1)) == 64 / NB - 1) peel();
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < NB; u++) f[u] = fn[u];
+                bad = badn;
+            }
+        }
+    } else
     for (; b0 + 8 * G <= nfast; b0 += 8 * G, it++) {
         unsigned idx[8];
         unsigned bad = 0;

@@ -457,14 +457,15 @@ def test_sorted_scoring_validation_variant_many_beams(cuda, oracle, monkeypatch)
     normals, _ = synth.make_draws(2, P)
     kw = dict(num_particles=P, map_width_m=51.2, map_height_m=51.2, origin_x=-25.6, origin_y=-25.6, map_mode=B.MAP_SHARED)
     lws = []
-    for v in ("0", "1", "2"):
+    for v in ("0", "1", "2", "5", "6"):
         monkeypatch.setenv("GMS_SCORE_V", v)
         h = cuda.create(**kw)
         for s, sc in enumerate(scans):
             h.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta, normals[s])
         lws.append(h.log_weights().copy())
         h.close()
-    assert np.array_equal(lws[0], lws[1]) and np.array_equal(lws[0], lws[2])
+    assert np.array_equal(lws[0], lws[1]) and np.array_equal(lws[0], lws[2]) and np.array_equal(lws[0], lws[3])
+    np.testing.assert_allclose(lws[4], lws[0], rtol=0, atol=1e-10)  # 4-beam batches: another product tree
     o = oracle.create(**kw)
     for s, sc in enumerate(scans):
         o.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta, normals[s])
