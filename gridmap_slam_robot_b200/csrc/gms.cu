@@ -84,6 +84,8 @@ struct gms_handle {
     uint32_t* dirty = nullptr;   // dirty-tile bitmap per slot: the PENDING set (read by the next likelihood refresh)
     uint32_t* dirty_alt = nullptr;  // shared map with the self-listing refresh: the buffer the last refresh consumed
     bool alt_needs_clear = false;
+    bool poses_sharded = false;  // peer exchange: the current pose array holds only this rank's block up to date
+    bool dead_dirty_pending = false;  // per-particle maps across ranks: dropped slots still carry dirty bits
     bool self_list = false;      // shared map, bitmap small enough: the refresh builds its own work list
     int* word_off = nullptr;
     int2* tile_list = nullptr;
@@ -125,6 +127,9 @@ struct gms_handle {
     unsigned* wp_counter = nullptr;
     bool tile_fx_valid = false;
     bool wpose_valid = false;  // Stats.weighted_pose is current (computed inside the normalise / resample kernels)
+    bool fold_wpose = false;   // host entry points (gms_update, gms_resample): the caller will ask for the weighted pose
+                               // right away (GridMapApp.java:192), so it is folded into the step's kernels (+3-5 us
+                               // each); the *_dev entry points leave it to gms_get_weighted_pose
     // multi-rank shared map: the step's resampling selects only this rank's children; the rest is selected
     // lazily if a getter asks for the full arrays before the next step (which overwrites them anyway)
     bool resample_partial = false;
@@ -636,6 +641,11 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
     if (rc) return rc;
     BeamSet& bs = cur_beams(h);
     if (d_xy != (const double*)bs.xy) bs.view(bs.cap);  // device-resident scan: private copies at the capacity offsets
+    if (h->dead_dirty_pending) {  // per-particle maps across ranks: see k_drop_dead_dirty
+        LAUNCH(GMS_PHASE_LIKELIHOOD, k_drop_dead_dirty<<<1, 1024, 0, h->stream>>>(h->slot[h->slot_cur] + h->lo, h->cnt, h->S,
+                                                                               h->g.tile_words, h->dirty, h->scratch2p));
+        h->dead_dirty_pending = false;
+    }
     if (fork) {  // likelihood refresh of the shared map: independent of the beams and of the motion update
         cudaStream_t main = h->stream;
         CK(cudaEventRecord(h->ev_fork_a, main));
@@ -714,6 +724,7 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
     h->pending = true;
     h->pend_dtheta = d_theta;
     h->pend_B = B;
+    h->poses_sharded = c.nranks > 1 && h->direct;
     return GMS_OK;
 }
 
@@ -739,10 +750,23 @@ int launch_select(gms_handle* h, int from, int to, double u01, unsigned long lon
     return GMS_OK;
 }
 
+// Peer exchange, no resampling since the last update: every rank holds only its own block of the moved poses; a
+// getter that needs all of them copies the other blocks out of their owners' arrays (peer mappings).  The
+// caller keeps the ranks between steps while it reads (documented in gms.h).
+int materialize_poses(gms_handle* h) {
+    if (!(h->direct && h->poses_sharded)) return GMS_OK;
+    const PoseTable t = pose_table(h, h->cur);
+    LAUNCH(GMS_PHASE_COUNT - 1, k_pose_fill_remote<<<blocks_for(h->P, 256), 256, 0, h->stream>>>(t, h->pose[h->cur], h->lo,
+                                                                                           h->cnt, h->P));
+    h->poses_sharded = false;
+    return GMS_OK;
+}
+
 // the part of a local-only resampling that was skipped (see resample_partial)
 int complete_resample(gms_handle* h) {
     if (!h->resample_partial) return GMS_OK;
     h->resample_partial = false;
+    h->stats_valid = false;  // Stats.strongest_now may be found among the children selected now
     const int from = h->cur ^ 1, to = h->cur;
     int rc = launch_select(h, from, to, h->partial_u01, h->partial_count, 0, h->lo);
     if (rc) return rc;
@@ -760,11 +784,12 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
             if (!h->tile_fx_valid)  // tile sums of trunc(w * 2^60): by-product of k_norm_coop / k_neff
                 LAUNCH(GMS_PHASE_RESAMPLE, k_neff<<<h->ntiles, 1024, 0, h->stream>>>(h->w[h->cur], P, h->ntiles, h->np, h->st));
             SelectArgs a = select_args(h, h->cur, nxt, u01, h->resample_count, m_begin, m_count);
-            if (!local_only) {  // the whole new generation passes through this launch: weighted pose for free
+            const bool fold = !local_only && h->fold_wpose;  // the whole new generation passes through this launch
+            if (fold) {
                 a.wp_part = h->wp_part;
                 a.wp_counter = h->wp_counter;
             }
-            h->wpose_valid = !local_only;
+            h->wpose_valid = fold;
             const unsigned long long* fx = h->np.fx;
             int ntiles = h->ntiles;
             const unsigned grid = (unsigned)std::max(1, std::min(h->num_sms, std::max(ntiles, (m_count + 1023) / 1024)));
@@ -776,6 +801,7 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
             if (rc) return rc;
         }
         h->resample_partial = local_only;
+        h->poses_sharded = false;  // the selection gathers every child it selects (the rest follows in complete_resample)
         h->partial_u01 = u01;
         h->partial_count = h->resample_count;
         h->cur = nxt;
@@ -792,6 +818,7 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
                                        h->slot[nxt], h->dup_src_rank, h->dup_src, h->dup_dst, h->dup_level, h->dirty,
                                        h->g.tile_words, h->scratch2p, h->st));
         h->slot_cur = nxt;
+        h->dead_dirty_pending = true;
         const int chunks = std::max(1, std::min(32, h->H / 16));
         for (int level = 0; level < 2; level++) {  // 0: pulls + copies of old-generation maps, 1: copies of pulled replicas
             LAUNCH(GMS_PHASE_MAP_COPY, k_job_rects<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(
@@ -843,7 +870,7 @@ int step_end(gms_handle* h, int policy, double u01) {
         a.lw = lw_src; a.lw_store = lw_src == h->lw[h->cur] ? nullptr : h->lw[h->cur];
         a.w = h->w[h->cur]; a.poses = pose_table(h, h->cur); a.P = h->P; a.ntiles = h->ntiles; a.policy = policy;
         a.np = h->np; a.st = h->st; a.xflags = xflags; a.nranks = c.nranks; a.seq = h->xseq;
-        a.pose_local = (c.nranks == 1 || !h->direct) ? h->pose[h->cur] : nullptr;
+        a.pose_local = (h->fold_wpose && (c.nranks == 1 || !h->direct)) ? h->pose[h->cur] : nullptr;
         a.wp_part = h->wp_part;
         h->wpose_valid = a.pose_local != nullptr;
         const unsigned grid = (unsigned)std::max(1, std::min(h->ntiles, h->num_sms));
@@ -933,7 +960,7 @@ int do_reset(gms_handle* h) {
     h->cur = 0; h->slot_cur = 0;
     h->step = 0; h->resample_count = 0;
     h->have_update = false; h->pending = false; h->stats_valid = false; h->tile_fx_valid = false;
-    h->resample_partial = false; h->wpose_valid = false;
+    h->resample_partial = false; h->wpose_valid = false; h->dead_dirty_pending = false;
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }
@@ -1229,6 +1256,7 @@ EXPORT int gms_update(gms_handle* h, const double* beam_xy, const double* beam_d
     if (int rc_ = check_beams(h, B, beam_xy, beam_dist, beam_hit, "gms_update")) return rc_;
     if (h->cfg.nranks != 1) return fail(h, GMS_ERR_STATE, "gms_update: multi-rank handles use update_begin/end");
     flip_beams(h);
+    h->fold_wpose = true;
     BeamSet& bs = cur_beams(h);
     int rc = upload_beams(h, bs, beam_xy, beam_dist, beam_hit, B, normals);
     if (rc) return rc;
@@ -1246,6 +1274,7 @@ EXPORT int gms_resample(gms_handle* h, double u01) {
     ENTER(h);
     { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (u01 >= 1.0) return fail(h, GMS_ERR_INVALID_ARG, "gms_resample: u01 must be < 1");
+    h->fold_wpose = true;
     LAUNCH(GMS_PHASE_RESAMPLE, k_set_resample_flag<<<1, 1, 0, h->stream>>>(h->st, 1));
     // SLAM.resample() returns nothing: the work is only enqueued; every getter synchronises before it reads
     return launch_resample(h, u01);
@@ -1269,6 +1298,7 @@ EXPORT int gms_get_weighted_pose(gms_handle* h, float pose[3]) {
     { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!pose) return GMS_ERR_INVALID_ARG;
     if (!h->wpose_valid) {  // otherwise the last normalise / resample launch already produced it
+        { int rc_ = materialize_poses(h); if (rc_) return rc_; }
         LAUNCH(GMS_PHASE_NORMALISE, k_weighted_pose<<<h->ntiles, 1024, 0, h->stream>>>(
                                         h->w[h->cur], h->pose[h->cur], h->P, h->ntiles, h->wp_part, h->wp_counter, h->st));
         h->stats_valid = false;
@@ -1303,6 +1333,7 @@ EXPORT int gms_get_poses(gms_handle* h, float* xyt) {
     ENTER(h);
     { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!xyt) return GMS_ERR_INVALID_ARG;
+    { int rc_ = materialize_poses(h); if (rc_) return rc_; }
     LAUNCH(GMS_PHASE_COUNT - 1,
            k_pose_unpack<<<blocks_for(h->P, 256), 256, 0, h->stream>>>(h->pose[h->cur], (float*)h->d_tmp, h->P));
     CK(cudaMemcpyAsync(xyt, h->d_tmp, (size_t)h->P * 12, cudaMemcpyDeviceToHost, h->stream));
@@ -1515,6 +1546,7 @@ EXPORT int gms_update_begin_dev(gms_handle* h, const double* d_xy, const double*
     ENTER_STEP(h);
     if (int rc_ = check_beams(h, B, d_xy, d_dist, d_hit, "gms_update_begin_dev")) return rc_;
     flip_beams(h);
+    h->fold_wpose = false;
     return step_begin(h, d_xy, d_dist, d_hit, B, d_center, d_theta, d_normals);
 }
 EXPORT int gms_join_streams(gms_handle* h) {
@@ -1539,6 +1571,7 @@ EXPORT int gms_step_dev(gms_handle* h, const double* d_xy, const double* d_dist,
     if (int rc_ = check_beams(h, B, d_xy, d_dist, d_hit, "gms_step_dev")) return rc_;
     if (policy < 0 || policy > 2 || u01 >= 1.0) return fail(h, GMS_ERR_INVALID_ARG, "bad resample policy / u01");
     flip_beams(h);
+    h->fold_wpose = false;
     int rc = step_begin(h, d_xy, d_dist, d_hit, B, d_center, d_theta, d_normals);
     if (rc) return rc;
     return step_end(h, policy, u01);
@@ -1688,6 +1721,7 @@ EXPORT int gms_update_raw(gms_handle* h, const double* angle, const double* dist
     if (int rc_ = check_beams(h, B, angle, dist, hit, "gms_update_raw")) return rc_;
     if (h->cfg.nranks != 1) return fail(h, GMS_ERR_STATE, "gms_update_raw: multi-rank handles use update_begin/end");
     flip_beams(h);
+    h->fold_wpose = true;
     BeamSet& bs = cur_beams(h);
     int rc = upload_raw_and_deskew(h, bs, angle, dist, hit, B, d_center, d_theta, normals);
     if (rc) return rc;

@@ -2058,11 +2058,20 @@ __global__ void __launch_bounds__(1024) k_assign_slots_mr(const int* __restrict_
         }
         if (q == myrank && tid == 0) st->num_dup = total;
     }
-    // slots of this rank that the new generation does not occupy: drop their pending likelihood tiles
-    __syncthreads();
+    // (The pending likelihood tiles of the slots the new generation no longer occupies are dropped by
+    // k_drop_dead_dirty at the start of the NEXT step: other ranks may still be pulling those slots — bitmap
+    // included — while this kernel runs.)
+}
+
+// slots of this rank that the current generation does not occupy: drop their pending likelihood tiles, so the
+// refresh does not rebuild maps nobody reads.  Runs after the exchange's barrier.
+__global__ void __launch_bounds__(1024) k_drop_dead_dirty(const int* __restrict__ gslot_local, int cnt, int S,
+                                                          int tile_words, uint32_t* __restrict__ dirty,
+                                                          int* __restrict__ occ /* S */) {
+    const int tid = threadIdx.x;
     for (int i = tid; i < S; i += 1024) occ[i] = 0;
     __syncthreads();
-    for (int m = myrank * cnt + tid; m < (myrank + 1) * cnt; m += 1024) occ[gslot_out[m]] = 1;
+    for (int m = tid; m < cnt; m += 1024) occ[gslot_local[m]] = 1;
     __syncthreads();
     for (int i = tid; i < S * tile_words; i += 1024)
         if (!occ[i / tile_words]) dirty[i] = 0u;
@@ -2273,6 +2282,12 @@ __global__ void k_counts_join(CellCounts* __restrict__ c, const uint32_t* __rest
 __global__ void k_pose_pack(const float* __restrict__ xyt, float4* __restrict__ pose, int P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P) pose[i] = make_float4(xyt[3 * i], xyt[3 * i + 1], xyt[3 * i + 2], 0.f);
+}
+// multi-rank peer exchange: poses are not replicated by the step; a getter that needs all of them first copies
+// the remote blocks out of their owners' pose arrays (peer mappings)
+__global__ void k_pose_fill_remote(PoseTable poses, float4* __restrict__ local, int lo, int cnt, int P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P && (i < lo || i >= lo + cnt)) local[i] = poses.at(i);
 }
 __global__ void k_pose_unpack(const float4* __restrict__ pose, float* __restrict__ xyt, int P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -47,6 +47,8 @@ def _run(handle, stepper, scans, torch, dev, maps_of, check_steps):
             entry["maps"] = {p: _digest(handle.get_map(p, B.MAP_FREE_COUNT), handle.get_map(p, B.MAP_OCC_COUNT),
                                         handle.get_map(p, B.MAP_LIKELIHOOD)) for p in maps_of(handle)}
         rec.append(entry)
+        if stepper is not None:
+            stepper.dist.barrier()  # no rank starts the next step while another still reads through peer mappings
     return rec
 
 

@@ -163,6 +163,9 @@ int gms_get_weighted_pose(gms_handle* h, float pose_xyt[3]);/* SLAM.getWeightedP
  * index after the update; after a resampling the index of its first child, which inherits its map slot
  * (GridMapApp.java:376-393 keeps drawing strongestParticle.m); -1 before any update or if it left no child. */
 int gms_get_strongest(gms_handle* h, int32_t* index, float pose_xyt[3], double* weight);
+/* Multi-rank handles on the peer exchange keep only their own block of poses current between an update and the
+ * next resampling; gms_get_poses / gms_get_weighted_pose then read the other blocks through the peer mappings,
+ * so the caller must not let another rank start its next step while it reads (e.g. a barrier after the reads). */
 int gms_get_poses(gms_handle* h, float* xyt /* 3*P */);     /* getParticles().get(i).pose          */
 int gms_get_weights(gms_handle* h, double* w /* P */);      /* getParticles().get(i).weight        */
 int gms_get_log_weights(gms_handle* h, double* lw /* P */); /* ln of the un-normalised products of
