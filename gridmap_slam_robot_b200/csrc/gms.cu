@@ -717,8 +717,8 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
             xp.dst[q] = q == c.rank ? h->xlw[(h->xseq + 1) & 1] : h->peer_xlw[(h->xseq + 1) & 1][q];
             xp.flag[q] = q == c.rank ? h->xflags : h->peer_flags[q];
         }
-        const unsigned grid = std::min<unsigned>(blocks_for((long long)c.nranks * h->cnt, 256), (unsigned)h->num_sms * 4);
-        LAUNCH(GMS_PHASE_EXCHANGE, k_xpush_lw<<<grid, 256, 0, h->stream>>>(h->lw[h->cur], h->lo, h->cnt, xp, c.rank,
+        const unsigned grid = std::max(1u, std::min<unsigned>(blocks_for((long long)c.nranks * h->cnt / 2, 1024 * 4), 64u));
+        LAUNCH(GMS_PHASE_EXCHANGE, k_xpush_lw<<<grid, 1024, 0, h->stream>>>(h->lw[h->cur], h->lo, h->cnt, xp, c.rank,
                                                                           h->xseq + 1, h->xticket));
     }
     h->pending = true;
@@ -792,8 +792,8 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
             h->wpose_valid = fold;
             const unsigned long long* fx = h->np.fx;
             int ntiles = h->ntiles;
-            const unsigned grid = (unsigned)std::max(1, std::min(h->num_sms, std::max(ntiles, (m_count + 1023) / 1024)));
-            LAUNCH_COOP(GMS_PHASE_RESAMPLE, k_resample_coop, grid, 1024, 0, &a, &fx, &ntiles);
+            const unsigned grid = (unsigned)std::max(1, std::min(h->num_sms * 6, std::max(ntiles, (m_count + 1023) / 1024)));
+            LAUNCH_COOP(GMS_PHASE_RESAMPLE, k_resample_coop, grid, kNormThreads, 0, &a, &fx, &ntiles);
         } else {
             h->wpose_valid = false;
             LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_literal<<<1, 32, 0, h->stream>>>(h->w[h->cur], P, (double*)h->cdf, h->st));
@@ -873,8 +873,8 @@ int step_end(gms_handle* h, int policy, double u01) {
         a.pose_local = (h->fold_wpose && (c.nranks == 1 || !h->direct)) ? h->pose[h->cur] : nullptr;
         a.wp_part = h->wp_part;
         h->wpose_valid = a.pose_local != nullptr;
-        const unsigned grid = (unsigned)std::max(1, std::min(h->ntiles, h->num_sms));
-        LAUNCH_COOP(GMS_PHASE_NORMALISE, k_norm_coop, grid, 1024, 0, &a);
+        const unsigned grid = (unsigned)std::max(1, std::min(h->ntiles, h->num_sms * 6));
+        LAUNCH_COOP(GMS_PHASE_NORMALISE, k_norm_coop, grid, kNormThreads, 0, &a);
         h->tile_fx_valid = true;
     }
     const bool skip = std::fabs(h->pend_dtheta) > (M_PI / 180.0) * c.skip_update_deg;

@@ -77,23 +77,41 @@ struct XPush {
     double* dst[kMaxRanks];               // receive buffer (f64[P]) of every rank for this exchange parity
     unsigned long long* flag[kMaxRanks];  // flag[q] = rank q's flag array (one u64 per sender)
 };
-__global__ void __launch_bounds__(256) k_xpush_lw(const double* __restrict__ lw, int lo, int cnt, XPush xp,
-                                                  int myrank, unsigned long long seq,
-                                                  unsigned* __restrict__ ticket) {
+__global__ void __launch_bounds__(1024) k_xpush_lw(const double* __restrict__ lw, int lo, int cnt, XPush xp,
+                                                   int myrank, unsigned long long seq,
+                                                   unsigned* __restrict__ ticket) {
     __shared__ bool s_last;
-    const long long total = (long long)xp.nranks * cnt;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int q = (int)(e / cnt), i = lo + (int)(e - (long long)q * cnt);
-        xp.dst[q][i] = lw[i];
+    // two particles (16 bytes) per store; destination-major so that a warp's stores form full 128-byte lines
+    const int pairs = cnt >> 1;
+    const long long total = (long long)xp.nranks * pairs;
+    const bool aligned = ((lo | cnt) & 1) == 0;
+    if (aligned) {
+        for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+             e += (long long)gridDim.x * blockDim.x) {
+            const int q = (int)(e / pairs), j = (int)(e - (long long)q * pairs);
+            reinterpret_cast<double2*>(xp.dst[q] + lo)[j] = reinterpret_cast<const double2*>(lw + lo)[j];
+        }
+    } else {
+        for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)xp.nranks * cnt;
+             e += (long long)gridDim.x * blockDim.x) {
+            const int q = (int)(e / cnt), i = lo + (int)(e - (long long)q * cnt);
+            xp.dst[q][i] = lw[i];
+        }
     }
-    __threadfence_system();  // this thread's stores are visible system-wide before anything it does next
+    // one system-scope fence per CTA: the barrier orders the CTA's stores before thread 0's fence (cumulativity),
+    // the ticket orders every CTA's fence before the last CTA's flag stores
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+    }
     __syncthreads();
     if (!s_last) return;
-    __threadfence_system();
-    if (threadIdx.x == 0) *ticket = 0u;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        *ticket = 0u;
+    }
+    __syncthreads();
     if ((int)threadIdx.x < xp.nranks)
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(xp.flag[threadIdx.x] + myrank), "l"(seq) : "memory");
 }
@@ -1450,6 +1468,63 @@ __device__ __forceinline__ void block_sum_vec_1024(double (&v)[N], double* s_buf
 struct SumOp { __device__ double operator()(double a, double b) const { return a + b; } };
 struct SumU64 { __device__ unsigned long long operator()(unsigned long long a, unsigned long long b) const { return a + b; } };
 
+// The same reductions for blocks of NT = 64 .. 1024 threads (NT / 32 a power of two): fixed trees, result in every thread.
+template <int NT, typename T, typename Op>
+__device__ __forceinline__ T block_reduce_nt(T v, Op op, T* s_buf /* NT / 32 */) {
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) s_buf[wid] = v;
+    __syncthreads();
+    v = s_buf[lane & (NW - 1)];
+#pragma unroll
+    for (int o = NW / 2; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <int NT, int N>
+__device__ __forceinline__ void block_sum_vec_nt(double (&v)[N], double* s_buf /* (NT / 32) * N */) {
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; k++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    __syncthreads();
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < N; k++) s_buf[k * NW + wid] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        v[k] = s_buf[k * NW + (lane & (NW - 1))];
+#pragma unroll
+        for (int o = NW / 2; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+}
+template <int NT>
+__device__ __forceinline__ void block_argmax_nt(double& best, int& bi, double* s_key, int* s_idx) {
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    __syncthreads();
+    if (lane == 0) { s_key[wid] = best; s_idx[wid] = bi; }
+    __syncthreads();
+    best = s_key[lane & (NW - 1)]; bi = s_idx[lane & (NW - 1)];
+#pragma unroll
+    for (int o = NW / 2; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+}
+
 // (max, first index of the max) over a block; result valid in every thread
 __device__ __forceinline__ void block_argmax_1024(double& best, int& bi, double* s_key, int* s_idx) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1497,13 +1572,16 @@ struct NormArgs {
     const float4* pose_local;  // all P poses in local memory (single rank / imported records), else nullptr: the
     double* wp_part;           // weighted pose (SLAM.getWeightedPose) then comes out of this kernel too
 };
-__global__ void __launch_bounds__(1024) k_norm_coop(NormArgs a) {
+constexpr int kNormThreads = 256;  // 4 consecutive particles per thread: a 1024-particle tile per CTA iteration;
+                                   // 6 CTAs/SM (888 co-resident) cover the 782 tiles of 8 x 100k particles in one wave
+__global__ void __launch_bounds__(kNormThreads, 6) k_norm_coop(NormArgs a) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double s_key[32];
-    __shared__ int s_idx[32];
-    __shared__ double s_d[32];
-    __shared__ double s_v[5 * 32];
-    __shared__ unsigned long long s_u[32];
+    constexpr int NT = kNormThreads, NW = NT / 32;
+    __shared__ double s_key[NW];
+    __shared__ int s_idx[NW];
+    __shared__ double s_d[NW];
+    __shared__ double s_v[5 * NW];
+    __shared__ unsigned long long s_u[NW];
     __shared__ bool s_last;
     const int tid = threadIdx.x, G = gridDim.x;
     if (a.xflags) {
@@ -1521,14 +1599,24 @@ __global__ void __launch_bounds__(1024) k_norm_coop(NormArgs a) {
     }
     // phase 1: per fixed tile, (max, first arg-max, sum exp(lw - tile max))
     for (int t = blockIdx.x; t < a.ntiles; t += G) {
-        const int i = t * 1024 + tid;
-        const double v = i < a.P ? __ldcg(a.lw + i) : kNegInf;
-        if (a.lw_store && i < a.P) a.lw_store[i] = v;
-        double best = v;
-        int bi = i < a.P ? i : 0x7fffffff;
-        block_argmax_1024(best, bi, s_key, s_idx);
-        const double e = i < a.P ? exp(v - best) : 0.0;
-        const double sum = block_reduce_1024(e, SumOp(), s_d);
+        const int i0 = t * 1024 + tid * 4;
+        double v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = i0 + j < a.P ? __ldcg(a.lw + i0 + j) : kNegInf;
+        if (a.lw_store)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (i0 + j < a.P) a.lw_store[i0 + j] = v[j];
+        double best = kNegInf;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (v[j] > best) { best = v[j]; bi = i0 + j; }  // ascending index: a later equal value never replaces
+        block_argmax_nt<NT>(best, bi, s_key, s_idx);
+        double e = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) e += i0 + j < a.P ? exp(v[j] - best) : 0.0;
+        const double sum = block_reduce_nt<NT>(e, SumOp(), s_d);
         if (tid == 0) { a.np.m[t] = best; a.np.idx[t] = bi; a.np.s[t] = sum; }
     }
     __threadfence();
@@ -1537,31 +1625,36 @@ __global__ void __launch_bounds__(1024) k_norm_coop(NormArgs a) {
     // every CTA combines the tile partials in the same fixed order -> (M, first arg-max, S)
     double best = kNegInf;
     int bi = 0x7fffffff;
-    for (int c = tid; c < a.ntiles; c += 1024) {
+    for (int c = tid; c < a.ntiles; c += NT) {
         const double v = __ldcg(a.np.m + c);
         const int vi = __ldcg(a.np.idx + c);
         if (v > best || (v == best && vi < bi)) { best = v; bi = vi; }
     }
-    block_argmax_1024(best, bi, s_key, s_idx);
+    block_argmax_nt<NT>(best, bi, s_key, s_idx);
     double acc = 0.0;
-    for (int c = tid; c < a.ntiles; c += 1024) acc += __ldcg(a.np.s + c) * exp(__ldcg(a.np.m + c) - best);
-    const double S = block_reduce_1024(acc, SumOp(), s_d);
-    // phase 2: w_i = exp(lw_i - M) / S, tile sums of w, w^2, trunc(w * 2^60)
+    for (int c = tid; c < a.ntiles; c += NT) acc += __ldcg(a.np.s + c) * exp(__ldcg(a.np.m + c) - best);
+    const double S = block_reduce_nt<NT>(acc, SumOp(), s_d);
+    // phase 2: w_i = exp(lw_i - M) / S, tile sums of w, w^2, trunc(w * 2^60) (+ weighted pose terms)
     for (int t = blockIdx.x; t < a.ntiles; t += G) {
-        const int i = t * 1024 + tid;
-        double wi = 0.0;
+        const int i0 = t * 1024 + tid * 4;
         double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // w, w^2, w*x, w*y, w*angleConstrain(theta)
-        if (i < a.P) {
-            wi = exp(__ldcg(a.lw + i) - best) / S;
-            a.w[i] = wi;
-            v[0] = wi; v[1] = wi * wi;
-            if (a.pose_local) {  // SLAM.getWeightedPose SLAM.java:165-178
-                const float4 p = a.pose_local[i];
-                v[2] = (double)p.x * wi; v[3] = (double)p.y * wi; v[4] = angle_constrain((double)p.z) * wi;
+        unsigned long long fx = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = i0 + j;
+            if (i < a.P) {
+                const double wi = exp(__ldcg(a.lw + i) - best) / S;
+                a.w[i] = wi;
+                v[0] += wi; v[1] += wi * wi;
+                fx += (unsigned long long)(wi * 0x1p60);
+                if (a.pose_local) {  // SLAM.getWeightedPose SLAM.java:165-178
+                    const float4 p = a.pose_local[i];
+                    v[2] += (double)p.x * wi; v[3] += (double)p.y * wi; v[4] += angle_constrain((double)p.z) * wi;
+                }
             }
         }
-        block_sum_vec_1024<5>(v, s_v);
-        const unsigned long long fx = block_reduce_1024((unsigned long long)(wi * 0x1p60), SumU64(), s_u);
+        block_sum_vec_nt<NT, 5>(v, s_v);
+        fx = block_reduce_nt<NT>(fx, SumU64(), s_u);
         if (tid == 0) {
             a.np.ws[t] = v[0]; a.np.q[t] = v[1]; a.np.fx[t] = fx;
             if (a.pose_local) { a.wp_part[4 * t] = v[2]; a.wp_part[4 * t + 1] = v[3]; a.wp_part[4 * t + 2] = v[4]; }
@@ -1576,14 +1669,14 @@ __global__ void __launch_bounds__(1024) k_norm_coop(NormArgs a) {
     if (!s_last) return;
     __threadfence();
     double f[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int c = tid; c < a.ntiles; c += 1024) {
+    for (int c = tid; c < a.ntiles; c += NT) {
         f[0] += __ldcg(a.np.ws + c);
         f[1] += __ldcg(a.np.q + c);
         if (a.pose_local) {
             f[2] += __ldcg(a.wp_part + 4 * c); f[3] += __ldcg(a.wp_part + 4 * c + 1); f[4] += __ldcg(a.wp_part + 4 * c + 2);
         }
     }
-    block_sum_vec_1024<5>(f, s_v);
+    block_sum_vec_nt<NT, 5>(f, s_v);
     const double sa = f[0], sq = f[1];
     if (tid == 0) {
         Stats* st = a.st;
@@ -1820,17 +1913,19 @@ __global__ void __launch_bounds__(256) k_select(SelectArgs a) {
 //            parallel scan (fixed-point tile sums of k_norm_coop / k_neff + a block-wide scan per tile) equals
 //            the sequential walk bit for bit on any number of threads / CTAs / ranks
 //   phase 2  selection + gather of the children [m_begin, m_begin + m_count)
-__global__ void __launch_bounds__(1024) k_resample_coop(SelectArgs a, const unsigned long long* __restrict__ tile_fx,
-                                                        int ntiles) {
+__global__ void __launch_bounds__(kNormThreads, 6) k_resample_coop(SelectArgs a,
+                                                                   const unsigned long long* __restrict__ tile_fx,
+                                                                   int ntiles) {
     cg::grid_group grid = cg::this_grid();
+    constexpr int NT = kNormThreads, NW = NT / 32;
     __shared__ unsigned long long s_coarse[2048];
-    __shared__ unsigned long long s_u[32];
-    __shared__ double s_v[4 * 32];
+    __shared__ unsigned long long s_u[NW];
+    __shared__ double s_v[4 * NW];
     __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, G = gridDim.x;
     if (a.st->xerror) return;        // uniform over the grid
     if (!a.st->do_resample) {        // uniform over the grid: the generation is carried over unchanged
-        for (int m0 = a.m_begin + blockIdx.x * 1024 + tid; m0 < a.m_begin + a.m_count; m0 += G * 1024) {
+        for (int m0 = a.m_begin + blockIdx.x * NT + tid; m0 < a.m_begin + a.m_count; m0 += G * NT) {
             a.parents[m0] = m0;
             a.pose_out[m0] = a.poses_in.at(m0);
             a.w_out[m0] = a.w_in[m0];
@@ -1839,12 +1934,18 @@ __global__ void __launch_bounds__(1024) k_resample_coop(SelectArgs a, const unsi
         return;
     }
     unsigned long long* cdf = static_cast<unsigned long long*>(const_cast<void*>(a.cdf));
-    for (int t = blockIdx.x; t < ntiles; t += G) {
+    for (int t = blockIdx.x; t < ntiles; t += G) {  // a tile = 1024 particles = 4 consecutive ones per thread
         unsigned long long acc = 0;
-        for (int c = tid; c < t; c += 1024) acc += __ldcg(tile_fx + c);
-        const unsigned long long carry = block_reduce_1024(acc, SumU64(), s_u);
-        const int i = t * 1024 + tid;
-        unsigned long long v = i < a.P ? (unsigned long long)(a.w_in[i] * 0x1p60) : 0ull;
+        for (int c = tid; c < t; c += NT) acc += __ldcg(tile_fx + c);
+        const unsigned long long carry = block_reduce_nt<NT>(acc, SumU64(), s_u);
+        const int i0 = t * 1024 + tid * 4;
+        unsigned long long x[4], run = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            run += i0 + j < a.P ? (unsigned long long)(a.w_in[i0 + j] * 0x1p60) : 0ull;
+            x[j] = run;  // inclusive within the thread
+        }
+        unsigned long long v = run;  // inclusive scan of the thread totals across the block
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned long long u = __shfl_up_sync(0xffffffffu, v, o);
@@ -1853,34 +1954,36 @@ __global__ void __launch_bounds__(1024) k_resample_coop(SelectArgs a, const unsi
         __syncthreads();
         if (lane == 31) s_u[wid] = v;
         __syncthreads();
-        unsigned long long wsum = s_u[lane];
+        unsigned long long wbase = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long u = __shfl_up_sync(0xffffffffu, wsum, o);
-            if (lane >= o) wsum += u;
-        }
-        const unsigned long long warp_excl = __shfl_sync(0xffffffffu, wsum, max(wid, 1) - 1);
-        if (i < a.P) cdf[i] = carry + (wid > 0 ? warp_excl : 0ull) + v;
+        for (int k = 0; k < NW; k++) wbase += k < wid ? s_u[k] : 0ull;
+        const unsigned long long excl = carry + wbase + v - run;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (i0 + j < a.P) cdf[i0 + j] = excl + x[j];
     }
     if (blockIdx.x == 0 && tid == 0) a.st->strongest_now = -1;
     __threadfence();
     grid.sync();
     const int stride = select_stride(a.P), ncoarse = (a.P + stride - 1) / stride;
-    for (int j = tid; j < ncoarse; j += 1024) s_coarse[j] = __ldcg(cdf + min(a.P - 1, (j + 1) * stride - 1));
+    for (int j = tid; j < ncoarse; j += NT) s_coarse[j] = __ldcg(cdf + min(a.P - 1, (j + 1) * stride - 1));
     __syncthreads();
     const double u01 = a.u01 < 0.0 ? philox_uniform(a.seed, a.resample_count) : a.u01;
     const int nchunks = (a.m_count + 1023) / 1024;
     for (int c = blockIdx.x; c < nchunks; c += G) {  // fixed chunks of 1024 children (fixed reduction order)
-        const int m0 = a.m_begin + c * 1024 + tid;
         double v[4] = {0.0, 0.0, 0.0, 0.0};
-        if (m0 < a.m_begin + a.m_count) {
-            float4 po;
-            double wo;
-            select_child<true>(a, m0, s_coarse, stride, ncoarse, u01, po, wo);
-            v[0] = (double)po.x * wo; v[1] = (double)po.y * wo; v[2] = angle_constrain((double)po.z) * wo; v[3] = wo;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int m0 = a.m_begin + c * 1024 + j * NT + tid;
+            if (m0 < a.m_begin + a.m_count) {
+                float4 po;
+                double wo;
+                select_child<true>(a, m0, s_coarse, stride, ncoarse, u01, po, wo);
+                v[0] += (double)po.x * wo; v[1] += (double)po.y * wo; v[2] += angle_constrain((double)po.z) * wo; v[3] += wo;
+            }
         }
         if (a.wp_part) {
-            block_sum_vec_1024<4>(v, s_v);
+            block_sum_vec_nt<NT, 4>(v, s_v);
             if (tid == 0) { a.wp_part[4 * c] = v[0]; a.wp_part[4 * c + 1] = v[1]; a.wp_part[4 * c + 2] = v[2]; a.wp_part[4 * c + 3] = v[3]; }
         }
     }
@@ -1894,10 +1997,10 @@ __global__ void __launch_bounds__(1024) k_resample_coop(SelectArgs a, const unsi
     if (!s_last) return;
     __threadfence();
     double f[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int c = tid; c < nchunks; c += 1024)
+    for (int c = tid; c < nchunks; c += NT)
 #pragma unroll
         for (int k = 0; k < 4; k++) f[k] += __ldcg(a.wp_part + 4 * c + k);
-    block_sum_vec_1024<4>(f, s_v);
+    block_sum_vec_nt<NT, 4>(f, s_v);
     if (tid == 0) {
         a.st->weighted_pose[0] = (float)(f[0] / f[3]);
         a.st->weighted_pose[1] = (float)(f[1] / f[3]);
