@@ -139,7 +139,8 @@ struct gms_handle {
                                 // (GMS_MAP_WIN_WORDS, e.g. 13000 = 52 KB: four CTAs per SM); 0 = the global-atomic
                                 // kernel (default: see DESIGN.md for the measurements)
     int score_g = 0;  // sub-threads per particle in k_score_sorted (0 = automatic; GMS_SCORE_G overrides: tuning knob)
-    int score_v = 0;  // index-validation variant of k_score_sorted (GMS_SCORE_V=1: ALU-lean form, same results)
+    int score_v = 2;  // variant of k_score_sorted (GMS_SCORE_V=0..6, identical cell indices; kernels.cuh / DESIGN.md §4.19):
+                      // 2 = folded magic constant + per-particle range guard + padded factor field (measured fastest)
     int num_sms = 148;
     int* ray_maxlen = nullptr;
     // GMS_UPDATE_SORTED scratch (allocated on first use)
@@ -484,7 +485,18 @@ int launch_likelihood(gms_handle* h) {
 
 // Thread-per-particle scoring in heading order pays off when one shared field serves many particles
 // (see k_score_sorted); per-particle maps and small particle sets keep one warp per particle.
-bool use_sorted_score(const gms_handle* h) { return h->cfg.map_mode == GMS_MAP_SHARED && h->cnt >= 4096 && h->coop; }
+// sub-threads per particle in k_score_sorted: enough threads to fill the machine (>= ~200k), at most one warp per particle
+int score_subthreads(const gms_handle* h, int cnt) {
+    if (h->score_g) return h->score_g;
+    int G = 1;
+    while (G < 32 && (long long)cnt * G < 200000) G *= 2;
+    return G;
+}
+// The heading sort only matters when a warp holds several particles (G < 32): with one warp per particle the
+// 32 lanes look up beams of the SAME particle, whatever the order (K3: 10k particles -> no sort, plain k_motion).
+bool use_sorted_score(const gms_handle* h) {
+    return h->cfg.map_mode == GMS_MAP_SHARED && h->coop && score_subthreads(h, h->cnt) < 32;
+}
 // every shared-map scoring of the step runs k_score_sorted (factor field + FMA cell index)
 bool use_fac_score(const gms_handle* h) { return h->cfg.map_mode == GMS_MAP_SHARED; }
 
@@ -506,11 +518,8 @@ int launch_score(gms_handle* h, const BeamSet& b, const float4* pose, int lo, in
     Phase ph(h, GMS_PHASE_SCORE);
     const size_t smem = std::max<size_t>(16, (size_t)B * 16);
     if (sorted) {
-        // sub-threads per particle: enough threads to fill the machine (>= ~150k), at most one warp per particle
-        int G = 1;
-        while (G < 32 && (long long)cnt * G < 200000) G *= 2;
-        if (h->score_g) G = h->score_g;
-        const int* order = use_sorted_score(h) ? h->sort.order : nullptr;
+        const int G = score_subthreads(h, cnt);
+        const int* order = (use_sorted_score(h) && pose == h->pose[h->cur] && cnt == h->cnt) ? h->sort.order : nullptr;
         const unsigned grid = blocks_for((long long)cnt * G, 128);
 #define SCORE_G(GG)                                                                                            \
     case GG:                                                                                                   \
