@@ -801,7 +801,7 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
             h->wpose_valid = fold;
             const unsigned long long* fx = h->np.fx;
             int ntiles = h->ntiles;
-            const unsigned grid = (unsigned)std::max(1, std::min(h->num_sms * 6, std::max(ntiles, (m_count + 1023) / 1024)));
+            const unsigned grid = (unsigned)std::max(1, std::min(h->num_sms * 6, std::max(ntiles, (m_count + kNormThreads - 1) / kNormThreads)));
             LAUNCH_COOP(GMS_PHASE_RESAMPLE, k_resample_coop, grid, kNormThreads, 0, &a, &fx, &ntiles);
         } else {
             h->wpose_valid = false;
@@ -1194,7 +1194,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
         CKC(cudaMalloc((void**)&h->np.fx, nt * 8));
         CKC(cudaMalloc((void**)&h->np.counter, 4));
         CKC(cudaMemset(h->np.counter, 0, 4));
-        CKC(cudaMalloc((void**)&h->wp_part, nt * 32));
+        CKC(cudaMalloc((void**)&h->wp_part, (nt * (1024 / kNormThreads) + 4) * 32));  // per chunk of kNormThreads children
         CKC(cudaMalloc((void**)&h->wp_counter, 4));
         CKC(cudaMemset(h->wp_counter, 0, 4));
         CKC(cudaMalloc((void**)&h->ray_maxlen, 4));

@@ -1969,18 +1969,15 @@ __global__ void __launch_bounds__(kNormThreads, 6) k_resample_coop(SelectArgs a,
     for (int j = tid; j < ncoarse; j += NT) s_coarse[j] = __ldcg(cdf + min(a.P - 1, (j + 1) * stride - 1));
     __syncthreads();
     const double u01 = a.u01 < 0.0 ? philox_uniform(a.seed, a.resample_count) : a.u01;
-    const int nchunks = (a.m_count + 1023) / 1024;
-    for (int c = blockIdx.x; c < nchunks; c += G) {  // fixed chunks of 1024 children (fixed reduction order)
+    const int nchunks = (a.m_count + NT - 1) / NT;
+    for (int c = blockIdx.x; c < nchunks; c += G) {  // fixed chunks of NT children, one per thread (fixed reduction order)
         double v[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int m0 = a.m_begin + c * 1024 + j * NT + tid;
-            if (m0 < a.m_begin + a.m_count) {
-                float4 po;
-                double wo;
-                select_child<true>(a, m0, s_coarse, stride, ncoarse, u01, po, wo);
-                v[0] += (double)po.x * wo; v[1] += (double)po.y * wo; v[2] += angle_constrain((double)po.z) * wo; v[3] += wo;
-            }
+        const int m0 = a.m_begin + c * NT + tid;
+        if (m0 < a.m_begin + a.m_count) {
+            float4 po;
+            double wo;
+            select_child<true>(a, m0, s_coarse, stride, ncoarse, u01, po, wo);
+            v[0] = (double)po.x * wo; v[1] = (double)po.y * wo; v[2] = angle_constrain((double)po.z) * wo; v[3] = wo;
         }
         if (a.wp_part) {
             block_sum_vec_nt<NT, 4>(v, s_v);
