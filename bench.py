@@ -463,6 +463,14 @@ def roofline_of(r, args):
         if inst:
             out["warp_instructions_per_launch"] = inst
             out["issue_frac"] = inst / (148 * 4 * sm_hz * score_ms * 1e-3)
+        if kc.get("l2_sectors_per_launch"):
+            # what the gather really moves: 32-byte sectors from L2 (and HBM behind it), from the ncu capture
+            out["l2_sector_gbs"] = kc["l2_sectors_per_launch"] * 32 / (score_ms * 1e-3) / 1e9
+            out["l2_hit_rate_pct"] = kc.get("l2_hit_rate_pct")
+            out["lts_throughput_pct_of_peak_ncu"] = kc.get("lts_throughput_pct_of_peak")
+            if kc.get("dram_bytes_per_launch"):
+                out["dram_gbs"] = kc["dram_bytes_per_launch"] / (score_ms * 1e-3) / 1e9
+                out["dram_frac_of_peak"] = out["dram_gbs"] / peak
         return out
     # per-particle maps: the scatter (map update) dominates.  SURVEY.md §8d: C * 2 * s_log bytes with s_log = 4 (one
     # counter of the 8-byte pair is read and written per ray cell); C from the true poses (n_r = 3 + |dfloor x| +

@@ -600,7 +600,7 @@ int launch_shared_update(gms_handle* h, const BeamSet& b, int B) {
 int launch_map_update(gms_handle* h, const BeamSet& b, const float4* pose, int lo, int cnt, const int* slot, int B) {
     if (B <= 0) return GMS_OK;
     Phase ph(h, GMS_PHASE_MAP_UPDATE);
-    if (h->map_win_words > 0) {  // one CTA per (particle, quadrant): shared-memory accumulation + coalesced flush
+    if (h->map_win_words > 0 && B <= kWinMaxBeams) {  // one CTA per (particle, quadrant): on-chip accumulation + coalesced flush
         LAUNCH(GMS_PHASE_MAP_UPDATE, k_map_update_win<<<(unsigned)cnt * 4u, kWinThreads, (size_t)h->map_win_words * 4, h->stream>>>(
                                          pose, lo, cnt, b.xy, b.meas, b.hit, B, h->counts, slot, h->rect, h->dirty,
                                          h->map_win_words, h->g));

@@ -1065,25 +1065,30 @@ __global__ void __launch_bounds__(128) k_map_update(const float4* __restrict__ p
 // sector).  A map is only ever written by its own particle, so the increments of one scan can be combined on
 // chip first: the rays of one quadrant all start in the same cell and move monotonically away from it, so they
 // live in a rectangle anchored at the start cell.  The CTA tiles that rectangle into windows of `win_words`
-// cells; per window it zeroes a shared-memory array of one u32 per cell (low half: free increments, high half:
-// occupied increments; a ray visits a cell at most 3 times, 3 * GMS_MAX_BEAMS < 65536), re-walks its rays (the
-// DDA is a handful of instructions per cell; a ray leaves the loop as soon as it is past the window in either
-// axis) accumulating with shared-memory atomics, and flushes the window with plain, coalesced 8-byte
+// cells, visited in row-major order; per window it zeroes a shared-memory array of one u32 per cell (low half:
+// free increments, high half: occupied increments; a ray visits a cell at most 3 times), advances every ray that
+// currently sits in the window until it leaves it (the DDA state stays in registers: each ray is walked once;
+// a first version re-walked every ray per window and was bound by those instructions, 2.9 ms) accumulating with
+// shared-memory atomics, and flushes the window with plain, coalesced 8-byte
 // read-modify-writes (old pair in, new pair out, dirty-tile marking from the two thresholded codes).  No global
 // atomics except on the start row / column, which neighbouring quadrants share.  Integer accumulation: the
 // result is independent of the order => deterministic, identical to the atomic kernel's.
 constexpr int kWinThreads = 256;
-__global__ void __launch_bounds__(kWinThreads, 4) k_map_update_win(const float4* __restrict__ pose, int lo, int cnt,
-                                                                const double2* __restrict__ all_xy,
-                                                                const float* __restrict__ meas,
-                                                                const uint8_t* __restrict__ hit, int B,
-                                                                CellCounts* __restrict__ counts,
-                                                                const int* __restrict__ slot, int4* __restrict__ rect,
-                                                                uint32_t* __restrict__ dirty, int win_words,
-                                                                Geometry g) {
+constexpr int kWinRaysPerThread = 2;                                   // a quadrant may hold up to 512 rays ...
+constexpr int kWinMaxBeams = kWinThreads * kWinRaysPerThread;          // ... so scans of up to 512 beams take this kernel
+__global__ void __launch_bounds__(kWinThreads, 3) k_map_update_win(const float4* __restrict__ pose, int lo, int cnt,
+                                                                   const double2* __restrict__ all_xy,
+                                                                   const float* __restrict__ meas,
+                                                                   const uint8_t* __restrict__ hit, int B,
+                                                                   CellCounts* __restrict__ counts,
+                                                                   const int* __restrict__ slot, int4* __restrict__ rect,
+                                                                   uint32_t* __restrict__ dirty, int win_words,
+                                                                   Geometry g) {
     extern __shared__ __align__(16) uint32_t s_win[];
     __shared__ int s_reach[2];
     __shared__ int s_box[4];
+    __shared__ int s_nrays;
+    __shared__ unsigned short s_rays[kWinMaxBeams];
     const int tid = threadIdx.x;
     const int li = blockIdx.x >> 2, quad = blockIdx.x & 3;
     if (li >= cnt) return;
@@ -1097,32 +1102,51 @@ __global__ void __launch_bounds__(kWinThreads, 4) k_map_update_win(const float4*
     const float sy = (float)((t.ty(0.0, 0.0) - g.posy) / g.res);
     const int x0 = java_d2i(floor((double)(sx + 0.5f))), y0 = java_d2i(floor((double)(sy + 0.5f)));  // RayIter.init
     if (tid == 0) {
-        s_reach[0] = -1; s_reach[1] = -1;
+        s_reach[0] = -1; s_reach[1] = -1; s_nrays = 0;
         s_box[0] = 0x7fffffff; s_box[1] = 0x7fffffff; s_box[2] = -1; s_box[3] = -1;
     }
     __syncthreads();
-    int rx = 0, ry = 0;  // of the last ray_of(): |dfloor x|, |dfloor y| between the ray's first and last cell
-    auto ray_of = [&](int b, RayIter& it) -> bool {  // true if beam b belongs to this quadrant
+    auto ray_init = [&](int b, RayIter& it, int& rx, int& ry) {
         const double2 m = all_xy[b];
         const float ex = (float)((t.tx(m.x, m.y) - g.posx) / g.res);
         const float ey = (float)((t.ty(m.x, m.y) - g.posy) / g.res);
         it.init(sx + 0.5f, sy + 0.5f, ex + 0.5f, ey + 0.5f, g.extra_steps);
-        rx = abs(java_d2i(floor((double)(ex + 0.5f))) - x0);
+        rx = abs(java_d2i(floor((double)(ex + 0.5f))) - x0);  // |dfloor x|, |dfloor y| between first and last cell
         ry = abs(java_d2i(floor((double)(ey + 0.5f))) - y0);
-        return ((it.x_inc < 0) ? -1 : 1) == qx && ((it.y_inc < 0) ? -1 : 1) == qy;
     };
-    // pass A: how far do this quadrant's rays reach (cells, clipped to the map)?  A ray makes |dfloor x| steps in
-    // x and |dfloor y| in y to its end point, plus at most `extra_steps` more in either axis.
+    // pass A: this quadrant's rays (list in shared memory, any order: integer accumulation commutes) and how far
+    // they reach: |dfloor| steps to the end point plus at most `extra_steps` more in either axis, clipped to the map
     for (int b = tid; b < B; b += kWinThreads) {
         RayIter it;
-        if (!ray_of(b, it) || !it.has_next(g.W, g.H)) continue;
+        int rx, ry;
+        ray_init(b, it, rx, ry);
+        if (((it.x_inc < 0) ? -1 : 1) != qx || ((it.y_inc < 0) ? -1 : 1) != qy || !it.has_next(g.W, g.H)) continue;
         const int lim_x = qx > 0 ? g.W - 1 - x0 : x0, lim_y = qy > 0 ? g.H - 1 - y0 : y0;
         atomicMax(&s_reach[0], min(rx + g.extra_steps, lim_x));
         atomicMax(&s_reach[1], min(ry + g.extra_steps, lim_y));
+        s_rays[atomicAdd(&s_nrays, 1)] = (unsigned short)b;
     }
     __syncthreads();
     const int RX = s_reach[0] + 1, RY = s_reach[1] + 1;  // the quadrant's rectangle: [0, RX) x [0, RY) in (wx, wy)
-    if (RX <= 0) return;                                  // no ray of this quadrant starts inside the map
+    const int nrays = s_nrays;
+    if (nrays == 0) return;
+    // every thread owns up to kWinRaysPerThread rays and keeps their DDA state in registers across the windows
+    RayIter it[kWinRaysPerThread];
+    float ms[kWinRaysPerThread];
+    bool wh[kWinRaysPerThread], live[kWinRaysPerThread];
+#pragma unroll
+    for (int r = 0; r < kWinRaysPerThread; r++) {
+        const int k = tid + r * kWinThreads;
+        live[r] = k < nrays;
+        ms[r] = 0.f; wh[r] = false;
+        if (live[r]) {
+            const int b = s_rays[k];
+            int rx, ry;
+            ray_init(b, it[r], rx, ry);
+            ms[r] = meas[b];
+            wh[r] = hit[b] != 0;
+        }
+    }
     // window shape: as square as the rectangle allows
     int WX, WY;
     {
@@ -1132,35 +1156,36 @@ __global__ void __launch_bounds__(kWinThreads, 4) k_map_update_win(const float4*
         else if (RY <= sq) { WY = RY; WX = min(RX, win_words / WY); }
         else { WX = sq; WY = sq; }
     }
+    // Windows in row-major order.  A ray only ever moves away from the start cell, one cell along one axis per step:
+    // when it leaves window (i, j) it enters (i+1, j) — the next one — or (i, j+1), which comes later in the order;
+    // it pauses (state in registers) and resumes there.  Every ray is walked exactly once.
     for (int oy = 0; oy < RY; oy += WY)
         for (int ox = 0; ox < RX; ox += WX) {
             const int wxe = min(ox + WX, RX), wye = min(oy + WY, RY);  // window = [ox, wxe) x [oy, wye)
             const int ww = wxe - ox, nwin = ww * (wye - oy);
             for (int i = tid; i < nwin; i += kWinThreads) s_win[i] = 0u;
             __syncthreads();
-            for (int b = tid; b < B; b += kWinThreads) {
-                RayIter it;
-                if (!ray_of(b, it)) continue;
-                if (rx + g.extra_steps < ox || ry + g.extra_steps < oy) continue;  // ends before this window begins
-                const float ms = meas[b];
-                const bool wh = hit[b] != 0;
-                int lx_ = it.x, ly_ = it.y;
-                bool finished = true, any = false;
-                while (it.has_next(g.W, g.H)) {
-                    lx_ = it.x; ly_ = it.y;
-                    any = true;
-                    const int wx = (lx_ - x0) * qx, wy = (ly_ - y0) * qy;
-                    if (wx >= wxe || wy >= wye) { finished = false; break; }  // past the window for good (monotone walk)
-                    if (wx >= ox && wy >= oy) {
-                        const float dX = sx - ((float)lx_ + 0.5f);
-                        const float dY = sy - ((float)ly_ + 0.5f);
-                        const float dist = __fsqrt_rn(dX * dX + dY * dY);
-                        const int cls = inverse_sensor_class(dist, ms, wh, g.tol_half);
-                        if (cls != 0) atomicAdd(&s_win[(wy - oy) * ww + (wx - ox)], cls == 1 ? 1u : 65536u);
-                    }
-                    it.advance();
+#pragma unroll
+            for (int r = 0; r < kWinRaysPerThread; r++) {
+                if (!live[r]) continue;
+                RayIter& w = it[r];
+                int wx = (w.x - x0) * qx, wy = (w.y - y0) * qy;
+                if (wx < ox || wx >= wxe || wy < oy || wy >= wye) continue;  // paused somewhere else
+                int lx_ = w.x, ly_ = w.y;
+                bool ended = true;
+                while (w.has_next(g.W, g.H)) {
+                    wx = (w.x - x0) * qx; wy = (w.y - y0) * qy;
+                    if (wx >= wxe || wy >= wye) { ended = false; break; }  // continues in a later window
+                    lx_ = w.x; ly_ = w.y;
+                    const float dX = sx - ((float)lx_ + 0.5f);
+                    const float dY = sy - ((float)ly_ + 0.5f);
+                    const float dist = __fsqrt_rn(dX * dX + dY * dY);
+                    const int cls = inverse_sensor_class(dist, ms[r], wh[r], g.tol_half);
+                    if (cls != 0) atomicAdd(&s_win[(wy - oy) * ww + (wx - ox)], cls == 1 ? 1u : 65536u);
+                    w.advance();
                 }
-                if (finished && any) {  // this window holds the ray's last cell: its box for the explored rectangle
+                if (ended) {  // the ray's last cell: its box for the explored rectangle
+                    live[r] = false;
                     atomicMin(&s_box[0], min(x0, lx_)); atomicMin(&s_box[1], min(y0, ly_));
                     atomicMax(&s_box[2], max(x0, lx_)); atomicMax(&s_box[3], max(y0, ly_));
                 }
