@@ -21,7 +21,7 @@ RESAMPLE_AUTO, RESAMPLE_LITERAL, RESAMPLE_FIXED = 0, 1, 2
 MAP_LOG, MAP_LIKELIHOOD, MAP_FREE_COUNT, MAP_OCC_COUNT = 0, 1, 2, 3
 POLICY_NEVER, POLICY_IF_NEFF_LOW, POLICY_ALWAYS = 0, 1, 2
 UPDATE_ATOMIC, UPDATE_SORTED = 0, 1
-IPC_NUM_HANDLES = 9
+IPC_NUM_HANDLES = 18
 MAX_BEAMS = 12800  # GMS_MAX_BEAMS
 PHASES = ("motion", "likelihood", "score", "normalise", "map_update", "resample", "map_copy", "exchange", "other")
 

@@ -105,6 +105,21 @@ struct gms_handle {
     const float4* peer_pose[2][kMaxRanks] = {};
     unsigned long long xseq = 0;
     bool direct = false;
+    // sharded normalise / resample (multi-rank shared map on the peer path): exchange areas (double-buffered by step
+    // parity), flags of the four rounds, and peer views of the arrays a remote parent is read from
+    unsigned char* xarea[2] = {nullptr, nullptr};
+    unsigned long long* xflags4 = nullptr;
+    int coarse_cap = 0;
+    size_t xarea_bytes = 0;
+    unsigned char* peer_xarea[2][kMaxRanks] = {};
+    unsigned long long* peer_xflags4[kMaxRanks] = {};
+    const unsigned long long* peer_cdf[kMaxRanks] = {};
+    const double* peer_w[2][kMaxRanks] = {};
+    const double* peer_lw[2][kMaxRanks] = {};
+    const int* peer_parents[kMaxRanks] = {};
+    bool sharded_post = false;   // enabled by gms_ipc_import for shared maps (GMS_SHARDED=0 keeps the replicated path)
+    bool tile_fx_sharded = false;  // np.fx holds the tile sums of the local block only
+    bool blocks_stale = false;   // pose / w / lw / parents hold only this rank's block: getters copy the rest from peers
     // beams: two step sets (the shared-map integration of step N may still read set N%2 on the side stream while
     // step N+1 uploads into the other) + one set for the GridMap operator entry points / the pose-optimiser hook
     int bcap = 0;
@@ -310,6 +325,7 @@ void free_all(gms_handle* h) {
         for (int k = 0; k < GMS_IPC_NUM_HANDLES; k++)
             if (h->ipc_opened[q][k]) cudaIpcCloseMemHandle(h->ipc_opened[q][k]);
     cudaFree(h->xlw[0]); cudaFree(h->xlw[1]); cudaFree(h->xflags); cudaFree(h->xticket);
+    cudaFree(h->xarea[0]); cudaFree(h->xarea[1]); cudaFree(h->xflags4);
     for (int i = 0; i < 2; i++) { cudaFree(h->pose[i]); cudaFree(h->w[i]); cudaFree(h->lw[i]); cudaFree(h->slot[i]); }
     cudaFree(h->parents); cudaFree(h->cdf); cudaFree(h->counts); cudaFree(h->lik); cudaFree(h->fac); cudaFree(h->rect);
     cudaFree(h->dirty); cudaFree(h->dirty_alt); cudaFree(h->word_off); cudaFree(h->tile_list); cudaFree(h->dup_rect);
@@ -324,7 +340,7 @@ void free_all(gms_handle* h) {
     cudaFree(h->sort.hist); cudaFree(h->sort.chunk_total); cudaFree(h->sort.offs); cudaFree(h->sort.key);
     cudaFree(h->sort.rank); cudaFree(h->sort.order);
     cudaFree(h->np.m); cudaFree(h->np.idx); cudaFree(h->np.s); cudaFree(h->np.ws); cudaFree(h->np.q); cudaFree(h->np.fx);
-    cudaFree(h->np.counter); cudaFree(h->wp_part); cudaFree(h->wp_counter);
+    cudaFree(h->np.x128); cudaFree(h->np.counter); cudaFree(h->wp_part); cudaFree(h->wp_counter);
     cudaFree(h->d_tmp); cudaFree(h->tmp_pose); cudaFree(h->tmp_slot); cudaFree(h->tmp_lw); cudaFree(h->st);
     if (h->h_st) cudaFreeHost(h->h_st);
     if (h->h_opt_poses) cudaFreeHost(h->h_opt_poses);
@@ -715,7 +731,7 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
         rc = launch_map_update(h, bs, h->pose[h->cur], h->lo, h->cnt, h->slot[h->slot_cur] + h->lo, B);
         if (rc) return rc;
     }
-    if (c.nranks > 1 && h->direct) {
+    if (c.nranks > 1 && h->direct && !h->sharded_post) {
         // this rank's log-weights -> every rank's receive buffer (NVLink stores), then one flag per receiver.  With
         // per-particle maps the flag also certifies that this rank's maps are final for the step (peers may pull
         // them when resampling), so the push is enqueued after the map integration.
@@ -759,11 +775,29 @@ int launch_select(gms_handle* h, int from, int to, double u01, unsigned long lon
     return GMS_OK;
 }
 
-// Peer exchange, no resampling since the last update: every rank holds only its own block of the moved poses; a
-// getter that needs all of them copies the other blocks out of their owners' arrays (peer mappings).  The
-// caller keeps the ranks between steps while it reads (documented in gms.h).
+// Peer exchange: between an update and the next full gather every rank holds only its own block of the moved
+// poses — and, with the sharded normalise / resample, of the weights, log-weights and parent indices.  A getter
+// that needs all of them copies the other blocks out of their owners' arrays (peer mappings).  The caller keeps
+// the ranks between steps while it reads (documented in gms.h).
 int materialize_poses(gms_handle* h) {
-    if (!(h->direct && h->poses_sharded)) return GMS_OK;
+    if (!h->direct) return GMS_OK;
+    if (h->blocks_stale) {
+        RemoteBlocks rb{};
+        rb.poses = pose_table(h, h->cur);
+        for (int q = 0; q < h->cfg.nranks; q++) {
+            const bool me = q == h->cfg.rank;
+            rb.w[q] = me ? h->w[h->cur] : h->peer_w[h->cur][q];
+            rb.lw[q] = me ? h->lw[h->cur] : h->peer_lw[h->cur][q];
+            rb.parents[q] = me ? h->parents : h->peer_parents[q];
+        }
+        rb.cnt = h->cnt; rb.lo = h->lo; rb.P = h->P;
+        LAUNCH(GMS_PHASE_COUNT - 1, k_fill_remote_blocks<<<blocks_for(h->P, 256), 256, 0, h->stream>>>(
+                                        rb, h->pose[h->cur], h->w[h->cur], h->lw[h->cur], h->parents));
+        h->blocks_stale = false;
+        h->poses_sharded = false;
+        return GMS_OK;
+    }
+    if (!h->poses_sharded) return GMS_OK;
     const PoseTable t = pose_table(h, h->cur);
     LAUNCH(GMS_PHASE_COUNT - 1, k_pose_fill_remote<<<blocks_for(h->P, 256), 256, 0, h->stream>>>(t, h->pose[h->cur], h->lo,
                                                                                            h->cnt, h->P));
@@ -771,8 +805,25 @@ int materialize_poses(gms_handle* h) {
     return GMS_OK;
 }
 
+// the exchange descriptor of the sharded normalise / resample kernels for the step with sequence number h->xseq
+Shard shard_of(const gms_handle* h) {
+    Shard sh{};
+    sh.nranks = h->cfg.nranks; sh.rank = h->cfg.rank; sh.seq = h->xseq; sh.coarse_cap = h->coarse_cap;
+    const int par = (int)(h->xseq & 1);
+    for (int q = 0; q < sh.nranks; q++) {
+        const bool me = q == h->cfg.rank;
+        sh.area[q] = me ? h->xarea[par] : h->peer_xarea[par][q];
+        sh.flags[q] = me ? h->xflags4 : h->peer_xflags4[q];
+        sh.cdfseg[q] = me ? static_cast<const unsigned long long*>(h->cdf) : h->peer_cdf[q];
+        sh.w[q] = me ? h->w[h->cur] : h->peer_w[h->cur][q];
+        sh.lw[q] = me ? h->lw[h->cur] : h->peer_lw[h->cur][q];
+    }
+    return sh;
+}
+
 // the part of a local-only resampling that was skipped (see resample_partial)
 int complete_resample(gms_handle* h) {
+    if (h->blocks_stale) { int rc_ = materialize_poses(h); if (rc_) return rc_; }  // sharded normalise / resample
     if (!h->resample_partial) return GMS_OK;
     h->resample_partial = false;
     h->stats_valid = false;  // Stats.strongest_now may be found among the children selected now
@@ -789,6 +840,25 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
         Phase ph(h, GMS_PHASE_RESAMPLE);
         const int nxt = h->cur ^ 1;
         const int m_begin = local_only ? h->lo : 0, m_count = local_only ? h->cnt : P;
+        if (h->sharded_post && h->direct && h->tile_fx_valid && h->tile_fx_sharded && h->resample_mode == GMS_RESAMPLE_FIXED) {
+            // every rank builds its own CDF segment and selects its own children (k_resample_shard)
+            SelectArgs a = select_args(h, h->cur, nxt, u01, h->resample_count, h->lo, h->cnt);
+            a.wp_counter = h->wp_counter;
+            const unsigned long long* fx = h->np.fx;
+            int ntiles = (h->cnt + 1023) / 1024, lo = h->lo, cnt = h->cnt;
+            Shard sh = shard_of(h);
+            const unsigned grid = (unsigned)std::max(1, std::min(h->num_sms * kNormCtasPerSm, std::max(ntiles, (cnt + kNormThreads - 1) / kNormThreads)));
+            LAUNCH_COOP(GMS_PHASE_RESAMPLE, k_resample_shard, grid, kNormThreads, 0, &a, &fx, &ntiles, &lo, &cnt, &sh);
+            h->resample_partial = false;
+            h->poses_sharded = false;
+            h->blocks_stale = true;
+            h->wpose_valid = false;
+            h->cur = nxt;
+            h->tile_fx_valid = false;
+            h->resample_count++;
+            return GMS_OK;
+        }
+        if (h->blocks_stale) { int rc_ = materialize_poses(h); if (rc_) return rc_; }  // the replicated CDF needs every rank's weights
         if (h->resample_mode == GMS_RESAMPLE_FIXED) {
             if (!h->tile_fx_valid)  // tile sums of trunc(w * 2^60): by-product of k_norm_coop / k_neff
                 LAUNCH(GMS_PHASE_RESAMPLE, k_neff<<<h->ntiles, 1024, 0, h->stream>>>(h->w[h->cur], P, h->ntiles, h->np, h->st));
@@ -801,7 +871,7 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
             h->wpose_valid = fold;
             const unsigned long long* fx = h->np.fx;
             int ntiles = h->ntiles;
-            const unsigned grid = (unsigned)std::max(1, std::min(h->num_sms * 6, std::max(ntiles, (m_count + kNormThreads - 1) / kNormThreads)));
+            const unsigned grid = (unsigned)std::max(1, std::min(h->num_sms * kNormCtasPerSm, std::max(ntiles, (m_count + kNormThreads - 1) / kNormThreads)));
             LAUNCH_COOP(GMS_PHASE_RESAMPLE, k_resample_coop, grid, kNormThreads, 0, &a, &fx, &ntiles);
         } else {
             h->wpose_valid = false;
@@ -863,8 +933,11 @@ int step_end(gms_handle* h, int policy, double u01) {
     h->stats_valid = false;
     const double* lw_src = h->lw[h->cur];
     const unsigned long long* xflags = nullptr;
+    const bool sharded = c.nranks > 1 && h->direct && h->sharded_post;
     if (c.nranks > 1) {
-        if (h->direct) {  // pushed by the peers (k_xpush_lw): the normalise kernel waits for every sender's flag
+        if (sharded) {  // every rank normalises its own block; three tiny exchange rounds inside the kernel
+            h->xseq++;
+        } else if (h->direct) {  // pushed by the peers (k_xpush_lw): the normalise kernel waits for every sender's flag
             h->xseq++;
             lw_src = h->xlw[h->xseq & 1];
             xflags = h->xflags;
@@ -877,12 +950,16 @@ int step_end(gms_handle* h, int policy, double u01) {
         Phase ph(h, GMS_PHASE_NORMALISE);
         NormArgs a{};
         a.lw = lw_src; a.lw_store = lw_src == h->lw[h->cur] ? nullptr : h->lw[h->cur];
-        a.w = h->w[h->cur]; a.poses = pose_table(h, h->cur); a.P = h->P; a.ntiles = h->ntiles; a.policy = policy;
+        a.w = h->w[h->cur]; a.poses = pose_table(h, h->cur); a.P = h->P; a.policy = policy;
+        a.lo = sharded ? h->lo : 0; a.cnt = sharded ? h->cnt : h->P; a.ntiles = (a.cnt + 1023) / 1024;
         a.np = h->np; a.st = h->st; a.xflags = xflags; a.nranks = c.nranks; a.seq = h->xseq;
         a.pose_local = (h->fold_wpose && (c.nranks == 1 || !h->direct)) ? h->pose[h->cur] : nullptr;
         a.wp_part = h->wp_part;
+        if (sharded) a.sh = shard_of(h);
         h->wpose_valid = a.pose_local != nullptr;
-        const unsigned grid = (unsigned)std::max(1, std::min(h->ntiles, h->num_sms * 6));
+        h->tile_fx_sharded = sharded;
+        if (sharded) h->blocks_stale = true;  // w / lw of the other ranks' blocks are not computed here
+        const unsigned grid = (unsigned)std::max(1, std::min(a.ntiles, h->num_sms * kNormCtasPerSm));
         LAUNCH_COOP(GMS_PHASE_NORMALISE, k_norm_coop, grid, kNormThreads, 0, &a);
         h->tile_fx_valid = true;
     }
@@ -1163,6 +1240,14 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
         CKC(cudaMemset(h->xflags, 0, kMaxRanks * 8));
         CKC(cudaMalloc((void**)&h->xticket, 4));
         CKC(cudaMemset(h->xticket, 0, 4));
+        h->coarse_cap = (h->cnt + kCoarseStep - 1) / kCoarseStep + 1;
+        h->xarea_bytes = sizeof(XArea) + (size_t)kMaxRanks * h->coarse_cap * 8;
+        for (int i = 0; i < 2; i++) {
+            CKC(cudaMalloc((void**)&h->xarea[i], h->xarea_bytes));
+            CKC(cudaMemset(h->xarea[i], 0, h->xarea_bytes));
+        }
+        CKC(cudaMalloc((void**)&h->xflags4, 4 * kMaxRanks * 8));
+        CKC(cudaMemset(h->xflags4, 0, 4 * kMaxRanks * 8));
     }
     h->d_tmp_bytes = std::max(h->cells * 8, P * 24);
     CKC(cudaMalloc(&h->d_tmp, h->d_tmp_bytes));
@@ -1192,6 +1277,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
         CKC(cudaMalloc((void**)&h->np.ws, nt * 8));
         CKC(cudaMalloc((void**)&h->np.q, nt * 8));
         CKC(cudaMalloc((void**)&h->np.fx, nt * 8));
+        CKC(cudaMalloc((void**)&h->np.x128, nt * 48));
         CKC(cudaMalloc((void**)&h->np.counter, 4));
         CKC(cudaMemset(h->np.counter, 0, 4));
         CKC(cudaMalloc((void**)&h->wp_part, (nt * (1024 / kNormThreads) + 4) * 32));  // per chunk of kNormThreads children
@@ -1648,7 +1734,8 @@ EXPORT int gms_ipc_export(gms_handle* h, void* handles) {
     static_assert(sizeof(cudaIpcMemHandle_t) == GMS_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
     cudaIpcMemHandle_t* out = static_cast<cudaIpcMemHandle_t*>(handles);
     void* ptr[GMS_IPC_NUM_HANDLES] = {h->counts, h->lik, h->rect, h->dirty, h->xlw[0], h->xlw[1], h->xflags,
-                                      h->pose[0], h->pose[1]};
+                                      h->pose[0], h->pose[1], h->w[0], h->w[1], h->lw[0], h->lw[1], h->parents,
+                                      h->cdf, h->xarea[0], h->xarea[1], h->xflags4};
     for (int k = 0; k < GMS_IPC_NUM_HANDLES; k++) CK(cudaIpcGetMemHandle(&out[k], ptr[k]));
     return GMS_OK;
 }
@@ -1659,7 +1746,8 @@ EXPORT int gms_ipc_import(gms_handle* h, const void* all_handles) {
     const cudaIpcMemHandle_t* in = static_cast<const cudaIpcMemHandle_t*>(all_handles);
     for (int q = 0; q < h->cfg.nranks; q++) {
         void* ptr[GMS_IPC_NUM_HANDLES] = {h->counts, h->lik, h->rect, h->dirty, h->xlw[0], h->xlw[1], h->xflags,
-                                          h->pose[0], h->pose[1]};
+                                          h->pose[0], h->pose[1], h->w[0], h->w[1], h->lw[0], h->lw[1], h->parents,
+                                          h->cdf, h->xarea[0], h->xarea[1], h->xflags4};
         if (q != h->cfg.rank)
             for (int k = 0; k < GMS_IPC_NUM_HANDLES; k++) {
                 if (h->ipc_opened[q][k]) { ptr[k] = h->ipc_opened[q][k]; continue; }
@@ -1675,9 +1763,21 @@ EXPORT int gms_ipc_import(gms_handle* h, const void* all_handles) {
         h->peer_flags[q] = static_cast<unsigned long long*>(ptr[6]);
         h->peer_pose[0][q] = static_cast<const float4*>(ptr[7]);
         h->peer_pose[1][q] = static_cast<const float4*>(ptr[8]);
+        h->peer_w[0][q] = static_cast<const double*>(ptr[9]);
+        h->peer_w[1][q] = static_cast<const double*>(ptr[10]);
+        h->peer_lw[0][q] = static_cast<const double*>(ptr[11]);
+        h->peer_lw[1][q] = static_cast<const double*>(ptr[12]);
+        h->peer_parents[q] = static_cast<const int*>(ptr[13]);
+        h->peer_cdf[q] = static_cast<const unsigned long long*>(ptr[14]);
+        h->peer_xarea[0][q] = static_cast<unsigned char*>(ptr[15]);
+        h->peer_xarea[1][q] = static_cast<unsigned char*>(ptr[16]);
+        h->peer_xflags4[q] = static_cast<unsigned long long*>(ptr[17]);
     }
     h->peers_ready = true;
     h->direct = true;
+    // shared map: every rank normalises and resamples only its own block (three tiny exchange rounds per step)
+    h->sharded_post = h->cfg.map_mode == GMS_MAP_SHARED &&
+                      !(std::getenv("GMS_SHARDED") && std::atoi(std::getenv("GMS_SHARDED")) == 0);
     return GMS_OK;
 }
 

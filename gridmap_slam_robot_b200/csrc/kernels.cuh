@@ -47,7 +47,8 @@ struct NormPartials {   // partial results of normalise: per score CTA (m, idx, 
     double* s;          // sum exp(lw - tile max)
     double* ws;         // sum of normalised weights of the tile
     double* q;          // sum of squared normalised weights of the tile
-    unsigned long long* fx;  // sum of trunc(w * 2^60) of the tile (feeds k_cdf_fixed)
+    unsigned long long* fx;  // sum of trunc(w * 2^60) of the tile (feeds the fixed-point CDF)
+    unsigned long long* x128;  // 6 u64 per tile: exact 128-bit sums of exp(lw - M), w^2, w (U128 below)
     unsigned* counter;  // last-block-done ticket
 };
 #define kNegInf (__longlong_as_double((long long)0xfff0000000000000ULL))
@@ -1087,7 +1088,7 @@ __global__ void __launch_bounds__(kWinThreads, 3) k_map_update_win(const float4*
     extern __shared__ __align__(16) uint32_t s_win[];
     __shared__ int s_reach[2];
     __shared__ int s_box[4];
-    __shared__ int s_nrays;
+    __shared__ int s_nrays, s_rowmax;
     __shared__ unsigned short s_rays[kWinMaxBeams];
     const int tid = threadIdx.x;
     const int li = blockIdx.x >> 2, quad = blockIdx.x & 3;
@@ -1164,6 +1165,7 @@ __global__ void __launch_bounds__(kWinThreads, 3) k_map_update_win(const float4*
             const int wxe = min(ox + WX, RX), wye = min(oy + WY, RY);  // window = [ox, wxe) x [oy, wye)
             const int ww = wxe - ox, nwin = ww * (wye - oy);
             for (int i = tid; i < nwin; i += kWinThreads) s_win[i] = 0u;
+            if (tid == 0) s_rowmax = -1;
             __syncthreads();
 #pragma unroll
             for (int r = 0; r < kWinRaysPerThread; r++) {
@@ -1184,6 +1186,7 @@ __global__ void __launch_bounds__(kWinThreads, 3) k_map_update_win(const float4*
                     if (cls != 0) atomicAdd(&s_win[(wy - oy) * ww + (wx - ox)], cls == 1 ? 1u : 65536u);
                     w.advance();
                 }
+                atomicMax(&s_rowmax, min(wy, wye - 1) - oy);  // wy only grows: the last one is the furthest row touched
                 if (ended) {  // the ray's last cell: its box for the explored rectangle
                     live[r] = false;
                     atomicMin(&s_box[0], min(x0, lx_)); atomicMin(&s_box[1], min(y0, ly_));
@@ -1192,44 +1195,44 @@ __global__ void __launch_bounds__(kWinThreads, 3) k_map_update_win(const float4*
             }
             __syncthreads();
             // flush: plain coalesced read-modify-write of the cells this scan touched (rows of the window are
-            // contiguous in the map, forwards or backwards).  The start row and column (wx == 0 or wy == 0) are
-            // shared with the neighbouring quadrants' CTAs, which flush concurrently: one 64-bit atomic each.
-            for (int i0 = tid; i0 < nwin; i0 += 8 * kWinThreads) {
-                uint32_t inc[8];
-                int cx[8], cy[8];
-                unsigned long long old[8];
+            // contiguous in the map, forwards or backwards).  A warp takes a row, a lane four cells at a time; rows
+            // beyond the last touched one are skipped.  The start row and column (wx == 0 or wy == 0) are shared
+            // with the neighbouring quadrants' CTAs, which flush concurrently: one 64-bit atomic each.
+            const int rows = min(wye - oy, s_rowmax + 1);
+            for (int yy = tid >> 5; yy < rows; yy += kWinThreads / 32) {
+                const int wy = oy + yy, cy = y0 + wy * qy;
+                const uint32_t* row = s_win + yy * ww;
+                for (int xg = (tid & 31) * 4; xg < ww; xg += 128) {
+                    uint32_t inc[4];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int i = i0 + u * kWinThreads;
-                    inc[u] = i < nwin ? s_win[i] : 0u;
-                    if (inc[u]) {
-                        const int yy = i / ww, xx = i - yy * ww;
-                        const int wx = ox + xx, wy = oy + yy;
-                        cx[u] = x0 + wx * qx; cy[u] = y0 + wy * qy;
-                        unsigned long long* cell = reinterpret_cast<unsigned long long*>(map + ((size_t)cx[u] + (size_t)cy[u] * g.W));
-                        if (wx == 0 || wy == 0) {
+                    for (int u = 0; u < 4; u++) inc[u] = xg + u < ww ? row[xg + u] : 0u;
+                    if ((inc[0] | inc[1] | inc[2] | inc[3]) == 0u) continue;
+                    unsigned long long old[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (!inc[u]) continue;
+                        const int wx = ox + xg + u;
+                        unsigned long long* cell = reinterpret_cast<unsigned long long*>(map + ((size_t)(x0 + wx * qx) + (size_t)cy * g.W));
+                        if (wx == 0 || wy == 0)
                             old[u] = atomicAdd(cell, (unsigned long long)(inc[u] & 0xffffu) | ((unsigned long long)(inc[u] >> 16) << 32));
-                            cx[u] |= 0x40000000;  // already stored
-                        } else {
+                        else
                             old[u] = __ldcg(cell);
-                        }
                     }
-                }
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    if (!inc[u]) continue;
-                    const bool stored = (cx[u] & 0x40000000) != 0;
-                    const int x = cx[u] & 0x3fffffff, y = cy[u];
-                    const uint32_t of = (uint32_t)old[u], oo = (uint32_t)(old[u] >> 32);
-                    const uint32_t nf = of + (inc[u] & 0xffffu), no = oo + (inc[u] >> 16);
-                    if (!stored)
-                        __stcg(reinterpret_cast<unsigned long long*>(map + ((size_t)x + (size_t)y * g.W)),
-                               (unsigned long long)nf | ((unsigned long long)no << 32));
-                    bool flip;
-                    if (oo == 0 && no == 0) flip = of == 0;       // never occupied: flips on its first free hit
-                    else if (of == 0 && nf == 0) flip = oo == 0;  // never freed: flips on its first occupied hit
-                    else flip = cell_code(of, oo, g) != cell_code(nf, no, g);
-                    if (flip) mark_dirty(bitmap, x, y, g);
+                    for (int u = 0; u < 4; u++) {
+                        if (!inc[u]) continue;
+                        const int wx = ox + xg + u, x = x0 + wx * qx;
+                        const uint32_t of = (uint32_t)old[u], oo = (uint32_t)(old[u] >> 32);
+                        const uint32_t nf = of + (inc[u] & 0xffffu), no = oo + (inc[u] >> 16);
+                        if (!(wx == 0 || wy == 0))
+                            __stcg(reinterpret_cast<unsigned long long*>(map + ((size_t)x + (size_t)cy * g.W)),
+                                   (unsigned long long)nf | ((unsigned long long)no << 32));
+                        bool flip;
+                        if (oo == 0 && no == 0) flip = of == 0;       // never occupied: flips on its first free hit
+                        else if (of == 0 && nf == 0) flip = oo == 0;  // never freed: flips on its first occupied hit
+                        else flip = cell_code(of, oo, g) != cell_code(nf, no, g);
+                        if (flip) mark_dirty(bitmap, x, cy, g);
+                    }
                 }
             }
             __syncthreads();
@@ -1571,83 +1574,186 @@ __device__ __forceinline__ void block_argmax_1024(double& best, int& bi, double*
     }
 }
 
-// Normalise + Neff + strongest in ONE cooperative launch (grid <= one CTA per SM, grid-wide barriers).
-// Every sum over particles runs over FIXED tiles of 1024 consecutive particle indices, each reduced by a fixed
-// shuffle tree, and the tile results are combined in tile order: the results do not depend on the grid
-// size, on which CTA handled a tile, on the scoring kernel's processing order, or on how many ranks share the
-// particle set (run-to-run, rank-to-rank bit-identical).
-//   phase 0  (multi-rank peer exchange) wait until every rank's log-weights of exchange `seq` have landed
-//   phase 1  per tile: (max, first arg-max, sum exp(lw - tile max)); ONE grid barrier; every CTA then folds the
-//            tile partials in tile order -> M (SLAM.java:110-115 keeps the first maximum: strict >) and
-//            S = sum_t s_t * exp(m_t - M)
-//   phase 2  w_i = exp(lw_i - M) / S (SLAM.java:119-121), tile sums of w, w^2, trunc(w * 2^60)
-//   final    (last CTA to finish) Neff = (sum w)^2 / sum w^2 (SLAM.java:180-190), strongest pose snapshot,
-//            resample decision
+// ---- exact sums ---------------------------------------------------------------------------------------------
+// Sums over particles that must not depend on how the particles are partitioned (tiles, CTAs, ranks) are
+// accumulated EXACTLY: every non-negative term x < 2^27 is converted to the integer floor(x * 2^100) (128 bits)
+// and the integers are added.  Integer addition is associative, so any grouping gives the same total; the
+// truncation error is < 2^-100 per term.  (Up to 2^20 terms of at most 2^127 / 2^20 each: no overflow.)
+struct U128 {
+    unsigned long long lo, hi;
+};
+__device__ __forceinline__ U128 fx100(double x) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
+    const int e = (int)((bits >> 52) & 0x7ffull);
+    U128 r{0ull, 0ull};
+    if (e == 0 || e == 0x7ff || (long long)bits < 0) return r;  // zero / subnormal / non-finite / negative: no contribution
+    const unsigned long long mant = (bits & 0xfffffffffffffull) | (1ull << 52);
+    const int sh = e - 975;  // x = mant * 2^(e - 1075); floor(x * 2^100) = mant shifted by e - 975
+    if (sh >= 64) { r.hi = mant << (sh - 64); }
+    else if (sh > 0) { r.lo = mant << sh; r.hi = mant >> (64 - sh); }
+    else if (sh > -64) { r.lo = mant >> (-sh); }
+    return r;
+}
+__device__ __forceinline__ void add128(U128& a, const U128 b) {
+    const unsigned long long lo = a.lo + b.lo;
+    a.hi += b.hi + (lo < a.lo ? 1ull : 0ull);
+    a.lo = lo;
+}
+__device__ __forceinline__ double to_double100(const U128 a) {  // deterministic function of the integer
+    return (double)a.hi * 0x1p-36 + (double)a.lo * 0x1p-100;
+}
+template <int NT>
+__device__ __forceinline__ U128 block_sum128_nt(U128 v, unsigned long long* s_buf /* 2 * NT / 32 */) {
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        U128 u;
+        u.lo = __shfl_xor_sync(0xffffffffu, v.lo, o);
+        u.hi = __shfl_xor_sync(0xffffffffu, v.hi, o);
+        add128(v, u);
+    }
+    __syncthreads();
+    if (lane == 0) { s_buf[2 * wid] = v.lo; s_buf[2 * wid + 1] = v.hi; }
+    __syncthreads();
+    v.lo = s_buf[2 * (lane & (NW - 1))]; v.hi = s_buf[2 * (lane & (NW - 1)) + 1];
+#pragma unroll
+    for (int o = NW / 2; o > 0; o >>= 1) {
+        U128 u;
+        u.lo = __shfl_xor_sync(0xffffffffu, v.lo, o);
+        u.hi = __shfl_xor_sync(0xffffffffu, v.hi, o);
+        add128(v, u);
+    }
+    return v;
+}
+
+// ---- sharded normalise / resample: what ranks tell each other (a few hundred bytes per step and rank) -----------
+// Multi-rank shared map on the peer path: every rank normalises ONLY its own block of particles and selects ONLY its
+// own children.  Three tiny all-to-all rounds replace the exchange of per-particle data:
+//   A  {max log-weight of the block, its first index, that particle's pose}        -> global M, strongest, its pose
+//   B  exact sum of exp(lw - M) over the block                                     -> S
+//   C  fixed-point weight total of the block (CDF offsets), exact sums of w, w^2   -> Neff, resample decision
+// and, only when a resampling follows,
+//   D  every 64th value of the block's (block-relative) fixed-point CDF            -> children find their parent's
+//      rank and 64-particle bucket locally, and finish the search with <= 6 reads of that rank's CDF segment
+// Each record is stored into every rank's XArea (peer-mapped, double-buffered by step parity), followed by
+// __threadfence_system and a release store of the step sequence number into that rank's flag for the round;
+// consumers poll their own flags (ld.acquire.sys, bounded spin -> Stats.xerror).
+constexpr int kCoarseStep = 64;
+struct XRecA { double m; int idx; float x, y, t; int pad; };
+struct XRecB { unsigned long long lo, hi; };
+struct XRecC { unsigned long long T, q_lo, q_hi, w_lo, w_hi, pad; };
+struct XArea {  // followed in memory by kMaxRanks coarse tables of `coarse_cap` u64 each
+    XRecA a[kMaxRanks];
+    XRecB b[kMaxRanks];
+    XRecC c[kMaxRanks];
+};
+struct Shard {           // by value in the kernel arguments; nranks == 0: not sharded
+    int nranks, rank;
+    unsigned long long seq;
+    unsigned char* area[kMaxRanks];         // every rank's XArea of this step's parity (area[rank] = my own)
+    unsigned long long* flags[kMaxRanks];   // every rank's flag block: [round][sender]
+    const unsigned long long* cdfseg[kMaxRanks];  // every rank's block-relative CDF segment (k_resample_coop)
+    const double* w[kMaxRanks];             // every rank's weight / log-weight / pose arrays of the current generation
+    const double* lw[kMaxRanks];
+    int coarse_cap;
+};
+__device__ __forceinline__ unsigned long long* coarse_of(unsigned char* area, int coarse_cap, int sender) {
+    return reinterpret_cast<unsigned long long*>(area + sizeof(XArea)) + (size_t)sender * coarse_cap;
+}
+// threads 0 .. nranks-1 of the calling CTA: wait until every rank's flag of `round` carries `seq`
+__device__ __forceinline__ void shard_wait(const Shard& sh, int round, Stats* st) {
+    if ((int)threadIdx.x < sh.nranks) {
+        const unsigned long long* f = sh.flags[sh.rank] + round * kMaxRanks + threadIdx.x;
+        unsigned long long v = 0;
+        for (long long spins = 0; spins < 8000000; spins++) {  // ~4 s with the sleeps: never hang the device
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= sh.seq) break;
+            __nanosleep(100);
+        }
+        if (v < sh.seq) st->xerror = 1;
+    }
+    __syncthreads();  // the acquiring threads' view is handed to the whole CTA
+}
+// thread q < nranks of ONE CTA: after it stored its record into rank q's area: fence, then raise my flag there
+__device__ __forceinline__ void shard_signal(const Shard& sh, int round) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(sh.flags[threadIdx.x] + round * kMaxRanks + sh.rank), "l"(sh.seq)
+                 : "memory");
+}
+
+// Normalise + Neff + strongest in ONE cooperative launch (grid barriers inside), over the block [lo, lo + cnt) of
+// the particle index: the whole set (single rank, or lw replicated by k_xpush_lw / an all-gather) or this rank's
+// shard (see above).  M and the first arg-max are order-independent by nature; S, sum w and sum w^2 are exact
+// integer sums (U128); the CDF is u64 fixed point.  So the weights, Neff, the strongest particle and the parent
+// indices do not depend on the grid size, on which CTA handled which tile, on the scoring kernel's processing
+// order, or on how many ranks share the particle set (run-to-run, rank-to-rank bit-identical).
+//   phase 0  (replicated peer exchange only) wait until every rank's log-weights have landed
+//   phase 1  tile maxima -> grid barrier -> block max [round A] -> M (SLAM.java:110-115 keeps the first maximum)
+//   phase 2  e_i = exp(lw_i - M), exact tile sums -> grid barrier -> block sum [round B] -> S
+//   phase 3  w_i = e_i / S (SLAM.java:119-121); tile sums of trunc(w * 2^60), exact tile sums of w and w^2
+//   final    (last CTA to finish) block totals [round C] -> Neff = (sum w)^2 / sum w^2 (SLAM.java:180-190),
+//            strongest pose snapshot, resample decision
 struct NormArgs {
-    const double* lw;    // all P log-weights (own array, or the peer-exchange receive buffer)
-    double* lw_store;    // peer exchange: the received values are also filed in the handle's own lw array (else null)
+    const double* lw;    // log-weights, indexed by GLOBAL particle index (own array, or the lw receive buffer)
+    double* lw_store;    // replicated peer exchange: received values are also filed in the handle's own lw array
     double* w;
     PoseTable poses;
-    int P, ntiles, policy;
+    int P, lo, cnt, ntiles, policy;  // ntiles = ceil(cnt / 1024), tiles start at lo
     NormPartials np;
     Stats* st;
-    const unsigned long long* xflags;  // nullptr unless the peer exchange is active
+    const unsigned long long* xflags;  // replicated peer exchange: arrival flags of the log-weights, else nullptr
     int nranks;
     unsigned long long seq;
-    const float4* pose_local;  // all P poses in local memory (single rank / imported records), else nullptr: the
-    double* wp_part;           // weighted pose (SLAM.getWeightedPose) then comes out of this kernel too
+    const float4* pose_local;  // fold the weighted pose (SLAM.getWeightedPose) into this launch: all poses of the block
+    double* wp_part;           // are local (single rank / imported records), else nullptr
+    Shard sh;
 };
-constexpr int kNormThreads = 256;  // 4 consecutive particles per thread: a 1024-particle tile per CTA iteration;
-                                   // 6 CTAs/SM (888 co-resident) cover the 782 tiles of 8 x 100k particles in one wave
-__global__ void __launch_bounds__(kNormThreads, 6) k_norm_coop(NormArgs a) {
+constexpr int kNormThreads = 256;   // 4 consecutive particles per thread: a 1024-particle tile per CTA iteration
+constexpr int kNormCtasPerSm = 4;   // <= 64 registers (the exact 128-bit sums need them): 592 co-resident CTAs
+__global__ void __launch_bounds__(kNormThreads, kNormCtasPerSm) k_norm_coop(NormArgs a) {
     cg::grid_group grid = cg::this_grid();
     constexpr int NT = kNormThreads, NW = NT / 32;
     __shared__ double s_key[NW];
     __shared__ int s_idx[NW];
-    __shared__ double s_d[NW];
-    __shared__ double s_v[5 * NW];
-    __shared__ unsigned long long s_u[NW];
+    __shared__ double s_v[3 * NW];
+    __shared__ unsigned long long s_u[2 * NW];
     __shared__ bool s_last;
     const int tid = threadIdx.x, G = gridDim.x;
+    const bool sharded = a.sh.nranks > 0;
+    const int end = a.lo + a.cnt;
     if (a.xflags) {
         if (tid < a.nranks) {  // every CTA polls for itself: no extra grid barrier
             unsigned long long v = 0;
             long long spins = 0;
-            for (; spins < 8000000; spins++) {  // ~4 s with the sleeps: never hang the device
+            for (; spins < 8000000; spins++) {
                 asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.xflags + tid) : "memory");
                 if (v >= a.seq) break;
                 __nanosleep(200);
             }
             if (v < a.seq) a.st->xerror = 1;
         }
-        __syncthreads();  // the acquiring threads' view is handed to the whole CTA
+        __syncthreads();
     }
-    // phase 1: per fixed tile, (max, first arg-max, sum exp(lw - tile max))
+    // phase 1: per tile, (max, first arg-max)
     for (int t = blockIdx.x; t < a.ntiles; t += G) {
-        const int i0 = t * 1024 + tid * 4;
-        double v[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = i0 + j < a.P ? __ldcg(a.lw + i0 + j) : kNegInf;
-        if (a.lw_store)
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (i0 + j < a.P) a.lw_store[i0 + j] = v[j];
+        const int i0 = a.lo + t * 1024 + tid * 4;
         double best = kNegInf;
         int bi = 0x7fffffff;
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (v[j] > best) { best = v[j]; bi = i0 + j; }  // ascending index: a later equal value never replaces
+        for (int j = 0; j < 4; j++) {
+            if (i0 + j < end) {
+                const double v = __ldcg(a.lw + i0 + j);
+                if (a.lw_store) a.lw_store[i0 + j] = v;
+                if (v > best) { best = v; bi = i0 + j; }  // ascending index: a later equal value never replaces
+            }
+        }
         block_argmax_nt<NT>(best, bi, s_key, s_idx);
-        double e = 0.0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) e += i0 + j < a.P ? exp(v[j] - best) : 0.0;
-        const double sum = block_reduce_nt<NT>(e, SumOp(), s_d);
-        if (tid == 0) { a.np.m[t] = best; a.np.idx[t] = bi; a.np.s[t] = sum; }
+        if (tid == 0) { a.np.m[t] = best; a.np.idx[t] = bi; }
     }
     __threadfence();
     grid.sync();
     if (*(volatile int*)&a.st->xerror) return;  // uniform: set (if at all) before the barrier
-    // every CTA combines the tile partials in the same fixed order -> (M, first arg-max, S)
     double best = kNegInf;
     int bi = 0x7fffffff;
     for (int c = tid; c < a.ntiles; c += NT) {
@@ -1656,36 +1762,91 @@ __global__ void __launch_bounds__(kNormThreads, 6) k_norm_coop(NormArgs a) {
         if (v > best || (v == best && vi < bi)) { best = v; bi = vi; }
     }
     block_argmax_nt<NT>(best, bi, s_key, s_idx);
-    double acc = 0.0;
-    for (int c = tid; c < a.ntiles; c += NT) acc += __ldcg(a.np.s + c) * exp(__ldcg(a.np.m + c) - best);
-    const double S = block_reduce_nt<NT>(acc, SumOp(), s_d);
-    // phase 2: w_i = exp(lw_i - M) / S, tile sums of w, w^2, trunc(w * 2^60) (+ weighted pose terms)
+    float4 bpose = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sharded) {
+        if (blockIdx.x == 0 && tid < a.sh.nranks) {  // round A
+            const float4 p = a.poses.at(bi);  // my own block: local
+            XRecA r; r.m = best; r.idx = bi; r.x = p.x; r.y = p.y; r.t = p.z; r.pad = 0;
+            reinterpret_cast<XArea*>(a.sh.area[tid])->a[a.sh.rank] = r;
+            shard_signal(a.sh, 0);
+        }
+        shard_wait(a.sh, 0, a.st);
+        const XArea* mine = reinterpret_cast<const XArea*>(a.sh.area[a.sh.rank]);
+        best = kNegInf; bi = 0x7fffffff;
+        for (int q = 0; q < a.sh.nranks; q++) {
+            const volatile XRecA* r = &mine->a[q];
+            const double rm = r->m;
+            const int ri = r->idx;
+            if (rm > best || (rm == best && ri < bi)) { best = rm; bi = ri; bpose = make_float4(r->x, r->y, r->t, 0.f); }
+        }
+    }
+    // phase 2: e_i = exp(lw_i - M) (parked in w), exact tile sums
     for (int t = blockIdx.x; t < a.ntiles; t += G) {
-        const int i0 = t * 1024 + tid * 4;
-        double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // w, w^2, w*x, w*y, w*angleConstrain(theta)
+        const int i0 = a.lo + t * 1024 + tid * 4;
+        U128 acc{0ull, 0ull};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (i0 + j < end) {
+                const double e = exp(__ldcg(a.lw + i0 + j) - best);
+                a.w[i0 + j] = e;
+                add128(acc, fx100(e));
+            }
+        }
+        acc = block_sum128_nt<NT>(acc, s_u);
+        if (tid == 0) { a.np.x128[6 * t] = acc.lo; a.np.x128[6 * t + 1] = acc.hi; }
+    }
+    __threadfence();
+    grid.sync();
+    U128 sacc{0ull, 0ull};
+    for (int c = tid; c < a.ntiles; c += NT) add128(sacc, U128{__ldcg(a.np.x128 + 6 * c), __ldcg(a.np.x128 + 6 * c + 1)});
+    sacc = block_sum128_nt<NT>(sacc, s_u);
+    if (sharded) {
+        if (blockIdx.x == 0 && tid < a.sh.nranks) {  // round B
+            reinterpret_cast<XArea*>(a.sh.area[tid])->b[a.sh.rank] = XRecB{sacc.lo, sacc.hi};
+            shard_signal(a.sh, 1);
+        }
+        shard_wait(a.sh, 1, a.st);
+        const XArea* mine = reinterpret_cast<const XArea*>(a.sh.area[a.sh.rank]);
+        sacc = U128{0ull, 0ull};
+        for (int q = 0; q < a.sh.nranks; q++) {
+            const volatile XRecB* r = &mine->b[q];
+            add128(sacc, U128{r->lo, r->hi});
+        }
+    }
+    const double S = to_double100(sacc);
+    // phase 3: w_i = e_i / S; tile sums
+    for (int t = blockIdx.x; t < a.ntiles; t += G) {
+        const int i0 = a.lo + t * 1024 + tid * 4;
+        U128 qacc{0ull, 0ull}, wacc{0ull, 0ull};
+        double v[3] = {0.0, 0.0, 0.0};  // w*x, w*y, w*angleConstrain(theta) (folded weighted pose only)
         unsigned long long fx = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int i = i0 + j;
-            if (i < a.P) {
-                const double wi = exp(__ldcg(a.lw + i) - best) / S;
+            if (i < end) {
+                const double wi = a.w[i] / S;
                 a.w[i] = wi;
-                v[0] += wi; v[1] += wi * wi;
                 fx += (unsigned long long)(wi * 0x1p60);
+                add128(wacc, fx100(wi));
+                add128(qacc, fx100(wi * wi));
                 if (a.pose_local) {  // SLAM.getWeightedPose SLAM.java:165-178
                     const float4 p = a.pose_local[i];
-                    v[2] += (double)p.x * wi; v[3] += (double)p.y * wi; v[4] += angle_constrain((double)p.z) * wi;
+                    v[0] += (double)p.x * wi; v[1] += (double)p.y * wi; v[2] += angle_constrain((double)p.z) * wi;
                 }
             }
         }
-        block_sum_vec_nt<NT, 5>(v, s_v);
+        qacc = block_sum128_nt<NT>(qacc, s_u);
+        wacc = block_sum128_nt<NT>(wacc, s_u);
         fx = block_reduce_nt<NT>(fx, SumU64(), s_u);
+        if (a.pose_local) block_sum_vec_nt<NT, 3>(v, s_v);
         if (tid == 0) {
-            a.np.ws[t] = v[0]; a.np.q[t] = v[1]; a.np.fx[t] = fx;
-            if (a.pose_local) { a.wp_part[4 * t] = v[2]; a.wp_part[4 * t + 1] = v[3]; a.wp_part[4 * t + 2] = v[4]; }
+            a.np.fx[t] = fx;
+            a.np.x128[6 * t + 2] = qacc.lo; a.np.x128[6 * t + 3] = qacc.hi;
+            a.np.x128[6 * t + 4] = wacc.lo; a.np.x128[6 * t + 5] = wacc.hi;
+            if (a.pose_local) { a.wp_part[4 * t] = v[0]; a.wp_part[4 * t + 1] = v[1]; a.wp_part[4 * t + 2] = v[2]; }
         }
     }
-    // the last CTA to finish folds the tile sums (fixed order) and publishes the step's statistics
+    // the last CTA to finish folds the tile sums and publishes the step's statistics
     if (tid == 0) {
         __threadfence();
         s_last = atomicAdd(a.np.counter, 1u) == (unsigned)G - 1u;
@@ -1693,22 +1854,41 @@ __global__ void __launch_bounds__(kNormThreads, 6) k_norm_coop(NormArgs a) {
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    double f[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    U128 qt{0ull, 0ull}, wt{0ull, 0ull};
+    unsigned long long T = 0;
+    double f[3] = {0.0, 0.0, 0.0};
     for (int c = tid; c < a.ntiles; c += NT) {
-        f[0] += __ldcg(a.np.ws + c);
-        f[1] += __ldcg(a.np.q + c);
-        if (a.pose_local) {
-            f[2] += __ldcg(a.wp_part + 4 * c); f[3] += __ldcg(a.wp_part + 4 * c + 1); f[4] += __ldcg(a.wp_part + 4 * c + 2);
+        add128(qt, U128{__ldcg(a.np.x128 + 6 * c + 2), __ldcg(a.np.x128 + 6 * c + 3)});
+        add128(wt, U128{__ldcg(a.np.x128 + 6 * c + 4), __ldcg(a.np.x128 + 6 * c + 5)});
+        T += __ldcg(a.np.fx + c);
+        if (a.pose_local) { f[0] += __ldcg(a.wp_part + 4 * c); f[1] += __ldcg(a.wp_part + 4 * c + 1); f[2] += __ldcg(a.wp_part + 4 * c + 2); }
+    }
+    qt = block_sum128_nt<NT>(qt, s_u);
+    wt = block_sum128_nt<NT>(wt, s_u);
+    T = block_reduce_nt<NT>(T, SumU64(), s_u);
+    if (a.pose_local) block_sum_vec_nt<NT, 3>(f, s_v);
+    if (sharded) {
+        if (tid < a.sh.nranks) {  // round C
+            XRecC r; r.T = T; r.q_lo = qt.lo; r.q_hi = qt.hi; r.w_lo = wt.lo; r.w_hi = wt.hi; r.pad = 0;
+            reinterpret_cast<XArea*>(a.sh.area[tid])->c[a.sh.rank] = r;
+            shard_signal(a.sh, 2);
+        }
+        shard_wait(a.sh, 2, a.st);
+        const XArea* mine = reinterpret_cast<const XArea*>(a.sh.area[a.sh.rank]);
+        qt = U128{0ull, 0ull}; wt = U128{0ull, 0ull};
+        for (int q = 0; q < a.sh.nranks; q++) {
+            const volatile XRecC* r = &mine->c[q];
+            add128(qt, U128{r->q_lo, r->q_hi});
+            add128(wt, U128{r->w_lo, r->w_hi});
         }
     }
-    block_sum_vec_nt<NT, 5>(f, s_v);
-    const double sa = f[0], sq = f[1];
     if (tid == 0) {
         Stats* st = a.st;
+        const double sa = to_double100(wt), sq = to_double100(qt);
         if (a.pose_local) {
-            st->weighted_pose[0] = (float)(f[2] / sa);
-            st->weighted_pose[1] = (float)(f[3] / sa);
-            st->weighted_pose[2] = (float)(f[4] / sa);
+            st->weighted_pose[0] = (float)(f[0] / sa);
+            st->weighted_pose[1] = (float)(f[1] / sa);
+            st->weighted_pose[2] = (float)(f[2] / sa);
         }
         const double neff = (sa * sa) / sq;
         st->neff = neff;
@@ -1717,7 +1897,7 @@ __global__ void __launch_bounds__(kNormThreads, 6) k_norm_coop(NormArgs a) {
         st->strongest = bi;
         st->strongest_now = bi;
         st->strongest_w = 1.0 / S;
-        const float4 p = a.poses.at(bi);
+        const float4 p = sharded ? bpose : a.poses.at(bi);
         st->strongest_pose[0] = p.x; st->strongest_pose[1] = p.y; st->strongest_pose[2] = p.z;
         st->do_resample = a.policy == 2 || (a.policy == 1 && neff < (double)(a.P / 2));  // GridMapApp.java:185
         *a.np.counter = 0u;
@@ -1938,7 +2118,7 @@ __global__ void __launch_bounds__(256) k_select(SelectArgs a) {
 //            parallel scan (fixed-point tile sums of k_norm_coop / k_neff + a block-wide scan per tile) equals
 //            the sequential walk bit for bit on any number of threads / CTAs / ranks
 //   phase 2  selection + gather of the children [m_begin, m_begin + m_count)
-__global__ void __launch_bounds__(kNormThreads, 6) k_resample_coop(SelectArgs a,
+__global__ void __launch_bounds__(kNormThreads, kNormCtasPerSm) k_resample_coop(SelectArgs a,
                                                                    const unsigned long long* __restrict__ tile_fx,
                                                                    int ntiles) {
     cg::grid_group grid = cg::this_grid();
@@ -2029,6 +2209,157 @@ __global__ void __launch_bounds__(kNormThreads, 6) k_resample_coop(SelectArgs a,
         a.st->weighted_pose[2] = (float)(f[2] / f[3]);
         *a.wp_counter = 0u;
     }
+}
+
+// Sharded resampling (multi-rank shared map on the peer path): this rank builds the CDF segment of ITS particles and
+// selects ITS children; see "sharded normalise / resample" above for the protocol.
+//   phase 1  block-relative u64 fixed-point CDF of the block (tile sums of k_norm_coop + a block scan per tile);
+//            every 64th value goes to every rank's coarse table (round D)
+//   phase 2  per child: rank of the parent from the ranks' weight totals (round C), 64-particle bucket from the local
+//            copy of that rank's coarse table, <= 6 probes of that rank's CDF segment (NVLink reads when remote), then
+//            the parent's pose, weight and log-weight through the peer mappings
+// The integers are those of the replicated CDF (c_i = offset of the rank + block-relative prefix), so the parents are
+// the ones a single rank computes.
+__global__ void __launch_bounds__(kNormThreads, kNormCtasPerSm) k_resample_shard(SelectArgs a, const unsigned long long* __restrict__ tile_fx,
+                                                                    int ntiles, int lo, int cnt, Shard sh) {
+    constexpr int NT = kNormThreads, NW = NT / 32;
+    __shared__ unsigned long long s_u[NW];
+    __shared__ unsigned long long s_base[kMaxRanks + 1];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, G = gridDim.x;
+    Stats* st = a.st;
+    if (st->xerror) return;        // uniform over the grid
+    if (!st->do_resample) {        // uniform over the grid (and over the ranks): the generation is carried over unchanged
+        for (int m0 = lo + blockIdx.x * NT + tid; m0 < lo + cnt; m0 += G * NT) {
+            a.parents[m0] = m0;
+            a.pose_out[m0] = a.poses_in.at(m0);
+            a.w_out[m0] = a.w_in[m0];
+            a.lw_out[m0] = a.lw_in[m0];
+        }
+        return;
+    }
+    unsigned long long* seg = static_cast<unsigned long long*>(const_cast<void*>(a.cdf));  // [cnt], block-relative
+    for (int t = blockIdx.x; t < ntiles; t += G) {
+        unsigned long long acc = 0;
+        for (int c = tid; c < t; c += NT) acc += __ldcg(tile_fx + c);
+        const unsigned long long carry = block_reduce_nt<NT>(acc, SumU64(), s_u);
+        const int k0 = t * 1024 + tid * 4;  // position inside the block
+        unsigned long long x[4], run = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            run += k0 + j < cnt ? (unsigned long long)(a.w_in[lo + k0 + j] * 0x1p60) : 0ull;
+            x[j] = run;
+        }
+        unsigned long long v = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        __syncthreads();
+        if (lane == 31) s_u[wid] = v;
+        __syncthreads();
+        unsigned long long wbase = 0;
+#pragma unroll
+        for (int k = 0; k < NW; k++) wbase += k < wid ? s_u[k] : 0ull;
+        const unsigned long long excl = carry + wbase + v - run;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int k = k0 + j;
+            if (k >= cnt) continue;
+            const unsigned long long c = excl + x[j];
+            seg[k] = c;
+            if (((k + 1) & (kCoarseStep - 1)) == 0 || k == cnt - 1)  // round D: coarse sample j = k / 64 to every rank
+                for (int q = 0; q < sh.nranks; q++) coarse_of(sh.area[q], sh.coarse_cap, sh.rank)[k / kCoarseStep] = c;
+        }
+    }
+    __threadfence_system();  // segment + coarse samples visible system-wide before this thread's CTA takes its ticket
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(a.wp_counter, 1u) == (unsigned)G - 1u;
+    __syncthreads();
+    if (s_last) {
+        if (tid == 0) { __threadfence_system(); *a.wp_counter = 0u; }
+        __syncthreads();
+        if (tid < sh.nranks) shard_signal(sh, 3);
+    }
+    shard_wait(sh, 3, st);
+    if (*(volatile int*)&st->xerror) return;
+    // offsets of the ranks' segments in the global CDF (round C totals), in shared memory
+    const XArea* mine = reinterpret_cast<const XArea*>(sh.area[sh.rank]);
+    if (tid == 0) {
+        unsigned long long b = 0;
+        for (int q = 0; q < sh.nranks; q++) { s_base[q] = b; b += reinterpret_cast<const volatile XRecC*>(&mine->c[q])->T; }
+        s_base[sh.nranks] = b;
+    }
+    __syncthreads();
+    const int P = a.P, ncoarse = (cnt + kCoarseStep - 1) / kCoarseStep;
+    const double u01 = a.u01 < 0.0 ? philox_uniform(a.seed, a.resample_count) : a.u01;
+    const double r = u01 * 1.0 / (double)P;
+    auto key_of = [&](int m) -> unsigned long long {
+        const double U = r + (double)m * 1.0 / (double)P;
+        return (unsigned long long)(U * 0x1p60);
+    };
+    // global CDF value of particle i (any rank): offset + block-relative prefix
+    auto cdf_of = [&](int i) -> unsigned long long { const int q = i / cnt; return s_base[q] + __ldcg(sh.cdfseg[q] + (i - q * cnt)); };
+    for (int m0 = lo + blockIdx.x * NT + tid; m0 < lo + cnt; m0 += G * NT) {
+        const unsigned long long key = key_of(m0);
+        int q = 0;
+        while (q < sh.nranks - 1 && key > s_base[q + 1]) q++;  // first rank whose last CDF value is not below the key
+        const unsigned long long kk = key - s_base[q];
+        const unsigned long long* coarse = coarse_of(sh.area[sh.rank], sh.coarse_cap, q);
+        int l = 0, hgh = ncoarse - 1;
+        while (l < hgh) {  // first bucket whose last value is not below the key
+            const int mid = (l + hgh) >> 1;
+            if (kk > __ldcg(coarse + mid)) l = mid + 1; else hgh = mid;
+        }
+        hgh = min(cnt - 1, (l + 1) * kCoarseStep - 1);
+        l = l * kCoarseStep;
+        const unsigned long long* rs = sh.cdfseg[q];
+        while (l < hgh) {
+            const int mid = (l + hgh) >> 1;
+            if (kk > __ldcg(rs + mid)) l = mid + 1; else hgh = mid;
+        }
+        const int parent = q * cnt + l;
+        a.parents[m0] = parent;
+        a.pose_out[m0] = a.poses_in.at(parent);
+        a.w_out[m0] = __ldcg(sh.w[q] + parent);
+        a.lw_out[m0] = __ldcg(sh.lw[q] + parent);
+    }
+    // where the strongest particle of the update lives now: its first child (every rank computes the same number)
+    if (blockIdx.x == 0 && tid == 0) {
+        const int sb = st->strongest;
+        int first = 0;
+        if (sb > 0) {
+            const unsigned long long cprev = cdf_of(sb - 1);
+            int l = 0, hgh = P;  // smallest m with key(m) > cprev (key is non-decreasing in m)
+            while (l < hgh) {
+                const int mid = (l + hgh) >> 1;
+                if (key_of(mid) > cprev) hgh = mid; else l = mid + 1;
+            }
+            first = l;
+        }
+        const bool has_child = first < P && (sb == P - 1 || !(key_of(first) > cdf_of(sb)));
+        st->strongest_now = has_child ? first : -1;
+    }
+}
+
+// getters on a sharded handle: copy the other ranks' blocks out of their owners' arrays (peer mappings)
+struct RemoteBlocks {
+    PoseTable poses;
+    const double* w[kMaxRanks];
+    const double* lw[kMaxRanks];
+    const int* parents[kMaxRanks];
+    int cnt, lo, P;
+};
+__global__ void k_fill_remote_blocks(RemoteBlocks rb, float4* __restrict__ pose, double* __restrict__ w,
+                                     double* __restrict__ lw, int* __restrict__ parents) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rb.P || (i >= rb.lo && i < rb.lo + rb.cnt)) return;
+    const int q = i / rb.cnt;
+    pose[i] = rb.poses.p[q][i];
+    w[i] = rb.w[q][i];
+    lw[i] = rb.lw[q][i];
+    parents[i] = rb.parents[q][i];
 }
 
 // Per-particle maps: slot assignment.  parents[] is non-decreasing, so the first child of a parent is

@@ -267,7 +267,7 @@ int gms_read_neff(gms_handle* h, double* neff_out);  /* sync + read Neff of the 
  * over NVLink, a flag per sender replaces the collective (the caller skips its all-gather between begin and
  * end), and the resampling reads a remote parent's pose through the peer mapping of that rank's pose array. */
 #define GMS_IPC_HANDLE_BYTES 64
-#define GMS_IPC_NUM_HANDLES 9
+#define GMS_IPC_NUM_HANDLES 18
 int gms_ipc_export(gms_handle* h, void* handles /* GMS_IPC_NUM_HANDLES * GMS_IPC_HANDLE_BYTES */);
 int gms_ipc_import(gms_handle* h, const void* all_handles /* nranks * the above, rank-major */);
 
