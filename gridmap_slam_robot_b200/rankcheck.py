@@ -39,7 +39,9 @@ def _run(handle, stepper, scans, torch, dev, maps_of, check_steps):
             stepper.step(*args, policy=B.POLICY_ALWAYS, u01=-1.0)
         else:
             handle.step_dev(*args, None, B.POLICY_ALWAYS, -1.0)
-        neff = handle.read_neff()
+        neff = handle.read_neff()  # synchronises this rank's stream
+        if stepper is not None:
+            stepper.dist.barrier()  # ... and now every rank's: the getters below read other ranks' blocks through peer mappings
         strongest = handle.strongest()
         entry = {"neff": neff, "parents": handle.parents().copy(), "poses": handle.poses().copy(),
                  "weights": handle.weights().copy(), "strongest": (strongest[0], strongest[1].tobytes())}

@@ -163,9 +163,12 @@ int gms_get_weighted_pose(gms_handle* h, float pose_xyt[3]);/* SLAM.getWeightedP
  * index after the update; after a resampling the index of its first child, which inherits its map slot
  * (GridMapApp.java:376-393 keeps drawing strongestParticle.m); -1 before any update or if it left no child. */
 int gms_get_strongest(gms_handle* h, int32_t* index, float pose_xyt[3], double* weight);
-/* Multi-rank handles on the peer exchange keep only their own block of poses current between an update and the
- * next resampling; gms_get_poses / gms_get_weighted_pose then read the other blocks through the peer mappings,
- * so the caller must not let another rank start its next step while it reads (e.g. a barrier after the reads). */
+/* Multi-rank handles on the peer exchange hold only their own block of particles (poses; with a shared map also
+ * weights, log-weights and parent indices: every rank normalises and resamples its own block).  The getters of
+ * per-particle arrays copy the other blocks out of their owners' arrays through the peer mappings, so they are
+ * collective in spirit: call them only when EVERY rank has finished the step (gms_sync / gms_read_neff on each rank,
+ * then a barrier) and do not let a rank start its next step before the others have read (a barrier after the reads).
+ * gms_read_neff, gms_get_strongest and the map getters need no such care. */
 int gms_get_poses(gms_handle* h, float* xyt /* 3*P */);     /* getParticles().get(i).pose          */
 int gms_get_weights(gms_handle* h, double* w /* P */);      /* getParticles().get(i).weight        */
 int gms_get_log_weights(gms_handle* h, double* lw /* P */); /* ln of the un-normalised products of

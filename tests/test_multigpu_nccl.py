@@ -37,9 +37,12 @@ def _steps(h, stepper, scans, normals, uniforms, lo, cnt, dev, map_particles=(0,
         else:
             h.update_begin_dev(*args)
             h.update_end_dev(B.POLICY_ALWAYS, float(uniforms[s]))
+        neff = h.read_neff()  # synchronises this rank's stream
+        if stepper:
+            stepper.dist.barrier()  # ... and now every rank's: the getters read other ranks' blocks through peer mappings
         maps = {p: (h.get_map(p, B.MAP_FREE_COUNT).copy(), h.get_map(p, B.MAP_OCC_COUNT).copy(),
                     h.get_map(p, B.MAP_LIKELIHOOD).copy()) for p in map_particles}
-        out.append((h.read_neff(), h.parents().copy(), h.poses().copy(), h.weights().copy(), maps))
+        out.append((neff, h.parents().copy(), h.poses().copy(), h.weights().copy(), maps))
         if stepper:
             stepper.dist.barrier()  # no rank starts the next step while another still reads through peer mappings
     return out
