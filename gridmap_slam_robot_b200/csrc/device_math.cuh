@@ -272,6 +272,39 @@ __device__ __forceinline__ void apply_measurement(CellCounts* __restrict__ map, 
     box.y0 = min(box.y0, ly); box.y1 = max(box.y1, ly);
 }
 
+// The same walk with fire-and-forget reductions (RED.E.ADD.64: no value returns, nothing waits for L2): used
+// where no dirty-tile bookkeeping hangs on the transition, i.e. per-particle maps, whose likelihood field is
+// evaluated on demand from the counters (k_score_pp).  NEG subtracts the increments again: the getter of a
+// particle's likelihoodData needs the counters as they were BEFORE the last scan was integrated.
+template <bool NEG>
+__device__ __forceinline__ void apply_measurement_red(CellCounts* __restrict__ map, const Geometry& g, float sx, float sy,
+                                                      float ex, float ey, float meas, bool was_hit, CellBox& box) {
+    RayIter it;
+    it.init(sx + 0.5f, sy + 0.5f, ex + 0.5f, ey + 0.5f, g.extra_steps);
+    box.x0 = box.y0 = 0x7fffffff;
+    box.x1 = box.y1 = -1;
+    if (!it.has_next(g.W, g.H)) return;
+    box.x0 = box.x1 = it.x;
+    box.y0 = box.y1 = it.y;
+    int lx = it.x, ly = it.y;
+    const unsigned long long inc_free = NEG ? ~0ull : 1ull;                      // pair - 1 (no borrow: n_free >= 1)
+    const unsigned long long inc_occ = NEG ? (0ull - (1ull << 32)) : (1ull << 32);
+    while (it.has_next(g.W, g.H)) {
+        lx = it.x;
+        ly = it.y;
+        const float dX = sx - ((float)lx + 0.5f);
+        const float dY = sy - ((float)ly + 0.5f);
+        const float dist = __fsqrt_rn(dX * dX + dY * dY);
+        const int cls = inverse_sensor_class(dist, meas, was_hit, g.tol_half);
+        if (cls != 0)
+            atomicAdd(reinterpret_cast<unsigned long long*>(map + ((size_t)lx + (size_t)ly * g.W)),
+                      cls == 1 ? inc_free : inc_occ);
+        it.advance();
+    }
+    box.x0 = min(box.x0, lx); box.x1 = max(box.x1, lx);
+    box.y0 = min(box.y0, ly); box.y1 = max(box.y1, ly);
+}
+
 // ---- warp helpers ----
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -85,7 +86,23 @@ struct gms_handle {
     uint32_t* dirty_alt = nullptr;  // shared map with the self-listing refresh: the buffer the last refresh consumed
     bool alt_needs_clear = false;
     bool poses_sharded = false;  // peer exchange: the current pose array holds only this rank's block up to date
-    bool dead_dirty_pending = false;  // per-particle maps across ranks: dropped slots still carry dirty bits
+    // Per-particle maps: likelihoodData is VIRTUAL (kernels.cuh, k_score_pp): the step scores against the counters,
+    // no field is stored.  What Java's array would hold is described by `field_state` for every local slot at once,
+    // plus a few per-slot overrides left by the per-map operator entry points; getters materialise it on demand.
+    //   FIELD_ZERO        never computed since reset (GridMap.java:110-111: all 0.0)
+    //   FIELD_FRESH       blur(codes of the slot's counters now)
+    //   FIELD_BEFORE_LAST blur(codes of the counters as they were before the last step's scan was integrated):
+    //                     computeLikelihoodMap runs before integrateObservation (SLAM.java:93-105), so that is what
+    //                     the array holds between two updates; recovered by subtracting that scan's increments
+    //                     (same pose, same beam table, same kernel => same cells) from a scratch copy
+    enum { FIELD_ZERO = 0, FIELD_FRESH = 1, FIELD_BEFORE_LAST = 2 };
+    int field_state = FIELD_ZERO;
+    int field_B = 0;              // beams of the scan a FIELD_BEFORE_LAST field excludes (it is cur_beams())
+    struct FieldOverride { bool fresh; double* snap; };  // fresh: blur(counters now); else an explicit copy
+    std::unordered_map<int, FieldOverride> field_ovr;    // slot -> override
+    CellCounts* fld_counts = nullptr;  // scratch counter map for the subtraction (allocated on first use)
+    float4* upd_pose[2] = {nullptr, nullptr};  // poses the last scan was integrated from, once gms_set_poses has
+    bool use_upd_pose = false;                 // replaced the live ones (otherwise those are still pose[cur])
     bool self_list = false;      // shared map, bitmap small enough: the refresh builds its own work list
     int* word_off = nullptr;
     int2* tile_list = nullptr;
@@ -150,9 +167,6 @@ struct gms_handle {
     bool resample_partial = false;
     double partial_u01 = 0;
     unsigned long long partial_count = 0;
-    int map_win_words = 0;      // per-particle map update: cells of the shared-memory window of k_map_update_win
-                                // (GMS_MAP_WIN_WORDS, e.g. 13000 = 52 KB: four CTAs per SM); 0 = the global-atomic
-                                // kernel (default: see DESIGN.md for the measurements)
     int score_g = 0;  // sub-threads per particle in k_score_sorted (0 = automatic; GMS_SCORE_G overrides: tuning knob)
     int score_v = 2;  // variant of k_score_sorted (GMS_SCORE_V=0..6, identical cell indices; kernels.cuh / DESIGN.md §4.19):
                       // 2 = folded magic constant + per-particle range guard + padded factor field (measured fastest)
@@ -328,6 +342,8 @@ void free_all(gms_handle* h) {
     cudaFree(h->xarea[0]); cudaFree(h->xarea[1]); cudaFree(h->xflags4);
     for (int i = 0; i < 2; i++) { cudaFree(h->pose[i]); cudaFree(h->w[i]); cudaFree(h->lw[i]); cudaFree(h->slot[i]); }
     cudaFree(h->parents); cudaFree(h->cdf); cudaFree(h->counts); cudaFree(h->lik); cudaFree(h->fac); cudaFree(h->rect);
+    cudaFree(h->fld_counts); cudaFree(h->upd_pose[0]); cudaFree(h->upd_pose[1]);
+    for (auto& kv : h->field_ovr) cudaFree(kv.second.snap);
     cudaFree(h->dirty); cudaFree(h->dirty_alt); cudaFree(h->word_off); cudaFree(h->tile_list); cudaFree(h->dup_rect);
     cudaFree(h->dup_src_rank); cudaFree(h->dup_level); cudaFree(h->dup_src); cudaFree(h->dup_dst); cudaFree(h->scratch2p);
     free_beamset(h->bs[0]); free_beamset(h->bs[1]); free_beamset(h->ops);
@@ -402,6 +418,10 @@ int ensure_beams(gms_handle* h, int B) {
     CK(cudaStreamSynchronize(h->side_a));
     CK(cudaStreamSynchronize(h->side_b));
     h->b_pending = false;
+    // a virtual per-particle field in state FIELD_BEFORE_LAST is defined through the last step's beam table: carry it over
+    const bool keep_scan = h->cfg.map_mode == GMS_MAP_PER_PARTICLE && h->field_state == gms_handle::FIELD_BEFORE_LAST;
+    BeamSet old_scan = h->bs[h->bset];
+    if (keep_scan) h->bs[h->bset] = BeamSet{};
     free_beamset(h->bs[0]); free_beamset(h->bs[1]); free_beamset(h->ops);
     cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start);
     cudaFree(h->raw_angle); cudaFree(h->raw_dist);
@@ -412,6 +432,14 @@ int ensure_beams(gms_handle* h, int B) {
     int rc;
     for (BeamSet* b : {&h->bs[0], &h->bs[1], &h->ops})
         if ((rc = alloc_beamset(h, *b, cap))) return rc;
+    if (keep_scan) {
+        BeamSet& nb = h->bs[h->bset];
+        const size_t n = (size_t)h->field_B;
+        CK(cudaMemcpy(nb.xy, old_scan.xy, n * 16, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(nb.hit, old_scan.hit, n, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(nb.meas, old_scan.meas, n * 4, cudaMemcpyDeviceToDevice));
+        free_beamset(old_scan);
+    }
     CK(cudaMalloc((void**)&h->raw_angle, (size_t)cap * 8));
     CK(cudaMalloc((void**)&h->raw_dist, (size_t)cap * 8));
     if (h->cfg.map_mode == GMS_MAP_SHARED) {
@@ -491,12 +519,23 @@ int launch_likelihood(gms_handle* h) {
         h->alt_needs_clear = true;
         return GMS_OK;
     }
-    const int nwords = h->S * h->g.tile_words;
+    // one map (the shared map with a bitmap too large for the self-listing refresh)
+    const int nwords = h->g.tile_words;
     LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_scan<<<1, 1024, 0, h->stream>>>(h->dirty, nwords, h->word_off, h->st));
     LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_emit<<<blocks_for(nwords, 256), 256, 0, h->stream>>>(
                                      h->dirty, nwords, h->g.tile_words, h->word_off, h->tile_list));
-    return launch_blur(h, h->counts, h->lik, h->fac, h->tile_list, SelfList{nullptr, 0},
-                       (long long)h->S * h->tiles_per_map, true);
+    return launch_blur(h, h->counts, h->lik, h->fac, h->tile_list, SelfList{nullptr, 0}, h->tiles_per_map, true);
+}
+
+// every tile of ONE counter map -> `out` (GridMap.computeLikelihoodMap on a whole map; per-particle maps materialise
+// their virtual field with it, the combined-map fusion its sign map)
+int launch_blur_whole(gms_handle* h, const CellCounts* map, double* out, uint32_t* bitmap, int* word_off, int2* list) {
+    LAUNCH(GMS_PHASE_LIKELIHOOD, k_fill_dirty<<<blocks_for(h->g.tile_words, 256), 256, 0, h->stream>>>(
+                                     bitmap, 1, h->g.tile_words, h->tiles_per_map));
+    LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_scan<<<1, 1024, 0, h->stream>>>(bitmap, h->g.tile_words, word_off, h->st));
+    LAUNCH(GMS_PHASE_LIKELIHOOD, k_lik_emit<<<blocks_for(h->g.tile_words, 256), 256, 0, h->stream>>>(
+                                     bitmap, h->g.tile_words, h->g.tile_words, word_off, list));
+    return launch_blur(h, map, out, nullptr, list, SelfList{nullptr, 0}, h->tiles_per_map, false);
 }
 
 // Thread-per-particle scoring in heading order pays off when one shared field serves many particles
@@ -530,7 +569,7 @@ int launch_score_sorted(gms_handle* h, unsigned grid, size_t smem, const float4*
 }
 
 int launch_score(gms_handle* h, const BeamSet& b, const float4* pose, int lo, int cnt, const int* slot, double* lw,
-                 ExchangeRec* xlocal, int B, bool sorted = false) {
+                 ExchangeRec* xlocal, int B, bool sorted, const double* field) {
     Phase ph(h, GMS_PHASE_SCORE);
     const size_t smem = std::max<size_t>(16, (size_t)B * 16);
     if (sorted) {
@@ -553,7 +592,17 @@ int launch_score(gms_handle* h, const BeamSet& b, const float4* pose, int lo, in
         return fail(h, GMS_ERR_STATE, "launch_score: bad sub-thread count");
     }
     const unsigned grid = std::min<unsigned>(blocks_for(cnt, 8), (unsigned)h->num_sms * 8);
-    LAUNCH(GMS_PHASE_SCORE, k_score<<<grid, 256, smem, h->stream>>>(pose, lo, cnt, b.hit_xy, b.num_hit, h->lik, slot, lw,
+    if (!field) {  // per-particle maps, field = blur(codes of the counters now): evaluated where it is read
+        if (h->g.khalf == 3 && (h->W & 1) == 0)
+            LAUNCH(GMS_PHASE_SCORE, k_score_pp<3><<<cnt, kPpWarps * 32, 0, h->stream>>>(pose, lo, cnt, b.hit_xy, b.num_hit,
+                                                                                         h->counts, slot, lw, xlocal, h->g));
+        else
+            LAUNCH(GMS_PHASE_SCORE, k_score_pp<0><<<cnt, kPpWarps * 32, 0, h->stream>>>(pose, lo, cnt, b.hit_xy, b.num_hit,
+                                                                                         h->counts, slot, lw, xlocal, h->g));
+        return GMS_OK;
+    }
+    // one stored field (the shared map's, or a materialised per-particle one: `slot` is then null)
+    LAUNCH(GMS_PHASE_SCORE, k_score<<<grid, 256, smem, h->stream>>>(pose, lo, cnt, b.hit_xy, b.num_hit, field, slot, lw,
                                                                      xlocal, h->g));
     return GMS_OK;
 }
@@ -616,15 +665,13 @@ int launch_shared_update(gms_handle* h, const BeamSet& b, int B) {
 int launch_map_update(gms_handle* h, const BeamSet& b, const float4* pose, int lo, int cnt, const int* slot, int B) {
     if (B <= 0) return GMS_OK;
     Phase ph(h, GMS_PHASE_MAP_UPDATE);
-    if (h->map_win_words > 0 && B <= kWinMaxBeams) {  // one CTA per (particle, quadrant): on-chip accumulation + coalesced flush
-        LAUNCH(GMS_PHASE_MAP_UPDATE, k_map_update_win<<<(unsigned)cnt * 4u, kWinThreads, (size_t)h->map_win_words * 4, h->stream>>>(
-                                         pose, lo, cnt, b.xy, b.meas, b.hit, B, h->counts, slot, h->rect, h->dirty,
-                                         h->map_win_words, h->g));
-        return GMS_OK;
-    }
     const long long total = (long long)cnt * B;
-    LAUNCH(GMS_PHASE_MAP_UPDATE, k_map_update<<<blocks_for(total, 128), 128, 0, h->stream>>>(
-                                     pose, lo, cnt, b.xy, b.meas, b.hit, B, h->counts, slot, h->rect, h->dirty, h->g));
+    if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE)  // no dirty-tile bookkeeping: fire-and-forget reductions
+        LAUNCH(GMS_PHASE_MAP_UPDATE, k_map_update_red<false><<<blocks_for(total, 128), 128, 0, h->stream>>>(
+                                         pose, lo, cnt, b.xy, b.meas, b.hit, B, h->counts, slot, h->rect, h->g));
+    else
+        LAUNCH(GMS_PHASE_MAP_UPDATE, k_map_update<<<blocks_for(total, 128), 128, 0, h->stream>>>(
+                                         pose, lo, cnt, b.xy, b.meas, b.hit, B, h->counts, slot, h->rect, h->dirty, h->g));
     return GMS_OK;
 }
 
@@ -654,6 +701,11 @@ int run_pose_optimizer(gms_handle* h, const double* d_xy, const double* d_dist, 
     return GMS_OK;
 }
 
+void clear_field_overrides(gms_handle* h) {
+    for (auto& kv : h->field_ovr) cudaFree(kv.second.snap);
+    h->field_ovr.clear();
+}
+
 int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const uint8_t* d_hit, int B, double d_center,
                double d_theta, const double* d_normals) {
     const gms_config& c = h->cfg;
@@ -666,11 +718,6 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
     if (rc) return rc;
     BeamSet& bs = cur_beams(h);
     if (d_xy != (const double*)bs.xy) bs.view(bs.cap);  // device-resident scan: private copies at the capacity offsets
-    if (h->dead_dirty_pending) {  // per-particle maps across ranks: see k_drop_dead_dirty
-        LAUNCH(GMS_PHASE_LIKELIHOOD, k_drop_dead_dirty<<<1, 1024, 0, h->stream>>>(h->slot[h->slot_cur] + h->lo, h->cnt, h->S,
-                                                                               h->g.tile_words, h->dirty, h->scratch2p));
-        h->dead_dirty_pending = false;
-    }
     if (fork) {  // likelihood refresh of the shared map: independent of the beams and of the motion update
         cudaStream_t main = h->stream;
         CK(cudaEventRecord(h->ev_fork_a, main));
@@ -709,7 +756,13 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
             LAUNCH(GMS_PHASE_MOTION, k_motion<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(ma));
         }
     }
-    if (!fork) {  // computeLikelihoodMap precedes findBestPoseOptim and probabilityOf (SLAM.java:93-99)
+    if (!shared) {
+        // computeLikelihoodMap of every particle (SLAM.java:93): the field is virtual, so this is bookkeeping only —
+        // from here on every slot's likelihoodData is blur(codes of its counters now)
+        clear_field_overrides(h);
+        h->field_state = gms_handle::FIELD_FRESH;
+        h->use_upd_pose = false;
+    } else if (!fork) {  // computeLikelihoodMap precedes findBestPoseOptim and probabilityOf (SLAM.java:93-99)
         rc = launch_likelihood(h);
         if (rc) return rc;
     }
@@ -723,13 +776,15 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
     }
     if (fork) CK(cudaStreamWaitEvent(h->stream, h->ev_done_a, 0));
     rc = launch_score(h, bs, h->pose[h->cur], h->lo, h->cnt, shared ? nullptr : h->slot[h->slot_cur] + h->lo, h->lw[h->cur],
-                      (c.nranks > 1 && !h->direct) ? h->xlocal : nullptr, B, use_fac_score(h));
+                      (c.nranks > 1 && !h->direct) ? h->xlocal : nullptr, B, use_fac_score(h), shared ? h->lik : nullptr);
     if (rc) return rc;
 
     const bool skip = std::fabs(d_theta) > (M_PI / 180.0) * c.skip_update_deg;  // SLAM.java:82
-    if (!shared && !skip) {
+    if (!shared && !skip && B > 0) {
         rc = launch_map_update(h, bs, h->pose[h->cur], h->lo, h->cnt, h->slot[h->slot_cur] + h->lo, B);
         if (rc) return rc;
+        h->field_state = gms_handle::FIELD_BEFORE_LAST;  // likelihoodData now lags the counters by this scan
+        h->field_B = B;
     }
     if (c.nranks > 1 && h->direct && !h->sharded_post) {
         // this rank's log-weights -> every rank's receive buffer (NVLink stores), then one flag per receiver.  With
@@ -833,6 +888,32 @@ int complete_resample(gms_handle* h) {
     return launch_select(h, from, to, h->partial_u01, h->partial_count, h->lo + h->cnt, h->P - h->lo - h->cnt);
 }
 
+// Per-map operator results (explicit fields left by gms_map_compute_likelihood / the modifying gms_map_* calls) after
+// a single-rank resampling: the child in new slot ns inherits the override of its parent's old slot.  Slow path
+// (three small D2H copies + a synchronisation); only the per-map operator entry points create overrides.
+int remap_field_overrides(gms_handle* h, int old_slots) {
+    std::vector<int> parents((size_t)h->P), so((size_t)h->P), sn((size_t)h->P);
+    CK(cudaMemcpyAsync(parents.data(), h->parents, (size_t)h->P * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(so.data(), h->slot[old_slots], (size_t)h->P * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(sn.data(), h->slot[h->slot_cur], (size_t)h->P * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::unordered_map<int, gms_handle::FieldOverride> next;
+    for (int m = 0; m < h->P; m++) {
+        auto it = h->field_ovr.find(so[parents[m]]);
+        if (it == h->field_ovr.end()) continue;
+        gms_handle::FieldOverride o{it->second.fresh, nullptr};
+        if (it->second.snap) {
+            CK(cudaMalloc((void**)&o.snap, h->cells * 8));
+            CK(cudaMemcpyAsync(o.snap, it->second.snap, h->cells * 8, cudaMemcpyDeviceToDevice, h->stream));
+        }
+        next[sn[m]] = o;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    clear_field_overrides(h);
+    h->field_ovr.swap(next);
+    return GMS_OK;
+}
+
 int launch_resample(gms_handle* h, double u01, bool local_only = false) {
     const int P = h->P;
     h->stats_valid = false;  // Stats.strongest_now changes
@@ -887,30 +968,31 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
         h->tile_fx_valid = false;
     }
     h->resample_count++;
-    if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE && h->cfg.nranks > 1) {
+    if (h->cfg.map_mode != GMS_MAP_PER_PARTICLE) return GMS_OK;
+    if (h->cfg.nranks > 1 && !h->field_ovr.empty())
+        return fail(h, GMS_ERR_STATE, "per-particle maps across ranks: per-map operator results (gms_map_*) cannot follow "
+                                      "their particles through a resampling; call an update first");
+    const int old_slots = h->slot_cur;
+    if (h->cfg.nranks > 1) {
         if (!h->peers_ready)
             return fail(h, GMS_ERR_STATE, "per-particle maps across ranks: call gms_ipc_import before resampling");
         Phase ph(h, GMS_PHASE_MAP_COPY);
         const int nxt = h->slot_cur ^ 1;
         LAUNCH(GMS_PHASE_MAP_COPY, k_assign_slots_mr<<<1, 1024, 0, h->stream>>>(
                                        h->parents, P, h->cnt, h->cfg.nranks, h->S, h->cfg.rank, h->slot[h->slot_cur],
-                                       h->slot[nxt], h->dup_src_rank, h->dup_src, h->dup_dst, h->dup_level, h->dirty,
-                                       h->g.tile_words, h->scratch2p, h->st));
+                                       h->slot[nxt], h->dup_src_rank, h->dup_src, h->dup_dst, h->dup_level, h->scratch2p,
+                                       h->st));
         h->slot_cur = nxt;
-        h->dead_dirty_pending = true;
         const int chunks = std::max(1, std::min(32, h->H / 16));
         for (int level = 0; level < 2; level++) {  // 0: pulls + copies of old-generation maps, 1: copies of pulled replicas
             LAUNCH(GMS_PHASE_MAP_COPY, k_job_rects<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(
                                            h->dup_src_rank, h->dup_src, h->dup_dst, h->dup_level, level, h->dup_rect,
                                            h->rect, h->st, h->peers, h->g));
             LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps<<<(unsigned)((long long)chunks * h->cnt), 256, 0, h->stream>>>(
-                                           h->counts, h->lik, h->dirty, h->dup_src, h->dup_dst, h->dup_rect, h->st,
-                                           h->cells, h->W, h->g.tile_words, chunks, h->dup_src_rank, h->peers,
-                                           h->dup_level, level));
+                                           h->counts, h->dup_src, h->dup_dst, h->dup_rect, h->st, h->cells, h->W, chunks,
+                                           h->dup_src_rank, h->peers, h->dup_level, level));
         }
-        return GMS_OK;
-    }
-    if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE) {
+    } else {
         Phase ph(h, GMS_PHASE_MAP_COPY);
         const int nxt = h->slot_cur ^ 1;
         LAUNCH(GMS_PHASE_MAP_COPY, k_assign_slots<<<1, 1024, 0, h->stream>>>(
@@ -919,9 +1001,16 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
         h->slot_cur = nxt;
         const int chunks = std::max(1, std::min(32, h->H / 16));
         LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps<<<(unsigned)((long long)chunks * P), 256, 0, h->stream>>>(
-                                       h->counts, h->lik, h->dirty, h->dup_src, h->dup_dst, h->dup_rect, h->st,
-                                       h->cells, h->W, h->g.tile_words, chunks, nullptr, h->peers, nullptr, 0));
+                                       h->counts, h->dup_src, h->dup_dst, h->dup_rect, h->st, h->cells, h->W, chunks,
+                                       nullptr, h->peers, nullptr, 0));
     }
+    // the virtual likelihood field follows the particles: a child inherits its parent's
+    if (h->use_upd_pose) {  // ... and the pose its parent's last scan was integrated from
+        LAUNCH(GMS_PHASE_COUNT - 1, k_gather_pose<<<blocks_for(P, 256), 256, 0, h->stream>>>(h->parents, h->upd_pose[0],
+                                                                                              h->upd_pose[1], P));
+        std::swap(h->upd_pose[0], h->upd_pose[1]);
+    }
+    if (!h->field_ovr.empty()) return remap_field_overrides(h, old_slots);
     return GMS_OK;
 }
 
@@ -999,6 +1088,54 @@ int slot_of(gms_handle* h, int particle, int* slot) {
     return GMS_OK;
 }
 
+// ---- per-particle maps: the virtual likelihood field, materialised for the entry points that expose it ----------
+// `*out` = likelihoodData of the particle in slot s as Java would hold it now (see gms_handle::field_state); the
+// pointer (the handle's one-map buffer or an explicit copy) is valid until the next call that materialises a field.
+int field_of(gms_handle* h, int particle, int s, const double** out) {
+    if (h->cfg.map_mode == GMS_MAP_SHARED) { *out = h->lik; return GMS_OK; }
+    const CellCounts* map = h->counts + (size_t)s * h->cells;
+    int state = h->field_state;
+    auto it = h->field_ovr.find(s);
+    if (it != h->field_ovr.end()) {
+        if (it->second.snap) { *out = it->second.snap; return GMS_OK; }
+        state = gms_handle::FIELD_FRESH;
+    }
+    *out = h->lik;
+    if (state == gms_handle::FIELD_ZERO) {
+        CK(cudaMemsetAsync(h->lik, 0, h->cells * 8, h->stream));
+        return GMS_OK;
+    }
+    if (state == gms_handle::FIELD_BEFORE_LAST) {
+        // counters before the last scan = counters now - that scan's increments, replayed from the pose it was
+        // integrated from (the particle's pose: resampling copies it with the map, motion has not run since)
+        if (!h->fld_counts) CK(cudaMalloc((void**)&h->fld_counts, h->cells * sizeof(CellCounts)));
+        CK(cudaMemcpyAsync(h->fld_counts, map, h->cells * sizeof(CellCounts), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemsetAsync(h->tmp_slot, 0, sizeof(int), h->stream));
+        const BeamSet& b = cur_beams(h);
+        const float4* poses = h->use_upd_pose ? h->upd_pose[0] : h->pose[h->cur];
+        LAUNCH(GMS_PHASE_COUNT - 1, k_map_update_red<true><<<blocks_for(h->field_B, 128), 128, 0, h->stream>>>(
+                                        poses, particle, 1, b.xy, b.meas, b.hit, h->field_B, h->fld_counts, h->tmp_slot,
+                                        nullptr, h->g));
+        map = h->fld_counts;
+    }
+    return launch_blur_whole(h, map, h->lik, h->dirty, h->word_off, h->tile_list);
+}
+// before a per-map operator changes the counters of slot s: likelihoodData must keep what it holds (Java only
+// rebuilds it in computeLikelihoodMap), so the virtual field becomes an explicit copy
+int pin_field(gms_handle* h, int particle, int s) {
+    if (h->cfg.map_mode == GMS_MAP_SHARED) return GMS_OK;
+    auto it = h->field_ovr.find(s);
+    if (it != h->field_ovr.end() && it->second.snap) return GMS_OK;
+    const double* f = nullptr;
+    int rc = field_of(h, particle, s, &f);
+    if (rc) return rc;
+    double* snap = nullptr;
+    CK(cudaMalloc((void**)&snap, h->cells * 8));
+    CK(cudaMemcpyAsync(snap, f, h->cells * 8, cudaMemcpyDeviceToDevice, h->stream));
+    h->field_ovr[s] = gms_handle::FieldOverride{false, snap};
+    return GMS_OK;
+}
+
 // host scan -> device beam set `b` through the pinned staging ring: one packed block, no stream synchronisation
 int upload_beams(gms_handle* h, BeamSet& b, const double* xy, const double* dist, const uint8_t* hit, int B,
                  const double* normals = nullptr) {
@@ -1034,19 +1171,23 @@ int do_reset(gms_handle* h) {
     // GridMap.createMapData(null) GridMap.java:106-117: logData = logOdds(0.5) = 0.0 (no counts),
     // likelihoodData = 0.0 until the first computeLikelihoodMap; the whole map is dirty.
     CK(cudaMemsetAsync(h->counts, 0, (size_t)h->S * h->cells * sizeof(CellCounts), h->stream));
-    CK(cudaMemsetAsync(h->lik, 0, (size_t)h->S * h->cells * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->lik, 0, h->cells * sizeof(double), h->stream));  // the shared map's field (per-particle maps:
+                                                                          // scratch; their field is virtual, FIELD_ZERO)
     // nothing explored yet; every tile needs its first likelihood build
     LAUNCH(GMS_PHASE_COUNT - 1, k_fill_rect<<<blocks_for(h->S, 256), 256, 0, h->stream>>>(
                                     h->rect, h->S, make_int4(0x7fffffff, 0x7fffffff, -1, -1)));
-    LAUNCH(GMS_PHASE_COUNT - 1, k_fill_dirty<<<blocks_for((long long)h->S * h->g.tile_words, 256), 256, 0, h->stream>>>(
-                                    h->dirty, h->S, h->g.tile_words, h->tiles_per_map));
+    LAUNCH(GMS_PHASE_COUNT - 1, k_fill_dirty<<<blocks_for(h->g.tile_words, 256), 256, 0, h->stream>>>(
+                                    h->dirty, 1, h->g.tile_words, h->tiles_per_map));
+    clear_field_overrides(h);
+    h->field_state = gms_handle::FIELD_ZERO;
+    h->use_upd_pose = false;
     if (h->dirty_alt) CK(cudaMemsetAsync(h->dirty_alt, 0, (size_t)h->g.tile_words * 4, h->stream));
     h->alt_needs_clear = false;
     CK(cudaMemsetAsync(h->st, 0, sizeof(Stats), h->stream));
     h->cur = 0; h->slot_cur = 0;
     h->step = 0; h->resample_count = 0;
     h->have_update = false; h->pending = false; h->stats_valid = false; h->tile_fx_valid = false;
-    h->resample_partial = false; h->wpose_valid = false; h->dead_dirty_pending = false;
+    h->resample_partial = false; h->wpose_valid = false;
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }
@@ -1207,7 +1348,9 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->parents, P * 4));
     CKC(cudaMalloc((void**)&h->cdf, P * 8));
     CKC(cudaMalloc((void**)&h->counts, (size_t)h->S * h->cells * sizeof(CellCounts)));
-    CKC(cudaMalloc((void**)&h->lik, (size_t)h->S * h->cells * sizeof(double)));
+    // ONE field: the shared map's likelihoodData; with per-particle maps the field is virtual (k_score_pp) and this
+    // is the buffer a getter materialises one particle's field into
+    CKC(cudaMalloc((void**)&h->lik, h->cells * sizeof(double)));
     if (cfg->map_mode == GMS_MAP_SHARED) {  // + one sentinel element holding 1.0 for out-of-map end points
         // padded square (side 2^fac_lp) + one sentinel element, all 1.0 until the first refresh writes the map's cells
         const size_t nfac = (size_t)g.fac_pitch * g.fac_pitch + 1;
@@ -1216,14 +1359,14 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
         CKC(cudaGetLastError());
     }
     CKC(cudaMalloc((void**)&h->rect, (size_t)h->S * sizeof(int4)));
-    CKC(cudaMalloc((void**)&h->dirty, (size_t)h->S * g.tile_words * 4));
+    CKC(cudaMalloc((void**)&h->dirty, (size_t)g.tile_words * 4));  // dirty tiles of the shared map / scratch work list
     if (cfg->map_mode == GMS_MAP_SHARED && g.tile_words <= kSelfListWords &&
         !(std::getenv("GMS_SELF_LIST") && std::atoi(std::getenv("GMS_SELF_LIST")) == 0)) {
         CKC(cudaMalloc((void**)&h->dirty_alt, (size_t)g.tile_words * 4));
         h->self_list = true;
     }
-    CKC(cudaMalloc((void**)&h->word_off, (size_t)h->S * g.tile_words * 4));
-    CKC(cudaMalloc((void**)&h->tile_list, (size_t)h->S * h->tiles_per_map * sizeof(int2)));
+    CKC(cudaMalloc((void**)&h->word_off, (size_t)g.tile_words * 4));
+    CKC(cudaMalloc((void**)&h->tile_list, (size_t)h->tiles_per_map * sizeof(int2)));
     CKC(cudaMalloc((void**)&h->dup_rect, P * sizeof(int4)));
     CKC(cudaMalloc((void**)&h->dup_src, P * 4));
     CKC(cudaMalloc((void**)&h->dup_dst, P * 4));
@@ -1264,8 +1407,6 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->sort.order, (size_t)h->cnt * 4));
     h->ntiles = (h->P + 1023) / 1024;
     if (const char* e = std::getenv("GMS_SCORE_V")) h->score_v = std::max(0, std::min(6, std::atoi(e)));
-    if (const char* e = std::getenv("GMS_MAP_WIN_WORDS")) h->map_win_words = std::max(0, std::min(56000, std::atoi(e)));
-    CKC(cudaFuncSetAttribute(k_map_update_win, cudaFuncAttributeMaxDynamicSharedMemorySize, 56000 * 4));
     if (const char* e = std::getenv("GMS_SCORE_G")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) h->score_g = v; }
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, h->dev) == cudaSuccess) h->num_sms = prop.multiProcessorCount; }
     {
@@ -1291,7 +1432,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaFuncSetAttribute(k_likelihood<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CKC(cudaFuncSetAttribute(k_likelihood<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CKC(cudaFuncSetAttribute(k_likelihood_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    if (g.khalf == 3 && (h->W & 1) == 0 && !(std::getenv("GMS_LIK_TMA") && std::atoi(std::getenv("GMS_LIK_TMA")) == 0)) {
+    if (cfg->map_mode == GMS_MAP_SHARED && g.khalf == 3 && (h->W & 1) == 0 && !(std::getenv("GMS_LIK_TMA") && std::atoi(std::getenv("GMS_LIK_TMA")) == 0)) {
         // TMA descriptor of counts[S][H][W] (8-byte cells); box = one tile + halo.  Any failure keeps the plain kernel.
         typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1471,7 +1612,11 @@ EXPORT int gms_get_map(gms_handle* h, int32_t particle, int32_t kind, void* dst,
     if (rc) return rc;
     const CellCounts* c = h->counts + (size_t)s * h->cells;
     const unsigned nb = blocks_for((long long)h->cells, 256);
-    if (kind == GMS_MAP_LIKELIHOOD) return copy_out(h, dst, h->lik + (size_t)s * h->cells, bytes);
+    if (kind == GMS_MAP_LIKELIHOOD) {
+        const double* f = nullptr;
+        if ((rc = field_of(h, particle, s, &f))) return rc;
+        return copy_out(h, dst, f, bytes);
+    }
     if (kind == GMS_MAP_LOG)
         LAUNCH(GMS_PHASE_COUNT - 1,
                k_counts_to_log<<<nb, 256, 0, h->stream>>>(c, (double*)h->d_tmp, h->cells, h->g.l_free, h->g.l_occ));
@@ -1485,6 +1630,14 @@ EXPORT int gms_set_poses(gms_handle* h, const float* xyt) {
     ENTER(h);
     { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!xyt) return GMS_ERR_INVALID_ARG;
+    if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE && h->field_state == gms_handle::FIELD_BEFORE_LAST && !h->use_upd_pose) {
+        // the virtual likelihood fields are defined through the poses the last scan was integrated from: keep them
+        { int rc_ = materialize_poses(h); if (rc_) return rc_; }
+        for (int i = 0; i < 2; i++)
+            if (!h->upd_pose[i]) CK(cudaMalloc((void**)&h->upd_pose[i], (size_t)h->P * sizeof(float4)));
+        CK(cudaMemcpyAsync(h->upd_pose[0], h->pose[h->cur], (size_t)h->P * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+        h->use_upd_pose = true;
+    }
     CK(cudaMemcpyAsync(h->d_tmp, xyt, (size_t)h->P * 12, cudaMemcpyHostToDevice, h->stream));
     LAUNCH(GMS_PHASE_COUNT - 1,
            k_pose_pack<<<blocks_for(h->P, 256), 256, 0, h->stream>>>((const float*)h->d_tmp, h->pose[h->cur], h->P));
@@ -1508,14 +1661,16 @@ EXPORT int gms_set_map_counts(gms_handle* h, int32_t particle, const uint32_t* n
     int s;
     int rc = slot_of(h, particle, &s);
     if (rc) return rc;
+    if ((rc = pin_field(h, particle, s))) return rc;
     uint32_t* tmp = (uint32_t*)h->d_tmp;  // cells*8 bytes: two u32 planes
     CK(cudaMemcpyAsync(tmp, nf, h->cells * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(tmp + h->cells, no, h->cells * 4, cudaMemcpyHostToDevice, h->stream));
     LAUNCH(GMS_PHASE_COUNT - 1, k_counts_join<<<blocks_for((long long)h->cells, 256), 256, 0, h->stream>>>(
                                     h->counts + (size_t)s * h->cells, tmp, tmp + h->cells, h->cells));
     LAUNCH(GMS_PHASE_COUNT - 1, k_fill_rect<<<1, 1, 0, h->stream>>>(h->rect + s, 1, make_int4(0, 0, h->W - 1, h->H - 1)));
-    LAUNCH(GMS_PHASE_COUNT - 1, k_fill_dirty<<<blocks_for(h->g.tile_words, 256), 256, 0, h->stream>>>(
-                                    h->dirty + (size_t)s * h->g.tile_words, 1, h->g.tile_words, h->tiles_per_map));
+    if (h->cfg.map_mode == GMS_MAP_SHARED)
+        LAUNCH(GMS_PHASE_COUNT - 1, k_fill_dirty<<<blocks_for(h->g.tile_words, 256), 256, 0, h->stream>>>(
+                                        h->dirty, 1, h->g.tile_words, h->tiles_per_map));
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }
@@ -1527,9 +1682,13 @@ EXPORT int gms_map_apply_measurement(gms_handle* h, int32_t particle, float sx, 
     int s;
     int rc = slot_of(h, particle, &s);
     if (rc) return rc;
-    LAUNCH(GMS_PHASE_MAP_UPDATE, k_apply_one<<<1, 1, 0, h->stream>>>(
-                                     h->counts + (size_t)s * h->cells, h->rect + s,
-                                     h->dirty + (size_t)s * h->g.tile_words, sx, sy, ex, ey, meas, was_hit, h->g));
+    if ((rc = pin_field(h, particle, s))) return rc;
+    if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE)
+        LAUNCH(GMS_PHASE_MAP_UPDATE, k_apply_one_red<<<1, 1, 0, h->stream>>>(h->counts + (size_t)s * h->cells, h->rect + s, sx, sy,
+                                                                            ex, ey, meas, was_hit, h->g));
+    else
+        LAUNCH(GMS_PHASE_MAP_UPDATE, k_apply_one<<<1, 1, 0, h->stream>>>(h->counts, h->rect, h->dirty, sx, sy, ex, ey, meas,
+                                                                        was_hit, h->g));
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }
@@ -1549,6 +1708,7 @@ EXPORT int gms_map_integrate_observation(gms_handle* h, int32_t particle, const 
     int s;
     int rc = slot_of(h, particle, &s);
     if (rc) return rc;
+    if ((rc = pin_field(h, particle, s))) return rc;
     if ((rc = upload_beams(h, h->ops, bxy, bdist, bhit, B))) return rc;
     if ((rc = launch_pack(h, h->ops, (const double*)h->ops.xy, h->ops.dist, h->ops.hit, B))) return rc;
     if ((rc = stage_pose_slot(h, pose, s))) return rc;
@@ -1562,10 +1722,15 @@ EXPORT int gms_map_compute_likelihood(gms_handle* h, int32_t particle) {
     int s;
     int rc = slot_of(h, particle, &s);
     if (rc) return rc;
-    // the whole map of this slot (GridMap.computeLikelihoodMap has no notion of dirty tiles); tiles
-    // pending on other slots are rebuilt by the same pass, which only brings them up to date earlier
+    if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE) {  // virtual field: from now on blur(codes of this slot's counters)
+        auto it = h->field_ovr.find(s);
+        if (it != h->field_ovr.end()) cudaFree(it->second.snap);
+        h->field_ovr[s] = gms_handle::FieldOverride{true, nullptr};
+        return GMS_OK;
+    }
+    // the whole map (GridMap.computeLikelihoodMap has no notion of dirty tiles)
     LAUNCH(GMS_PHASE_LIKELIHOOD, k_fill_dirty<<<blocks_for(h->g.tile_words, 256), 256, 0, h->stream>>>(
-                                     h->dirty + (size_t)s * h->g.tile_words, 1, h->g.tile_words, h->tiles_per_map));
+                                     h->dirty, 1, h->g.tile_words, h->tiles_per_map));
     if ((rc = launch_likelihood(h))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
@@ -1580,8 +1745,10 @@ EXPORT int gms_map_probability_of(gms_handle* h, int32_t particle, const float p
     if (rc) return rc;
     if ((rc = upload_beams(h, h->ops, bxy, nullptr, bhit, B))) return rc;
     if ((rc = launch_pack(h, h->ops, (const double*)h->ops.xy, h->ops.dist, h->ops.hit, B))) return rc;
-    if ((rc = stage_pose_slot(h, pose, s))) return rc;
-    if ((rc = launch_score(h, h->ops, h->tmp_pose, 0, 1, h->tmp_slot, h->tmp_lw, nullptr, B))) return rc;
+    const double* f = nullptr;
+    if ((rc = field_of(h, particle, s, &f))) return rc;
+    if ((rc = stage_pose_slot(h, pose, 0))) return rc;
+    if ((rc = launch_score(h, h->ops, h->tmp_pose, 0, 1, nullptr, h->tmp_lw, nullptr, B, false, f))) return rc;
     double lw = 0;
     if ((rc = copy_out(h, &lw, h->tmp_lw, 8))) return rc;
     if (log_prob) *log_prob = lw;
@@ -1755,9 +1922,7 @@ EXPORT int gms_ipc_import(gms_handle* h, const void* all_handles) {
                 h->ipc_opened[q][k] = ptr[k];
             }
         h->peers.counts[q] = static_cast<const CellCounts*>(ptr[0]);
-        h->peers.lik[q] = static_cast<const double*>(ptr[1]);
         h->peers.rect[q] = static_cast<const int4*>(ptr[2]);
-        h->peers.dirty[q] = static_cast<const uint32_t*>(ptr[3]);
         h->peer_xlw[0][q] = static_cast<double*>(ptr[4]);
         h->peer_xlw[1][q] = static_cast<double*>(ptr[5]);
         h->peer_flags[q] = static_cast<unsigned long long*>(ptr[6]);
@@ -1847,8 +2012,10 @@ EXPORT int gms_render_map(gms_handle* h, int32_t particle, int32_t likelihood, u
     int s;
     int rc = slot_of(h, particle, &s);
     if (rc) return rc;
+    const double* f = h->lik;
+    if (likelihood && (rc = field_of(h, particle, s, &f))) return rc;
     LAUNCH(GMS_PHASE_COUNT - 1, k_render<<<blocks_for((long long)h->cells, 256), 256, 0, h->stream>>>(
-                                    h->counts + (size_t)s * h->cells, h->lik + (size_t)s * h->cells, h->cells, likelihood,
+                                    h->counts + (size_t)s * h->cells, f, h->cells, likelihood,
                                     h->g.l_free, h->g.l_occ, (uint32_t*)h->d_tmp));
     return copy_out(h, abgr_out, h->d_tmp, h->cells * 4);
 }

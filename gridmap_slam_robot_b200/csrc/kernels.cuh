@@ -58,9 +58,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 constexpr int kMaxRanks = 16;
 struct PeerTable {  // per-particle maps across ranks: every rank's arenas, mapped into this process (cudaIpc)
     const CellCounts* counts[kMaxRanks];
-    const double* lik[kMaxRanks];
     const int4* rect[kMaxRanks];
-    const uint32_t* dirty[kMaxRanks];
 };
 
 // Peer exchange (multi-rank, replaces the NCCL all-gather).  Only the f64 log-weights travel: after scoring,
@@ -777,6 +775,127 @@ __global__ void __launch_bounds__(256) k_score(const float4* __restrict__ pose, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Per-particle maps: the likelihood field evaluated WHERE IT IS READ.
+// GridMap.computeLikelihoodMap (GridMap.java:233-250) rebuilds likelihoodData[W*H] of every particle before the
+// scan is scored, and GridMap.probabilityOf (GridMap.java:261-294) then reads it at B_hit cells.  The field at a
+// cell is a pure function of the thresholded codes within khalf cells (separable blur, Util.java:378-426), so the
+// step evaluates it only at the cells the scan looks up: (2*khalf+1)^2 counter pairs per lookup, 7 x 7 for the
+// reference's 0.05 m cells, straight from the counter map — O(B * k^2) per particle and step instead of
+// O(touched tiles * k), and no per-particle field in HBM at all (the reference spends ~3/4 of its step in that
+// rebuild; the tile kernel took 0.51 of the 2.24 ms K2pp step and the field doubled every map copy).
+// Same f64 operation order as k_likelihood (tap index ascending, multiply then add, no FMA; rows and columns
+// outside the map contribute 0.0) => the value is bit-identical to the stored field's.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double code_of(const CellCounts c, const Geometry& g) {
+    return 0.5 * (double)cell_code_fast(c, g);  // {0, .5, 1}: what k_likelihood keeps as f32 in shared memory
+}
+// KH = 3, even W (rows and slots start 16-byte aligned): the 7 cells of a row are covered by four aligned pairs
+template <int KH>
+__device__ __forceinline__ double field_at(const CellCounts* __restrict__ cmap, int gx, int gy, const Geometry& g,
+                                           const double* __restrict__ kr) {
+    double total = 0.0;
+    if constexpr (KH == 3) {
+        const int xs = gx - 3, xa = xs & ~1, o = xs - xa;  // first tap column, its aligned pair, 0 / 1
+#pragma unroll
+        for (int r = 0; r < 7; r++) {
+            const int y = gy + r - 3;
+            double h = 0.0;
+            if (y >= 0 && y < g.H) {
+                const uint4* row = reinterpret_cast<const uint4*>(cmap + (size_t)y * g.W);
+                uint4 v[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int x = xa + 2 * q;
+                    v[q] = (x >= 0 && x < g.W) ? __ldg(row + (x >> 1)) : make_uint4(0u, 0u, 0u, 0u);
+                }
+                double c[8];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int x = xa + 2 * q;
+                    const bool in = x >= 0 && x < g.W;
+                    c[2 * q] = in ? code_of(CellCounts{v[q].x, v[q].y}, g) : 0.0;
+                    c[2 * q + 1] = in ? code_of(CellCounts{v[q].z, v[q].w}, g) : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < 7; i++) h += kr[i] * (o ? c[i + 1] : c[i]);
+            }
+            total += kr[r] * h;
+        }
+    } else {
+        const int k = g.khalf;
+        for (int r = 0; r < g.ktaps; r++) {
+            const int y = gy + r - k;
+            double h = 0.0;
+            if (y >= 0 && y < g.H) {
+                const CellCounts* row = cmap + (size_t)y * g.W;
+                for (int i = 0; i < g.ktaps; i++) {
+                    const int x = gx + i - k;
+                    const double c = (x >= 0 && x < g.W) ? code_of(row[x], g) : 0.0;
+                    h += g.kernel[i] * c;
+                }
+            }
+            total += g.kernel[r] * h;
+        }
+    }
+    return total;
+}
+
+// A5 for per-particle maps: one CTA of kPpWarps warps per particle, hit beams across the CTA's threads (beam b goes
+// to thread b mod 128: a thread multiplies its factors in beam order, takes one log, each warp sums its 32 logs with
+// the fixed xor tree and thread 0 adds the kPpWarps partial sums in warp order) — one fixed reduction shape for every
+// particle count, so log-weights are bit-identical run to run and for every rank count.  Four warps per particle
+// because a lookup is a burst of 28 independent 16-byte loads followed by ~110 f64 operations: with one warp per
+// particle 1000 particles left the SMs 12 % occupied and the kernel latency-bound (ncu, r02j: 126 us).
+constexpr int kPpWarps = 4;
+template <int KH>
+__global__ void __launch_bounds__(kPpWarps * 32) k_score_pp(const float4* __restrict__ pose, int lo, int cnt,
+                                                           const double2* __restrict__ hit_xy,
+                                                           const int* __restrict__ num_hit,
+                                                           const CellCounts* __restrict__ counts,
+                                                           const int* __restrict__ slot, double* __restrict__ lw,
+                                                           ExchangeRec* __restrict__ xlocal, Geometry g) {
+    __shared__ double s_part[kPpWarps];
+    const int li = blockIdx.x;
+    if (li >= cnt) return;
+    const int nh = *num_hit;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double kr[2 * KH + 1];
+#pragma unroll
+    for (int i = 0; i < 2 * KH + 1; i++) kr[i] = g.kernel[i];
+    const int i = lo + li;
+    const float4 p = pose[i];
+    const Xform t(p.x, p.y, p.z);
+    const CellCounts* cmap = counts + (size_t)slot[li] * ((size_t)g.W * g.H);
+    double prod = 1.0;
+    int exp2 = 0, it = 0;
+    for (int b = tid; b < nh; b += kPpWarps * 32, it++) {
+        const double2 m = __ldg(hit_xy + b);
+        const int gx = cell_of(t.tx(m.x, m.y) - g.posx, g.res, g.inv_res);  // (int): toward zero
+        const int gy = cell_of(t.ty(m.x, m.y) - g.posy, g.res, g.inv_res);
+        if (!(gx < 0 || gy < 0 || gx >= g.W || gy >= g.H)) {
+            const double val = field_at<KH>(cmap, gx, gy, g, kr);
+            prod *= val == 0.5 ? g.uniform_term : g.z_hit * val + g.random_term;
+        }
+        if ((it & 63) == 63) peel_exponent(prod, exp2);  // factors in [0.01, 0.91]: no underflow between two peels
+    }
+    peel_exponent(prod, exp2);
+    const double l = warp_sum(log(prod) + (double)exp2 * 0.6931471805599453);
+    if (lane == 0) s_part[wid] = l;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = s_part[0];
+#pragma unroll
+        for (int w = 1; w < kPpWarps; w++) tot += s_part[w];
+        lw[i] = tot;
+        if (xlocal) {
+            ExchangeRec r;
+            r.lw = tot; r.x = p.x; r.y = p.y; r.t = p.z; r.pad = 0;
+            xlocal[li] = r;
+        }
+    }
+}
+
 // Shared map, many particles: ONE THREAD per particle, the 32 lanes of a warp take 32 particles that
 // are neighbours in heading (k_motion / k_sort_*).  Why (ncu, profiles/r01_*): with beams across lanes a
 // warp-wide gather touches ~17-25 different 128-byte lines, and the L1 tag stage retires one line per
@@ -1060,187 +1179,35 @@ __global__ void __launch_bounds__(128) k_map_update(const float4* __restrict__ p
     }
 }
 
-// Per-particle maps, windowed: ONE CTA per (particle, quadrant of the ray fan).  The atomic kernel above is bound
-// by the L2 atomic unit (ncu, K2pp: 7.8e7 64-bit ATOMG in 1.05 ms = ~40 atomics/clk chip-wide, 9 % of the HBM
-// roofline, DRAM traffic 2.3x the algorithmic bytes because every non-horizontal DDA step lands in a new 32-byte
-// sector).  A map is only ever written by its own particle, so the increments of one scan can be combined on
-// chip first: the rays of one quadrant all start in the same cell and move monotonically away from it, so they
-// live in a rectangle anchored at the start cell.  The CTA tiles that rectangle into windows of `win_words`
-// cells, visited in row-major order; per window it zeroes a shared-memory array of one u32 per cell (low half:
-// free increments, high half: occupied increments; a ray visits a cell at most 3 times), advances every ray that
-// currently sits in the window until it leaves it (the DDA state stays in registers: each ray is walked once;
-// a first version re-walked every ray per window and was bound by those instructions, 2.9 ms) accumulating with
-// shared-memory atomics, and flushes the window with plain, coalesced 8-byte
-// read-modify-writes (old pair in, new pair out, dirty-tile marking from the two thresholded codes).  No global
-// atomics except on the start row / column, which neighbouring quadrants share.  Integer accumulation: the
-// result is independent of the order => deterministic, identical to the atomic kernel's.
-constexpr int kWinThreads = 256;
-constexpr int kWinRaysPerThread = 2;                                   // a quadrant may hold up to 512 rays ...
-constexpr int kWinMaxBeams = kWinThreads * kWinRaysPerThread;          // ... so scans of up to 512 beams take this kernel
-__global__ void __launch_bounds__(kWinThreads, 3) k_map_update_win(const float4* __restrict__ pose, int lo, int cnt,
-                                                                   const double2* __restrict__ all_xy,
-                                                                   const float* __restrict__ meas,
-                                                                   const uint8_t* __restrict__ hit, int B,
-                                                                   CellCounts* __restrict__ counts,
-                                                                   const int* __restrict__ slot, int4* __restrict__ rect,
-                                                                   uint32_t* __restrict__ dirty, int win_words,
-                                                                   Geometry g) {
-    extern __shared__ __align__(16) uint32_t s_win[];
-    __shared__ int s_reach[2];
-    __shared__ int s_box[4];
-    __shared__ int s_nrays, s_rowmax;
-    __shared__ unsigned short s_rays[kWinMaxBeams];
-    const int tid = threadIdx.x;
-    const int li = blockIdx.x >> 2, quad = blockIdx.x & 3;
-    if (li >= cnt) return;
-    const int qx = (quad & 1) ? -1 : 1, qy = (quad & 2) ? -1 : 1;  // direction of travel of this CTA's rays
+// The same without dirty-tile bookkeeping (fire-and-forget RED): the step's kernel for per-particle maps now that
+// their likelihood field is evaluated on demand.  NEG: subtract (see apply_measurement_red); `rect` may be null.
+template <bool NEG>
+__global__ void __launch_bounds__(128) k_map_update_red(const float4* __restrict__ pose, int lo, int cnt,
+                                                        const double2* __restrict__ all_xy,
+                                                        const float* __restrict__ meas,
+                                                        const uint8_t* __restrict__ hit, int B,
+                                                        CellCounts* __restrict__ counts, const int* __restrict__ slot,
+                                                        int4* __restrict__ rect, Geometry g) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)cnt * B) return;
+    const int li = (int)(gid / B);
+    const int b = (int)(gid - (long long)li * B);
     const int s = slot[li];
-    CellCounts* map = counts + (size_t)s * ((size_t)g.W * g.H);
-    uint32_t* bitmap = dirty + (size_t)s * g.tile_words;
     const float4 p = pose[lo + li];
     const Xform t(p.x, p.y, p.z);
     const float sx = (float)((t.tx(0.0, 0.0) - g.posx) / g.res);
     const float sy = (float)((t.ty(0.0, 0.0) - g.posy) / g.res);
-    const int x0 = java_d2i(floor((double)(sx + 0.5f))), y0 = java_d2i(floor((double)(sy + 0.5f)));  // RayIter.init
-    if (tid == 0) {
-        s_reach[0] = -1; s_reach[1] = -1; s_nrays = 0;
-        s_box[0] = 0x7fffffff; s_box[1] = 0x7fffffff; s_box[2] = -1; s_box[3] = -1;
-    }
-    __syncthreads();
-    auto ray_init = [&](int b, RayIter& it, int& rx, int& ry) {
-        const double2 m = all_xy[b];
-        const float ex = (float)((t.tx(m.x, m.y) - g.posx) / g.res);
-        const float ey = (float)((t.ty(m.x, m.y) - g.posy) / g.res);
-        it.init(sx + 0.5f, sy + 0.5f, ex + 0.5f, ey + 0.5f, g.extra_steps);
-        rx = abs(java_d2i(floor((double)(ex + 0.5f))) - x0);  // |dfloor x|, |dfloor y| between first and last cell
-        ry = abs(java_d2i(floor((double)(ey + 0.5f))) - y0);
-    };
-    // pass A: this quadrant's rays (list in shared memory, any order: integer accumulation commutes) and how far
-    // they reach: |dfloor| steps to the end point plus at most `extra_steps` more in either axis, clipped to the map
-    for (int b = tid; b < B; b += kWinThreads) {
-        RayIter it;
-        int rx, ry;
-        ray_init(b, it, rx, ry);
-        if (((it.x_inc < 0) ? -1 : 1) != qx || ((it.y_inc < 0) ? -1 : 1) != qy || !it.has_next(g.W, g.H)) continue;
-        const int lim_x = qx > 0 ? g.W - 1 - x0 : x0, lim_y = qy > 0 ? g.H - 1 - y0 : y0;
-        atomicMax(&s_reach[0], min(rx + g.extra_steps, lim_x));
-        atomicMax(&s_reach[1], min(ry + g.extra_steps, lim_y));
-        s_rays[atomicAdd(&s_nrays, 1)] = (unsigned short)b;
-    }
-    __syncthreads();
-    const int RX = s_reach[0] + 1, RY = s_reach[1] + 1;  // the quadrant's rectangle: [0, RX) x [0, RY) in (wx, wy)
-    const int nrays = s_nrays;
-    if (nrays == 0) return;
-    // every thread owns up to kWinRaysPerThread rays and keeps their DDA state in registers across the windows
-    RayIter it[kWinRaysPerThread];
-    float ms[kWinRaysPerThread];
-    bool wh[kWinRaysPerThread], live[kWinRaysPerThread];
-#pragma unroll
-    for (int r = 0; r < kWinRaysPerThread; r++) {
-        const int k = tid + r * kWinThreads;
-        live[r] = k < nrays;
-        ms[r] = 0.f; wh[r] = false;
-        if (live[r]) {
-            const int b = s_rays[k];
-            int rx, ry;
-            ray_init(b, it[r], rx, ry);
-            ms[r] = meas[b];
-            wh[r] = hit[b] != 0;
-        }
-    }
-    // window shape: as square as the rectangle allows
-    int WX, WY;
-    {
-        int sq = 1;
-        while ((sq + 1) * (sq + 1) <= win_words) sq++;
-        if (RX <= sq) { WX = RX; WY = min(RY, win_words / WX); }
-        else if (RY <= sq) { WY = RY; WX = min(RX, win_words / WY); }
-        else { WX = sq; WY = sq; }
-    }
-    // Windows in row-major order.  A ray only ever moves away from the start cell, one cell along one axis per step:
-    // when it leaves window (i, j) it enters (i+1, j) — the next one — or (i, j+1), which comes later in the order;
-    // it pauses (state in registers) and resumes there.  Every ray is walked exactly once.
-    for (int oy = 0; oy < RY; oy += WY)
-        for (int ox = 0; ox < RX; ox += WX) {
-            const int wxe = min(ox + WX, RX), wye = min(oy + WY, RY);  // window = [ox, wxe) x [oy, wye)
-            const int ww = wxe - ox, nwin = ww * (wye - oy);
-            for (int i = tid; i < nwin; i += kWinThreads) s_win[i] = 0u;
-            if (tid == 0) s_rowmax = -1;
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < kWinRaysPerThread; r++) {
-                if (!live[r]) continue;
-                RayIter& w = it[r];
-                int wx = (w.x - x0) * qx, wy = (w.y - y0) * qy;
-                if (wx < ox || wx >= wxe || wy < oy || wy >= wye) continue;  // paused somewhere else
-                int lx_ = w.x, ly_ = w.y;
-                bool ended = true;
-                while (w.has_next(g.W, g.H)) {
-                    wx = (w.x - x0) * qx; wy = (w.y - y0) * qy;
-                    if (wx >= wxe || wy >= wye) { ended = false; break; }  // continues in a later window
-                    lx_ = w.x; ly_ = w.y;
-                    const float dX = sx - ((float)lx_ + 0.5f);
-                    const float dY = sy - ((float)ly_ + 0.5f);
-                    const float dist = __fsqrt_rn(dX * dX + dY * dY);
-                    const int cls = inverse_sensor_class(dist, ms[r], wh[r], g.tol_half);
-                    if (cls != 0) atomicAdd(&s_win[(wy - oy) * ww + (wx - ox)], cls == 1 ? 1u : 65536u);
-                    w.advance();
-                }
-                atomicMax(&s_rowmax, min(wy, wye - 1) - oy);  // wy only grows: the last one is the furthest row touched
-                if (ended) {  // the ray's last cell: its box for the explored rectangle
-                    live[r] = false;
-                    atomicMin(&s_box[0], min(x0, lx_)); atomicMin(&s_box[1], min(y0, ly_));
-                    atomicMax(&s_box[2], max(x0, lx_)); atomicMax(&s_box[3], max(y0, ly_));
-                }
-            }
-            __syncthreads();
-            // flush: plain coalesced read-modify-write of the cells this scan touched (rows of the window are
-            // contiguous in the map, forwards or backwards).  A warp takes a row, a lane four cells at a time; rows
-            // beyond the last touched one are skipped.  The start row and column (wx == 0 or wy == 0) are shared
-            // with the neighbouring quadrants' CTAs, which flush concurrently: one 64-bit atomic each.
-            const int rows = min(wye - oy, s_rowmax + 1);
-            for (int yy = tid >> 5; yy < rows; yy += kWinThreads / 32) {
-                const int wy = oy + yy, cy = y0 + wy * qy;
-                const uint32_t* row = s_win + yy * ww;
-                for (int xg = (tid & 31) * 4; xg < ww; xg += 128) {
-                    uint32_t inc[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) inc[u] = xg + u < ww ? row[xg + u] : 0u;
-                    if ((inc[0] | inc[1] | inc[2] | inc[3]) == 0u) continue;
-                    unsigned long long old[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        if (!inc[u]) continue;
-                        const int wx = ox + xg + u;
-                        unsigned long long* cell = reinterpret_cast<unsigned long long*>(map + ((size_t)(x0 + wx * qx) + (size_t)cy * g.W));
-                        if (wx == 0 || wy == 0)
-                            old[u] = atomicAdd(cell, (unsigned long long)(inc[u] & 0xffffu) | ((unsigned long long)(inc[u] >> 16) << 32));
-                        else
-                            old[u] = __ldcg(cell);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        if (!inc[u]) continue;
-                        const int wx = ox + xg + u, x = x0 + wx * qx;
-                        const uint32_t of = (uint32_t)old[u], oo = (uint32_t)(old[u] >> 32);
-                        const uint32_t nf = of + (inc[u] & 0xffffu), no = oo + (inc[u] >> 16);
-                        if (!(wx == 0 || wy == 0))
-                            __stcg(reinterpret_cast<unsigned long long*>(map + ((size_t)x + (size_t)cy * g.W)),
-                                   (unsigned long long)nf | ((unsigned long long)no << 32));
-                        bool flip;
-                        if (oo == 0 && no == 0) flip = of == 0;       // never occupied: flips on its first free hit
-                        else if (of == 0 && nf == 0) flip = oo == 0;  // never freed: flips on its first occupied hit
-                        else flip = cell_code(of, oo, g) != cell_code(nf, no, g);
-                        if (flip) mark_dirty(bitmap, x, cy, g);
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    if (tid == 0 && s_box[2] >= 0) {
+    const double2 m = all_xy[b];
+    const float ex = (float)((t.tx(m.x, m.y) - g.posx) / g.res);
+    const float ey = (float)((t.ty(m.x, m.y) - g.posy) / g.res);
+    CellBox box;
+    apply_measurement_red<NEG>(counts + (size_t)s * ((size_t)g.W * g.H), g, sx, sy, ex, ey, meas[b], hit[b] != 0, box);
+    if (rect && box.x1 >= 0) {
         int* r = reinterpret_cast<int*>(rect + s);
-        atomicMin(r + 0, s_box[0]); atomicMin(r + 1, s_box[1]);
-        atomicMax(r + 2, s_box[2]); atomicMax(r + 3, s_box[3]);
+        atomicMin(r + 0, box.x0);
+        atomicMin(r + 1, box.y0);
+        atomicMax(r + 2, box.x1);
+        atomicMax(r + 3, box.y1);
     }
 }
 
@@ -2409,14 +2376,10 @@ __global__ void __launch_bounds__(1024) k_assign_slots(const int* __restrict__ p
             dup_dst[rd] = d;
             slot_out[m] = d;
             // Outside the explored boxes both maps are blank (identical), so only the union of the two
-            // boxes (+ the blur half-width for the likelihood field) has to move; the child inherits
-            // the parent's box.  Source slots are never destinations (a parent with a child is not dead).
+            // boxes has to move; the child inherits the parent's box.  Source slots are never destinations
+            // (a parent with a child is not dead).
             const int4 a = rect[sp], b = rect[d];
-            int4 r = make_int4(min(a.x, b.x), min(a.y, b.y), max(a.z, b.z), max(a.w, b.w));
-            if (r.x <= r.z && r.y <= r.w)
-                r = make_int4(max(r.x - g.khalf, 0), max(r.y - g.khalf, 0), min(r.z + g.khalf, g.W - 1),
-                              min(r.w + g.khalf, g.H - 1));
-            dup_rect[rd] = r;
+            dup_rect[rd] = make_int4(min(a.x, b.x), min(a.y, b.y), max(a.z, b.z), max(a.w, b.w));
             rect[d] = a;
             rd++;
         } else {
@@ -2453,8 +2416,7 @@ __global__ void __launch_bounds__(1024) k_assign_slots_mr(const int* __restrict_
                                                           int myrank, const int* __restrict__ gslot_in,
                                                           int* __restrict__ gslot_out, int* __restrict__ job_src_rank,
                                                           int* __restrict__ job_src_slot, int* __restrict__ job_dst,
-                                                          int* __restrict__ job_level, uint32_t* __restrict__ dirty,
-                                                          int tile_words, int* __restrict__ scratch /* 2*R*S */,
+                                                          int* __restrict__ job_level, int* __restrict__ scratch /* 2*R*S */,
                                                           Stats* __restrict__ st) {
     __shared__ int s_buf[1024];
     const int tid = threadIdx.x;
@@ -2514,27 +2476,10 @@ __global__ void __launch_bounds__(1024) k_assign_slots_mr(const int* __restrict_
         }
         if (q == myrank && tid == 0) st->num_dup = total;
     }
-    // (The pending likelihood tiles of the slots the new generation no longer occupies are dropped by
-    // k_drop_dead_dirty at the start of the NEXT step: other ranks may still be pulling those slots — bitmap
-    // included — while this kernel runs.)
 }
 
-// slots of this rank that the current generation does not occupy: drop their pending likelihood tiles, so the
-// refresh does not rebuild maps nobody reads.  Runs after the exchange's barrier.
-__global__ void __launch_bounds__(1024) k_drop_dead_dirty(const int* __restrict__ gslot_local, int cnt, int S,
-                                                          int tile_words, uint32_t* __restrict__ dirty,
-                                                          int* __restrict__ occ /* S */) {
-    const int tid = threadIdx.x;
-    for (int i = tid; i < S; i += 1024) occ[i] = 0;
-    __syncthreads();
-    for (int m = tid; m < cnt; m += 1024) occ[gslot_local[m]] = 1;
-    __syncthreads();
-    for (int i = tid; i < S * tile_words; i += 1024)
-        if (!occ[i / tile_words]) dirty[i] = 0u;
-}
-
-// copy rectangle of every job (union of the two explored boxes + blur half-width); the child inherits the
-// parent's box.  The parent's box is read from the parent's rank.
+// copy rectangle of every job (union of the two explored boxes); the child inherits the parent's box.  The
+// parent's box is read from the parent's rank.
 __global__ void __launch_bounds__(256) k_job_rects(const int* __restrict__ job_src_rank,
                                                    const int* __restrict__ job_src_slot,
                                                    const int* __restrict__ job_dst, const int* __restrict__ job_level,
@@ -2545,22 +2490,19 @@ __global__ void __launch_bounds__(256) k_job_rects(const int* __restrict__ job_s
     const int4 a = peers.rect[job_src_rank[k]][job_src_slot[k]];
     const int d = job_dst[k];
     const int4 b = rect[d];
-    int4 r = make_int4(min(a.x, b.x), min(a.y, b.y), max(a.z, b.z), max(a.w, b.w));
-    if (r.x <= r.z && r.y <= r.w)
-        r = make_int4(max(r.x - g.khalf, 0), max(r.y - g.khalf, 0), min(r.z + g.khalf, g.W - 1), min(r.w + g.khalf, g.H - 1));
-    job_rect[k] = r;
+    job_rect[k] = make_int4(min(a.x, b.x), min(a.y, b.y), max(a.z, b.z), max(a.w, b.w));
     rect[d] = a;
 }
 
-// GridMap.createMapData(other) GridMap.java:118-124: both arrays of the parent are copied — restricted to
-// the rectangle k_assign_slots computed (identical result, see there) — plus the dirty-tile bitmap.
-// grid = chunks_per_map * max_dups; CTAs beyond num_dup exit.  Rows are moved as 16-byte vectors.
+// GridMap.createMapData(other) GridMap.java:118-124 copies logData and likelihoodData of the parent.  Here a map IS
+// its counter pairs (logData in closed form; the field is evaluated on demand from them), so the copy moves 8 bytes
+// per cell — restricted to the rectangle k_assign_slots computed (identical result, see there).
+// grid = chunks_per_map * max_dups; CTAs beyond num_dup exit.  Rows are moved as 16-byte vectors, 8 per thread in flight.
 // With `dup_src_rank` the source slot lives in another rank's arena: the same kernel then PULLS the rows
 // over NVLink through the peer mappings of PeerTable (cudaIpc), one 16-byte load per lane.
-__global__ void __launch_bounds__(256) k_copy_maps(CellCounts* __restrict__ counts, double* __restrict__ lik,
-                                                   uint32_t* __restrict__ dirty, const int* __restrict__ dup_src,
+__global__ void __launch_bounds__(256) k_copy_maps(CellCounts* __restrict__ counts, const int* __restrict__ dup_src,
                                                    const int* __restrict__ dup_dst, const int4* __restrict__ dup_rect,
-                                                   const Stats* __restrict__ st, size_t cells, int W, int tile_words,
+                                                   const Stats* __restrict__ st, size_t cells, int W,
                                                    int chunks_per_map, const int* __restrict__ dup_src_rank,
                                                    PeerTable peers, const int* __restrict__ job_level, int level) {
     const int k = blockIdx.x / chunks_per_map;
@@ -2568,18 +2510,7 @@ __global__ void __launch_bounds__(256) k_copy_maps(CellCounts* __restrict__ coun
     if (job_level && job_level[k] != level) return;
     const int chunk = blockIdx.x - k * chunks_per_map;
     const int src = dup_src[k], dst = dup_dst[k];
-    const CellCounts* src_counts = counts;
-    const double* src_lik = lik;
-    const uint32_t* src_dirty = dirty;
-    if (dup_src_rank) {
-        const int q = dup_src_rank[k];
-        src_counts = peers.counts[q];
-        src_lik = peers.lik[q];
-        src_dirty = peers.dirty[q];
-    }
-    if (chunk == 0)
-        for (int i = threadIdx.x; i < tile_words; i += 256)
-            dirty[(size_t)dst * tile_words + i] = src_dirty[(size_t)src * tile_words + i];
+    const CellCounts* src_counts = dup_src_rank ? peers.counts[dup_src_rank[k]] : counts;
     const int4 r = dup_rect[k];
     if (r.x > r.z || r.y > r.w) return;
     const int rows = r.w - r.y + 1;
@@ -2587,37 +2518,30 @@ __global__ void __launch_bounds__(256) k_copy_maps(CellCounts* __restrict__ coun
     const int y0 = r.y + chunk * per, y1 = min(r.w + 1, y0 + per);
     const CellCounts* cs = src_counts + (size_t)src * cells;
     CellCounts* cd = counts + (size_t)dst * cells;
-    const double* ls = src_lik + (size_t)src * cells;
-    double* ld = lik + (size_t)dst * cells;
     if (((cells | (size_t)W) & 1) == 0) {  // even row length and slot size: rows start 16-byte aligned
         const int x0 = r.x & ~1, n2 = ((r.z | 1) - x0 + 1) / 2;  // pairs of cells per row
         const uint4* cs4 = reinterpret_cast<const uint4*>(cs);
         uint4* cd4 = reinterpret_cast<uint4*>(cd);
-        const uint4* ls4 = reinterpret_cast<const uint4*>(ls);
-        uint4* ld4 = reinterpret_cast<uint4*>(ld);
-        const int total = (y1 - y0) * n2;  // (row, pair) flattened: 4 independent 16-byte loads per array in flight
-        for (int e0 = threadIdx.x; e0 < total; e0 += 4 * 256) {
-            size_t o[4];
-            uint4 a[4], b[4];
+        const int total = (y1 - y0) * n2;  // (row, pair) flattened: 8 independent 16-byte loads in flight per thread
+        for (int e0 = threadIdx.x; e0 < total; e0 += 8 * 256) {
+            size_t o[8];
+            uint4 a[8];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 const int e = e0 + u * 256;
                 const int yy = e / n2, xx = e - yy * n2;
                 o[u] = ((size_t)(y0 + yy) * W + x0) / 2 + xx;
-                if (e < total) { a[u] = cs4[o[u]]; b[u] = ls4[o[u]]; }
+                if (e < total) a[u] = cs4[o[u]];  // plain loads: many children read the same parent (L2 hits)
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (e0 + u * 256 < total) { cd4[o[u]] = a[u]; ld4[o[u]] = b[u]; }
+            for (int u = 0; u < 8; u++)
+                if (e0 + u * 256 < total) __stcs(cd4 + o[u], a[u]);  // written once, read next step at the earliest
         }
     } else {
         const int n = r.z - r.x + 1;
         for (int y = y0; y < y1; y++) {
             const size_t o = (size_t)y * W + r.x;
-            for (int i = threadIdx.x; i < n; i += 256) {
-                cd[o + i] = cs[o + i];
-                ld[o + i] = ls[o + i];
-            }
+            for (int i = threadIdx.x; i < n; i += 256) cd[o + i] = cs[o + i];
         }
     }
 }
@@ -2744,6 +2668,17 @@ __global__ void k_pose_pack(const float* __restrict__ xyt, float4* __restrict__ 
 __global__ void k_pose_fill_remote(PoseTable poses, float4* __restrict__ local, int lo, int cnt, int P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P && (i < lo || i >= lo + cnt)) local[i] = poses.at(i);
+}
+__global__ void k_gather_pose(const int* __restrict__ parents, const float4* __restrict__ in, float4* __restrict__ out, int P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) out[i] = in[parents[i]];
+}
+// GridMap.applyMeasurement on one per-particle map (no dirty-tile bookkeeping)
+__global__ void k_apply_one_red(CellCounts* __restrict__ counts, int4* __restrict__ rect, float sx, float sy, float ex,
+                                float ey, float meas, int was_hit, Geometry g) {
+    CellBox box;
+    apply_measurement_red<false>(counts, g, sx, sy, ex, ey, meas, was_hit != 0, box);
+    if (box.x1 >= 0) *rect = make_int4(min(rect->x, box.x0), min(rect->y, box.y0), max(rect->z, box.x1), max(rect->w, box.y1));
 }
 __global__ void k_pose_unpack(const float4* __restrict__ pose, float* __restrict__ xyt, int P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

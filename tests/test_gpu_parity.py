@@ -136,7 +136,8 @@ def test_determinism_and_profile(cuda):
             h.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta, normals[s])
             h.resample(float(uniforms[s]))
         ms, launches = h.profile_read()
-        assert launches["score"] >= steps and launches["map_update"] >= steps and ms["likelihood"] > 0
+        # per-particle maps: no likelihood-field launches in the step (the field is evaluated where the scan reads it)
+        assert launches["score"] >= steps and launches["map_update"] >= steps and ms["score"] > 0
         outs.append((h.poses().tobytes(), h.weights().tobytes(), h.get_map(5, B.MAP_FREE_COUNT).tobytes(),
                      h.get_map(5, B.MAP_LIKELIHOOD).tobytes(), h.parents().tobytes()))
         h.close()
