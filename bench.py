@@ -294,13 +294,13 @@ def time_workload(ctx, name, wl, P_total, steps, warmup, e2e_steps):
     hits = [s.num_hits for s in scans]
     flush = ctx["flush"]
 
-    def step(i):
+    def step(i, policy=B.POLICY_ALWAYS):
         k = i % nscan
         a = (t_xy[k].data_ptr(), t_d[k].data_ptr(), t_h[k].data_ptr(), Bn, scans[k].d_center, scans[k].d_theta)
         if runner:
-            runner.step(*a, policy=B.POLICY_ALWAYS)
+            runner.step(*a, policy=policy)
         else:
-            h.step_dev(*a, None, B.POLICY_ALWAYS, -1.0)
+            h.step_dev(*a, None, policy, -1.0)
 
     def barrier():
         if dist:
@@ -360,10 +360,28 @@ def time_workload(ctx, name, wl, P_total, steps, warmup, e2e_steps):
     sampler.stop_flag = True
     t_b2b = e0.elapsed_time(e1) * 1e-3
     scored_b2b = sum(P_total * hits[(warmup + steps + i) % nscan] for i in range(steps))
+    t_never = None
+    if wl["mode"] == "per_particle":
+        # the other regime of the per-particle path: no resampling, so EVERY particle's map takes the scan (with a
+        # resampling only the selected parents' maps do: the rest is dropped); same steps, back to back
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        step(warmup + 2 * steps - 1, B.POLICY_NEVER)  # leaves its scan pending, like every step of the loop below
+        barrier()
+        h.profile_reset()
+        h.profile_enable(True)
+        e2.record(stream)
+        for i in range(steps):  # each step integrates its predecessor's scan into every map, then scores its own
+            step(warmup + 2 * steps + i, B.POLICY_NEVER)
+        e3.record(stream)
+        barrier()
+        phase_never, _ = h.profile_read()
+        h.profile_enable(False)
+        t_never = e2.elapsed_time(e3) * 1e-3 / steps
     if dist:
-        t = torch.tensor([t_dev, t_b2b], dtype=torch.float64, device=dev)
+        t = torch.tensor([t_dev, t_b2b, t_never or 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_b2b = float(t[0].item()), float(t[1].item())
+        t_never = float(t[2].item()) if t_never is not None else None
     neff = h.read_neff()
 
     # ---- e2e: host buffers, copies inside the timed region ----
@@ -432,7 +450,8 @@ def time_workload(ctx, name, wl, P_total, steps, warmup, e2e_steps):
     barrier()
     h.close()
     return dict(name=name, wl=wl, P_total=P_total, P_local=P_total // world, W=W, H=H, steps=steps, warmup=warmup,
-                t_dev=t_dev, t_b2b=t_b2b, scored=scored, scored_b2b=scored_b2b, t_wall=t_wall, phase_ms=phase_ms,
+                t_dev=t_dev, t_b2b=t_b2b, t_never=t_never, phase_never=phase_never if t_never is not None else None,
+                scored=scored, scored_b2b=scored_b2b, t_wall=t_wall, phase_ms=phase_ms,
                 phase_launches=phase_launches, launches=int(launches), neff=neff, e2e=e2e, clocks=sampler.result(),
                 hits=float(np.mean(hits)), scans=scans)
 
@@ -485,11 +504,14 @@ def roofline_of(r, args):
         cells_per_scan.append(float(np.sum(3 + np.abs(np.floor(ex / res) - np.floor(x / res)) +
                                            np.abs(np.floor(ey / res) - np.floor(y / res)))))
     ub = r["P_local"] * float(np.mean(cells_per_scan)) * 8.0
-    upd_ms = r["phase_ms"]["map_update"] / max(1, steps)
-    return {"kernel": "k_map_update", "bound": kc.get("bound", "l2_atomic"), "achieved": ub / (upd_ms * 1e-3) / 1e9,
+    # measured in the no-resample regime, where every particle's map takes the scan (with a resampling only the
+    # selected parents' maps do, and the step is dominated by the streaming map copies instead)
+    upd_ms = (r.get("phase_never") or r["phase_ms"])["map_update"] / max(1, steps)
+    return {"kernel": "k_map_update_red", "bound": kc.get("bound", "l2_atomic"), "achieved": ub / (upd_ms * 1e-3) / 1e9,
             "peak": peak, "unit": "GB/s", "frac": ub / (upd_ms * 1e-3) / 1e9 / peak,
             "traffic": kc.get("dram_bytes_per_launch"), "traffic_source": kc.get("source"), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": ub, "launch_ms": upd_ms,
+            "regime": "no_resample (every map integrates the scan)",
             "note": "scatter of counter increments: see DESIGN.md §3 for what bounds it"}
 
 
@@ -503,7 +525,16 @@ def summarise(r, args, world, scaling):
            "gpu_launches": r["launches"], "clocks": r["clocks"], "neff_last": r["neff"]}
     if r["e2e"]:
         out["e2e"] = r["e2e"]
+    if r.get("t_never") is not None:
+        out["no_resample"] = no_resample_of(r)
     return out
+
+
+def no_resample_of(r):
+    return {"ms_per_step": 1e3 * r["t_never"],
+            "phases_ms_per_step": {k: v / r["steps"] for k, v in (r.get("phase_never") or {}).items() if v > 0},
+            "note": "same scans with GMS_RESAMPLE_NEVER, back to back: every particle's map integrates the scan "
+                    "(with a resampling only the selected parents' maps do, the others are dropped with their particles)"}
 
 
 def run_gpu(args, wl):
@@ -582,6 +613,8 @@ def run_gpu(args, wl):
     }
     if r["e2e"]:
         line["e2e"] = r["e2e"]
+    if r.get("t_never") is not None:
+        line["no_resample"] = no_resample_of(r)
     if parity:
         line["parity_check"] = parity
     if extra:

@@ -101,6 +101,15 @@ struct gms_handle {
     struct FieldOverride { bool fresh; double* snap; };  // fresh: blur(counters now); else an explicit copy
     std::unordered_map<int, FieldOverride> field_ovr;    // slot -> override
     CellCounts* fld_counts = nullptr;  // scratch counter map for the subtraction (allocated on first use)
+    // Deferred integration (per-particle maps): an update leaves integrateObservation (SLAM.java:103-105) PENDING.  If a
+    // resampling comes next, only the particles it selected as parents are integrated (the others are dropped with
+    // their maps: dead work); anything else that reads or writes a map, and the next update, integrates all first.
+    bool integ_pending = false;
+    bool defer_integration = true;     // GMS_DEFER_INTEGRATION=0: integrate inside every update (round-1 order)
+    int field_bset = 0;                // beam-table set a FIELD_BEFORE_LAST field refers to
+    int integ_B = 0, integ_pose_buf = 0, integ_slot_buf = 0, integ_bset = 0;
+    int* used = nullptr;               // P flags: particle was selected as a parent by the last resampling
+    unsigned long long mapseq = 0;     // per-particle maps across ranks: sequence number of k_maps_final
     float4* upd_pose[2] = {nullptr, nullptr};  // poses the last scan was integrated from, once gms_set_poses has
     bool use_upd_pose = false;                 // replaced the live ones (otherwise those are still pose[cur])
     bool self_list = false;      // shared map, bitmap small enough: the refresh builds its own work list
@@ -220,6 +229,8 @@ struct gms_handle {
 
 namespace {
 
+int flush_integration(gms_handle* h);
+
 int fail(gms_handle* h, int code, const std::string& msg) {
     if (h) h->err = msg; else g_create_err = msg;
     return code;
@@ -239,11 +250,19 @@ int cuda_fail(gms_handle* h, cudaError_t e, const char* what) {
 #define ENTER_STEP(h)                                              \
     if (!(h)) return GMS_ERR_INVALID_ARG;                          \
     CK(cudaSetDevice((h)->dev))
-#define ENTER(h)                                                   \
+#define ENTER_KEEP(h)                                              \
     ENTER_STEP(h);                                                 \
     if ((h)->b_pending) {                                          \
         CK(cudaStreamWaitEvent((h)->stream, (h)->ev_done_b, 0));   \
         (h)->b_pending = false;                                    \
+    }
+// ENTER_KEEP: entry points that neither read nor write a map (resampling, particle-array getters, bookkeeping): a
+// pending integration of per-particle maps stays pending.  ENTER: everything else integrates first.
+#define ENTER(h)                                                   \
+    ENTER_KEEP(h);                                                 \
+    if ((h)->integ_pending) {                                      \
+        int rc_flush_ = flush_integration(h);                      \
+        if (rc_flush_) return rc_flush_;                           \
     }
 
 struct Phase {  // RAII: CUDA events around one phase when profiling is on
@@ -342,7 +361,7 @@ void free_all(gms_handle* h) {
     cudaFree(h->xarea[0]); cudaFree(h->xarea[1]); cudaFree(h->xflags4);
     for (int i = 0; i < 2; i++) { cudaFree(h->pose[i]); cudaFree(h->w[i]); cudaFree(h->lw[i]); cudaFree(h->slot[i]); }
     cudaFree(h->parents); cudaFree(h->cdf); cudaFree(h->counts); cudaFree(h->lik); cudaFree(h->fac); cudaFree(h->rect);
-    cudaFree(h->fld_counts); cudaFree(h->upd_pose[0]); cudaFree(h->upd_pose[1]);
+    cudaFree(h->fld_counts); cudaFree(h->upd_pose[0]); cudaFree(h->upd_pose[1]); cudaFree(h->used);
     for (auto& kv : h->field_ovr) cudaFree(kv.second.snap);
     cudaFree(h->dirty); cudaFree(h->dirty_alt); cudaFree(h->word_off); cudaFree(h->tile_list); cudaFree(h->dup_rect);
     cudaFree(h->dup_src_rank); cudaFree(h->dup_level); cudaFree(h->dup_src); cudaFree(h->dup_dst); cudaFree(h->scratch2p);
@@ -418,10 +437,12 @@ int ensure_beams(gms_handle* h, int B) {
     CK(cudaStreamSynchronize(h->side_a));
     CK(cudaStreamSynchronize(h->side_b));
     h->b_pending = false;
+    if (int rc_ = flush_integration(h)) return rc_;  // a pending integration reads the tables that are about to go
+    CK(cudaStreamSynchronize(h->stream));
     // a virtual per-particle field in state FIELD_BEFORE_LAST is defined through the last step's beam table: carry it over
     const bool keep_scan = h->cfg.map_mode == GMS_MAP_PER_PARTICLE && h->field_state == gms_handle::FIELD_BEFORE_LAST;
-    BeamSet old_scan = h->bs[h->bset];
-    if (keep_scan) h->bs[h->bset] = BeamSet{};
+    BeamSet old_scan = h->bs[h->field_bset];
+    if (keep_scan) h->bs[h->field_bset] = BeamSet{};
     free_beamset(h->bs[0]); free_beamset(h->bs[1]); free_beamset(h->ops);
     cudaFree(h->ray_cells); cudaFree(h->ray_count); cudaFree(h->ray_start);
     cudaFree(h->raw_angle); cudaFree(h->raw_dist);
@@ -433,7 +454,7 @@ int ensure_beams(gms_handle* h, int B) {
     for (BeamSet* b : {&h->bs[0], &h->bs[1], &h->ops})
         if ((rc = alloc_beamset(h, *b, cap))) return rc;
     if (keep_scan) {
-        BeamSet& nb = h->bs[h->bset];
+        BeamSet& nb = h->bs[h->field_bset];
         const size_t n = (size_t)h->field_B;
         CK(cudaMemcpy(nb.xy, old_scan.xy, n * 16, cudaMemcpyDeviceToDevice));
         CK(cudaMemcpy(nb.hit, old_scan.hit, n, cudaMemcpyDeviceToDevice));
@@ -662,18 +683,33 @@ int launch_shared_update(gms_handle* h, const BeamSet& b, int B) {
 }
 
 // per-particle maps (or one explicit {pose, slot} pair): one thread per (particle, beam) ray
-int launch_map_update(gms_handle* h, const BeamSet& b, const float4* pose, int lo, int cnt, const int* slot, int B) {
+int launch_map_update(gms_handle* h, const BeamSet& b, const float4* pose, int lo, int cnt, const int* slot, int B,
+                      const int* used = nullptr) {
     if (B <= 0) return GMS_OK;
     Phase ph(h, GMS_PHASE_MAP_UPDATE);
     const long long total = (long long)cnt * B;
     if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE)  // no dirty-tile bookkeeping: fire-and-forget reductions
         LAUNCH(GMS_PHASE_MAP_UPDATE, k_map_update_red<false><<<blocks_for(total, 128), 128, 0, h->stream>>>(
-                                         pose, lo, cnt, b.xy, b.meas, b.hit, B, h->counts, slot, h->rect, h->g));
+                                         pose, lo, cnt, b.xy, b.meas, b.hit, B, h->counts, slot, h->rect, used, h->st, h->g));
     else
         LAUNCH(GMS_PHASE_MAP_UPDATE, k_map_update<<<blocks_for(total, 128), 128, 0, h->stream>>>(
                                          pose, lo, cnt, b.xy, b.meas, b.hit, B, h->counts, slot, h->rect, h->dirty, h->g));
     return GMS_OK;
 }
+
+// the pending integration of the last update: every local particle, or (`used`) only the parents a resampling selected
+int integrate_pending(gms_handle* h, const int* used) {
+    if (!h->integ_pending) return GMS_OK;
+    h->integ_pending = false;
+    int rc = launch_map_update(h, h->bs[h->integ_bset], h->pose[h->integ_pose_buf], h->lo, h->cnt,
+                               h->slot[h->integ_slot_buf] + h->lo, h->integ_B, used);
+    if (rc) return rc;
+    h->field_state = gms_handle::FIELD_BEFORE_LAST;  // likelihoodData now lags the counters by this scan
+    h->field_B = h->integ_B;
+    h->field_bset = h->integ_bset;
+    return GMS_OK;
+}
+int flush_integration(gms_handle* h) { return integrate_pending(h, nullptr); }
 
 // A4 — GridMap.findBestPoseOptim GridMap.java:348-369 as a CPU hook between motion and scoring: the local
 // particles' poses go to the host, the callback may replace them, they come back.  Default: no hook (the
@@ -714,7 +750,9 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
     const bool shared = c.map_mode == GMS_MAP_SHARED;
     const bool hook = h->opt_fn != nullptr;
     const bool fork = shared && h->overlap && !hook;
-    int rc = ensure_beams(h, B);  // grow the beam tables (if needed) while every stream can still be drained from here
+    int rc = flush_integration(h);  // an update without a resampling in between: integrate the previous scan everywhere
+    if (rc) return rc;
+    rc = ensure_beams(h, B);  // grow the beam tables (if needed) while every stream can still be drained from here
     if (rc) return rc;
     BeamSet& bs = cur_beams(h);
     if (d_xy != (const double*)bs.xy) bs.view(bs.cap);  // device-resident scan: private copies at the capacity offsets
@@ -781,10 +819,10 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
 
     const bool skip = std::fabs(d_theta) > (M_PI / 180.0) * c.skip_update_deg;  // SLAM.java:82
     if (!shared && !skip && B > 0) {
-        rc = launch_map_update(h, bs, h->pose[h->cur], h->lo, h->cnt, h->slot[h->slot_cur] + h->lo, B);
-        if (rc) return rc;
-        h->field_state = gms_handle::FIELD_BEFORE_LAST;  // likelihoodData now lags the counters by this scan
-        h->field_B = B;
+        // integrateObservation (SLAM.java:103-105) is left pending: see gms_handle::integ_pending
+        h->integ_pending = true;
+        h->integ_B = B; h->integ_pose_buf = h->cur; h->integ_slot_buf = h->slot_cur; h->integ_bset = h->bset;
+        if (!h->defer_integration && (rc = flush_integration(h))) return rc;
     }
     if (c.nranks > 1 && h->direct && !h->sharded_post) {
         // this rank's log-weights -> every rank's receive buffer (NVLink stores), then one flag per receiver.  With
@@ -973,9 +1011,23 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
         return fail(h, GMS_ERR_STATE, "per-particle maps across ranks: per-map operator results (gms_map_*) cannot follow "
                                       "their particles through a resampling; call an update first");
     const int old_slots = h->slot_cur;
+    if (h->cfg.nranks > 1 && !h->peers_ready)
+        return fail(h, GMS_ERR_STATE, "per-particle maps across ranks: call gms_ipc_import before resampling");
+    if (h->integ_pending) {  // the scan goes into the maps of the selected parents only: the others are dropped
+        if (!h->used) CK(cudaMalloc((void**)&h->used, (size_t)P * 4));
+        CK(cudaMemsetAsync(h->used, 0, (size_t)P * 4, h->stream));
+        LAUNCH(GMS_PHASE_MAP_UPDATE, k_mark_used<<<blocks_for(P, 256), 256, 0, h->stream>>>(h->parents, P, h->used));
+        int rc_ = integrate_pending(h, h->used);
+        if (rc_) return rc_;
+    }
     if (h->cfg.nranks > 1) {
-        if (!h->peers_ready)
-            return fail(h, GMS_ERR_STATE, "per-particle maps across ranks: call gms_ipc_import before resampling");
+        {   // every rank's maps are final before any rank pulls one (k_maps_final)
+            Phase ph(h, GMS_PHASE_EXCHANGE);
+            Shard sh{};
+            sh.nranks = h->cfg.nranks; sh.rank = h->cfg.rank; sh.seq = ++h->mapseq;
+            for (int q = 0; q < sh.nranks; q++) sh.flags[q] = q == h->cfg.rank ? h->xflags4 : h->peer_xflags4[q];
+            LAUNCH(GMS_PHASE_EXCHANGE, k_maps_final<<<1, 32, 0, h->stream>>>(sh, h->st));
+        }
         Phase ph(h, GMS_PHASE_MAP_COPY);
         const int nxt = h->slot_cur ^ 1;
         LAUNCH(GMS_PHASE_MAP_COPY, k_assign_slots_mr<<<1, 1024, 0, h->stream>>>(
@@ -1094,7 +1146,7 @@ int slot_of(gms_handle* h, int particle, int* slot) {
 int field_of(gms_handle* h, int particle, int s, const double** out) {
     if (h->cfg.map_mode == GMS_MAP_SHARED) { *out = h->lik; return GMS_OK; }
     const CellCounts* map = h->counts + (size_t)s * h->cells;
-    int state = h->field_state;
+    int state = h->integ_pending ? (int)gms_handle::FIELD_FRESH : h->field_state;  // pending: the counters still lack the scan
     auto it = h->field_ovr.find(s);
     if (it != h->field_ovr.end()) {
         if (it->second.snap) { *out = it->second.snap; return GMS_OK; }
@@ -1111,11 +1163,11 @@ int field_of(gms_handle* h, int particle, int s, const double** out) {
         if (!h->fld_counts) CK(cudaMalloc((void**)&h->fld_counts, h->cells * sizeof(CellCounts)));
         CK(cudaMemcpyAsync(h->fld_counts, map, h->cells * sizeof(CellCounts), cudaMemcpyDeviceToDevice, h->stream));
         CK(cudaMemsetAsync(h->tmp_slot, 0, sizeof(int), h->stream));
-        const BeamSet& b = cur_beams(h);
+        const BeamSet& b = h->bs[h->field_bset];
         const float4* poses = h->use_upd_pose ? h->upd_pose[0] : h->pose[h->cur];
         LAUNCH(GMS_PHASE_COUNT - 1, k_map_update_red<true><<<blocks_for(h->field_B, 128), 128, 0, h->stream>>>(
                                         poses, particle, 1, b.xy, b.meas, b.hit, h->field_B, h->fld_counts, h->tmp_slot,
-                                        nullptr, h->g));
+                                        nullptr, nullptr, h->st, h->g));
         map = h->fld_counts;
     }
     return launch_blur_whole(h, map, h->lik, h->dirty, h->word_off, h->tile_list);
@@ -1181,6 +1233,7 @@ int do_reset(gms_handle* h) {
     clear_field_overrides(h);
     h->field_state = gms_handle::FIELD_ZERO;
     h->use_upd_pose = false;
+    h->integ_pending = false;
     if (h->dirty_alt) CK(cudaMemsetAsync(h->dirty_alt, 0, (size_t)h->g.tile_words * 4, h->stream));
     h->alt_needs_clear = false;
     CK(cudaMemsetAsync(h->st, 0, sizeof(Stats), h->stream));
@@ -1406,6 +1459,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->sort.rank, (size_t)h->cnt * 4));
     CKC(cudaMalloc((void**)&h->sort.order, (size_t)h->cnt * 4));
     h->ntiles = (h->P + 1023) / 1024;
+    if (const char* e = std::getenv("GMS_DEFER_INTEGRATION")) h->defer_integration = std::atoi(e) != 0;
     if (const char* e = std::getenv("GMS_SCORE_V")) h->score_v = std::max(0, std::min(6, std::atoi(e)));
     if (const char* e = std::getenv("GMS_SCORE_G")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) h->score_g = v; }
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, h->dev) == cudaSuccess) h->num_sms = prop.multiProcessorCount; }
@@ -1482,7 +1536,7 @@ EXPORT int gms_get_info(const gms_handle* h, gms_info* info) {
 }
 
 EXPORT int gms_reset(gms_handle* h) {
-    ENTER(h);
+    ENTER_KEEP(h);
     return do_reset(h);
 }
 
@@ -1507,7 +1561,7 @@ EXPORT int gms_update(gms_handle* h, const double* beam_xy, const double* beam_d
 }
 
 EXPORT int gms_resample(gms_handle* h, double u01) {
-    ENTER(h);
+    ENTER_KEEP(h);
     { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (u01 >= 1.0) return fail(h, GMS_ERR_INVALID_ARG, "gms_resample: u01 must be < 1");
     h->fold_wpose = true;
@@ -1517,7 +1571,7 @@ EXPORT int gms_resample(gms_handle* h, double u01) {
 }
 
 EXPORT int gms_calculate_neff(gms_handle* h, double* neff_out) {
-    ENTER(h);
+    ENTER_KEEP(h);
     { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!neff_out) return GMS_ERR_INVALID_ARG;
     LAUNCH(GMS_PHASE_NORMALISE, k_neff<<<h->ntiles, 1024, 0, h->stream>>>(h->w[h->cur], h->P, h->ntiles, h->np, h->st));
@@ -1530,7 +1584,7 @@ EXPORT int gms_calculate_neff(gms_handle* h, double* neff_out) {
 }
 
 EXPORT int gms_get_weighted_pose(gms_handle* h, float pose[3]) {
-    ENTER(h);
+    ENTER_KEEP(h);
     { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!pose) return GMS_ERR_INVALID_ARG;
     if (!h->wpose_valid) {  // otherwise the last normalise / resample launch already produced it
@@ -1547,7 +1601,7 @@ EXPORT int gms_get_weighted_pose(gms_handle* h, float pose[3]) {
 }
 
 EXPORT int gms_get_strongest(gms_handle* h, int32_t* index, float pose[3], double* weight) {
-    ENTER(h);
+    ENTER_KEEP(h);
     { int rc_ = complete_resample(h); if (rc_) return rc_; }  // the first child may belong to another rank's block
     int rc = fetch_stats(h);
     if (rc) return rc;
@@ -1566,7 +1620,7 @@ EXPORT int gms_get_strongest(gms_handle* h, int32_t* index, float pose[3], doubl
 }
 
 EXPORT int gms_get_poses(gms_handle* h, float* xyt) {
-    ENTER(h);
+    ENTER_KEEP(h);
     { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!xyt) return GMS_ERR_INVALID_ARG;
     { int rc_ = materialize_poses(h); if (rc_) return rc_; }
@@ -1583,19 +1637,19 @@ static int copy_out(gms_handle* h, void* dst, const void* src, size_t bytes) {
     return GMS_OK;
 }
 EXPORT int gms_get_weights(gms_handle* h, double* w) {
-    ENTER(h);
+    ENTER_KEEP(h);
     { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!w) return GMS_ERR_INVALID_ARG;
     return copy_out(h, w, h->w[h->cur], (size_t)h->P * 8);
 }
 EXPORT int gms_get_log_weights(gms_handle* h, double* lw) {
-    ENTER(h);
+    ENTER_KEEP(h);
     { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!lw) return GMS_ERR_INVALID_ARG;
     return copy_out(h, lw, h->lw[h->cur], (size_t)h->P * 8);
 }
 EXPORT int gms_get_parents(gms_handle* h, int32_t* parents) {
-    ENTER(h);
+    ENTER_KEEP(h);
     { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!parents) return GMS_ERR_INVALID_ARG;
     return copy_out(h, parents, h->parents, (size_t)h->P * 4);
@@ -1646,7 +1700,7 @@ EXPORT int gms_set_poses(gms_handle* h, const float* xyt) {
     return GMS_OK;
 }
 EXPORT int gms_set_weights(gms_handle* h, const double* w) {
-    ENTER(h);
+    ENTER_KEEP(h);
     { int rc_ = complete_resample(h); if (rc_) return rc_; }
     if (!w) return GMS_ERR_INVALID_ARG;
     CK(cudaMemcpyAsync(h->w[h->cur], w, (size_t)h->P * 8, cudaMemcpyHostToDevice, h->stream));
@@ -1758,7 +1812,7 @@ EXPORT int gms_map_probability_of(gms_handle* h, int32_t particle, const float p
 
 EXPORT int gms_trace_rays(gms_handle* h, const float* rays, int32_t n, int32_t extra, int32_t* cells_xy, int32_t cap,
                           int32_t* counts) {
-    ENTER(h);
+    ENTER_KEEP(h);
     if (!rays || !counts || n < 0 || cap < 0 || extra < 0 || (cap > 0 && !cells_xy)) return GMS_ERR_INVALID_ARG;
     if (n == 0) return GMS_OK;
     float4* d_rays = nullptr;
@@ -1812,17 +1866,17 @@ EXPORT int gms_update_begin_dev(gms_handle* h, const double* d_xy, const double*
     return step_begin(h, d_xy, d_dist, d_hit, B, d_center, d_theta, d_normals);
 }
 EXPORT int gms_join_streams(gms_handle* h) {
-    ENTER(h);  // the main stream now waits for the map integration running on the side stream
+    ENTER_KEEP(h);  // the main stream now waits for the map integration running on the side stream
     return GMS_OK;
 }
 EXPORT int gms_set_pose_optimizer(gms_handle* h, gms_pose_optimizer_fn fn, void* user) {
-    ENTER(h);
+    ENTER_KEEP(h);
     h->opt_fn = fn;
     h->opt_user = user;
     return GMS_OK;
 }
 EXPORT int gms_update_end_dev(gms_handle* h, int32_t policy, double u01) {
-    ENTER(h);
+    ENTER_KEEP(h);
     if (policy < 0 || policy > 2 || u01 >= 1.0) return fail(h, GMS_ERR_INVALID_ARG, "bad resample policy / u01");
     return step_end(h, policy, u01);
 }
@@ -1847,7 +1901,7 @@ EXPORT int gms_exchange_buffers(gms_handle* h, void** dl, size_t* lb, void** dg,
     return GMS_OK;
 }
 EXPORT int gms_read_neff(gms_handle* h, double* neff) {
-    ENTER(h);
+    ENTER_KEEP(h);
     if (!neff) return GMS_ERR_INVALID_ARG;
     int rc = fetch_stats(h);
     if (rc) return rc;
@@ -1855,24 +1909,24 @@ EXPORT int gms_read_neff(gms_handle* h, double* neff) {
     return GMS_OK;
 }
 EXPORT int gms_sync(gms_handle* h) {
-    ENTER(h);  // joins a pending map integration into the main stream first
+    ENTER_KEEP(h);  // joins a pending map integration into the main stream first
     CK(cudaStreamSynchronize(h->stream));
     return GMS_OK;
 }
 EXPORT int gms_set_stream(gms_handle* h, void* s) {
-    ENTER(h);
+    ENTER_KEEP(h);
     CK(cudaStreamSynchronize(h->stream));
     h->stream = s ? (cudaStream_t)s : h->own_stream;
     return GMS_OK;
 }
 EXPORT int gms_profile_enable(gms_handle* h, int32_t on) {
-    ENTER(h);
+    ENTER_KEEP(h);
     int rc = flush_profile(h);
     h->profile = on != 0;
     return rc;
 }
 EXPORT int gms_profile_read(gms_handle* h, double* ms, int64_t* launches) {
-    ENTER(h);
+    ENTER_KEEP(h);
     int rc = flush_profile(h);
     if (rc) return rc;
     for (int i = 0; i < GMS_PHASE_COUNT; i++) {
@@ -1882,7 +1936,7 @@ EXPORT int gms_profile_read(gms_handle* h, double* ms, int64_t* launches) {
     return GMS_OK;
 }
 EXPORT int gms_profile_reset(gms_handle* h) {
-    ENTER(h);
+    ENTER_KEEP(h);
     int rc = flush_profile(h);
     for (int i = 0; i < GMS_PHASE_COUNT; i++) { h->phase_ms[i] = 0; h->phase_launches[i] = 0; }
     return rc;
@@ -1895,7 +1949,7 @@ EXPORT int gms_launch_count(gms_handle* h, int64_t* n) {
 
 // ---- per-particle maps across ranks: peer mappings (one process per GPU on one node) ----------------
 EXPORT int gms_ipc_export(gms_handle* h, void* handles) {
-    ENTER(h);
+    ENTER_KEEP(h);
     if (!handles) return GMS_ERR_INVALID_ARG;
     if (h->cfg.nranks < 2) return fail(h, GMS_ERR_STATE, "gms_ipc_export: single-rank handle");
     static_assert(sizeof(cudaIpcMemHandle_t) == GMS_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
@@ -1907,7 +1961,7 @@ EXPORT int gms_ipc_export(gms_handle* h, void* handles) {
     return GMS_OK;
 }
 EXPORT int gms_ipc_import(gms_handle* h, const void* all_handles) {
-    ENTER(h);
+    ENTER_KEEP(h);
     if (!all_handles) return GMS_ERR_INVALID_ARG;
     if (h->cfg.nranks < 2) return fail(h, GMS_ERR_STATE, "gms_ipc_import: single-rank handle");
     const cudaIpcMemHandle_t* in = static_cast<const cudaIpcMemHandle_t*>(all_handles);
@@ -1979,7 +2033,7 @@ int upload_raw_and_deskew(gms_handle* h, BeamSet& b, const double* angle, const 
 
 EXPORT int gms_deskew(gms_handle* h, const double* angle, const double* dist, int32_t B, double d_center,
                       double d_theta, double* out_xy, double* out_dist) {
-    ENTER(h);
+    ENTER_KEEP(h);
     if (B < 0 || (B > 0 && (!angle || !dist || !out_xy || !out_dist))) return fail(h, GMS_ERR_INVALID_ARG, "gms_deskew: bad arrays");
     int rc = upload_raw_and_deskew(h, h->ops, angle, dist, nullptr, B, d_center, d_theta);
     if (rc || B == 0) return rc;

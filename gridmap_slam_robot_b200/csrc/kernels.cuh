@@ -1181,17 +1181,23 @@ __global__ void __launch_bounds__(128) k_map_update(const float4* __restrict__ p
 
 // The same without dirty-tile bookkeeping (fire-and-forget RED): the step's kernel for per-particle maps now that
 // their likelihood field is evaluated on demand.  NEG: subtract (see apply_measurement_red); `rect` may be null.
+// `used` (nullable, indexed by the global particle index): integrate only the particles flagged there — when a
+// resampling follows the update, a particle without children is dropped together with its map
+// (SLAM.java:133-153 builds the new list from copies of the selected particles), so integrating the scan into
+// it is dead work; the resampling marks the parents it selected (k_mark_used) and only those are integrated.
 template <bool NEG>
 __global__ void __launch_bounds__(128) k_map_update_red(const float4* __restrict__ pose, int lo, int cnt,
                                                         const double2* __restrict__ all_xy,
                                                         const float* __restrict__ meas,
                                                         const uint8_t* __restrict__ hit, int B,
                                                         CellCounts* __restrict__ counts, const int* __restrict__ slot,
-                                                        int4* __restrict__ rect, Geometry g) {
+                                                        int4* __restrict__ rect, const int* __restrict__ used,
+                                                        const Stats* __restrict__ st, Geometry g) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)cnt * B) return;
     const int li = (int)(gid / B);
     const int b = (int)(gid - (long long)li * B);
+    if (used && (st->xerror || !used[lo + li])) return;
     const int s = slot[li];
     const float4 p = pose[lo + li];
     const Xform t(p.x, p.y, p.z);
@@ -2668,6 +2674,19 @@ __global__ void k_pose_pack(const float* __restrict__ xyt, float4* __restrict__ 
 __global__ void k_pose_fill_remote(PoseTable poses, float4* __restrict__ local, int lo, int cnt, int P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P && (i < lo || i >= lo + cnt)) local[i] = poses.at(i);
+}
+// parents selected by the last resampling (every rank holds the whole parents[] of a per-particle-map resampling)
+__global__ void k_mark_used(const int* __restrict__ parents, int P, int* __restrict__ used) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < P) used[parents[m]] = 1;  // benign race: all writers store 1
+}
+// Per-particle maps across ranks: the maps a resampling copies are final only once their owners have integrated
+// the scan into them (deferred until the parents are known, see k_map_update_red).  One CTA: raise my flag on every
+// rank (after the integration kernel, in stream order), then wait for every rank's flag — the copy kernels behind
+// this one in the stream may pull from any rank.
+__global__ void k_maps_final(Shard sh, Stats* st) {
+    if ((int)threadIdx.x < sh.nranks) shard_signal(sh, 0);
+    shard_wait(sh, 0, st);
 }
 __global__ void k_gather_pose(const int* __restrict__ parents, const float4* __restrict__ in, float4* __restrict__ out, int P) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

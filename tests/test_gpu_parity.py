@@ -553,3 +553,80 @@ def test_full_size_per_particle_maps_sampled_parity(cuda, oracle):
     """BASELINE config 1 with the reference's own map semantics (and config 4's per-GPU share): 1k particles x 360
     beams, each particle with its own 1024^2 map."""
     checks.check_full_size_sampled_pp(cuda, oracle, P=1000, beams=360, grid_m=51.2)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_per_particle_operator_sequences_match_oracle(cuda, oracle, seed):
+    """Per-particle maps keep no likelihood field and integrate a scan only where a map survives:
+    random interleavings of updates, resamplings, pose injection and the per-map GridMap operators must leave
+    exactly what the reference's eager arrays would hold (GridMap.java:106-124,173-250; SLAM.java:80-153) —
+    counters and likelihoodData bit for bit, parents equal, log-probabilities to 1e-9."""
+    from gridmap_slam_robot_b200 import synth
+
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    P, beams, steps = 6, 90, 40
+    kw = dict(num_particles=P, map_width_m=10.0, map_height_m=10.0, origin_x=-5.0, origin_y=-5.0,
+              map_mode=B.MAP_PER_PARTICLE, resample_mode=B.RESAMPLE_LITERAL)
+    g, o = cuda.create(**kw), oracle.create(**kw)
+    scans = synth.make_scans(steps, beams, max_range=4.0)
+    normals, uniforms = synth.make_draws(steps, P, seed=seed)
+    cells = g.W * g.H
+
+    def compare(tag):
+        for i in range(P):
+            for kind in (B.MAP_FREE_COUNT, B.MAP_OCC_COUNT, B.MAP_LIKELIHOOD):
+                assert np.array_equal(g.get_map(i, kind), o.get_map(i, kind)), (tag, i, kind)
+        assert np.array_equal(g.poses(), o.poses()), tag
+        assert np.array_equal(g.parents(), o.parents()), tag
+
+    k = 0
+    for it in range(steps):
+        op = rng.choice(["update", "update", "update_resample", "resample", "set_poses", "apply", "integrate",
+                         "compute", "prob", "set_counts", "read_field", "read_counts"])
+        p = int(rng.integers(P))
+        sc = scans[k % steps]
+        if op in ("update", "update_resample"):
+            d_theta = sc.d_theta if rng.random() > 0.15 else 1.0  # > 30 degrees: the update skips the integration
+            for h in (g, o):
+                h.update(sc.beam_xy, sc.beam_dist, sc.beam_hit, sc.d_center, d_theta, normals[k % steps])
+            k += 1
+            if op == "update_resample":
+                for h in (g, o):
+                    h.resample(float(uniforms[it]))
+        elif op == "resample":
+            for h in (g, o):
+                h.resample(float(uniforms[it]))
+        elif op == "set_poses":
+            xyt = rng.uniform(-1.0, 1.0, size=(P, 3)).astype(np.float32)
+            for h in (g, o):
+                h.set_poses(xyt)
+        elif op == "apply":
+            a = rng.uniform(20.0, 180.0, size=4).astype(np.float32)
+            for h in (g, o):
+                h.map_apply_measurement(p, float(a[0]), float(a[1]), float(a[2]), float(a[3]), 30.0, bool(it & 1))
+        elif op == "integrate":
+            pose = rng.uniform(-1.0, 1.0, size=3).astype(np.float32)
+            for h in (g, o):
+                h.map_integrate_observation(p, pose, sc.beam_xy, sc.beam_dist, sc.beam_hit)
+        elif op == "compute":
+            for h in (g, o):
+                h.map_compute_likelihood(p)
+        elif op == "prob":
+            pose = rng.uniform(-0.5, 0.5, size=3).astype(np.float32)
+            lg, _ = g.map_probability_of(p, pose, sc.beam_xy, sc.beam_hit)
+            lo_, _ = o.map_probability_of(p, pose, sc.beam_xy, sc.beam_hit)
+            assert abs(lg - lo_) <= 1e-9 * max(1.0, abs(lo_)), (it, lg, lo_)
+        elif op == "set_counts":
+            nf = rng.integers(0, 3, size=cells).astype(np.uint32)
+            no = rng.integers(0, 2, size=cells).astype(np.uint32)
+            for h in (g, o):
+                h.set_map_counts(p, nf, no)
+        elif op == "read_field":
+            assert np.array_equal(g.get_map(p, B.MAP_LIKELIHOOD), o.get_map(p, B.MAP_LIKELIHOOD)), (it, op)
+        else:
+            assert np.array_equal(g.get_map(p, B.MAP_FREE_COUNT), o.get_map(p, B.MAP_FREE_COUNT)), (it, op)
+        if it % 4 == 3:
+            compare((it, op))
+    compare("end")
+    g.close()
+    o.close()
