@@ -176,7 +176,17 @@ int gms_get_log_weights(gms_handle* h, double* lw /* P */); /* ln of the un-norm
                                                                finite where Java's product underflows */
 int gms_get_parents(gms_handle* h, int32_t* parents /* P */);/* index i chosen for each m, SLAM.java:147 */
 /* getParticles().get(particle).m.{logData,likelihoodData} GridMap.java:72-74 (particle ignored in
- * shared mode).  bytes must equal W*H*sizeof(element of kind). */
+ * shared mode).  bytes must equal W*H*sizeof(element of kind).
+ * Per-particle maps hold only the counter pairs in device memory.  Two things the reference does eagerly are
+ * evaluated on demand, with results identical to the eager arrays at every observable point:
+ *  - likelihoodData: the step scores the scan against the field evaluated at the looked-up cells straight from the
+ *    counters; GMS_MAP_LIKELIHOOD (and gms_render_map / gms_map_probability_of) materialise the array Java would
+ *    hold at that moment — rebuilt by computeLikelihoodMap before the scan is scored, i.e. from the counters as
+ *    they were BEFORE the last update integrated its scan (SLAM.java:93-105);
+ *  - integrateObservation of an update: left pending until the next call that reads or writes a map (or the next
+ *    update).  If gms_resample / the resampling of gms_update_end_dev comes first, the scan is integrated only into
+ *    the maps of the particles it selects as parents; the others are dropped with their maps (SLAM.java:133-153).
+ * GMS_DEFER_INTEGRATION=0 (environment) integrates inside every update instead. */
 int gms_get_map(gms_handle* h, int32_t particle, int32_t kind, void* dst, size_t bytes);
 
 /* ---- state injection (tests, replay of a saved state) ---------------------------------------- */

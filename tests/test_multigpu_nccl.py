@@ -48,10 +48,11 @@ def _steps(h, stepper, scans, normals, uniforms, lo, cnt, dev, map_particles=(0,
     return out
 
 
-def _worker(rank, world, port, P, steps, beams, q, mode=1, peer=True):
+def _worker(rank, world, port, P, steps, beams, q, mode=1, peer=True, sharded=False):
     import torch
     import torch.distributed as dist
 
+    os.environ["GMS_SHARDED"] = "1" if sharded else "0"  # read by gms_ipc_import
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -77,7 +78,7 @@ def _worker(rank, world, port, P, steps, beams, q, mode=1, peer=True):
     dist.destroy_process_group()
 
 
-def _run(cuda, P, steps, beams, world, mode, peer=True):
+def _run(cuda, P, steps, beams, world, mode, peer=True, sharded=False):
     import torch
     import torch.multiprocessing as mp
 
@@ -90,7 +91,7 @@ def _run(cuda, P, steps, beams, world, mode, peer=True):
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, P, steps, beams, q, mode, peer)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, P, steps, beams, q, mode, peer, sharded)) for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=300) for _ in range(world)]
@@ -132,6 +133,13 @@ WORLDS = [2, 4, 8]
 def test_ranks_equal_one_gpu(cuda, world):
     """Peer exchange: log-weights pushed into every rank's receive buffer (NVLink), poses read through peer maps."""
     _run(cuda, P=8192, steps=6, beams=360, world=world, mode=1)
+
+
+@pytest.mark.parametrize("world", WORLDS)
+def test_ranks_equal_one_gpu_sharded_normalise(cuda, world):
+    """GMS_SHARDED=1: every rank normalises and resamples only its own block (exact 128-bit sums, four tiny exchange
+    rounds); same bar."""
+    _run(cuda, P=8192, steps=6, beams=360, world=world, mode=1, sharded=True)
 
 
 def test_two_gpus_equal_one_gpu_nccl_all_gather(cuda):
