@@ -143,6 +143,8 @@ struct gms_handle {
     const double* peer_w[2][kMaxRanks] = {};
     const double* peer_lw[2][kMaxRanks] = {};
     const int* peer_parents[kMaxRanks] = {};
+    bool exact_sums = false;     // GMS_SHARDED=1 (any handle): the normalise with exact 128-bit sums, so that a sharded
+                                 // multi-rank run and a single-rank run agree bit for bit
     bool sharded_post = false;   // enabled by gms_ipc_import for shared maps (GMS_SHARDED=0 keeps the replicated path)
     bool tile_fx_sharded = false;  // np.fx holds the tile sums of the local block only
     bool blocks_stale = false;   // pose / w / lw / parents hold only this rank's block: getters copy the rest from peers
@@ -176,6 +178,11 @@ struct gms_handle {
     bool resample_partial = false;
     double partial_u01 = 0;
     unsigned long long partial_count = 0;
+    bool copy_bulk = true;      // single-rank map copies on the TMA engine (GMS_COPY_BULK=0: per-thread 16-byte copies)
+    int copy_chunks = 8;        // CTAs per copied map (GMS_COPY_CHUNKS)
+    bool score_dynamic = false;  // k_score_sorted draws its work items from a counter when they exceed the resident warps
+                                // (GMS_SCORE_DYNAMIC=1; measured no faster at 100k particles: 0.110 vs 0.108 ms)
+    unsigned* score_work = nullptr;
     int score_g = 0;  // sub-threads per particle in k_score_sorted (0 = automatic; GMS_SCORE_G overrides: tuning knob)
     int score_v = 2;  // variant of k_score_sorted (GMS_SCORE_V=0..6, identical cell indices; kernels.cuh / DESIGN.md §4.19):
                       // 2 = folded magic constant + per-particle range guard + padded factor field (measured fastest)
@@ -361,6 +368,7 @@ void free_all(gms_handle* h) {
     cudaFree(h->xarea[0]); cudaFree(h->xarea[1]); cudaFree(h->xflags4);
     for (int i = 0; i < 2; i++) { cudaFree(h->pose[i]); cudaFree(h->w[i]); cudaFree(h->lw[i]); cudaFree(h->slot[i]); }
     cudaFree(h->parents); cudaFree(h->cdf); cudaFree(h->counts); cudaFree(h->lik); cudaFree(h->fac); cudaFree(h->rect);
+    cudaFree(h->score_work);
     cudaFree(h->fld_counts); cudaFree(h->upd_pose[0]); cudaFree(h->upd_pose[1]); cudaFree(h->used);
     for (auto& kv : h->field_ovr) cudaFree(kv.second.snap);
     cudaFree(h->dirty); cudaFree(h->dirty_alt); cudaFree(h->word_off); cudaFree(h->tile_list); cudaFree(h->dup_rect);
@@ -584,8 +592,19 @@ int launch_score_sorted(gms_handle* h, unsigned grid, size_t smem, const float4*
         CK(cudaFuncSetAttribute(k_score_sorted<G, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done[h->dev & 63] = true;
     }
+    unsigned* work = nullptr;
+    if (h->score_dynamic) {  // more items than resident warps: persistent CTAs draw them from a counter
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score_sorted<G, V>, 128, smem));
+        const unsigned resident = (unsigned)std::max(1, per_sm) * (unsigned)h->num_sms;
+        if (grid > resident + resident / 8) {
+            CK(cudaMemsetAsync(h->score_work, 0, 4, h->stream));
+            work = h->score_work;
+            grid = resident;
+        }
+    }
     LAUNCH(GMS_PHASE_SCORE, k_score_sorted<G, V><<<grid, 128, smem, h->stream>>>(pose, lo, cnt, b.hit_xy, b.num_hit, h->fac,
-                                                                                 order, lw, xlocal, b.rmax2, h->g));
+                                                                                 order, lw, xlocal, b.rmax2, work, h->g));
     return GMS_OK;
 }
 
@@ -1051,10 +1070,16 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
                                        h->parents, P, h->slot[h->slot_cur], h->slot[nxt], h->dup_src, h->dup_dst,
                                        h->dup_rect, h->rect, h->scratch2p, h->st, h->g));
         h->slot_cur = nxt;
-        const int chunks = std::max(1, std::min(32, h->H / 16));
-        LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps<<<(unsigned)((long long)chunks * P), 256, 0, h->stream>>>(
-                                       h->counts, h->dup_src, h->dup_dst, h->dup_rect, h->st, h->cells, h->W, chunks,
-                                       nullptr, h->peers, nullptr, 0));
+        if (h->copy_bulk && ((h->cells | (size_t)h->W) & 1) == 0) {  // TMA engine: rows start 16-byte aligned
+            const int chunks = std::max(1, std::min(h->copy_chunks, h->H / 16));
+            LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps_bulk<<<(unsigned)((long long)chunks * P), 32, kCpStages * kCpSeg, h->stream>>>(
+                                           h->counts, h->dup_src, h->dup_dst, h->dup_rect, h->st, h->cells, h->W, chunks));
+        } else {
+            const int chunks = std::max(1, std::min(32, h->H / 16));
+            LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps<<<(unsigned)((long long)chunks * P), 256, 0, h->stream>>>(
+                                           h->counts, h->dup_src, h->dup_dst, h->dup_rect, h->st, h->cells, h->W, chunks,
+                                           nullptr, h->peers, nullptr, 0));
+        }
     }
     // the virtual likelihood field follows the particles: a child inherits its parent's
     if (h->use_upd_pose) {  // ... and the pose its parent's last scan was integrated from
@@ -1100,8 +1125,13 @@ int step_end(gms_handle* h, int policy, double u01) {
         h->wpose_valid = a.pose_local != nullptr;
         h->tile_fx_sharded = sharded;
         if (sharded) h->blocks_stale = true;  // w / lw of the other ranks' blocks are not computed here
-        const unsigned grid = (unsigned)std::max(1, std::min(a.ntiles, h->num_sms * kNormCtasPerSm));
-        LAUNCH_COOP(GMS_PHASE_NORMALISE, k_norm_coop, grid, kNormThreads, 0, &a);
+        if (h->exact_sums) {  // GMS_SHARDED=1: exact, order-free sums (two grid barriers)
+            const unsigned grid = (unsigned)std::max(1, std::min(a.ntiles, h->num_sms * kNormCtasPerSm));
+            LAUNCH_COOP(GMS_PHASE_NORMALISE, k_norm_coop, grid, kNormThreads, 0, &a);
+        } else {              // fixed tiles, one grid barrier
+            const unsigned grid = (unsigned)std::max(1, std::min(a.ntiles, h->num_sms * 6));
+            LAUNCH_COOP(GMS_PHASE_NORMALISE, k_norm_tiles, grid, kNormThreads, 0, &a);
+        }
         h->tile_fx_valid = true;
     }
     const bool skip = std::fabs(h->pend_dtheta) > (M_PI / 180.0) * c.skip_update_deg;
@@ -1459,6 +1489,12 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaMalloc((void**)&h->sort.rank, (size_t)h->cnt * 4));
     CKC(cudaMalloc((void**)&h->sort.order, (size_t)h->cnt * 4));
     h->ntiles = (h->P + 1023) / 1024;
+    if (const char* e = std::getenv("GMS_SHARDED")) h->exact_sums = std::atoi(e) != 0;
+    if (const char* e = std::getenv("GMS_SCORE_DYNAMIC")) h->score_dynamic = std::atoi(e) != 0;
+    if (const char* e = std::getenv("GMS_COPY_BULK")) h->copy_bulk = std::atoi(e) != 0;
+    if (const char* e = std::getenv("GMS_COPY_CHUNKS")) h->copy_chunks = std::max(1, std::min(64, std::atoi(e)));
+    CKC(cudaFuncSetAttribute(k_copy_maps_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, kCpStages * kCpSeg));
+    CKC(cudaMalloc((void**)&h->score_work, 4));
     if (const char* e = std::getenv("GMS_DEFER_INTEGRATION")) h->defer_integration = std::atoi(e) != 0;
     if (const char* e = std::getenv("GMS_SCORE_V")) h->score_v = std::max(0, std::min(6, std::atoi(e)));
     if (const char* e = std::getenv("GMS_SCORE_G")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) h->score_g = v; }

@@ -918,7 +918,8 @@ __global__ void __launch_bounds__(128, (V == 3 || V == 4) ? 8 : 1) k_score_sorte
                                                       const int* __restrict__ num_hit, const double* __restrict__ fac,
                                                       const int* __restrict__ order, double* __restrict__ lw,
                                                       ExchangeRec* __restrict__ xlocal,
-                                                      const double* __restrict__ rmax2, Geometry g) {
+                                                      const double* __restrict__ rmax2, unsigned* __restrict__ work,
+                                                      Geometry g) {
     constexpr int K = (V == 3 || V == 5 || V == 6) ? 2 : (V == 4 ? 0 : V);  // which index-validation code
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -942,11 +943,19 @@ __global__ void __launch_bounds__(128, (V == 3 || V == 4) ? 8 : 1) k_score_sorte
                 : "memory");
         }
     }
-    const int t = (blockIdx.x * blockDim.x + tid) / G, gsub = (blockIdx.x * blockDim.x + tid) % G;
-    const int li = t < cnt ? (order ? order[t] : t) : -1;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (li >= 0) p = pose[lo + li];
-    const Xform x(p.x, p.y, p.z);
+    // Work item = one warp's worth of (particle, sub-thread) pairs.  `work` == null: one item per warp, the grid covers
+    // them all (small sets).  Otherwise the grid is exactly the resident CTAs and every warp draws items from the
+    // counter until none are left: at 100k particles the static grid was 1563 CTAs on 592 resident ones = 2.64 waves,
+    // i.e. a third wave 64 % full (12 % of the kernel's time idle); drawn items keep every warp busy to the end.
+    // Which warp scores a particle does not enter its result.
+    const int lane = tid & 31;
+    const int nitems = (int)(((long long)cnt * G + 31) / 32);
+    auto next_item = [&]() -> int {
+        unsigned v = 0;
+        if (lane == 0) v = atomicAdd(work, 1u);
+        return (int)__shfl_sync(0xffffffffu, v, 0);
+    };
+    int item = work ? next_item() : (int)(blockIdx.x * (blockDim.x >> 5) + (tid >> 5));
     if (nh > 0) {
         uint32_t done = 0;
         while (!done) {
@@ -957,6 +966,12 @@ __global__ void __launch_bounds__(128, (V == 3 || V == 4) ? 8 : 1) k_score_sorte
                 : "memory");
         }
     }
+  for (; item < nitems; item = work ? next_item() : nitems) {
+    const int t = (item * 32 + lane) / G, gsub = (item * 32 + lane) % G;
+    const int li = t < cnt ? (order ? order[t] : t) : -1;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (li >= 0) p = pose[lo + li];
+    const Xform x(p.x, p.y, p.z);
     const int nhe = li >= 0 ? nh : 0;  // idle sub-threads still take part in the shuffles below
     // Fast path for (int) ((world - position) / resolution), GridMap.java:273-274: q~ = the same quantity
     // evaluated with two FMAs from per-particle constants.  |q~ - q_java| < 1e-9 for every finite input
@@ -1143,6 +1158,7 @@ __global__ void __launch_bounds__(128, (V == 3 || V == 4) ? 8 : 1) k_score_sorte
             xlocal[li] = r;
         }
     }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1877,6 +1893,137 @@ __global__ void __launch_bounds__(kNormThreads, kNormCtasPerSm) k_norm_coop(Norm
     }
 }
 
+// The default normalise: the same step over FIXED tiles of 1024 consecutive particle indices with plain f64 sums —
+// each tile reduced by a fixed shuffle tree, tile results combined in tile order, S = sum_t s_t * exp(m_t - M) from
+// per-tile maxima — which needs ONE grid barrier instead of two (the exact sums above need M before the first
+// exponential).  Independent of the grid size, of which CTA handled a tile, of the scoring kernel's order and of the
+// rank count as long as every rank normalises the whole set (single rank, replicated peer exchange, all-gather):
+// the default.  17 us against 24 us at 100k particles.  k_norm_coop (exact, order-free sums) serves GMS_SHARDED=1.
+__global__ void __launch_bounds__(kNormThreads, 6) k_norm_tiles(NormArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    constexpr int NT = kNormThreads, NW = NT / 32;
+    __shared__ double s_key[NW];
+    __shared__ int s_idx[NW];
+    __shared__ double s_d[NW];
+    __shared__ double s_v[5 * NW];
+    __shared__ unsigned long long s_u[NW];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x, G = gridDim.x;
+    if (a.xflags) {
+        if (tid < a.nranks) {  // every CTA polls for itself: no extra grid barrier
+            unsigned long long v = 0;
+            long long spins = 0;
+            for (; spins < 8000000; spins++) {  // ~4 s with the sleeps: never hang the device
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.xflags + tid) : "memory");
+                if (v >= a.seq) break;
+                __nanosleep(200);
+            }
+            if (v < a.seq) a.st->xerror = 1;
+        }
+        __syncthreads();  // the acquiring threads' view is handed to the whole CTA
+    }
+    // phase 1: per fixed tile, (max, first arg-max, sum exp(lw - tile max))
+    for (int t = blockIdx.x; t < a.ntiles; t += G) {
+        const int i0 = t * 1024 + tid * 4;
+        double v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = i0 + j < a.P ? __ldcg(a.lw + i0 + j) : kNegInf;
+        if (a.lw_store)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (i0 + j < a.P) a.lw_store[i0 + j] = v[j];
+        double best = kNegInf;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (v[j] > best) { best = v[j]; bi = i0 + j; }  // ascending index: a later equal value never replaces
+        block_argmax_nt<NT>(best, bi, s_key, s_idx);
+        double e = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) e += i0 + j < a.P ? exp(v[j] - best) : 0.0;
+        const double sum = block_reduce_nt<NT>(e, SumOp(), s_d);
+        if (tid == 0) { a.np.m[t] = best; a.np.idx[t] = bi; a.np.s[t] = sum; }
+    }
+    __threadfence();
+    grid.sync();
+    if (*(volatile int*)&a.st->xerror) return;  // uniform: set (if at all) before the barrier
+    // every CTA combines the tile partials in the same fixed order -> (M, first arg-max, S)
+    double best = kNegInf;
+    int bi = 0x7fffffff;
+    for (int c = tid; c < a.ntiles; c += NT) {
+        const double v = __ldcg(a.np.m + c);
+        const int vi = __ldcg(a.np.idx + c);
+        if (v > best || (v == best && vi < bi)) { best = v; bi = vi; }
+    }
+    block_argmax_nt<NT>(best, bi, s_key, s_idx);
+    double acc = 0.0;
+    for (int c = tid; c < a.ntiles; c += NT) acc += __ldcg(a.np.s + c) * exp(__ldcg(a.np.m + c) - best);
+    const double S = block_reduce_nt<NT>(acc, SumOp(), s_d);
+    // phase 2: w_i = exp(lw_i - M) / S, tile sums of w, w^2, trunc(w * 2^60) (+ weighted pose terms)
+    for (int t = blockIdx.x; t < a.ntiles; t += G) {
+        const int i0 = t * 1024 + tid * 4;
+        double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // w, w^2, w*x, w*y, w*angleConstrain(theta)
+        unsigned long long fx = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = i0 + j;
+            if (i < a.P) {
+                const double wi = exp(__ldcg(a.lw + i) - best) / S;
+                a.w[i] = wi;
+                v[0] += wi; v[1] += wi * wi;
+                fx += (unsigned long long)(wi * 0x1p60);
+                if (a.pose_local) {  // SLAM.getWeightedPose SLAM.java:165-178
+                    const float4 p = a.pose_local[i];
+                    v[2] += (double)p.x * wi; v[3] += (double)p.y * wi; v[4] += angle_constrain((double)p.z) * wi;
+                }
+            }
+        }
+        block_sum_vec_nt<NT, 5>(v, s_v);
+        fx = block_reduce_nt<NT>(fx, SumU64(), s_u);
+        if (tid == 0) {
+            a.np.ws[t] = v[0]; a.np.q[t] = v[1]; a.np.fx[t] = fx;
+            if (a.pose_local) { a.wp_part[4 * t] = v[2]; a.wp_part[4 * t + 1] = v[3]; a.wp_part[4 * t + 2] = v[4]; }
+        }
+    }
+    // the last CTA to finish folds the tile sums (fixed order) and publishes the step's statistics
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(a.np.counter, 1u) == (unsigned)G - 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double f[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int c = tid; c < a.ntiles; c += NT) {
+        f[0] += __ldcg(a.np.ws + c);
+        f[1] += __ldcg(a.np.q + c);
+        if (a.pose_local) {
+            f[2] += __ldcg(a.wp_part + 4 * c); f[3] += __ldcg(a.wp_part + 4 * c + 1); f[4] += __ldcg(a.wp_part + 4 * c + 2);
+        }
+    }
+    block_sum_vec_nt<NT, 5>(f, s_v);
+    const double sa = f[0], sq = f[1];
+    if (tid == 0) {
+        Stats* st = a.st;
+        if (a.pose_local) {
+            st->weighted_pose[0] = (float)(f[2] / sa);
+            st->weighted_pose[1] = (float)(f[3] / sa);
+            st->weighted_pose[2] = (float)(f[4] / sa);
+        }
+        const double neff = (sa * sa) / sq;
+        st->neff = neff;
+        st->lw_max = best;
+        st->sum_exp = S;
+        st->strongest = bi;
+        st->strongest_now = bi;
+        st->strongest_w = 1.0 / S;
+        const float4 p = a.poses.at(bi);
+        st->strongest_pose[0] = p.x; st->strongest_pose[1] = p.y; st->strongest_pose[2] = p.z;
+        st->do_resample = a.policy == 2 || (a.policy == 1 && neff < (double)(a.P / 2));  // GridMapApp.java:185
+        *a.np.counter = 0u;
+    }
+}
+
 // SLAM.calculateNeff on the current weights (after set_weights / resample); also the fixed-point tile
 // sums k_cdf_fixed needs.  Same last-block pattern.
 __global__ void __launch_bounds__(1024) k_neff(const double* __restrict__ w, int P, int ntiles, NormPartials np,
@@ -2550,6 +2697,72 @@ __global__ void __launch_bounds__(256) k_copy_maps(CellCounts* __restrict__ coun
             for (int i = threadIdx.x; i < n; i += 256) cd[o + i] = cs[o + i];
         }
     }
+}
+
+// The same copy on the TMA engine (single rank, 16-byte aligned rows): ONE thread per CTA moves row segments of up
+// to kCpSeg bytes global -> shared (cp.async.bulk + mbarrier::complete_tx) -> global (cp.async.bulk.global.shared +
+// bulk groups) through a ring of kCpStages buffers, kCpLead loads ahead of the stores.  No per-element index
+// arithmetic, no registers holding data: the per-thread version above spends 52 % of its issue slots on addresses
+// (ncu r02j) and reaches 3.9 TB/s of writes.
+constexpr int kCpStages = 8, kCpLead = 6, kCpSeg = 4096;
+__global__ void __launch_bounds__(32) k_copy_maps_bulk(CellCounts* __restrict__ counts, const int* __restrict__ dup_src,
+                                                       const int* __restrict__ dup_dst,
+                                                       const int4* __restrict__ dup_rect,
+                                                       const Stats* __restrict__ st, size_t cells, int W,
+                                                       int chunks_per_map) {
+    extern __shared__ __align__(128) unsigned char s_ring[];  // kCpStages * kCpSeg
+    __shared__ __align__(8) uint64_t s_bar[kCpStages];
+    const int k = blockIdx.x / chunks_per_map;
+    if (k >= st->num_dup || threadIdx.x != 0) return;
+    const int chunk = blockIdx.x - k * chunks_per_map;
+    const int4 r = dup_rect[k];
+    if (r.x > r.z || r.y > r.w) return;
+    const int rows = r.w - r.y + 1;
+    const int per = (rows + chunks_per_map - 1) / chunks_per_map;
+    const int y0 = r.y + chunk * per, y1 = min(r.w + 1, y0 + per);
+    if (y0 >= y1) return;
+    const int x0 = r.x & ~1;
+    const unsigned rowbytes = (unsigned)(((r.z | 1) - x0 + 1) * (int)sizeof(CellCounts));
+    const int segs = (int)((rowbytes + kCpSeg - 1) / kCpSeg);
+    const int total = (y1 - y0) * segs;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(counts + (size_t)dup_src[k] * cells);
+    unsigned char* dst = reinterpret_cast<unsigned char*>(counts + (size_t)dup_dst[k] * cells);
+    for (int i = 0; i < kCpStages; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    auto seg_of = [&](int i, size_t& off, unsigned& bytes) {
+        const int yy = i / segs, sg = i - yy * segs;
+        off = ((size_t)(y0 + yy) * W + x0) * sizeof(CellCounts) + (size_t)sg * kCpSeg;
+        bytes = min((unsigned)kCpSeg, rowbytes - (unsigned)sg * kCpSeg);
+    };
+    for (int i = 0; i < total + kCpLead; i++) {
+        if (i < total) {
+            const int sgi = i % kCpStages;
+            // the store that last read this stage (iteration i - kCpStages) must have finished reading shared memory
+            if (i >= kCpStages) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kCpStages - 1 - kCpLead) : "memory");
+            size_t off; unsigned bytes;
+            seg_of(i, off, bytes);
+            const uint32_t bar = smem_u32(&s_bar[sgi]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(s_ring + sgi * kCpSeg)), "l"(src + off), "r"(bytes), "r"(bar) : "memory");
+        }
+        const int j = i - kCpLead;
+        if (j >= 0) {
+            const int sgj = j % kCpStages;
+            const uint32_t bar = smem_u32(&s_bar[sgj]), phase = (uint32_t)(j / kCpStages) & 1u;
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+            size_t off; unsigned bytes;
+            seg_of(j, off, bytes);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(dst + off), "r"(smem_u32(s_ring + sgj * kCpSeg)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // shared memory must outlive the last store's read
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -100,7 +100,9 @@ def _run(cuda, P, steps, beams, world, mode, peer=True, sharded=False):
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    os.environ["GMS_SHARDED"] = "1" if sharded else "0"  # the single-rank run uses the same (exact-sum) normalise
     h = cuda.create(**_cfg(P, mode))
+    os.environ.pop("GMS_SHARDED", None)
     scans = synth.make_scans(steps, beams, max_range=12.0)
     normals, uniforms = synth.make_draws(steps, P)
     single = _steps(h, None, scans, normals, uniforms, 0, P, torch.device("cuda", 0),
