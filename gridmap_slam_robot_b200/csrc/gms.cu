@@ -184,8 +184,9 @@ struct gms_handle {
                                 // (GMS_SCORE_DYNAMIC=1; measured no faster at 100k particles: 0.110 vs 0.108 ms)
     unsigned* score_work = nullptr;
     int score_g = 0;  // sub-threads per particle in k_score_sorted (0 = automatic; GMS_SCORE_G overrides: tuning knob)
-    int score_v = 2;  // variant of k_score_sorted (GMS_SCORE_V=0..6, identical cell indices; kernels.cuh / DESIGN.md §4.19):
-                      // 2 = folded magic constant + per-particle range guard + padded factor field (measured fastest)
+    int score_v = 7;  // variant of k_score_sorted (GMS_SCORE_V=0..7, identical cell indices; kernels.cuh / DESIGN.md §4.19):
+                      // 2 = folded magic constant + per-particle range guard + padded factor field; 7 = 2 with the index
+                      // validation amortised over the eight lookups of a batch (measured fastest: 0.102 vs 0.108 ms, K4)
     int num_sms = 148;
     int* ray_maxlen = nullptr;
     // GMS_UPDATE_SORTED scratch (allocated on first use)
@@ -618,7 +619,8 @@ int launch_score(gms_handle* h, const BeamSet& b, const float4* pose, int lo, in
         const unsigned grid = blocks_for((long long)cnt * G, 128);
 #define SCORE_G(GG)                                                                                            \
     case GG:                                                                                                   \
-        return h->score_v == 6   ? launch_score_sorted<GG, 6>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
+        return h->score_v == 7   ? launch_score_sorted<GG, 7>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
+               : h->score_v == 6 ? launch_score_sorted<GG, 6>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
                : h->score_v == 5 ? launch_score_sorted<GG, 5>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
                : h->score_v == 4 ? launch_score_sorted<GG, 4>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
                : h->score_v == 3 ? launch_score_sorted<GG, 3>(h, grid, smem, pose, lo, cnt, b, order, lw, xlocal) \
@@ -1496,7 +1498,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     CKC(cudaFuncSetAttribute(k_copy_maps_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, kCpStages * kCpSeg));
     CKC(cudaMalloc((void**)&h->score_work, 4));
     if (const char* e = std::getenv("GMS_DEFER_INTEGRATION")) h->defer_integration = std::atoi(e) != 0;
-    if (const char* e = std::getenv("GMS_SCORE_V")) h->score_v = std::max(0, std::min(6, std::atoi(e)));
+    if (const char* e = std::getenv("GMS_SCORE_V")) h->score_v = std::max(0, std::min(7, std::atoi(e)));
     if (const char* e = std::getenv("GMS_SCORE_G")) { const int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) h->score_g = v; }
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, h->dev) == cudaSuccess) h->num_sms = prop.multiProcessorCount; }
     {

@@ -920,7 +920,7 @@ __global__ void __launch_bounds__(128, (V == 3 || V == 4) ? 8 : 1) k_score_sorte
                                                       ExchangeRec* __restrict__ xlocal,
                                                       const double* __restrict__ rmax2, unsigned* __restrict__ work,
                                                       Geometry g) {
-    constexpr int K = (V == 3 || V == 5 || V == 6) ? 2 : (V == 4 ? 0 : V);  // which index-validation code
+    constexpr int K = (V == 3 || V == 5 || V == 6 || V == 7) ? 2 : (V == 4 ? 0 : V);  // which index-validation code
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
     double2* s_xy = reinterpret_cast<double2*>(smem_raw);
@@ -1072,6 +1072,45 @@ __global__ void __launch_bounds__(128, (V == 3 || V == 4) ? 8 : 1) k_score_sorte
                 for (int u = 0; u < NB; u++) f[u] = fn[u];
                 bad = badn;
             }
+        }
+    } else if constexpr (V == 7) {
+        // V = 2 with the validation amortised over the batch: instead of a compare / select / flag per lookup (the
+        // ALU pipe is this kernel's busiest: 43 % against 23 % FP64 and 13 % FMA, ncu r02), the eight lookups share
+        // one running unsigned minimum of the shifted fractions and one running OR of the fixed-point coordinates —
+        // a 3-input min and a 3-input LOP per lookup — and are judged once.  The index is masked into the padded
+        // square, so a coordinate outside it (judged afterwards) still loads from inside the array.  A batch that
+        // fails (probability ~2e-3: one of 16 coordinates within the margin of a cell border) is redone lookup by
+        // lookup with V = 2's test: same accepted set per lookup, same factors.
+        const unsigned idxmask = pitch * pitch - 1u;
+        for (; b0 + 8 * G <= nfast; b0 += 8 * G, it++) {
+            unsigned idx[8];
+            unsigned m8 = 0xffffffffu, o8 = 0u;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const double2 m = s_xy[b0 + u * G + gsub];
+                const double tx = fma(m.x, cinv, fma(-m.y, sinv, pqxm));
+                const double ty = fma(m.x, sinv, fma(m.y, cinv, pqym));
+                const unsigned ix = (unsigned)__double2loint(tx), iy = (unsigned)__double2loint(ty);
+                m8 = min(m8, min(ix * fmul + fadd, iy * fmul + fadd));
+                o8 |= ix | iy;
+                idx[u] = (__umulhi(iy, fmul) * pitch + __umulhi(ix, fmul)) & idxmask;
+            }
+            double f[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) f[u] = __ldg(fac + idx[u]);
+            if (!(m8 >= fthr && o8 < bound)) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const double2 m = s_xy[b0 + u * G + gsub];
+                    const double tx = fma(m.x, cinv, fma(-m.y, sinv, pqxm));
+                    const double ty = fma(m.x, sinv, fma(m.y, cinv, pqym));
+                    const unsigned ix = (unsigned)__double2loint(tx), iy = (unsigned)__double2loint(ty);
+                    const bool ok = min(ix * fmul + fadd, iy * fmul + fadd) >= fthr && (ix | iy) < bound;
+                    if (!ok) f[u] = factor_exact(m);
+                }
+            }
+            mant *= ((f[0] * f[1]) * (f[2] * f[3])) * ((f[4] * f[5]) * (f[6] * f[7]));
+            if ((it & 7) == 7) peel();
         }
     } else
     for (; b0 + 8 * G <= nfast; b0 += 8 * G, it++) {
