@@ -179,7 +179,7 @@ struct gms_handle {
     double partial_u01 = 0;
     unsigned long long partial_count = 0;
     bool copy_bulk = true;      // single-rank map copies on the TMA engine (GMS_COPY_BULK=0: per-thread 16-byte copies)
-    int copy_chunks = 8;        // CTAs per copied map (GMS_COPY_CHUNKS)
+    int copy_chunks = 16;       // CTAs per copied map (GMS_COPY_CHUNKS; 4 / 8 / 16 / 32 -> 0.239 / 0.231 / 0.226 / 0.240 ms, K2pp)
     bool score_dynamic = false;  // k_score_sorted draws its work items from a counter when they exceed the resident warps
                                 // (GMS_SCORE_DYNAMIC=1; measured no faster at 100k particles: 0.110 vs 0.108 ms)
     unsigned* score_work = nullptr;
@@ -1061,9 +1061,17 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
             LAUNCH(GMS_PHASE_MAP_COPY, k_job_rects<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(
                                            h->dup_src_rank, h->dup_src, h->dup_dst, h->dup_level, level, h->dup_rect,
                                            h->rect, h->st, h->peers, h->g));
-            LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps<<<(unsigned)((long long)chunks * h->cnt), 256, 0, h->stream>>>(
-                                           h->counts, h->dup_src, h->dup_dst, h->dup_rect, h->st, h->cells, h->W, chunks,
-                                           h->dup_src_rank, h->peers, h->dup_level, level));
+            const bool bulk = h->copy_bulk && ((h->cells | (size_t)h->W) & 1) == 0;
+            if (level == 0 || !bulk)  // pulls over NVLink (level 0), and every copy without the TMA path
+                LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps<<<(unsigned)((long long)chunks * h->cnt), 256, 0, h->stream>>>(
+                                               h->counts, h->dup_src, h->dup_dst, h->dup_rect, h->st, h->cells, h->W, chunks,
+                                               h->dup_src_rank, h->peers, h->dup_level, level, bulk ? h->cfg.rank : -1));
+            if (bulk) {  // copies whose source map is on this rank: TMA engine
+                const int bchunks = std::max(1, std::min(h->copy_chunks, h->H / 16));
+                LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps_bulk<<<(unsigned)((long long)bchunks * h->cnt), 32, kCpStages * kCpSeg, h->stream>>>(
+                                               h->counts, h->dup_src, h->dup_dst, h->dup_rect, h->st, h->cells, h->W, bchunks,
+                                               h->dup_src_rank, h->cfg.rank, h->dup_level, level));
+            }
         }
     } else {
         Phase ph(h, GMS_PHASE_MAP_COPY);
@@ -1075,12 +1083,13 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
         if (h->copy_bulk && ((h->cells | (size_t)h->W) & 1) == 0) {  // TMA engine: rows start 16-byte aligned
             const int chunks = std::max(1, std::min(h->copy_chunks, h->H / 16));
             LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps_bulk<<<(unsigned)((long long)chunks * P), 32, kCpStages * kCpSeg, h->stream>>>(
-                                           h->counts, h->dup_src, h->dup_dst, h->dup_rect, h->st, h->cells, h->W, chunks));
+                                           h->counts, h->dup_src, h->dup_dst, h->dup_rect, h->st, h->cells, h->W, chunks,
+                                           nullptr, 0, nullptr, 0));
         } else {
             const int chunks = std::max(1, std::min(32, h->H / 16));
             LAUNCH(GMS_PHASE_MAP_COPY, k_copy_maps<<<(unsigned)((long long)chunks * P), 256, 0, h->stream>>>(
                                            h->counts, h->dup_src, h->dup_dst, h->dup_rect, h->st, h->cells, h->W, chunks,
-                                           nullptr, h->peers, nullptr, 0));
+                                           nullptr, h->peers, nullptr, 0, -1));
         }
     }
     // the virtual likelihood field follows the particles: a child inherits its parent's

@@ -2696,10 +2696,13 @@ __global__ void __launch_bounds__(256) k_copy_maps(CellCounts* __restrict__ coun
                                                    const int* __restrict__ dup_dst, const int4* __restrict__ dup_rect,
                                                    const Stats* __restrict__ st, size_t cells, int W,
                                                    int chunks_per_map, const int* __restrict__ dup_src_rank,
-                                                   PeerTable peers, const int* __restrict__ job_level, int level) {
+                                                   PeerTable peers, const int* __restrict__ job_level, int level,
+                                                   int skip_rank /* jobs whose source is this rank are left to
+                                                                    k_copy_maps_bulk; -1: none */) {
     const int k = blockIdx.x / chunks_per_map;
     if (k >= st->num_dup) return;
     if (job_level && job_level[k] != level) return;
+    if (dup_src_rank && dup_src_rank[k] == skip_rank) return;
     const int chunk = blockIdx.x - k * chunks_per_map;
     const int src = dup_src[k], dst = dup_dst[k];
     const CellCounts* src_counts = dup_src_rank ? peers.counts[dup_src_rank[k]] : counts;
@@ -2738,7 +2741,7 @@ __global__ void __launch_bounds__(256) k_copy_maps(CellCounts* __restrict__ coun
     }
 }
 
-// The same copy on the TMA engine (single rank, 16-byte aligned rows): ONE thread per CTA moves row segments of up
+// The same copy on the TMA engine (source on this rank, 16-byte aligned rows): ONE thread per CTA moves row segments of up
 // to kCpSeg bytes global -> shared (cp.async.bulk + mbarrier::complete_tx) -> global (cp.async.bulk.global.shared +
 // bulk groups) through a ring of kCpStages buffers, kCpLead loads ahead of the stores.  No per-element index
 // arithmetic, no registers holding data: the per-thread version above spends 52 % of its issue slots on addresses
@@ -2748,11 +2751,14 @@ __global__ void __launch_bounds__(32) k_copy_maps_bulk(CellCounts* __restrict__ 
                                                        const int* __restrict__ dup_dst,
                                                        const int4* __restrict__ dup_rect,
                                                        const Stats* __restrict__ st, size_t cells, int W,
-                                                       int chunks_per_map) {
+                                                       int chunks_per_map, const int* __restrict__ dup_src_rank,
+                                                       int myrank, const int* __restrict__ job_level, int level) {
     extern __shared__ __align__(128) unsigned char s_ring[];  // kCpStages * kCpSeg
     __shared__ __align__(8) uint64_t s_bar[kCpStages];
     const int k = blockIdx.x / chunks_per_map;
     if (k >= st->num_dup || threadIdx.x != 0) return;
+    // multi-rank: only the jobs of this level whose source map lives on this rank (pulls stay with k_copy_maps)
+    if (job_level && (job_level[k] != level || dup_src_rank[k] != myrank)) return;
     const int chunk = blockIdx.x - k * chunks_per_map;
     const int4 r = dup_rect[k];
     if (r.x > r.z || r.y > r.w) return;
