@@ -289,17 +289,35 @@ __device__ __forceinline__ void apply_measurement_red(CellCounts* __restrict__ m
     int lx = it.x, ly = it.y;
     const unsigned long long inc_free = NEG ? ~0ull : 1ull;                      // pair - 1 (no borrow: n_free >= 1)
     const unsigned long long inc_occ = NEG ? (0ull - (1ull << 32)) : (1ull << 32);
+    // Four DDA steps, then their four classifications and reductions: the DDA's error term is the only serial
+    // dependence (RayIterator.java:112-130), so the square roots and the REDs of a group overlap with the next
+    // group's walk.  Matters when few rays are in flight (only the selected parents' maps take a scan: the kernel
+    // is then bound by this loop's latency, 74 us for ~10 maps before the unrolling).
     while (it.has_next(g.W, g.H)) {
-        lx = it.x;
-        ly = it.y;
-        const float dX = sx - ((float)lx + 0.5f);
-        const float dY = sy - ((float)ly + 0.5f);
-        const float dist = __fsqrt_rn(dX * dX + dY * dY);
-        const int cls = inverse_sensor_class(dist, meas, was_hit, g.tol_half);
-        if (cls != 0)
-            atomicAdd(reinterpret_cast<unsigned long long*>(map + ((size_t)lx + (size_t)ly * g.W)),
-                      cls == 1 ? inc_free : inc_occ);
-        it.advance();
+        int cx[4], cy[4];
+        bool live[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            live[j] = it.has_next(g.W, g.H);
+            cx[j] = it.x;
+            cy[j] = it.y;
+            if (live[j]) {
+                lx = it.x;
+                ly = it.y;
+                it.advance();
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (!live[j]) continue;
+            const float dX = sx - ((float)cx[j] + 0.5f);
+            const float dY = sy - ((float)cy[j] + 0.5f);
+            const float dist = __fsqrt_rn(dX * dX + dY * dY);  // (float) Math.sqrt((double) f32) == sqrt.rn.f32
+            const int cls = inverse_sensor_class(dist, meas, was_hit, g.tol_half);
+            if (cls != 0)
+                atomicAdd(reinterpret_cast<unsigned long long*>(map + ((size_t)cx[j] + (size_t)cy[j] * g.W)),
+                          cls == 1 ? inc_free : inc_occ);
+        }
     }
     box.x0 = min(box.x0, lx); box.x1 = max(box.x1, lx);
     box.y0 = min(box.y0, ly); box.y1 = max(box.y1, ly);

@@ -805,15 +805,15 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
     bool packed = false;
     {
         Phase ph(h, GMS_PHASE_MOTION);
+        PackArgs pk{(const double2*)d_xy, d_dist, d_hit, B, h->g.res_f, bs.hit_xy, bs.meas, bs.xy, bs.hit, bs.num_hit, bs.rmax2};
+        int do_pack = hook ? 0 : 1;
         if (sorted) {  // motion + heading sort + beam packing: one cooperative launch
-            PackArgs pk{(const double2*)d_xy, d_dist, d_hit, B, h->g.res_f, bs.hit_xy, bs.meas, bs.xy, bs.hit, bs.num_hit, bs.rmax2};
-            int do_pack = hook ? 0 : 1;
             const unsigned grid = std::min<unsigned>(blocks_for(h->cnt, 1024), (unsigned)h->num_sms);
             LAUNCH_COOP(GMS_PHASE_MOTION, k_motion_sort, grid, 1024, 0, &ma, &h->sort, &pk, &do_pack);
-            packed = do_pack != 0;
-        } else {
-            LAUNCH(GMS_PHASE_MOTION, k_motion<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(ma));
+        } else {       // motion + beam packing
+            LAUNCH(GMS_PHASE_MOTION, k_motion<<<blocks_for(h->cnt, 256), 256, 0, h->stream>>>(ma, pk, do_pack));
         }
+        packed = do_pack != 0;
     }
     if (!shared) {
         // computeLikelihoodMap of every particle (SLAM.java:93): the field is virtual, so this is bookkeeping only —

@@ -223,9 +223,26 @@ __device__ __forceinline__ float4 motion_one(const MotionArgs& a, int li) {
     a.pose[i] = p;
     return p;
 }
-__global__ void __launch_bounds__(256) k_motion(MotionArgs a) {
+struct PackArgs {
+    const double2* in_xy;
+    const double* in_dist;
+    const uint8_t* in_hit;
+    int B;
+    float res_f;
+    double2* hit_xy;
+    float* meas;
+    double2* all_xy;
+    uint8_t* all_hit;
+    int* num_hit;
+    double* rmax2;
+};
+// motion of every local particle; with `do_pack` the last CTA of the grid also packs the beam table (one launch less
+// on the per-particle path, where nothing else shares the launch)
+__global__ void __launch_bounds__(256) k_motion(MotionArgs a, PackArgs pk, int do_pack) {
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li < a.cnt) motion_one(a, li);
+    if (do_pack && blockIdx.x == gridDim.x - 1)
+        pack_beams_cta(pk.in_xy, pk.in_dist, pk.in_hit, pk.B, pk.res_f, pk.hit_xy, pk.meas, pk.all_xy, pk.all_hit, pk.num_hit, pk.rmax2);
 }
 
 // Motion + heading sort + beam packing in ONE cooperative launch (shared map, many particles).  The sort only
@@ -239,19 +256,6 @@ __global__ void __launch_bounds__(256) k_motion(MotionArgs a) {
 struct SortBufs {
     unsigned *hist, *offs, *chunk_total, *key, *rank;
     int* order;
-};
-struct PackArgs {
-    const double2* in_xy;
-    const double* in_dist;
-    const uint8_t* in_hit;
-    int B;
-    float res_f;
-    double2* hit_xy;
-    float* meas;
-    double2* all_xy;
-    uint8_t* all_hit;
-    int* num_hit;
-    double* rmax2;
 };
 __global__ void __launch_bounds__(1024) k_motion_sort(MotionArgs a, SortBufs sb, PackArgs pk, int do_pack) {
     cg::grid_group grid = cg::this_grid();
