@@ -108,7 +108,7 @@ struct gms_handle {
     bool defer_integration = true;     // GMS_DEFER_INTEGRATION=0: integrate inside every update (round-1 order)
     int field_bset = 0;                // beam-table set a FIELD_BEFORE_LAST field refers to
     int integ_B = 0, integ_pose_buf = 0, integ_slot_buf = 0, integ_bset = 0;
-    int* used = nullptr;               // P flags: particle was selected as a parent by the last resampling
+    int* used = nullptr;               // [0] = n, [1..n] = local particles the last resampling selected as parents
     unsigned long long mapseq = 0;     // per-particle maps across ranks: sequence number of k_maps_final
     float4* upd_pose[2] = {nullptr, nullptr};  // poses the last scan was integrated from, once gms_set_poses has
     bool use_upd_pose = false;                 // replaced the live ones (otherwise those are still pose[cur])
@@ -705,13 +705,17 @@ int launch_shared_update(gms_handle* h, const BeamSet& b, int B) {
 
 // per-particle maps (or one explicit {pose, slot} pair): one thread per (particle, beam) ray
 int launch_map_update(gms_handle* h, const BeamSet& b, const float4* pose, int lo, int cnt, const int* slot, int B,
-                      const int* used = nullptr) {
+                      const int* ulist = nullptr, const int* n_used = nullptr) {
     if (B <= 0) return GMS_OK;
     Phase ph(h, GMS_PHASE_MAP_UPDATE);
     const long long total = (long long)cnt * B;
-    if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE)  // no dirty-tile bookkeeping: fire-and-forget reductions
-        LAUNCH(GMS_PHASE_MAP_UPDATE, k_map_update_red<false><<<blocks_for(total, 128), 128, 0, h->stream>>>(
-                                         pose, lo, cnt, b.xy, b.meas, b.hit, B, h->counts, slot, h->rect, used, h->st, h->g));
+    if (h->cfg.map_mode == GMS_MAP_PER_PARTICLE) {  // no dirty-tile bookkeeping: fire-and-forget reductions
+        // a listed launch may spread its rays 8 to a warp (kSparseRays): cover that mapping too
+        const long long threads = ulist ? std::max<long long>(total, std::min<long long>(total, kSparseRays) * 4) : total;
+        LAUNCH(GMS_PHASE_MAP_UPDATE, k_map_update_red<false><<<blocks_for(threads, 128), 128, 0, h->stream>>>(
+                                         pose, lo, cnt, b.xy, b.meas, b.hit, B, h->counts, slot, h->rect, ulist, n_used,
+                                         h->st, h->g));
+    }
     else
         LAUNCH(GMS_PHASE_MAP_UPDATE, k_map_update<<<blocks_for(total, 128), 128, 0, h->stream>>>(
                                          pose, lo, cnt, b.xy, b.meas, b.hit, B, h->counts, slot, h->rect, h->dirty, h->g));
@@ -719,18 +723,18 @@ int launch_map_update(gms_handle* h, const BeamSet& b, const float4* pose, int l
 }
 
 // the pending integration of the last update: every local particle, or (`used`) only the parents a resampling selected
-int integrate_pending(gms_handle* h, const int* used) {
+int integrate_pending(gms_handle* h, const int* ulist, const int* n_used) {
     if (!h->integ_pending) return GMS_OK;
     h->integ_pending = false;
     int rc = launch_map_update(h, h->bs[h->integ_bset], h->pose[h->integ_pose_buf], h->lo, h->cnt,
-                               h->slot[h->integ_slot_buf] + h->lo, h->integ_B, used);
+                               h->slot[h->integ_slot_buf] + h->lo, h->integ_B, ulist, n_used);
     if (rc) return rc;
     h->field_state = gms_handle::FIELD_BEFORE_LAST;  // likelihoodData now lags the counters by this scan
     h->field_B = h->integ_B;
     h->field_bset = h->integ_bset;
     return GMS_OK;
 }
-int flush_integration(gms_handle* h) { return integrate_pending(h, nullptr); }
+int flush_integration(gms_handle* h) { return integrate_pending(h, nullptr, nullptr); }
 
 // A4 — GridMap.findBestPoseOptim GridMap.java:348-369 as a CPU hook between motion and scoring: the local
 // particles' poses go to the host, the callback may replace them, they come back.  Default: no hook (the
@@ -1035,10 +1039,11 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
     if (h->cfg.nranks > 1 && !h->peers_ready)
         return fail(h, GMS_ERR_STATE, "per-particle maps across ranks: call gms_ipc_import before resampling");
     if (h->integ_pending) {  // the scan goes into the maps of the selected parents only: the others are dropped
-        if (!h->used) CK(cudaMalloc((void**)&h->used, (size_t)P * 4));
-        CK(cudaMemsetAsync(h->used, 0, (size_t)P * 4, h->stream));
-        LAUNCH(GMS_PHASE_MAP_UPDATE, k_mark_used<<<blocks_for(P, 256), 256, 0, h->stream>>>(h->parents, P, h->used));
-        int rc_ = integrate_pending(h, h->used);
+        if (!h->used) CK(cudaMalloc((void**)&h->used, (size_t)(h->cnt + 1) * 4));  // [0]: length, [1..]: the list
+        CK(cudaMemsetAsync(h->used, 0, 4, h->stream));
+        LAUNCH(GMS_PHASE_MAP_UPDATE, k_list_parents<<<blocks_for(P, 256), 256, 0, h->stream>>>(h->parents, P, h->lo, h->cnt,
+                                                                                            h->used + 1, h->used));
+        int rc_ = integrate_pending(h, h->used + 1, h->used);
         if (rc_) return rc_;
     }
     if (h->cfg.nranks > 1) {
@@ -1208,7 +1213,7 @@ int field_of(gms_handle* h, int particle, int s, const double** out) {
         const float4* poses = h->use_upd_pose ? h->upd_pose[0] : h->pose[h->cur];
         LAUNCH(GMS_PHASE_COUNT - 1, k_map_update_red<true><<<blocks_for(h->field_B, 128), 128, 0, h->stream>>>(
                                         poses, particle, 1, b.xy, b.meas, b.hit, h->field_B, h->fld_counts, h->tmp_slot,
-                                        nullptr, nullptr, h->st, h->g));
+                                        nullptr, nullptr, nullptr, h->st, h->g));
         map = h->fld_counts;
     }
     return launch_blur_whole(h, map, h->lik, h->dirty, h->word_off, h->tile_list);

@@ -1179,8 +1179,22 @@ __global__ void __launch_bounds__(128, (V == 3 || V == 4) ? 8 : 1) k_score_sorte
         mant *= ((f[0] * f[1]) * (f[2] * f[3])) * ((f[4] * f[5]) * (f[6] * f[7]));
         if ((it & 7) == 7) peel();  // factors are in [0.01, 0.91]: 64 of them cannot underflow a normalised mantissa
     }
+    // beams left over after the last full batch (none at G = 2 with 720 beams; 208 of 720 at G = 32, i.e. one warp
+    // per particle, K3): the same fast path one lookup at a time — round 2's first half sent them through the exact
+    // division and K3's scoring took 45 us for 7.2 M lookups
     for (int b = b0 + gsub, j = 0; b < nhe; b += G, j++) {
-        mant *= factor_exact(s_xy[b]);
+        const double2 m = s_xy[b];
+        double f;
+        if (K == 2 && b < nfast) {
+            const double tx = fma(m.x, cinv, fma(-m.y, sinv, pqxm));
+            const double ty = fma(m.x, sinv, fma(m.y, cinv, pqym));
+            const unsigned ix = (unsigned)__double2loint(tx), iy = (unsigned)__double2loint(ty);
+            const bool ok = min(ix * fmul + fadd, iy * fmul + fadd) >= fthr && (ix | iy) < bound;
+            f = ok ? __ldg(fac + (__umulhi(iy, fmul) * pitch + __umulhi(ix, fmul))) : factor_exact(m);
+        } else {
+            f = factor_exact(m);
+        }
+        mant *= f;
         if ((j & 31) == 31) peel();
     }
     peel();
@@ -1240,23 +1254,37 @@ __global__ void __launch_bounds__(128) k_map_update(const float4* __restrict__ p
 
 // The same without dirty-tile bookkeeping (fire-and-forget RED): the step's kernel for per-particle maps now that
 // their likelihood field is evaluated on demand.  NEG: subtract (see apply_measurement_red); `rect` may be null.
-// `used` (nullable, indexed by the global particle index): integrate only the particles flagged there — when a
-// resampling follows the update, a particle without children is dropped together with its map
-// (SLAM.java:133-153 builds the new list from copies of the selected particles), so integrating the scan into
-// it is dead work; the resampling marks the parents it selected (k_mark_used) and only those are integrated.
+// `ulist` / `n_used` (nullable): integrate only the listed local particles — when a resampling follows the update,
+// a particle without children is dropped together with its map (SLAM.java:133-153 builds the new list from copies
+// of the selected particles), so integrating the scan into it is dead work; the resampling lists the parents it
+// selected (k_list_parents) and only those are integrated.  A short list (a handful of parents is the usual
+// outcome) leaves the machine almost empty and the kernel bound by the latency of the ray loop, whose REDs
+// serialise over the distinct sectors of a warp's lanes: such launches put 8 rays instead of 32 into a warp.
+constexpr int kSparseRays = 65536;  // up to this many rays: 8 per warp
 template <bool NEG>
 __global__ void __launch_bounds__(128) k_map_update_red(const float4* __restrict__ pose, int lo, int cnt,
                                                         const double2* __restrict__ all_xy,
                                                         const float* __restrict__ meas,
                                                         const uint8_t* __restrict__ hit, int B,
                                                         CellCounts* __restrict__ counts, const int* __restrict__ slot,
-                                                        int4* __restrict__ rect, const int* __restrict__ used,
+                                                        int4* __restrict__ rect, const int* __restrict__ ulist,
+                                                        const int* __restrict__ n_used,
                                                         const Stats* __restrict__ st, Geometry g) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)cnt * B) return;
-    const int li = (int)(gid / B);
-    const int b = (int)(gid - (long long)li * B);
-    if (used && (st->xerror || !used[lo + li])) return;
+    long long r = gid;
+    long long nrays = (long long)cnt * B;
+    if (ulist) {
+        if (st->xerror) return;
+        nrays = (long long)(*n_used) * B;
+        if (nrays <= kSparseRays) {
+            if ((threadIdx.x & 31) >= 8) return;
+            r = (gid >> 5) * 8 + (threadIdx.x & 31);
+        }
+    }
+    if (r >= nrays) return;
+    int li = (int)(r / B);
+    const int b = (int)(r - (long long)li * B);
+    if (ulist) li = ulist[li];
     const int s = slot[li];
     const float4 p = pose[lo + li];
     const Xform t(p.x, p.y, p.z);
@@ -2937,10 +2965,17 @@ __global__ void k_pose_fill_remote(PoseTable poses, float4* __restrict__ local, 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P && (i < lo || i >= lo + cnt)) local[i] = poses.at(i);
 }
-// parents selected by the last resampling (every rank holds the whole parents[] of a per-particle-map resampling)
-__global__ void k_mark_used(const int* __restrict__ parents, int P, int* __restrict__ used) {
+// The parents the last resampling selected, as a list of LOCAL particle indices (every rank holds the whole
+// parents[] of a per-particle-map resampling; a parent counts if any rank's child descends from it).  parents[] is
+// non-decreasing (systematic resampling, SLAM.java:139-150; the identity when the step did not resample), so a
+// parent's first child is where the value changes: each parent is listed exactly once, in no particular order
+// (the integration adds integers).
+__global__ void k_list_parents(const int* __restrict__ parents, int P, int lo, int cnt, int* __restrict__ ulist,
+                               int* __restrict__ n_used) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m < P) used[parents[m]] = 1;  // benign race: all writers store 1
+    if (m >= P) return;
+    const int p = parents[m];
+    if ((m == 0 || parents[m - 1] != p) && p >= lo && p < lo + cnt) ulist[atomicAdd(n_used, 1)] = p - lo;
 }
 // Per-particle maps across ranks: the maps a resampling copies are final only once their owners have integrated
 // the scan into them (deferred until the parents are known, see k_map_update_red).  One CTA: raise my flag on every
