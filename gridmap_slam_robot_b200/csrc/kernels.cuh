@@ -851,8 +851,7 @@ __device__ __forceinline__ double field_at(const CellCounts* __restrict__ cmap, 
 // particle count, so log-weights are bit-identical run to run and for every rank count.  Four warps per particle
 // because a lookup is a burst of 28 independent 16-byte loads followed by ~110 f64 operations: with one warp per
 // particle 1000 particles left the SMs 12 % occupied and the kernel latency-bound (ncu, r02j: 126 us).
-constexpr int kPpWarps = 4;
-template <int KH>
+template <int KH, int kPpWarps>
 __global__ void __launch_bounds__(kPpWarps * 32) k_score_pp(const float4* __restrict__ pose, int lo, int cnt,
                                                            const double2* __restrict__ hit_xy,
                                                            const int* __restrict__ num_hit,
@@ -2195,8 +2194,8 @@ __global__ void __launch_bounds__(256) k_import_exchange(const ExchangeRec* __re
 // LITERAL CDF: Java's sequential f64 running sum, c_i = c_{i-1} + w_i in particle order.  One warp:
 // coalesced 32-wide loads, the dependent add chain is replayed through shuffles.
 __global__ void __launch_bounds__(32) k_cdf_literal(const double* __restrict__ w, int P, double* __restrict__ cdf,
-                                                    Stats* __restrict__ st) {
-    if (!st->do_resample || st->xerror) return;
+                                                    Stats* __restrict__ st, int force) {
+    if (!(force || st->do_resample) || st->xerror) return;
     const int lane = threadIdx.x;
     if (lane == 0) st->strongest_now = -1;
     double c = 0.0;  // 0.0 + w[0] == w[0]: same as Java's c = particles.get(0).weight (SLAM.java:137)
@@ -2231,6 +2230,7 @@ struct SelectArgs {
     double* w_out;
     double* lw_out;
     int m_begin, m_count;  // children [m_begin, m_begin + m_count)
+    int force;             // SLAM.resample() called explicitly: resample whatever the step's policy decided
     double* wp_part;       // k_resample_coop selecting ALL children: SLAM.getWeightedPose of the new generation comes
     unsigned* wp_counter;  // out of the same kernel (tile partials + last-CTA ticket); nullptr otherwise
 };
@@ -2283,7 +2283,7 @@ __global__ void __launch_bounds__(256) k_select(SelectArgs a) {
     __shared__ unsigned long long s_coarse[2048];
     const int m0 = a.m_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (a.st->xerror) return;
-    const bool resample = a.st->do_resample != 0;  // uniform over the grid
+    const bool resample = a.force || a.st->do_resample != 0;  // uniform over the grid
     const int stride = select_stride(a.P), ncoarse = (a.P + stride - 1) / stride;
     if (resample) {
         const unsigned long long* raw = static_cast<const unsigned long long*>(a.cdf);  // 8-byte keys either way
@@ -2320,7 +2320,7 @@ __global__ void __launch_bounds__(kNormThreads, kNormCtasPerSm) k_resample_coop(
     __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, G = gridDim.x;
     if (a.st->xerror) return;        // uniform over the grid
-    if (!a.st->do_resample) {        // uniform over the grid: the generation is carried over unchanged
+    if (!(a.force || a.st->do_resample)) {  // uniform over the grid: the generation is carried over unchanged
         for (int m0 = a.m_begin + blockIdx.x * NT + tid; m0 < a.m_begin + a.m_count; m0 += G * NT) {
             a.parents[m0] = m0;
             a.pose_out[m0] = a.poses_in.at(m0);
@@ -2420,7 +2420,7 @@ __global__ void __launch_bounds__(kNormThreads, kNormCtasPerSm) k_resample_shard
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, G = gridDim.x;
     Stats* st = a.st;
     if (st->xerror) return;        // uniform over the grid
-    if (!st->do_resample) {        // uniform over the grid (and over the ranks): the generation is carried over unchanged
+    if (!(a.force || st->do_resample)) {  // uniform over the grid (and over the ranks): the generation is carried over unchanged
         for (int m0 = lo + blockIdx.x * NT + tid; m0 < lo + cnt; m0 += G * NT) {
             a.parents[m0] = m0;
             a.pose_out[m0] = a.poses_in.at(m0);
