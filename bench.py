@@ -136,13 +136,19 @@ def make_scans(wl, n):
 
 
 def config_of(name, wl, P_total, world, W=None, H=None, hits=None, update_mode="atomic"):
-    """The `config` object: identical for the GPU arm and the reference arm of one (workload, N, scaling)."""
+    """The `config` object: identical (as a dict) for the GPU arm and the reference arm of one (workload, N, scaling)."""
     cells = int(round(wl["grid_m"] / 0.05))
+    ring = make_scans(wl, SCAN_RING)
     return {"workload": f"{name}: {wl['desc']}", "particles_total": P_total, "particles_per_gpu": P_total // world,
             "beams": wl["B"], "grid": f"{W or cells}x{H or cells}", "map_mode": wl["mode"],
             "resample": "every step (GMS_RESAMPLE_ALWAYS)", "motion_noise": "device Philox",
             "map_update": update_mode, "scan_ring": SCAN_RING,
-            "parallelism": f"particles sharded over {world} rank(s)"}
+            "parallelism": f"particles sharded over {world} rank(s)",
+            "beams_scored": float(np.mean([s.num_hits for s in ring])),
+            "l2": "GPU arm: flushed between timed steps (256 MiB memset, untimed), see back_to_back for the unflushed "
+                  "figure; reference arm: host caches left as they are",
+            "timed_window": "GPU arm: per step a CUDA event pair, closed after the library's side streams have been "
+                            "joined; reference arm: wall clock around update + resample + weighted pose of each step"}
 
 
 def score_bytes(P, B, s=8):
@@ -598,10 +604,7 @@ def run_gpu(args, wl):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["t_dev"] / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": dict(config_of(args.workload, wl, P_total, world, r["W"], r["H"], update_mode=args.update_mode),
-                       beams_scored=r["hits"],
-                       l2="flushed between timed steps (256 MiB memset, untimed); see back_to_back for the unflushed figure",
-                       timed_window="per step: event, step, join of the library's side streams, event"),
+        "config": config_of(args.workload, wl, P_total, world, r["W"], r["H"], update_mode=args.update_mode),
         "back_to_back": {"ms_per_step": 1e3 * r["t_b2b"] / args.steps, "value": r["scored_b2b"] / r["t_b2b"],
                          "note": "same steps, no L2 flush, no gaps: one event pair around all of them"},
         "ms_per_step_wall": 1e3 * r["t_wall"] / args.steps,
