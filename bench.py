@@ -264,6 +264,43 @@ def cpu_model():
     return "unknown"
 
 
+def native_e2e(lib_path, wl, P_total, scans, steps, warm=5):
+    """The same end-to-end step from a compiled host: csrc/e2e_host (C++) drives gms_update + gms_resample +
+    gms_get_strongest + gms_get_weighted_pose through the C-ABI with host beam arrays — what the Java shim's FFM
+    downcalls cost, without the Python interpreter between the calls.  Runs after this process has released its
+    handle; returns None if the helper is not built."""
+    import struct
+    import subprocess
+    import tempfile
+
+    from gridmap_slam_robot_b200 import build as b
+
+    try:
+        exe = b.build_e2e_host()
+    except Exception:
+        return None
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+        f.write(struct.pack("<ii", len(scans), wl["B"]))
+        for sc in scans:
+            f.write(struct.pack("<dd", sc.d_center, sc.d_theta))
+            f.write(np.ascontiguousarray(sc.beam_xy, np.float64).tobytes())
+            f.write(np.ascontiguousarray(sc.beam_dist, np.float64).tobytes())
+            f.write(np.ascontiguousarray(sc.beam_hit, np.uint8).tobytes())
+        path = f.name
+    try:
+        out = subprocess.run([exe, lib_path, path, str(P_total), str(wl["grid_m"]), "1" if wl["mode"] == "shared" else "0",
+                              str(steps), str(warm)], capture_output=True, text=True, timeout=300)
+        if out.returncode != 0:
+            return {"error": (out.stderr or out.stdout)[-300:]}
+        r = json.loads(out.stdout.strip().splitlines()[-1])
+    finally:
+        os.unlink(path)
+    return {"value": r["value"], "unit": "scores/s", "ms_per_step": r["ms_per_step"], "steps": r["steps"],
+            "h2d_bytes_per_step": wl["B"] * 25, "d2h_bytes_per_step": 208,
+            "host": "compiled C++ loop over the C-ABI (gridmap_slam_robot_b200/csrc/e2e_host.cpp): gms_update + "
+                    "gms_resample + gms_get_strongest + gms_get_weighted_pose, host beam arrays"}
+
+
 def kernel_counters(workload):
     """ncu counters of the workload's dominant kernel (profiles/kernel_counters.json, written from this round's
     `ncu --set full` capture): DRAM bytes and executed warp instructions per launch."""
@@ -397,10 +434,12 @@ def time_workload(ctx, name, wl, P_total, steps, warmup, e2e_steps):
     if e2e_steps and world == 1:
         h.set_stream(None)
 
+        host = [(xy.numpy(), d.numpy(), hh.numpy()) for xy, d, hh in pinned]  # the caller's arrays (pinned memory)
+
         def e2e_step(i):
             k = i % nscan
-            xy, d, hh = pinned[k]
-            h.update(xy.numpy(), d.numpy(), hh.numpy(), scans[k].d_center, scans[k].d_theta, None)
+            xy, d, hh = host[k]
+            h.update(xy, d, hh, scans[k].d_center, scans[k].d_theta, None)
             h.resample(-1.0)
             h.strongest()
             return h.weighted_pose()
@@ -616,6 +655,10 @@ def run_gpu(args, wl):
     }
     if r["e2e"]:
         line["e2e"] = r["e2e"]
+    if world == 1 and r["e2e"]:
+        ne = native_e2e(lib.path, wl, P_total, r["scans"], max(3, min(args.steps, 200)))
+        if ne:
+            line["e2e_native"] = ne
     if r.get("t_never") is not None:
         line["no_resample"] = no_resample_of(r)
     if parity:

@@ -118,11 +118,13 @@ def _ptr(a):
         return None
     if isinstance(a, int):
         return a
-    return a.ctypes.data
+    return a.__array_interface__["data"][0]  # the address, without building a ctypes helper object (a.ctypes)
 
 
 def _arr(a, dtype, n=None):
-    a = np.ascontiguousarray(a, dtype=dtype)
+    # the common case costs nothing: an ndarray of the right dtype that is already C-contiguous is passed through
+    if not (type(a) is np.ndarray and a.dtype == dtype and a.flags.c_contiguous):
+        a = np.ascontiguousarray(a, dtype=dtype)
     if n is not None and a.size != n:
         raise ValueError(f"expected {n} elements, got {a.size}")
     return a

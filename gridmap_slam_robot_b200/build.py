@@ -45,6 +45,16 @@ def build_libgms(force=False, verbose=False):
     return out
 
 
+def build_e2e_host(force=False):
+    """The compiled host loop over the C-ABI that bench.py times as `e2e_native` (plain g++: it only dlopens the library)."""
+    out = os.path.join(CSRC, "e2e_host")
+    src = os.path.join(CSRC, "e2e_host.cpp")
+    if force or _newer(out, [src, os.path.join(ROOT, "include", "gms.h")]):
+        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+        subprocess.check_call([gxx, "-std=c++17", "-O2", "-o", out, src, "-ldl"])
+    return out
+
+
 def build_oracle(force=False):
     odir = os.path.join(ROOT, "oracle")
     out = os.path.join(odir, "libgms_ref.so")
@@ -57,4 +67,5 @@ def build_oracle(force=False):
 if __name__ == "__main__":
     force = "--force" in sys.argv
     print(build_libgms(force=force, verbose="-v" in sys.argv))
+    print(build_e2e_host(force=force))
     print(build_oracle(force=force))

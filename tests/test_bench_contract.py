@@ -27,3 +27,16 @@ def test_other_ranks_of_the_reference_arm_stay_silent():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_native_e2e_helper_runs_over_the_c_abi(oracle):
+    """csrc/e2e_host.cpp (bench.py's `e2e_native`) is a plain C-ABI client: exercised here against the oracle library,
+    which exports the same entry points (the GPU box runs it against libgms.so)."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    wl = dict(bench.WORKLOADS["K2"])
+    scans = bench.make_scans(wl, 3)
+    r = bench.native_e2e(oracle.path, wl, 64, scans, 2, warm=1)
+    assert r and "error" not in r, r
+    assert r["steps"] == 2 and r["ms_per_step"] > 0 and r["value"] > 0 and r["h2d_bytes_per_step"] == 25 * wl["B"]
