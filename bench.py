@@ -19,7 +19,9 @@ One JSON line on stdout (rank 0):
   back_to_back the same steps enqueued without flushes or gaps, one event pair around all of them (steady state:
                the likelihood refresh of step t+1 overlaps the tail of step t, as in production)
   e2e          the same step through the host-buffer C-ABI calls the Java shim would make
-               (GridMapApp.java:178-192), H2D/D2H inside the timed region
+               (GridMapApp.java:178-192), H2D/D2H inside the timed region, driven from Python (ctypes binding)
+  e2e_native   the same calls from a compiled host loop (csrc/e2e_host.cpp, a plain C-ABI client): what the boundary
+               costs without an interpreter between the calls
   parity_check (N > 1) rank-count invariance, checked before anything is timed: a seeded replay on N ranks equals
                the same replay on one rank (parents, pose bytes, weights, every map); the run aborts on a mismatch
   extra        (default workload only) short timed runs of BASELINE config 4 as written (100k particles in total,
