@@ -554,7 +554,17 @@ def roofline_of(r, args):
     # measured in the no-resample regime, where every particle's map takes the scan (with a resampling only the
     # selected parents' maps do, and the step is dominated by the streaming map copies instead)
     upd_ms = (r.get("phase_never") or r["phase_ms"])["map_update"] / max(1, steps)
+    copy = None
+    if kc.get("copy") and r["phase_ms"].get("map_copy"):
+        # the resampling regime is dominated by the streaming map copies: DRAM bytes of the launch (ncu: the child
+        # maps written once; the parents' reads hit L2) / the event-timed copy phase of this run
+        cp_ms = r["phase_ms"]["map_copy"] / max(1, steps)
+        cb = kc["copy"]["dram_bytes_per_launch"]
+        copy = {"kernel": kc["copy"]["kernel"], "bound": "hbm", "achieved": cb / (cp_ms * 1e-3) / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": cb / (cp_ms * 1e-3) / 1e9 / peak, "traffic": cb,
+                "traffic_source": kc["copy"]["source"], "launch_ms": cp_ms, "regime": "resampling every step"}
     return {"kernel": "k_map_update_red", "bound": kc.get("bound", "l2_atomic"), "achieved": ub / (upd_ms * 1e-3) / 1e9,
+            "copy": copy,
             "peak": peak, "unit": "GB/s", "frac": ub / (upd_ms * 1e-3) / 1e9 / peak,
             "traffic": kc.get("dram_bytes_per_launch"), "traffic_source": kc.get("source"), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": ub, "launch_ms": upd_ms,
