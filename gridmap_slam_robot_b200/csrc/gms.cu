@@ -1072,7 +1072,7 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
         }
         Phase ph(h, GMS_PHASE_MAP_COPY);
         const int nxt = h->slot_cur ^ 1;
-        LAUNCH(GMS_PHASE_MAP_COPY, k_assign_slots_mr<<<1, 1024, 0, h->stream>>>(
+        LAUNCH(GMS_PHASE_MAP_COPY, k_assign_slots_mr<<<h->cfg.nranks, 1024, 0, h->stream>>>(
                                        h->parents, P, h->cnt, h->cfg.nranks, h->S, h->cfg.rank, h->slot[h->slot_cur],
                                        h->slot[nxt], h->dup_src_rank, h->dup_src, h->dup_dst, h->dup_level, h->scratch2p,
                                        h->st));

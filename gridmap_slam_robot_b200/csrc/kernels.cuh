@@ -2648,11 +2648,14 @@ __global__ void __launch_bounds__(1024) k_assign_slots_mr(const int* __restrict_
     const int tid = threadIdx.x;
     int* occ = scratch;
     int* freelist = scratch + R * S;
-    for (int i = tid; i < R * S; i += 1024) occ[i] = 0;
-    __syncthreads();
-    for (int p = tid; p < P; p += 1024) occ[(p / cnt) * S + gslot_in[p]] = 1;
-    __syncthreads();
-    for (int q = 0; q < R; q++) {
+    // one CTA per rank q: the ranks' tables are independent of each other (a single CTA walking all R ranks cost
+    // ~40 us of the 8-GPU resampling)
+    {
+        const int q = blockIdx.x;
+        for (int i = tid; i < S; i += 1024) occ[q * S + i] = 0;
+        __syncthreads();
+        for (int p = q * cnt + tid; p < (q + 1) * cnt; p += 1024) occ[q * S + gslot_in[p]] = 1;
+        __syncthreads();
         const int per_s = (S + 1023) / 1024;
         const int s0 = min(S, tid * per_s), s1 = min(S, s0 + per_s);
         int nf = 0;
