@@ -65,9 +65,85 @@ __device__ __forceinline__ double angle_constrain(double a) {
     return a;
 }
 
+// ---- sin / cos as a FIXED sequence of IEEE f64 operations ------------------------------------------------------
+// MathUtil.sin/cos delegate to FastMath (commons-math3 3.6.1, not in the reference tree); FastMath, libm and
+// CUDA's sin/cos are all accurate to about an ulp and all different in the last bit now and then.  So that the
+// CUDA path and the oracle cannot differ — not even with probability 2^-29 per f32-rounded use, and not in the f64
+// de-skew where an ulp can move an end point across a cell border — both evaluate the classic published scheme
+// (Sun's fdlibm 5.3: e_rem_pio2.c medium-size reduction by Cody-Waite with a 33+33+53-bit pi/2, k_sin.c / k_cos.c
+// minimax polynomials on [-pi/4, pi/4]; < 1 ulp) with the operations in the order written here: +, -, *, rint and
+// integer tests only, no fused multiply-add (--fmad=false), so every step is correctly rounded and identical on
+// any IEEE machine.  Arguments beyond 2^20 * pi/2 (never an angle on this path) and non-finite ones go to CUDA's
+// sin / cos.  The oracle restates the same scheme in C (oracle/gms_ref.c), oracle/pyref.py a third time in Python.
+namespace trig {
+constexpr double S1 = -0x1.5555555555549p-3, S2 = 0x1.111111110f8a6p-7, S3 = -0x1.a01a019c161d5p-13,
+                 S4 = 0x1.71de357b1fe7dp-19, S5 = -0x1.ae5e68a2b9cebp-26, S6 = 0x1.5d93a5acfd57cp-33;
+constexpr double C1 = 0x1.555555555554cp-5, C2 = -0x1.6c16c16c15177p-10, C3 = 0x1.a01a019cb1590p-16,
+                 C4 = -0x1.27e4f809c52adp-22, C5 = 0x1.1ee9ebdb4b1c4p-29, C6 = -0x1.8fae9be8838d4p-37;
+constexpr double kInvPio2 = 0x1.45f306dc9c883p-1;  // 53 bits of 2/pi
+constexpr double kPio2_1 = 0x1.921fb54400000p+0, kPio2_1t = 0x1.0b4611a626331p-34;  // first 33 bits of pi/2, rest
+constexpr double kPio2_2 = 0x1.0b4611a600000p-34, kPio2_2t = 0x1.3198a2e037073p-69;  // second 33 bits, rest
+constexpr double kPio2_3 = 0x1.3198a2e000000p-69, kPio2_3t = 0x1.b839a252049c1p-104;  // third 33 bits, rest
+constexpr double kPio4 = 0x1.921fb54442d18p-1;
+constexpr double kMedium = 1647099.0;  // < 2^20 * pi/2: fn * kPio2_1 is exact below it
+
+__device__ __forceinline__ double kernel_sin(double x, double y) {  // |x| <= pi/4, y: tail of x
+    const double z = x * x, v = z * x;
+    const double r = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
+    return x - ((z * (0.5 * y - v * r) - y) - v * S1);
+}
+__device__ __forceinline__ double kernel_cos(double x, double y) {
+    const double z = x * x;
+    double w = z * z;
+    const double r = z * (C1 + z * (C2 + z * C3)) + (w * w) * (C4 + z * (C5 + z * C6));
+    const double hz = 0.5 * z;
+    w = 1.0 - hz;
+    return w + (((1.0 - w) - hz) + (z * r - x * y));
+}
+__device__ __forceinline__ int biased_exponent(double x) { return (__double2hiint(x) >> 20) & 0x7ff; }
+// x = n * pi/2 + (y0 + y1), |y0 + y1| <= pi/4 (+ an ulp); returns n
+__device__ __forceinline__ int rem_pio2(double x, double& y0, double& y1) {
+    if (fabs(x) <= kPio4) { y0 = x; y1 = 0.0; return 0; }
+    const double fn = rint(x * kInvPio2);
+    double r = x - fn * kPio2_1, w = fn * kPio2_1t;  // good to 85 bits
+    y0 = r - w;
+    const int ex = biased_exponent(x);
+    if (ex - biased_exponent(y0) > 16) {  // cancellation: x is close to a multiple of pi/2 — second round, 118 bits
+        double t = r;
+        w = fn * kPio2_2;
+        r = t - w;
+        w = fn * kPio2_2t - ((t - r) - w);
+        y0 = r - w;
+        if (ex - biased_exponent(y0) > 49) {  // third round, 151 bits: covers every f64 below kMedium
+            t = r;
+            w = fn * kPio2_3;
+            r = t - w;
+            w = fn * kPio2_3t - ((t - r) - w);
+            y0 = r - w;
+        }
+    }
+    y1 = (r - y0) - w;
+    return (int)fn;
+}
+}  // namespace trig
+__device__ __forceinline__ double sin_fixed(double x) {
+    if (!(fabs(x) < trig::kMedium)) return sin(x);
+    double a, b;
+    const int n = trig::rem_pio2(x, a, b) & 3;
+    const double v = (n & 1) ? trig::kernel_cos(a, b) : trig::kernel_sin(a, b);
+    return (n & 2) ? -v : v;
+}
+__device__ __forceinline__ double cos_fixed(double x) {
+    if (!(fabs(x) < trig::kMedium)) return cos(x);
+    double a, b;
+    const int n = trig::rem_pio2(x, a, b) & 3;
+    const double v = (n & 1) ? trig::kernel_sin(a, b) : trig::kernel_cos(a, b);
+    return ((n + 1) & 2) ? -v : v;
+}
+
 // MathUtil.cos(float) / sin(float) MathUtil.java:30-40: (float) FastMath.cos((double) radians).
-__device__ __forceinline__ float cos_f(float r) { return (float)cos((double)r); }
-__device__ __forceinline__ float sin_f(float r) { return (float)sin((double)r); }
+__device__ __forceinline__ float cos_f(float r) { return (float)cos_fixed((double)r); }
+__device__ __forceinline__ float sin_f(float r) { return (float)sin_fixed((double)r); }
 
 // Transform.fromRobotToWorld Transform.java:13-32: cos/sin rounded to f32, then widened.
 struct Xform {
@@ -101,8 +177,8 @@ __device__ __forceinline__ void philox_normals(uint64_t seed, uint32_t gidx, uin
     double u1 = u53(c[0], c[1], true), u2 = u53(c[2], c[3], false);
     double r = sqrt(-2.0 * log(u1));
     double a = 6.283185307179586 * u2;
-    zd = r * cos(a);
-    zt = r * sin(a);
+    zd = r * cos_fixed(a);
+    zt = r * sin_fixed(a);
 }
 __device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t n) {
     uint32_t c[4] = {(uint32_t)n, (uint32_t)(n >> 32), 0u, 1u};

@@ -1033,7 +1033,7 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
             LAUNCH_COOP(GMS_PHASE_RESAMPLE, k_resample_coop, grid, kNormThreads, 0, &a, &fx, &ntiles);
         } else {
             h->wpose_valid = false;
-            LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_literal<<<1, 32, 0, h->stream>>>(h->w[h->cur], P, (double*)h->cdf, h->st,
+            LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_literal<<<1, 256, 0, h->stream>>>(h->w[h->cur], P, (double*)h->cdf, h->st,
                                                                               h->force_resample ? 1 : 0));
             int rc = launch_select(h, h->cur, nxt, u01, h->resample_count, m_begin, m_count);
             if (rc) return rc;

@@ -2193,24 +2193,48 @@ __global__ void __launch_bounds__(256) k_import_exchange(const ExchangeRec* __re
 // ------------------------------------------------------------------------------------------------
 // A7 — SLAM.resample SLAM.java:133-153.
 // ------------------------------------------------------------------------------------------------
-// LITERAL CDF: Java's sequential f64 running sum, c_i = c_{i-1} + w_i in particle order.  One warp:
-// coalesced 32-wide loads, the dependent add chain is replayed through shuffles.
-__global__ void __launch_bounds__(32) k_cdf_literal(const double* __restrict__ w, int P, double* __restrict__ cdf,
-                                                    Stats* __restrict__ st, int force) {
+// LITERAL CDF: Java's sequential f64 running sum, c_i = c_{i-1} + w_i in particle order.  The rounding after
+// every addition makes the chain inherently serial, so the kernel only keeps everything else off it: 256 threads
+// stage a chunk of weights in shared memory (all loads in flight at once: one DRAM latency instead of one per 32
+// values), ONE thread replays the dependent additions over shared memory, sixteen operands loaded ahead of their
+// additions, and all threads store the chunk coalesced.  (Round 2's first version, one warp replaying the chain
+// through shuffles with a global load every 32 values, took 24 us for 1000 particles.)
+constexpr int kCdfChunk = 2048;
+__global__ void __launch_bounds__(256) k_cdf_literal(const double* __restrict__ w, int P, double* __restrict__ cdf,
+                                                     Stats* __restrict__ st, int force) {
     if (!(force || st->do_resample) || st->xerror) return;
-    const int lane = threadIdx.x;
-    if (lane == 0) st->strongest_now = -1;
+    __shared__ double s_w[kCdfChunk];
+    const int tid = threadIdx.x;
+    if (tid == 0) st->strongest_now = -1;
     double c = 0.0;  // 0.0 + w[0] == w[0]: same as Java's c = particles.get(0).weight (SLAM.java:137)
-    for (int base = 0; base < P; base += 32) {
-        const double v = base + lane < P ? w[base + lane] : 0.0;
-        double mine = 0.0;
+    for (int base = 0; base < P; base += kCdfChunk) {
+        const int n = min(kCdfChunk, P - base);
+        double v[kCdfChunk / 256];
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-            const double wj = __shfl_sync(0xffffffffu, v, j);
-            c = c + wj;
-            if (lane == j) mine = c;
+        for (int j = 0; j < kCdfChunk / 256; j++) v[j] = tid + j * 256 < n ? w[base + tid + j * 256] : 0.0;
+#pragma unroll
+        for (int j = 0; j < kCdfChunk / 256; j++) s_w[tid + j * 256] = v[j];
+        __syncthreads();
+        if (tid == 0) {
+            int i = 0;
+            for (; i + 16 <= n; i += 16) {
+                double x[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) x[j] = s_w[i + j];
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    c = c + x[j];
+                    s_w[i + j] = c;
+                }
+            }
+            for (; i < n; i++) {
+                c = c + s_w[i];
+                s_w[i] = c;
+            }
         }
-        if (base + lane < P) cdf[base + lane] = mine;
+        __syncthreads();
+        for (int i = tid; i < n; i += 256) cdf[base + i] = s_w[i];
+        __syncthreads();
     }
 }
 
@@ -2851,8 +2875,8 @@ __global__ void __launch_bounds__(32) k_copy_maps_bulk(CellCounts* __restrict__ 
 // rows adjacent to the path
 // ------------------------------------------------------------------------------------------------
 // GridMapApp.onHandleData GridMapApp.java:140-175 + Measurement(double x, double y, boolean, int)
-// Observation.java:69-76.  MathUtil.cos/sin(double) = FastMath (commons-math3) -> CUDA cos/sin: f64
-// results agree to ~1 ulp, not bit for bit.
+// Observation.java:69-76.  MathUtil.cos/sin(double) = FastMath (commons-math3) -> cos_fixed / sin_fixed
+// (device_math.cuh): the same operation sequence as the oracle's, so the de-skewed beams are bit-identical.
 __global__ void __launch_bounds__(256) k_deskew(const double* __restrict__ angle, const double* __restrict__ dist,
                                                 int n, double d_center, double d_theta, double2* __restrict__ out_xy,
                                                 double* __restrict__ out_dist) {
@@ -2862,8 +2886,8 @@ __global__ void __launch_bounds__(256) k_deskew(const double* __restrict__ angle
     const double delta_theta = d_theta * d_i;
     const double delta_x = d_center * d_i;
     const double a = angle[i] + delta_theta;
-    const double x_a = dist[i] * cos(a) + delta_x;
-    const double y_a = dist[i] * sin(a);
+    const double x_a = dist[i] * cos_fixed(a) + delta_x;
+    const double y_a = dist[i] * sin_fixed(a);
     out_xy[i] = make_double2(x_a, y_a);
     out_dist[i] = sqrt(x_a * x_a + y_a * y_a);
 }

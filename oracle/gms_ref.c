@@ -15,7 +15,7 @@
  * float op double -> double, compound assignment narrows, (int) truncates toward zero and saturates.
  *
  * Third-party arithmetic not in the reference tree (commons-math3 3.6.1, build.gradle:59):
- * FastMath.sin/cos -> libm sin/cos here (results are rounded to f32 at every hot-path use);
+ * FastMath.sin/cos -> sin_fixed / cos_fixed below (a published < 1 ulp scheme as a fixed operation sequence);
  * NormalDistribution.sample() = sd * nextGaussian() + mean -> the standard normal draws are INPUTS
  * (injected) or come from the Philox generator below; BOBYQAOptimizer with an objective that is
  * identically zero (Odometry.java:99-103) -> identity on the start pose (GridMap.java:348-369).
@@ -118,9 +118,93 @@ static double angle_constrain(double a) {
     while (a > M_PI) a -= M_PI * 2;
     return a;
 }
+/* MathUtil.sin / cos (MathUtil.java:30-48) delegate to FastMath.sin / cos of commons-math3, which is not in the
+ * reference tree.  FastMath, glibc and CUDA are each accurate to about an ulp and disagree in the last bit now
+ * and then, so the oracle does not call libm here: it evaluates the classic published scheme — Sun's fdlibm 5.3,
+ * e_rem_pio2.c (medium arguments: Cody-Waite reduction by pi/2 held as 33 + 33 + 53 bits, up to three rounds),
+ * k_sin.c and k_cos.c (minimax polynomials on [-pi/4, pi/4]), error < 1 ulp — written out as a fixed sequence of
+ * IEEE operations (no contraction: -ffp-contract=off), which any implementation can reproduce bit for bit; the
+ * CUDA library does (device_math.cuh), oracle/pyref.py restates it a third time.  |x| >= 2^20 * pi/2 (never an
+ * angle on this path) and non-finite arguments go to libm.  tests/test_trig.py holds it within 1 ulp of an
+ * exact (mpmath) sine / cosine. */
+static const double TS1 = -0x1.5555555555549p-3, TS2 = 0x1.111111110f8a6p-7, TS3 = -0x1.a01a019c161d5p-13,
+                    TS4 = 0x1.71de357b1fe7dp-19, TS5 = -0x1.ae5e68a2b9cebp-26, TS6 = 0x1.5d93a5acfd57cp-33;
+static const double TC1 = 0x1.555555555554cp-5, TC2 = -0x1.6c16c16c15177p-10, TC3 = 0x1.a01a019cb1590p-16,
+                    TC4 = -0x1.27e4f809c52adp-22, TC5 = 0x1.1ee9ebdb4b1c4p-29, TC6 = -0x1.8fae9be8838d4p-37;
+static double poly_sin(double x, double tail) { /* k_sin.c, the form that takes the tail of the argument */
+    double z = x * x;
+    double v = z * x;
+    double r = TS2 + z * (TS3 + z * (TS4 + z * (TS5 + z * TS6)));
+    return x - ((z * (0.5 * tail - v * r) - tail) - v * TS1);
+}
+static double poly_cos(double x, double tail) { /* k_cos.c */
+    double z = x * x;
+    double zz = z * z;
+    double r = z * (TC1 + z * (TC2 + z * TC3)) + (zz * zz) * (TC4 + z * (TC5 + z * TC6));
+    double hz = 0.5 * z;
+    double w = 1.0 - hz;
+    return w + (((1.0 - w) - hz) + (z * r - x * tail));
+}
+static int exponent_field(double x) {
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return (int)((u >> 52) & 0x7ff);
+}
+/* e_rem_pio2.c, medium case: quadrant count, reduced argument as head + tail */
+static int reduce_pio2(double x, double *head, double *tail) {
+    static const double inv = 0x1.45f306dc9c883p-1;
+    static const double p1 = 0x1.921fb54400000p+0, p1t = 0x1.0b4611a626331p-34;
+    static const double p2 = 0x1.0b4611a600000p-34, p2t = 0x1.3198a2e037073p-69;
+    static const double p3 = 0x1.3198a2e000000p-69, p3t = 0x1.b839a252049c1p-104;
+    if (fabs(x) <= 0x1.921fb54442d18p-1) { *head = x; *tail = 0.0; return 0; }
+    double fn = rint(x * inv); /* default rounding mode: to nearest, ties to even */
+    double r = x - fn * p1;
+    double w = fn * p1t;
+    double y = r - w;
+    int ex = exponent_field(x);
+    if (ex - exponent_field(y) > 16) {
+        double t = r;
+        w = fn * p2;
+        r = t - w;
+        w = fn * p2t - ((t - r) - w);
+        y = r - w;
+        if (ex - exponent_field(y) > 49) {
+            t = r;
+            w = fn * p3;
+            r = t - w;
+            w = fn * p3t - ((t - r) - w);
+            y = r - w;
+        }
+    }
+    *head = y;
+    *tail = (r - y) - w;
+    return (int)fn;
+}
+static double sin_fixed(double x) {
+    if (!(fabs(x) < 1647099.0)) return sin(x);
+    double a, b;
+    int q = reduce_pio2(x, &a, &b) & 3;
+    switch (q) {
+    case 0: return poly_sin(a, b);
+    case 1: return poly_cos(a, b);
+    case 2: return -poly_sin(a, b);
+    default: return -poly_cos(a, b);
+    }
+}
+static double cos_fixed(double x) {
+    if (!(fabs(x) < 1647099.0)) return cos(x);
+    double a, b;
+    int q = reduce_pio2(x, &a, &b) & 3;
+    switch (q) {
+    case 0: return poly_cos(a, b);
+    case 1: return -poly_sin(a, b);
+    case 2: return -poly_cos(a, b);
+    default: return poly_sin(a, b);
+    }
+}
 /* MathUtil.cos(float)/sin(float) MathUtil.java:30-40: (float) FastMath.cos((double) radians). */
-static inline float cos_f(float r) { return (float)cos((double)r); }
-static inline float sin_f(float r) { return (float)sin((double)r); }
+static inline float cos_f(float r) { return (float)cos_fixed((double)r); }
+static inline float sin_f(float r) { return (float)sin_fixed((double)r); }
 
 /* Util.logOdds(double) Util.java:35-37: Math.log(odds / (1.0f - odds)). */
 static double log_odds(double p) { return log(p / (1.0 - p)); }
@@ -155,8 +239,8 @@ static void philox_normals(uint64_t seed, uint32_t gidx, uint64_t step, double *
     double u1 = u53(c[0], c[1], 1), u2 = u53(c[2], c[3], 0);
     double r = sqrt(-2.0 * log(u1));
     double a = 6.283185307179586 * u2;
-    *zd = r * cos(a);
-    *zt = r * sin(a);
+    *zd = r * cos_fixed(a);
+    *zt = r * sin_fixed(a);
 }
 /* stream 1: the resampling uniform of resample number n. */
 static double philox_uniform(uint64_t seed, uint64_t n) {
@@ -1109,8 +1193,8 @@ static void deskew(const double *angle, const double *dist, int n, double d_cent
         double d_i = -(n - i) / (double)n;
         double delta_theta = d_theta * d_i;
         double delta_x = d_center * d_i;
-        double x_a = dist[i] * cos(angle[i] + delta_theta) + delta_x;
-        double y_a = dist[i] * sin(angle[i] + delta_theta);
+        double x_a = dist[i] * cos_fixed(angle[i] + delta_theta) + delta_x;
+        double y_a = dist[i] * sin_fixed(angle[i] + delta_theta);
         xy[2 * i] = x_a; xy[2 * i + 1] = y_a;
         od[i] = sqrt(x_a * x_a + y_a * y_a);
     }

@@ -13,6 +13,7 @@ rounded with f32(), which equals the correctly rounded binary32 operation for + 
 References are to java/GridMapGL/src/main/java/com/fmsz/gridmapgl/.
 """
 import math
+import struct
 
 import numpy as np
 
@@ -43,12 +44,84 @@ def angle_constrain(a):  # MathUtil.java:65-72
     return a
 
 
+# FastMath.sin / cos (commons-math3, not in the reference tree) -> the published fdlibm 5.3 scheme (e_rem_pio2.c medium
+# reduction, k_sin.c, k_cos.c; < 1 ulp) as a fixed sequence of IEEE operations — the same sequence oracle/gms_ref.c and
+# the CUDA library evaluate, so all three agree bit for bit (Python floats are IEEE f64, no contraction).
+_H = float.fromhex
+_TS = [_H(v) for v in ("-0x1.5555555555549p-3", "0x1.111111110f8a6p-7", "-0x1.a01a019c161d5p-13",
+                       "0x1.71de357b1fe7dp-19", "-0x1.ae5e68a2b9cebp-26", "0x1.5d93a5acfd57cp-33")]
+_TC = [_H(v) for v in ("0x1.555555555554cp-5", "-0x1.6c16c16c15177p-10", "0x1.a01a019cb1590p-16",
+                       "-0x1.27e4f809c52adp-22", "0x1.1ee9ebdb4b1c4p-29", "-0x1.8fae9be8838d4p-37")]
+_INV_PIO2 = _H("0x1.45f306dc9c883p-1")
+_PIO2 = [(_H("0x1.921fb54400000p+0"), _H("0x1.0b4611a626331p-34")), (_H("0x1.0b4611a600000p-34"), _H("0x1.3198a2e037073p-69")),
+         (_H("0x1.3198a2e000000p-69"), _H("0x1.b839a252049c1p-104"))]
+_PIO4 = _H("0x1.921fb54442d18p-1")
+
+
+def _exponent_field(x):
+    return (struct.unpack("<Q", struct.pack("<d", x))[0] >> 52) & 0x7FF
+
+
+def _poly_sin(x, tail):
+    z = x * x
+    v = z * x
+    r = _TS[1] + z * (_TS[2] + z * (_TS[3] + z * (_TS[4] + z * _TS[5])))
+    return x - ((z * (0.5 * tail - v * r) - tail) - v * _TS[0])
+
+
+def _poly_cos(x, tail):
+    z = x * x
+    zz = z * z
+    r = z * (_TC[0] + z * (_TC[1] + z * _TC[2])) + (zz * zz) * (_TC[3] + z * (_TC[4] + z * _TC[5]))
+    hz = 0.5 * z
+    w = 1.0 - hz
+    return w + (((1.0 - w) - hz) + (z * r - x * tail))
+
+
+def _reduce_pio2(x):
+    if abs(x) <= _PIO4:
+        return 0, x, 0.0
+    n = round(x * _INV_PIO2)  # ties to even, like rint
+    fn = float(n)
+    r = x - fn * _PIO2[0][0]
+    w = fn * _PIO2[0][1]
+    y = r - w
+    ex = _exponent_field(x)
+    for (hi, lo), gap in ((_PIO2[1], 16), (_PIO2[2], 49)):
+        if ex - _exponent_field(y) <= gap:
+            break
+        t = r
+        w = fn * hi
+        r = t - w
+        w = fn * lo - ((t - r) - w)
+        y = r - w
+    return n, y, (r - y) - w
+
+
+def sin_fixed(x):
+    x = float(x)
+    if not abs(x) < 1647099.0:
+        return math.sin(x) if math.isfinite(x) else math.nan
+    n, a, b = _reduce_pio2(x)
+    q = n & 3
+    return (_poly_sin(a, b), _poly_cos(a, b), -_poly_sin(a, b), -_poly_cos(a, b))[q]
+
+
+def cos_fixed(x):
+    x = float(x)
+    if not abs(x) < 1647099.0:
+        return math.cos(x) if math.isfinite(x) else math.nan
+    n, a, b = _reduce_pio2(x)
+    q = n & 3
+    return (_poly_cos(a, b), -_poly_sin(a, b), -_poly_cos(a, b), _poly_sin(a, b))[q]
+
+
 def cos_f(theta_f):  # MathUtil.java:36-38 (float overload)
-    return f32(math.cos(theta_f))
+    return f32(cos_fixed(theta_f))
 
 
 def sin_f(theta_f):  # MathUtil.java:30-32
-    return f32(math.sin(theta_f))
+    return f32(sin_fixed(theta_f))
 
 
 def log_odds(p):  # Util.java:35-37

@@ -16,6 +16,7 @@ import numpy as np
 import appendix_b as AB
 from gridmap_slam_robot_b200 import binding as B
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 LW_TOL = 1e-9
 W_RTOL = 1e-9
@@ -319,22 +320,65 @@ def _raw_sweeps(steps, beams):
     return [(ang, sc.beam_dist, sc.beam_hit, sc.d_center, sc.d_theta) for sc in scans]
 
 
+def _pyref():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("pyref", os.path.join(ROOT, "oracle", "pyref.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def trig_probe_angles():
+    """Angles that exercise every branch of the fixed-sequence sin / cos: the no-reduction interval, all four
+    quadrants, one / two / three reduction rounds (arguments next to multiples of pi/2, incl. the f64 closest to
+    one), signed zeros, the edge of the medium range and what lies beyond it."""
+    rng = np.random.default_rng(2026)
+    k = np.arange(-64, 65, dtype=np.float64)
+    near = np.concatenate([np.nextafter(k * (np.pi / 2), np.inf), k * (np.pi / 2), np.nextafter(k * (np.pi / 2), -np.inf),
+                           k * (np.pi / 4)])
+    return np.concatenate([rng.uniform(-np.pi, np.pi, 4000), rng.uniform(-40.0, 40.0, 4000), rng.uniform(-1.6e6, 1.6e6, 2000),
+                           rng.uniform(-1e-6, 1e-6, 200), near,
+                           [0.0, -0.0, 5e-324, 1e-300, float.fromhex("0x1.921fb54442d18p-1"), -float.fromhex("0x1.921fb54442d18p-1"),
+                            float.fromhex("0x1.921fb54442d19p-1"), 355.0, 52174.0, 1146408.0,
+                            1647098.9999, -1647098.9999, 1647099.0, 1.0e7, -3.0e9]])
+
+
+def check_trig_probe(lib):
+    """sin / cos as the library evaluates them, read through gms_deskew (dist = 1, no motion: x = cos(a), y = sin(a)),
+    against oracle/pyref.py's restatement of the same operation sequence: bit for bit (beyond the medium range
+    every implementation defers to its libm: there a few ulp)."""
+    ref = _pyref()
+    a = trig_probe_angles()
+    h = lib.create(num_particles=1, map_width_m=0.5, map_height_m=0.5, map_mode=B.MAP_SHARED)
+    xy, od = h.deskew(a, np.ones_like(a), 0.0, 0.0)
+    h.close()
+    c = np.asarray([ref.cos_fixed(v) for v in a])
+    s = np.asarray([ref.sin_fixed(v) for v in a])
+    med = np.abs(a) < 1647099.0
+    assert np.array_equal(xy[med, 0].view(np.uint64), c[med].view(np.uint64)), "cos differs from the fixed sequence"
+    assert np.array_equal(xy[med, 1].view(np.uint64), s[med].view(np.uint64)), "sin differs from the fixed sequence"
+    np.testing.assert_allclose(xy[~med, 0], c[~med], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(xy[~med, 1], s[~med], rtol=0, atol=1e-15)
+    assert np.array_equal(od, np.sqrt(xy[:, 0] * xy[:, 0] + xy[:, 1] * xy[:, 1]))
+
+
 def check_deskew_reference_formula(lib):
-    """GridMapApp.java:140-175 restated with numpy (same libm): the oracle must match it bit for bit,
-    the CUDA path to a few ulp (FastMath / CUDA / libm sin and cos are not correctly rounded)."""
+    """GridMapApp.java:140-175 restated in Python with oracle/pyref.py's sin / cos (the fixed operation sequence all
+    three implementations share): oracle AND CUDA must match it bit for bit."""
+    ref = _pyref()
     h = lib.create(num_particles=1, map_width_m=0.5, map_height_m=0.5, map_mode=B.MAP_SHARED)
     rng = np.random.default_rng(11)
     n = 97
     ang, dist = rng.uniform(-np.pi, np.pi, n), rng.uniform(0.05, 11.0, n)
     dc, dth = 0.07, -0.21
     d_i = -(n - np.arange(n)) / float(n)
-    x = dist * np.cos(ang + dth * d_i) + dc * d_i
-    y = dist * np.sin(ang + dth * d_i)
+    a = ang + dth * d_i
+    x = dist * np.asarray([ref.cos_fixed(v) for v in a]) + dc * d_i
+    y = dist * np.asarray([ref.sin_fixed(v) for v in a])
     xy, od = h.deskew(ang, dist, dc, dth)
-    tol = 0 if not h.info.is_cuda else 8 * np.finfo(np.float64).eps * 11.0
-    np.testing.assert_allclose(xy[:, 0], x, rtol=0, atol=tol)
-    np.testing.assert_allclose(xy[:, 1], y, rtol=0, atol=tol)
-    np.testing.assert_allclose(od, np.sqrt(x * x + y * y), rtol=0, atol=tol)
+    assert np.array_equal(xy[:, 0], x) and np.array_equal(xy[:, 1], y)
+    assert np.array_equal(od, np.sqrt(x * x + y * y))
     h.close()
 
 
@@ -356,12 +400,12 @@ def check_next_rows(cuda, oracle):
             g.resample(float(uniforms[s]))
             o.resample(float(uniforms[s]))
             assert np.array_equal(g.parents(), o.parents())
-    # de-skewed beams differ by ulps between libm and CUDA, which can move an end point across a cell
-    # boundary: counts are compared as "almost all cells equal"
-    for p in (0, P - 1):
+    # the de-skewed beams are bit-identical (both libraries evaluate sin / cos as the same operation sequence), so
+    # the integer counters are too
+    for p in range(P):
         for kind in (B.MAP_FREE_COUNT, B.MAP_OCC_COUNT):
             a, b = g.get_map(p, kind), o.get_map(p, kind)
-            assert np.mean(a != b) < 1e-4, (p, kind, np.sum(a != b))
+            assert np.array_equal(a, b), (p, kind, np.sum(a != b))
     # renderer hand-off: packed ABGR gray words
     for lik in (False, True):
         a, b = g.render_map(0, lik), o.render_map(0, lik)
