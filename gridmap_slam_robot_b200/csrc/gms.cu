@@ -147,6 +147,7 @@ struct gms_handle {
     bool exact_sums = false;     // GMS_SHARDED=1 (any handle): the normalise with exact 128-bit sums, so that a sharded
                                  // multi-rank run and a single-rank run agree bit for bit
     bool sharded_post = false;   // enabled by gms_ipc_import for shared maps (GMS_SHARDED=0 keeps the replicated path)
+    bool xpull = true;           // replicated peer exchange as a pull inside k_norm_tiles (XPull); GMS_PULL=0: k_xpush_lw
     bool tile_fx_sharded = false;  // np.fx holds the tile sums of the local block only
     bool blocks_stale = false;   // pose / w / lw / parents hold only this rank's block: getters copy the rest from peers
     // beams: two step sets (the shared-map integration of step N may still read set N%2 on the side stream while
@@ -777,6 +778,11 @@ void clear_field_overrides(gms_handle* h) {
     h->field_ovr.clear();
 }
 
+// replicated peer exchange in its pull form: the fixed-tile normalise reads every rank's block from its owner
+bool pulling(const gms_handle* h) {
+    return h->cfg.nranks > 1 && h->direct && !h->sharded_post && h->xpull && !h->exact_sums;
+}
+
 int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const uint8_t* d_hit, int B, double d_center,
                double d_theta, const double* d_normals) {
     const gms_config& c = h->cfg;
@@ -848,7 +854,10 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
         if (rc) return rc;
     }
     if (fork) CK(cudaStreamWaitEvent(h->stream, h->ev_done_a, 0));
-    rc = launch_score(h, bs, h->pose[h->cur], h->lo, h->cnt, shared ? nullptr : h->slot[h->slot_cur] + h->lo, h->lw[h->cur],
+    // (pull exchange: the log-weights go straight into this rank's exchange buffer of the coming exchange; the
+    // normalise files every rank's values, this rank's included, in lw[cur])
+    rc = launch_score(h, bs, h->pose[h->cur], h->lo, h->cnt, shared ? nullptr : h->slot[h->slot_cur] + h->lo,
+                      pulling(h) ? h->xlw[(h->xseq + 1) & 1] : h->lw[h->cur],
                       (c.nranks > 1 && !h->direct) ? h->xlocal : nullptr, B, use_fac_score(h), shared ? h->lik : nullptr);
     if (rc) return rc;
 
@@ -859,7 +868,7 @@ int step_begin(gms_handle* h, const double* d_xy, const double* d_dist, const ui
         h->integ_B = B; h->integ_pose_buf = h->cur; h->integ_slot_buf = h->slot_cur; h->integ_bset = h->bset;
         if (!h->defer_integration && (rc = flush_integration(h))) return rc;
     }
-    if (c.nranks > 1 && h->direct && !h->sharded_post) {
+    if (c.nranks > 1 && h->direct && !h->sharded_post && !pulling(h)) {
         // this rank's log-weights -> every rank's receive buffer (NVLink stores), then one flag per receiver.  With
         // per-particle maps the flag also certifies that this rank's maps are final for the step (peers may pull
         // them when resampling), so the push is enqueued after the map integration.
@@ -1149,6 +1158,17 @@ int step_end(gms_handle* h, int policy, double u01) {
         a.w = h->w[h->cur]; a.poses = pose_table(h, h->cur); a.P = h->P; a.policy = policy;
         a.lo = sharded ? h->lo : 0; a.cnt = sharded ? h->cnt : h->P; a.ntiles = (a.cnt + 1023) / 1024;
         a.np = h->np; a.st = h->st; a.xflags = xflags; a.nranks = c.nranks; a.seq = h->xseq;
+        if (pulling(h)) {  // every block is read from its owner's exchange buffer; the flags are raised in the kernel
+            a.lw = nullptr;
+            a.lw_store = h->lw[h->cur];
+            a.pull.cnt = h->cnt;
+            a.pull.myrank = c.rank;
+            const int par = (int)(h->xseq & 1);
+            for (int q = 0; q < c.nranks; q++) {
+                a.pull.src[q] = q == c.rank ? h->xlw[par] : h->peer_xlw[par][q];
+                a.pull.flag[q] = q == c.rank ? h->xflags : h->peer_flags[q];
+            }
+        }
         a.pose_local = (h->fold_wpose && (c.nranks == 1 || !h->direct)) ? h->pose[h->cur] : nullptr;
         a.wp_part = h->wp_part;
         if (sharded) a.sh = shard_of(h);
@@ -1521,6 +1541,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     h->ntiles = (h->P + 1023) / 1024;
     if (const char* e = std::getenv("GMS_SHARDED")) h->exact_sums = std::atoi(e) != 0;
     if (const char* e = std::getenv("GMS_SCORE_DYNAMIC")) h->score_dynamic = std::atoi(e) != 0;
+    if (const char* e = std::getenv("GMS_PULL")) h->xpull = std::atoi(e) != 0;
     // by the TOTAL particle count (the same on every rank): 100 particles x 360 beams 0.043 -> 0.033 ms with 8 warps,
     // 1000 particles 0.061 -> 0.073 ms
     h->pp_warps = h->P <= 256 ? 8 : 4;

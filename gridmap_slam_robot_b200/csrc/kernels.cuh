@@ -114,6 +114,25 @@ __global__ void __launch_bounds__(1024) k_xpush_lw(const double* __restrict__ lw
     if ((int)threadIdx.x < xp.nranks)
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(xp.flag[threadIdx.x] + myrank), "l"(seq) : "memory");
 }
+// The same exchange as a PULL (default; GMS_PULL=0 keeps the push above).  The scoring kernel writes this rank's
+// block of log-weights into its OWN exchange buffer; nothing is stored over NVLink and no exchange kernel runs.
+// The normalise kernel that follows in stream order raises this rank's flag on every rank first (the kernel
+// boundary has made the scoring kernel's stores visible at this GPU's L2, which is where a peer's NVLink read is
+// served), waits for every rank's flag, and reads each 1024-particle tile from the buffer of the rank that owns
+// it (8-byte __ldcg loads through the peer mapping: L1 is bypassed, the requester's L2 does not
+// cache peer memory), filing the values in the handle's own lw array.  Per rank and step 8 B x (P - cnt) arrive
+// over NVLink in one round trip instead of 8 B x cnt x R stores, two system fences and a launch (8 x 100k
+// particles: exchange phase 0.023 ms -> 0).  Buffers are double-buffered by exchange parity: a rank rewrites a
+// buffer two steps later, and it cannot get there before every peer has raised its next flag, which a peer does
+// only after its reads of this step (stream order).
+struct XPull {
+    int cnt;                              // particles per rank; 0: not pulling
+    int myrank;
+    const double* src[kMaxRanks];         // every rank's exchange buffer (f64[P], GLOBAL index) for this parity
+    unsigned long long* flag[kMaxRanks];  // flag[q] = rank q's flag array (one u64 per sender)
+};
+// (Raising the flags from the scoring kernel's last CTA instead — a launch gap earlier — was measured and dropped: the
+// per-CTA system-scope fence ahead of the ticket cost the scoring kernel 14 us, the normalise gained 5.)
 // every rank's pose array of the current generation, indexable by GLOBAL particle index (single rank, or
 // records imported by an all-gather: every entry is the local array)
 struct PoseTable {
@@ -1769,6 +1788,7 @@ struct NormArgs {
     const float4* pose_local;  // fold the weighted pose (SLAM.getWeightedPose) into this launch: all poses of the block
     double* wp_part;           // are local (single rank / imported records), else nullptr
     Shard sh;
+    XPull pull;                // replicated peer exchange, pull form (k_norm_tiles only): see XPull
 };
 constexpr int kNormThreads = 256;   // 4 consecutive particles per thread: a 1024-particle tile per CTA iteration
 constexpr int kNormCtasPerSm = 4;   // <= 64 registers (the exact 128-bit sums need them): 592 co-resident CTAs
@@ -1979,8 +1999,14 @@ __global__ void __launch_bounds__(kNormThreads, 6) k_norm_tiles(NormArgs a) {
     __shared__ double s_d[NW];
     __shared__ double s_v[5 * NW];
     __shared__ unsigned long long s_u[NW];
+    __shared__ double s_tile[1024];
     __shared__ bool s_last;
     const int tid = threadIdx.x, G = gridDim.x;
+    const bool pull = a.pull.cnt > 0;
+    if (pull && blockIdx.x == 0 && tid < a.nranks) {  // this rank's block is final (kernel boundary): tell every rank
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.pull.flag[tid] + a.pull.myrank), "l"(a.seq) : "memory");
+    }
     if (a.xflags) {
         if (tid < a.nranks) {  // every CTA polls for itself: no extra grid barrier
             unsigned long long v = 0;
@@ -1994,12 +2020,35 @@ __global__ void __launch_bounds__(kNormThreads, 6) k_norm_tiles(NormArgs a) {
         }
         __syncthreads();  // the acquiring threads' view is handed to the whole CTA
     }
+    const double* lw2 = pull ? a.lw_store : a.lw;  // phase 2 re-reads the values: pulled ones from the local copy phase 1 filed
     // phase 1: per fixed tile, (max, first arg-max, sum exp(lw - tile max))
     for (int t = blockIdx.x; t < a.ntiles; t += G) {
         const int i0 = t * 1024 + tid * 4;
         double v[4];
+        if (pull && (a.pull.cnt & 1) == 0) {
+            // each value from the exchange buffer of the rank that owns the particle.  The tile is staged through
+            // shared memory so that a warp's request is 512 contiguous bytes and every 32-byte sector crosses NVLink
+            // once (a thread's own four values are 32 bytes apart from its neighbour's: read directly, every sector
+            // would be requested four times — measured +10 us at 2 x 100k particles)
 #pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = i0 + j < a.P ? __ldcg(a.lw + i0 + j) : kNegInf;
+            for (int k = 0; k < 2; k++) {
+                const int e = 2 * (tid + k * NT), i = t * 1024 + e;  // cnt and P are even: a pair never straddles ranks
+                double2 d = make_double2(kNegInf, kNegInf);
+                if (i < a.P) d = __ldcg(reinterpret_cast<const double2*>(a.pull.src[i / a.pull.cnt] + i));
+                s_tile[e] = d.x;
+                s_tile[e + 1] = d.y;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[j] = s_tile[tid * 4 + j];
+            __syncthreads();
+        } else if (pull) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[j] = i0 + j < a.P ? __ldcg(a.pull.src[(i0 + j) / a.pull.cnt] + i0 + j) : kNegInf;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[j] = i0 + j < a.P ? __ldcg(a.lw + i0 + j) : kNegInf;
+        }
         if (a.lw_store)
 #pragma unroll
             for (int j = 0; j < 4; j++)
@@ -2040,7 +2089,7 @@ __global__ void __launch_bounds__(kNormThreads, 6) k_norm_tiles(NormArgs a) {
         for (int j = 0; j < 4; j++) {
             const int i = i0 + j;
             if (i < a.P) {
-                const double wi = exp(__ldcg(a.lw + i) - best) / S;
+                const double wi = exp(__ldcg(lw2 + i) - best) / S;
                 a.w[i] = wi;
                 v[0] += wi; v[1] += wi * wi;
                 fx += (unsigned long long)(wi * 0x1p60);
