@@ -10,7 +10,8 @@ systematic resampling (every step: the policy is GMS_RESAMPLE_ALWAYS so that no 
 Default workload at N=1 is K4, the configuration BASELINE.json's target is quoted on (100k particles x
 720 beams, 4096^2 shared grid); it fits one GPU.  With N>1 ranks the particles are sharded
 (100k per GPU, weak scaling; --scaling strong shards BASELINE's fixed 100k) and the only data-path
-exchange is the push of the f64 log-weights into every rank's receive buffer over NVLink.
+exchange is that of the f64 log-weights: every rank's normalise kernel reads the other ranks' blocks over NVLink
+(peer mappings).
 
 One JSON line on stdout (rank 0):
   value        device-resident throughput: scans already in HBM, one CUDA-event pair per step on the stream the
@@ -490,9 +491,9 @@ def time_workload(ctx, name, wl, P_total, steps, warmup, e2e_steps):
         te = float(te.item())
         e2e = {"value": sc / te, "unit": "scores/s", "ms_per_step": 1e3 * te / e2e_steps, "steps": e2e_steps,
                "h2d_bytes_per_step": Bn * 25 * world, "d2h_bytes_per_step": 104 * world,
-               "calls": "per rank: H2D of the scan from pinned memory + gms_update_begin_dev (scoring, push of the "
-                        "log-weights into every rank's receive buffer over NVLink) + gms_update_end_dev(resample) + "
-                        "gms_read_neff"}
+               "calls": "per rank: H2D of the scan from pinned memory + gms_update_begin_dev (scoring into the rank's "
+                        "exchange buffer) + gms_update_end_dev (normalise pulls every rank's log-weights over NVLink; "
+                        "resample) + gms_read_neff"}
     W, H = h.W, h.H
     barrier()
     h.close()

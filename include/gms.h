@@ -244,7 +244,8 @@ int gms_set_stream(gms_handle* h, void* cuda_stream);
 #define GMS_PHASE_MAP_UPDATE 4
 #define GMS_PHASE_RESAMPLE 5
 #define GMS_PHASE_MAP_COPY 6
-#define GMS_PHASE_EXCHANGE 7    /* multi-rank: push of the log-weights / import of all-gathered records */
+#define GMS_PHASE_EXCHANGE 7    /* multi-rank: push of the log-weights (GMS_PULL=0) / import of all-gathered records /
+                                   the maps-final round of per-particle maps; the default pull is inside NORMALISE */
 #define GMS_PHASE_COUNT 9       /* the last slot collects everything else (getters, resets, rows of §8f) */
 int gms_profile_enable(gms_handle* h, int32_t on);
 /* ms[GMS_PHASE_COUNT], launches[GMS_PHASE_COUNT]: accumulated since the last gms_profile_reset. */

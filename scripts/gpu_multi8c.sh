@@ -1,8 +1,10 @@
 #!/bin/bash
-# One gpurun --gpus 8 call: the driver's scaling invocation at N = 8 only (default settings: pull exchange, extras, parity check).
+# One gpurun --gpus 8 call: the driver's scaling invocation at N = 8 (default settings: pull exchange, extras, parity check),
+# then the same workload with the push exchange (GMS_PULL=0) for the A/B.
 tag=${1:-r04e}
 mkdir -p gpurun_out
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29508 bench.py --gpus 8 --steps 30 --warmup 5 --no-cpu > gpurun_out/${tag}_bench_n8.json 2> gpurun_out/${tag}_bench_n8.err; echo "bench N=8 rc=$?"
+GMS_PULL=0 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29509 bench.py --gpus 8 --steps 30 --warmup 5 --no-cpu --no-extra --no-parity > gpurun_out/${tag}_bench_n8_push.json 2> gpurun_out/${tag}_bench_n8_push.err; echo "bench N=8 (push) rc=$?"
 python - <<PY
 import json,glob
 for f in sorted(glob.glob("gpurun_out/${tag}_bench_n*.json")):
