@@ -970,14 +970,20 @@ __global__ void __launch_bounds__(128, (V == 3 || V == 4) ? 8 : 1) k_score_sorte
     // counter until none are left: at 100k particles the static grid was 1563 CTAs on 592 resident ones = 2.64 waves,
     // i.e. a third wave 64 % full (12 % of the kernel's time idle); drawn items keep every warp busy to the end.
     // Which warp scores a particle does not enter its result.
-    const int lane = tid & 31;
+    // A CTA draws its warps' items TOGETHER, as one run of consecutive items: neighbours in the heading order read the
+    // same lines of the factor field, and the static grid's L1 hit rate (82 %) comes from the four warps of a CTA
+    // working on four consecutive items at the same time.  (Drawn warp by warp — the first version of this mode —
+    // consecutive items scatter over the SMs: 0.110 ms against the static grid's 0.097.)
+    const int lane = tid & 31, wid = tid >> 5, nw = (int)(blockDim.x >> 5);
     const int nitems = (int)(((long long)cnt * G + 31) / 32);
+    __shared__ unsigned s_next;
     auto next_item = [&]() -> int {
-        unsigned v = 0;
-        if (lane == 0) v = atomicAdd(work, 1u);
-        return (int)__shfl_sync(0xffffffffu, v, 0);
+        __syncthreads();  // every warp has taken its item of the previous draw
+        if (tid == 0) s_next = atomicAdd(work, (unsigned)nw);
+        __syncthreads();
+        return (int)s_next + wid;
     };
-    int item = work ? next_item() : (int)(blockIdx.x * (blockDim.x >> 5) + (tid >> 5));
+    int item = work ? next_item() : (int)(blockIdx.x * nw + wid);
     if (nh > 0) {
         uint32_t done = 0;
         while (!done) {
@@ -988,7 +994,9 @@ __global__ void __launch_bounds__(128, (V == 3 || V == 4) ? 8 : 1) k_score_sorte
                 : "memory");
         }
     }
-  for (; item < nitems; item = work ? next_item() : nitems) {
+  // (the condition is uniform over the CTA — next_item() holds barriers; a warp whose item lies beyond the last one
+  // runs the body with idle lanes: li = -1 below)
+  for (; item - wid < nitems; item = work ? next_item() : nitems + wid) {
     const int t = (item * 32 + lane) / G, gsub = (item * 32 + lane) % G;
     const int li = t < cnt ? (order ? order[t] : t) : -1;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
