@@ -147,6 +147,7 @@ struct gms_handle {
     bool exact_sums = false;     // GMS_SHARDED=1 (any handle): the normalise with exact 128-bit sums, so that a sharded
                                  // multi-rank run and a single-rank run agree bit for bit
     bool sharded_post = false;   // enabled by gms_ipc_import for shared maps (GMS_SHARDED=0 keeps the replicated path)
+    bool small_fused = true;     // LITERAL resampling of <= 2048 particles on one rank as one launch (GMS_SMALL_FUSED=0: three)
     bool xpull = true;           // replicated peer exchange as a pull inside k_norm_tiles (XPull); GMS_PULL=0: k_xpush_lw
     bool tile_fx_sharded = false;  // np.fx holds the tile sums of the local block only
     bool blocks_stale = false;   // pose / w / lw / parents hold only this rank's block: getters copy the rest from peers
@@ -1002,6 +1003,7 @@ int remap_field_overrides(gms_handle* h, int old_slots) {
 
 int launch_resample(gms_handle* h, double u01, bool local_only = false) {
     const int P = h->P;
+    bool parents_listed = false;  // k_resample_small has already listed the selected parents
     h->stats_valid = false;  // Stats.strongest_now changes
     {
         Phase ph(h, GMS_PHASE_RESAMPLE);
@@ -1040,6 +1042,15 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
             int ntiles = h->ntiles;
             const unsigned grid = (unsigned)std::max(1, std::min(h->num_sms * kNormCtasPerSm, std::max(ntiles, (m_count + kNormThreads - 1) / kNormThreads)));
             LAUNCH_COOP(GMS_PHASE_RESAMPLE, k_resample_coop, grid, kNormThreads, 0, &a, &fx, &ntiles);
+        } else if (h->small_fused && h->cfg.nranks == 1 && P <= kCdfChunk) {
+            // CDF + selection (+ the list of selected parents, when a scan waits for it) in one single-CTA launch
+            h->wpose_valid = false;
+            const bool list = h->cfg.map_mode == GMS_MAP_PER_PARTICLE && h->integ_pending;
+            if (list && !h->used) CK(cudaMalloc((void**)&h->used, (size_t)(h->cnt + 1) * 4));  // [0]: length, [1..]: the list
+            const SelectArgs a = select_args(h, h->cur, nxt, u01, h->resample_count, 0, P);
+            LAUNCH(GMS_PHASE_RESAMPLE, k_resample_small<<<1, 1024, 0, h->stream>>>(a, h->lo, h->cnt, list ? h->used + 1 : nullptr,
+                                                                                   list ? h->used : nullptr));
+            parents_listed = list;
         } else {
             h->wpose_valid = false;
             LAUNCH(GMS_PHASE_RESAMPLE, k_cdf_literal<<<1, 256, 0, h->stream>>>(h->w[h->cur], P, (double*)h->cdf, h->st,
@@ -1064,10 +1075,12 @@ int launch_resample(gms_handle* h, double u01, bool local_only = false) {
     if (h->cfg.nranks > 1 && !h->peers_ready)
         return fail(h, GMS_ERR_STATE, "per-particle maps across ranks: call gms_ipc_import before resampling");
     if (h->integ_pending) {  // the scan goes into the maps of the selected parents only: the others are dropped
-        if (!h->used) CK(cudaMalloc((void**)&h->used, (size_t)(h->cnt + 1) * 4));  // [0]: length, [1..]: the list
-        CK(cudaMemsetAsync(h->used, 0, 4, h->stream));
-        LAUNCH(GMS_PHASE_MAP_UPDATE, k_list_parents<<<blocks_for(P, 256), 256, 0, h->stream>>>(h->parents, P, h->lo, h->cnt,
-                                                                                            h->used + 1, h->used));
+        if (!parents_listed) {
+            if (!h->used) CK(cudaMalloc((void**)&h->used, (size_t)(h->cnt + 1) * 4));  // [0]: length, [1..]: the list
+            CK(cudaMemsetAsync(h->used, 0, 4, h->stream));
+            LAUNCH(GMS_PHASE_MAP_UPDATE, k_list_parents<<<blocks_for(P, 256), 256, 0, h->stream>>>(h->parents, P, h->lo, h->cnt,
+                                                                                                h->used + 1, h->used));
+        }
         int rc_ = integrate_pending(h, h->used + 1, h->used);
         if (rc_) return rc_;
     }
@@ -1542,6 +1555,7 @@ EXPORT int gms_create(const gms_config* cfg, gms_handle** out) {
     if (const char* e = std::getenv("GMS_SHARDED")) h->exact_sums = std::atoi(e) != 0;
     if (const char* e = std::getenv("GMS_SCORE_DYNAMIC")) h->score_dynamic = std::atoi(e) != 0;
     if (const char* e = std::getenv("GMS_PULL")) h->xpull = std::atoi(e) != 0;
+    if (const char* e = std::getenv("GMS_SMALL_FUSED")) h->small_fused = std::atoi(e) != 0;
     // by the TOTAL particle count (the same on every rank): 100 particles x 360 beams 0.043 -> 0.033 ms with 8 warps,
     // 1000 particles 0.061 -> 0.073 ms
     h->pp_warps = h->P <= 256 ? 8 : 4;

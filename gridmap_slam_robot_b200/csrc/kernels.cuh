@@ -2322,9 +2322,10 @@ __device__ __forceinline__ int select_stride(int P) {
     while ((P + stride - 1) / stride > 2048) stride <<= 1;
     return stride;
 }
-template <bool FIXED>
+template <bool FIXED, bool SMEM = false>  // SMEM: a.cdf points into shared memory (k_resample_small)
 __device__ __forceinline__ void select_child(const SelectArgs& a, int m0, const unsigned long long* s_coarse, int stride,
-                                             int ncoarse, double u01, float4& pose_o, double& w_o) {
+                                             int ncoarse, double u01, float4& pose_o, double& w_o,
+                                             const void* cdf_smem = nullptr) {
     using Key = typename std::conditional<FIXED, unsigned long long, double>::type;
     const int P = a.P;
     const double r = u01 * 1.0 / (double)P;
@@ -2334,7 +2335,7 @@ __device__ __forceinline__ void select_child(const SelectArgs& a, int m0, const 
     };
     // two-level search: every `stride`-th CDF value (<= 2048 of them) is staged in shared memory with one
     // round of independent loads, which replaces the top ~11 dependent global probes of a plain bisection
-    const Key* cdf = static_cast<const Key*>(a.cdf);
+    const Key* cdf = static_cast<const Key*>(SMEM ? cdf_smem : a.cdf);
     const Key key = key_of(m0);
     const Key* coarse = reinterpret_cast<const Key*>(s_coarse);
     int lo = 0, hi = ncoarse - 1;
@@ -2346,7 +2347,7 @@ __device__ __forceinline__ void select_child(const SelectArgs& a, int m0, const 
     lo = lo * stride;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (key > __ldcg(cdf + mid)) lo = mid + 1; else hi = mid;
+        if (key > (SMEM ? cdf[mid] : __ldcg(cdf + mid))) lo = mid + 1; else hi = mid;
     }
     a.parents[m0] = lo;
     pose_o = a.poses_in.at(lo);
@@ -2356,7 +2357,8 @@ __device__ __forceinline__ void select_child(const SelectArgs& a, int m0, const 
     a.lw_out[m0] = __ldcg(a.lw_in + lo);
     // the strongest particle of the last update lives on as its FIRST child (slam.py / gms_get_strongest)
     const int sb = a.st->strongest;
-    if (lo == sb && (m0 == 0 || sb == 0 ? m0 == 0 : !(key_of(m0 - 1) > __ldcg(cdf + sb - 1)))) a.st->strongest_now = m0;
+    if (lo == sb && (m0 == 0 || sb == 0 ? m0 == 0 : !(key_of(m0 - 1) > (SMEM ? cdf[sb - 1] : __ldcg(cdf + sb - 1)))))
+        a.st->strongest_now = m0;
 }
 
 // LITERAL mode (P <= 2048 by default): Java's sequential f64 CDF (k_cdf_literal) + this selection kernel.
@@ -2385,6 +2387,74 @@ __global__ void __launch_bounds__(256) k_select(SelectArgs a) {
     float4 po;
     double wo;
     select_child<FIXED>(a, m0, s_coarse, stride, ncoarse, u01, po, wo);
+}
+
+// LITERAL mode on one rank with at most kCdfChunk particles (the reference's own sizes: K1, K2, K2pp): k_cdf_literal,
+// k_select<false> and — per-particle maps with a pending scan — k_list_parents as ONE launch of one CTA.  The CDF
+// never leaves shared memory for the search (it is still written out: getters and the oracle comparison read it);
+// the same chain, the same two-level search and the same strongest_now rule as the separate kernels, so parents,
+// poses and weights are the same bits.  Saves two launches and a memset per resampling (~10 us of launch gaps).
+__global__ void __launch_bounds__(1024) k_resample_small(SelectArgs a, int lo, int cnt, int* __restrict__ ulist,
+                                                         int* __restrict__ n_used) {
+    __shared__ double s_cdf[kCdfChunk];
+    __shared__ unsigned long long s_coarse[kCdfChunk / 32];
+    const int tid = threadIdx.x, P = a.P;
+    if (a.st->xerror) return;
+    const bool resample = a.force || a.st->do_resample != 0;
+    if (tid == 0 && n_used) *n_used = 0;
+    if (resample) {
+#pragma unroll
+        for (int j = 0; j < kCdfChunk / 1024; j++) {
+            const int i = tid + j * 1024;
+            s_cdf[i] = i < P ? a.w_in[i] : 0.0;
+        }
+        if (tid == 0) a.st->strongest_now = -1;
+        __syncthreads();
+        if (tid == 0) {  // Java's sequential f64 running sum (SLAM.java:137-147), see k_cdf_literal
+            double c = 0.0;
+            int i = 0;
+            for (; i + 16 <= P; i += 16) {
+                double x[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) x[j] = s_cdf[i + j];
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    c = c + x[j];
+                    s_cdf[i + j] = c;
+                }
+            }
+            for (; i < P; i++) {
+                c = c + s_cdf[i];
+                s_cdf[i] = c;
+            }
+        }
+        __syncthreads();
+        double* cdf_out = static_cast<double*>(const_cast<void*>(a.cdf));
+        const int stride = select_stride(P), ncoarse = (P + stride - 1) / stride;  // stride == 32 here
+        for (int i = tid; i < P; i += 1024) cdf_out[i] = s_cdf[i];
+        for (int j = tid; j < ncoarse; j += 1024) s_coarse[j] = (unsigned long long)__double_as_longlong(s_cdf[min(P - 1, (j + 1) * stride - 1)]);
+        __syncthreads();
+        const double u01 = a.u01 < 0.0 ? philox_uniform(a.seed, a.resample_count) : a.u01;
+        for (int m0 = tid; m0 < P; m0 += 1024) {
+            float4 po;
+            double wo;
+            select_child<false, true>(a, m0, s_coarse, stride, ncoarse, u01, po, wo, s_cdf);
+        }
+    } else {  // the generation is carried over unchanged
+        for (int m0 = tid; m0 < P; m0 += 1024) {
+            a.parents[m0] = m0;
+            a.pose_out[m0] = a.poses_in.at(m0);
+            a.w_out[m0] = a.w_in[m0];
+            a.lw_out[m0] = __ldcg(a.lw_in + m0);
+        }
+    }
+    if (ulist) {  // k_list_parents
+        __syncthreads();
+        for (int m = tid; m < P; m += 1024) {
+            const int p = a.parents[m];
+            if ((m == 0 || a.parents[m - 1] != p) && p >= lo && p < lo + cnt) ulist[atomicAdd(n_used, 1)] = p - lo;
+        }
+    }
 }
 
 // FIXED mode: CDF + selection in ONE cooperative launch.
