@@ -276,10 +276,14 @@ int gms_read_neff(gms_handle* h, double* neff_out);  /* sync + read Neff of the 
  * rank imports the lot; resampling then pulls remote parents' maps over NVLink inside
  * gms_update_end_dev / gms_resample.  The caller must run a barrier across ranks after the resampling
  * call before the next update (old slots are only released then).  Handles hold 2x the slots.
- * The same import also switches the exchange of every multi-rank handle to the PEER path: after scoring each
- * rank stores its block of f64 log-weights (8 bytes per particle) directly into every rank's receive buffer
- * over NVLink, a flag per sender replaces the collective (the caller skips its all-gather between begin and
- * end), and the resampling reads a remote parent's pose through the peer mapping of that rank's pose array. */
+ * The same import also switches the exchange of every multi-rank handle to the PEER path: the scoring of
+ * gms_update_begin_dev writes the rank's block of f64 log-weights (8 bytes per particle) into the rank's own
+ * exchange buffer, and the normalise kernel of gms_update_end_dev raises a flag per sender on every rank and reads
+ * every other rank's block through its peer mapping over NVLink (the caller skips its all-gather between begin
+ * and end; GMS_PULL=0 in the environment: each rank stores its block into every rank's receive buffer instead);
+ * the resampling reads a remote parent's pose through the peer mapping of that rank's pose array.  Between begin
+ * and end the log-weights of the running step are not readable through the getters (they are filed in the
+ * handle's arrays by the normalise). */
 #define GMS_IPC_HANDLE_BYTES 64
 #define GMS_IPC_NUM_HANDLES 18
 int gms_ipc_export(gms_handle* h, void* handles /* GMS_IPC_NUM_HANDLES * GMS_IPC_HANDLE_BYTES */);
