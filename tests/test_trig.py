@@ -50,3 +50,41 @@ def test_trig_probe_oracle(oracle):
 @pytest.mark.gpu
 def test_trig_probe_cuda(cuda):
     checks.check_trig_probe(cuda)
+
+
+def test_fixed_sequence_symmetries():
+    """Exact identities of the operation sequence (they follow from IEEE negation being exact and the reduction being
+    odd in x): sin(-x) == -sin(x), cos(-x) == cos(x) bit for bit; sin^2 + cos^2 within 3 ulp of 1."""
+    ref = checks._pyref()
+    for x in checks.trig_probe_angles()[::2]:
+        x = float(x)
+        if not abs(x) < 1647099.0:
+            continue
+        s, c = ref.sin_fixed(x), ref.cos_fixed(x)
+        assert ref.sin_fixed(-x) == -s and ref.cos_fixed(-x) == c, x
+        assert abs(s * s + c * c - 1.0) <= 3 * 2.220446049250313e-16, x
+
+
+def test_motion_step_uses_the_fixed_sequence(oracle):
+    """Odometry.apply (Odometry.java:77-96): x' = (float)(x + (double)(float)cos(theta') * d) — the oracle's f32 pose after
+    one noise-free motion step equals the value computed here from pyref's cos_fixed / sin_fixed, for headings
+    spread over every quadrant (libm's cos differs from the sequence in ~3 % of f64 results, so a library call
+    slipping back in would show up as an f32 mismatch only with probability 2^-29 per pose: the f64 probe through
+    gms_deskew in test_trig_probe_* is the sharp test; this one pins the call site)."""
+    ref = checks._pyref()
+    from gridmap_slam_robot_b200 import binding as B
+
+    P = 256
+    h = oracle.create(num_particles=P, map_width_m=4.0, map_height_m=4.0, origin_x=-2.0, origin_y=-2.0,
+                      map_mode=B.MAP_SHARED)
+    rng = np.random.default_rng(7)
+    poses = np.stack([rng.uniform(-1, 1, P), rng.uniform(-1, 1, P), rng.uniform(-3.1, 3.1, P)], 1).astype(np.float32)
+    h.set_poses(poses)
+    xy = np.zeros((0, 2)); dist = np.zeros(0); hit = np.zeros(0, np.uint8)
+    dc, dth = 0.125, 0.0625
+    h.update(xy, dist, hit, dc, dth, np.zeros((P, 2)))
+    got = h.poses()
+    for i in range(P):
+        want = ref.motion_sample(tuple(float(v) for v in poses[i]), dc, dth, 0.0, 0.0)
+        assert tuple(float(v) for v in got[i]) == tuple(want), i
+    h.close()
