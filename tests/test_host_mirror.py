@@ -143,3 +143,17 @@ def test_binding_constants_match_the_header():
         subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
     assert [int(v) for v in out] == [ctypes.sizeof(B.Config), ctypes.sizeof(B.Info)]
+
+
+def test_environment_knobs_are_documented():
+    """Every GMS_* variable the library reads is listed in INTEGRATION.md's table, and nothing is listed that the
+    library does not read."""
+    import re
+
+    code = open(os.path.join(ROOT, "gridmap_slam_robot_b200", "csrc", "gms.cu")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    read = set(re.findall(r'getenv\("(GMS_[A-Z_0-9]+)"\)', code))
+    listed = set(re.findall(r"`(GMS_[A-Z_0-9]+)=", doc))
+    assert read, "no getenv found: the scan is broken"
+    assert read - listed == set(), f"undocumented: {sorted(read - listed)}"
+    assert listed - read == set(), f"documented but never read: {sorted(listed - read)}"
