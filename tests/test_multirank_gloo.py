@@ -1,6 +1,6 @@
-"""CPU, world_size 2 over gloo: the multi-rank stepping logic (gridmap_slam_robot_b200/parallel.py)
+"""CPU, world_size 2 and 4 over gloo: the multi-rank stepping logic (gridmap_slam_robot_b200/parallel.py)
 around the oracle library.  Rank-count invariance: parents, poses, weights and the
-integer map counts of a 2-rank run equal those of the 1-rank run on the same inputs."""
+integer map counts of an R-rank run equal those of the 1-rank run on the same inputs."""
 import os
 import socket
 import sys
@@ -71,10 +71,11 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def test_two_ranks_equal_one_rank(oracle):
+@pytest.mark.parametrize("world", [2, 4])
+def test_ranks_equal_one_rank(oracle, world):
     from gridmap_slam_robot_b200 import binding as B
 
-    P, steps, beams, world = 64, 4, 60, 2
+    P, steps, beams = 64, 4, 60
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
